@@ -1,0 +1,231 @@
+/*
+ * kdf.h — C ABI of libkdf_sm100.so, the B200 (sm_100a) k-mer engine that
+ * replaces the Jellyfish / samtools subprocesses of jlanej/kmer_denovo_filter.
+ *
+ * The reference has no FFI: its seam is a set of Python functions that wrap
+ * subprocesses.  Each entry point below names the reference call site it
+ * replaces (paths relative to the reference's src/kmer_denovo_filter/).
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types in any signature;
+ *   - every pointer marked DEV is device memory owned (allocated and freed) by
+ *     the caller; the library never allocates or frees device memory;
+ *   - every launch is ordered on the `stream` argument (a cudaStream_t passed
+ *     as void*; NULL = legacy default stream) and returns without synchronising;
+ *   - return value: 0 = KDF_OK, negative = error; kdf_last_error() gives the
+ *     text of the last error on the calling thread;
+ *   - no global mutable state besides that thread-local error string.
+ *
+ * Data layouts
+ *   Stream ("packed read batch"): all sequences of a batch concatenated with
+ *   exactly one invalid separator base between consecutive sequences.
+ *     codes : uint64 words, 32 bases per word, base i of the stream in bits
+ *             [62 - 2*(i%32), +2) of word i/32  (A=0 C=1 G=2 T=3; first base
+ *             most significant, so a k-mer read out of the stream is already
+ *             the Jellyfish/lexicographic integer key);
+ *     valid : uint32 words, 32 bases per word, base i at bit 31 - (i%32);
+ *             0 for N / IUPAC / separator / padding.
+ *   Both arrays hold n_words = ceil(n_bases/32) words; bits past n_bases must
+ *   be 0.  A window (k-mer) starting at p is counted iff valid[p..p+k) are all 1.
+ *
+ *   Table: open addressing, linear probing, any capacity >= 2.
+ *     key_words == 1 (k <= 32): 16-byte slots {u64 key; u32 plane0; u32 plane1}
+ *     key_words == 2 (k <= 64): 32-byte slots {u64 lo; u64 hi; u32 plane0;
+ *                                u32 plane1; u64 pad}
+ *   Empty slots hold all-ones key words (never a canonical k-mer).
+ *   plane0 / plane1 are two independent u32 value planes (child count, parent
+ *   count, reference flag ...).
+ */
+#ifndef KDF_H_
+#define KDF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KDF_VERSION 1
+
+/* status codes */
+#define KDF_OK 0
+#define KDF_ERR_ARG (-1)      /* invalid argument                               */
+#define KDF_ERR_CUDA (-2)     /* CUDA runtime error (text in kdf_last_error)    */
+#define KDF_ERR_NO_DEVICE (-3)
+#define KDF_ERR_FULL (-4)     /* table full: Jellyfish would spill to .jf_N files
+                                 (core/jellyfish_wrappers.py:59-70); we refuse  */
+#define KDF_ERR_CAPACITY (-5) /* output buffer too small; *n_out has the need   */
+
+/* update modes of kdf_count_stream / kdf_update_keys */
+#define KDF_MODE_INSERT_COUNT 0     /* jellyfish count -C             : insert if absent, plane += arg */
+#define KDF_MODE_INSERT_ONLY 1      /* jellyfish count --if priming   : insert if absent, planes untouched */
+#define KDF_MODE_COUNT_IF_PRESENT 2 /* jellyfish count -C --if f.fa   : plane += arg only for existing keys */
+#define KDF_MODE_MARK_IF_PRESENT 3  /* jellyfish query ref.jf (== 0?) : plane |= arg only for existing keys */
+
+/* stats block written by the kernels (DEV, 4 x u64, caller zeroes it) */
+#define KDF_STAT_WINDOWS 0 /* valid k-mer instances processed            */
+#define KDF_STAT_FULL 1    /* != 0 : an insert found no free slot         */
+#define KDF_STAT_HITS 2    /* instances that matched an existing key      */
+#define KDF_STAT_NEW 3     /* keys newly inserted                         */
+#define KDF_N_STATS 4
+
+typedef struct kdf_table kdf_table; /* opaque host-side descriptor */
+
+typedef struct kdf_stream {
+  const uint64_t* codes; /* DEV */
+  const uint32_t* valid; /* DEV */
+  uint64_t n_bases;
+} kdf_stream;
+
+typedef struct kdf_device_props {
+  int sm_count;
+  int cc_major, cc_minor;
+  int l2_bytes;
+  uint64_t hbm_bytes;
+  char name[128];
+} kdf_device_props;
+
+/* ---- housekeeping ------------------------------------------------------ */
+int kdf_version(void);
+const char* kdf_last_error(void);
+int kdf_device_info(int device, kdf_device_props* out);
+
+/* ---- table ------------------------------------------------------------- */
+/* key_words for a k-mer size (1 for k<=32, 2 for k<=64, 0 = unsupported).   */
+int kdf_key_words(int k);
+/* bytes of device memory the caller must provide for `capacity` slots.      */
+size_t kdf_table_bytes(uint64_t capacity, int key_words);
+/* Capacity planning (replaces -s sizing: core/jellyfish_wrappers.py:73-107,
+ * :155 `max(2n, 10M)`, :400 `max(2n, 1M)`): slots for n keys at load 0.5.    */
+uint64_t kdf_table_capacity_for(uint64_t n_keys);
+
+/* Wrap caller memory as a table for k-mer size k and clear it (async).
+ * Replaces the hash that `jellyfish count -s` allocates
+ * (discovery/pipeline.py:114-122; core/jellyfish_wrappers.py:167-176).      */
+int kdf_table_create(kdf_table** out, int k, uint64_t capacity,
+                     void* slots /*DEV*/, void* stream);
+int kdf_table_destroy(kdf_table* t);
+int kdf_table_clear(kdf_table* t, void* stream);                 /* all slots -> empty */
+int kdf_table_clear_plane(kdf_table* t, int plane, void* stream); /* one value plane -> 0 */
+int kdf_table_info(const kdf_table* t, int* k, int* key_words, uint64_t* capacity);
+
+/* ---- K1: rolling extract + canonicalise --------------------------------
+ * One output per window start p in [0, n_bases): canonical key (lo[, hi]) and
+ * a validity bit (same bit layout as `valid`).  Semantics of
+ * kmer_utils.py:30-38 (canonicalize) and :91-121 (_extract_read_kmers), with
+ * the Jellyfish rule that any non-ACGT base breaks the window.
+ * out_hi may be NULL when k <= 32.                                          */
+int kdf_extract_canonical(const kdf_stream* s, int k,
+                          uint64_t* out_lo /*DEV n_bases*/,
+                          uint64_t* out_hi /*DEV n_bases or NULL*/,
+                          uint32_t* out_ok /*DEV n_words*/, void* stream);
+
+/* ---- K1+K2 fused: extract, canonicalise and update the table -----------
+ * mode INSERT_COUNT       : `jellyfish count -m k -C`
+ *                           (discovery/pipeline.py:114-122,
+ *                            core/jellyfish_wrappers.py:313-321, :411-419)
+ * mode COUNT_IF_PRESENT   : `jellyfish count -C --if`
+ *                           (core/jellyfish_wrappers.py:167-176,
+ *                            discovery/pipeline.py:377-386)
+ * mode MARK_IF_PRESENT    : reference subtraction, the dual of
+ *                           `jellyfish query ref.jf -s cand.fa`
+ *                           (discovery/pipeline.py:286-304): the reference is
+ *                           streamed against the child table instead.
+ * stats: DEV u64[KDF_N_STATS] accumulated (not cleared) by the kernel; may be NULL. */
+int kdf_count_stream(kdf_table* t, const kdf_stream* s, int mode, int plane,
+                     uint32_t arg, uint64_t* stats /*DEV*/, void* stream);
+
+/* ---- K2 on explicit keys (filter priming, post all-to-all insert) ------ */
+int kdf_update_keys(kdf_table* t, const uint64_t* lo /*DEV*/,
+                    const uint64_t* hi /*DEV or NULL*/, uint64_t n, int mode,
+                    int plane, uint32_t arg, uint64_t* stats /*DEV*/, void* stream);
+
+/* ---- K3: threshold + stream compaction ---------------------------------
+ * Emits every occupied slot whose planes satisfy
+ *   min0 <= plane0 <= max0  and  min1 <= plane1 <= max1.
+ * Replaces `jellyfish dump -c -L n` (discovery/pipeline.py:207-211,
+ * core/jellyfish_wrappers.py:262) and the `count == 0` / `<= parent_max_count`
+ * line filters (discovery/pipeline.py:302, :528, :578).
+ * Output order is unspecified (as is Jellyfish's dump order).  Any of the
+ * output arrays may be NULL (count only).  n_out: DEV u64 counter, caller
+ * zeroes it; on return-time it holds the number of matches even when
+ * cap is too small (entries beyond cap are dropped).                        */
+int kdf_threshold_compact(const kdf_table* t, uint32_t min0, uint32_t max0,
+                          uint32_t min1, uint32_t max1,
+                          uint64_t* out_lo /*DEV*/, uint64_t* out_hi /*DEV*/,
+                          uint32_t* out_p0 /*DEV*/, uint32_t* out_p1 /*DEV*/,
+                          uint64_t cap, uint64_t* n_out /*DEV*/, void* stream);
+
+/* ---- K4: batched lookup -------------------------------------------------
+ * `jellyfish query <jf> -s keys.fa` (kmer_utils.py:152-183,
+ * discovery/pipeline.py:515-517, :565-567).  out_found[i] = 1/0; out_p0/out_p1
+ * receive the planes (0 when absent); any may be NULL.                      */
+int kdf_lookup_keys(const kdf_table* t, const uint64_t* lo /*DEV*/,
+                    const uint64_t* hi /*DEV or NULL*/, uint64_t n,
+                    uint8_t* out_found /*DEV*/, uint32_t* out_p0 /*DEV*/,
+                    uint32_t* out_p1 /*DEV*/, void* stream);
+
+/* ---- K4+K5: per-read membership scan + distinct reduction ---------------
+ * For read r occupying stream bases [read_starts[r], read_starts[r]+read_lens[r]):
+ *   out_ndistinct[r] = |{canonical k-mers of r present in the table}|
+ *   out_nhits[r]     = number of window starts whose canonical k-mer is present
+ * (core/bam_scanner.py:434-443; kmer_utils.py:209-238 scan_read).
+ * Reads with out_ndistinct >= min_distinct and >= 1 additionally append every
+ * hit as (stream position, slot index) to hit_pos/hit_slot (unordered);
+ * *n_hits (DEV u64, caller zeroes) always counts them, entries beyond
+ * hit_cap are dropped.  hit_pos/hit_slot may be NULL.  A read with more than
+ * 1024 hit windows reports out_ndistinct = 0xFFFFFFFF and always emits its
+ * hits; the caller finishes the distinct count from the emitted slot indices. */
+#define KDF_NDISTINCT_OVERFLOW 0xFFFFFFFFu
+int kdf_scan_reads(const kdf_table* t, const kdf_stream* s,
+                   const uint64_t* read_starts /*DEV n_reads*/,
+                   const uint32_t* read_lens /*DEV n_reads*/,
+                   uint64_t n_reads, uint32_t min_distinct,
+                   uint32_t* out_ndistinct /*DEV*/, uint32_t* out_nhits /*DEV*/,
+                   uint64_t* hit_pos /*DEV*/, uint32_t* hit_slot /*DEV*/,
+                   uint64_t hit_cap, uint64_t* n_hits /*DEV*/,
+                   uint64_t* stats /*DEV*/, void* stream);
+
+/* ---- K6: owner binning in front of the all-to-all -----------------------
+ * owner(key) = mix64(key) % n_ranks (independent of the slot index bits).
+ * Pass 1 (out_lo == NULL): histogram of valid windows per owner into
+ * counts[n_ranks] (DEV u64, caller zeroes).  Pass 2: scatter canonical keys to
+ * out_lo/out_hi at bin_offsets[owner] + running cursor (cursors: DEV u64
+ * [n_ranks], caller zeroes).  No reference analogue (single-host Jellyfish).  */
+int kdf_partition_stream(const kdf_stream* s, int k, int n_ranks,
+                         uint64_t* counts /*DEV*/,
+                         const uint64_t* bin_offsets /*DEV or NULL*/,
+                         uint64_t* cursors /*DEV or NULL*/,
+                         uint64_t* out_lo /*DEV or NULL*/,
+                         uint64_t* out_hi /*DEV or NULL*/, void* stream);
+
+/* ---- host helpers (CPU, no device) --------------------------------------
+ * Pack ASCII sequences into the stream layout.  seqs: concatenated bytes,
+ * offsets[n_seqs+1].  Returns the stream length in bases (sum of lengths +
+ * n_seqs-1 separators) and fills codes/valid (n_words each, caller-allocated,
+ * pre-zeroed not required) and read_offsets[n_seqs+1] (may be NULL).
+ * Upper/lower-case ACGT are valid; everything else is invalid.
+ * With codes == NULL only the length is computed.                           */
+uint64_t kdf_pack_sequences(const char* seqs, const uint64_t* offsets,
+                            uint64_t n_seqs, uint64_t* codes, uint32_t* valid,
+                            uint64_t* read_offsets);
+
+/* Test hook: runs the device window-iterator templates on the CPU (host
+ * instantiation of the same code) so the bit manipulation can be verified
+ * without a GPU.  Not used by any product path.                             */
+int kdf_debug_extract_host(const uint64_t* codes, const uint32_t* valid,
+                           uint64_t n_bases, int k, int use_random_access,
+                           uint64_t* out_lo, uint64_t* out_hi, uint8_t* out_ok);
+
+/* Random-access microbenchmark used for the "HBM random-access roofline"
+ * (SURVEY §8d): n_ops uniformly random 32-byte sector reads (atomic == 0) or
+ * sector read + 4-byte atomic add (atomic == 1) over buf_bytes.            */
+int kdf_bench_random_access(void* buf /*DEV*/, uint64_t buf_bytes,
+                            uint64_t n_ops, int atomic, uint64_t* sink /*DEV*/,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KDF_H_ */

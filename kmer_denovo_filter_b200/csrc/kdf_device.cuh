@@ -1,0 +1,270 @@
+// kdf_device.cuh — device-side building blocks of the sm_100a k-mer engine.
+//
+// Everything here is integer work bound by HBM / L2 sector traffic; there is no
+// dense contraction anywhere on this path, so no tensor-core (tcgen05) code.
+//
+// Canonical k-mer semantics follow the reference (kmer_utils.py:30-38
+// canonicalize, :91-121 _extract_read_kmers) in the 2-bit encoding A0 C1 G2 T3
+// with the first base most significant, where lexicographic min == integer min.
+#pragma once
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define KDF_HD __host__ __device__ __forceinline__
+#define KDF_D __device__ __forceinline__
+#else
+#define KDF_HD inline
+#define KDF_D inline
+#endif
+
+namespace kdf {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+static constexpr u64 EMPTY = ~0ull;
+
+// ---------------------------------------------------------------- keys ----
+template <int KW> struct Key;
+template <> struct Key<1> {
+  u64 lo;
+  KDF_HD bool operator==(const Key& o) const { return lo == o.lo; }
+};
+template <> struct Key<2> {
+  u64 lo, hi;
+  KDF_HD bool operator==(const Key& o) const { return lo == o.lo && hi == o.hi; }
+};
+
+struct __align__(16) Slot1 {
+  u64 key;
+  u32 p0, p1;
+};
+struct __align__(32) Slot2 {
+  u64 lo, hi;
+  u32 p0, p1;
+  u64 pad;
+};
+template <int KW> struct SlotOf;
+template <> struct SlotOf<1> { typedef Slot1 type; };
+template <> struct SlotOf<2> { typedef Slot2 type; };
+
+// ------------------------------------------------------------- hashing ----
+KDF_HD u64 mix64(u64 x) {
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return x;
+}
+KDF_HD u64 hash_key(const Key<1>& k) { return mix64(k.lo); }
+KDF_HD u64 hash_key(const Key<2>& k) {
+  return mix64(k.lo ^ mix64(k.hi + 0x9E3779B97F4A7C15ULL));
+}
+
+KDF_HD u64 mulhi64(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+  return __umul64hi(a, b);
+#else
+  return (u64)(((unsigned __int128)a * (unsigned __int128)b) >> 64);
+#endif
+}
+// slot index uses the high bits of the hash, owner rank the low 32 bits.
+KDF_HD u64 slot_of(u64 h, u64 capacity) { return mulhi64(h, capacity); }
+KDF_HD u32 owner_of(u64 h, u32 n_ranks) { return (u32)(h & 0xffffffffu) % n_ranks; }
+
+// -------------------------------------------------- reverse complement ----
+KDF_HD u64 brev64(u64 x) {
+#if defined(__CUDA_ARCH__)
+  return __brevll(x);
+#else
+  x = ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
+  x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+  x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+  x = ((x >> 8) & 0x00FF00FF00FF00FFULL) | ((x & 0x00FF00FF00FF00FFULL) << 8);
+  x = ((x >> 16) & 0x0000FFFF0000FFFFULL) | ((x & 0x0000FFFF0000FFFFULL) << 16);
+  return (x >> 32) | (x << 32);
+#endif
+}
+// reverse the order of the 32 two-bit groups of a word and complement them
+KDF_HD u64 revcomp_word(u64 x) {
+  u64 r = brev64(~x);
+  return ((r >> 1) & 0x5555555555555555ULL) | ((r & 0x5555555555555555ULL) << 1);
+}
+// reverse complement of a k-mer key, k <= 32
+KDF_HD Key<1> revcomp(const Key<1>& f, int k) {
+  Key<1> r;
+  r.lo = revcomp_word(f.lo) >> (64 - 2 * k);
+  return r;
+}
+// reverse complement of a k-mer key, 33 <= k <= 64
+KDF_HD Key<2> revcomp(const Key<2>& f, int k) {
+  u64 a = revcomp_word(f.lo);  // becomes the high word of the reversed 128 bits
+  u64 b = revcomp_word(f.hi);
+  int sh = 128 - 2 * k;  // 0..62
+  Key<2> r;
+  if (sh == 0) {
+    r.hi = a;
+    r.lo = b;
+  } else {
+    r.hi = a >> sh;
+    r.lo = (b >> sh) | (a << (64 - sh));
+  }
+  return r;
+}
+KDF_HD Key<1> kmin(const Key<1>& a, const Key<1>& b) {
+  Key<1> r;
+  r.lo = a.lo < b.lo ? a.lo : b.lo;
+  return r;
+}
+KDF_HD Key<2> kmin(const Key<2>& a, const Key<2>& b) {
+  bool a_le = (a.hi < b.hi) || (a.hi == b.hi && a.lo <= b.lo);
+  return a_le ? a : b;
+}
+
+// ------------------------------------------------------- stream access ----
+struct StreamView {
+  const u64* codes;
+  const u32* valid;
+  u64 n_bases;
+  u64 n_words;
+};
+
+KDF_HD u64 ld_code(const StreamView& s, u64 w) {
+#if defined(__CUDA_ARCH__)
+  return w < s.n_words ? __ldg(s.codes + w) : 0ull;
+#else
+  return w < s.n_words ? s.codes[w] : 0ull;
+#endif
+}
+KDF_HD u32 ld_valid(const StreamView& s, u64 w) {
+#if defined(__CUDA_ARCH__)
+  return w < s.n_words ? __ldg(s.valid + w) : 0u;
+#else
+  return w < s.n_words ? s.valid[w] : 0u;
+#endif
+}
+
+// Rolling iterator over the 32 window starts of stream word `w`:
+// positions 32w .. 32w+31.  `fwd`/`rc` are kept incrementally; the base and
+// validity shift registers move 2 / 1 bits per step.
+template <int KW> struct WindowIter;
+
+template <> struct WindowIter<1> {
+  u64 b0, b1;   // base shift register (b0 holds the current window at its top)
+  u64 vv;       // validity shift register (MSB = current start)
+  Key<1> rc;
+  int k;
+  KDF_HD WindowIter(const StreamView& s, u64 w, int k_) : k(k_) {
+    b0 = ld_code(s, w);
+    b1 = ld_code(s, w + 1);
+    vv = ((u64)ld_valid(s, w) << 32) | (u64)ld_valid(s, w + 1);
+    Key<1> f = fwd();
+    rc = revcomp(f, k);
+  }
+  KDF_HD bool any_valid() const { return vv != 0; }
+  KDF_HD Key<1> fwd() const {
+    Key<1> f;
+    f.lo = b0 >> (64 - 2 * k);
+    return f;
+  }
+  KDF_HD bool ok() const { return ((~vv) >> (64 - k)) == 0; }
+  KDF_HD Key<1> canonical() const { return kmin(fwd(), rc); }
+  KDF_HD void advance() {
+    b0 = (b0 << 2) | (b1 >> 62);
+    b1 <<= 2;
+    vv <<= 1;
+    u64 nb = (b0 >> (64 - 2 * k)) & 3ull;  // newest base of the new window
+    rc.lo = (rc.lo >> 2) | ((3ull - nb) << (2 * (k - 1)));
+  }
+};
+
+template <> struct WindowIter<2> {
+  u64 b0, b1, b2;
+  u64 v0, v1;  // 96 validity bits: v0 = words w,w+1 ; v1 = word w+2 in its top half
+  Key<2> rc;
+  int k;
+  KDF_HD WindowIter(const StreamView& s, u64 w, int k_) : k(k_) {
+    b0 = ld_code(s, w);
+    b1 = ld_code(s, w + 1);
+    b2 = ld_code(s, w + 2);
+    v0 = ((u64)ld_valid(s, w) << 32) | (u64)ld_valid(s, w + 1);
+    v1 = ((u64)ld_valid(s, w + 2) << 32);
+    rc = revcomp(fwd(), k);
+  }
+  KDF_HD bool any_valid() const { return (v0 | v1) != 0; }
+  KDF_HD Key<2> fwd() const {
+    int sh = 128 - 2 * k;  // 0..62
+    Key<2> f;
+    if (sh == 0) {
+      f.hi = b0;
+      f.lo = b1;
+    } else {
+      f.hi = b0 >> sh;
+      f.lo = (b1 >> sh) | (b0 << (64 - sh));
+    }
+    return f;
+  }
+  KDF_HD bool ok() const { return k == 64 ? (~v0 == 0) : (((~v0) >> (64 - k)) == 0); }
+  KDF_HD Key<2> canonical() const { return kmin(fwd(), rc); }
+  KDF_HD void advance() {
+    b0 = (b0 << 2) | (b1 >> 62);
+    b1 = (b1 << 2) | (b2 >> 62);
+    b2 <<= 2;
+    v0 = (v0 << 1) | (v1 >> 63);
+    v1 <<= 1;
+    // newest base = last base of the new window = bits just above the cut
+    int sh = 128 - 2 * k;
+    u64 nb = (sh == 0 ? b1 : (b1 >> sh)) & 3ull;
+    rc.lo = (rc.lo >> 2) | (rc.hi << 62);
+    rc.hi = (rc.hi >> 2) | ((3ull - nb) << (2 * (k - 1) - 64));
+  }
+};
+
+// Random-access extraction of the window starting at stream position p
+// (used by the per-read scan, where lanes stride through one read).
+template <int KW> struct WindowAt;
+
+template <> struct WindowAt<1> {
+  KDF_HD static bool get(const StreamView& s, u64 p, int k, Key<1>& out) {
+    u64 w = p >> 5;
+    int off = (int)(p & 31);
+    u64 c0 = ld_code(s, w), c1 = ld_code(s, w + 1);
+    u64 vv = ((u64)ld_valid(s, w) << 32) | (u64)ld_valid(s, w + 1);
+    u64 x = off ? ((c0 << (2 * off)) | (c1 >> (64 - 2 * off))) : c0;
+    vv <<= off;
+    Key<1> f;
+    f.lo = x >> (64 - 2 * k);
+    out = kmin(f, revcomp(f, k));
+    return ((~vv) >> (64 - k)) == 0;
+  }
+};
+template <> struct WindowAt<2> {
+  KDF_HD static bool get(const StreamView& s, u64 p, int k, Key<2>& out) {
+    u64 w = p >> 5;
+    int off = (int)(p & 31);
+    u64 c0 = ld_code(s, w), c1 = ld_code(s, w + 1), c2 = ld_code(s, w + 2);
+    u64 v0 = ((u64)ld_valid(s, w) << 32) | (u64)ld_valid(s, w + 1);
+    u64 v1 = ((u64)ld_valid(s, w + 2) << 32);
+    u64 x0 = c0, x1 = c1;
+    if (off) {
+      x0 = (c0 << (2 * off)) | (c1 >> (64 - 2 * off));
+      x1 = (c1 << (2 * off)) | (c2 >> (64 - 2 * off));
+      v0 = (v0 << off) | (v1 >> (64 - off));
+    }
+    int sh = 128 - 2 * k;
+    Key<2> f;
+    if (sh == 0) {
+      f.hi = x0;
+      f.lo = x1;
+    } else {
+      f.hi = x0 >> sh;
+      f.lo = (x1 >> sh) | (x0 << (64 - sh));
+    }
+    out = kmin(f, revcomp(f, k));
+    return k == 64 ? (~v0 == 0) : (((~v0) >> (64 - k)) == 0);
+  }
+};
+
+}  // namespace kdf

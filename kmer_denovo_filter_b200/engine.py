@@ -1,0 +1,479 @@
+"""ctypes binding of ``libkdf_sm100.so`` (C ABI in ``include/kdf.h``).
+
+PyTorch is used for device buffers and streams only; every computation on the
+k-mer path is a hand-written sm_100a kernel reached through the C ABI.  There
+is **no CPU fallback**: constructing :class:`CudaEngine` without the compiled
+library or without a CUDA device raises.
+
+Reference seams replaced (reference ``src/kmer_denovo_filter/``):
+``core/jellyfish_wrappers.py`` (count / count --if / dump), ``kmer_utils.py``
+``JellyfishKmerQuery`` (query), ``discovery/pipeline.py`` Modules 1-2.
+"""
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkdf_sm100.so")
+
+KDF_OK = 0
+MODE_INSERT_COUNT = 0
+MODE_INSERT_ONLY = 1
+MODE_COUNT_IF_PRESENT = 2
+MODE_MARK_IF_PRESENT = 3
+STAT_WINDOWS, STAT_FULL, STAT_HITS, STAT_NEW, N_STATS = 0, 1, 2, 3, 4
+NDISTINCT_OVERFLOW = 0xFFFFFFFF
+U32_MAX = 0xFFFFFFFF
+
+
+class KdfError(RuntimeError):
+    """Raised when a libkdf call fails (mirrors the reference's
+    ``RuntimeError("jellyfish ... failed: <stderr>")``,
+    ``core/jellyfish_wrappers.py:239-242``)."""
+
+
+class _Stream(ctypes.Structure):
+    _fields_ = [("codes", ctypes.c_void_p), ("valid", ctypes.c_void_p),
+                ("n_bases", ctypes.c_uint64)]
+
+
+class _DeviceProps(ctypes.Structure):
+    _fields_ = [("sm_count", ctypes.c_int), ("cc_major", ctypes.c_int),
+                ("cc_minor", ctypes.c_int), ("l2_bytes", ctypes.c_int),
+                ("hbm_bytes", ctypes.c_uint64), ("name", ctypes.c_char * 128)]
+
+
+# name -> (restype, argtypes); every symbol include/kdf.h declares
+_vp, _u64, _u32, _i = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int
+_SIGNATURES = {
+    "kdf_version": (_i, []),
+    "kdf_last_error": (ctypes.c_char_p, []),
+    "kdf_device_info": (_i, [_i, ctypes.POINTER(_DeviceProps)]),
+    "kdf_key_words": (_i, [_i]),
+    "kdf_table_bytes": (ctypes.c_size_t, [_u64, _i]),
+    "kdf_table_capacity_for": (_u64, [_u64]),
+    "kdf_table_create": (_i, [ctypes.POINTER(_vp), _i, _u64, _vp, _vp]),
+    "kdf_table_destroy": (_i, [_vp]),
+    "kdf_table_clear": (_i, [_vp, _vp]),
+    "kdf_table_clear_plane": (_i, [_vp, _i, _vp]),
+    "kdf_table_info": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_u64)]),
+    "kdf_extract_canonical": (_i, [ctypes.POINTER(_Stream), _i, _vp, _vp, _vp, _vp]),
+    "kdf_count_stream": (_i, [_vp, ctypes.POINTER(_Stream), _i, _i, _u32, _vp, _vp]),
+    "kdf_update_keys": (_i, [_vp, _vp, _vp, _u64, _i, _i, _u32, _vp, _vp]),
+    "kdf_threshold_compact": (_i, [_vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _u64, _vp, _vp]),
+    "kdf_lookup_keys": (_i, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp]),
+    "kdf_scan_reads": (_i, [_vp, ctypes.POINTER(_Stream), _vp, _vp, _u64, _u32, _vp, _vp, _vp, _vp,
+                            _u64, _vp, _vp, _vp]),
+    "kdf_partition_stream": (_i, [ctypes.POINTER(_Stream), _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "kdf_pack_sequences": (_u64, [_vp, _vp, _u64, _vp, _vp, _vp]),
+    "kdf_debug_extract_host": (_i, [_vp, _vp, _u64, _i, _i, _vp, _vp, _vp]),
+    "kdf_bench_random_access": (_i, [_vp, _u64, _u64, _i, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load_library(path=None):
+    """Load the shared library once; fail loudly when it is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.isfile(p):
+        raise KdfError(
+            "libkdf_sm100.so not found at %s — build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)" % p)
+    lib = ctypes.CDLL(p)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+# ---------------------------------------------------------------------------
+# host-side packing (CPU helper of the library; no device needed)
+# ---------------------------------------------------------------------------
+
+class HostStream:
+    """Packed stream in host memory (numpy): ``codes`` u64, ``valid`` u32,
+    ``n_bases``, ``read_starts`` u64, ``read_lens`` u32."""
+
+    __slots__ = ("codes", "valid", "n_bases", "read_starts", "read_lens")
+
+    def __init__(self, codes, valid, n_bases, read_starts, read_lens):
+        self.codes = codes
+        self.valid = valid
+        self.n_bases = int(n_bases)
+        self.read_starts = read_starts
+        self.read_lens = read_lens
+
+    @property
+    def n_reads(self):
+        return int(self.read_lens.shape[0])
+
+    @property
+    def n_words(self):
+        return (self.n_bases + 31) // 32
+
+    def window_count_upper_bound(self, k):
+        l = self.read_lens.astype(np.int64) - (k - 1)
+        return int(np.clip(l, 0, None).sum())
+
+
+def pack_sequences(seqs):
+    """Pack an iterable of str/bytes sequences into a :class:`HostStream`."""
+    lib = load_library()
+    bs = [s.encode("latin-1") if isinstance(s, str) else bytes(s) for s in seqs]
+    n = len(bs)
+    lens = np.fromiter((len(b) for b in bs), dtype=np.uint64, count=n)
+    offsets = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(lens, out=offsets[1:])
+    blob = b"".join(bs)
+    buf = np.frombuffer(blob, dtype=np.uint8) if blob else np.zeros(1, dtype=np.uint8)
+    total = int(lens.sum()) + max(n - 1, 0)
+    n_words = (total + 31) // 32
+    codes = np.zeros(max(n_words, 1), dtype=np.uint64)
+    valid = np.zeros(max(n_words, 1), dtype=np.uint32)
+    read_offsets = np.zeros(n + 1, dtype=np.uint64)
+    got = lib.kdf_pack_sequences(_np_ptr(buf), _np_ptr(offsets), n, _np_ptr(codes),
+                                 _np_ptr(valid), _np_ptr(read_offsets))
+    assert got == total
+    return HostStream(codes[:n_words], valid[:n_words], total,
+                      read_offsets[:n].copy(), lens.astype(np.uint32))
+
+
+def debug_extract_host(hs, k, random_access=False):
+    """Run the device iterator templates on the CPU (test hook)."""
+    lib = load_library()
+    n = hs.n_bases
+    lo = np.zeros(max(n, 1), dtype=np.uint64)
+    hi = np.zeros(max(n, 1), dtype=np.uint64)
+    ok = np.zeros(max(n, 1), dtype=np.uint8)
+    codes = np.ascontiguousarray(hs.codes)
+    valid = np.ascontiguousarray(hs.valid)
+    if codes.size == 0:
+        return lo[:0], hi[:0], ok[:0].astype(bool)
+    rc = lib.kdf_debug_extract_host(_np_ptr(codes), _np_ptr(valid), n, k,
+                                    1 if random_access else 0, _np_ptr(lo), _np_ptr(hi), _np_ptr(ok))
+    if rc != KDF_OK:
+        raise KdfError(lib.kdf_last_error().decode())
+    return lo[:n], hi[:n], ok[:n].astype(bool)
+
+
+# ---------------------------------------------------------------------------
+# device side
+# ---------------------------------------------------------------------------
+
+class DeviceStream:
+    """A packed stream resident in HBM (torch tensors as raw buffers)."""
+
+    __slots__ = ("codes", "valid", "n_bases", "read_starts", "read_lens", "_c")
+
+    def __init__(self, codes, valid, n_bases, read_starts=None, read_lens=None):
+        self.codes = codes          # torch.int64 (bit pattern of u64)
+        self.valid = valid          # torch.int32 (bit pattern of u32)
+        self.n_bases = int(n_bases)
+        self.read_starts = read_starts  # torch.int64 or None
+        self.read_lens = read_lens      # torch.int32 or None
+        self._c = _Stream(codes.data_ptr(), valid.data_ptr(), self.n_bases)
+
+    @property
+    def n_reads(self):
+        return 0 if self.read_lens is None else int(self.read_lens.shape[0])
+
+    def c(self):
+        return ctypes.byref(self._c)
+
+
+class KmerTable:
+    """Device hash table handle; owns the torch buffer that backs the slots."""
+
+    def __init__(self, engine, k, capacity):
+        self.engine = engine
+        self.k = int(k)
+        self.capacity = int(capacity)
+        lib = engine.lib
+        self.key_words = lib.kdf_key_words(self.k)
+        if not self.key_words:
+            raise KdfError("k=%d unsupported by the GPU engine (1..64)" % k)
+        nbytes = lib.kdf_table_bytes(self.capacity, self.key_words)
+        torch = engine.torch
+        # int64 storage guarantees >= 256-byte alignment from the caching allocator
+        self.buf = torch.empty(nbytes // 8, dtype=torch.int64, device=engine.device)
+        h = ctypes.c_void_p()
+        engine._check(lib.kdf_table_create(ctypes.byref(h), self.k, self.capacity,
+                                           self.buf.data_ptr(), engine.stream_ptr()))
+        self.handle = h
+
+    @property
+    def nbytes(self):
+        return self.buf.numel() * 8
+
+    def close(self):
+        if self.handle is not None:
+            self.engine.lib.kdf_table_destroy(self.handle)
+            self.handle = None
+            self.buf = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CudaEngine:
+    """One engine per GPU / process.  All calls are ordered on torch's current
+    stream of ``device``."""
+
+    def __init__(self, device=None):
+        import torch
+        self.torch = torch
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise KdfError("CUDA device required: the k-mer engine has no CPU fallback")
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        props = _DeviceProps()
+        self._check(self.lib.kdf_device_info(self.device.index or 0, ctypes.byref(props)))
+        self.props = {"sm_count": props.sm_count, "cc": (props.cc_major, props.cc_minor),
+                      "l2_bytes": props.l2_bytes, "hbm_bytes": props.hbm_bytes,
+                      "name": props.name.decode()}
+        self.launches = 0  # kernels launched through this engine (bench.py gpu_launches)
+
+    # -- plumbing ----------------------------------------------------------
+    def _check(self, rc):
+        if rc != KDF_OK:
+            raise KdfError("libkdf error %d: %s" % (rc, self.lib.kdf_last_error().decode()))
+
+    def stream_ptr(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def zeros(self, n, dtype):
+        return self.torch.zeros(n, dtype=dtype, device=self.device)
+
+    def empty(self, n, dtype):
+        return self.torch.empty(n, dtype=dtype, device=self.device)
+
+    def new_stats(self):
+        return self.zeros(N_STATS, self.torch.int64)
+
+    def read_stats(self, stats):
+        v = stats.cpu().numpy().view(np.uint64)
+        return {"windows": int(v[STAT_WINDOWS]), "full": int(v[STAT_FULL]),
+                "hits": int(v[STAT_HITS]), "new": int(v[STAT_NEW])}
+
+    # -- data movement -----------------------------------------------------
+    def upload(self, hs, non_blocking=False, with_reads=True):
+        """HostStream → DeviceStream (H2D copies on the current stream)."""
+        torch = self.torch
+        codes = torch.from_numpy(np.ascontiguousarray(hs.codes).view(np.int64))
+        valid = torch.from_numpy(np.ascontiguousarray(hs.valid).view(np.int32))
+        rs = rl = None
+        if with_reads and hs.read_lens is not None:
+            rs = torch.from_numpy(np.ascontiguousarray(hs.read_starts).view(np.int64)).to(
+                self.device, non_blocking=non_blocking)
+            rl = torch.from_numpy(np.ascontiguousarray(hs.read_lens).view(np.int32)).to(
+                self.device, non_blocking=non_blocking)
+        return DeviceStream(codes.to(self.device, non_blocking=non_blocking),
+                            valid.to(self.device, non_blocking=non_blocking),
+                            hs.n_bases, rs, rl)
+
+    def keys_to_device(self, keys, key_words):
+        """Python ints / numpy → (lo, hi) int64 device tensors."""
+        torch = self.torch
+        if isinstance(keys, tuple):
+            lo_np, hi_np = keys
+        else:
+            ks = list(keys)
+            lo_np = np.fromiter((x & 0xFFFFFFFFFFFFFFFF for x in ks), dtype=np.uint64, count=len(ks))
+            hi_np = np.fromiter((x >> 64 for x in ks), dtype=np.uint64, count=len(ks))
+        lo = torch.from_numpy(lo_np.view(np.int64)).to(self.device)
+        hi = torch.from_numpy(hi_np.view(np.int64)).to(self.device) if key_words == 2 else None
+        return lo, hi
+
+    @staticmethod
+    def keys_to_pyints(lo, hi=None):
+        lo_np = lo.cpu().numpy().view(np.uint64)
+        if hi is None:
+            return [int(x) for x in lo_np.tolist()]
+        hi_np = hi.cpu().numpy().view(np.uint64)
+        return [(int(h) << 64) | int(l) for h, l in zip(hi_np.tolist(), lo_np.tolist())]
+
+    # -- tables --------------------------------------------------------------
+    def capacity_for(self, n_keys):
+        return int(self.lib.kdf_table_capacity_for(int(n_keys)))
+
+    def new_table(self, k, n_keys=None, capacity=None):
+        if capacity is None:
+            capacity = self.capacity_for(n_keys or 0)
+        self.launches += 1
+        return KmerTable(self, k, capacity)
+
+    def clear_plane(self, table, plane):
+        self._check(self.lib.kdf_table_clear_plane(table.handle, plane, self.stream_ptr()))
+        self.launches += 1
+
+    # -- kernels -------------------------------------------------------------
+    def extract_canonical(self, ds, k):
+        """K1 → (lo, hi|None, ok_words) device tensors."""
+        torch = self.torch
+        kw = self.lib.kdf_key_words(k)
+        if not kw:
+            raise KdfError("k=%d unsupported (1..64)" % k)
+        n = max(ds.n_bases, 1)
+        lo = self.empty(n, torch.int64)
+        hi = self.empty(n, torch.int64) if kw == 2 else None
+        ok = self.zeros(max((ds.n_bases + 31) // 32, 1), torch.int32)
+        self._check(self.lib.kdf_extract_canonical(
+            ds.c(), k, lo.data_ptr(), hi.data_ptr() if hi is not None else None,
+            ok.data_ptr(), self.stream_ptr()))
+        self.launches += 1
+        return lo[:ds.n_bases], (hi[:ds.n_bases] if hi is not None else None), ok
+
+    def count_stream(self, table, ds, mode=MODE_INSERT_COUNT, plane=0, arg=1, stats=None):
+        """K1+K2 fused."""
+        self._check(self.lib.kdf_count_stream(
+            table.handle, ds.c(), mode, plane, arg,
+            stats.data_ptr() if stats is not None else None, self.stream_ptr()))
+        self.launches += 1
+
+    def update_keys(self, table, lo, hi=None, mode=MODE_INSERT_ONLY, plane=0, arg=1, stats=None):
+        n = int(lo.shape[0])
+        self._check(self.lib.kdf_update_keys(
+            table.handle, lo.data_ptr() if n else None,
+            hi.data_ptr() if (hi is not None and n) else None, n, mode, plane, arg,
+            stats.data_ptr() if stats is not None else None, self.stream_ptr()))
+        if n:
+            self.launches += 1
+
+    def check_not_full(self, stats):
+        if self.read_stats(stats)["full"]:
+            raise KdfError("k-mer table full (libkdf error %d): size it with more slots" % -4)
+
+    def threshold_count(self, table, min0=0, max0=U32_MAX, min1=0, max1=U32_MAX):
+        n_out = self.zeros(1, self.torch.int64)
+        self._check(self.lib.kdf_threshold_compact(
+            table.handle, min0, max0, min1, max1, None, None, None, None, 0,
+            n_out.data_ptr(), self.stream_ptr()))
+        self.launches += 1
+        return int(n_out.item())
+
+    def threshold_compact(self, table, min0=0, max0=U32_MAX, min1=0, max1=U32_MAX,
+                          want_planes=False, n_expected=None):
+        """K3 → (n, lo, hi|None, p0|None, p1|None); exact two-pass sizing."""
+        torch = self.torch
+        n = self.threshold_count(table, min0, max0, min1, max1) if n_expected is None else int(n_expected)
+        cap = max(n, 1)
+        lo = self.empty(cap, torch.int64)
+        hi = self.empty(cap, torch.int64) if table.key_words == 2 else None
+        p0 = self.empty(cap, torch.int32) if want_planes else None
+        p1 = self.empty(cap, torch.int32) if want_planes else None
+        n_out = self.zeros(1, torch.int64)
+        self._check(self.lib.kdf_threshold_compact(
+            table.handle, min0, max0, min1, max1, lo.data_ptr(),
+            hi.data_ptr() if hi is not None else None,
+            p0.data_ptr() if p0 is not None else None,
+            p1.data_ptr() if p1 is not None else None,
+            cap, n_out.data_ptr(), self.stream_ptr()))
+        self.launches += 1
+        got = int(n_out.item())
+        if got > cap:
+            raise KdfError("threshold_compact: %d matches exceed buffer %d" % (got, cap))
+        return (got, lo[:got], hi[:got] if hi is not None else None,
+                p0[:got] if p0 is not None else None, p1[:got] if p1 is not None else None)
+
+    def lookup_keys(self, table, lo, hi=None, want_planes=True):
+        """K4 → (found u8, p0, p1) device tensors."""
+        torch = self.torch
+        n = int(lo.shape[0])
+        found = self.zeros(max(n, 1), torch.uint8)
+        p0 = self.zeros(max(n, 1), torch.int32) if want_planes else None
+        p1 = self.zeros(max(n, 1), torch.int32) if want_planes else None
+        if n:
+            self._check(self.lib.kdf_lookup_keys(
+                table.handle, lo.data_ptr(), hi.data_ptr() if hi is not None else None, n,
+                found.data_ptr(), p0.data_ptr() if p0 is not None else None,
+                p1.data_ptr() if p1 is not None else None, self.stream_ptr()))
+            self.launches += 1
+        return found[:n], (p0[:n] if p0 is not None else None), (p1[:n] if p1 is not None else None)
+
+    def scan_reads(self, table, ds, min_distinct=1, hit_cap=None, stats=None, want_hits=True):
+        """K4+K5 → dict(ndistinct, nhits, hit_pos, hit_slot, n_hits)."""
+        torch = self.torch
+        n_reads = ds.n_reads
+        nd = self.zeros(max(n_reads, 1), torch.int32)
+        nh = self.zeros(max(n_reads, 1), torch.int32)
+        if hit_cap is None:
+            hit_cap = 1 << 16
+        while True:
+            n_hits = self.zeros(1, torch.int64)
+            hp = self.empty(max(hit_cap, 1), torch.int64) if want_hits else None
+            hsl = self.empty(max(hit_cap, 1), torch.int32) if want_hits else None
+            st = None
+            if stats is not None:
+                st = self.zeros(N_STATS, torch.int64)
+            if n_reads:
+                self._check(self.lib.kdf_scan_reads(
+                    table.handle, ds.c(), ds.read_starts.data_ptr(), ds.read_lens.data_ptr(),
+                    n_reads, min_distinct, nd.data_ptr(), nh.data_ptr(),
+                    hp.data_ptr() if hp is not None else None,
+                    hsl.data_ptr() if hsl is not None else None,
+                    hit_cap if want_hits else 0, n_hits.data_ptr(),
+                    st.data_ptr() if st is not None else None, self.stream_ptr()))
+                self.launches += 1
+            total = int(n_hits.item())
+            if not want_hits or total <= hit_cap:
+                break
+            hit_cap = total  # exact retry (rare: only when hits are dense)
+        if stats is not None and st is not None:
+            stats += st
+        return {"ndistinct": nd[:n_reads], "nhits": nh[:n_reads],
+                "hit_pos": hp[:total] if hp is not None else None,
+                "hit_slot": hsl[:total] if hsl is not None else None, "n_hits": total}
+
+    def partition_stream(self, ds, k, n_ranks):
+        """K6 → (counts np.int64[n_ranks], lo, hi|None) with keys grouped by owner."""
+        torch = self.torch
+        kw = self.lib.kdf_key_words(k)
+        counts = self.zeros(n_ranks, torch.int64)
+        self._check(self.lib.kdf_partition_stream(ds.c(), k, n_ranks, counts.data_ptr(),
+                                                  None, None, None, None, self.stream_ptr()))
+        self.launches += 1
+        c = counts.cpu().numpy().astype(np.int64)
+        total = int(c.sum())
+        offs = np.zeros(n_ranks, dtype=np.int64)
+        offs[1:] = np.cumsum(c[:-1])
+        d_offs = torch.from_numpy(offs).to(self.device)
+        cursors = self.zeros(n_ranks, torch.int64)
+        lo = self.empty(max(total, 1), torch.int64)
+        hi = self.empty(max(total, 1), torch.int64) if kw == 2 else None
+        if total:
+            self._check(self.lib.kdf_partition_stream(
+                ds.c(), k, n_ranks, counts.data_ptr(), d_offs.data_ptr(), cursors.data_ptr(),
+                lo.data_ptr(), hi.data_ptr() if hi is not None else None, self.stream_ptr()))
+            self.launches += 1
+        return c, lo[:total], (hi[:total] if hi is not None else None)
+
+    def bench_random_access(self, buf, n_ops, atomic):
+        sink = self.zeros(1, self.torch.int64)
+        self._check(self.lib.kdf_bench_random_access(
+            buf.data_ptr(), buf.numel() * buf.element_size(), n_ops, 1 if atomic else 0,
+            sink.data_ptr(), self.stream_ptr()))
+        self.launches += 1

@@ -1,0 +1,288 @@
+"""GPU parity tests: every kernel of libkdf_sm100.so, called through the C ABI
+(ctypes), against the CPU oracle on the same seeded inputs.  Bit-exact."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import kmers
+
+pytestmark = pytest.mark.gpu
+
+KS = [5, 21, 31, 32, 33, 47, 63]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from kmer_denovo_filter_b200 import engine
+    return engine.CudaEngine()
+
+
+def _rand_seqs(seed, n=400, maxlen=260, alphabet="ACGTACGTACGTACGTACGTN"):
+    rng = random.Random(seed)
+    return ["".join(rng.choice(alphabet) for _ in range(rng.randint(0, maxlen))) for _ in range(n)]
+
+
+def _genome_reads(seed, glen=20000, n=1500, rl=150, err=0.01):
+    """Reads sampled from a random genome so that k-mers repeat (counts > 1)."""
+    rng = random.Random(seed)
+    g = "".join(rng.choice("ACGT") for _ in range(glen))
+    out = []
+    for _ in range(n):
+        s = rng.randrange(0, glen - rl)
+        r = list(g[s:s + rl])
+        for i in range(rl):
+            x = rng.random()
+            if x < err:
+                r[i] = rng.choice("ACGT")
+            elif x < err + 0.001:
+                r[i] = "N"
+        r = "".join(r)
+        if rng.random() < 0.5:
+            r = kmers.reverse_complement(r)
+        out.append(r)
+    return g, out
+
+
+def _table_dict(eng, table):
+    n, lo, hi, p0, p1 = eng.threshold_compact(table, want_planes=True)
+    keys = eng.keys_to_pyints(lo, hi)
+    a = p0.cpu().numpy().view(np.uint32).tolist()
+    b = p1.cpu().numpy().view(np.uint32).tolist()
+    assert len(set(keys)) == len(keys), "duplicate keys in table"
+    return {k: (x, y) for k, x, y in zip(keys, a, b)}
+
+
+@pytest.mark.parametrize("k", KS)
+def test_extract_canonical(eng, k):
+    from kmer_denovo_filter_b200 import engine
+    seqs = _rand_seqs(k)
+    hs = engine.pack_sequences(seqs)
+    ds = eng.upload(hs)
+    lo, hi, okw = eng.extract_canonical(ds, k)
+    codes, valid, _s, _l = kmers.encode_stream(seqs)
+    ohi, olo, ook = kmers.canonical_windows(codes, valid, k)
+    n = ook.shape[0]
+    okw = okw.cpu().numpy().view(np.uint32)
+    idx = np.arange(hs.n_bases)
+    ok = ((okw[idx >> 5] >> (31 - (idx & 31)).astype(np.uint32)) & 1).astype(bool)
+    assert not ok[n:].any()
+    assert np.array_equal(ok[:n], ook)
+    glo = lo.cpu().numpy().view(np.uint64)
+    assert np.array_equal(glo[:n][ook], olo[ook])
+    if hi is not None:
+        ghi = hi.cpu().numpy().view(np.uint64)
+        assert np.array_equal(ghi[:n][ook], ohi[ook])
+
+
+@pytest.mark.parametrize("k", KS)
+def test_count_stream_equals_oracle(eng, k):
+    from kmer_denovo_filter_b200 import engine
+    _g, reads = _genome_reads(k)
+    want = kmers.count_sequences(reads, k)
+    hs = engine.pack_sequences(reads)
+    ds = eng.upload(hs)
+    t = eng.new_table(k, n_keys=len(want))
+    st = eng.new_stats()
+    eng.count_stream(t, ds, engine.MODE_INSERT_COUNT, 0, 1, st)
+    s = eng.read_stats(st)
+    assert s["full"] == 0
+    assert s["windows"] == sum(want.values())
+    assert s["new"] == len(want)
+    assert s["hits"] == s["windows"] - s["new"]
+    got = _table_dict(eng, t)
+    assert {key: v[0] for key, v in got.items()} == want
+    assert all(v[1] == 0 for v in got.values())
+
+
+def test_count_is_deterministic_and_high_load(eng):
+    """Two runs give the same multiset; load factor 0.95 still exact."""
+    from kmer_denovo_filter_b200 import engine
+    k = 31
+    _g, reads = _genome_reads(7, glen=8000, n=800)
+    want = kmers.count_sequences(reads, k)
+    ds = eng.upload(engine.pack_sequences(reads))
+    cap = int(len(want) / 0.95) + 1
+    for _ in range(2):
+        t = eng.new_table(k, capacity=cap)
+        st = eng.new_stats()
+        eng.count_stream(t, ds, engine.MODE_INSERT_COUNT, 0, 1, st)
+        assert eng.read_stats(st)["full"] == 0
+        assert {key: v[0] for key, v in _table_dict(eng, t).items()} == want
+
+
+def test_table_full_is_reported(eng):
+    from kmer_denovo_filter_b200 import engine
+    k = 21
+    _g, reads = _genome_reads(3, glen=5000, n=300)
+    want = kmers.count_sequences(reads, k)
+    ds = eng.upload(engine.pack_sequences(reads))
+    t = eng.new_table(k, capacity=len(want) // 2)
+    st = eng.new_stats()
+    eng.count_stream(t, ds, engine.MODE_INSERT_COUNT, 0, 1, st)
+    assert eng.read_stats(st)["full"] == 1
+    with pytest.raises(engine.KdfError):
+        eng.check_not_full(st)
+
+
+@pytest.mark.parametrize("k", [31, 47])
+def test_filtered_count_mark_lookup_threshold(eng, k):
+    """count --if (plane 1), reference mark, lookup and threshold compaction."""
+    from kmer_denovo_filter_b200 import engine
+    g, child = _genome_reads(11 + k, glen=12000, n=900)
+    _g2, parent = _genome_reads(12 + k, glen=12000, n=900)
+    parent = parent[:300] + child[:200]
+    cc = kmers.count_sequences(child, k)
+    pc = kmers.count_sequences(parent, k)
+    rc = kmers.count_sequences([g[:6000]], k)
+    ds_c = eng.upload(engine.pack_sequences(child))
+    ds_p = eng.upload(engine.pack_sequences(parent))
+    ds_r = eng.upload(engine.pack_sequences([g[:6000]]))
+    t = eng.new_table(k, n_keys=len(cc))
+    eng.count_stream(t, ds_c, engine.MODE_INSERT_COUNT, 0, 1)
+    st = eng.new_stats()
+    eng.count_stream(t, ds_p, engine.MODE_COUNT_IF_PRESENT, 1, 1, st)
+    s = eng.read_stats(st)
+    assert s["windows"] == sum(pc.values()) and s["new"] == 0
+    assert s["hits"] == sum(c for key, c in pc.items() if key in cc)
+    got = _table_dict(eng, t)
+    assert set(got) == set(cc)
+    for key, (a, b) in got.items():
+        assert a == cc[key] and b == pc.get(key, 0)
+    # threshold: child count >= 3 and parent count <= 0
+    n, lo, hi, _a, _b = eng.threshold_compact(t, min0=3, max1=0)
+    want = {key for key in cc if cc[key] >= 3 and pc.get(key, 0) == 0}
+    assert n == len(want) and set(eng.keys_to_pyints(lo, hi)) == want
+    assert eng.threshold_count(t, min0=3) == sum(1 for c in cc.values() if c >= 3)
+    # mark-if-present with the reference, on a cleared plane 1
+    eng.clear_plane(t, 1)
+    eng.count_stream(t, ds_r, engine.MODE_MARK_IF_PRESENT, 1, 1)
+    got = _table_dict(eng, t)
+    for key, (a, b) in got.items():
+        assert a == cc[key] and b == (1 if key in rc else 0)
+    # lookup: present and absent keys
+    probe = list(cc)[:500] + [key for key in pc if key not in cc][:500]
+    lo, hi = eng.keys_to_device(probe, t.key_words)
+    found, p0, _p1 = eng.lookup_keys(t, lo, hi)
+    found = found.cpu().numpy().astype(bool).tolist()
+    p0 = p0.cpu().numpy().view(np.uint32).tolist()
+    for key, f, c in zip(probe, found, p0):
+        assert f == (key in cc) and c == cc.get(key, 0)
+
+
+@pytest.mark.parametrize("k", [31, 63])
+def test_update_keys_insert_only_then_count_if(eng, k):
+    from kmer_denovo_filter_b200 import engine
+    _g, reads = _genome_reads(21 + k, glen=9000, n=700)
+    full = kmers.count_sequences(reads, k)
+    filt = sorted(full)[::3]
+    t = eng.new_table(k, n_keys=len(filt))
+    lo, hi = eng.keys_to_device(filt + filt[:10], t.key_words)  # duplicates are harmless
+    st = eng.new_stats()
+    eng.update_keys(t, lo, hi, engine.MODE_INSERT_ONLY, 0, 0, st)
+    assert eng.read_stats(st)["new"] == len(filt)
+    ds = eng.upload(engine.pack_sequences(reads))
+    eng.count_stream(t, ds, engine.MODE_COUNT_IF_PRESENT, 0, 1)
+    got = _table_dict(eng, t)
+    assert {key: v[0] for key, v in got.items()} == {key: full[key] for key in filt}
+
+
+@pytest.mark.parametrize("k", [5, 31, 47])
+@pytest.mark.parametrize("min_distinct", [1, 3])
+def test_scan_reads(eng, k, min_distinct):
+    from kmer_denovo_filter_b200 import engine
+    from oracle import discovery
+    _g, reads = _genome_reads(31 + k, glen=6000, n=600, rl=120)
+    reads += ["", "ACG", "N" * 50]
+    full = kmers.count_sequences(reads, k)
+    pu = set(sorted(full)[::7])
+    t = eng.new_table(k, n_keys=len(pu))
+    lo, hi = eng.keys_to_device(sorted(pu), t.key_words)
+    eng.update_keys(t, lo, hi, engine.MODE_INSERT_ONLY, 0, 0)
+    hs = engine.pack_sequences(reads)
+    ds = eng.upload(hs)
+    res = eng.scan_reads(t, ds, min_distinct=min_distinct, hit_cap=16)  # forces the retry path
+    nd = res["ndistinct"].cpu().numpy().view(np.uint32).tolist()
+    nh = res["nhits"].cpu().numpy().view(np.uint32).tolist()
+    # slot -> key map to decode hit slots
+    slot_keys = {}
+    hp = res["hit_pos"].cpu().numpy().view(np.uint64)
+    hsl = res["hit_slot"].cpu().numpy().view(np.uint32)
+    starts = hs.read_starts
+    want_hits = {}
+    for r, seq in enumerate(reads):
+        uniq, idx = discovery.scan_read_numeric(seq, k, pu)
+        assert nd[r] == len(uniq), r
+        assert nh[r] == len(idx), r
+        if len(uniq) >= max(1, min_distinct):
+            for i in idx:
+                want_hits[int(starts[r]) + i] = None
+    assert sorted(hp.tolist()) == sorted(want_hits)
+    # every emitted slot decodes to the canonical key at that position
+    klo, khi, kok = engine.debug_extract_host(hs, k)
+    found, _a, _b = eng.lookup_keys(t, lo, hi, want_planes=False)
+    assert bool(found.all())
+    n, tlo, thi, _p0, _p1 = eng.threshold_compact(t)
+    assert n == len(pu)
+
+
+def test_scan_reads_overflow_path(eng):
+    """A read with more than 1024 hit windows reports the overflow sentinel and
+    still emits every hit."""
+    from kmer_denovo_filter_b200 import engine
+    k = 5
+    rng = random.Random(5)
+    long_read = "".join(rng.choice("ACGT") for _ in range(3000))
+    pu = set(kmers.count_sequences([long_read], k))
+    t = eng.new_table(k, n_keys=len(pu))
+    lo, hi = eng.keys_to_device(sorted(pu), t.key_words)
+    eng.update_keys(t, lo, hi, engine.MODE_INSERT_ONLY, 0, 0)
+    hs = engine.pack_sequences([long_read, "ACGTACGTAC"])
+    res = eng.scan_reads(t, eng.upload(hs), min_distinct=1)
+    nd = res["ndistinct"].cpu().numpy().view(np.uint32).tolist()
+    nh = res["nhits"].cpu().numpy().view(np.uint32).tolist()
+    assert nd[0] == engine.NDISTINCT_OVERFLOW and nh[0] == 3000 - k + 1
+    assert res["n_hits"] == nh[0] + nh[1]
+    slots = res["hit_slot"].cpu().numpy()
+    pos = res["hit_pos"].cpu().numpy().view(np.uint64)
+    first = slots[pos < 3000]
+    assert len(set(first.tolist())) == len(pu)
+
+
+@pytest.mark.parametrize("k", [31, 47])
+@pytest.mark.parametrize("n_ranks", [1, 2, 8])
+def test_partition_stream(eng, k, n_ranks):
+    from kmer_denovo_filter_b200 import engine
+    _g, reads = _genome_reads(41 + k, glen=5000, n=500)
+    hs = engine.pack_sequences(reads)
+    ds = eng.upload(hs)
+    counts, lo, hi = eng.partition_stream(ds, k, n_ranks)
+    codes, valid, _s, _l = kmers.encode_stream(reads)
+    ohi, olo, ook = kmers.canonical_windows(codes, valid, k)
+    want = sorted(kmers.to_pyints(ohi[ook], olo[ook]))
+    got = eng.keys_to_pyints(lo, hi)
+    assert sorted(got) == want
+    assert int(counts.sum()) == len(want)
+    # every key of bin r maps to owner r, and equal keys share a bin
+    off = 0
+    owner_of = {}
+    for r in range(n_ranks):
+        for key in got[off:off + int(counts[r])]:
+            assert owner_of.setdefault(key, r) == r
+        off += int(counts[r])
+    if n_ranks > 1:
+        assert (counts > 0).all()
+        assert counts.max() < 2.0 * counts.mean()
+
+
+def test_empty_stream_is_a_noop(eng):
+    from kmer_denovo_filter_b200 import engine
+    hs = engine.pack_sequences([])
+    ds = eng.upload(hs)
+    t = eng.new_table(31, n_keys=10)
+    st = eng.new_stats()
+    eng.count_stream(t, ds, engine.MODE_INSERT_COUNT, 0, 1, st)
+    assert eng.read_stats(st) == {"windows": 0, "full": 0, "hits": 0, "new": 0}
+    assert eng.threshold_count(t) == 0
+    res = eng.scan_reads(t, ds)
+    assert res["n_hits"] == 0
