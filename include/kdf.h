@@ -211,6 +211,57 @@ uint64_t kdf_pack_sequences(const char* seqs, const uint64_t* offsets,
                             uint64_t n_seqs, uint64_t* codes, uint32_t* valid,
                             uint64_t* read_offsets);
 
+/* ---- host BGZF/BAM decode -> packed batches (CPU, multi-threaded) --------
+ * Replaces, for BAM input, `samtools fasta -F 0xD00` in front of Jellyfish
+ * (core/jellyfish_wrappers.py:159-165; discovery/pipeline.py:106-112, 369-375)
+ * and the pysam iteration of the anchoring scan (core/bam_scanner.py:405-414).
+ *   KDF_BAM_FASTA : drop flag & 0xD00; inside a run of consecutive records with
+ *                   the same QNAME keep the first record of each read-part
+ *                   (READ1 / READ2 / other) — what samtools fasta emits.
+ *   KDF_BAM_SCAN  : drop secondary (0x100) and duplicate (0x400) records only.
+ *   KDF_BAM_ALL   : every record.
+ * A batch owns its host memory until kdf_bam_batch_free.  Metadata arrays are
+ * filled only when want_meta != 0.  max_bases == 0 reads to end of file.     */
+#define KDF_BAM_FASTA 0
+#define KDF_BAM_SCAN 1
+#define KDF_BAM_ALL 2
+
+typedef struct kdf_bam kdf_bam;
+
+typedef struct kdf_bam_batch {
+  void* impl;
+  uint64_t n_reads;
+  uint64_t n_bases;              /* stream length incl. separators            */
+  const uint64_t* codes;         /* HOST, stream layout                       */
+  const uint32_t* valid;         /* HOST                                      */
+  const uint64_t* read_starts;   /* HOST n_reads                              */
+  const uint32_t* read_lens;     /* HOST n_reads                              */
+  const uint64_t* rec_index;     /* HOST n_reads: record number in the file   */
+  const int32_t* ref_id;         /* --- metadata (want_meta) ---              */
+  const int32_t* pos;
+  const int32_t* next_ref_id;
+  const int32_t* next_pos;
+  const uint16_t* flag;
+  const uint8_t* mapq;
+  const uint64_t* qname_off;     /* n_reads+1 offsets into qname_blob         */
+  const char* qname_blob;
+  const uint64_t* cigar_off;     /* n_reads+1 offsets into cigar_blob         */
+  const uint32_t* cigar_blob;    /* BAM encoding: len<<4 | op                 */
+  const uint64_t* sa_off;        /* n_reads+1 offsets into sa_blob (SA:Z)     */
+  const char* sa_blob;
+  int at_eof;
+} kdf_bam_batch;
+
+int kdf_bam_open(const char* path, int n_threads, kdf_bam** out);
+void kdf_bam_close(kdf_bam* b);
+int kdf_bam_n_refs(const kdf_bam* b);
+const char* kdf_bam_ref_name(const kdf_bam* b, int i);
+int64_t kdf_bam_ref_len(const kdf_bam* b, int i);
+int kdf_bam_next_batch(kdf_bam* b, int mode, uint64_t max_bases, int want_meta,
+                       kdf_bam_batch* out);
+void kdf_bam_batch_free(kdf_bam_batch* batch);
+const char* kdf_host_last_error(void);
+
 /* Test hook: runs the device window-iterator templates on the CPU (host
  * instantiation of the same code) so the bit manipulation can be verified
  * without a GPU.  Not used by any product path.                             */

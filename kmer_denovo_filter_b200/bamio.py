@@ -1,0 +1,276 @@
+"""Host BAM input: ctypes binding of the library's multi-threaded BGZF/BAM decoder.
+
+Replaces ``samtools fasta -F 0xD00`` (reference ``core/jellyfish_wrappers.py:
+159-165``, ``discovery/pipeline.py:106-112, 369-375``) and the pysam iteration
+of the anchoring scan (``core/bam_scanner.py:405-414``) for BAM input.  Reads are
+delivered as packed batches (:class:`HostBatch`) ready for upload; alignment
+metadata comes as flat numpy arrays with pysam-like per-record accessors for
+the (few) informative reads the CPU cluster step needs.
+"""
+
+import ctypes
+import os
+
+import numpy as np
+
+from . import engine as _engine
+
+MODE_FASTA = 0   # samtools fasta -F 0xD00 semantics (counting input)
+MODE_SCAN = 1    # skip secondary + duplicate (anchoring scan)
+MODE_ALL = 2
+
+_vp, _u64, _i = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int
+
+
+class _Batch(ctypes.Structure):
+    _fields_ = [
+        ("impl", _vp), ("n_reads", _u64), ("n_bases", _u64),
+        ("codes", _vp), ("valid", _vp), ("read_starts", _vp), ("read_lens", _vp),
+        ("rec_index", _vp), ("ref_id", _vp), ("pos", _vp), ("next_ref_id", _vp),
+        ("next_pos", _vp), ("flag", _vp), ("mapq", _vp), ("qname_off", _vp),
+        ("qname_blob", _vp), ("cigar_off", _vp), ("cigar_blob", _vp),
+        ("sa_off", _vp), ("sa_blob", _vp), ("at_eof", _i),
+    ]
+
+
+def _arr(ptr, n, dtype):
+    if not ptr or n == 0:
+        return np.zeros(0, dtype=dtype)
+    ct = np.ctypeslib.as_ctypes_type(dtype)
+    return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ct)), shape=(int(n),))
+
+
+class Record:
+    """pysam.AlignedSegment look-alike built lazily from a :class:`HostBatch`."""
+
+    __slots__ = ("batch", "i")
+
+    def __init__(self, batch, i):
+        self.batch = batch
+        self.i = i
+
+    @property
+    def flag(self):
+        return int(self.batch.flag[self.i])
+
+    @property
+    def query_name(self):
+        b = self.batch
+        return bytes(b.qname_blob[int(b.qname_off[self.i]):int(b.qname_off[self.i + 1])]).decode()
+
+    @property
+    def reference_id(self):
+        return int(self.batch.ref_id[self.i])
+
+    @property
+    def reference_name(self):
+        r = self.reference_id
+        return self.batch.ref_names[r] if r >= 0 else None
+
+    @property
+    def reference_start(self):
+        return int(self.batch.pos[self.i])
+
+    @property
+    def cigartuples(self):
+        b = self.batch
+        c = b.cigar_blob[int(b.cigar_off[self.i]):int(b.cigar_off[self.i + 1])]
+        if c.shape[0] == 0:
+            return None
+        return [(int(x) & 15, int(x) >> 4) for x in c.tolist()]
+
+    @property
+    def reference_end(self):
+        cig = self.cigartuples
+        if self.is_unmapped or not cig:
+            return None
+        end = self.reference_start
+        for op, ln in cig:
+            if op in (0, 2, 3, 7, 8):
+                end += ln
+        return end
+
+    @property
+    def mapping_quality(self):
+        return int(self.batch.mapq[self.i])
+
+    @property
+    def query_length(self):
+        return int(self.batch.read_lens[self.i])
+
+    is_paired = property(lambda s: bool(s.flag & 0x1))
+    is_proper_pair = property(lambda s: bool(s.flag & 0x2))
+    is_unmapped = property(lambda s: bool(s.flag & 0x4))
+    mate_is_unmapped = property(lambda s: bool(s.flag & 0x8))
+    is_reverse = property(lambda s: bool(s.flag & 0x10))
+    is_secondary = property(lambda s: bool(s.flag & 0x100))
+    is_duplicate = property(lambda s: bool(s.flag & 0x400))
+    is_supplementary = property(lambda s: bool(s.flag & 0x800))
+
+    def has_tag(self, tag):
+        if tag != "SA":
+            raise KeyError("only the SA tag is decoded")
+        b = self.batch
+        return b.sa_off[self.i + 1] > b.sa_off[self.i]
+
+    def get_tag(self, tag):
+        if not self.has_tag(tag):
+            raise KeyError(tag)
+        b = self.batch
+        return bytes(b.sa_blob[int(b.sa_off[self.i]):int(b.sa_off[self.i + 1])]).decode()
+
+    def get_aligned_pairs(self, matches_only=True):
+        """(query_pos, ref_pos) for M/=/X columns (``core/bam_scanner.py:111``)."""
+        pairs = []
+        q = 0
+        r = self.reference_start
+        for op, ln in self.cigartuples or ():
+            if op in (0, 7, 8):
+                pairs.extend((q + j, r + j) for j in range(ln))
+                q += ln
+                r += ln
+            elif op in (1, 4):
+                q += ln
+            elif op in (2, 3):
+                r += ln
+        return pairs
+
+    @property
+    def query_sequence(self):
+        """Decode the read from the packed stream (N for invalid bases)."""
+        b = self.batch
+        n = int(b.read_lens[self.i])
+        if n == 0:
+            return None
+        p = int(b.read_starts[self.i]) + np.arange(n, dtype=np.uint64)
+        c = (b.codes[p >> np.uint64(5)] >> (np.uint64(62) - np.uint64(2) * (p & np.uint64(31)))) & np.uint64(3)
+        v = (b.valid[p >> np.uint64(5)] >> (np.uint32(31) - (p & np.uint64(31)).astype(np.uint32))) & np.uint32(1)
+        s = np.frombuffer(b"ACGT", dtype=np.uint8)[c.astype(np.int64)]
+        s = np.where(v.astype(bool), s, ord("N")).astype(np.uint8)
+        return s.tobytes().decode()
+
+
+class HostBatch(_engine.HostStream):
+    """A packed batch plus optional per-record metadata (numpy views into the
+    library-owned buffers; call :meth:`close` or let it be collected)."""
+
+    def __init__(self, lib, raw, ref_names, want_meta):
+        self._lib = lib
+        self._raw = raw
+        n = int(raw.n_reads)
+        nw = (int(raw.n_bases) + 31) // 32
+        super().__init__(_arr(raw.codes, nw, np.uint64), _arr(raw.valid, nw, np.uint32),
+                         raw.n_bases, _arr(raw.read_starts, n, np.uint64),
+                         _arr(raw.read_lens, n, np.uint32))
+        self.ref_names = ref_names
+        self.rec_index = _arr(raw.rec_index, n, np.uint64)
+        self.at_eof = bool(raw.at_eof)
+        self.has_meta = bool(want_meta)
+        if want_meta:
+            self.ref_id = _arr(raw.ref_id, n, np.int32)
+            self.pos = _arr(raw.pos, n, np.int32)
+            self.next_ref_id = _arr(raw.next_ref_id, n, np.int32)
+            self.next_pos = _arr(raw.next_pos, n, np.int32)
+            self.flag = _arr(raw.flag, n, np.uint16)
+            self.mapq = _arr(raw.mapq, n, np.uint8)
+            self.qname_off = _arr(raw.qname_off, n + 1, np.uint64)
+            self.qname_blob = _arr(raw.qname_blob, int(self.qname_off[-1]) if n else 0, np.uint8)
+            self.cigar_off = _arr(raw.cigar_off, n + 1, np.uint64)
+            self.cigar_blob = _arr(raw.cigar_blob, int(self.cigar_off[-1]) if n else 0, np.uint32)
+            self.sa_off = _arr(raw.sa_off, n + 1, np.uint64)
+            self.sa_blob = _arr(raw.sa_blob, int(self.sa_off[-1]) if n else 0, np.uint8)
+
+    def record(self, i):
+        if not self.has_meta:
+            raise _engine.KdfError("batch was decoded without metadata")
+        return Record(self, int(i))
+
+    def close(self):
+        if self._raw is not None:
+            self._lib.kdf_bam_batch_free(ctypes.byref(self._raw))
+            self._raw = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BamReader:
+    """Sequential BAM decoder.  ``for batch in BamReader(p).batches(MODE_FASTA)``."""
+
+    def __init__(self, path, threads=None):
+        self.lib = _engine.load_library()
+        if not os.path.isfile(path):
+            raise FileNotFoundError(path)
+        lower = path.lower()
+        if lower.endswith(".cram"):
+            raise _engine.KdfError(
+                "CRAM input is not supported by the built-in decoder (needs htslib codecs); "
+                "convert with `samtools view -b` first")
+        if threads is None:
+            threads = os.cpu_count() or 1
+        h = _vp()
+        rc = self.lib.kdf_bam_open(path.encode(), int(threads), ctypes.byref(h))
+        if rc != 0:
+            raise _engine.KdfError("cannot read BAM %s: %s" % (
+                path, self.lib.kdf_host_last_error().decode()))
+        self.handle = h
+        self.path = path
+        n = self.lib.kdf_bam_n_refs(h)
+        self.references = [self.lib.kdf_bam_ref_name(h, i).decode() for i in range(n)]
+        self.lengths = [int(self.lib.kdf_bam_ref_len(h, i)) for i in range(n)]
+
+    def next_batch(self, mode, max_bases=0, want_meta=False):
+        raw = _Batch()
+        rc = self.lib.kdf_bam_next_batch(self.handle, mode, int(max_bases), 1 if want_meta else 0,
+                                         ctypes.byref(raw))
+        if rc != 0:
+            raise _engine.KdfError("BAM decode failed for %s: %s" % (
+                self.path, self.lib.kdf_host_last_error().decode()))
+        return HostBatch(self.lib, raw, self.references, want_meta)
+
+    def batches(self, mode, max_bases=0, want_meta=False):
+        while True:
+            b = self.next_batch(mode, max_bases, want_meta)
+            if b.n_reads:
+                yield b
+            if b.at_eof:
+                break
+
+    def close(self):
+        if self.handle is not None:
+            self.lib.kdf_bam_close(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def read_fasta_sequences(path):
+    """Sequences of a (possibly gzip-compressed) FASTA as a list of bytes."""
+    import gzip
+    opener = gzip.open if path.endswith(".gz") else open
+    names, seqs, cur = [], [], []
+    with opener(path, "rb") as fh:
+        for line in fh:
+            if line.startswith(b">"):
+                if names:
+                    seqs.append(b"".join(cur))
+                names.append(line[1:].split()[0].decode() if len(line) > 1 else "")
+                cur = []
+            else:
+                cur.append(line.strip())
+    if names:
+        seqs.append(b"".join(cur))
+    return names, seqs

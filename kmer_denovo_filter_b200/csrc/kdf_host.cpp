@@ -1,3 +1,505 @@
-// kdf_host.cpp — host-side (CPU) parts of libkdf_sm100.so: BGZF/BAM decode into
-// packed pinned batches.  Filled in by the host-reader milestone.
+// kdf_host.cpp — host-side (CPU) half of libkdf_sm100.so: a multi-threaded
+// BGZF/BAM decoder that emits 2-bit packed read batches (the stream layout of
+// include/kdf.h) plus per-record alignment metadata.
+//
+// Replaces, for BAM input, the two record streams the reference obtains from
+// third-party tools:
+//   KDF_BAM_FASTA : `samtools fasta -F 0xD00 X.bam`
+//                   (core/jellyfish_wrappers.py:159-165,
+//                    discovery/pipeline.py:106-112, 369-375): drop records with
+//                   flag & 0xD00, then within a run of consecutive records with
+//                   the same QNAME keep the first record of each read-part
+//                   (READ1 / READ2 / other).
+//   KDF_BAM_SCAN  : pysam iteration of the anchoring scan
+//                   (core/bam_scanner.py:405-414): skip secondary and duplicate
+//                   records, keep supplementary and unmapped ones.
+//   KDF_BAM_ALL   : every record.
+// CRAM is not supported (needs htslib codecs); see DESIGN.md.
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <string>
+#include <vector>
+
 #include "../../include/kdf.h"
+
+namespace {
+
+thread_local std::string g_host_err;
+
+struct BlockRef {
+  uint64_t coff;   // offset of the block in the compressed file
+  uint32_t csize;  // total block size
+  uint32_t usize;  // uncompressed size (ISIZE)
+};
+
+struct Bam {
+  FILE* fh = nullptr;
+  int threads = 1;
+  std::vector<std::string> ref_names;
+  std::vector<int32_t> ref_lens;
+  std::string header_text;
+  std::vector<uint8_t> carry;  // undecoded tail of the previous chunk
+  bool eof = false;
+  uint64_t record_index = 0;  // file-order index of the next record
+  // collapse state of the FASTA stream (persists across batches)
+  std::string cur_qname;
+  unsigned seen_parts = 0;
+};
+
+bool inflate_block(const uint8_t* src, uint32_t csize, uint8_t* dst, uint32_t usize) {
+  // BGZF: 18-byte header (with BC subfield), deflate payload, crc32 + isize
+  if (csize < 26) return false;
+  uint16_t xlen = (uint16_t)(src[10] | (src[11] << 8));
+  uint32_t hdr = 12 + xlen;
+  z_stream zs;
+  memset(&zs, 0, sizeof(zs));
+  if (inflateInit2(&zs, -15) != Z_OK) return false;
+  zs.next_in = const_cast<uint8_t*>(src + hdr);
+  zs.avail_in = csize - hdr - 8;
+  zs.next_out = dst;
+  zs.avail_out = usize;
+  int rc = inflate(&zs, Z_FINISH);
+  inflateEnd(&zs);
+  return rc == Z_STREAM_END && zs.total_out == usize;
+}
+
+// Read up to `want_bytes` of uncompressed data worth of BGZF blocks and inflate
+// them in parallel, appending to `out`.
+bool read_chunk(Bam* b, uint64_t want_bytes, std::vector<uint8_t>& out) {
+  std::vector<uint8_t> comp;
+  std::vector<BlockRef> blocks;
+  uint64_t total_u = 0;
+  while (total_u < want_bytes) {
+    uint8_t hdr[18];
+    size_t got = fread(hdr, 1, 18, b->fh);
+    if (got == 0) {
+      b->eof = true;
+      break;
+    }
+    if (got != 18 || hdr[0] != 31 || hdr[1] != 139 || hdr[2] != 8 || !(hdr[3] & 4)) {
+      g_host_err = "not a BGZF block (is this a BAM file?)";
+      return false;
+    }
+    uint16_t xlen = (uint16_t)(hdr[10] | (hdr[11] << 8));
+    // locate the BC subfield (normally the only one)
+    std::vector<uint8_t> extra(xlen);
+    memcpy(extra.data(), hdr + 12, xlen < 6 ? xlen : 6);
+    if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, b->fh) != (size_t)(xlen - 6)) {
+      g_host_err = "truncated BGZF header";
+      return false;
+    }
+    int bsize = -1;
+    for (uint32_t p = 0; p + 4 <= xlen;) {
+      uint16_t slen = (uint16_t)(extra[p + 2] | (extra[p + 3] << 8));
+      if (extra[p] == 'B' && extra[p + 1] == 'C' && slen == 2 && p + 6 <= xlen)
+        bsize = (extra[p + 4] | (extra[p + 5] << 8)) + 1;
+      p += 4 + slen;
+    }
+    if (bsize < 0) {
+      g_host_err = "BGZF block without BC subfield";
+      return false;
+    }
+    uint32_t rest = (uint32_t)bsize - 12 - xlen;
+    size_t at = comp.size();
+    comp.resize(at + (size_t)bsize);
+    memcpy(comp.data() + at, hdr, 12);
+    memcpy(comp.data() + at + 12, extra.data(), xlen);
+    if (fread(comp.data() + at + 12 + xlen, 1, rest, b->fh) != rest) {
+      g_host_err = "truncated BGZF block";
+      return false;
+    }
+    const uint8_t* tail = comp.data() + at + bsize - 4;
+    uint32_t isize = tail[0] | (tail[1] << 8) | (tail[2] << 16) | ((uint32_t)tail[3] << 24);
+    blocks.push_back({(uint64_t)at, (uint32_t)bsize, isize});
+    total_u += isize;
+  }
+  size_t base = out.size();
+  out.resize(base + total_u);
+  std::vector<uint64_t> uoff(blocks.size() + 1, 0);
+  for (size_t i = 0; i < blocks.size(); ++i) uoff[i + 1] = uoff[i] + blocks[i].usize;
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic, 8) num_threads(b->threads) reduction(| : bad)
+  for (long i = 0; i < (long)blocks.size(); ++i) {
+    if (blocks[i].usize == 0) continue;
+    if (!inflate_block(comp.data() + blocks[i].coff, blocks[i].csize, out.data() + base + uoff[i],
+                       blocks[i].usize))
+      bad |= 1;
+  }
+  if (bad) {
+    g_host_err = "BGZF inflate failed";
+    return false;
+  }
+  return true;
+}
+
+inline int32_t rd_i32(const uint8_t* p) {
+  int32_t v;
+  memcpy(&v, p, 4);
+  return v;
+}
+inline uint16_t rd_u16(const uint8_t* p) {
+  uint16_t v;
+  memcpy(&v, p, 2);
+  return v;
+}
+
+bool parse_header(Bam* b) {
+  // the header may span several blocks: keep reading until complete
+  std::vector<uint8_t>& buf = b->carry;
+  auto need = [&](size_t n) -> bool {
+    while (buf.size() < n && !b->eof) {
+      if (!read_chunk(b, 1 << 20, buf)) return false;
+    }
+    return buf.size() >= n;
+  };
+  if (!need(12) || memcmp(buf.data(), "BAM\1", 4) != 0) {
+    if (g_host_err.empty()) g_host_err = "missing BAM magic";
+    return false;
+  }
+  int32_t l_text = rd_i32(buf.data() + 4);
+  if (!need(12 + (size_t)l_text)) return false;
+  b->header_text.assign((const char*)buf.data() + 8, (size_t)l_text);
+  size_t off = 8 + (size_t)l_text;
+  int32_t n_ref = rd_i32(buf.data() + off);
+  off += 4;
+  for (int32_t i = 0; i < n_ref; ++i) {
+    if (!need(off + 4)) return false;
+    int32_t l_name = rd_i32(buf.data() + off);
+    off += 4;
+    if (!need(off + (size_t)l_name + 4)) return false;
+    b->ref_names.emplace_back((const char*)buf.data() + off, (size_t)(l_name > 0 ? l_name - 1 : 0));
+    off += (size_t)l_name;
+    b->ref_lens.push_back(rd_i32(buf.data() + off));
+    off += 4;
+  }
+  buf.erase(buf.begin(), buf.begin() + (long)off);
+  return true;
+}
+
+// nibble -> 2-bit code / validity; index = BAM 4-bit base (=ACMGRSVTWYHKDBN)
+const uint8_t NIB_CODE[16] = {0, 0, 1, 0, 2, 0, 0, 0, 3, 0, 0, 0, 0, 0, 0, 0};
+const uint8_t NIB_OK[16] = {0, 1, 1, 0, 1, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0};
+
+inline void or_word64(uint64_t* w, uint64_t v, bool shared) {
+  if (!v) return;
+  if (shared)
+    __atomic_fetch_or(w, v, __ATOMIC_RELAXED);
+  else
+    *w |= v;
+}
+inline void or_word32(uint32_t* w, uint32_t v, bool shared) {
+  if (!v) return;
+  if (shared)
+    __atomic_fetch_or(w, v, __ATOMIC_RELAXED);
+  else
+    *w |= v;
+}
+
+// pack l_seq bases (BAM nibbles) at stream position `start`
+void pack_record(const uint8_t* nib, uint32_t l_seq, uint64_t start, uint64_t* codes,
+                 uint32_t* valid) {
+  if (!l_seq) return;
+  uint64_t first_w = start >> 5, last_w = (start + l_seq - 1) >> 5;
+  uint64_t cw = 0;
+  uint32_t vw = 0;
+  uint64_t w = first_w;
+  for (uint32_t i = 0; i < l_seq; ++i) {
+    uint8_t byte = nib[i >> 1];
+    uint8_t n = (i & 1) ? (byte & 15) : (byte >> 4);
+    uint64_t p = start + i;
+    uint64_t pw = p >> 5;
+    if (pw != w) {
+      bool shared = (w == first_w) || (w == last_w);
+      or_word64(codes + w, cw, shared);
+      or_word32(valid + w, vw, shared);
+      cw = 0;
+      vw = 0;
+      w = pw;
+    }
+    unsigned sh = (unsigned)(p & 31);
+    cw |= (uint64_t)NIB_CODE[n] << (62 - 2 * sh);
+    vw |= (uint32_t)NIB_OK[n] << (31 - sh);
+  }
+  or_word64(codes + w, cw, true);
+  or_word32(valid + w, vw, true);
+}
+
+}  // namespace
+
+struct kdf_bam_batch_impl {
+  std::vector<uint64_t> codes;
+  std::vector<uint32_t> valid;
+  std::vector<uint64_t> read_starts;
+  std::vector<uint32_t> read_lens;
+  std::vector<uint64_t> rec_index;
+  std::vector<int32_t> ref_id, pos, next_ref_id, next_pos;
+  std::vector<uint16_t> flag;
+  std::vector<uint8_t> mapq;
+  std::vector<uint64_t> qname_off, cigar_off, sa_off;  // n+1 each
+  std::vector<char> qname_blob, sa_blob;
+  std::vector<uint32_t> cigar_blob;
+  uint64_t n_bases = 0;
+};
+
+extern "C" {
+
+int kdf_bam_open(const char* path, int n_threads, kdf_bam** out) {
+  if (!path || !out) {
+    g_host_err = "kdf_bam_open: NULL argument";
+    return KDF_ERR_ARG;
+  }
+  FILE* fh = fopen(path, "rb");
+  if (!fh) {
+    g_host_err = std::string("cannot open ") + path;
+    return KDF_ERR_ARG;
+  }
+  Bam* b = new Bam;
+  b->fh = fh;
+  b->threads = n_threads > 0 ? n_threads : 1;
+  g_host_err.clear();
+  if (!parse_header(b)) {
+    fclose(fh);
+    delete b;
+    return KDF_ERR_ARG;
+  }
+  *out = reinterpret_cast<kdf_bam*>(b);
+  return KDF_OK;
+}
+
+void kdf_bam_close(kdf_bam* h) {
+  Bam* b = reinterpret_cast<Bam*>(h);
+  if (!b) return;
+  if (b->fh) fclose(b->fh);
+  delete b;
+}
+
+const char* kdf_host_last_error(void) { return g_host_err.c_str(); }
+
+int kdf_bam_n_refs(const kdf_bam* h) { return (int)reinterpret_cast<const Bam*>(h)->ref_names.size(); }
+const char* kdf_bam_ref_name(const kdf_bam* h, int i) {
+  const Bam* b = reinterpret_cast<const Bam*>(h);
+  return (i >= 0 && i < (int)b->ref_names.size()) ? b->ref_names[i].c_str() : "";
+}
+int64_t kdf_bam_ref_len(const kdf_bam* h, int i) {
+  const Bam* b = reinterpret_cast<const Bam*>(h);
+  return (i >= 0 && i < (int)b->ref_lens.size()) ? b->ref_lens[i] : -1;
+}
+
+int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
+                       kdf_bam_batch* out) {
+  Bam* b = reinterpret_cast<Bam*>(h);
+  if (!b || !out) {
+    g_host_err = "kdf_bam_next_batch: NULL argument";
+    return KDF_ERR_ARG;
+  }
+  if (mode < KDF_BAM_FASTA || mode > KDF_BAM_ALL) {
+    g_host_err = "kdf_bam_next_batch: bad mode";
+    return KDF_ERR_ARG;
+  }
+  kdf_bam_batch_impl* im = new kdf_bam_batch_impl;
+  struct Kept {
+    size_t off;  // offset of the record body in buf
+    uint64_t start;
+    uint32_t l_seq;
+  };
+  std::vector<Kept> kept;
+  uint64_t n_bases = 0;
+  std::vector<uint8_t> buf;
+  buf.swap(b->carry);
+  size_t off = 0;
+  bool done = false;
+  while (!done) {
+    // parse all complete records currently in buf
+    while (true) {
+      if (buf.size() - off < 4) break;
+      int32_t bs = rd_i32(buf.data() + off);
+      if (bs < 32) {
+        g_host_err = "corrupt BAM record";
+        delete im;
+        return KDF_ERR_ARG;
+      }
+      if (buf.size() - off - 4 < (size_t)bs) break;
+      const uint8_t* r = buf.data() + off + 4;
+      uint16_t flag = rd_u16(r + 14);
+      uint8_t l_name = r[8];
+      uint32_t l_seq = (uint32_t)rd_i32(r + 16);
+      bool keep = true;
+      if (mode == KDF_BAM_FASTA) {
+        if (flag & 0xD00) {
+          keep = false;
+        } else {
+          const char* qn = (const char*)r + 32;
+          size_t ql = l_name ? (size_t)l_name - 1 : 0;
+          if (b->cur_qname.size() != ql || memcmp(b->cur_qname.data(), qn, ql) != 0) {
+            b->cur_qname.assign(qn, ql);
+            b->seen_parts = 0;
+          }
+          bool r1 = flag & 0x40, r2 = flag & 0x80;
+          unsigned part = (r1 && !r2) ? 1u : ((r2 && !r1) ? 2u : 0u);
+          if (b->seen_parts & (1u << part))
+            keep = false;
+          else
+            b->seen_parts |= 1u << part;
+        }
+      } else if (mode == KDF_BAM_SCAN) {
+        if (flag & 0x500) keep = false;
+      }
+      if (keep) {
+        if (max_bases && !kept.empty() && n_bases + l_seq + 1 > max_bases) {
+          done = true;
+          break;  // leave this record for the next batch
+        }
+        uint64_t start = kept.empty() ? 0 : n_bases + 1;
+        kept.push_back({off + 4, start, l_seq});
+        n_bases = start + l_seq;
+        im->rec_index.push_back(b->record_index);
+      }
+      b->record_index++;
+      off += 4 + (size_t)bs;
+    }
+    if (done) break;
+    if (b->eof) break;
+    // need more data: drop nothing (kept offsets point into buf), just append
+    if (!read_chunk(b, 64ull << 20, buf)) {
+      delete im;
+      return KDF_ERR_ARG;
+    }
+  }
+  // NOTE: when a batch limit stops us mid-buffer the collapse state already
+  // reflects only the records consumed so far (the break precedes any update
+  // for the postponed record? no — state was updated; undo by re-evaluating):
+  // to stay exact we re-derive the state on the next call from the carry, so
+  // roll the state back when the postponed record was a fresh keep.
+  if (done && mode == KDF_BAM_FASTA) {
+    // the postponed record set its part bit; clear it so it is kept next time
+    const uint8_t* r = buf.data() + off + 4;
+    uint16_t flag = rd_u16(r + 14);
+    bool r1 = flag & 0x40, r2 = flag & 0x80;
+    unsigned part = (r1 && !r2) ? 1u : ((r2 && !r1) ? 2u : 0u);
+    b->seen_parts &= ~(1u << part);
+  }
+  size_t n = kept.size();
+  uint64_t n_words = (n_bases + 31) / 32;
+  im->n_bases = n_bases;
+  im->codes.assign(n_words ? n_words : 1, 0);
+  im->valid.assign(n_words ? n_words : 1, 0);
+  im->read_starts.resize(n);
+  im->read_lens.resize(n);
+#pragma omp parallel for schedule(static) num_threads(b->threads)
+  for (long i = 0; i < (long)n; ++i) {
+    const uint8_t* r = buf.data() + kept[i].off;
+    uint8_t l_name = r[8];
+    uint16_t n_cig = rd_u16(r + 12);
+    const uint8_t* nib = r + 32 + l_name + 4 * (size_t)n_cig;
+    pack_record(nib, kept[i].l_seq, kept[i].start, im->codes.data(), im->valid.data());
+    im->read_starts[i] = kept[i].start;
+    im->read_lens[i] = kept[i].l_seq;
+  }
+  if (want_meta) {
+    im->ref_id.resize(n);
+    im->pos.resize(n);
+    im->next_ref_id.resize(n);
+    im->next_pos.resize(n);
+    im->flag.resize(n);
+    im->mapq.resize(n);
+    im->qname_off.assign(n + 1, 0);
+    im->cigar_off.assign(n + 1, 0);
+    im->sa_off.assign(n + 1, 0);
+    for (size_t i = 0; i < n; ++i) {
+      const uint8_t* r = buf.data() + kept[i].off;
+      int32_t bs = rd_i32(r - 4);
+      uint8_t l_name = r[8];
+      uint16_t n_cig = rd_u16(r + 12);
+      uint32_t l_seq = kept[i].l_seq;
+      im->ref_id[i] = rd_i32(r);
+      im->pos[i] = rd_i32(r + 4);
+      im->mapq[i] = r[9];
+      im->flag[i] = rd_u16(r + 14);
+      im->next_ref_id[i] = rd_i32(r + 20);
+      im->next_pos[i] = rd_i32(r + 24);
+      size_t ql = l_name ? (size_t)l_name - 1 : 0;
+      im->qname_blob.insert(im->qname_blob.end(), (const char*)r + 32, (const char*)r + 32 + ql);
+      im->qname_off[i + 1] = im->qname_blob.size();
+      const uint8_t* cg = r + 32 + l_name;
+      for (uint16_t c = 0; c < n_cig; ++c) {
+        uint32_t v;
+        memcpy(&v, cg + 4 * c, 4);
+        im->cigar_blob.push_back(v);
+      }
+      im->cigar_off[i + 1] = im->cigar_blob.size();
+      // walk aux tags for SA:Z
+      const uint8_t* t = cg + 4 * (size_t)n_cig + (l_seq + 1) / 2 + l_seq;
+      const uint8_t* end = r + bs;
+      while (t + 3 <= end) {
+        char t0 = (char)t[0], t1 = (char)t[1], ty = (char)t[2];
+        t += 3;
+        size_t adv = 0;
+        switch (ty) {
+          case 'A': case 'c': case 'C': adv = 1; break;
+          case 's': case 'S': adv = 2; break;
+          case 'i': case 'I': case 'f': adv = 4; break;
+          case 'Z': case 'H': {
+            const uint8_t* z = (const uint8_t*)memchr(t, 0, (size_t)(end - t));
+            if (!z) { t = end; adv = 0; break; }
+            if (t0 == 'S' && t1 == 'A' && ty == 'Z')
+              im->sa_blob.insert(im->sa_blob.end(), (const char*)t, (const char*)z);
+            adv = (size_t)(z - t) + 1;
+            break;
+          }
+          case 'B': {
+            if (t + 5 > end) { t = end; break; }
+            char sub = (char)t[0];
+            uint32_t cnt;
+            memcpy(&cnt, t + 1, 4);
+            size_t sz = (sub == 'c' || sub == 'C') ? 1 : ((sub == 's' || sub == 'S') ? 2 : 4);
+            adv = 5 + sz * cnt;
+            break;
+          }
+          default: t = end; break;
+        }
+        if (t >= end) break;
+        t += adv;
+      }
+      im->sa_off[i + 1] = im->sa_blob.size();
+    }
+  }
+  // keep undecoded tail for the next call
+  b->carry.assign(buf.begin() + (long)off, buf.end());
+  memset(out, 0, sizeof(*out));
+  out->impl = im;
+  out->n_reads = n;
+  out->n_bases = n_bases;
+  out->codes = im->codes.data();
+  out->valid = im->valid.data();
+  out->read_starts = im->read_starts.data();
+  out->read_lens = im->read_lens.data();
+  out->rec_index = im->rec_index.data();
+  if (want_meta) {
+    out->ref_id = im->ref_id.data();
+    out->pos = im->pos.data();
+    out->next_ref_id = im->next_ref_id.data();
+    out->next_pos = im->next_pos.data();
+    out->flag = im->flag.data();
+    out->mapq = im->mapq.data();
+    out->qname_off = im->qname_off.data();
+    out->qname_blob = im->qname_blob.data();
+    out->cigar_off = im->cigar_off.data();
+    out->cigar_blob = im->cigar_blob.data();
+    out->sa_off = im->sa_off.data();
+    out->sa_blob = im->sa_blob.data();
+  }
+  out->at_eof = (b->eof && b->carry.empty()) ? 1 : 0;
+  return KDF_OK;
+}
+
+void kdf_bam_batch_free(kdf_bam_batch* batch) {
+  if (!batch || !batch->impl) return;
+  delete reinterpret_cast<kdf_bam_batch_impl*>(batch->impl);
+  memset(batch, 0, sizeof(*batch));
+}
+
+}  // extern "C"

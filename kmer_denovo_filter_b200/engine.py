@@ -70,6 +70,15 @@ _SIGNATURES = {
     "kdf_pack_sequences": (_u64, [_vp, _vp, _u64, _vp, _vp, _vp]),
     "kdf_debug_extract_host": (_i, [_vp, _vp, _u64, _i, _i, _vp, _vp, _vp]),
     "kdf_bench_random_access": (_i, [_vp, _u64, _u64, _i, _vp, _vp]),
+    # host BGZF/BAM decoder (bound in bamio.py)
+    "kdf_bam_open": (_i, [ctypes.c_char_p, _i, ctypes.POINTER(_vp)]),
+    "kdf_bam_close": (None, [_vp]),
+    "kdf_bam_n_refs": (_i, [_vp]),
+    "kdf_bam_ref_name": (ctypes.c_char_p, [_vp, _i]),
+    "kdf_bam_ref_len": (ctypes.c_int64, [_vp, _i]),
+    "kdf_bam_next_batch": (_i, [_vp, _i, _u64, _i, _vp]),
+    "kdf_bam_batch_free": (None, [_vp]),
+    "kdf_host_last_error": (ctypes.c_char_p, []),
 }
 
 _lib = None

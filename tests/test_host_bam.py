@@ -1,0 +1,112 @@
+"""The library's C++ BGZF/BAM decoder against the oracle's stdlib reader on the
+GIAB fixtures: record streams (samtools-fasta semantics, scan semantics),
+packed bases, metadata, batching."""
+import numpy as np
+import pytest
+
+from kmer_denovo_filter_b200 import bamio, engine
+from oracle import bam as obam
+
+
+def _decode(batch, i):
+    return batch.record(i).query_sequence if batch.has_meta else bamio.Record(batch, i).query_sequence
+
+
+@pytest.mark.parametrize("who", ["child", "mother", "father"])
+def test_fasta_stream_matches_oracle(giab_paths, giab_records, who):
+    want = obam.fasta_stream(giab_records[who])
+    with bamio.BamReader(giab_paths[who], threads=4) as rd:
+        batches = list(rd.batches(bamio.MODE_FASTA, want_meta=True))
+    assert len(batches) == 1
+    b = batches[0]
+    assert b.n_reads == len(want)
+    assert [b.record(i).query_name for i in range(0, b.n_reads, 97)] == \
+        [r.qname for r in want[::97]]
+    hs = engine.pack_sequences([r.seq for r in want])
+    assert b.n_bases == hs.n_bases
+    assert np.array_equal(b.codes, hs.codes) and np.array_equal(b.valid, hs.valid)
+    assert np.array_equal(b.read_starts, hs.read_starts)
+    assert np.array_equal(b.read_lens, hs.read_lens)
+
+
+def test_scan_stream_and_metadata(giab_paths, giab_records):
+    recs = giab_records["child"]
+    want = [(i, r) for i, r in enumerate(recs) if not (r.flag & 0x500)]
+    with bamio.BamReader(giab_paths["child"], threads=2) as rd:
+        assert rd.references == giab_records["child_refs"][0]
+        assert rd.lengths == giab_records["child_refs"][1]
+        b = rd.next_batch(bamio.MODE_SCAN, want_meta=True)
+    assert b.at_eof and b.n_reads == len(want)
+    assert b.rec_index.tolist() == [i for i, _r in want]
+    for j in list(range(0, len(want), 53)) + [len(want) - 1]:
+        o = want[j][1]
+        m = b.record(j)
+        assert m.query_name == o.qname and m.flag == o.flag
+        assert m.reference_name == o.reference_name
+        assert m.reference_start == o.pos and m.reference_end == o.reference_end
+        assert m.mapping_quality == o.mapq
+        assert (m.cigartuples or []) == (o.cigar or [])
+        assert m.has_tag("SA") == o.has_tag("SA")
+        if o.has_tag("SA"):
+            assert m.get_tag("SA") == o.get_tag("SA")
+        seq = o.seq.upper()
+        assert m.query_sequence == "".join(c if c in "ACGT" else "N" for c in seq)
+        assert m.get_aligned_pairs() == o.get_aligned_pairs(matches_only=True)
+    n_sa = sum(1 for _i, r in want if r.has_tag("SA"))
+    assert int((b.sa_off[1:] > b.sa_off[:-1]).sum()) == n_sa
+
+
+@pytest.mark.parametrize("mode", [bamio.MODE_FASTA, bamio.MODE_SCAN, bamio.MODE_ALL])
+def test_batching_is_equivalent_to_one_shot(giab_paths, mode):
+    with bamio.BamReader(giab_paths["mother"], threads=3) as rd:
+        whole = rd.next_batch(mode, want_meta=True)
+    names, lens, idx = [], [], []
+    with bamio.BamReader(giab_paths["mother"], threads=3) as rd:
+        nb = 0
+        for b in rd.batches(mode, max_bases=200_000, want_meta=True):
+            nb += 1
+            assert b.n_bases <= 200_000
+            lens += b.read_lens.tolist()
+            idx += b.rec_index.tolist()
+            names += [b.record(i).query_name for i in (0, b.n_reads - 1)]
+    assert nb > 5
+    assert lens == whole.read_lens.tolist()
+    assert idx == whole.rec_index.tolist()
+
+
+def test_synthetic_bam_roundtrip(tmp_path):
+    """Writer (oracle) → C++ reader: flags, collapse, odd lengths, IUPAC, empty seq."""
+    recs = [
+        obam.encode_record(0, 10, "q1", 0x41, 60, [(0, 7)], "ACGTNAC"),
+        obam.encode_record(0, 10, "q1", 0x41, 60, [(0, 7)], "TTTTTTT"),      # collapsed (same part)
+        obam.encode_record(0, 12, "q1", 0x81, 60, [(0, 5)], "GGRCC"),        # other part: kept
+        obam.encode_record(0, 20, "q2", 0x100, 0, [(0, 4)], "AAAA"),         # secondary
+        obam.encode_record(0, 21, "q3", 0x400, 0, [(0, 4)], "CCCC"),         # duplicate
+        obam.encode_record(0, 22, "q4", 0x800, 9, [(4, 2), (0, 2)], "GGTT",
+                           tags=b"SAZchr1,5,+,4M,60,0;\0"),                  # supplementary
+        obam.encode_record(-1, -1, "q5", 0x4, 0, [], "ACGTACGTA"),           # unmapped
+        obam.encode_record(0, 30, "q6", 0, 60, [], ""),                      # no sequence
+    ]
+    p = str(tmp_path / "t.bam")
+    obam.write_bam(p, ["chr1"], [1000], recs)
+    with bamio.BamReader(p) as rd:
+        f = rd.next_batch(bamio.MODE_FASTA, want_meta=True)
+    assert [f.record(i).query_name for i in range(f.n_reads)] == ["q1", "q1", "q5", "q6"]
+    assert [f.record(i).query_sequence for i in range(f.n_reads)] == ["ACGTNAC", "GGNCC", "ACGTACGTA", None]
+    with bamio.BamReader(p) as rd:
+        s = rd.next_batch(bamio.MODE_SCAN, want_meta=True)
+    assert [s.record(i).query_name for i in range(s.n_reads)] == ["q1", "q1", "q1", "q4", "q5", "q6"]
+    assert s.record(3).get_tag("SA") == "chr1,5,+,4M,60,0;"
+    assert s.record(3).is_supplementary and s.record(4).is_unmapped
+    assert s.record(3).get_aligned_pairs() == [(2, 22), (3, 23)]
+
+
+def test_not_a_bam(tmp_path):
+    p = tmp_path / "x.bam"
+    p.write_bytes(b"hello world, definitely not bgzf")
+    with pytest.raises(engine.KdfError):
+        bamio.BamReader(str(p))
+    with pytest.raises(engine.KdfError):
+        c = tmp_path / "x.cram"
+        c.write_bytes(b"CRAM")
+        bamio.BamReader(str(c))
