@@ -141,6 +141,16 @@ int kdf_update_keys(kdf_table* t, const uint64_t* lo /*DEV*/,
                     const uint64_t* hi /*DEV or NULL*/, uint64_t n, int mode,
                     int plane, uint32_t arg, uint64_t* stats /*DEV*/, void* stream);
 
+/* Per-key accumulation: plane0[key_i] += add0[i], plane1[key_i] += add1[i] for
+ * keys already in the table (add0/add1 may be NULL); keys not found are counted
+ * in *n_missing (DEV u64, may be NULL).  Used to grow a table (re-hash) and to
+ * merge per-rank counts; Jellyfish's analogue is `jellyfish merge`
+ * (core/jellyfish_wrappers.py:335-366).                                      */
+int kdf_add_planes(kdf_table* t, const uint64_t* lo /*DEV*/,
+                   const uint64_t* hi /*DEV or NULL*/, uint64_t n,
+                   const uint32_t* add0 /*DEV*/, const uint32_t* add1 /*DEV*/,
+                   uint64_t* n_missing /*DEV*/, void* stream);
+
 /* ---- K3: threshold + stream compaction ---------------------------------
  * Emits every occupied slot whose planes satisfy
  *   min0 <= plane0 <= max0  and  min1 <= plane1 <= max1.

@@ -1,0 +1,226 @@
+"""GPU-engine wrappers — same names and contracts as the reference's
+``core/jellyfish_wrappers.py``, with the Jellyfish / samtools subprocesses
+replaced by calls into ``libkdf_sm100.so``.
+
+Where the reference passes k-mer sets between stages as FASTA paths and
+``.jf`` index paths, these wrappers pass in-memory handles
+(:class:`~kmer_denovo_filter_b200.kmer_utils.KmerSet`, :class:`RefIndex`,
+``KmerTable``); every wrapper also accepts the reference's path arguments
+(FASTA of k-mers, Jellyfish ``binary/sorted`` file) and converts them.
+"""
+
+import json
+import logging
+import os
+
+import numpy as np
+
+from .. import bamio
+from .. import engine as _engine
+from ..kmer_utils import KmerSet, kmer_of
+
+logger = logging.getLogger(__name__)
+
+# bases per host→device batch while streaming a BAM (≈ 0.4 GB of packed input)
+BATCH_BASES = 1 << 30
+
+_default_engine = None
+
+
+def get_engine(engine=None):
+    """The process-wide :class:`CudaEngine` (one per GPU / process)."""
+    global _default_engine
+    if engine is not None:
+        return engine
+    if _default_engine is None:
+        _default_engine = _engine.CudaEngine()
+    return _default_engine
+
+
+def set_engine(engine):
+    global _default_engine
+    _default_engine = engine
+
+
+# ---------------------------------------------------------------------------
+# sizing (reference: _estimate_jf_hash_size :73-107, max(2n, 10M) :155)
+# ---------------------------------------------------------------------------
+
+def _parse_hash_size(text):
+    """'2G' / '500M' / '1000' → entries (Jellyfish ``-s`` syntax)."""
+    if text is None:
+        return None
+    t = str(text).strip().upper()
+    mult = 1
+    if t and t[-1] in "KMG":
+        mult = {"K": 1000, "M": 1000_000, "G": 1000_000_000}[t[-1]]
+        t = t[:-1]
+    return int(float(t) * mult)
+
+
+def _estimate_table_keys(bam_path, hbm_free_bytes, slot_bytes):
+    """Initial distinct-k-mer estimate for a BAM: ~4 bases per compressed byte,
+    one distinct k-mer per 4 bases, floor 1M; capped so the table uses at most
+    60 % of free HBM.  The count loop grows the table when this is too small."""
+    try:
+        size = os.path.getsize(bam_path)
+    except OSError:
+        size = 1 << 28
+    est = max(size, 1_000_000)
+    cap = int(hbm_free_bytes * 0.6 / slot_bytes / 2)
+    return max(min(est, cap), 1024)
+
+
+def _rehash(eng, table, new_capacity):
+    """Grow a table (Jellyfish's analogue: spill to ``.jf_N`` + ``merge``,
+    reference ``:59-70, 335-366``; here nothing is ever spilled or dropped)."""
+    n, lo, hi, p0, p1 = eng.threshold_compact(table, want_planes=True)
+    big = eng.new_table(table.k, capacity=new_capacity)
+    st = eng.new_stats()
+    eng.update_keys(big, lo, hi, _engine.MODE_INSERT_ONLY, 0, 0, st)
+    eng.add_planes(big, lo, hi, p0, p1)
+    eng.check_not_full(st)
+    table.close()
+    return big
+
+
+def count_bam_into_table(eng, bam_path, table, mode, plane, threads, grow=False,
+                         batch_bases=BATCH_BASES):
+    """Stream ``samtools fasta -F 0xD00``-equivalent reads of a BAM through
+    K1+K2.  Returns ``(table, stats dict)``; with ``grow`` the table is
+    re-hashed into a larger one before any batch could overfill it."""
+    total = {"windows": 0, "hits": 0, "new": 0, "reads": 0, "bases": 0}
+    with bamio.BamReader(bam_path, threads=threads) as rd:
+        for batch in rd.batches(bamio.MODE_FASTA, max_bases=batch_bases):
+            if grow:
+                worst = total["new"] + batch.window_count_upper_bound(table.k)
+                if worst > 0.85 * table.capacity:
+                    new_cap = eng.capacity_for(worst)
+                    logger.info("  growing k-mer table %d -> %d slots", table.capacity, new_cap)
+                    table = _rehash(eng, table, new_cap)
+            ds = eng.upload(batch, with_reads=False)
+            st = eng.new_stats()
+            eng.count_stream(table, ds, mode, plane, 1, st)
+            s = eng.read_stats(st)
+            if s["full"]:
+                raise _engine.KdfError(
+                    "k-mer table full while counting %s (capacity %d slots); "
+                    "pass a larger --jf-hash-size" % (bam_path, table.capacity))
+            for key in ("windows", "hits", "new"):
+                total[key] += s[key]
+            total["reads"] += batch.n_reads
+            total["bases"] += batch.n_bases
+            batch.close()
+    return table, total
+
+
+# ---------------------------------------------------------------------------
+# reference index (reference: _ensure_ref_jf :286-332)
+# ---------------------------------------------------------------------------
+
+class RefIndex:
+    """The reference k-mer set, held as what it is cheapest to stream against
+    the child table: either the packed reference sequence (built from the
+    FASTA) or an explicit key list (parsed from a Jellyfish ``.jf`` file)."""
+
+    def __init__(self, k, host_stream=None, keys=None, source=None):
+        self.k = k
+        self.host_stream = host_stream
+        self.keys = keys          # (lo u64, hi u64) numpy or None
+        self.source = source
+
+    def mark_present(self, eng, table, plane, stats=None):
+        """OR 1 into ``plane`` of every table key that occurs in the reference."""
+        if self.host_stream is not None:
+            ds = eng.upload(self.host_stream, with_reads=False)
+            eng.count_stream(table, ds, _engine.MODE_MARK_IF_PRESENT, plane, 1, stats)
+        else:
+            lo, hi = eng.keys_to_device(self.keys, table.key_words)
+            eng.update_keys(table, lo, hi, _engine.MODE_MARK_IF_PRESENT, plane, 1, stats)
+
+
+def read_jf_binary_sorted(path):
+    """Parse a Jellyfish ``binary/sorted`` index → ``(k, lo u64, hi u64, counts)``.
+
+    Format (as found in the reference fixture ``mini_ref.fa.k31.jf``): 9 ASCII
+    digits = header length, JSON header with ``key_len`` (bits) and
+    ``counter_len`` (bytes), then fixed-width little-endian records."""
+    with open(path, "rb") as fh:
+        data = fh.read()
+    hlen = int(data[:9].decode())
+    hdr = json.loads(data[9:9 + hlen].decode().rstrip("\0"))
+    fmt = hdr.get("format", "binary/sorted")
+    if fmt != "binary/sorted":
+        raise _engine.KdfError("unsupported Jellyfish format %r in %s" % (fmt, path))
+    kbits = int(hdr["key_len"])
+    cbytes = int(hdr["counter_len"])
+    kbytes = (kbits + 7) // 8
+    rec = kbytes + cbytes
+    body = np.frombuffer(data, dtype=np.uint8, offset=9 + hlen)
+    n = body.shape[0] // rec
+    body = body[:n * rec].reshape(n, rec)
+    keyb = np.zeros((n, 16), dtype=np.uint8)
+    keyb[:, :kbytes] = body[:, :kbytes]
+    words = keyb.view("<u8")
+    cb = np.zeros((n, 8), dtype=np.uint8)
+    cb[:, :cbytes] = body[:, kbytes:]
+    return kbits // 2, words[:, 0].copy(), words[:, 1].copy(), cb.view("<u8")[:, 0].copy()
+
+
+def _ensure_ref_jf(ref_fasta, kmer_size, threads, ref_jf=None, engine=None):
+    """Reference k-mer index.  An existing ``ref_jf`` / ``{ref_fasta}.k{k}.jf``
+    Jellyfish file is reused (parsed); otherwise the FASTA is packed.  Nothing is
+    written next to the FASTA (the reference caches a ``.jf`` there)."""
+    if ref_jf is None and ref_fasta:
+        cand = "%s.k%d.jf" % (ref_fasta, kmer_size)
+        if os.path.isfile(cand):
+            ref_jf = cand
+    if ref_jf and os.path.isfile(ref_jf) and not ref_fasta:
+        k, lo, hi, _c = read_jf_binary_sorted(ref_jf)
+        if k != kmer_size:
+            raise _engine.KdfError("reference index %s has k=%d, expected %d" % (ref_jf, k, kmer_size))
+        logger.info("Reference Jellyfish index found: %s (%d k-mers)", ref_jf, lo.shape[0])
+        return RefIndex(kmer_size, keys=(lo, hi), source=ref_jf)
+    if not ref_fasta:
+        raise _engine.KdfError("a reference FASTA or a Jellyfish reference index is required")
+    logger.info("Packing reference FASTA: %s (k=%d)", ref_fasta, kmer_size)
+    _names, seqs = bamio.read_fasta_sequences(ref_fasta)
+    hs = _engine.pack_sequences(seqs)
+    return RefIndex(kmer_size, host_stream=hs, source=ref_fasta)
+
+
+# ---------------------------------------------------------------------------
+# parent scans
+# ---------------------------------------------------------------------------
+
+def _as_kmer_set(eng, kmer_fasta, kmer_size):
+    if isinstance(kmer_fasta, KmerSet):
+        return kmer_fasta
+    return KmerSet.from_fasta(eng, kmer_size, kmer_fasta)
+
+
+def _scan_parent_jellyfish(parent_bam, ref_fasta, kmer_fasta, kmer_size, parent_dir,
+                           threads=4, n_filter_kmers=None, engine=None):
+    """Count the filter k-mers in a parent BAM → ``dict{canonical k-mer: count}``
+    holding only k-mers seen at least once (reference ``:115-283``:
+    ``samtools fasta | jellyfish count --if`` then ``dump -c -L 1``)."""
+    eng = get_engine(engine)
+    kset = _as_kmer_set(eng, kmer_fasta, kmer_size)
+    table = kset.build_table(n_min=n_filter_kmers or 0)
+    table, tot = count_bam_into_table(eng, parent_bam, table, _engine.MODE_COUNT_IF_PRESENT,
+                                      0, threads)
+    logger.info("  parent scan: %d reads, %d k-mer instances, %d hits",
+                tot["reads"], tot["windows"], tot["hits"])
+    n, lo, hi, p0, _p1 = eng.threshold_compact(table, min0=1, want_planes=True)
+    keys = eng.keys_to_pyints(lo, hi)
+    counts = p0.cpu().numpy().view(np.uint32).tolist()
+    table.close()
+    return {kmer_of(key, kmer_size): int(c) for key, c in zip(keys, counts)}
+
+
+def _build_proband_jf_index(proband_unique_fa, kmer_size, tmpdir, n_proband_unique=None,
+                            engine=None):
+    """Membership table of the proband-unique k-mers (reference ``:369-436``)."""
+    eng = get_engine(engine)
+    kset = _as_kmer_set(eng, proband_unique_fa, kmer_size)
+    return kset.build_table(n_min=n_proband_unique or 0)

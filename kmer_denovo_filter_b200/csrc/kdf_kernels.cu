@@ -319,6 +319,26 @@ __global__ void __launch_bounds__(256) k_lookup_keys(TableView<KW> t, const u64*
   }
 }
 
+// per-key plane accumulation for existing keys (table growth / count merging)
+template <int KW>
+__global__ void __launch_bounds__(256) k_add_planes(TableView<KW> t, const u64* lo, const u64* hi,
+                                                    u64 n, const u32* add0, const u32* add1,
+                                                    u64* n_missing) {
+  u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    Key<KW> key;
+    key.lo = lo[i];
+    if (KW == 2) ((u64*)&key)[KW - 1] = hi[i];
+    u64 idx;
+    if (find_slot<KW>(t, key, idx)) {
+      if (add0 && add0[i]) atomicAdd(&t.slots[idx].p0, add0[i]);
+      if (add1 && add1[i]) atomicAdd(&t.slots[idx].p1, add1[i]);
+    } else if (n_missing) {
+      atomicAdd(n_missing, 1ull);
+    }
+  }
+}
+
 // ------------------------------------------------------------- K5 ---------
 // One warp per read.  Lanes stride through the read's window starts; hits are
 // appended to a per-warp shared list in position order (ballot prefix), then
@@ -809,6 +829,25 @@ int kdf_lookup_keys(const kdf_table* t, const uint64_t* lo, const uint64_t* hi, 
     TableView<2> tv{(Slot2*)t->slots, t->capacity};
     int g = grid_for((const void*)k_lookup_keys<2>, 256, n, t->sm_count);
     k_lookup_keys<2><<<g, 256, 0, st>>>(tv, (const u64*)lo, (const u64*)hi, n, out_found, out_p0, out_p1);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return KDF_OK;
+}
+
+int kdf_add_planes(kdf_table* t, const uint64_t* lo, const uint64_t* hi, uint64_t n,
+                   const uint32_t* add0, const uint32_t* add1, uint64_t* n_missing, void* stream) {
+  if (!t) return fail(KDF_ERR_ARG, "kdf_add_planes: table is NULL");
+  if (n == 0) return KDF_OK;
+  if (!lo || (t->key_words == 2 && !hi)) return fail(KDF_ERR_ARG, "kdf_add_planes: NULL key array");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (t->key_words == 1) {
+    TableView<1> tv{(Slot1*)t->slots, t->capacity};
+    int g = grid_for((const void*)k_add_planes<1>, 256, n, t->sm_count);
+    k_add_planes<1><<<g, 256, 0, st>>>(tv, (const u64*)lo, (const u64*)hi, n, add0, add1, (u64*)n_missing);
+  } else {
+    TableView<2> tv{(Slot2*)t->slots, t->capacity};
+    int g = grid_for((const void*)k_add_planes<2>, 256, n, t->sm_count);
+    k_add_planes<2><<<g, 256, 0, st>>>(tv, (const u64*)lo, (const u64*)hi, n, add0, add1, (u64*)n_missing);
   }
   CUDA_TRY(cudaGetLastError());
   return KDF_OK;

@@ -1,0 +1,730 @@
+"""VCF-free discovery pipeline on the GPU k-mer engine.
+
+Function names, argument meaning, return values and every output file follow
+the reference's ``discovery/pipeline.py``; the Jellyfish / samtools /
+``jellyfish query`` work of Modules 0-3 runs as sm_100a kernels through
+``libkdf_sm100.so``.  The clustering, SV annotation and the writers are the
+reference's CPU steps, restated here (they consume the per-read reduction the
+GPU produces).
+
+Reference map (``discovery/pipeline.py``):
+  _extract_child_kmers_discovery :69    _subtract_reference_kmers :271
+  _count_parent_jellyfish :322          _filter_parents_discovery :462
+  _anchor_and_cluster :615              _write_bed :1156
+  _write_bedgraph :1197                 _write_read_coverage_bed :1281
+  _annotate_and_link_from_metadata :1351  _write_bedpe :1492
+  _classify_regions :1517               run_discovery_pipeline :2093
+"""
+
+import bisect
+import collections
+import json
+import logging
+import os
+import sys
+import time
+
+import numpy as np
+
+from .. import bamio
+from .. import engine as _engine
+from ..core import kmer_engine_wrappers as kw
+from ..core.kmer_engine_wrappers import (  # noqa: F401  (re-exported like the reference)
+    _build_proband_jf_index,
+    _ensure_ref_jf,
+    get_engine,
+)
+from ..kmer_utils import KmerSet, canonicalize
+
+logger = logging.getLogger(__name__)
+
+REF_PLANE = 1  # plane 1 of the child table holds the "in reference" flag
+
+
+class ChildCandidates:
+    """Module-1 handle: the child count table (plane 0 = count) and the
+    ``min_child_count`` threshold; replaces ``child_candidates.fa``."""
+
+    def __init__(self, eng, table, min_child_count, n_candidates, stats):
+        self.engine = eng
+        self.table = table
+        self.min_child_count = min_child_count
+        self.n_candidates = n_candidates
+        self.stats = stats
+
+    def close(self):
+        if self.table is not None:
+            self.table.close()
+            self.table = None
+
+
+# ── Module 1 ───────────────────────────────────────────────────────
+
+def _extract_child_kmers_discovery(child_bam, ref_fasta, kmer_size, min_child_count,
+                                   threads, tmpdir, jf_hash_size=None, engine=None):
+    """Count every canonical k-mer of the child and threshold by count.
+
+    Returns ``(ChildCandidates, n_candidates)``; the reference returns the
+    path of a FASTA holding the same set (``dump -c -L min_child_count``).
+    """
+    eng = get_engine(engine)
+    kwds = eng.lib.kdf_key_words(kmer_size)
+    if not kwds:
+        raise _engine.KdfError(
+            "k=%d is outside the GPU engine's range (k <= 63; 64-bit keys for k <= 32, "
+            "128-bit above)" % kmer_size)
+    slot_bytes = 16 if kwds == 1 else 32
+    free_b, _tot = eng.torch.cuda.mem_get_info(eng.device)
+    n_keys = kw._parse_hash_size(jf_hash_size)
+    if n_keys is None:
+        n_keys = kw._estimate_table_keys(child_bam, free_b, slot_bytes)
+    else:
+        n_keys = min(n_keys, int(free_b * 0.8 / slot_bytes))
+    t0 = time.monotonic()
+    table = eng.new_table(kmer_size, capacity=max(eng.capacity_for(n_keys // 2), 1024))
+    logger.info("Extracting child k-mers from BAM (k=%d, table slots=%d)…", kmer_size,
+                table.capacity)
+    table, tot = kw.count_bam_into_table(eng, child_bam, table, _engine.MODE_INSERT_COUNT, 0,
+                                         threads, grow=True)
+    n_candidates = eng.threshold_count(table, min0=min_child_count)
+    logger.info("Child k-mer counting complete (%.1fs): %d reads, %d k-mer instances, "
+                "%d distinct", time.monotonic() - t0, tot["reads"], tot["windows"], tot["new"])
+    logger.info("Child candidate k-mers (count >= %d): %d", min_child_count, n_candidates)
+    return ChildCandidates(eng, table, min_child_count, n_candidates, tot), n_candidates
+
+
+def _subtract_reference_kmers(ref_jf, child_candidates_fa, tmpdir):
+    """Remove candidates that occur in the reference → ``(KmerSet, n_non_ref)``.
+
+    The reference queries every candidate against ``ref.jf`` and keeps count
+    == 0; here the reference sequence is streamed against the child table
+    (mark-if-present) and the survivors are compacted.  The candidates handle
+    is released afterwards, as the reference deletes its input FASTA."""
+    cand = child_candidates_fa
+    eng = cand.engine
+    eng.clear_plane(cand.table, REF_PLANE)
+    ref_jf.mark_present(eng, cand.table, REF_PLANE)
+    n, lo, hi, _p0, _p1 = eng.threshold_compact(cand.table, min0=cand.min_child_count, max1=0)
+    k = cand.table.k
+    cand.close()
+    logger.info("Non-reference child k-mers after subtraction: %d", n)
+    return KmerSet(eng, k, lo, hi), n
+
+
+# ── Module 2 ───────────────────────────────────────────────────────
+
+def _count_parent_jellyfish(parent_bam, ref_fasta, kmer_fasta, kmer_size, parent_dir, threads,
+                            label="Parent", n_filter_kmers=None, engine=None):
+    """``samtools fasta | jellyfish count --if`` → table whose plane 0 holds the
+    parent's count of every filter k-mer (the reference returns a ``.jf`` path)."""
+    eng = get_engine(engine)
+    kset = kw._as_kmer_set(eng, kmer_fasta, kmer_size)
+    table = kset.build_table(n_min=n_filter_kmers or 0)
+    t0 = time.monotonic()
+    table, tot = kw.count_bam_into_table(eng, parent_bam, table, _engine.MODE_COUNT_IF_PRESENT,
+                                         0, threads)
+    logger.info("  %s counting complete (%.1fs): %d reads, %d k-mer instances probed, %d hits",
+                label, time.monotonic() - t0, tot["reads"], tot["windows"], tot["hits"])
+    return table
+
+
+def _filter_parents_discovery(mother_bam, father_bam, ref_fasta, child_non_ref_fa, kmer_size,
+                              threads, tmpdir, parent_max_count=0, engine=None):
+    """Keep k-mers seen at most ``parent_max_count`` times in the mother, then in
+    the father → ``(n_proband_unique, KmerSet | None)``."""
+    eng = get_engine(engine)
+    kset = kw._as_kmer_set(eng, child_non_ref_fa, kmer_size)
+    n_input = len(kset)
+    if n_input == 0:
+        return 0, None
+    logger.info("Filtering %d non-reference k-mers against parents…", n_input)
+    mt = _count_parent_jellyfish(mother_bam, ref_fasta, kset, kmer_size,
+                                 os.path.join(tmpdir or "", "mother"), threads, "Mother",
+                                 n_input, engine=eng)
+    n_surv, lo, hi, _a, _b = eng.threshold_compact(mt, max0=parent_max_count)
+    mt.close()
+    logger.info("Mother: %d / %d non-ref k-mers found (count > %d), %d surviving",
+                n_input - n_surv, n_input, parent_max_count, n_surv)
+    if n_surv == 0:
+        return 0, None
+    after_mother = KmerSet(eng, kmer_size, lo, hi)
+    ft = _count_parent_jellyfish(father_bam, ref_fasta, after_mother, kmer_size,
+                                 os.path.join(tmpdir or "", "father"), threads, "Father",
+                                 n_surv, engine=eng)
+    n_pu, lo, hi, _a, _b = eng.threshold_compact(ft, max0=parent_max_count)
+    ft.close()
+    logger.info("Father: %d / %d surviving k-mers found (count > %d), %d proband-unique",
+                n_surv - n_pu, n_surv, parent_max_count, n_pu)
+    if n_pu == 0:
+        return 0, None
+    return n_pu, KmerSet(eng, kmer_size, lo, hi)
+
+
+# ── Module 3 ───────────────────────────────────────────────────────
+
+def _collect_kmer_ref_positions(read, kmer_hit_indices, kmer_size):
+    """Counter{ref position: #hit k-mers covering it} (``core/bam_scanner.py:97-117``)."""
+    cig = read.cigartuples or ()
+    qlen = sum(ln for op, ln in cig if op in (0, 1, 4, 7, 8))
+    q2r = np.full(max(qlen, 1), -1, dtype=np.int64)
+    q = 0
+    r = read.reference_start
+    for op, ln in cig:
+        if op in (0, 7, 8):
+            q2r[q:q + ln] = np.arange(r, r + ln)
+            q += ln
+            r += ln
+        elif op in (1, 4):
+            q += ln
+        elif op in (2, 3):
+            r += ln
+    cov = collections.Counter()
+    if not len(kmer_hit_indices):
+        return cov
+    starts = np.fromiter(kmer_hit_indices, dtype=np.int64)
+    qpos = (starts[:, None] + np.arange(kmer_size)[None, :]).ravel()
+    qpos = qpos[qpos < q2r.shape[0]]
+    rpos = q2r[qpos]
+    rpos = rpos[rpos >= 0]
+    u, c = np.unique(rpos, return_counts=True)
+    for p, n in zip(u.tolist(), c.tolist()):
+        cov[p] = n
+    return cov
+
+
+def scan_child_reads(eng, child_bam, table, kmer_size, min_distinct_kmers_per_read, threads,
+                     batch_bases=kw.BATCH_BASES):
+    """GPU part of Module 3: per-read distinct / hit counts for every scanned
+    record plus, for reads meeting the threshold, their hit positions.
+
+    Yields ``(batch, ndistinct u32[], nhits u32[], hit_read_idx, hit_offset)``
+    per batch, hits sorted by (read, offset)."""
+    with bamio.BamReader(child_bam, threads=threads) as rd:
+        for batch in rd.batches(bamio.MODE_SCAN, max_bases=batch_bases, want_meta=True):
+            ds = eng.upload(batch)
+            res = eng.scan_reads(table, ds, min_distinct=max(1, min_distinct_kmers_per_read))
+            nd = res["ndistinct"].cpu().numpy().view(np.uint32)
+            nh = res["nhits"].cpu().numpy().view(np.uint32)
+            if res["n_hits"]:
+                pos = res["hit_pos"].cpu().numpy().view(np.uint64)
+                slot = res["hit_slot"].cpu().numpy().view(np.uint32)
+                order = np.argsort(pos, kind="stable")
+                pos = pos[order]
+                slot = slot[order]
+                ridx = np.searchsorted(batch.read_starts, pos, side="right") - 1
+                off = (pos - batch.read_starts[ridx]).astype(np.int64)
+            else:
+                ridx = np.zeros(0, dtype=np.int64)
+                off = np.zeros(0, dtype=np.int64)
+                slot = np.zeros(0, dtype=np.uint32)
+            # finish the rare overflow reads (> 1024 hit windows) from the slot list
+            ov = np.flatnonzero(nd == _engine.NDISTINCT_OVERFLOW)
+            if ov.size:
+                nd = nd.copy()
+                for r in ov.tolist():
+                    nd[r] = np.unique(slot[ridx == r]).shape[0]
+            yield batch, nd, nh, ridx, off, slot
+
+
+def _cluster_hits(read_hits, merge_distance):
+    """Sort by (chrom, start) and merge greedily (reference ``:1107-1144``)."""
+    regions, region_reads, region_kmers = [], {}, {}
+    if not read_hits:
+        return regions, region_reads, region_kmers
+    read_hits.sort(key=lambda h: (h[0], h[1]))
+    cur = None
+    for chrom, start, end, name, kmers, _supp in read_hits:
+        if cur is not None and chrom == cur[0] and start <= cur[2] + merge_distance:
+            cur[2] = max(cur[2], end)
+            cur[3].add(name)
+            cur[4].update(kmers)
+            continue
+        if cur is not None:
+            key = (cur[0], cur[1], cur[2])
+            regions.append(key)
+            region_reads[key] = cur[3]
+            region_kmers[key] = cur[4]
+        cur = [chrom, start, end, {name}, set(kmers)]
+    key = (cur[0], cur[1], cur[2])
+    regions.append(key)
+    region_reads[key] = cur[3]
+    region_kmers[key] = cur[4]
+    return regions, region_reads, region_kmers
+
+
+def _anchor_and_cluster(child_bam, ref_fasta, proband_unique_kmers, kmer_size,
+                        merge_distance=500, threads=1, min_distinct_kmers_per_read=1,
+                        proband_unique_fa=None, proband_jf=None, n_proband_unique=None,
+                        tmpdir=None, memory_limit_gb=None, engine=None):
+    """Find reads carrying proband-unique k-mers and cluster them into regions.
+
+    ``proband_jf`` is the device membership table (or pass the set through
+    ``proband_unique_kmers`` / ``proband_unique_fa``).  Returns the reference's
+    8-tuple ``(regions, region_reads, total_informative, region_kmers,
+    unmapped_informative, read_sv_meta, kmer_coverage, read_coverage)``.
+    Informative reads are de-duplicated on ``(query_name, is_supplementary)``
+    in BAM file order.
+    """
+    eng = get_engine(engine)
+    table = proband_jf
+    owns = False
+    if table is None:
+        if proband_unique_fa is not None:
+            kset = kw._as_kmer_set(eng, proband_unique_fa, kmer_size)
+        else:
+            kset = KmerSet.from_strings(eng, kmer_size, proband_unique_kmers or ())
+        table = kset.build_table()
+        owns = True
+    t0 = time.monotonic()
+    read_hits = []
+    reads_seen = set()
+    read_sv_meta = {}
+    kmer_coverage = collections.defaultdict(collections.Counter)
+    read_coverage = collections.defaultdict(collections.Counter)
+    unmapped_informative = 0
+    total_scanned = 0
+    per_read = []  # (record index, n_distinct, n_hits) of reads with >= 1 hit
+    for batch, nd, nh, ridx, off, _slot in scan_child_reads(
+            eng, child_bam, table, kmer_size, min_distinct_kmers_per_read, threads):
+        total_scanned += batch.n_reads
+        hit_reads = np.flatnonzero(nh > 0)
+        for r in hit_reads.tolist():
+            per_read.append((int(batch.rec_index[r]), int(nd[r]), int(nh[r])))
+        informative = np.flatnonzero(nd >= max(1, min_distinct_kmers_per_read))
+        lo_i = np.searchsorted(ridx, informative, side="left")
+        hi_i = np.searchsorted(ridx, informative, side="right")
+        for r, a, b in zip(informative.tolist(), lo_i.tolist(), hi_i.tolist()):
+            read = batch.record(r)
+            dedup_key = (read.query_name, read.is_supplementary)
+            if dedup_key in reads_seen:
+                continue
+            reads_seen.add(dedup_key)
+            if read.is_unmapped:
+                unmapped_informative += 1
+                continue
+            hit_idx = off[a:b].tolist()
+            seq = read.query_sequence
+            unique_in_read = {canonicalize(seq[i:i + kmer_size]) for i in hit_idx}
+            chrom = read.reference_name
+            read_hits.append((chrom, read.reference_start, read.reference_end,
+                              dedup_key[0], unique_in_read, dedup_key[1]))
+            cov = _collect_kmer_ref_positions(read, hit_idx, kmer_size)
+            kmer_coverage[chrom] += cov
+            rc = read_coverage[chrom]
+            for pos in cov:
+                rc[pos] += 1
+            max_clip = 0
+            for op, ln in read.cigartuples or ():
+                if op == 4 and ln > max_clip:
+                    max_clip = ln
+            has_sa = read.has_tag("SA")
+            read_sv_meta[dedup_key] = {
+                "has_sa": has_sa,
+                "sa_str": read.get_tag("SA") if (has_sa and not dedup_key[1]) else None,
+                "is_paired": read.is_paired,
+                "is_proper_pair": read.is_proper_pair,
+                "mate_is_unmapped": read.mate_is_unmapped if read.is_paired else False,
+                "max_clip": max_clip,
+            }
+        batch.close()
+    if owns:
+        table.close()
+    total_informative = len(read_hits) + unmapped_informative
+    logger.info("Anchoring complete: %d informative reads (%d mapped, %d unmapped) from %d "
+                "scanned (%.1fs)", total_informative, len(read_hits), unmapped_informative,
+                total_scanned, time.monotonic() - t0)
+    _anchor_and_cluster.last_per_read = per_read
+    if not read_hits:
+        return ([], {}, total_informative, {}, unmapped_informative, read_sv_meta,
+                kmer_coverage, read_coverage)
+    regions, region_reads, region_kmers = _cluster_hits(read_hits, merge_distance)
+    logger.info("Clustered %d mapped informative reads into %d regions", len(read_hits),
+                len(regions))
+    return (regions, region_reads, total_informative, region_kmers, unmapped_informative,
+            read_sv_meta, kmer_coverage, read_coverage)
+
+
+# ── Module 4: annotation + writers (CPU, output contract) ──────────
+
+def _infer_sv_type(region_a, region_b):
+    return "BND" if region_a[0] != region_b[0] else "INTRA"
+
+
+def _annotate_and_link_from_metadata(regions, region_reads, read_sv_meta):
+    """Per-region SV evidence and SA-tag links (reference ``:1351-1489``)."""
+    membership = collections.defaultdict(set)
+    for rk in regions:
+        for qname in region_reads.get(rk, ()):
+            membership[qname].add(rk)
+    annotations = {rk: {"split_reads": 0, "discordant_pairs": 0, "max_clip_len": 0,
+                        "unmapped_mates": 0} for rk in regions}
+    if not membership:
+        return annotations, []
+    split_done = set()
+    for (qname, _supp), meta in read_sv_meta.items():
+        for rk in membership.get(qname, ()):
+            ann = annotations[rk]
+            if meta["has_sa"] and (qname, rk) not in split_done:
+                split_done.add((qname, rk))
+                ann["split_reads"] += 1
+            if meta["is_paired"]:
+                if meta["mate_is_unmapped"]:
+                    ann["unmapped_mates"] += 1
+                elif not meta["is_proper_pair"]:
+                    ann["discordant_pairs"] += 1
+            ann["max_clip_len"] = max(ann["max_clip_len"], meta["max_clip"])
+    by_chrom = collections.defaultdict(list)
+    for rk in regions:
+        by_chrom[rk[0]].append(rk)
+    starts = {}
+    for chrom, lst in by_chrom.items():
+        lst.sort(key=lambda x: x[1])
+        starts[chrom] = [x[1] for x in lst]
+    bridges = collections.defaultdict(set)
+    for (qname, _supp), meta in read_sv_meta.items():
+        sa = meta.get("sa_str")
+        if not sa or qname not in membership:
+            continue
+        for entry in sa.rstrip(";").split(";"):
+            fields = entry.split(",")
+            if len(fields) < 3 or fields[0] not in starts:
+                continue
+            try:
+                sa_pos = int(fields[1]) - 1
+            except ValueError:
+                continue
+            j = bisect.bisect_right(starts[fields[0]], sa_pos) - 1
+            if j < 0:
+                continue
+            target = by_chrom[fields[0]][j]
+            if not (target[1] <= sa_pos < target[2]):
+                continue
+            for prim in membership[qname]:
+                if prim != target:
+                    bridges[tuple(sorted((prim, target)))].add(qname)
+    for qname, rset in membership.items():
+        if len(rset) > 1:
+            ordered = sorted(rset)
+            for i, a in enumerate(ordered):
+                for b in ordered[i + 1:]:
+                    bridges[(a, b)].add(qname)
+    links = [{"region_a": a, "region_b": b, "supporting_reads": bridges[(a, b)],
+              "sv_type_hint": _infer_sv_type(a, b)} for a, b in sorted(bridges)]
+    return annotations, links
+
+
+def _classify_regions(regions, region_annotations, sv_links):
+    """SV / SMALL / AMBIGUOUS (reference ``:1517-1546``)."""
+    linked = {l["region_a"] for l in sv_links} | {l["region_b"] for l in sv_links}
+    for rk in regions:
+        ann = region_annotations.get(rk, {})
+        evid = [ann.get("split_reads", 0), ann.get("discordant_pairs", 0),
+                ann.get("unmapped_mates", 0)]
+        if max(evid) >= 2 or rk in linked:
+            ann["class"] = "SV"
+        elif not any(evid):
+            ann["class"] = "SMALL"
+        else:
+            ann["class"] = "AMBIGUOUS"
+        region_annotations[rk] = ann
+
+
+def _write_bed(regions, region_reads, region_kmers, bed_path, region_annotations=None,
+               filters=None):
+    region_annotations = region_annotations or {}
+    with open(bed_path, "w") as fh:
+        if filters:
+            fh.write("#filters: %s\n" % " ".join("%s=%s" % kv for kv in sorted(filters.items())))
+        fh.write("#chrom\tstart\tend\treads\tunique_kmers\tsplit_reads\tdiscordant_pairs"
+                 "\tmax_clip_len\tunmapped_mates\tclass\n")
+        for rk in regions:
+            ann = region_annotations.get(rk, {})
+            cols = [rk[0], rk[1], rk[2], len(region_reads.get(rk, ())),
+                    len(region_kmers.get(rk, ())), ann.get("split_reads", 0),
+                    ann.get("discordant_pairs", 0), ann.get("max_clip_len", 0),
+                    ann.get("unmapped_mates", 0), ann.get("class", "SMALL")]
+            fh.write("\t".join(str(c) for c in cols) + "\n")
+    logger.info("BED file written: %s (%d regions)", bed_path, len(regions))
+
+
+def _runs(sorted_items):
+    """Merge (pos, value) pairs, sorted by pos, into (start, end, value) runs."""
+    run = None
+    for pos, val in sorted_items:
+        if run is not None and pos == run[1] and val == run[2]:
+            run[1] = pos + 1
+            continue
+        if run is not None:
+            yield tuple(run)
+        run = [pos, pos + 1, val]
+    if run is not None:
+        yield tuple(run)
+
+
+def _write_bedgraph(kmer_coverage, bedgraph_path, read_coverage=None, min_reads=3):
+    """4-column bedGraph of k-mer coverage (reference ``:1197-1278``)."""
+    with open(bedgraph_path, "w") as fh:
+        fh.write("#track type=bedGraph description=\"De novo k-mer coverage (unique k-mer base "
+                 "overlaps per position, min_reads>=%d)\"\n" % min_reads)
+        for chrom in sorted(kmer_coverage):
+            cov = kmer_coverage[chrom]
+            if not cov:
+                continue
+            rc = read_coverage.get(chrom, {}) if read_coverage else None
+            kept = [(p, cov[p]) for p in sorted(cov)
+                    if rc is None or rc.get(p, 0) >= min_reads]
+            for s, e, v in _runs(kept):
+                fh.write("%s\t%d\t%d\t%s\n" % (chrom, s, e, v))
+
+
+def _write_read_coverage_bed(kmer_coverage, read_coverage, bed_path, min_reads=3):
+    """Per-position read support BED (reference ``:1281-1348``)."""
+    with open(bed_path, "w") as fh:
+        fh.write("#track description=\"De novo k-mer read support (min_reads>=%d)\"\n"
+                 "#chrom\tstart\tend\tread_count\tavg_kmers_per_read\n" % min_reads)
+        for chrom in sorted(read_coverage):
+            rc = read_coverage[chrom]
+            kc = kmer_coverage.get(chrom, {})
+            kept = [(p, (n, round(kc.get(p, 0) / n, 1)))
+                    for p, n in sorted(rc.items()) if n >= min_reads]
+            for s, e, (n, avg) in _runs(kept):
+                fh.write("%s\t%d\t%d\t%s\t%s\n" % (chrom, s, e, n, avg))
+
+
+def _write_bedpe(links, bedpe_path):
+    with open(bedpe_path, "w") as fh:
+        fh.write("#chrom1\tstart1\tend1\tchrom2\tstart2\tend2\tsv_id\tsupporting_reads\tsv_type\n")
+        for i, link in enumerate(links, 1):
+            a, b = link["region_a"], link["region_b"]
+            fh.write("%s\t%d\t%d\t%s\t%d\t%d\tSV_%d\t%d\t%s\n" % (
+                a[0], a[1], a[2], b[0], b[1], b[2], i, len(link["supporting_reads"]),
+                link["sv_type_hint"]))
+
+
+def _parse_candidate_summary(summary_path, dka_dkt_min=0.25, dka_min=10):
+    """High-quality candidates of a VCF-mode summary.txt (reference ``:1549-1606``)."""
+    out = []
+    in_table = False
+    with open(summary_path) as fh:
+        for raw in fh:
+            text = raw.strip()
+            if not in_table:
+                in_table = text.startswith("Variant") and "DKU" in text
+                continue
+            if text.startswith("-------"):
+                continue
+            if not text or text.startswith("="):
+                break
+            parts = text.split()
+            if len(parts) < 12:
+                continue
+            chrom, pos = parts[0].rsplit(":", 1)
+            ref, alt = parts[1].split(">")
+            dka, dka_dkt = int(parts[4]), float(parts[6])
+            if dka_dkt > dka_dkt_min and dka > dka_min:
+                out.append({"chrom": chrom, "pos": int(pos), "ref": ref, "alt": alt,
+                            "dka": dka, "dka_dkt": dka_dkt, "call": parts[-1]})
+    return out
+
+
+def _compare_candidates_to_regions(candidates, regions):
+    res = []
+    for cand in candidates:
+        hit = next(((c, s, e) for c, s, e in regions
+                    if c == cand["chrom"] and s < cand["pos"] <= e), None)
+        res.append(dict(cand, captured=hit is not None,
+                        region=("%s:%d-%d" % (hit[0], hit[1] + 1, hit[2])) if hit else None))
+    return res
+
+
+#: curated DNM loci the reference reports on (Sulovari et al. 2023; reference ``:1641-1649``)
+SULOVARI_DNM_REGIONS = [
+    ("chr17", 53340465, 107, "deletion"),
+    ("chr14", 23280711, None, "microsatellite_expansion"),
+    ("chr3", 85552367, 64, "sv_like"),
+    ("chr5", 97089276, 43, "sv_like"),
+    ("chr8", 125785998, 43, "sv_like"),
+    ("chr18", 62805217, 34, "sv_like"),
+    ("chr7", 142786222, 10607, "deletion"),
+]
+
+
+def _evaluate_dnm_regions(discovery_regions, region_detail, dnm_regions=None):
+    """Per-locus detection summary (reference ``:1653-1783``)."""
+    dnm_regions = SULOVARI_DNM_REGIONS if dnm_regions is None else dnm_regions
+    detail = {(d["chrom"], d["start"], d["end"]): d for d in region_detail}
+    rank = {"SV": 3, "AMBIGUOUS": 2, "SMALL": 1}
+    out = []
+    for chrom, pos, size, event_type in dnm_regions:
+        lo, hi = pos, pos + (size if size else 1)
+        matches = [r for r in discovery_regions if r[0] == chrom and r[1] < hi and lo < r[2]]
+        ds = [detail.get(m, {}) for m in matches]
+        span_lo = min([lo] + [m[1] for m in matches])
+        span_hi = max([hi] + [m[2] for m in matches])
+        kmers = sum(d.get("unique_kmers", 0) for d in ds)
+        classes = [d.get("class", "SMALL") for d in ds]
+        out.append({
+            "locus": "%s:%d" % (chrom, pos),
+            "event_type": event_type,
+            "event_size": size,
+            "detected": bool(matches),
+            "discovery_regions": ["%s:%d-%d" % (m[0], m[1] + 1, m[2]) for m in matches],
+            "total_reads": sum(d.get("reads", 0) for d in ds),
+            "total_unique_kmers": kmers,
+            "max_clip_len": max([0] + [d.get("max_clip_len", 0) for d in ds]),
+            "unmapped_mates": sum(d.get("unmapped_mates", 0) for d in ds),
+            "discordant_pairs": sum(d.get("discordant_pairs", 0) for d in ds),
+            "split_reads": sum(d.get("split_reads", 0) for d in ds),
+            "sv_class": max(classes, key=lambda c: rank.get(c, 0)) if classes else "NONE",
+            "kmer_signal": round(kmers / max(span_hi - span_lo, 1), 4) if matches else 0.0,
+            "assessment": "DETECTED" if matches else "NOT_DETECTED",
+        })
+    return out
+
+
+def _write_empty_discovery_outputs(bed_path, metrics_path, summary_path, metrics,
+                                   bedpe_path=None):
+    _write_bed([], {}, {}, bed_path)
+    if bedpe_path:
+        _write_bedpe([], bedpe_path)
+    with open(metrics_path, "w") as fh:
+        json.dump(metrics, fh, indent=2)
+    from .summary import _write_discovery_summary
+    _write_discovery_summary(summary_path, [], {}, {}, metrics)
+
+
+def _validate(args):
+    """Input rules of the reference (``utils.py:230-350``) that concern this path."""
+    errs = []
+    k = args.kmer_size
+    if k < 3 or k % 2 == 0 or k > 201:
+        errs.append("--kmer-size must be an odd number in [3, 201], got %d" % k)
+    elif k > 63:
+        errs.append("--kmer-size %d: the GPU engine supports k <= 63 (128-bit keys)" % k)
+    for name in ("child", "mother", "father"):
+        p = getattr(args, name)
+        if not os.path.isfile(p):
+            errs.append("--%s file not found: %s" % (name, p))
+    if not args.ref_fasta and not getattr(args, "ref_jf", None):
+        errs.append("discovery mode needs --ref-fasta or --ref-jf")
+    if args.ref_fasta and not os.path.isfile(args.ref_fasta):
+        errs.append("--ref-fasta file not found: %s" % args.ref_fasta)
+    if errs:
+        for e in errs:
+            logger.error(e)
+        sys.exit(1)
+
+
+def run_discovery_pipeline(args, engine=None):
+    """Run the VCF-free discovery pipeline (reference ``:2093``).  Returns the
+    metrics dict that is also written to ``{out_prefix}.metrics.json``."""
+    start = time.monotonic()
+    logging.basicConfig(level=logging.DEBUG if getattr(args, "debug_kmers", False) else logging.INFO,
+                        format="%(asctime)s %(levelname)s %(message)s")
+    _validate(args)
+    eng = get_engine(engine)
+    out_prefix = args.out_prefix
+    bed_path = out_prefix + ".bed"
+    metrics_path = out_prefix + ".metrics.json"
+    summary_path = out_prefix + ".summary.txt"
+    bedpe_path = getattr(args, "sv_bedpe", None) or out_prefix + ".sv.bedpe"
+    bedgraph_path = out_prefix + ".kmer_coverage.bedgraph"
+    read_cov_bed_path = out_prefix + ".read_coverage.bed"
+    min_bedgraph_reads = getattr(args, "min_bedgraph_reads", 3)
+    min_dk = getattr(args, "min_distinct_kmers_per_read", None)
+    if min_dk is None:
+        min_dk = max(1, args.kmer_size // 4)
+    k = args.kmer_size
+    threads = max(1, args.threads)
+
+    def finish_empty(n_cand, n_non_ref):
+        m = {"mode": "discovery", "child_candidate_kmers": n_cand, "non_ref_kmers": n_non_ref,
+             "proband_unique_kmers": 0, "informative_reads": 0,
+             "unmapped_informative_reads": 0, "candidate_regions": 0}
+        _write_empty_discovery_outputs(bed_path, metrics_path, summary_path, m, bedpe_path)
+        return m
+
+    ref_index = _ensure_ref_jf(args.ref_fasta, k, threads, getattr(args, "ref_jf", None), eng)
+    cand, n_candidates = _extract_child_kmers_discovery(
+        args.child, args.ref_fasta, k, args.min_child_count, threads, None,
+        jf_hash_size=getattr(args, "jf_hash_size", None), engine=eng)
+    if n_candidates == 0:
+        cand.close()
+        return finish_empty(0, 0)
+    non_ref, n_non_ref = _subtract_reference_kmers(ref_index, cand, None)
+    if n_non_ref == 0:
+        return finish_empty(n_candidates, 0)
+    n_pu, pu = _filter_parents_discovery(args.mother, args.father, args.ref_fasta, non_ref, k,
+                                         threads, None, args.parent_max_count, engine=eng)
+    if n_pu == 0:
+        return finish_empty(n_candidates, n_non_ref)
+    pu_table = _build_proband_jf_index(pu, k, None, n_pu, engine=eng)
+    (regions, region_reads, total_informative, region_kmers, unmapped_informative,
+     read_sv_meta, kmer_coverage, read_coverage) = _anchor_and_cluster(
+        args.child, args.ref_fasta, None, k, merge_distance=args.cluster_distance,
+        threads=threads, min_distinct_kmers_per_read=min_dk, proband_jf=pu_table,
+        n_proband_unique=n_pu, engine=eng)
+    pu_table.close()
+
+    min_reads, min_kmers = args.min_supporting_reads, args.min_distinct_kmers
+    if min_reads > 1 or min_kmers > 1:
+        regions = [r for r in regions if len(region_reads.get(r, ())) >= min_reads
+                   and len(region_kmers.get(r, ())) >= min_kmers]
+    annotations, links = _annotate_and_link_from_metadata(regions, region_reads, read_sv_meta)
+    _classify_regions(regions, annotations, links)
+    _write_bed(regions, region_reads, region_kmers, bed_path, region_annotations=annotations,
+               filters={"min_distinct_kmers_per_read": min_dk, "min_supporting_reads": min_reads,
+                        "min_distinct_kmers": min_kmers})
+    _write_bedgraph(kmer_coverage, bedgraph_path, read_coverage, min_bedgraph_reads)
+    _write_read_coverage_bed(kmer_coverage, read_coverage, read_cov_bed_path, min_bedgraph_reads)
+    _write_bedpe(links, bedpe_path)
+
+    metrics = {
+        "mode": "discovery",
+        "child_candidate_kmers": n_candidates,
+        "non_ref_kmers": n_non_ref,
+        "proband_unique_kmers": n_pu,
+        "informative_reads": total_informative,
+        "unmapped_informative_reads": unmapped_informative,
+        "candidate_regions": len(regions),
+        "filters": {"min_distinct_kmers_per_read": min_dk, "min_supporting_reads": min_reads,
+                    "min_distinct_kmers": min_kmers, "min_bedgraph_reads": min_bedgraph_reads},
+        "regions": [],
+    }
+    for rk in regions:
+        ann = annotations.get(rk, {})
+        metrics["regions"].append({
+            "chrom": rk[0], "start": rk[1], "end": rk[2], "size": rk[2] - rk[1],
+            "reads": len(region_reads.get(rk, ())),
+            "unique_kmers": len(region_kmers.get(rk, ())),
+            "split_reads": ann.get("split_reads", 0),
+            "discordant_pairs": ann.get("discordant_pairs", 0),
+            "max_clip_len": ann.get("max_clip_len", 0),
+            "unmapped_mates": ann.get("unmapped_mates", 0),
+            "class": ann.get("class", "SMALL"),
+        })
+    comparison = None
+    cs = getattr(args, "candidate_summary", None)
+    if cs and os.path.isfile(cs):
+        comparison = _compare_candidates_to_regions(_parse_candidate_summary(cs), regions)
+        n_cap = sum(1 for c in comparison if c["captured"])
+        metrics["candidate_comparison"] = {
+            "hq_candidates": len(comparison), "captured": n_cap,
+            "capture_rate": (n_cap / len(comparison)) if comparison else 0.0,
+            "candidates": [{"variant": "%s:%d %s>%s" % (c["chrom"], c["pos"], c["ref"], c["alt"]),
+                            "dka": c["dka"], "dka_dkt": c["dka_dkt"], "captured": c["captured"],
+                            "region": c["region"]} for c in comparison],
+        }
+    dnm = _evaluate_dnm_regions(regions, metrics["regions"])
+    n_det = sum(1 for d in dnm if d["detected"])
+    metrics["dnm_evaluation"] = {"total_loci": len(dnm), "detected": n_det,
+                                 "detection_rate": (n_det / len(dnm)) if dnm else 0.0,
+                                 "loci": dnm}
+    with open(metrics_path, "w") as fh:
+        json.dump(metrics, fh, indent=2)
+    from .summary import _write_discovery_summary
+    _write_discovery_summary(summary_path, regions, region_reads, region_kmers, metrics,
+                             candidate_comparison=comparison, region_annotations=annotations,
+                             dnm_evaluation=dnm)
+    logger.info("Discovery pipeline finished in %.1fs", time.monotonic() - start)
+    return metrics

@@ -62,6 +62,7 @@ _SIGNATURES = {
     "kdf_extract_canonical": (_i, [ctypes.POINTER(_Stream), _i, _vp, _vp, _vp, _vp]),
     "kdf_count_stream": (_i, [_vp, ctypes.POINTER(_Stream), _i, _i, _u32, _vp, _vp]),
     "kdf_update_keys": (_i, [_vp, _vp, _vp, _u64, _i, _i, _u32, _vp, _vp]),
+    "kdf_add_planes": (_i, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp]),
     "kdf_threshold_compact": (_i, [_vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _u64, _vp, _vp]),
     "kdf_lookup_keys": (_i, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp]),
     "kdf_scan_reads": (_i, [_vp, ctypes.POINTER(_Stream), _vp, _vp, _u64, _u32, _vp, _vp, _vp, _vp,
@@ -371,6 +372,19 @@ class CudaEngine:
             stats.data_ptr() if stats is not None else None, self.stream_ptr()))
         if n:
             self.launches += 1
+
+    def add_planes(self, table, lo, hi=None, add0=None, add1=None):
+        """Add per-key values to the planes of existing keys; returns #missing."""
+        n = int(lo.shape[0])
+        if not n:
+            return 0
+        miss = self.zeros(1, self.torch.int64)
+        self._check(self.lib.kdf_add_planes(
+            table.handle, lo.data_ptr(), hi.data_ptr() if hi is not None else None, n,
+            add0.data_ptr() if add0 is not None else None,
+            add1.data_ptr() if add1 is not None else None, miss.data_ptr(), self.stream_ptr()))
+        self.launches += 1
+        return int(miss.item())
 
     def check_not_full(self, stats):
         if self.read_stats(stats)["full"]:

@@ -1,0 +1,91 @@
+"""CPU tests of the product's host-side post-processing (cluster, annotate,
+classify, writers) fed with the oracle's read hits, against the goldens."""
+import json
+import os
+
+from kmer_denovo_filter_b200.discovery import pipeline as P
+from kmer_denovo_filter_b200.discovery import summary as S
+from oracle import discovery, kmers
+
+
+def test_cluster_annotate_write_match_golden(giab_paths, giab_records, oracle_discovery, tmp_path):
+    r = oracle_discovery
+    a = discovery.anchor(giab_records["child"], 31, r["proband_unique"], 7)
+    hits = [(c, s, e, q, {kmers.kmer_of(x, 31) for x in ks}, supp)
+            for c, s, e, q, ks, supp in a["read_hits"]]
+    regions, rreads, rkmers = P._cluster_hits(list(hits), 500)
+    ann, links = P._annotate_and_link_from_metadata(regions, rreads, a["read_sv_meta"])
+    P._classify_regions(regions, ann, links)
+    gold = giab_paths["expected_discovery"]
+    bed = str(tmp_path / "o.bed")
+    P._write_bed(regions, rreads, rkmers, bed, ann,
+                 {"min_distinct_kmers_per_read": 7, "min_supporting_reads": 1,
+                  "min_distinct_kmers": 1})
+    assert open(bed).read() == open(os.path.join(gold, "giab_discovery.bed")).read()
+    bg = str(tmp_path / "o.bedgraph")
+    P._write_bedgraph(a["kmer_coverage"], bg, a["read_coverage"], 3)
+    assert open(bg).read() == open(os.path.join(gold, "giab_discovery.kmer_coverage.bedgraph")).read()
+    rc = str(tmp_path / "o.rc.bed")
+    P._write_read_coverage_bed(a["kmer_coverage"], a["read_coverage"], rc, 3)
+    assert open(rc).read() == open(os.path.join(gold, "giab_discovery.read_coverage.bed")).read()
+    pe = str(tmp_path / "o.bedpe")
+    P._write_bedpe(links, pe)
+    assert open(pe).read() == open(os.path.join(gold, "giab_discovery.sv.bedpe")).read()
+    metrics = json.load(open(os.path.join(gold, "giab_discovery.metrics.json")))
+    comp = P._compare_candidates_to_regions(
+        P._parse_candidate_summary(os.path.join(giab_paths["expected_vcf"], "summary.txt")), regions)
+    dnm = P._evaluate_dnm_regions(regions, metrics["regions"])
+    assert dnm == metrics["dnm_evaluation"]["loci"]
+    assert [c["captured"] for c in comp] == [True, True, True]
+    text = S._write_discovery_summary(str(tmp_path / "s.txt"), regions, rreads, rkmers, metrics,
+                                      comp, ann, dnm)
+    assert text == open(os.path.join(gold, "giab_discovery.summary.txt")).read()
+
+
+def test_kmer_ref_positions_with_insertion():
+    """reference tests/discovery/test_pipeline.py:1383-1439 (insertion splits coverage)."""
+    class R:
+        reference_start = 100
+        cigartuples = [(0, 10), (1, 3), (0, 10)]
+    cov = P._collect_kmer_ref_positions(R, [8], 5)      # q 8..12: 8,9 aligned; 10..12 inserted
+    assert dict(cov) == {108: 1, 109: 1}
+    cov = P._collect_kmer_ref_positions(R, [0, 1], 5)
+    assert dict(cov) == {100: 1, 101: 2, 102: 2, 103: 2, 104: 2, 105: 1}
+    assert dict(P._collect_kmer_ref_positions(R, [], 5)) == {}
+
+
+def test_sv_linking_and_classes():
+    regions = [("chr1", 100, 300), ("chr1", 5000, 5200), ("chr2", 10, 90)]
+    rreads = {regions[0]: {"a", "b"}, regions[1]: {"a"}, regions[2]: {"c"}}
+    meta = {
+        ("a", False): {"has_sa": True, "sa_str": "chr2,50,+,50M,60,0;", "is_paired": True,
+                       "is_proper_pair": False, "mate_is_unmapped": False, "max_clip": 40},
+        ("a", True): {"has_sa": True, "sa_str": None, "is_paired": True, "is_proper_pair": False,
+                      "mate_is_unmapped": False, "max_clip": 10},
+        ("b", False): {"has_sa": False, "sa_str": None, "is_paired": True, "is_proper_pair": True,
+                       "mate_is_unmapped": True, "max_clip": 0},
+        ("c", False): {"has_sa": False, "sa_str": None, "is_paired": False, "is_proper_pair": False,
+                       "mate_is_unmapped": False, "max_clip": 3},
+    }
+    ann, links = P._annotate_and_link_from_metadata(regions, rreads, meta)
+    assert ann[regions[0]] == {"split_reads": 1, "discordant_pairs": 2, "max_clip_len": 40,
+                               "unmapped_mates": 1}
+    pairs = [(l["region_a"], l["region_b"], l["sv_type_hint"]) for l in links]
+    assert (regions[0], regions[1], "INTRA") in pairs and (regions[0], regions[2], "BND") in pairs
+    P._classify_regions(regions, ann, links)
+    assert [ann[r]["class"] for r in regions] == ["SV", "SV", "SV"]
+    ann2, links2 = P._annotate_and_link_from_metadata([regions[2]], {regions[2]: {"c"}}, meta)
+    P._classify_regions([regions[2]], ann2, links2)
+    assert ann2[regions[2]]["class"] == "SMALL"
+
+
+def test_cli_defaults_match_reference():
+    from kmer_denovo_filter_b200 import cli
+    a = cli.parse_discovery_args(["--child", "c", "--mother", "m", "--father", "f",
+                                  "--out-prefix", "o"])
+    assert (a.kmer_size, a.min_child_count, a.cluster_distance, a.min_supporting_reads,
+            a.min_distinct_kmers, a.min_bedgraph_reads, a.parent_max_count, a.threads,
+            a.min_distinct_kmers_per_read, a.min_baseq) == (31, 3, 500, 1, 1, 3, 0, 4, None, 20)
+    v = cli.parse_vcf_args(["--child", "c", "--mother", "m", "--father", "f", "--vcf", "v",
+                            "--output", "o"])
+    assert (v.kmer_size, v.min_mapq, v.min_baseq, v.proband_id) == (31, 20, 20, None)
