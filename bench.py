@@ -1,0 +1,451 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the trio discovery k-mer path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm
+
+A step is one pass of the whole k-mer hot path over one synthetic trio
+(BASELINE.json config "synthetic chr20-scale (64 Mbp) 30x trio ... 1 B200"):
+child count -> threshold -> reference subtraction -> mother / father filtered
+counts -> proband-unique set -> per-read distinct-hit scan.  The metric is
+canonical k-mer instances counted + queried per second, summed over stages.
+At N > 1 every rank holds 1/N of each sample's reads of an N x 64 Mbp genome
+(weak scaling); the child table is partitioned by hash range and k-mers are
+routed to their owner with an NCCL all-to-all.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "canonical k-mers/s counted+queried (trio discovery k-mer path)"
+UNIT = "k-mers/s"
+# algorithmic bytes per k-mer instance (SURVEY §8d / DESIGN.md "Roofline")
+ALGO_BYTES = {
+    # insert+count: key read + count read + count write, plus the packed input
+    ("count", 1): 16.0, ("count", 2): 24.0,
+    # update-if-present, miss: key read
+    ("probe", 1): 8.0, ("probe", 2): 16.0,
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--k", type=int, default=31)
+    ap.add_argument("--genome-mbp", type=float, default=64.0, help="genome size per GPU (Mbp)")
+    ap.add_argument("--depth", type=float, default=30.0)
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--denovo", type=int, default=100)
+    ap.add_argument("--cpu-sample-mbp", type=float, default=8.0,
+                    help="genome size of the bounded CPU sample (same depth)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-random-bench", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region
+    (B200_PROFILING.md "clocks DURING the timed region")."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            try:
+                self.proc.kill()
+            except Exception:
+                pass
+        self.fh.close()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                    pw.append(float(f[3]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "power_w_max": float(max(pw)), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def stream_to_host(torch, s, pin):
+    """Device packed-stream dict -> HostStream on (pinned) host memory."""
+    from kmer_denovo_filter_b200 import engine
+
+    def h(t):
+        c = torch.empty(t.shape, dtype=t.dtype, pin_memory=pin)
+        c.copy_(t)
+        return c
+    keep = [h(s["codes"]), h(s["valid"]), h(s["read_starts"]), h(s["read_lens"])]
+    hs = engine.HostStream(keep[0].numpy().view(np.uint64), keep[1].numpy().view(np.uint32),
+                           s["n_bases"], keep[2].numpy().view(np.uint64),
+                           keep[3].numpy().view(np.uint32))
+    hs_bytes = sum(t.numel() * t.element_size() for t in keep)
+    return hs, keep, hs_bytes
+
+
+def to_device_stream(engine_mod, s):
+    return engine_mod.DeviceStream(s["codes"], s["valid"], s["n_bases"], s["read_starts"],
+                                   s["read_lens"])
+
+
+def make_host_sample(torch, genome_bp, depth, read_len, denovo):
+    """The bounded CPU sample: same generator, smaller genome, host numpy."""
+    from kmer_denovo_filter_b200 import synth
+    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() \
+        else torch.device("cpu")
+    trio = synth.make_trio(torch, dev, int(genome_bp), depth=depth, read_len=read_len,
+                           n_denovo=denovo)
+    out = {}
+    for who in ("child", "mother", "father", "ref"):
+        s = trio[who]
+        out[who] = (s["codes"].cpu().numpy().view(np.uint64), s["valid"].cpu().numpy().view(np.uint32),
+                    s["n_bases"], s["read_starts"].cpu().numpy().view(np.uint64),
+                    s["read_lens"].cpu().numpy().view(np.uint32))
+    del trio
+    if torch.cuda.is_available():
+        torch.cuda.empty_cache()
+    return out
+
+
+def cpu_chain(sample, k, threads):
+    """One pass of the CPU restatement (oracle C twin) over the sample."""
+    from oracle import ckdf
+    t0 = time.perf_counter()
+    res = ckdf.discovery_chain(sample["child"], sample["mother"][:3], sample["father"][:3],
+                               sample["ref"][:3], k, threads=threads,
+                               child_capacity=max(int(sample["child"][2]) // 4, 1024))
+    dt = time.perf_counter() - t0
+    return res, dt
+
+
+def sample_text(args):
+    return ("1 pass of the same chain over a synthetic trio of a %.0f Mbp genome at %gx "
+            "(same generator, read length, error/variant rates; %.3g of the GPU step's k-mers)"
+            % (args.cpu_sample_mbp, args.depth, args.cpu_sample_mbp / args.genome_mbp))
+
+
+# --------------------------------------------------------------------------
+# reference arm: the CPU restatement of the Jellyfish path, all host cores
+# --------------------------------------------------------------------------
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    from oracle import ckdf
+    threads = ckdf.max_threads()
+    sample = make_host_sample(torch, args.cpu_sample_mbp * 1e6, args.depth, args.read_len,
+                              min(args.denovo, 100))
+    for _ in range(args.warmup):
+        cpu_chain(sample, args.k, threads)
+    units, total = 0, 0.0
+    for _ in range(args.steps):
+        res, dt = cpu_chain(sample, args.k, threads)
+        units += res["units"]
+        total += dt
+    value = units / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64" if args.k <= 32 else "u128", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": sample_text(args),
+                         "note": "jellyfish/samtools/pysam are absent from this image; this is "
+                                 "the C/OpenMP restatement of the Jellyfish path (oracle/kdf_oracle.c)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "stage_sizes": {x: int(res[x]) for x in ("candidates", "non_ref", "after_mother",
+                                                  "proband_unique")},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, world):
+    return {
+        "workload": "synthetic trio, %g Mbp genome per GPU, %gx, 2x%d bp reads, %d de novo "
+                    "events, discovery k-mer chain (child count, ref subtraction, 2 parent "
+                    "count --if passes, per-read scan)" % (args.genome_mbp, args.depth,
+                                                           args.read_len, args.denovo),
+        "k": args.k, "min_child_count": 3, "parent_max_count": 0,
+        "genome_bp_total": int(args.genome_mbp * 1e6) * world,
+        "table": "hash-partitioned across %d GPU(s)" % world if world > 1 else "single GPU",
+        "l2_policy": "inputs (0.7 GB per sample) and the child table (GBs) are larger than L2; no flush",
+    }
+
+
+# --------------------------------------------------------------------------
+# this repo's arm
+# --------------------------------------------------------------------------
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from kmer_denovo_filter_b200 import engine, synth
+    from kmer_denovo_filter_b200.discovery import kmer_chain
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = engine.CudaEngine(dev)   # raises if the library or a GPU is missing: no fallback
+
+    # ---- synthetic trio, resident in HBM ---------------------------------
+    genome_bp = int(args.genome_mbp * 1e6) * world
+    trio = synth.make_trio(torch, dev, genome_bp, depth=args.depth, read_len=args.read_len,
+                           n_denovo=args.denovo, rank=rank, world=world)
+    d = {w: to_device_stream(engine, trio[w]) for w in ("child", "mother", "father", "ref")}
+    torch.cuda.synchronize()
+
+    if world > 1:
+        from kmer_denovo_filter_b200.discovery import kmer_chain_dist
+        def step(streams):
+            return kmer_chain_dist.discover_streams_dist(
+                eng, streams["child"], streams["mother"], streams["father"], streams["ref"],
+                args.k, fetch=True)
+    else:
+        def step(streams):
+            return kmer_chain.discover_streams(
+                eng, streams["child"], streams["mother"], streams["father"], streams["ref"],
+                args.k, fetch=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_region(streams, n_steps):
+        """-> (device ms max over ranks, units summed over ranks, last result)."""
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        units = 0
+        res = None
+        for _ in range(n_steps):
+            res = step(streams)
+            units += res["units"]
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            u = torch.tensor([units], dtype=torch.int64, device=dev)
+            dist.all_reduce(u, op=dist.ReduceOp.SUM)
+            units = int(u.item())
+        return ms, units, res
+
+    # ---- device-resident: warm-up, then K timed steps ---------------------
+    for _ in range(args.warmup):
+        step(d)
+    eng.timers = {}
+    launches0 = eng.launches
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms, units, res = timed_region(d, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    launches = eng.launches - launches0
+    ktimes = eng.kernel_times_ms()
+    eng.timers = None
+    value = units / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel ---------------------------------
+    kw = 1 if args.k <= 32 else 2
+    per_kernel = {n: {"launches": len(v), "ms_total": float(sum(v)), "ms_avg": float(np.mean(v))}
+                  for n, v in ktimes.items()}
+    dom = max(per_kernel, key=lambda n: per_kernel[n]["ms_total"]) if per_kernel else None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline = None
+    if dom is not None:
+        child_windows = res.get("child_windows") or 0
+        if not child_windows:
+            L = args.read_len
+            child_windows = int(d["child"].n_reads * (L - args.k + 1) * (1 - 1e-4) ** args.k)
+        in_bytes = args.read_len / (4.0 * (args.read_len - args.k + 1))
+        if dom.startswith("count_stream/mode0") or dom.startswith("insert"):
+            per_unit = ALGO_BYTES[("count", kw)] + in_bytes
+        else:
+            per_unit = ALGO_BYTES[("probe", kw)] + in_bytes
+        units_per_launch = res.get("dominant_units_per_launch") or child_windows
+        achieved = units_per_launch * per_unit / (per_kernel[dom]["ms_avg"] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
+                    "algorithmic_bytes_per_kmer": per_unit,
+                    "kmers_per_launch": int(units_per_launch),
+                    "kernel_ms_avg": per_kernel[dom]["ms_avg"],
+                    "kernel_share_of_step": per_kernel[dom]["ms_total"] / ms,
+                    "traffic": None}
+        prof = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+        if os.path.isfile(prof):
+            try:
+                roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+
+    # ---- sector-granular random-access roofline (same box, same run) ------
+    random_access = None
+    if rank == 0 and not args.no_random_bench:
+        buf = torch.zeros(1 << 30, dtype=torch.int64, device=dev)   # 8 GiB
+        n_ops = 1 << 28
+        random_access = {}
+        for name, atomic in (("gather32", 0), ("gather32_atomic", 1)):
+            eng.bench_random_access(buf, n_ops, atomic)
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.bench_random_access(buf, n_ops, atomic)
+            e1.record()
+            torch.cuda.synchronize()
+            t = e0.elapsed_time(e1) * 1e-3
+            random_access[name] = {"gops": n_ops / t / 1e9,
+                                   "sector_gbs": n_ops * (64 if atomic else 32) / t / 1e9}
+        del buf
+        if roofline is not None:
+            is_count = roofline["kernel"].startswith(("count_stream/mode0", "insert"))
+            ref_ops = random_access["gather32_atomic" if is_count else "gather32"]["gops"] * 1e9
+            kps = roofline["kmers_per_launch"] / (roofline["kernel_ms_avg"] * 1e-3)
+            roofline["random_fraction"] = kps / ref_ops
+            roofline["random_fraction_note"] = (
+                "k-mers/s of the dominant kernel / ops/s of uniformly random 32 B sector "
+                "%s over 8 GiB measured in this run" % ("read + atomic add" if is_count else "reads"))
+    if world > 1:
+        dist.barrier()
+
+    # ---- end to end: host buffers, H2D + D2H inside the timed region ------
+    e2e = None
+    if not args.no_e2e:
+        hosts, keep, h2d = {}, [], 0
+        for w in ("child", "mother", "father", "ref"):
+            hs, kp, nb = stream_to_host(torch, trio[w], pin=True)
+            hosts[w] = hs
+            keep.append(kp)
+            if w == "child":
+                h2d += nb
+            else:
+                h2d += hs.codes.nbytes + hs.valid.nbytes
+        del d
+        del trio
+        torch.cuda.empty_cache()
+        step(hosts)
+        ems, eunits, eres = timed_region(hosts, args.steps)
+        d2h = 0
+        if eres["ndistinct"] is not None:
+            d2h += eres["ndistinct"].nbytes + eres["nhits"].nbytes
+        d2h += 8 * 6 + 32   # stage counters and stats read back per step
+        e2e = {"value": eunits / (ems * 1e-3), "unit": UNIT, "ms_per_step": ems / args.steps,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "api": "kmer_denovo_filter_b200.discovery.kmer_chain.discover_streams(HostStream...) "
+                      "-> libkdf_sm100 C ABI; pinned host buffers"}
+
+    # ---- CPU baseline (rank 0, N = 1 only) -------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import ckdf
+        threads = ckdf.max_threads()
+        sample = make_host_sample(torch, args.cpu_sample_mbp * 1e6, args.depth, args.read_len,
+                                  min(args.denovo, 100))
+        cres, dt = cpu_chain(sample, args.k, threads)
+        cpu = {"value": cres["units"] / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "seconds": dt, "sample": sample_text(args)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64" if args.k <= 32 else "u128", "data": "synthetic",
+            "config": workload_config(args, world),
+            "units_per_step": units // args.steps,
+            "stage_sizes": {x: int(res[x]) for x in ("candidates", "non_ref", "after_mother",
+                                                      "proband_unique", "informative_reads")},
+            "roofline": roofline, "kernels": per_kernel, "random_access": random_access,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+            "device": eng.props["name"],
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -266,8 +266,29 @@ class CudaEngine:
                       "l2_bytes": props.l2_bytes, "hbm_bytes": props.hbm_bytes,
                       "name": props.name.decode()}
         self.launches = 0  # kernels launched through this engine (bench.py gpu_launches)
+        # name -> [(start event, end event)] when per-kernel timing is switched on
+        # (bench.py roofline: CUDA events on the launching stream); None = off
+        self.timers = None
 
     # -- plumbing ----------------------------------------------------------
+    def _t0(self):
+        if self.timers is None:
+            return None
+        ev = self.torch.cuda.Event(enable_timing=True)
+        ev.record(self.torch.cuda.current_stream(self.device))
+        return ev
+
+    def _t1(self, name, ev0):
+        if ev0 is None:
+            return
+        ev1 = self.torch.cuda.Event(enable_timing=True)
+        ev1.record(self.torch.cuda.current_stream(self.device))
+        self.timers.setdefault(name, []).append((ev0, ev1))
+
+    def kernel_times_ms(self):
+        """name -> list of launch durations (ms); call after a synchronize."""
+        return {n: [a.elapsed_time(b) for a, b in evs] for n, evs in (self.timers or {}).items()}
+
     def _check(self, rc):
         if rc != KDF_OK:
             raise KdfError("libkdf error %d: %s" % (rc, self.lib.kdf_last_error().decode()))
@@ -334,7 +355,10 @@ class CudaEngine:
         if capacity is None:
             capacity = self.capacity_for(n_keys or 0)
         self.launches += 1
-        return KmerTable(self, k, capacity)
+        ev = self._t0()
+        t = KmerTable(self, k, capacity)
+        self._t1("table_clear", ev)
+        return t
 
     def clear_plane(self, table, plane):
         self._check(self.lib.kdf_table_clear_plane(table.handle, plane, self.stream_ptr()))
@@ -359,9 +383,11 @@ class CudaEngine:
 
     def count_stream(self, table, ds, mode=MODE_INSERT_COUNT, plane=0, arg=1, stats=None):
         """K1+K2 fused."""
+        ev = self._t0()
         self._check(self.lib.kdf_count_stream(
             table.handle, ds.c(), mode, plane, arg,
             stats.data_ptr() if stats is not None else None, self.stream_ptr()))
+        self._t1("count_stream/mode%d/kw%d" % (mode, table.key_words), ev)
         self.launches += 1
 
     def update_keys(self, table, lo, hi=None, mode=MODE_INSERT_ONLY, plane=0, arg=1, stats=None):
@@ -392,9 +418,11 @@ class CudaEngine:
 
     def threshold_count(self, table, min0=0, max0=U32_MAX, min1=0, max1=U32_MAX):
         n_out = self.zeros(1, self.torch.int64)
+        ev = self._t0()
         self._check(self.lib.kdf_threshold_compact(
             table.handle, min0, max0, min1, max1, None, None, None, None, 0,
             n_out.data_ptr(), self.stream_ptr()))
+        self._t1("threshold_compact", ev)
         self.launches += 1
         return int(n_out.item())
 
@@ -409,12 +437,14 @@ class CudaEngine:
         p0 = self.empty(cap, torch.int32) if want_planes else None
         p1 = self.empty(cap, torch.int32) if want_planes else None
         n_out = self.zeros(1, torch.int64)
+        ev = self._t0()
         self._check(self.lib.kdf_threshold_compact(
             table.handle, min0, max0, min1, max1, lo.data_ptr(),
             hi.data_ptr() if hi is not None else None,
             p0.data_ptr() if p0 is not None else None,
             p1.data_ptr() if p1 is not None else None,
             cap, n_out.data_ptr(), self.stream_ptr()))
+        self._t1("threshold_compact", ev)
         self.launches += 1
         got = int(n_out.item())
         if got > cap:
@@ -453,6 +483,7 @@ class CudaEngine:
             if stats is not None:
                 st = self.zeros(N_STATS, torch.int64)
             if n_reads:
+                ev = self._t0()
                 self._check(self.lib.kdf_scan_reads(
                     table.handle, ds.c(), ds.read_starts.data_ptr(), ds.read_lens.data_ptr(),
                     n_reads, min_distinct, nd.data_ptr(), nh.data_ptr(),
@@ -460,6 +491,7 @@ class CudaEngine:
                     hsl.data_ptr() if hsl is not None else None,
                     hit_cap if want_hits else 0, n_hits.data_ptr(),
                     st.data_ptr() if st is not None else None, self.stream_ptr()))
+                self._t1("scan_reads/kw%d" % table.key_words, ev)
                 self.launches += 1
             total = int(n_hits.item())
             if not want_hits or total <= hit_cap:
