@@ -33,11 +33,24 @@ METRIC = "canonical k-mers/s counted+queried (trio discovery k-mer path)"
 UNIT = "k-mers/s"
 # algorithmic bytes per k-mer instance (SURVEY §8d / DESIGN.md "Roofline")
 ALGO_BYTES = {
-    # insert+count: key read + count read + count write, plus the packed input
+    # insert+count: key read + count read + count write
     ("count", 1): 16.0, ("count", 2): 24.0,
-    # update-if-present, miss: key read
+    # update-if-present / membership, miss: key read
     ("probe", 1): 8.0, ("probe", 2): 16.0,
+    # hash-range binning: key written once
+    ("bin", 1): 8.0, ("bin", 2): 16.0,
 }
+
+
+def kernel_class(name):
+    """(class, reads the packed stream?) of a timed kernel name."""
+    if name.startswith(("count_stream/mode0", "count_stream/mode1")):
+        return "count", True
+    if name.startswith("count_bins"):
+        return "count", False
+    if name.startswith("bin_stream"):
+        return "bin", True
+    return "probe", True
 
 
 def parse_args():
@@ -271,12 +284,12 @@ def main():
         def step(streams):
             return kmer_chain_dist.discover_streams_dist(
                 eng, streams["child"], streams["mother"], streams["father"], streams["ref"],
-                args.k, fetch=True)
+                args.k, fetch=False)
     else:
         def step(streams):
             return kmer_chain.discover_streams(
                 eng, streams["child"], streams["mother"], streams["father"], streams["ref"],
-                args.k, fetch=True)
+                args.k, fetch=False)
 
     def barrier():
         if world > 1:
@@ -339,10 +352,8 @@ def main():
             L = args.read_len
             child_windows = int(d["child"].n_reads * (L - args.k + 1) * (1 - 1e-4) ** args.k)
         in_bytes = args.read_len / (4.0 * (args.read_len - args.k + 1))
-        if dom.startswith("count_stream/mode0") or dom.startswith("insert"):
-            per_unit = ALGO_BYTES[("count", kw)] + in_bytes
-        else:
-            per_unit = ALGO_BYTES[("probe", kw)] + in_bytes
+        kclass, reads_stream = kernel_class(dom)
+        per_unit = ALGO_BYTES[(kclass, kw)] + (in_bytes if reads_stream else 0.0)
         units_per_launch = res.get("dominant_units_per_launch") or child_windows
         achieved = units_per_launch * per_unit / (per_kernel[dom]["ms_avg"] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
@@ -380,7 +391,7 @@ def main():
                                    "sector_gbs": n_ops * (64 if atomic else 32) / t / 1e9}
         del buf
         if roofline is not None:
-            is_count = roofline["kernel"].startswith(("count_stream/mode0", "insert"))
+            is_count = kernel_class(roofline["kernel"])[0] == "count"
             ref_ops = random_access["gather32_atomic" if is_count else "gather32"]["gops"] * 1e9
             kps = roofline["kmers_per_launch"] / (roofline["kernel_ms_avg"] * 1e-3)
             roofline["random_fraction"] = kps / ref_ops
@@ -408,9 +419,11 @@ def main():
         step(hosts)
         ems, eunits, eres = timed_region(hosts, args.steps)
         d2h = 0
-        if eres["ndistinct"] is not None:
-            d2h += eres["ndistinct"].nbytes + eres["nhits"].nbytes
-        d2h += 8 * 6 + 32   # stage counters and stats read back per step
+        if eres.get("reads") is not None:     # sparse per-read records + sorted hits
+            d2h += sum(int(a.nbytes) for a in eres["reads"].values())
+        elif eres["ndistinct"] is not None:
+            d2h += 8 * int(eres["ndistinct"].shape[0])
+        d2h += 8 * 16 + 4 * 32   # stage counters, bin cursors' flags and stats read back per step
         e2e = {"value": eunits / (ems * 1e-3), "unit": UNIT, "ms_per_step": ems / args.steps,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "api": "kmer_denovo_filter_b200.discovery.kmer_chain.discover_streams(HostStream...) "

@@ -28,13 +28,16 @@
  *   Both arrays hold n_words = ceil(n_bases/32) words; bits past n_bases must
  *   be 0.  A window (k-mer) starting at p is counted iff valid[p..p+k) are all 1.
  *
- *   Table: open addressing, linear probing, any capacity >= 2.
- *     key_words == 1 (k <= 32): 16-byte slots {u64 key; u32 plane0; u32 plane1}
- *     key_words == 2 (k <= 64): 32-byte slots {u64 lo; u64 hi; u32 plane0;
- *                                u32 plane1; u64 pad}
- *   Empty slots hold all-ones key words (never a canonical k-mer).
- *   plane0 / plane1 are two independent u32 value planes (child count, parent
- *   count, reference flag ...).
+ *   Table: open addressing over 32-byte buckets, linear probing by bucket; the
+ *   caller provides one 32-byte-aligned device buffer of kdf_table_bytes():
+ *     keys  : capacity slots of key_words u64 each (k <= 32: 4 keys per bucket;
+ *             k <= 64: 2 {lo, hi} keys per bucket); empty = all-ones words
+ *             (never a canonical k-mer); a probe reads one whole bucket;
+ *     plane0: u32[capacity], plane1: u32[capacity] — two independent value
+ *             planes (child count, parent count, reference flag ...), touched
+ *             only when a key is found.
+ *   capacity must be a multiple of 4.  Read-only tables whose keys fit in
+ *   160 KB are copied to shared memory by the stream kernels.
  */
 #ifndef KDF_H_
 #define KDF_H_
@@ -46,7 +49,7 @@
 extern "C" {
 #endif
 
-#define KDF_VERSION 1
+#define KDF_VERSION 2
 
 /* status codes */
 #define KDF_OK 0
@@ -197,18 +200,71 @@ int kdf_scan_reads(const kdf_table* t, const kdf_stream* s,
                    uint64_t hit_cap, uint64_t* n_hits /*DEV*/,
                    uint64_t* stats /*DEV*/, void* stream);
 
-/* ---- K6: owner binning in front of the all-to-all -----------------------
- * owner(key) = mix64(key) % n_ranks (independent of the slot index bits).
- * Pass 1 (out_lo == NULL): histogram of valid windows per owner into
- * counts[n_ranks] (DEV u64, caller zeroes).  Pass 2: scatter canonical keys to
- * out_lo/out_hi at bin_offsets[owner] + running cursor (cursors: DEV u64
- * [n_ranks], caller zeroes).  No reference analogue (single-host Jellyfish).  */
-int kdf_partition_stream(const kdf_stream* s, int k, int n_ranks,
-                         uint64_t* counts /*DEV*/,
-                         const uint64_t* bin_offsets /*DEV or NULL*/,
-                         uint64_t* cursors /*DEV or NULL*/,
-                         uint64_t* out_lo /*DEV or NULL*/,
-                         uint64_t* out_hi /*DEV or NULL*/, void* stream);
+/* ---- K4+K5, sparse form: emit hits, then reduce per read -----------------
+ * kdf_scan_stream_hits appends (stream position, slot) of every window whose
+ * canonical k-mer is in the table (unordered; *n_hits counts all, entries
+ * beyond hit_cap are dropped).  kdf_reduce_hits sorts the hits by position and
+ * writes one record per read that has hits: read index, number of distinct
+ * k-mers hit, number of hit windows, index of its first hit in the sorted
+ * arrays (core/bam_scanner.py:434-443).  Records are unordered.  Scratch:
+ * kdf_reduce_hits_scratch_bytes(n_hits) device bytes.  sorted_pos_out /
+ * sorted_slot_out (n_hits entries) may be NULL.                              */
+int kdf_scan_stream_hits(const kdf_table* t, const kdf_stream* s,
+                         uint64_t* hit_pos /*DEV*/, uint32_t* hit_slot /*DEV*/,
+                         uint64_t hit_cap, uint64_t* n_hits /*DEV*/,
+                         uint64_t* stats /*DEV*/, void* stream);
+size_t kdf_reduce_hits_scratch_bytes(uint64_t n_hits);
+int kdf_reduce_hits(const uint64_t* hit_pos /*DEV*/, const uint32_t* hit_slot /*DEV*/,
+                    uint64_t n_hits, const uint64_t* read_starts /*DEV, ascending*/,
+                    uint64_t n_reads, void* scratch /*DEV*/, size_t scratch_bytes,
+                    uint64_t* sorted_pos_out /*DEV*/, uint32_t* sorted_slot_out /*DEV*/,
+                    uint64_t* rec_read /*DEV*/, uint32_t* rec_ndistinct /*DEV*/,
+                    uint32_t* rec_nhits /*DEV*/, uint64_t* rec_first /*DEV*/,
+                    uint64_t* n_recs /*DEV, caller zeroes*/, void* stream);
+
+/* ---- K2p / K6: binning of canonical k-mers ---------------------------------
+ * Bins are fixed-capacity regions of `bins`: bin b holds keys
+ * [b*bin_cap, b*bin_cap + min(cursors[b], bin_cap)) (u64 keys for k <= 32,
+ * {lo, hi} pairs for k <= 64).  cursors (DEV u64[n_parts]) and *overflow (DEV
+ * u64) are zeroed by the caller once and accumulate over calls, so several
+ * streams can be appended.  A key that does not fit sets *overflow != 0 and is
+ * dropped: the caller must check it and retry with larger bins.
+ *   by_owner == 0 : bin = hash range (top log2(n_parts) bits of the bucket
+ *                   hash; n_parts a power of two <= 256) — input of
+ *                   kdf_count_bins; replaces nothing in the reference, it is
+ *                   how `jellyfish count` (discovery/pipeline.py:114-122) is
+ *                   kept out of DRAM-random-access territory on the GPU;
+ *   by_owner == 1 : bin = owner rank of a multi-GPU run (any n_parts <= 256),
+ *                   in front of the all-to-all.                              */
+int kdf_bin_stream(const kdf_stream* s, int k, int by_owner, int n_parts,
+                   uint64_t* bins /*DEV*/, uint64_t bin_cap, uint64_t* cursors /*DEV*/,
+                   uint64_t* overflow /*DEV*/, uint64_t* stats /*DEV or NULL*/, void* stream);
+int kdf_bin_keys(const uint64_t* lo /*DEV*/, const uint64_t* hi /*DEV or NULL*/, uint64_t n,
+                 int k, int by_owner, int n_parts, uint64_t* bins /*DEV*/, uint64_t bin_cap,
+                 uint64_t* cursors /*DEV*/, uint64_t* overflow /*DEV*/, void* stream);
+
+/* Count every hash-range bin in an L2-resident table slice and emit.
+ * For each bin p: clear `slice` (a table of slice_capacity slots in caller
+ * memory of kdf_table_bytes(slice_capacity, key_words)); insert+count the child
+ * keys of bin p into plane 0; OR 1 into plane 1 for every reference key of bin
+ * p that is present (ref_bins may be NULL); then emit, exactly as
+ * kdf_threshold_compact does, the slots with min0 <= plane0 <= max0 and
+ * min1 <= plane1 <= max1.  This is `jellyfish count -C` + `dump -c -L` +
+ * `query ref.jf` (discovery/pipeline.py:114-122, :207-211, :286-304) in one
+ * call whose table never leaves L2.
+ * counters: DEV u64[6], caller zeroes: [0] keys applied, [1] != 0 slice full
+ * (results invalid: retry with a larger slice), [2] instances that found their
+ * key, [3] distinct keys, [4] keys with plane0 >= count_min0, [5] occupied
+ * slots seen by the emit pass.  n_out as in kdf_threshold_compact.           */
+int kdf_count_bins(int k, int n_parts, const uint64_t* child_bins /*DEV*/,
+                   uint64_t child_bin_cap, const uint64_t* child_cursors /*DEV*/,
+                   const uint64_t* ref_bins /*DEV or NULL*/, uint64_t ref_bin_cap,
+                   const uint64_t* ref_cursors /*DEV or NULL*/, void* slice /*DEV*/,
+                   uint64_t slice_capacity, uint32_t min0, uint32_t max0, uint32_t min1,
+                   uint32_t max1, uint64_t* out_lo /*DEV*/, uint64_t* out_hi /*DEV*/,
+                   uint32_t* out_p0 /*DEV*/, uint32_t* out_p1 /*DEV*/, uint64_t out_cap,
+                   uint64_t* n_out /*DEV*/, uint32_t count_min0, uint64_t* counters /*DEV*/,
+                   void* stream);
 
 /* ---- host helpers (CPU, no device) --------------------------------------
  * Pack ASCII sequences into the stream layout.  seqs: concatenated bytes,
@@ -278,6 +334,12 @@ const char* kdf_host_last_error(void);
 int kdf_debug_extract_host(const uint64_t* codes, const uint32_t* valid,
                            uint64_t n_bases, int k, int use_random_access,
                            uint64_t* out_lo, uint64_t* out_hi, uint8_t* out_ok);
+
+/* Test hook: the device hash functions on the host (partition, bucket and
+ * owner of each key); any output may be NULL.                               */
+int kdf_debug_hash_host(const uint64_t* lo, const uint64_t* hi, uint64_t n, int key_words,
+                        int log2_parts, uint32_t n_buckets, uint32_t n_ranks,
+                        uint32_t* out_part, uint32_t* out_bucket, uint32_t* out_owner);
 
 /* Random-access microbenchmark used for the "HBM random-access roofline"
  * (SURVEY §8d): n_ops uniformly random 32-byte sector reads (atomic == 0) or

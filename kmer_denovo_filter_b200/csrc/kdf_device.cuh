@@ -36,20 +36,53 @@ template <> struct Key<2> {
   KDF_HD bool operator==(const Key& o) const { return lo == o.lo && hi == o.hi; }
 };
 
-struct __align__(16) Slot1 {
-  u64 key;
-  u32 p0, p1;
-};
-struct __align__(32) Slot2 {
-  u64 lo, hi;
-  u32 p0, p1;
-  u64 pad;
-};
-template <int KW> struct SlotOf;
-template <> struct SlotOf<1> { typedef Slot1 type; };
-template <> struct SlotOf<2> { typedef Slot2 type; };
-
 // ------------------------------------------------------------- hashing ----
+// One 64-bit multiply per key.  The high 32 bits of the product select the
+// table partition (top bits) and the bucket; the low 32 bits select the owner
+// rank of a multi-GPU run, so owner and bucket are decorrelated.
+static constexpr u64 HASH_MUL = 0x9E3779B97F4A7C15ULL;
+static constexpr u64 HASH_MUL_HI = 0xD6E8FEB86659FD93ULL;
+
+KDF_HD u64 hash_key(const Key<1>& k) {
+  u64 x = k.lo ^ (k.lo >> 32);
+  return x * HASH_MUL;
+}
+KDF_HD u64 hash_key(const Key<2>& k) {
+  u64 y = k.lo ^ (k.hi * HASH_MUL_HI);
+  y ^= y >> 32;
+  return y * HASH_MUL;
+}
+KDF_HD u32 mulhi32(u32 a, u32 b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (u32)(((u64)a * (u64)b) >> 32);
+#endif
+}
+KDF_HD u64 mulhi64(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+  return __umul64hi(a, b);
+#else
+  return (u64)(((unsigned __int128)a * (unsigned __int128)b) >> 64);
+#endif
+}
+// partition of a key among 2^log2_parts hash ranges (0 when log2_parts == 0)
+KDF_HD u32 part_of(u64 h, int log2_parts) {
+  return log2_parts ? (u32)(h >> 32) >> (32 - log2_parts) : 0u;
+}
+// bucket inside a table (or table slice) that covers one partition: uses the
+// hash bits below the partition bits
+KDF_HD u32 bucket_of(u64 h, int log2_parts, u32 n_buckets) {
+  return mulhi32((u32)(h >> 32) << log2_parts, n_buckets);
+}
+// owner rank (multi-GPU): low product bits, re-mixed
+KDF_HD u32 owner_of(u64 h, u32 n_ranks) {
+  u32 l = (u32)h;
+  l ^= l >> 15;
+  l *= 0x2C1B3C6Du;
+  return mulhi32(l, n_ranks);
+}
+// 64-bit mixer (random-access microbenchmark addresses only)
 KDF_HD u64 mix64(u64 x) {
   x ^= x >> 33;
   x *= 0xff51afd7ed558ccdULL;
@@ -58,21 +91,6 @@ KDF_HD u64 mix64(u64 x) {
   x ^= x >> 33;
   return x;
 }
-KDF_HD u64 hash_key(const Key<1>& k) { return mix64(k.lo); }
-KDF_HD u64 hash_key(const Key<2>& k) {
-  return mix64(k.lo ^ mix64(k.hi + 0x9E3779B97F4A7C15ULL));
-}
-
-KDF_HD u64 mulhi64(u64 a, u64 b) {
-#if defined(__CUDA_ARCH__)
-  return __umul64hi(a, b);
-#else
-  return (u64)(((unsigned __int128)a * (unsigned __int128)b) >> 64);
-#endif
-}
-// slot index uses the high bits of the hash, owner rank the low 32 bits.
-KDF_HD u64 slot_of(u64 h, u64 capacity) { return mulhi64(h, capacity); }
-KDF_HD u32 owner_of(u64 h, u32 n_ranks) { return (u32)(h & 0xffffffffu) % n_ranks; }
 
 // -------------------------------------------------- reverse complement ----
 KDF_HD u64 brev64(u64 x) {

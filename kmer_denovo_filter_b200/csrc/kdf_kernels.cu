@@ -1,26 +1,36 @@
 // kdf_kernels.cu — sm_100a kernels + C ABI (include/kdf.h) of the k-mer engine.
 //
 // Kernel inventory (SURVEY §2 native table):
-//   K1  k_extract          rolling extract + canonicalise
-//   K2  k_count_stream     K1 fused with open-addressing insert / count /
-//                          update-if-present / mark-if-present
-//       k_update_keys      K2 on explicit key arrays
+//   K1  k_extract           rolling extract + canonicalise
+//   K2  k_stream            K1 fused with a bucketed open-addressing table op:
+//                           insert+count / insert / count-if-present /
+//                           mark-if-present / emit-hits; table in L2/HBM or,
+//                           for small read-only sets, copied to shared memory
+//       k_update_keys       the same table ops on explicit key arrays
+//   K2p k_bin_stream/_keys  hash-range binning of canonical k-mers (shared-memory
+//                           staged), feeding k_update_keys on an L2-resident
+//                           table slice per bin (kdf_count_bins)
 //   K3  k_threshold_compact threshold + stream compaction (dump -L, == 0, <= pmc)
-//   K4  k_lookup_keys      batched membership / count lookup
-//   K5  k_scan_reads       per-read membership scan + distinct reduction
-//   K6  k_partition_stream owner binning in front of the NCCL all-to-all
+//   K4  k_lookup_keys       batched membership / count lookup
+//   K5  k_scan_reads        dense per-read scan + distinct reduction
+//       k_reduce_hits       sparse per-read reduction of an emitted hit list
+//   K6  k_bin_stream<OWNER> owner binning in front of the NCCL all-to-all
+//
+// Nothing here is a dense contraction, so there is no tensor-core code: the
+// work is bounded by L2 / HBM sector traffic and instruction issue.
 //
 // Mapping: stream kernels give each thread one 32-base word = 32 consecutive
 // window starts, so code/valid loads are 8-byte coalesced and the canonical
-// k-mer is maintained by a 2-bit rolling update.  Table traffic is the bound:
-// one 32-byte sector per probe; probes are issued eight at a time per thread
-// (loads first, resolution after) so that every thread keeps eight independent
-// sector reads in flight.
+// k-mer is maintained by a 2-bit rolling update.  A table probe reads one
+// 32-byte bucket (4 x 64-bit keys or 2 x 128-bit keys) with a single 256-bit
+// load; CHUNK probes are issued back to back before the first is resolved.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
 
 #include <string>
+
+#include <cub/device/device_radix_sort.cuh>
 
 #include "../../include/kdf.h"
 #include "kdf_device.cuh"
@@ -44,40 +54,87 @@ struct kdf_table {
   int k;
   int key_words;
   u64 capacity;
-  void* slots;
+  void* base;
   int sm_count;
+  int log2_parts;  // hash bits consumed above the bucket bits (table slices)
 };
 
+// SoA table: keys[capacity] (KW words each, 32-byte buckets), p0[capacity], p1[capacity]
 template <int KW> struct TableView {
-  typename SlotOf<KW>::type* slots;
-  u64 capacity;
+  u64* keys;
+  u32* p0;
+  u32* p1;
+  u32 n_buckets;
+  int log2_parts;
 };
+template <int KW> struct SPB { static constexpr int v = 4 / KW; };  // slots per bucket
 
-// ----------------------------------------------------- slot primitives ----
-__device__ __forceinline__ Key<1> ld_key(const Slot1* p) {
-  Key<1> k;
-  k.lo = __ldcg(&p->key);
-  return k;
+template <int KW>
+static TableView<KW> view_of_table(const kdf_table* t) {
+  TableView<KW> v;
+  v.keys = (u64*)t->base;
+  v.p0 = (u32*)((char*)t->base + t->capacity * 8ull * KW);
+  v.p1 = v.p0 + t->capacity;
+  v.n_buckets = (u32)(t->capacity / SPB<KW>::v);
+  v.log2_parts = t->log2_parts;
+  return v;
 }
-__device__ __forceinline__ Key<2> ld_key(const Slot2* p) {
-  ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(p));
-  Key<2> k;
-  k.lo = v.x;
-  k.hi = v.y;
-  return k;
-}
-__device__ __forceinline__ bool is_empty(const Key<1>& k) { return k.lo == EMPTY; }
-__device__ __forceinline__ bool is_empty(const Key<2>& k) { return k.lo == EMPTY && k.hi == EMPTY; }
-// may the loaded value be (a possibly torn view of) an empty slot?
-__device__ __forceinline__ bool maybe_empty(const Key<1>& k) { return k.lo == EMPTY; }
-__device__ __forceinline__ bool maybe_empty(const Key<2>& k) { return k.lo == EMPTY || k.hi == EMPTY; }
 
-__device__ __forceinline__ Key<1> cas_key(Slot1* p, const Key<1>& val) {
+// ----------------------------------------------------- bucket primitives --
+struct Bucket {
+  u64 q[4];
+};
+__device__ __forceinline__ Bucket ld_bucket(const u64* p) {
+  Bucket b;
+  asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(b.q[0]), "=l"(b.q[1]), "=l"(b.q[2]), "=l"(b.q[3])
+               : "l"(p)
+               : "memory");
+  return b;
+}
+__device__ __forceinline__ Bucket lds_bucket(const u64* p) {
+  Bucket b;
+  ulonglong2 a = *reinterpret_cast<const ulonglong2*>(p);
+  ulonglong2 c = *reinterpret_cast<const ulonglong2*>(p + 2);
+  b.q[0] = a.x;
+  b.q[1] = a.y;
+  b.q[2] = c.x;
+  b.q[3] = c.y;
+  return b;
+}
+// index of the slot holding `key` in the bucket, or -1
+__device__ __forceinline__ int match_in(const Bucket& b, const Key<1>& key) {
+  int j = -1;
+  if (b.q[3] == key.lo) j = 3;
+  if (b.q[2] == key.lo) j = 2;
+  if (b.q[1] == key.lo) j = 1;
+  if (b.q[0] == key.lo) j = 0;
+  return j;
+}
+__device__ __forceinline__ int match_in(const Bucket& b, const Key<2>& key) {
+  int j = -1;
+  if (b.q[2] == key.lo && b.q[3] == key.hi) j = 1;
+  if (b.q[0] == key.lo && b.q[1] == key.hi) j = 0;
+  return j;
+}
+__device__ __forceinline__ bool has_empty(const Bucket& b, Key<1>) {
+  return b.q[0] == EMPTY || b.q[1] == EMPTY || b.q[2] == EMPTY || b.q[3] == EMPTY;
+}
+__device__ __forceinline__ bool has_empty(const Bucket& b, Key<2>) {
+  return (b.q[0] == EMPTY && b.q[1] == EMPTY) || (b.q[2] == EMPTY && b.q[3] == EMPTY);
+}
+// slot j of the bucket may be (a possibly torn view of) an empty slot
+__device__ __forceinline__ bool maybe_empty(const Bucket& b, int j, Key<1>) { return b.q[j] == EMPTY; }
+__device__ __forceinline__ bool maybe_empty(const Bucket& b, int j, Key<2>) {
+  return b.q[2 * j] == EMPTY || b.q[2 * j + 1] == EMPTY;
+}
+
+__device__ __forceinline__ Key<1> cas_key(u64* p, const Key<1>& val) {
   Key<1> old;
-  old.lo = atomicCAS(&p->key, EMPTY, val.lo);
+  old.lo = atomicCAS(p, EMPTY, val.lo);
   return old;
 }
-__device__ __forceinline__ Key<2> cas_key(Slot2* p, const Key<2>& val) {
+__device__ __forceinline__ Key<2> cas_key(u64* p, const Key<2>& val) {
   Key<2> old;
   asm volatile(
       "{\n\t"
@@ -92,55 +149,89 @@ __device__ __forceinline__ Key<2> cas_key(Slot2* p, const Key<2>& val) {
       : "memory");
   return old;
 }
+__device__ __forceinline__ bool is_empty_key(const Key<1>& k) { return k.lo == EMPTY; }
+__device__ __forceinline__ bool is_empty_key(const Key<2>& k) { return k.lo == EMPTY && k.hi == EMPTY; }
 
-template <int MODE, typename SlotT>
-__device__ __forceinline__ void apply_plane(SlotT* p, int plane, u32 arg) {
-  u32* addr = plane ? &p->p1 : &p->p0;
-  if (MODE == KDF_MODE_INSERT_COUNT || MODE == KDF_MODE_COUNT_IF_PRESENT) {
-    atomicAdd(addr, arg);  // result unused -> RED
-  } else if (MODE == KDF_MODE_MARK_IF_PRESENT) {
-    atomicOr(addr, arg);
-  }
-}
+// table operations (also the `mode` values of the C ABI, plus the hit emitter)
+constexpr int OP_INSERT_COUNT = KDF_MODE_INSERT_COUNT;
+constexpr int OP_INSERT_ONLY = KDF_MODE_INSERT_ONLY;
+constexpr int OP_COUNT_IF_PRESENT = KDF_MODE_COUNT_IF_PRESENT;
+constexpr int OP_MARK_IF_PRESENT = KDF_MODE_MARK_IF_PRESENT;
+constexpr int OP_EMIT_HITS = 4;
+
+struct HitSink {
+  u64* pos;
+  u32* slot;
+  u64 cap;
+  u64* n;
+};
 
 struct LocalStats {
   u32 windows, hits, fresh, full;
 };
 
-// Finish one probe whose home slot (idx) has already been loaded into `cur`.
-template <int KW, int MODE>
-__device__ __forceinline__ void resolve(const TableView<KW>& t, u64 idx, const Key<KW>& key,
-                                        Key<KW> cur, int plane, u32 arg, LocalStats& st) {
-  typedef typename SlotOf<KW>::type SlotT;
-  constexpr bool kInsert = (MODE == KDF_MODE_INSERT_COUNT || MODE == KDF_MODE_INSERT_ONLY);
-  for (u64 n = 0; n < t.capacity; ++n) {
-    SlotT* p = t.slots + idx;
-    if (cur == key) {
-      apply_plane<MODE>(p, plane, arg);
-      st.hits++;
-      return;
+// result codes of a resolved probe
+constexpr u32 R_MISS = 0, R_HIT = 1, R_NEW = 2, R_FULL = 3;
+
+template <int OP, int KW>
+__device__ __forceinline__ void on_found(const TableView<KW>& t, u64 slot, int plane, u32 arg,
+                                         u64 pos, const HitSink& sink) {
+  if (OP == OP_INSERT_COUNT || OP == OP_COUNT_IF_PRESENT) {
+    atomicAdd((plane ? t.p1 : t.p0) + slot, arg);  // result unused -> RED
+  } else if (OP == OP_MARK_IF_PRESENT) {
+    atomicOr((plane ? t.p1 : t.p0) + slot, arg);
+  } else if (OP == OP_EMIT_HITS) {
+    u64 o = atomicAdd(sink.n, 1ull);
+    if (o < sink.cap) {
+      sink.pos[o] = pos;
+      sink.slot[o] = (u32)slot;
+    }
+  }
+}
+
+// Finish a probe whose home bucket `b` has been loaded into `bk` (the rare
+// path: a hit of a probing op, a new key, or a full bucket).  Everything is
+// passed by value so that the callers keep their state in registers.
+template <int KW, int OP>
+__device__ __noinline__ u32 resolve_slow(TableView<KW> t, u32 b, Key<KW> key, Bucket bk, int plane,
+                                         u32 arg, u64 pos, HitSink sink) {
+  constexpr bool kInsert = (OP == OP_INSERT_COUNT || OP == OP_INSERT_ONLY);
+  constexpr int S = SPB<KW>::v;
+  for (u32 n = 0; n < t.n_buckets; ++n) {
+    int j = match_in(bk, key);
+    if (j >= 0) {
+      on_found<OP, KW>(t, (u64)b * S + j, plane, arg, pos, sink);
+      return R_HIT;
     }
     if (kInsert) {
-      if (maybe_empty(cur)) {
-        Key<KW> old = cas_key(p, key);
-        if (is_empty(old)) {
-          apply_plane<MODE>(p, plane, arg);
-          st.fresh++;
-          return;
-        }
-        if (old == key) {
-          apply_plane<MODE>(p, plane, arg);
-          st.hits++;
-          return;
+#pragma unroll
+      for (int c = 0; c < S; ++c) {
+        if (maybe_empty(bk, c, key)) {
+          u64 slot = (u64)b * S + c;
+          Key<KW> old = cas_key(t.keys + slot * KW, key);
+          if (is_empty_key(old)) {
+            on_found<OP, KW>(t, slot, plane, arg, pos, sink);
+            return R_NEW;
+          }
+          if (old == key) {
+            on_found<OP, KW>(t, slot, plane, arg, pos, sink);
+            return R_HIT;
+          }
         }
       }
     } else {
-      if (is_empty(cur)) return;  // miss
+      if (has_empty(bk, key)) return R_MISS;
     }
-    idx = (idx + 1 == t.capacity) ? 0 : idx + 1;
-    cur = ld_key(t.slots + idx);
+    b = (b + 1 == t.n_buckets) ? 0 : b + 1;
+    bk = ld_bucket(t.keys + (u64)b * 4);
   }
-  st.full = 1;
+  return R_FULL;
+}
+
+__device__ __forceinline__ void tally(LocalStats& st, u32 code) {
+  st.hits += (code == R_HIT) ? 1u : 0u;
+  st.fresh += (code == R_NEW) ? 1u : 0u;
+  st.full |= (code == R_FULL) ? 1u : 0u;
 }
 
 __device__ __forceinline__ void flush_stats(const LocalStats& st, u64* stats) {
@@ -186,11 +277,22 @@ __global__ void __launch_bounds__(256) k_extract(StreamView s, int k, u64* out_l
 }
 
 // ------------------------------------------------------------- K2 ---------
-constexpr int CHUNK = 8;
-
-template <int KW, int MODE>
-__global__ void __launch_bounds__(256) k_count_stream(TableView<KW> t, StreamView s, int k,
-                                                      int plane, u32 arg, u64* stats) {
+// One fast-path decision per probe: for probing ops "bucket has an empty slot
+// and no match" (a miss, the common case against a filter set), for inserting
+// ops "bucket holds the key" (the common case at sequencing depth).  Anything
+// else goes to resolve_slow.
+template <int KW, int OP, bool SMEM, int CHUNK>
+__global__ void __launch_bounds__(SMEM ? 512 : 256)
+    k_stream(TableView<KW> t, StreamView s, int k, int plane, u32 arg, u64* stats, HitSink sink) {
+  extern __shared__ __align__(32) u64 sm_keys[];
+  constexpr bool kInsert = (OP == OP_INSERT_COUNT || OP == OP_INSERT_ONLY);
+  constexpr int S = SPB<KW>::v;
+  static_assert(!(SMEM && kInsert), "shared-memory tables are read-only");
+  if (SMEM) {
+    u32 n = t.n_buckets * 4;
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) sm_keys[i] = __ldg(t.keys + i);
+    __syncthreads();
+  }
   LocalStats st = {0, 0, 0, 0};
   u64 stride = (u64)gridDim.x * blockDim.x;
   for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < s.n_words; w += stride) {
@@ -199,71 +301,165 @@ __global__ void __launch_bounds__(256) k_count_stream(TableView<KW> t, StreamVie
 #pragma unroll 1
     for (int c = 0; c < 32 / CHUNK; ++c) {
       Key<KW> keys[CHUNK];
-      Key<KW> cur[CHUNK];
-      u64 idx[CHUNK];
+      Bucket bk[CHUNK];
+      u32 bidx[CHUNK];
       u32 okm = 0;
 #pragma unroll
       for (int u = 0; u < CHUNK; ++u) {
         bool ok = it.ok();
         keys[u] = it.canonical();
         it.advance();
+        bidx[u] = bucket_of(hash_key(keys[u]), t.log2_parts, t.n_buckets);
         if (ok) {
           okm |= 1u << u;
-          idx[u] = slot_of(hash_key(keys[u]), t.capacity);
-          cur[u] = ld_key(t.slots + idx[u]);
+          bk[u] = SMEM ? lds_bucket(sm_keys + (u64)bidx[u] * 4) : ld_bucket(t.keys + (u64)bidx[u] * 4);
         }
       }
       st.windows += __popc(okm);
+      u32 slow = 0;
 #pragma unroll
       for (int u = 0; u < CHUNK; ++u) {
-        if (okm & (1u << u)) resolve<KW, MODE>(t, idx[u], keys[u], cur[u], plane, arg, st);
+        if (okm & (1u << u)) {
+          if (kInsert) {
+            int j = match_in(bk[u], keys[u]);
+            if (j >= 0 && OP == OP_INSERT_COUNT) {
+              st.hits++;
+              atomicAdd((plane ? t.p1 : t.p0) + (u64)bidx[u] * S + j, arg);
+            } else if (j >= 0) {
+              st.hits++;
+            } else {
+              slow |= 1u << u;
+            }
+          } else {
+            bool miss = match_in(bk[u], keys[u]) < 0 && has_empty(bk[u], keys[u]);
+            if (!miss) slow |= 1u << u;
+          }
+        }
+      }
+      if (slow) {
+        u64 pos0 = (w << 5) + c * CHUNK;
+#pragma unroll
+        for (int u = 0; u < CHUNK; ++u) {
+          if (slow & (1u << u))
+            tally(st, resolve_slow<KW, OP>(t, bidx[u], keys[u], bk[u], plane, arg, pos0 + u, sink));
+        }
       }
     }
   }
   flush_stats(st, stats);
 }
 
-template <int KW, int MODE>
+// the same table ops on an explicit key array; n may live on the device
+// (n_dev != NULL: n = min(*n_dev, n_max)) so that bins filled by k_bin_* can be
+// consumed without a host round trip.  Keys are read once: evict-first loads.
+template <int KW> __device__ __forceinline__ Key<KW> ld_key_stream(const u64* lo, const u64* hi, u64 i);
+template <> __device__ __forceinline__ Key<1> ld_key_stream<1>(const u64* lo, const u64*, u64 i) {
+  Key<1> k;
+  k.lo = __ldcs(lo + i);
+  return k;
+}
+template <> __device__ __forceinline__ Key<2> ld_key_stream<2>(const u64* lo, const u64* hi, u64 i) {
+  Key<2> k;
+  if (hi) {
+    k.lo = __ldcs(lo + i);
+    k.hi = __ldcs(hi + i);
+  } else {  // interleaved {lo, hi} pairs (bins)
+    ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2*>(lo) + i);
+    k.lo = v.x;
+    k.hi = v.y;
+  }
+  return k;
+}
+
+template <int KW, int OP>
 __global__ void __launch_bounds__(256) k_update_keys(TableView<KW> t, const u64* lo, const u64* hi,
-                                                     u64 n, int plane, u32 arg, u64* stats) {
+                                                     u64 n_max, const u64* n_dev, int plane, u32 arg,
+                                                     u64* stats) {
+  constexpr int CHUNK = 4;
+  constexpr bool kInsert = (OP == OP_INSERT_COUNT || OP == OP_INSERT_ONLY);
+  constexpr int S = SPB<KW>::v;
+  u64 n = n_max;
+  if (n_dev) {
+    u64 nd = *n_dev;
+    n = nd < n_max ? nd : n_max;
+  }
   LocalStats st = {0, 0, 0, 0};
+  HitSink sink = {nullptr, nullptr, 0, nullptr};
   u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    Key<KW> key;
-    key.lo = lo[i];
-    if (KW == 2) ((u64*)&key)[KW - 1] = hi[i];
-    u64 idx = slot_of(hash_key(key), t.capacity);
-    Key<KW> cur = ld_key(t.slots + idx);
-    st.windows++;
-    resolve<KW, MODE>(t, idx, key, cur, plane, arg, st);
+  for (u64 i0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * CHUNK) {
+    Key<KW> keys[CHUNK];
+    Bucket bk[CHUNK];
+    u32 bidx[CHUNK];
+    u32 okm = 0;
+#pragma unroll
+    for (int u = 0; u < CHUNK; ++u) {
+      u64 i = i0 + (u64)u * stride;
+      if (i < n) {
+        okm |= 1u << u;
+        keys[u] = ld_key_stream<KW>(lo, hi, i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < CHUNK; ++u) {
+      if (okm & (1u << u)) {
+        bidx[u] = bucket_of(hash_key(keys[u]), t.log2_parts, t.n_buckets);
+        bk[u] = ld_bucket(t.keys + (u64)bidx[u] * 4);
+      }
+    }
+    st.windows += __popc(okm);
+    u32 slow = 0;
+#pragma unroll
+    for (int u = 0; u < CHUNK; ++u) {
+      if (okm & (1u << u)) {
+        int j = match_in(bk[u], keys[u]);
+        if (kInsert && j >= 0) {
+          st.hits++;
+          if (OP == OP_INSERT_COUNT) atomicAdd((plane ? t.p1 : t.p0) + (u64)bidx[u] * S + j, arg);
+        } else if (!kInsert && j < 0 && has_empty(bk[u], keys[u])) {
+          // miss
+        } else {
+          slow |= 1u << u;
+        }
+      }
+    }
+    if (slow) {
+#pragma unroll
+      for (int u = 0; u < CHUNK; ++u) {
+        if (slow & (1u << u))
+          tally(st, resolve_slow<KW, OP>(t, bidx[u], keys[u], bk[u], plane, arg, 0, sink));
+      }
+    }
   }
   flush_stats(st, stats);
 }
 
 // ------------------------------------------------------------- K3 ---------
 template <int KW>
-__global__ void __launch_bounds__(256) k_threshold_compact(TableView<KW> t, u32 min0, u32 max0,
-                                                           u32 min1, u32 max1, u64* out_lo,
+__global__ void __launch_bounds__(256) k_threshold_compact(TableView<KW> t, u64 capacity, u32 min0,
+                                                           u32 max0, u32 min1, u32 max1, u64* out_lo,
                                                            u64* out_hi, u32* out_p0, u32* out_p1,
-                                                           u64 cap, u64* n_out) {
-  typedef typename SlotOf<KW>::type SlotT;
+                                                           u64 cap, u64* n_out, u32 count_min0,
+                                                           u64* n_count, u64* n_occupied) {
   u64 stride = (u64)gridDim.x * blockDim.x;
   u64 first = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  u64 rounds = (t.capacity + stride - 1) / stride;
+  u64 rounds = (capacity + stride - 1) / stride;
   unsigned lane = threadIdx.x & 31;
+  u32 cnt_ge = 0, cnt_occ = 0;
   for (u64 r = 0; r < rounds; ++r) {
     u64 i = first + r * stride;
     bool keep = false;
     Key<KW> key;
     key.lo = 0;
     u32 p0 = 0, p1 = 0;
-    if (i < t.capacity) {
-      const SlotT* p = t.slots + i;
-      key = ld_key(p);
-      if (!is_empty(key)) {
-        p0 = __ldcg(&p->p0);
-        p1 = __ldcg(&p->p1);
+    if (i < capacity) {
+      key.lo = __ldcg(t.keys + i * KW);
+      if (KW == 2) ((u64*)&key)[KW - 1] = __ldcg(t.keys + i * KW + 1);
+      if (!is_empty_key(key)) {
+        p0 = __ldcg(t.p0 + i);
+        p1 = __ldcg(t.p1 + i);
         keep = p0 >= min0 && p0 <= max0 && p1 >= min1 && p1 <= max1;
+        cnt_occ++;
+        cnt_ge += (p0 >= count_min0) ? 1u : 0u;
       }
     }
     unsigned m = __ballot_sync(0xffffffffu, keep);
@@ -283,21 +479,32 @@ __global__ void __launch_bounds__(256) k_threshold_compact(TableView<KW> t, u32 
       }
     }
   }
+  if (n_count || n_occupied) {
+    for (int o = 16; o; o >>= 1) {
+      cnt_ge += __shfl_xor_sync(0xffffffffu, cnt_ge, o);
+      cnt_occ += __shfl_xor_sync(0xffffffffu, cnt_occ, o);
+    }
+    if (lane == 0) {
+      if (n_count && cnt_ge) atomicAdd(n_count, (u64)cnt_ge);
+      if (n_occupied && cnt_occ) atomicAdd(n_occupied, (u64)cnt_occ);
+    }
+  }
 }
 
 // ------------------------------------------------------------- K4 ---------
-// static table (no concurrent inserts): keys may use the read-only path
 template <int KW>
 __device__ __forceinline__ bool find_slot(const TableView<KW>& t, const Key<KW>& key, u64& idx_out) {
-  u64 idx = slot_of(hash_key(key), t.capacity);
-  for (u64 n = 0; n < t.capacity; ++n) {
-    Key<KW> cur = ld_key(t.slots + idx);
-    if (cur == key) {
-      idx_out = idx;
+  constexpr int S = SPB<KW>::v;
+  u32 b = bucket_of(hash_key(key), t.log2_parts, t.n_buckets);
+  for (u32 n = 0; n < t.n_buckets; ++n) {
+    Bucket bk = ld_bucket(t.keys + (u64)b * 4);
+    int j = match_in(bk, key);
+    if (j >= 0) {
+      idx_out = (u64)b * S + j;
       return true;
     }
-    if (is_empty(cur)) return false;
-    idx = (idx + 1 == t.capacity) ? 0 : idx + 1;
+    if (has_empty(bk, key)) return false;
+    b = (b + 1 == t.n_buckets) ? 0 : b + 1;
   }
   return false;
 }
@@ -314,8 +521,8 @@ __global__ void __launch_bounds__(256) k_lookup_keys(TableView<KW> t, const u64*
     u64 idx;
     bool f = find_slot<KW>(t, key, idx);
     if (out_found) out_found[i] = f ? 1 : 0;
-    if (out_p0) out_p0[i] = f ? __ldcg(&t.slots[idx].p0) : 0u;
-    if (out_p1) out_p1[i] = f ? __ldcg(&t.slots[idx].p1) : 0u;
+    if (out_p0) out_p0[i] = f ? __ldcg(t.p0 + idx) : 0u;
+    if (out_p1) out_p1[i] = f ? __ldcg(t.p1 + idx) : 0u;
   }
 }
 
@@ -331,8 +538,8 @@ __global__ void __launch_bounds__(256) k_add_planes(TableView<KW> t, const u64* 
     if (KW == 2) ((u64*)&key)[KW - 1] = hi[i];
     u64 idx;
     if (find_slot<KW>(t, key, idx)) {
-      if (add0 && add0[i]) atomicAdd(&t.slots[idx].p0, add0[i]);
-      if (add1 && add1[i]) atomicAdd(&t.slots[idx].p1, add1[i]);
+      if (add0 && add0[i]) atomicAdd(t.p0 + idx, add0[i]);
+      if (add1 && add1[i]) atomicAdd(t.p1 + idx, add1[i]);
     } else if (n_missing) {
       atomicAdd(n_missing, 1ull);
     }
@@ -340,12 +547,11 @@ __global__ void __launch_bounds__(256) k_add_planes(TableView<KW> t, const u64* 
 }
 
 // ------------------------------------------------------------- K5 ---------
-// One warp per read.  Lanes stride through the read's window starts; hits are
-// appended to a per-warp shared list in position order (ballot prefix), then
-// the warp counts distinct slot indices among them.
+// Dense form: one warp per read.  Lanes stride through the read's window
+// starts; hits are appended to a per-warp shared list in position order
+// (ballot prefix), then the warp counts distinct slot indices among them.
 constexpr int SCAN_WARPS = 4;
 constexpr int SCAN_HCAP = 1024;
-#define KDF_NDISTINCT_OVERFLOW 0xFFFFFFFFu
 
 template <int KW>
 __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan_reads(
@@ -459,19 +665,151 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan_reads(
   }
 }
 
-// ------------------------------------------------------------- K6 ---------
-constexpr int MAX_RANKS = 64;
+// Sparse form: hits (stream position, slot) sorted by position -> one record
+// per read that has hits.  A hit is the first of its read iff the previous
+// hit lies before the read's start; each thread owning a first hit walks its
+// read's run (<= read length entries) and counts distinct slots.
+__global__ void __launch_bounds__(128) k_reduce_hits(const u64* pos, const u32* slot, u64 n_hits,
+                                                     const u64* read_starts, u64 n_reads,
+                                                     u64* rec_read, u32* rec_ndistinct,
+                                                     u32* rec_nhits, u64* rec_first, u64* n_recs) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_hits) return;
+  u64 p = pos[i];
+  // r = last read with read_starts[r] <= p
+  u64 lo = 0, hi = n_reads;
+  while (hi - lo > 1) {
+    u64 mid = (lo + hi) >> 1;
+    if (read_starts[mid] <= p) lo = mid; else hi = mid;
+  }
+  u64 r = lo;
+  u64 rs = read_starts[r];
+  if (i > 0 && pos[i - 1] >= rs) return;  // not the first hit of this read
+  u64 rend = (r + 1 < n_reads) ? read_starts[r + 1] : ~0ull;
+  u64 j = i;
+  u32 nh = 0, nd = 0;
+  while (j < n_hits && pos[j] < rend) {
+    u32 sj = slot[j];
+    bool dup = false;
+    for (u64 q = i; q < j; ++q) {
+      if (slot[q] == sj) {
+        dup = true;
+        break;
+      }
+    }
+    nd += dup ? 0u : 1u;
+    ++nh;
+    ++j;
+  }
+  u64 o = atomicAdd(n_recs, 1ull);
+  rec_read[o] = r;
+  rec_ndistinct[o] = nd;
+  rec_nhits[o] = nh;
+  rec_first[o] = i;
+}
 
-template <int KW, bool SCATTER>
-__global__ void __launch_bounds__(256) k_partition_stream(StreamView s, int k, u32 n_ranks,
-                                                          u64* counts, const u64* bin_offsets,
-                                                          u64* cursors, u64* out_lo, u64* out_hi) {
-  __shared__ u32 sh_cnt[MAX_RANKS];
-  if (!SCATTER) {
-    for (int i = threadIdx.x; i < MAX_RANKS; i += blockDim.x) sh_cnt[i] = 0;
+// ----------------------------------------------------------- K2p / K6 -----
+// Bin canonical k-mers by hash range (BY_OWNER = false: partition bits of the
+// bucket hash, for the L2-sliced count) or by owner rank (BY_OWNER = true, in
+// front of the all-to-all).  Every bin is a fixed-capacity region of `bins`;
+// keys are staged in shared-memory queues and flushed a queue at a time so
+// that global writes are contiguous runs.  A bin that overflows sets
+// *overflow and drops the key: the caller must size bins or retry.
+constexpr int BIN_THREADS = 256;
+constexpr int BIN_MAX_PARTS = 256;
+
+template <int KW>
+__device__ __forceinline__ void st_key(u64* bins, u64 idx, const Key<KW>& key);
+template <> __device__ __forceinline__ void st_key<1>(u64* bins, u64 idx, const Key<1>& key) {
+  bins[idx] = key.lo;
+}
+template <> __device__ __forceinline__ void st_key<2>(u64* bins, u64 idx, const Key<2>& key) {
+  reinterpret_cast<ulonglong2*>(bins)[idx] = make_ulonglong2(key.lo, key.hi);
+}
+
+template <int KW>
+struct BinStage {
+  // dynamic shared memory layout: cnt[P] u32 | gbase[P] u64 | queue[P][QCAP] keys
+  u32* cnt;
+  u64* gbase;
+  u64* queue;
+  int n_parts;
+  int qcap;
+  __device__ void init(unsigned char* smem, int P, int Q) {
+    n_parts = P;
+    qcap = Q;
+    gbase = reinterpret_cast<u64*>(smem);
+    queue = gbase + P;
+    cnt = reinterpret_cast<u32*>(queue + (size_t)P * Q * KW);
+    for (int i = threadIdx.x; i < P; i += blockDim.x) cnt[i] = 0;
+  }
+  static size_t bytes(int P, int Q) { return (size_t)P * 8 + (size_t)P * Q * KW * 8 + (size_t)P * 4; }
+  // append a key; queue overflow falls back to a direct global append
+  __device__ __forceinline__ void push(u32 p, const Key<KW>& key, u64* bins, u64 bin_cap, u64* cursors,
+                                       u64* overflow) {
+    u32 o = atomicAdd(&cnt[p], 1u);
+    if (o < (u32)qcap) {
+      u64* q = queue + ((size_t)p * qcap + o) * KW;
+      q[0] = key.lo;
+      if (KW == 2) q[1] = ((const u64*)&key)[KW - 1];
+    } else {
+      u64 g = atomicAdd(cursors + p, 1ull);
+      if (g < bin_cap) st_key<KW>(bins, (u64)p * bin_cap + g, key);
+      else atomicOr(overflow, 1ull);
+    }
+  }
+  // all threads: write every queue to its bin and reset the counters
+  __device__ void flush(u64* bins, u64 bin_cap, u64* cursors, u64* overflow) {
+    __syncthreads();
+    for (int p = threadIdx.x; p < n_parts; p += blockDim.x) {
+      u32 c = cnt[p];
+      if (c > (u32)qcap) c = qcap;
+      gbase[p] = c ? atomicAdd(cursors + p, (u64)c) : 0ull;
+    }
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    for (int p = warp; p < n_parts; p += n_warps) {
+      u32 c = cnt[p];
+      if (c > (u32)qcap) c = qcap;
+      u64 g0 = gbase[p];
+      for (u32 i = lane; i < c; i += 32) {
+        u64 g = g0 + i;
+        const u64* q = queue + ((size_t)p * qcap + i) * KW;
+        if (g < bin_cap) {
+          Key<KW> key;
+          key.lo = q[0];
+          if (KW == 2) ((u64*)&key)[KW - 1] = q[1];
+          st_key<KW>(bins, (u64)p * bin_cap + g, key);
+        } else {
+          atomicOr(overflow, 1ull);
+        }
+      }
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < n_parts; p += blockDim.x) cnt[p] = 0;
     __syncthreads();
   }
-  const unsigned lane = threadIdx.x & 31;
+};
+
+template <int KW, bool BY_OWNER>
+__device__ __forceinline__ u32 bin_of(const Key<KW>& key, int log2_parts, u32 n_parts) {
+  u64 h = hash_key(key);
+  return BY_OWNER ? owner_of(h, n_parts) : part_of(h, log2_parts);
+}
+
+// windows handled per thread between two flushes
+constexpr int BIN_WPR = 16;
+
+template <int KW, bool BY_OWNER>
+__global__ void __launch_bounds__(BIN_THREADS) k_bin_stream(StreamView s, int k, int log2_parts,
+                                                            u32 n_parts, int qcap, u64* bins,
+                                                            u64 bin_cap, u64* cursors, u64* overflow,
+                                                            u64* stats) {
+  extern __shared__ __align__(16) unsigned char bin_smem[];
+  BinStage<KW> stage;
+  stage.init(bin_smem, (int)n_parts, qcap);
+  __syncthreads();
+  u32 windows = 0;
   u64 stride = (u64)gridDim.x * blockDim.x;
   u64 n_iter = (s.n_words + stride - 1) / stride;
   u64 w0 = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -479,62 +817,64 @@ __global__ void __launch_bounds__(256) k_partition_stream(StreamView s, int k, u
     u64 w = w0 + itn * stride;
     WindowIter<KW> it(s, w, k);  // loads beyond n_words read as invalid
 #pragma unroll 1
-    for (int j = 0; j < 32; ++j) {
-      bool ok = it.ok();
-      Key<KW> key = it.canonical();
-      it.advance();
-      u32 owner = ok ? owner_of(hash_key(key), n_ranks) : 0xffffffffu;
-      if (!SCATTER) {
-        if (ok) atomicAdd(&sh_cnt[owner], 1u);
-      } else {
-        unsigned peers = __match_any_sync(0xffffffffu, owner);
+    for (int c = 0; c < 32 / BIN_WPR; ++c) {
+#pragma unroll 4
+      for (int j = 0; j < BIN_WPR; ++j) {
+        bool ok = it.ok();
+        Key<KW> key = it.canonical();
+        it.advance();
         if (ok) {
-          int leader = __ffs(peers) - 1;
-          u64 base = 0;
-          if ((int)lane == leader) base = atomicAdd(cursors + owner, (u64)__popc(peers));
-          base = __shfl_sync(peers, base, leader);
-          u64 o = bin_offsets[owner] + base + __popc(peers & ((1u << lane) - 1));
-          out_lo[o] = key.lo;
-          if (KW == 2) out_hi[o] = ((const u64*)&key)[KW - 1];
+          windows++;
+          stage.push(bin_of<KW, BY_OWNER>(key, log2_parts, n_parts), key, bins, bin_cap, cursors,
+                     overflow);
         }
       }
+      stage.flush(bins, bin_cap, cursors, overflow);
     }
   }
-  if (!SCATTER) {
-    __syncthreads();
-    for (u32 i = threadIdx.x; i < n_ranks; i += blockDim.x)
-      if (sh_cnt[i]) atomicAdd(counts + i, (u64)sh_cnt[i]);
+  if (stats) {
+    for (int o = 16; o; o >>= 1) windows += __shfl_xor_sync(0xffffffffu, windows, o);
+    if ((threadIdx.x & 31) == 0 && windows) atomicAdd(stats + KDF_STAT_WINDOWS, (u64)windows);
+  }
+}
+
+template <int KW, bool BY_OWNER>
+__global__ void __launch_bounds__(BIN_THREADS) k_bin_keys(const u64* lo, const u64* hi, u64 n,
+                                                          int log2_parts, u32 n_parts, int qcap,
+                                                          u64* bins, u64 bin_cap, u64* cursors,
+                                                          u64* overflow) {
+  extern __shared__ __align__(16) unsigned char bin_smem[];
+  BinStage<KW> stage;
+  stage.init(bin_smem, (int)n_parts, qcap);
+  __syncthreads();
+  u64 per_round = (u64)gridDim.x * blockDim.x * BIN_WPR;
+  u64 n_rounds = (n + per_round - 1) / per_round;
+  for (u64 r = 0; r < n_rounds; ++r) {
+    u64 base = r * per_round + (u64)blockIdx.x * blockDim.x * BIN_WPR + threadIdx.x;
+#pragma unroll 4
+    for (int j = 0; j < BIN_WPR; ++j) {
+      u64 i = base + (u64)j * blockDim.x;
+      if (i < n) {
+        Key<KW> key = ld_key_stream<KW>(lo, hi, i);
+        stage.push(bin_of<KW, BY_OWNER>(key, log2_parts, n_parts), key, bins, bin_cap, cursors,
+                   overflow);
+      }
+    }
+    stage.flush(bins, bin_cap, cursors, overflow);
   }
 }
 
 // ------------------------------------------------ table maintenance -------
-__global__ void __launch_bounds__(256) k_clear_table(ulonglong2* p, u64 n_units, int key_words) {
-  // 16-byte units: KW=1 slot = {key, planes} ; KW=2 slot = {lo, hi} {planes, pad}
+__global__ void __launch_bounds__(256) k_fill_u64x2(ulonglong2* p, u64 n_units, u64 value) {
   u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_units; i += stride) {
-    ulonglong2 v;
-    if (key_words == 1)
-      v = make_ulonglong2(EMPTY, 0ull);
-    else
-      v = (i & 1) ? make_ulonglong2(0ull, 0ull) : make_ulonglong2(EMPTY, EMPTY);
-    p[i] = v;
-  }
-}
-
-template <int KW>
-__global__ void __launch_bounds__(256) k_clear_plane(TableView<KW> t, int plane) {
-  u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < t.capacity; i += stride) {
-    if (plane)
-      t.slots[i].p1 = 0;
-    else
-      t.slots[i].p0 = 0;
-  }
+  ulonglong2 v = make_ulonglong2(value, value);
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_units; i += stride) p[i] = v;
 }
 
 // ---------------------------------------------- random-access roofline ----
 __global__ void __launch_bounds__(256) k_bench_random(u32* buf, u64 n_sectors, u64 n_ops, int atomic,
                                                       u64* sink) {
+  constexpr int CHUNK = 8;
   u64 stride = (u64)gridDim.x * blockDim.x;
   u32 acc = 0;
   for (u64 i0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_ops; i0 += stride * CHUNK) {
@@ -557,9 +897,9 @@ __global__ void __launch_bounds__(256) k_bench_random(u32* buf, u64 n_sectors, u
 }
 
 // ------------------------------------------------------------ host side ---
-static int grid_for(const void* func, int block, u64 work_items, int sm_count) {
+static int grid_for(const void* func, int block, size_t smem, u64 work_items, int sm_count) {
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, block, 0) != cudaSuccess ||
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, block, smem) != cudaSuccess ||
       per_sm < 1)
     per_sm = 1;
   u64 full = (u64)sm_count * per_sm;
@@ -583,6 +923,112 @@ static StreamView view_of(const kdf_stream* s) {
   v.n_bases = s->n_bases;
   v.n_words = (s->n_bases + 31) / 32;
   return v;
+}
+
+// shared-memory budget for a read-only table copy (keys only)
+static const size_t SMEM_TABLE_MAX = 160 * 1024;
+
+template <int KW, int OP, bool SMEM, int CHUNK>
+static int launch_stream(const kdf_table* t, const StreamView& v, int plane, u32 arg, u64* stats,
+                         const HitSink& sink, cudaStream_t st) {
+  TableView<KW> tv = view_of_table<KW>(t);
+  const void* fn = (const void*)k_stream<KW, OP, SMEM, CHUNK>;
+  size_t smem = SMEM ? (size_t)tv.n_buckets * 32 : 0;
+  int block = SMEM ? 512 : 256;
+  if (SMEM) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int g = grid_for(fn, block, smem, v.n_words, t->sm_count);
+  k_stream<KW, OP, SMEM, CHUNK><<<g, block, smem, st>>>(tv, v, t->k, plane, arg, stats, sink);
+  CUDA_TRY(cudaGetLastError());
+  return KDF_OK;
+}
+
+template <int KW>
+static int dispatch_stream(const kdf_table* t, const StreamView& v, int op, int plane, u32 arg,
+                           u64* stats, const HitSink& sink, cudaStream_t st) {
+  bool small = (size_t)(t->capacity / SPB<KW>::v) * 32 <= SMEM_TABLE_MAX && t->log2_parts == 0;
+  switch (op) {
+    case OP_INSERT_COUNT:
+      return launch_stream<KW, OP_INSERT_COUNT, false, 8>(t, v, plane, arg, stats, sink, st);
+    case OP_INSERT_ONLY:
+      return launch_stream<KW, OP_INSERT_ONLY, false, 8>(t, v, plane, arg, stats, sink, st);
+    case OP_COUNT_IF_PRESENT:
+      return small ? launch_stream<KW, OP_COUNT_IF_PRESENT, true, 4>(t, v, plane, arg, stats, sink, st)
+                   : launch_stream<KW, OP_COUNT_IF_PRESENT, false, 8>(t, v, plane, arg, stats, sink, st);
+    case OP_MARK_IF_PRESENT:
+      return small ? launch_stream<KW, OP_MARK_IF_PRESENT, true, 4>(t, v, plane, arg, stats, sink, st)
+                   : launch_stream<KW, OP_MARK_IF_PRESENT, false, 8>(t, v, plane, arg, stats, sink, st);
+    case OP_EMIT_HITS:
+      return small ? launch_stream<KW, OP_EMIT_HITS, true, 4>(t, v, plane, arg, stats, sink, st)
+                   : launch_stream<KW, OP_EMIT_HITS, false, 8>(t, v, plane, arg, stats, sink, st);
+    default:
+      return fail(KDF_ERR_ARG, "unknown table operation");
+  }
+}
+
+template <int KW, int OP>
+static int launch_update_keys(const kdf_table* t, const u64* lo, const u64* hi, u64 n_max,
+                              const u64* n_dev, int plane, u32 arg, u64* stats, cudaStream_t st) {
+  TableView<KW> tv = view_of_table<KW>(t);
+  int g = grid_for((const void*)k_update_keys<KW, OP>, 256, 0, (n_max + 3) / 4, t->sm_count);
+  k_update_keys<KW, OP><<<g, 256, 0, st>>>(tv, lo, hi, n_max, n_dev, plane, arg, stats);
+  CUDA_TRY(cudaGetLastError());
+  return KDF_OK;
+}
+
+template <int KW>
+static int dispatch_update_keys(const kdf_table* t, const u64* lo, const u64* hi, u64 n_max,
+                                const u64* n_dev, int op, int plane, u32 arg, u64* stats,
+                                cudaStream_t st) {
+  switch (op) {
+    case OP_INSERT_COUNT:
+      return launch_update_keys<KW, OP_INSERT_COUNT>(t, lo, hi, n_max, n_dev, plane, arg, stats, st);
+    case OP_INSERT_ONLY:
+      return launch_update_keys<KW, OP_INSERT_ONLY>(t, lo, hi, n_max, n_dev, plane, arg, stats, st);
+    case OP_COUNT_IF_PRESENT:
+      return launch_update_keys<KW, OP_COUNT_IF_PRESENT>(t, lo, hi, n_max, n_dev, plane, arg, stats, st);
+    case OP_MARK_IF_PRESENT:
+      return launch_update_keys<KW, OP_MARK_IF_PRESENT>(t, lo, hi, n_max, n_dev, plane, arg, stats, st);
+    default:
+      return fail(KDF_ERR_ARG, "unknown table operation");
+  }
+}
+
+static int clear_table_async(const kdf_table* t, cudaStream_t st) {
+  // keys -> all ones, planes -> 0; both regions are multiples of 16 bytes
+  u64 key_units = t->capacity * 8ull * t->key_words / 16;
+  u64 plane_units = t->capacity * 8ull / 16;
+  ulonglong2* kp = (ulonglong2*)t->base;
+  ulonglong2* pp = kp + key_units;
+  int g = grid_for((const void*)k_fill_u64x2, 256, 0, key_units, t->sm_count);
+  k_fill_u64x2<<<g, 256, 0, st>>>(kp, key_units, EMPTY);
+  g = grid_for((const void*)k_fill_u64x2, 256, 0, plane_units, t->sm_count);
+  k_fill_u64x2<<<g, 256, 0, st>>>(pp, plane_units, 0ull);
+  CUDA_TRY(cudaGetLastError());
+  return KDF_OK;
+}
+
+template <int KW>
+static int launch_threshold(const kdf_table* t, u32 min0, u32 max0, u32 min1, u32 max1, u64* out_lo,
+                            u64* out_hi, u32* out_p0, u32* out_p1, u64 cap, u64* n_out,
+                            u32 count_min0, u64* n_count, u64* n_occ, cudaStream_t st) {
+  TableView<KW> tv = view_of_table<KW>(t);
+  int g = grid_for((const void*)k_threshold_compact<KW>, 256, 0, t->capacity, t->sm_count);
+  k_threshold_compact<KW><<<g, 256, 0, st>>>(tv, t->capacity, min0, max0, min1, max1, out_lo, out_hi,
+                                             out_p0, out_p1, cap, n_out, count_min0, n_count, n_occ);
+  CUDA_TRY(cudaGetLastError());
+  return KDF_OK;
+}
+
+static int check_table_args(int k, uint64_t capacity, const void* slots, const char* who) {
+  int kw = kdf_key_words(k);
+  if (!kw) return fail(KDF_ERR_ARG, std::string(who) + ": k must be in 1..64");
+  if (capacity < 4 || (capacity & 3))
+    return fail(KDF_ERR_ARG, std::string(who) + ": capacity must be a multiple of 4, >= 4");
+  if (capacity / (4 / kw) > 0xffffffffull)
+    return fail(KDF_ERR_ARG, std::string(who) + ": capacity exceeds 2^32 buckets");
+  if (((uintptr_t)slots & 31) != 0)
+    return fail(KDF_ERR_ARG, std::string(who) + ": table memory must be 32-byte aligned");
+  return KDF_OK;
 }
 
 extern "C" {
@@ -615,44 +1061,36 @@ int kdf_key_words(int k) {
 }
 
 size_t kdf_table_bytes(uint64_t capacity, int key_words) {
-  if (key_words == 1) return (size_t)capacity * sizeof(Slot1);
-  if (key_words == 2) return (size_t)capacity * sizeof(Slot2);
-  return 0;
+  if (key_words != 1 && key_words != 2) return 0;
+  return (size_t)capacity * (8 * (size_t)key_words + 8);
 }
 
 uint64_t kdf_table_capacity_for(uint64_t n_keys) {
   uint64_t c = n_keys * 2;
   if (c < 1024) c = 1024;
-  return (c + 7) & ~7ull;  // whole 128-byte lines for either slot size
+  return (c + 7) & ~7ull;  // whole buckets for either key width
 }
 
 int kdf_table_clear(kdf_table* t, void* stream) {
   if (!t) return fail(KDF_ERR_ARG, "kdf_table_clear: table is NULL");
-  cudaStream_t st = (cudaStream_t)stream;
-  u64 units = kdf_table_bytes(t->capacity, t->key_words) / 16;
-  int g = grid_for((const void*)k_clear_table, 256, units, t->sm_count);
-  k_clear_table<<<g, 256, 0, st>>>((ulonglong2*)t->slots, units, t->key_words);
-  CUDA_TRY(cudaGetLastError());
-  return KDF_OK;
+  return clear_table_async(t, (cudaStream_t)stream);
 }
 
 int kdf_table_create(kdf_table** out, int k, uint64_t capacity, void* slots, void* stream) {
   if (!out || !slots) return fail(KDF_ERR_ARG, "kdf_table_create: NULL argument");
-  int kw = kdf_key_words(k);
-  if (!kw) return fail(KDF_ERR_ARG, "kdf_table_create: k must be in 1..64");
-  if (capacity < 2) return fail(KDF_ERR_ARG, "kdf_table_create: capacity must be >= 2");
-  if (((uintptr_t)slots & 31) != 0)
-    return fail(KDF_ERR_ARG, "kdf_table_create: slots must be 32-byte aligned");
+  int rc = check_table_args(k, capacity, slots, "kdf_table_create");
+  if (rc != KDF_OK) return rc;
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
     return fail(KDF_ERR_NO_DEVICE, "no CUDA device visible");
   kdf_table* t = new kdf_table;
   t->k = k;
-  t->key_words = kw;
+  t->key_words = kdf_key_words(k);
   t->capacity = capacity;
-  t->slots = slots;
+  t->base = slots;
   t->sm_count = current_sm_count();
-  int rc = kdf_table_clear(t, stream);
+  t->log2_parts = 0;
+  rc = kdf_table_clear(t, stream);
   if (rc != KDF_OK) {
     delete t;
     return rc;
@@ -676,17 +1114,8 @@ int kdf_table_info(const kdf_table* t, int* k, int* key_words, uint64_t* capacit
 
 int kdf_table_clear_plane(kdf_table* t, int plane, void* stream) {
   if (!t || (plane != 0 && plane != 1)) return fail(KDF_ERR_ARG, "kdf_table_clear_plane: bad argument");
-  cudaStream_t st = (cudaStream_t)stream;
-  if (t->key_words == 1) {
-    TableView<1> v{(Slot1*)t->slots, t->capacity};
-    int g = grid_for((const void*)k_clear_plane<1>, 256, t->capacity, t->sm_count);
-    k_clear_plane<1><<<g, 256, 0, st>>>(v, plane);
-  } else {
-    TableView<2> v{(Slot2*)t->slots, t->capacity};
-    int g = grid_for((const void*)k_clear_plane<2>, 256, t->capacity, t->sm_count);
-    k_clear_plane<2><<<g, 256, 0, st>>>(v, plane);
-  }
-  CUDA_TRY(cudaGetLastError());
+  char* p = (char*)t->base + t->capacity * 8ull * t->key_words + (plane ? t->capacity * 4ull : 0);
+  CUDA_TRY(cudaMemsetAsync(p, 0, t->capacity * 4ull, (cudaStream_t)stream));
   return KDF_OK;
 }
 
@@ -701,68 +1130,43 @@ int kdf_extract_canonical(const kdf_stream* s, int k, uint64_t* out_lo, uint64_t
   int sm = current_sm_count();
   cudaStream_t st = (cudaStream_t)stream;
   if (kw == 1) {
-    int g = grid_for((const void*)k_extract<1>, 256, v.n_words, sm);
+    int g = grid_for((const void*)k_extract<1>, 256, 0, v.n_words, sm);
     k_extract<1><<<g, 256, 0, st>>>(v, k, (u64*)out_lo, (u64*)out_hi, out_ok);
   } else {
-    int g = grid_for((const void*)k_extract<2>, 256, v.n_words, sm);
+    int g = grid_for((const void*)k_extract<2>, 256, 0, v.n_words, sm);
     k_extract<2><<<g, 256, 0, st>>>(v, k, (u64*)out_lo, (u64*)out_hi, out_ok);
   }
   CUDA_TRY(cudaGetLastError());
   return KDF_OK;
 }
 
-}  // extern "C"
-
-template <int KW, int MODE>
-static int launch_count_stream(kdf_table* t, const StreamView& v, int plane, u32 arg, u64* stats,
-                               cudaStream_t st) {
-  TableView<KW> tv{(typename SlotOf<KW>::type*)t->slots, t->capacity};
-  int g = grid_for((const void*)k_count_stream<KW, MODE>, 256, v.n_words, t->sm_count);
-  k_count_stream<KW, MODE><<<g, 256, 0, st>>>(tv, v, t->k, plane, arg, stats);
-  CUDA_TRY(cudaGetLastError());
-  return KDF_OK;
-}
-
-extern "C" int kdf_count_stream(kdf_table* t, const kdf_stream* s, int mode, int plane, uint32_t arg,
+int kdf_count_stream(kdf_table* t, const kdf_stream* s, int mode, int plane, uint32_t arg,
                      uint64_t* stats, void* stream) {
   if (!t || !s) return fail(KDF_ERR_ARG, "kdf_count_stream: NULL argument");
   if (plane != 0 && plane != 1) return fail(KDF_ERR_ARG, "kdf_count_stream: plane must be 0 or 1");
+  if (mode < 0 || mode > KDF_MODE_MARK_IF_PRESENT) return fail(KDF_ERR_ARG, "kdf_count_stream: unknown mode");
   StreamView v = view_of(s);
   if (v.n_words == 0) return KDF_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  u64* sp = (u64*)stats;
-#define KDF_DISPATCH(KW)                                                                    \
-  switch (mode) {                                                                           \
-    case KDF_MODE_INSERT_COUNT:                                                             \
-      return launch_count_stream<KW, KDF_MODE_INSERT_COUNT>(t, v, plane, arg, sp, st);      \
-    case KDF_MODE_INSERT_ONLY:                                                              \
-      return launch_count_stream<KW, KDF_MODE_INSERT_ONLY>(t, v, plane, arg, sp, st);       \
-    case KDF_MODE_COUNT_IF_PRESENT:                                                         \
-      return launch_count_stream<KW, KDF_MODE_COUNT_IF_PRESENT>(t, v, plane, arg, sp, st);  \
-    case KDF_MODE_MARK_IF_PRESENT:                                                          \
-      return launch_count_stream<KW, KDF_MODE_MARK_IF_PRESENT>(t, v, plane, arg, sp, st);   \
-    default:                                                                                \
-      return fail(KDF_ERR_ARG, "kdf_count_stream: unknown mode");                           \
-  }
-  if (t->key_words == 1) {
-    KDF_DISPATCH(1)
-  } else {
-    KDF_DISPATCH(2)
-  }
-#undef KDF_DISPATCH
+  HitSink sink = {nullptr, nullptr, 0, nullptr};
+  if (t->key_words == 1)
+    return dispatch_stream<1>(t, v, mode, plane, arg, (u64*)stats, sink, (cudaStream_t)stream);
+  return dispatch_stream<2>(t, v, mode, plane, arg, (u64*)stats, sink, (cudaStream_t)stream);
 }
 
-template <int KW, int MODE>
-static int launch_update_keys(kdf_table* t, const u64* lo, const u64* hi, u64 n, int plane, u32 arg,
-                              u64* stats, cudaStream_t st) {
-  TableView<KW> tv{(typename SlotOf<KW>::type*)t->slots, t->capacity};
-  int g = grid_for((const void*)k_update_keys<KW, MODE>, 256, n, t->sm_count);
-  k_update_keys<KW, MODE><<<g, 256, 0, st>>>(tv, lo, hi, n, plane, arg, stats);
-  CUDA_TRY(cudaGetLastError());
-  return KDF_OK;
+int kdf_scan_stream_hits(const kdf_table* t, const kdf_stream* s, uint64_t* hit_pos,
+                         uint32_t* hit_slot, uint64_t hit_cap, uint64_t* n_hits, uint64_t* stats,
+                         void* stream) {
+  if (!t || !s || !n_hits) return fail(KDF_ERR_ARG, "kdf_scan_stream_hits: NULL argument");
+  if (hit_cap && (!hit_pos || !hit_slot)) return fail(KDF_ERR_ARG, "kdf_scan_stream_hits: NULL hit arrays");
+  if (t->capacity > 0xffffffffull)
+    return fail(KDF_ERR_ARG, "kdf_scan_stream_hits: table capacity must fit 32-bit slot indices");
+  StreamView v = view_of(s);
+  if (v.n_words == 0) return KDF_OK;
+  HitSink sink = {(u64*)hit_pos, hit_slot, hit_cap, (u64*)n_hits};
+  if (t->key_words == 1)
+    return dispatch_stream<1>(t, v, OP_EMIT_HITS, 0, 0, (u64*)stats, sink, (cudaStream_t)stream);
+  return dispatch_stream<2>(t, v, OP_EMIT_HITS, 0, 0, (u64*)stats, sink, (cudaStream_t)stream);
 }
-
-extern "C" {
 
 int kdf_update_keys(kdf_table* t, const uint64_t* lo, const uint64_t* hi, uint64_t n, int mode,
                     int plane, uint32_t arg, uint64_t* stats, void* stream) {
@@ -770,29 +1174,13 @@ int kdf_update_keys(kdf_table* t, const uint64_t* lo, const uint64_t* hi, uint64
   if (n == 0) return KDF_OK;
   if (!lo || (t->key_words == 2 && !hi)) return fail(KDF_ERR_ARG, "kdf_update_keys: NULL key array");
   if (plane != 0 && plane != 1) return fail(KDF_ERR_ARG, "kdf_update_keys: plane must be 0 or 1");
+  if (mode < 0 || mode > KDF_MODE_MARK_IF_PRESENT) return fail(KDF_ERR_ARG, "kdf_update_keys: unknown mode");
   cudaStream_t st = (cudaStream_t)stream;
-  const u64* l = (const u64*)lo;
-  const u64* h = (const u64*)hi;
-  u64* sp = (u64*)stats;
-#define KDF_DISPATCH(KW)                                                                       \
-  switch (mode) {                                                                              \
-    case KDF_MODE_INSERT_COUNT:                                                                \
-      return launch_update_keys<KW, KDF_MODE_INSERT_COUNT>(t, l, h, n, plane, arg, sp, st);    \
-    case KDF_MODE_INSERT_ONLY:                                                                 \
-      return launch_update_keys<KW, KDF_MODE_INSERT_ONLY>(t, l, h, n, plane, arg, sp, st);     \
-    case KDF_MODE_COUNT_IF_PRESENT:                                                            \
-      return launch_update_keys<KW, KDF_MODE_COUNT_IF_PRESENT>(t, l, h, n, plane, arg, sp, st); \
-    case KDF_MODE_MARK_IF_PRESENT:                                                             \
-      return launch_update_keys<KW, KDF_MODE_MARK_IF_PRESENT>(t, l, h, n, plane, arg, sp, st); \
-    default:                                                                                   \
-      return fail(KDF_ERR_ARG, "kdf_update_keys: unknown mode");                               \
-  }
-  if (t->key_words == 1) {
-    KDF_DISPATCH(1)
-  } else {
-    KDF_DISPATCH(2)
-  }
-#undef KDF_DISPATCH
+  if (t->key_words == 1)
+    return dispatch_update_keys<1>(t, (const u64*)lo, (const u64*)hi, n, nullptr, mode, plane, arg,
+                                   (u64*)stats, st);
+  return dispatch_update_keys<2>(t, (const u64*)lo, (const u64*)hi, n, nullptr, mode, plane, arg,
+                                 (u64*)stats, st);
 }
 
 int kdf_threshold_compact(const kdf_table* t, uint32_t min0, uint32_t max0, uint32_t min1,
@@ -800,19 +1188,11 @@ int kdf_threshold_compact(const kdf_table* t, uint32_t min0, uint32_t max0, uint
                           uint32_t* out_p1, uint64_t cap, uint64_t* n_out, void* stream) {
   if (!t || !n_out) return fail(KDF_ERR_ARG, "kdf_threshold_compact: NULL argument");
   cudaStream_t st = (cudaStream_t)stream;
-  if (t->key_words == 1) {
-    TableView<1> tv{(Slot1*)t->slots, t->capacity};
-    int g = grid_for((const void*)k_threshold_compact<1>, 256, t->capacity, t->sm_count);
-    k_threshold_compact<1><<<g, 256, 0, st>>>(tv, min0, max0, min1, max1, (u64*)out_lo, (u64*)out_hi,
-                                              out_p0, out_p1, cap, (u64*)n_out);
-  } else {
-    TableView<2> tv{(Slot2*)t->slots, t->capacity};
-    int g = grid_for((const void*)k_threshold_compact<2>, 256, t->capacity, t->sm_count);
-    k_threshold_compact<2><<<g, 256, 0, st>>>(tv, min0, max0, min1, max1, (u64*)out_lo, (u64*)out_hi,
-                                              out_p0, out_p1, cap, (u64*)n_out);
-  }
-  CUDA_TRY(cudaGetLastError());
-  return KDF_OK;
+  if (t->key_words == 1)
+    return launch_threshold<1>(t, min0, max0, min1, max1, (u64*)out_lo, (u64*)out_hi, out_p0, out_p1,
+                               cap, (u64*)n_out, 0, nullptr, nullptr, st);
+  return launch_threshold<2>(t, min0, max0, min1, max1, (u64*)out_lo, (u64*)out_hi, out_p0, out_p1, cap,
+                             (u64*)n_out, 0, nullptr, nullptr, st);
 }
 
 int kdf_lookup_keys(const kdf_table* t, const uint64_t* lo, const uint64_t* hi, uint64_t n,
@@ -822,12 +1202,12 @@ int kdf_lookup_keys(const kdf_table* t, const uint64_t* lo, const uint64_t* hi, 
   if (!lo || (t->key_words == 2 && !hi)) return fail(KDF_ERR_ARG, "kdf_lookup_keys: NULL key array");
   cudaStream_t st = (cudaStream_t)stream;
   if (t->key_words == 1) {
-    TableView<1> tv{(Slot1*)t->slots, t->capacity};
-    int g = grid_for((const void*)k_lookup_keys<1>, 256, n, t->sm_count);
+    TableView<1> tv = view_of_table<1>(t);
+    int g = grid_for((const void*)k_lookup_keys<1>, 256, 0, n, t->sm_count);
     k_lookup_keys<1><<<g, 256, 0, st>>>(tv, (const u64*)lo, (const u64*)hi, n, out_found, out_p0, out_p1);
   } else {
-    TableView<2> tv{(Slot2*)t->slots, t->capacity};
-    int g = grid_for((const void*)k_lookup_keys<2>, 256, n, t->sm_count);
+    TableView<2> tv = view_of_table<2>(t);
+    int g = grid_for((const void*)k_lookup_keys<2>, 256, 0, n, t->sm_count);
     k_lookup_keys<2><<<g, 256, 0, st>>>(tv, (const u64*)lo, (const u64*)hi, n, out_found, out_p0, out_p1);
   }
   CUDA_TRY(cudaGetLastError());
@@ -841,12 +1221,12 @@ int kdf_add_planes(kdf_table* t, const uint64_t* lo, const uint64_t* hi, uint64_
   if (!lo || (t->key_words == 2 && !hi)) return fail(KDF_ERR_ARG, "kdf_add_planes: NULL key array");
   cudaStream_t st = (cudaStream_t)stream;
   if (t->key_words == 1) {
-    TableView<1> tv{(Slot1*)t->slots, t->capacity};
-    int g = grid_for((const void*)k_add_planes<1>, 256, n, t->sm_count);
+    TableView<1> tv = view_of_table<1>(t);
+    int g = grid_for((const void*)k_add_planes<1>, 256, 0, n, t->sm_count);
     k_add_planes<1><<<g, 256, 0, st>>>(tv, (const u64*)lo, (const u64*)hi, n, add0, add1, (u64*)n_missing);
   } else {
-    TableView<2> tv{(Slot2*)t->slots, t->capacity};
-    int g = grid_for((const void*)k_add_planes<2>, 256, n, t->sm_count);
+    TableView<2> tv = view_of_table<2>(t);
+    int g = grid_for((const void*)k_add_planes<2>, 256, 0, n, t->sm_count);
     k_add_planes<2><<<g, 256, 0, st>>>(tv, (const u64*)lo, (const u64*)hi, n, add0, add1, (u64*)n_missing);
   }
   CUDA_TRY(cudaGetLastError());
@@ -868,14 +1248,14 @@ int kdf_scan_reads(const kdf_table* t, const kdf_stream* s, const uint64_t* read
   cudaStream_t st = (cudaStream_t)stream;
   const int block = SCAN_WARPS * 32;
   if (t->key_words == 1) {
-    TableView<1> tv{(Slot1*)t->slots, t->capacity};
-    int g = grid_for((const void*)k_scan_reads<1>, block, n_reads * 32, t->sm_count);
+    TableView<1> tv = view_of_table<1>(t);
+    int g = grid_for((const void*)k_scan_reads<1>, block, 0, n_reads * 32, t->sm_count);
     k_scan_reads<1><<<g, block, 0, st>>>(tv, v, t->k, (const u64*)read_starts, read_lens, n_reads, min_distinct,
                                          out_ndistinct, out_nhits, (u64*)hit_pos, hit_slot, hit_cap,
                                          (u64*)n_hits, (u64*)stats);
   } else {
-    TableView<2> tv{(Slot2*)t->slots, t->capacity};
-    int g = grid_for((const void*)k_scan_reads<2>, block, n_reads * 32, t->sm_count);
+    TableView<2> tv = view_of_table<2>(t);
+    int g = grid_for((const void*)k_scan_reads<2>, block, 0, n_reads * 32, t->sm_count);
     k_scan_reads<2><<<g, block, 0, st>>>(tv, v, t->k, (const u64*)read_starts, read_lens, n_reads, min_distinct,
                                          out_ndistinct, out_nhits, (u64*)hit_pos, hit_slot, hit_cap,
                                          (u64*)n_hits, (u64*)stats);
@@ -884,35 +1264,177 @@ int kdf_scan_reads(const kdf_table* t, const kdf_stream* s, const uint64_t* read
   return KDF_OK;
 }
 
-int kdf_partition_stream(const kdf_stream* s, int k, int n_ranks, uint64_t* counts,
-                         const uint64_t* bin_offsets, uint64_t* cursors, uint64_t* out_lo,
-                         uint64_t* out_hi, void* stream) {
-  if (!s) return fail(KDF_ERR_ARG, "kdf_partition_stream: NULL stream");
+size_t kdf_reduce_hits_scratch_bytes(uint64_t n_hits) {
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const u64*)nullptr, (u64*)nullptr,
+                                  (const u32*)nullptr, (u32*)nullptr, (int)n_hits);
+  // sorted pos + sorted slot + cub temp, each 256-byte aligned
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  return al(n_hits * 8) + al(n_hits * 4) + al(tmp) + 256;
+}
+
+int kdf_reduce_hits(const uint64_t* hit_pos, const uint32_t* hit_slot, uint64_t n_hits,
+                    const uint64_t* read_starts, uint64_t n_reads, void* scratch,
+                    size_t scratch_bytes, uint64_t* sorted_pos_out, uint32_t* sorted_slot_out,
+                    uint64_t* rec_read, uint32_t* rec_ndistinct, uint32_t* rec_nhits,
+                    uint64_t* rec_first, uint64_t* n_recs, void* stream) {
+  if (n_hits == 0) return KDF_OK;
+  if (!hit_pos || !hit_slot || !read_starts || !n_reads || !scratch || !rec_read || !rec_ndistinct ||
+      !rec_nhits || !rec_first || !n_recs)
+    return fail(KDF_ERR_ARG, "kdf_reduce_hits: NULL argument");
+  if (n_hits > 0x7fffffffull) return fail(KDF_ERR_ARG, "kdf_reduce_hits: too many hits for one call");
+  if (scratch_bytes < kdf_reduce_hits_scratch_bytes(n_hits))
+    return fail(KDF_ERR_CAPACITY, "kdf_reduce_hits: scratch too small");
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  char* p = (char*)(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+  u64* spos = sorted_pos_out ? (u64*)sorted_pos_out : (u64*)p;
+  p += al(n_hits * 8);
+  u32* sslot = sorted_slot_out ? sorted_slot_out : (u32*)p;
+  p += al(n_hits * 4);
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const u64*)hit_pos, spos, hit_slot, sslot, (int)n_hits);
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(p, tmp, (const u64*)hit_pos, spos, hit_slot, sslot,
+                                           (int)n_hits, 0, 64, st));
+  int g = (int)((n_hits + 127) / 128);
+  k_reduce_hits<<<g, 128, 0, st>>>(spos, sslot, n_hits, (const u64*)read_starts, n_reads, (u64*)rec_read,
+                                   rec_ndistinct, rec_nhits, (u64*)rec_first, (u64*)n_recs);
+  CUDA_TRY(cudaGetLastError());
+  return KDF_OK;
+}
+
+// ---- binning -------------------------------------------------------------
+static int bin_qcap(int n_parts, int kw) {
+  // ~64 KB of queues per CTA -> 3 CTAs per SM
+  int q = (64 * 1024) / (n_parts * 8 * kw);
+  if (q > 96) q = 96;
+  if (q < 8) q = 8;
+  return q;
+}
+
+int kdf_bin_stream(const kdf_stream* s, int k, int by_owner, int n_parts, uint64_t* bins,
+                   uint64_t bin_cap, uint64_t* cursors, uint64_t* overflow, uint64_t* stats,
+                   void* stream) {
+  if (!s || !bins || !cursors || !overflow) return fail(KDF_ERR_ARG, "kdf_bin_stream: NULL argument");
   int kw = kdf_key_words(k);
-  if (!kw) return fail(KDF_ERR_ARG, "kdf_partition_stream: k must be in 1..64");
-  if (n_ranks < 1 || n_ranks > MAX_RANKS) return fail(KDF_ERR_ARG, "kdf_partition_stream: n_ranks must be 1..64");
-  bool scatter = out_lo != nullptr;
-  if (!scatter && !counts) return fail(KDF_ERR_ARG, "kdf_partition_stream: counts required for the histogram pass");
-  if (scatter && (!bin_offsets || !cursors || (kw == 2 && !out_hi)))
-    return fail(KDF_ERR_ARG, "kdf_partition_stream: scatter pass needs bin_offsets, cursors and outputs");
+  if (!kw) return fail(KDF_ERR_ARG, "kdf_bin_stream: k must be in 1..64");
+  if (n_parts < 1 || n_parts > BIN_MAX_PARTS) return fail(KDF_ERR_ARG, "kdf_bin_stream: n_parts must be 1..256");
+  int log2p = 0;
+  if (!by_owner) {
+    while ((1 << log2p) < n_parts) ++log2p;
+    if ((1 << log2p) != n_parts) return fail(KDF_ERR_ARG, "kdf_bin_stream: hash-range bins need a power-of-two count");
+  }
   StreamView v = view_of(s);
   if (v.n_words == 0) return KDF_OK;
   int sm = current_sm_count();
   cudaStream_t st = (cudaStream_t)stream;
-#define KDF_PART(KW, SC)                                                                   \
-  {                                                                                        \
-    int g = grid_for((const void*)k_partition_stream<KW, SC>, 256, v.n_words, sm);         \
-    k_partition_stream<KW, SC><<<g, 256, 0, st>>>(v, k, (u32)n_ranks, (u64*)counts,        \
-                                                  (const u64*)bin_offsets, (u64*)cursors,  \
-                                                  (u64*)out_lo, (u64*)out_hi);             \
+  int qcap = bin_qcap(n_parts, kw);
+#define KDF_BIN(KW, OWN)                                                                          \
+  {                                                                                               \
+    size_t smem = BinStage<KW>::bytes(n_parts, qcap);                                             \
+    const void* fn = (const void*)k_bin_stream<KW, OWN>;                                          \
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    int g = grid_for(fn, BIN_THREADS, smem, v.n_words, sm);                                       \
+    k_bin_stream<KW, OWN><<<g, BIN_THREADS, smem, st>>>(v, k, log2p, (u32)n_parts, qcap, (u64*)bins, \
+                                                        bin_cap, (u64*)cursors, (u64*)overflow,   \
+                                                        (u64*)stats);                             \
   }
   if (kw == 1) {
-    if (scatter) KDF_PART(1, true) else KDF_PART(1, false)
+    if (by_owner) KDF_BIN(1, true) else KDF_BIN(1, false)
   } else {
-    if (scatter) KDF_PART(2, true) else KDF_PART(2, false)
+    if (by_owner) KDF_BIN(2, true) else KDF_BIN(2, false)
   }
-#undef KDF_PART
+#undef KDF_BIN
   CUDA_TRY(cudaGetLastError());
+  return KDF_OK;
+}
+
+int kdf_bin_keys(const uint64_t* lo, const uint64_t* hi, uint64_t n, int k, int by_owner,
+                 int n_parts, uint64_t* bins, uint64_t bin_cap, uint64_t* cursors,
+                 uint64_t* overflow, void* stream) {
+  if (!bins || !cursors || !overflow) return fail(KDF_ERR_ARG, "kdf_bin_keys: NULL argument");
+  int kw = kdf_key_words(k);
+  if (!kw) return fail(KDF_ERR_ARG, "kdf_bin_keys: k must be in 1..64");
+  if (n == 0) return KDF_OK;
+  if (!lo) return fail(KDF_ERR_ARG, "kdf_bin_keys: NULL key array");
+  if (n_parts < 1 || n_parts > BIN_MAX_PARTS) return fail(KDF_ERR_ARG, "kdf_bin_keys: n_parts must be 1..256");
+  int log2p = 0;
+  if (!by_owner) {
+    while ((1 << log2p) < n_parts) ++log2p;
+    if ((1 << log2p) != n_parts) return fail(KDF_ERR_ARG, "kdf_bin_keys: hash-range bins need a power-of-two count");
+  }
+  int sm = current_sm_count();
+  cudaStream_t st = (cudaStream_t)stream;
+  int qcap = bin_qcap(n_parts, kw);
+#define KDF_BINK(KW, OWN)                                                                         \
+  {                                                                                               \
+    size_t smem = BinStage<KW>::bytes(n_parts, qcap);                                             \
+    const void* fn = (const void*)k_bin_keys<KW, OWN>;                                            \
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    int g = grid_for(fn, BIN_THREADS, smem, (n + BIN_WPR - 1) / BIN_WPR, sm);                     \
+    k_bin_keys<KW, OWN><<<g, BIN_THREADS, smem, st>>>((const u64*)lo, (const u64*)hi, n, log2p,   \
+                                                      (u32)n_parts, qcap, (u64*)bins, bin_cap,    \
+                                                      (u64*)cursors, (u64*)overflow);             \
+  }
+  if (kw == 1) {
+    if (by_owner) KDF_BINK(1, true) else KDF_BINK(1, false)
+  } else {
+    if (by_owner) KDF_BINK(2, true) else KDF_BINK(2, false)
+  }
+#undef KDF_BINK
+  CUDA_TRY(cudaGetLastError());
+  return KDF_OK;
+}
+
+int kdf_count_bins(int k, int n_parts, const uint64_t* child_bins, uint64_t child_bin_cap,
+                   const uint64_t* child_cursors, const uint64_t* ref_bins, uint64_t ref_bin_cap,
+                   const uint64_t* ref_cursors, void* slice, uint64_t slice_capacity,
+                   uint32_t min0, uint32_t max0, uint32_t min1, uint32_t max1, uint64_t* out_lo,
+                   uint64_t* out_hi, uint32_t* out_p0, uint32_t* out_p1, uint64_t out_cap,
+                   uint64_t* n_out, uint32_t count_min0, uint64_t* counters, void* stream) {
+  if (!child_bins || !child_cursors || !slice || !n_out || !counters)
+    return fail(KDF_ERR_ARG, "kdf_count_bins: NULL argument");
+  int rc = check_table_args(k, slice_capacity, slice, "kdf_count_bins");
+  if (rc != KDF_OK) return rc;
+  int log2p = 0;
+  while ((1 << log2p) < n_parts) ++log2p;
+  if (n_parts < 1 || n_parts > BIN_MAX_PARTS || (1 << log2p) != n_parts)
+    return fail(KDF_ERR_ARG, "kdf_count_bins: n_parts must be a power of two <= 256");
+  kdf_table t;
+  t.k = k;
+  t.key_words = kdf_key_words(k);
+  t.capacity = slice_capacity;
+  t.base = slice;
+  t.sm_count = current_sm_count();
+  t.log2_parts = log2p;
+  cudaStream_t st = (cudaStream_t)stream;
+  u64* ctr = (u64*)counters;  // [0..3] = stats block (windows = keys applied, full, hits, new), [4] = #(p0 >= count_min0), [5] = #occupied
+  const int kw = t.key_words;
+  for (int p = 0; p < n_parts; ++p) {
+    rc = clear_table_async(&t, st);
+    if (rc != KDF_OK) return rc;
+    const u64* cb = (const u64*)child_bins + (u64)p * child_bin_cap * kw;
+    if (kw == 1)
+      rc = launch_update_keys<1, OP_INSERT_COUNT>(&t, cb, nullptr, child_bin_cap, (const u64*)child_cursors + p, 0, 1, ctr, st);
+    else
+      rc = launch_update_keys<2, OP_INSERT_COUNT>(&t, cb, nullptr, child_bin_cap, (const u64*)child_cursors + p, 0, 1, ctr, st);
+    if (rc != KDF_OK) return rc;
+    if (ref_bins && ref_cursors) {
+      const u64* rb = (const u64*)ref_bins + (u64)p * ref_bin_cap * kw;
+      if (kw == 1)
+        rc = launch_update_keys<1, OP_MARK_IF_PRESENT>(&t, rb, nullptr, ref_bin_cap, (const u64*)ref_cursors + p, 1, 1, nullptr, st);
+      else
+        rc = launch_update_keys<2, OP_MARK_IF_PRESENT>(&t, rb, nullptr, ref_bin_cap, (const u64*)ref_cursors + p, 1, 1, nullptr, st);
+      if (rc != KDF_OK) return rc;
+    }
+    if (kw == 1)
+      rc = launch_threshold<1>(&t, min0, max0, min1, max1, (u64*)out_lo, (u64*)out_hi, out_p0, out_p1, out_cap,
+                               (u64*)n_out, count_min0, ctr + 4, ctr + 5, st);
+    else
+      rc = launch_threshold<2>(&t, min0, max0, min1, max1, (u64*)out_lo, (u64*)out_hi, out_p0, out_p1, out_cap,
+                               (u64*)n_out, count_min0, ctr + 4, ctr + 5, st);
+    if (rc != KDF_OK) return rc;
+  }
   return KDF_OK;
 }
 
@@ -920,7 +1442,7 @@ int kdf_bench_random_access(void* buf, uint64_t buf_bytes, uint64_t n_ops, int a
                             uint64_t* sink, void* stream) {
   if (!buf || buf_bytes < 32 || !sink) return fail(KDF_ERR_ARG, "kdf_bench_random_access: bad argument");
   int sm = current_sm_count();
-  int g = grid_for((const void*)k_bench_random, 256, n_ops / CHUNK + 1, sm);
+  int g = grid_for((const void*)k_bench_random, 256, 0, n_ops / 8 + 1, sm);
   k_bench_random<<<g, 256, 0, (cudaStream_t)stream>>>((u32*)buf, buf_bytes / 32, n_ops, atomic, (u64*)sink);
   CUDA_TRY(cudaGetLastError());
   return KDF_OK;
@@ -1013,6 +1535,30 @@ int kdf_debug_extract_host(const uint64_t* codes, const uint32_t* valid, uint64_
         it.advance();
       }
     }
+  }
+  return KDF_OK;
+}
+
+// Test hook: the hash functions of the device code, on the host.
+int kdf_debug_hash_host(const uint64_t* lo, const uint64_t* hi, uint64_t n, int key_words,
+                        int log2_parts, uint32_t n_buckets, uint32_t n_ranks, uint32_t* out_part,
+                        uint32_t* out_bucket, uint32_t* out_owner) {
+  if (!lo || (key_words == 2 && !hi)) return fail(KDF_ERR_ARG, "kdf_debug_hash_host: NULL keys");
+  for (u64 i = 0; i < n; ++i) {
+    u64 h;
+    if (key_words == 1) {
+      Key<1> k;
+      k.lo = lo[i];
+      h = hash_key(k);
+    } else {
+      Key<2> k;
+      k.lo = lo[i];
+      k.hi = hi[i];
+      h = hash_key(k);
+    }
+    if (out_part) out_part[i] = part_of(h, log2_parts);
+    if (out_bucket) out_bucket[i] = bucket_of(h, log2_parts, n_buckets);
+    if (out_owner) out_owner[i] = owner_of(h, n_ranks ? n_ranks : 1);
   }
   return KDF_OK;
 }

@@ -31,6 +31,87 @@ def default_child_capacity(eng, n_bases):
     return eng.capacity_for(max(n_bases // 8, 512))
 
 
+# One table slice of the partitioned child count: 2^21 slots = 32 MB of keys +
+# planes for 64-bit keys, a quarter of B200's L2, so a slice stays L2-resident
+# while its bin is streamed through it.
+SLICE_SLOTS = 1 << 21
+MAX_PARTS = 256
+
+
+def _pow2_at_least(x):
+    p = 1
+    while p < x:
+        p *= 2
+    return p
+
+
+def plan_partitions(n_windows_max, slots_needed=None):
+    """(n_parts, slice_capacity) for about ``slots_needed`` table slots in total."""
+    if slots_needed is None:
+        slots_needed = max(n_windows_max // 4, 1024)   # 4 bases per distinct k-mer, load 0.5
+    n_parts = min(MAX_PARTS, _pow2_at_least((slots_needed + SLICE_SLOTS - 1) // SLICE_SLOTS))
+    slice_cap = max(1024, (slots_needed + n_parts - 1) // n_parts)
+    return n_parts, (slice_cap + 3) & ~3
+
+
+def _bin_capacity(n_keys_max, n_parts):
+    mean = n_keys_max / n_parts
+    return int(mean + 8 * (mean ** 0.5) + 64)
+
+
+def count_child_partitioned(eng, child_streams, ref_streams, k, min_child_count,
+                            n_parts=None, slice_capacity=None):
+    """Module 1 + reference subtraction without a table in HBM: bin the child's
+    (and the reference's) canonical k-mers by hash range, then count each bin in
+    an L2-resident table slice and emit the keys with count >= min_child_count
+    that are not in the reference.
+
+    ``child_streams`` / ``ref_streams``: lists of DeviceStream.  Returns dict:
+    child_windows, ref_windows, child_distinct, candidates, non_ref, lo, hi."""
+    n_max = sum(s.n_bases for s in child_streams)
+    r_max = sum(s.n_bases for s in ref_streams)
+    p_auto, s_auto = plan_partitions(n_max)
+    n_parts = n_parts or p_auto
+    slice_capacity = slice_capacity or s_auto
+    bin_cap = _bin_capacity(n_max, n_parts)
+    ref_cap = _bin_capacity(r_max, n_parts)
+    while True:   # bins: retry with exact sizes if the hash ranges are skewed
+        cb = eng.new_bins(k, n_parts, bin_cap)
+        rb = eng.new_bins(k, n_parts, ref_cap) if ref_streams else None
+        st_c, st_r = eng.new_stats(), eng.new_stats()
+        for s in child_streams:
+            eng.bin_stream(cb, s, st_c)
+        for s in ref_streams:
+            eng.bin_stream(rb, s, st_r)
+        over_c = cb.overflowed()
+        over_r = rb.overflowed() if rb is not None else False
+        if not over_c and not over_r:
+            break
+        if over_c:
+            bin_cap = int(cb.counts().max()) + 4
+        if over_r:
+            ref_cap = int(rb.counts().max()) + 4
+        del cb, rb
+    out_cap = max(1 << 16, n_max // 64)
+    while True:   # slices / output: retry when a slice was full or the output too small
+        res = eng.count_bins(cb, rb, slice_capacity, min0=min_child_count, max1=0,
+                             count_min0=min_child_count, out_cap=out_cap)
+        if res["full"]:
+            if slice_capacity >= 2 * bin_cap:
+                raise _engine.KdfError("child k-mer table slice full at %d slots" % slice_capacity)
+            slice_capacity = min(slice_capacity * 4, 2 * bin_cap + 4)
+            continue
+        if res["n_out"] > out_cap:
+            out_cap = res["n_out"]
+            continue
+        break
+    return {"child_windows": eng.read_stats(st_c)["windows"],
+            "ref_windows": eng.read_stats(st_r)["windows"] if ref_streams else 0,
+            "child_distinct": res["distinct"], "candidates": res["n_count"],
+            "non_ref": res["n_out"], "lo": res["lo"], "hi": res["hi"],
+            "n_parts": n_parts, "slice_capacity": slice_capacity}
+
+
 def _primed_table(eng, k, lo, hi, n):
     t = eng.new_table(k, n_keys=max(n, 1))
     eng.update_keys(t, lo, hi, _engine.MODE_INSERT_ONLY, 0, 0)
@@ -39,7 +120,8 @@ def _primed_table(eng, k, lo, hi, n):
 
 def discover_streams(eng, child, mother, father, ref, k, min_child_count=3,
                      parent_max_count=0, min_distinct_kmers_per_read=None,
-                     child_capacity=None, want_hits=False, fetch=True):
+                     child_capacity=None, want_hits=False, fetch=True, partitioned=None,
+                     sparse_scan=True):
     """Child count → threshold → reference subtraction → mother / father
     filtered counts → proband-unique set → per-read distinct-hit reduction.
 
@@ -50,39 +132,51 @@ def discover_streams(eng, child, mother, father, ref, k, min_child_count=3,
     all stages (the unit of BASELINE.json's metric)."""
     if min_distinct_kmers_per_read is None:
         min_distinct_kmers_per_read = max(1, k // 4)   # discovery/pipeline.py:2119-2121
+    if partitioned is None:
+        partitioned = child_capacity is None
     stats = eng.new_stats()
     d_child = _on_device(eng, child, True)
     d_ref = _on_device(eng, ref, False)
     d_mother = _on_device(eng, mother, False)
     d_father = _on_device(eng, father, False)
 
-    # Module 1: jellyfish count -C ; dump -L min_child_count
-    # Sized for 4 bases per distinct k-mer (30x data holds ~14 bases per distinct
-    # k-mer); when that is too small the count is redone in a larger table — never
-    # a silent drop (Jellyfish would spill to .jf_N files and merge).
-    if child_capacity is None:
-        child_capacity = default_child_capacity(eng, d_child.n_bases)
-    while True:
-        table = eng.new_table(k, capacity=child_capacity)
-        eng.count_stream(table, d_child, _engine.MODE_INSERT_COUNT, 0, 1, stats)
-        st = eng.read_stats(stats)
-        if not st["full"]:
-            child_windows, child_distinct = st["windows"], st["new"]
-            break
+    # Module 1 + reference subtraction: jellyfish count -C ; dump -L ; query ref.jf
+    if partitioned:
+        c = count_child_partitioned(eng, [d_child], [d_ref], k, min_child_count)
+        n_cand, n_nonref, lo, hi = c["candidates"], c["non_ref"], c["lo"], c["hi"]
+        child_windows, child_distinct = c["child_windows"], c["child_distinct"]
+        child_capacity = c["n_parts"] * c["slice_capacity"]
+        units_binned = c["child_windows"] + c["ref_windows"]
+    else:
+        # direct form: one table in HBM, sized for 4 bases per distinct k-mer; when
+        # that is too small the count is redone in a larger table — never a silent
+        # drop (Jellyfish would spill to .jf_N files and merge).
+        units_binned = 0
+        if child_capacity is None:
+            child_capacity = default_child_capacity(eng, d_child.n_bases)
+        while True:
+            table = eng.new_table(k, capacity=child_capacity)
+            eng.count_stream(table, d_child, _engine.MODE_INSERT_COUNT, 0, 1, stats)
+            st = eng.read_stats(stats)
+            if not st["full"]:
+                child_windows, child_distinct = st["windows"], st["new"]
+                break
+            table.close()
+            if child_capacity >= 2 * d_child.n_bases:
+                raise _engine.KdfError("child k-mer table full at %d slots" % child_capacity)
+            child_capacity = min(child_capacity * 4, eng.capacity_for(d_child.n_bases))
+            stats.zero_()
+        # reference subtraction: stream the reference against the child table
+        eng.count_stream(table, d_ref, _engine.MODE_MARK_IF_PRESENT, REF_PLANE, 1, stats)
+        n_cand = eng.threshold_count(table, min0=min_child_count)
+        n_nonref, lo, hi, _a, _b = eng.threshold_compact(table, min0=min_child_count, max1=0)
+        eng.check_not_full(stats)
         table.close()
-        if child_capacity >= 2 * d_child.n_bases:
-            raise _engine.KdfError("child k-mer table full at %d slots" % child_capacity)
-        child_capacity = min(child_capacity * 4, eng.capacity_for(d_child.n_bases))
-        stats.zero_()
-    # reference subtraction: stream the reference against the child table
-    eng.count_stream(table, d_ref, _engine.MODE_MARK_IF_PRESENT, REF_PLANE, 1, stats)
-    n_cand = eng.threshold_count(table, min0=min_child_count)
-    n_nonref, lo, hi, _a, _b = eng.threshold_compact(table, min0=min_child_count, max1=0)
-    eng.check_not_full(stats)
-    table.close()
     out = {"child_windows": child_windows, "child_distinct": child_distinct,
-           "child_capacity": child_capacity, "candidates": n_cand, "non_ref": n_nonref, "after_mother": 0, "proband_unique": 0,
-           "pu": None, "ndistinct": None, "nhits": None, "informative_reads": 0, "hits": None}
+           "child_capacity": child_capacity, "candidates": n_cand,
+           "non_ref": n_nonref, "after_mother": 0, "proband_unique": 0,
+           "pu": None, "ndistinct": None, "nhits": None, "informative_reads": 0, "hits": None,
+           "reads": None}
 
     # Module 2: count --if against mother, then father
     n_pu = 0
@@ -103,18 +197,32 @@ def discover_streams(eng, child, mother, father, ref, k, min_child_count=3,
     if n_pu:
         out["pu"] = KmerSet(eng, k, lo, hi)
         pt = _primed_table(eng, k, lo, hi, n_pu)
-        res = eng.scan_reads(pt, d_child, min_distinct=min_distinct_kmers_per_read, stats=stats,
-                             want_hits=want_hits)
-        nd, nh = res["ndistinct"], res["nhits"]
-        if fetch:
-            nd = nd.cpu().numpy().view(np.uint32)
-            nh = nh.cpu().numpy().view(np.uint32)
-            out["informative_reads"] = int((nd >= min_distinct_kmers_per_read).sum())
-        out["ndistinct"], out["nhits"] = nd, nh
-        if want_hits:
-            out["hits"] = (res["hit_pos"], res["hit_slot"], pt)
-        else:
+        if sparse_scan:
+            # hits are rare: emit them from a streaming probe, reduce per read on the
+            # device, return one record per read that has hits
+            sp = eng.scan_reads_sparse(pt, d_child, stats=stats)
+            out["reads"] = sp
+            out["informative_reads"] = int((sp["ndistinct"] >= min_distinct_kmers_per_read).sum())
+            if fetch:
+                nd = np.zeros(d_child.n_reads, dtype=np.uint32)
+                nh = np.zeros(d_child.n_reads, dtype=np.uint32)
+                nd[sp["read"].astype(np.int64)] = sp["ndistinct"]
+                nh[sp["read"].astype(np.int64)] = sp["nhits"]
+                out["ndistinct"], out["nhits"] = nd, nh
             pt.close()
+        else:
+            res = eng.scan_reads(pt, d_child, min_distinct=min_distinct_kmers_per_read,
+                                 stats=stats, want_hits=want_hits)
+            nd, nh = res["ndistinct"], res["nhits"]
+            if fetch:
+                nd = nd.cpu().numpy().view(np.uint32)
+                nh = nh.cpu().numpy().view(np.uint32)
+                out["informative_reads"] = int((nd >= min_distinct_kmers_per_read).sum())
+            out["ndistinct"], out["nhits"] = nd, nh
+            if want_hits:
+                out["hits"] = (res["hit_pos"], res["hit_slot"], pt)
+            else:
+                pt.close()
     st = eng.read_stats(stats)
-    out["units"] = st["windows"]
+    out["units"] = st["windows"] + units_binned
     return out

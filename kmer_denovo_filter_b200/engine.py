@@ -67,7 +67,15 @@ _SIGNATURES = {
     "kdf_lookup_keys": (_i, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp]),
     "kdf_scan_reads": (_i, [_vp, ctypes.POINTER(_Stream), _vp, _vp, _u64, _u32, _vp, _vp, _vp, _vp,
                             _u64, _vp, _vp, _vp]),
-    "kdf_partition_stream": (_i, [ctypes.POINTER(_Stream), _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "kdf_scan_stream_hits": (_i, [_vp, ctypes.POINTER(_Stream), _vp, _vp, _u64, _vp, _vp, _vp]),
+    "kdf_reduce_hits_scratch_bytes": (ctypes.c_size_t, [_u64]),
+    "kdf_reduce_hits": (_i, [_vp, _vp, _u64, _vp, _u64, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp, _vp,
+                             _vp, _vp, _vp]),
+    "kdf_bin_stream": (_i, [ctypes.POINTER(_Stream), _i, _i, _i, _vp, _u64, _vp, _vp, _vp, _vp]),
+    "kdf_bin_keys": (_i, [_vp, _vp, _u64, _i, _i, _i, _vp, _u64, _vp, _vp, _vp]),
+    "kdf_count_bins": (_i, [_i, _i, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _u64, _u32, _u32, _u32, _u32,
+                            _vp, _vp, _vp, _vp, _u64, _vp, _u32, _vp, _vp]),
+    "kdf_debug_hash_host": (_i, [_vp, _vp, _u64, _i, _i, _u32, _u32, _vp, _vp, _vp]),
     "kdf_pack_sequences": (_u64, [_vp, _vp, _u64, _vp, _vp, _vp]),
     "kdf_debug_extract_host": (_i, [_vp, _vp, _u64, _i, _i, _vp, _vp, _vp]),
     "kdf_bench_random_access": (_i, [_vp, _u64, _u64, _i, _vp, _vp]),
@@ -215,7 +223,7 @@ class KmerTable:
     def __init__(self, engine, k, capacity):
         self.engine = engine
         self.k = int(k)
-        self.capacity = int(capacity)
+        self.capacity = max(4, (int(capacity) + 3) & ~3)   # whole 32-byte buckets
         lib = engine.lib
         self.key_words = lib.kdf_key_words(self.k)
         if not self.key_words:
@@ -244,6 +252,61 @@ class KmerTable:
             self.close()
         except Exception:
             pass
+
+
+class KeyBins:
+    """Fixed-capacity bins of canonical k-mers in HBM (``kdf_bin_stream``)."""
+
+    def __init__(self, engine, k, n_parts, bin_cap, by_owner=False):
+        torch = engine.torch
+        self.engine = engine
+        self.k = int(k)
+        self.key_words = engine.lib.kdf_key_words(self.k)
+        if not self.key_words:
+            raise KdfError("k=%d unsupported by the GPU engine (1..64)" % k)
+        self.n_parts = int(n_parts)
+        self.bin_cap = max(4, (int(bin_cap) + 3) & ~3)
+        self.by_owner = bool(by_owner)
+        self.data = torch.empty(self.n_parts * self.bin_cap * self.key_words, dtype=torch.int64,
+                                device=engine.device)
+        self.cursors = torch.zeros(self.n_parts, dtype=torch.int64, device=engine.device)
+        self.overflow = torch.zeros(1, dtype=torch.int64, device=engine.device)
+
+    def counts(self):
+        """Keys *offered* to each bin (may exceed bin_cap after an overflow)."""
+        return self.cursors.cpu().numpy().astype(np.int64)
+
+    def overflowed(self):
+        return bool(int(self.overflow.item()))
+
+    def bin_keys(self, b, count=None):
+        """(lo, hi|None) device views of bin b."""
+        n = int(self.cursors[b].item()) if count is None else int(count)
+        n = min(n, self.bin_cap)
+        kw = self.key_words
+        seg = self.data[b * self.bin_cap * kw:(b * self.bin_cap + n) * kw]
+        if kw == 1:
+            return seg, None
+        pair = seg.view(-1, 2)
+        return pair[:, 0].contiguous(), pair[:, 1].contiguous()
+
+
+def debug_hash_host(lo, hi, key_words, log2_parts, n_buckets, n_ranks):
+    """Partition / bucket / owner of each key, computed on the host by the same
+    code the kernels use (test hook)."""
+    lib = load_library()
+    lo = np.ascontiguousarray(lo, dtype=np.uint64)
+    hi = np.ascontiguousarray(hi, dtype=np.uint64) if hi is not None else None
+    n = lo.shape[0]
+    part = np.zeros(max(n, 1), np.uint32)
+    bucket = np.zeros(max(n, 1), np.uint32)
+    owner = np.zeros(max(n, 1), np.uint32)
+    rc = lib.kdf_debug_hash_host(_np_ptr(lo), _np_ptr(hi) if hi is not None else None, n, key_words,
+                                 log2_parts, n_buckets, n_ranks, _np_ptr(part), _np_ptr(bucket),
+                                 _np_ptr(owner))
+    if rc != KDF_OK:
+        raise KdfError(lib.kdf_last_error().decode())
+    return part[:n], bucket[:n], owner[:n]
 
 
 class CudaEngine:
@@ -503,28 +566,128 @@ class CudaEngine:
                 "hit_pos": hp[:total] if hp is not None else None,
                 "hit_slot": hsl[:total] if hsl is not None else None, "n_hits": total}
 
-    def partition_stream(self, ds, k, n_ranks):
-        """K6 → (counts np.int64[n_ranks], lo, hi|None) with keys grouped by owner."""
+    def scan_reads_sparse(self, table, ds, stats=None, hit_cap=None):
+        """K4+K5, sparse form: emit every hit window, then reduce per read on the
+        device.  Returns dict(read u64[], ndistinct u32[], nhits u32[], first u64[],
+        hit_pos u64[] sorted, hit_slot u32[] sorted) as numpy arrays holding one
+        record per read with at least one hit, ordered by read index."""
         torch = self.torch
-        kw = self.lib.kdf_key_words(k)
-        counts = self.zeros(n_ranks, torch.int64)
-        self._check(self.lib.kdf_partition_stream(ds.c(), k, n_ranks, counts.data_ptr(),
-                                                  None, None, None, None, self.stream_ptr()))
-        self.launches += 1
-        c = counts.cpu().numpy().astype(np.int64)
-        total = int(c.sum())
-        offs = np.zeros(n_ranks, dtype=np.int64)
-        offs[1:] = np.cumsum(c[:-1])
-        d_offs = torch.from_numpy(offs).to(self.device)
-        cursors = self.zeros(n_ranks, torch.int64)
-        lo = self.empty(max(total, 1), torch.int64)
-        hi = self.empty(max(total, 1), torch.int64) if kw == 2 else None
-        if total:
-            self._check(self.lib.kdf_partition_stream(
-                ds.c(), k, n_ranks, counts.data_ptr(), d_offs.data_ptr(), cursors.data_ptr(),
-                lo.data_ptr(), hi.data_ptr() if hi is not None else None, self.stream_ptr()))
+        if hit_cap is None:
+            hit_cap = 1 << 20
+        while True:
+            n_hits = self.zeros(1, torch.int64)
+            hp = self.empty(max(hit_cap, 1), torch.int64)
+            hsl = self.empty(max(hit_cap, 1), torch.int32)
+            st = self.zeros(N_STATS, torch.int64) if stats is not None else None
+            ev = self._t0()
+            self._check(self.lib.kdf_scan_stream_hits(
+                table.handle, ds.c(), hp.data_ptr(), hsl.data_ptr(), hit_cap, n_hits.data_ptr(),
+                st.data_ptr() if st is not None else None, self.stream_ptr()))
+            self._t1("scan_stream_hits/kw%d" % table.key_words, ev)
             self.launches += 1
-        return c, lo[:total], (hi[:total] if hi is not None else None)
+            total = int(n_hits.item())
+            if total <= hit_cap:
+                break
+            hit_cap = total
+        if stats is not None:
+            stats += st
+        empty = {"read": np.zeros(0, np.uint64), "ndistinct": np.zeros(0, np.uint32),
+                 "nhits": np.zeros(0, np.uint32), "first": np.zeros(0, np.uint64),
+                 "hit_pos": np.zeros(0, np.uint64), "hit_slot": np.zeros(0, np.uint32)}
+        if total == 0:
+            return empty
+        n_reads = ds.n_reads
+        nbytes = int(self.lib.kdf_reduce_hits_scratch_bytes(total))
+        scratch = self.empty(nbytes, torch.uint8)
+        spos = self.empty(total, torch.int64)
+        sslot = self.empty(total, torch.int32)
+        rr = self.empty(total, torch.int64)
+        rnd = self.empty(total, torch.int32)
+        rnh = self.empty(total, torch.int32)
+        rf = self.empty(total, torch.int64)
+        n_recs = self.zeros(1, torch.int64)
+        ev = self._t0()
+        self._check(self.lib.kdf_reduce_hits(
+            hp.data_ptr(), hsl.data_ptr(), total, ds.read_starts.data_ptr(), n_reads,
+            scratch.data_ptr(), nbytes, spos.data_ptr(), sslot.data_ptr(), rr.data_ptr(),
+            rnd.data_ptr(), rnh.data_ptr(), rf.data_ptr(), n_recs.data_ptr(), self.stream_ptr()))
+        self._t1("reduce_hits", ev)
+        self.launches += 3   # radix sort passes + reduce
+        n = int(n_recs.item())
+        read = rr[:n].cpu().numpy().view(np.uint64)
+        order = np.argsort(read, kind="stable")
+        return {"read": read[order],
+                "ndistinct": rnd[:n].cpu().numpy().view(np.uint32)[order],
+                "nhits": rnh[:n].cpu().numpy().view(np.uint32)[order],
+                "first": rf[:n].cpu().numpy().view(np.uint64)[order],
+                "hit_pos": spos.cpu().numpy().view(np.uint64),
+                "hit_slot": sslot.cpu().numpy().view(np.uint32)}
+
+    # -- binning ---------------------------------------------------------------
+    def new_bins(self, k, n_parts, bin_cap, by_owner=False):
+        return KeyBins(self, k, n_parts, bin_cap, by_owner)
+
+    def bin_stream(self, bins, ds, stats=None):
+        """K2p / K6: append the canonical k-mers of a stream to hash-range (or owner) bins."""
+        ev = self._t0()
+        self._check(self.lib.kdf_bin_stream(
+            ds.c(), bins.k, 1 if bins.by_owner else 0, bins.n_parts, bins.data.data_ptr(),
+            bins.bin_cap, bins.cursors.data_ptr(), bins.overflow.data_ptr(),
+            stats.data_ptr() if stats is not None else None, self.stream_ptr()))
+        self._t1("bin_stream/kw%d" % bins.key_words, ev)
+        self.launches += 1
+
+    def bin_keys(self, bins, lo, hi=None, n=None):
+        n = int(lo.shape[0]) if n is None else int(n)
+        if not n:
+            return
+        ev = self._t0()
+        self._check(self.lib.kdf_bin_keys(
+            lo.data_ptr(), hi.data_ptr() if hi is not None else None, n, bins.k,
+            1 if bins.by_owner else 0, bins.n_parts, bins.data.data_ptr(), bins.bin_cap,
+            bins.cursors.data_ptr(), bins.overflow.data_ptr(), self.stream_ptr()))
+        self._t1("bin_keys/kw%d" % bins.key_words, ev)
+        self.launches += 1
+
+    def count_bins(self, child_bins, ref_bins, slice_capacity, min0=0, max0=U32_MAX, min1=0,
+                   max1=U32_MAX, count_min0=0, out_cap=1 << 20, want_planes=False):
+        """Count every bin in an L2-resident slice and emit (see include/kdf.h).
+        Returns dict(n_out, lo, hi, p0, p1, keys, full, hits, distinct, n_count, occupied);
+        lo/hi/p0/p1 hold min(n_out, out_cap) entries."""
+        torch = self.torch
+        k = child_bins.k
+        kw = child_bins.key_words
+        slice_capacity = max(4, (int(slice_capacity) + 3) & ~3)
+        slice_buf = self.empty(self.lib.kdf_table_bytes(slice_capacity, kw) // 8, torch.int64)
+        lo = self.empty(max(out_cap, 1), torch.int64)
+        hi = self.empty(max(out_cap, 1), torch.int64) if kw == 2 else None
+        p0 = self.empty(max(out_cap, 1), torch.int32) if want_planes else None
+        p1 = self.empty(max(out_cap, 1), torch.int32) if want_planes else None
+        n_out = self.zeros(1, torch.int64)
+        ctr = self.zeros(6, torch.int64)
+        ev = self._t0()
+        self._check(self.lib.kdf_count_bins(
+            k, child_bins.n_parts, child_bins.data.data_ptr(), child_bins.bin_cap,
+            child_bins.cursors.data_ptr(),
+            ref_bins.data.data_ptr() if ref_bins is not None else None,
+            ref_bins.bin_cap if ref_bins is not None else 0,
+            ref_bins.cursors.data_ptr() if ref_bins is not None else None,
+            slice_buf.data_ptr(), slice_capacity, min0, max0, min1, max1, lo.data_ptr(),
+            hi.data_ptr() if hi is not None else None,
+            p0.data_ptr() if p0 is not None else None, p1.data_ptr() if p1 is not None else None,
+            out_cap, n_out.data_ptr(), count_min0, ctr.data_ptr(), self.stream_ptr()))
+        self._t1("count_bins/kw%d" % kw, ev)
+        self.launches += child_bins.n_parts * (4 + (1 if ref_bins is not None else 0))
+        c = ctr.cpu().numpy().view(np.uint64)
+        n = int(n_out.item())
+        m = min(n, out_cap)
+        return {"n_out": n, "lo": lo[:m], "hi": hi[:m] if hi is not None else None,
+                "p0": p0[:m] if p0 is not None else None, "p1": p1[:m] if p1 is not None else None,
+                "keys": int(c[0]), "full": int(c[1]), "hits": int(c[2]), "distinct": int(c[3]),
+                "n_count": int(c[4]), "occupied": int(c[5])}
+
+    def debug_hash_host(self, lo, hi, key_words, log2_parts, n_buckets, n_ranks):
+        return debug_hash_host(lo, hi, key_words, log2_parts, n_buckets, n_ranks)
 
     def bench_random_access(self, buf, n_ops, atomic):
         sink = self.zeros(1, self.torch.int64)

@@ -250,29 +250,151 @@ def test_scan_reads_overflow_path(eng):
 
 
 @pytest.mark.parametrize("k", [31, 47])
-@pytest.mark.parametrize("n_ranks", [1, 2, 8])
-def test_partition_stream(eng, k, n_ranks):
+@pytest.mark.parametrize("n_parts,by_owner", [(1, True), (2, True), (3, True), (8, True),
+                                              (1, False), (16, False), (256, False)])
+def test_bin_stream(eng, k, n_parts, by_owner):
+    """K2p / K6: every valid canonical k-mer lands in exactly one bin, the bin is
+    the one the host-side hash predicts, equal keys share a bin."""
     from kmer_denovo_filter_b200 import engine
     _g, reads = _genome_reads(41 + k, glen=5000, n=500)
     hs = engine.pack_sequences(reads)
     ds = eng.upload(hs)
-    counts, lo, hi = eng.partition_stream(ds, k, n_ranks)
     codes, valid, _s, _l = kmers.encode_stream(reads)
     ohi, olo, ook = kmers.canonical_windows(codes, valid, k)
     want = sorted(kmers.to_pyints(ohi[ook], olo[ook]))
-    got = eng.keys_to_pyints(lo, hi)
+    bins = eng.new_bins(k, n_parts, bin_cap=len(want) // n_parts * 4 + 512, by_owner=by_owner)
+    st = eng.new_stats()
+    eng.bin_stream(bins, ds, st)
+    assert not bins.overflowed()
+    counts = bins.counts()
+    assert int(counts.sum()) == len(want) == eng.read_stats(st)["windows"]
+    got = []
+    kw = 1 if k <= 32 else 2
+    log2p = n_parts.bit_length() - 1
+    for b in range(n_parts):
+        lo, hi = bins.bin_keys(b)
+        keys = eng.keys_to_pyints(lo, hi)
+        got.extend(keys)
+        if keys:
+            lo_np = np.array([x & 0xFFFFFFFFFFFFFFFF for x in keys], dtype=np.uint64)
+            hi_np = np.array([x >> 64 for x in keys], dtype=np.uint64)
+            part, _bk, owner = engine.debug_hash_host(lo_np, hi_np if kw == 2 else None, kw,
+                                                      0 if by_owner else log2p, 1024,
+                                                      n_parts if by_owner else 1)
+            assert ((owner if by_owner else part) == b).all()
     assert sorted(got) == want
-    assert int(counts.sum()) == len(want)
-    # every key of bin r maps to owner r, and equal keys share a bin
-    off = 0
-    owner_of = {}
-    for r in range(n_ranks):
-        for key in got[off:off + int(counts[r])]:
-            assert owner_of.setdefault(key, r) == r
-        off += int(counts[r])
-    if n_ranks > 1:
-        assert (counts > 0).all()
-        assert counts.max() < 2.0 * counts.mean()
+    if n_parts in (2, 3, 8, 16):
+        assert counts.min() > 0 and counts.max() < 2.0 * counts.mean()
+    # appending the same stream again doubles every bin (cursors accumulate)
+    eng.bin_stream(bins, ds)
+    assert (bins.counts() == 2 * counts).all()
+    assert not bins.overflowed()
+
+
+def test_bin_overflow_is_reported(eng):
+    from kmer_denovo_filter_b200 import engine
+    _g, reads = _genome_reads(77, glen=5000, n=500)
+    ds = eng.upload(engine.pack_sequences(reads))
+    bins = eng.new_bins(31, 4, bin_cap=100)
+    eng.bin_stream(bins, ds)
+    assert bins.overflowed()
+    assert bins.counts().sum() == kmers.canonical_windows(*kmers.encode_stream(reads)[:2], 31)[2].sum()
+
+
+@pytest.mark.parametrize("k", [31, 47])
+def test_bin_keys_matches_bin_stream(eng, k):
+    from kmer_denovo_filter_b200 import engine
+    _g, reads = _genome_reads(51 + k, glen=4000, n=300)
+    ds = eng.upload(engine.pack_sequences(reads))
+    lo, hi, ok = eng.extract_canonical(ds, k)
+    okb = np.unpackbits(ok.cpu().numpy().view(np.uint32).byteswap().view(np.uint8))[:ds.n_bases].astype(bool)
+    import torch
+    sel = torch.from_numpy(np.flatnonzero(okb)).to(eng.device)
+    klo = lo[sel].contiguous()
+    khi = hi[sel].contiguous() if hi is not None else None
+    a = eng.new_bins(k, 8, bin_cap=int(sel.shape[0]))
+    b = eng.new_bins(k, 8, bin_cap=int(sel.shape[0]))
+    eng.bin_stream(a, ds)
+    eng.bin_keys(b, klo, khi)
+    assert (a.counts() == b.counts()).all()
+    for p in range(8):
+        assert sorted(eng.keys_to_pyints(*a.bin_keys(p))) == sorted(eng.keys_to_pyints(*b.bin_keys(p)))
+
+
+@pytest.mark.parametrize("k", [21, 31, 47, 63])
+@pytest.mark.parametrize("n_parts", [1, 8, 64])
+def test_count_bins_equals_direct_table(eng, k, n_parts):
+    """The L2-sliced partitioned count (bins -> slice -> emit) gives the same
+    (key, count, in-reference) triples as the oracle."""
+    from kmer_denovo_filter_b200 import engine
+    g, child = _genome_reads(91 + k, glen=9000, n=1200)
+    ref = [g[:6000]]
+    want = kmers.count_sequences(child, k)
+    refk = kmers.count_sequences(ref, k)
+    dc = eng.upload(engine.pack_sequences(child))
+    dr = eng.upload(engine.pack_sequences(ref))
+    n_win = sum(want.values())
+    cb = eng.new_bins(k, n_parts, bin_cap=n_win // n_parts * 2 + 512)
+    rb = eng.new_bins(k, n_parts, bin_cap=6000 // n_parts * 2 + 512)
+    eng.bin_stream(cb, dc)
+    eng.bin_stream(rb, dr)
+    assert not cb.overflowed() and not rb.overflowed()
+    res = eng.count_bins(cb, rb, slice_capacity=2 * len(want) // n_parts + 64, want_planes=True,
+                         count_min0=3, out_cap=len(want) + 10)
+    assert res["full"] == 0
+    assert res["keys"] == n_win and res["distinct"] == len(want) == res["occupied"] == res["n_out"]
+    assert res["hits"] + res["distinct"] == n_win
+    assert res["n_count"] == sum(1 for c in want.values() if c >= 3)
+    keys = eng.keys_to_pyints(res["lo"], res["hi"])
+    p0 = res["p0"].cpu().numpy().view(np.uint32).tolist()
+    p1 = res["p1"].cpu().numpy().view(np.uint32).tolist()
+    assert dict(zip(keys, p0)) == want
+    assert {key for key, f in zip(keys, p1) if f} == set(want) & set(refk)
+    # thresholded emit: count >= 3 and not in the reference; undersized output is reported
+    res2 = eng.count_bins(cb, rb, slice_capacity=2 * len(want) // n_parts + 64, min0=3, max1=0,
+                          out_cap=len(want) + 10)
+    want2 = {key for key, c in want.items() if c >= 3 and key not in refk}
+    assert set(eng.keys_to_pyints(res2["lo"], res2["hi"])) == want2 and res2["n_out"] == len(want2)
+    res3 = eng.count_bins(cb, rb, slice_capacity=2 * len(want) // n_parts + 64, min0=3, max1=0,
+                          out_cap=5)
+    assert res3["n_out"] == len(want2) and res3["lo"].shape[0] == 5
+    # a slice that cannot hold the bin's distinct keys says so
+    res4 = eng.count_bins(cb, None, slice_capacity=max(4, len(want) // n_parts // 2), out_cap=4)
+    assert res4["full"] == 1
+
+
+@pytest.mark.parametrize("k", [31, 47])
+@pytest.mark.parametrize("big_table", [False, True])
+def test_scan_sparse_equals_dense(eng, k, big_table):
+    """Sparse hit list + device reduction == dense per-read scan == oracle,
+    for a shared-memory-resident table and for an L2/HBM one."""
+    from kmer_denovo_filter_b200 import engine
+    from oracle import discovery
+    g, reads = _genome_reads(61 + k, glen=6000, n=700)
+    reads = reads + ["", "ACGT", g[:k], g[100:100 + k + 1]]
+    allk = sorted(kmers.count_sequences([g[2000:2300]], k))
+    pu = set(allk[::3])
+    ds = eng.upload(engine.pack_sequences(reads))
+    t = eng.new_table(k, capacity=(1 << 16) if big_table else None, n_keys=len(pu))
+    lo, hi = eng.keys_to_device(sorted(pu), t.key_words)
+    eng.update_keys(t, lo, hi, engine.MODE_INSERT_ONLY, 0, 0)
+    dense = eng.scan_reads(t, ds, min_distinct=1)
+    nd = dense["ndistinct"].cpu().numpy().view(np.uint32)
+    nh = dense["nhits"].cpu().numpy().view(np.uint32)
+    st = eng.new_stats()
+    sp = eng.scan_reads_sparse(t, ds, stats=st, hit_cap=64)   # forces the exact-size retry
+    want_reads = np.flatnonzero(nh > 0)
+    assert np.array_equal(sp["read"], want_reads.astype(np.uint64))
+    assert np.array_equal(sp["ndistinct"], nd[want_reads])
+    assert np.array_equal(sp["nhits"], nh[want_reads])
+    assert eng.read_stats(st)["windows"] == sum(kmers.count_sequences(reads, k).values())
+    starts = ds.read_starts.cpu().numpy().view(np.uint64)
+    for j, r in enumerate(sp["read"].tolist()):
+        uniq, idx = discovery.scan_read_numeric(reads[r], k, pu)
+        assert sp["ndistinct"][j] == len(uniq) and sp["nhits"][j] == len(idx)
+        f = int(sp["first"][j])
+        got_idx = sp["hit_pos"][f:f + len(idx)] - starts[r]
+        assert sorted(got_idx.tolist()) == sorted(idx)
 
 
 def test_empty_stream_is_a_noop(eng):

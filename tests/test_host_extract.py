@@ -28,9 +28,9 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(engine.exported_symbols())
-    assert lib.kdf_version() == 1
+    assert lib.kdf_version() == 2
     assert lib.kdf_key_words(31) == 1 and lib.kdf_key_words(33) == 2 and lib.kdf_key_words(65) == 0
-    assert lib.kdf_table_bytes(10, 1) == 160 and lib.kdf_table_bytes(10, 2) == 320
+    assert lib.kdf_table_bytes(12, 1) == 192 and lib.kdf_table_bytes(12, 2) == 288
 
 
 def test_pack_layout_matches_oracle_stream():
