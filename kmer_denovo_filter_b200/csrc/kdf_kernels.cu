@@ -294,10 +294,16 @@ __global__ void __launch_bounds__(SMEM ? 512 : 256)
     __syncthreads();
   }
   LocalStats st = {0, 0, 0, 0};
+  // Warp-uniform trip counts (words past the end read as invalid) so that the
+  // warp can be re-converged explicitly after every divergent slow path:
+  // without the __syncwarp() below lanes drift apart for the rest of the kernel.
   u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < s.n_words; w += stride) {
+  u64 n_iter = (s.n_words + stride - 1) / stride;
+  u64 w0 = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  for (u64 itn = 0; itn < n_iter; ++itn) {
+    u64 w = w0 + itn * stride;
     WindowIter<KW> it(s, w, k);
-    if (!it.any_valid()) continue;
+    if (!__any_sync(0xffffffffu, it.any_valid())) continue;
 #pragma unroll 1
     for (int c = 0; c < 32 / CHUNK; ++c) {
       Key<KW> keys[CHUNK];
@@ -320,28 +326,27 @@ __global__ void __launch_bounds__(SMEM ? 512 : 256)
 #pragma unroll
       for (int u = 0; u < CHUNK; ++u) {
         if (okm & (1u << u)) {
+          int j = match_in(bk[u], keys[u]);
           if (kInsert) {
-            int j = match_in(bk[u], keys[u]);
-            if (j >= 0 && OP == OP_INSERT_COUNT) {
+            if (j >= 0) {
               st.hits++;
-              atomicAdd((plane ? t.p1 : t.p0) + (u64)bidx[u] * S + j, arg);
-            } else if (j >= 0) {
-              st.hits++;
+              if (OP == OP_INSERT_COUNT) atomicAdd((plane ? t.p1 : t.p0) + (u64)bidx[u] * S + j, arg);
             } else {
               slow |= 1u << u;
             }
           } else {
-            bool miss = match_in(bk[u], keys[u]) < 0 && has_empty(bk[u], keys[u]);
+            bool miss = j < 0 && has_empty(bk[u], keys[u]);
             if (!miss) slow |= 1u << u;
           }
         }
       }
-      if (slow) {
+      if (__any_sync(0xffffffffu, slow != 0)) {
         u64 pos0 = (w << 5) + c * CHUNK;
 #pragma unroll
         for (int u = 0; u < CHUNK; ++u) {
           if (slow & (1u << u))
             tally(st, resolve_slow<KW, OP>(t, bidx[u], keys[u], bk[u], plane, arg, pos0 + u, sink));
+          __syncwarp();
         }
       }
     }
@@ -386,7 +391,10 @@ __global__ void __launch_bounds__(256) k_update_keys(TableView<KW> t, const u64*
   LocalStats st = {0, 0, 0, 0};
   HitSink sink = {nullptr, nullptr, 0, nullptr};
   u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 i0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * CHUNK) {
+  u64 n_iter = (n + stride * CHUNK - 1) / (stride * CHUNK);   // warp-uniform (see k_stream)
+  u64 first = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  for (u64 itn = 0; itn < n_iter; ++itn) {
+    u64 i0 = first + itn * stride * CHUNK;
     Key<KW> keys[CHUNK];
     Bucket bk[CHUNK];
     u32 bidx[CHUNK];
@@ -422,11 +430,12 @@ __global__ void __launch_bounds__(256) k_update_keys(TableView<KW> t, const u64*
         }
       }
     }
-    if (slow) {
+    if (__any_sync(0xffffffffu, slow != 0)) {
 #pragma unroll
       for (int u = 0; u < CHUNK; ++u) {
         if (slow & (1u << u))
           tally(st, resolve_slow<KW, OP>(t, bidx[u], keys[u], bk[u], plane, arg, 0, sink));
+        __syncwarp();
       }
     }
   }
