@@ -189,15 +189,15 @@ __device__ __forceinline__ void on_found(const TableView<KW>& t, u64 slot, int p
   }
 }
 
-// Finish a probe whose home bucket `b` has been loaded into `bk` (the rare
-// path: a hit of a probing op, a new key, or a full bucket).  Everything is
-// passed by value so that the callers keep their state in registers.
+// Finish a probe starting at bucket `b` (the rare path: a new key, a full
+// bucket, or a probing op that has to look past a full bucket).
 template <int KW, int OP>
-__device__ __noinline__ u32 resolve_slow(TableView<KW> t, u32 b, Key<KW> key, Bucket bk, int plane,
-                                         u32 arg, u64 pos, HitSink sink) {
+__device__ __forceinline__ u32 resolve_from(const TableView<KW>& t, u32 b, const Key<KW>& key,
+                                            int plane, u32 arg, u64 pos, const HitSink& sink) {
   constexpr bool kInsert = (OP == OP_INSERT_COUNT || OP == OP_INSERT_ONLY);
   constexpr int S = SPB<KW>::v;
   for (u32 n = 0; n < t.n_buckets; ++n) {
+    Bucket bk = ld_bucket(t.keys + (u64)b * 4);
     int j = match_in(bk, key);
     if (j >= 0) {
       on_found<OP, KW>(t, (u64)b * S + j, plane, arg, pos, sink);
@@ -223,9 +223,70 @@ __device__ __noinline__ u32 resolve_slow(TableView<KW> t, u32 b, Key<KW> key, Bu
       if (has_empty(bk, key)) return R_MISS;
     }
     b = (b + 1 == t.n_buckets) ? 0 : b + 1;
-    bk = ld_bucket(t.keys + (u64)b * 4);
   }
   return R_FULL;
+}
+
+// Per-warp queue of probes that left the fast path.  Lanes push their rare
+// items as they meet them; the warp drains the queue 32 items at a time, so
+// the slow path runs with every lane busy instead of a few lanes per call.
+constexpr int SQ_CAP = 96;
+template <int KW> struct SlowQueue {
+  u64 lo[SQ_CAP];
+  u64 hi[KW == 2 ? SQ_CAP : 1];
+  u64 pos[SQ_CAP];
+  u32 b[SQ_CAP];
+  u32 count;
+};
+
+template <int KW, int OP>
+__device__ __forceinline__ u32 sq_push_or_resolve(SlowQueue<KW>& q, const TableView<KW>& t, u32 b,
+                                                  const Key<KW>& key, int plane, u32 arg, u64 pos,
+                                                  const HitSink& sink) {
+  u32 o = atomicAdd(&q.count, 1u);
+  if (o < (u32)SQ_CAP) {
+    q.lo[o] = key.lo;
+    if (KW == 2) q.hi[o] = ((const u64*)&key)[KW - 1];
+    q.pos[o] = pos;
+    q.b[o] = b;
+    return R_MISS;  // accounted for when drained
+  }
+  return resolve_from<KW, OP>(t, b, key, plane, arg, pos, sink);  // queue full: do it now
+}
+
+// all lanes of the warp: drain whole groups of 32 (or everything when `all`)
+template <int KW, int OP>
+__device__ __noinline__ u32 sq_drain(SlowQueue<KW>* qp, TableView<KW> t, int plane, u32 arg,
+                                     HitSink sink, bool all) {
+  SlowQueue<KW>& q = *qp;
+  const unsigned lane = threadIdx.x & 31;
+  __syncwarp();
+  u32 n = q.count;
+  if (n > (u32)SQ_CAP) n = SQ_CAP;
+  u32 packed = 0;  // hits | fresh << 10 | full << 20 of this lane
+  while (n >= 32 || (all && n > 0)) {
+    u32 take = n >= 32 ? 32 : n;
+    u32 base = n - take;
+    if (lane < take) {
+      Key<KW> key;
+      key.lo = q.lo[base + lane];
+      if (KW == 2) ((u64*)&key)[KW - 1] = q.hi[base + lane];
+      u32 code = resolve_from<KW, OP>(t, q.b[base + lane], key, plane, arg, q.pos[base + lane], sink);
+      packed += (code == R_HIT ? 1u : 0u) + (code == R_NEW ? (1u << 10) : 0u);
+      packed |= (code == R_FULL ? (1u << 20) : 0u);
+    }
+    n = base;
+    __syncwarp();
+  }
+  if (lane == 0) q.count = n;
+  __syncwarp();
+  return packed;
+}
+
+__device__ __forceinline__ void tally_packed(LocalStats& st, u32 packed) {
+  st.hits += packed & 1023u;
+  st.fresh += (packed >> 10) & 1023u;
+  st.full |= packed >> 20;
 }
 
 __device__ __forceinline__ void tally(LocalStats& st, u32 code) {
@@ -280,7 +341,7 @@ __global__ void __launch_bounds__(256) k_extract(StreamView s, int k, u64* out_l
 // One fast-path decision per probe: for probing ops "bucket has an empty slot
 // and no match" (a miss, the common case against a filter set), for inserting
 // ops "bucket holds the key" (the common case at sequencing depth).  Anything
-// else goes to resolve_slow.
+// else is queued per warp and resolved 32 items at a time.
 template <int KW, int OP, bool SMEM, int CHUNK>
 __global__ void __launch_bounds__(SMEM ? 512 : 256)
     k_stream(TableView<KW> t, StreamView s, int k, int plane, u32 arg, u64* stats, HitSink sink) {
@@ -293,10 +354,14 @@ __global__ void __launch_bounds__(SMEM ? 512 : 256)
     for (u32 i = threadIdx.x; i < n; i += blockDim.x) sm_keys[i] = __ldg(t.keys + i);
     __syncthreads();
   }
+  __shared__ SlowQueue<KW> sq[(SMEM ? 512 : 256) / 32];
+  SlowQueue<KW>& q = sq[threadIdx.x >> 5];
+  if ((threadIdx.x & 31) == 0) q.count = 0;
+  __syncwarp();
   LocalStats st = {0, 0, 0, 0};
   // Warp-uniform trip counts (words past the end read as invalid) so that the
-  // warp can be re-converged explicitly after every divergent slow path:
-  // without the __syncwarp() below lanes drift apart for the rest of the kernel.
+  // warp can be re-converged explicitly after every divergent section: without
+  // the __syncwarp() calls lanes drift apart for the rest of the kernel.
   u64 stride = (u64)gridDim.x * blockDim.x;
   u64 n_iter = (s.n_words + stride - 1) / stride;
   u64 w0 = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -322,35 +387,27 @@ __global__ void __launch_bounds__(SMEM ? 512 : 256)
         }
       }
       st.windows += __popc(okm);
-      u32 slow = 0;
+      u64 pos0 = (w << 5) + c * CHUNK;
 #pragma unroll
       for (int u = 0; u < CHUNK; ++u) {
         if (okm & (1u << u)) {
           int j = match_in(bk[u], keys[u]);
-          if (kInsert) {
-            if (j >= 0) {
-              st.hits++;
-              if (OP == OP_INSERT_COUNT) atomicAdd((plane ? t.p1 : t.p0) + (u64)bidx[u] * S + j, arg);
-            } else {
-              slow |= 1u << u;
-            }
-          } else {
-            bool miss = j < 0 && has_empty(bk[u], keys[u]);
-            if (!miss) slow |= 1u << u;
+          if (j >= 0) {  // found in the home bucket
+            st.hits++;
+            on_found<OP, KW>(t, (u64)bidx[u] * S + j, plane, arg, pos0 + u, sink);
+          } else if (kInsert) {  // new key (or full bucket): CAS path, queued
+            tally(st, sq_push_or_resolve<KW, OP>(q, t, bidx[u], keys[u], plane, arg, pos0 + u, sink));
+          } else if (!has_empty(bk[u], keys[u])) {  // full bucket: look further, queued
+            u32 nb = (bidx[u] + 1 == t.n_buckets) ? 0 : bidx[u] + 1;
+            tally(st, sq_push_or_resolve<KW, OP>(q, t, nb, keys[u], plane, arg, pos0 + u, sink));
           }
         }
       }
-      if (__any_sync(0xffffffffu, slow != 0)) {
-        u64 pos0 = (w << 5) + c * CHUNK;
-#pragma unroll
-        for (int u = 0; u < CHUNK; ++u) {
-          if (slow & (1u << u))
-            tally(st, resolve_slow<KW, OP>(t, bidx[u], keys[u], bk[u], plane, arg, pos0 + u, sink));
-          __syncwarp();
-        }
-      }
+      __syncwarp();
+      if (q.count >= 32) tally_packed(st, sq_drain<KW, OP>(&q, t, plane, arg, sink, false));
     }
   }
+  tally_packed(st, sq_drain<KW, OP>(&q, t, plane, arg, sink, true));
   flush_stats(st, stats);
 }
 
@@ -388,6 +445,10 @@ __global__ void __launch_bounds__(256) k_update_keys(TableView<KW> t, const u64*
     u64 nd = *n_dev;
     n = nd < n_max ? nd : n_max;
   }
+  __shared__ SlowQueue<KW> sq[256 / 32];
+  SlowQueue<KW>& q = sq[threadIdx.x >> 5];
+  if ((threadIdx.x & 31) == 0) q.count = 0;
+  __syncwarp();
   LocalStats st = {0, 0, 0, 0};
   HitSink sink = {nullptr, nullptr, 0, nullptr};
   u64 stride = (u64)gridDim.x * blockDim.x;
@@ -415,30 +476,25 @@ __global__ void __launch_bounds__(256) k_update_keys(TableView<KW> t, const u64*
       }
     }
     st.windows += __popc(okm);
-    u32 slow = 0;
 #pragma unroll
     for (int u = 0; u < CHUNK; ++u) {
       if (okm & (1u << u)) {
         int j = match_in(bk[u], keys[u]);
-        if (kInsert && j >= 0) {
+        if (j >= 0) {
           st.hits++;
-          if (OP == OP_INSERT_COUNT) atomicAdd((plane ? t.p1 : t.p0) + (u64)bidx[u] * S + j, arg);
-        } else if (!kInsert && j < 0 && has_empty(bk[u], keys[u])) {
-          // miss
-        } else {
-          slow |= 1u << u;
+          on_found<OP, KW>(t, (u64)bidx[u] * S + j, plane, arg, 0, sink);
+        } else if (kInsert) {
+          tally(st, sq_push_or_resolve<KW, OP>(q, t, bidx[u], keys[u], plane, arg, 0, sink));
+        } else if (!has_empty(bk[u], keys[u])) {
+          u32 nb = (bidx[u] + 1 == t.n_buckets) ? 0 : bidx[u] + 1;
+          tally(st, sq_push_or_resolve<KW, OP>(q, t, nb, keys[u], plane, arg, 0, sink));
         }
       }
     }
-    if (__any_sync(0xffffffffu, slow != 0)) {
-#pragma unroll
-      for (int u = 0; u < CHUNK; ++u) {
-        if (slow & (1u << u))
-          tally(st, resolve_slow<KW, OP>(t, bidx[u], keys[u], bk[u], plane, arg, 0, sink));
-        __syncwarp();
-      }
-    }
+    __syncwarp();
+    if (q.count >= 32) tally_packed(st, sq_drain<KW, OP>(&q, t, plane, arg, sink, false));
   }
+  tally_packed(st, sq_drain<KW, OP>(&q, t, plane, arg, sink, true));
   flush_stats(st, stats);
 }
 
