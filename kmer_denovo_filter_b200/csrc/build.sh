@@ -2,7 +2,7 @@
 # Build libkdf_sm100.so in-tree (cross-compiles for sm_100a without a GPU).
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
-OUT="${HERE}/../libkdf_sm100.so"
+OUT="${KDF_OUT:-${HERE}/../libkdf_sm100.so}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "${NVCC}" -std=c++17 -O3 -lineinfo \
   -gencode arch=compute_100a,code=sm_100a \

@@ -230,6 +230,24 @@ __device__ __forceinline__ u32 resolve_from(const TableView<KW>& t, u32 b, const
 // Per-warp queue of probes that left the fast path.  Lanes push their rare
 // items as they meet them; the warp drains the queue 32 items at a time, so
 // the slow path runs with every lane busy instead of a few lanes per call.
+#ifndef KDF_STREAM_CHUNK
+#define KDF_STREAM_CHUNK 4
+#endif
+#ifndef KDF_STREAM_BLOCKS
+#define KDF_STREAM_BLOCKS 3
+#endif
+#ifndef KDF_SMEM_CHUNK
+#define KDF_SMEM_CHUNK 4
+#endif
+#ifndef KDF_SMEM_BLOCKS
+#define KDF_SMEM_BLOCKS 1
+#endif
+#ifndef KDF_KEYS_CHUNK
+#define KDF_KEYS_CHUNK 4
+#endif
+#ifndef KDF_KEYS_BLOCKS
+#define KDF_KEYS_BLOCKS 2
+#endif
 constexpr int SQ_CAP = 96;
 template <int KW> struct SlowQueue {
   u64 lo[SQ_CAP];
@@ -343,7 +361,7 @@ __global__ void __launch_bounds__(256) k_extract(StreamView s, int k, u64* out_l
 // ops "bucket holds the key" (the common case at sequencing depth).  Anything
 // else is queued per warp and resolved 32 items at a time.
 template <int KW, int OP, bool SMEM, int CHUNK>
-__global__ void __launch_bounds__(SMEM ? 512 : 256)
+__global__ void __launch_bounds__(SMEM ? 512 : 256, SMEM ? KDF_SMEM_BLOCKS : KDF_STREAM_BLOCKS)
     k_stream(TableView<KW> t, StreamView s, int k, int plane, u32 arg, u64* stats, HitSink sink) {
   extern __shared__ __align__(32) u64 sm_keys[];
   constexpr bool kInsert = (OP == OP_INSERT_COUNT || OP == OP_INSERT_ONLY);
@@ -434,10 +452,10 @@ template <> __device__ __forceinline__ Key<2> ld_key_stream<2>(const u64* lo, co
 }
 
 template <int KW, int OP>
-__global__ void __launch_bounds__(256) k_update_keys(TableView<KW> t, const u64* lo, const u64* hi,
+__global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_update_keys(TableView<KW> t, const u64* lo, const u64* hi,
                                                      u64 n_max, const u64* n_dev, int plane, u32 arg,
                                                      u64* stats) {
-  constexpr int CHUNK = 4;
+  constexpr int CHUNK = KDF_KEYS_CHUNK;
   constexpr bool kInsert = (OP == OP_INSERT_COUNT || OP == OP_INSERT_ONLY);
   constexpr int S = SPB<KW>::v;
   u64 n = n_max;
@@ -1013,18 +1031,18 @@ static int dispatch_stream(const kdf_table* t, const StreamView& v, int op, int 
   bool small = (size_t)(t->capacity / SPB<KW>::v) * 32 <= SMEM_TABLE_MAX && t->log2_parts == 0;
   switch (op) {
     case OP_INSERT_COUNT:
-      return launch_stream<KW, OP_INSERT_COUNT, false, 8>(t, v, plane, arg, stats, sink, st);
+      return launch_stream<KW, OP_INSERT_COUNT, false, KDF_STREAM_CHUNK>(t, v, plane, arg, stats, sink, st);
     case OP_INSERT_ONLY:
-      return launch_stream<KW, OP_INSERT_ONLY, false, 8>(t, v, plane, arg, stats, sink, st);
+      return launch_stream<KW, OP_INSERT_ONLY, false, KDF_STREAM_CHUNK>(t, v, plane, arg, stats, sink, st);
     case OP_COUNT_IF_PRESENT:
-      return small ? launch_stream<KW, OP_COUNT_IF_PRESENT, true, 4>(t, v, plane, arg, stats, sink, st)
-                   : launch_stream<KW, OP_COUNT_IF_PRESENT, false, 8>(t, v, plane, arg, stats, sink, st);
+      return small ? launch_stream<KW, OP_COUNT_IF_PRESENT, true, KDF_SMEM_CHUNK>(t, v, plane, arg, stats, sink, st)
+                   : launch_stream<KW, OP_COUNT_IF_PRESENT, false, KDF_STREAM_CHUNK>(t, v, plane, arg, stats, sink, st);
     case OP_MARK_IF_PRESENT:
-      return small ? launch_stream<KW, OP_MARK_IF_PRESENT, true, 4>(t, v, plane, arg, stats, sink, st)
-                   : launch_stream<KW, OP_MARK_IF_PRESENT, false, 8>(t, v, plane, arg, stats, sink, st);
+      return small ? launch_stream<KW, OP_MARK_IF_PRESENT, true, KDF_SMEM_CHUNK>(t, v, plane, arg, stats, sink, st)
+                   : launch_stream<KW, OP_MARK_IF_PRESENT, false, KDF_STREAM_CHUNK>(t, v, plane, arg, stats, sink, st);
     case OP_EMIT_HITS:
-      return small ? launch_stream<KW, OP_EMIT_HITS, true, 4>(t, v, plane, arg, stats, sink, st)
-                   : launch_stream<KW, OP_EMIT_HITS, false, 8>(t, v, plane, arg, stats, sink, st);
+      return small ? launch_stream<KW, OP_EMIT_HITS, true, KDF_SMEM_CHUNK>(t, v, plane, arg, stats, sink, st)
+                   : launch_stream<KW, OP_EMIT_HITS, false, KDF_STREAM_CHUNK>(t, v, plane, arg, stats, sink, st);
     default:
       return fail(KDF_ERR_ARG, "unknown table operation");
   }
@@ -1034,7 +1052,7 @@ template <int KW, int OP>
 static int launch_update_keys(const kdf_table* t, const u64* lo, const u64* hi, u64 n_max,
                               const u64* n_dev, int plane, u32 arg, u64* stats, cudaStream_t st) {
   TableView<KW> tv = view_of_table<KW>(t);
-  int g = grid_for((const void*)k_update_keys<KW, OP>, 256, 0, (n_max + 3) / 4, t->sm_count);
+  int g = grid_for((const void*)k_update_keys<KW, OP>, 256, 0, (n_max + KDF_KEYS_CHUNK - 1) / KDF_KEYS_CHUNK, t->sm_count);
   k_update_keys<KW, OP><<<g, 256, 0, st>>>(tv, lo, hi, n_max, n_dev, plane, arg, stats);
   CUDA_TRY(cudaGetLastError());
   return KDF_OK;

@@ -19,12 +19,39 @@ from .. import engine as _engine
 from ..kmer_utils import KmerSet
 
 REF_PLANE = 1
+SMEM_TABLE_BYTES = 160 * 1024   # keys of a read-only table that the stream kernels copy to shared memory
 
 
-def _on_device(eng, s, with_reads):
-    if isinstance(s, _engine.DeviceStream):
-        return s
-    return eng.upload(s, non_blocking=True, with_reads=with_reads)
+class _Uploader:
+    """Host → device copies on a side stream, in the order the chain consumes
+    them, so that the parents' upload overlaps the child count (the copy engine
+    and the SMs run concurrently; each consumer waits on its own event)."""
+
+    def __init__(self, eng):
+        self.eng = eng
+        self.torch = eng.torch
+        self.side = None
+
+    def put(self, s, with_reads):
+        """-> (DeviceStream, ready event | None)"""
+        if isinstance(s, _engine.DeviceStream):
+            return s, None
+        torch = self.torch
+        if self.side is None:
+            self.side = torch.cuda.Stream(device=self.eng.device)
+        main = torch.cuda.current_stream(self.eng.device)
+        with torch.cuda.stream(self.side):
+            d = self.eng.upload(s, non_blocking=True, with_reads=with_reads)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        for t in (d.codes, d.valid, d.read_starts, d.read_lens):
+            if t is not None:
+                t.record_stream(main)
+        return d, ev
+
+    def wait(self, ev):
+        if ev is not None:
+            self.torch.cuda.current_stream(self.eng.device).wait_event(ev)
 
 
 def default_child_capacity(eng, n_bases):
@@ -113,7 +140,12 @@ def count_child_partitioned(eng, child_streams, ref_streams, k, min_child_count,
 
 
 def _primed_table(eng, k, lo, hi, n):
-    t = eng.new_table(k, n_keys=max(n, 1))
+    # small sets get load 0.25: they stay within the shared-memory budget of the
+    # stream kernels and almost no probe has to look past its home bucket
+    n_keys = max(n, 1)
+    if n_keys * 4 * 8 * eng.lib.kdf_key_words(k) <= SMEM_TABLE_BYTES:
+        n_keys *= 2
+    t = eng.new_table(k, n_keys=n_keys)
     eng.update_keys(t, lo, hi, _engine.MODE_INSERT_ONLY, 0, 0)
     return t
 
@@ -135,10 +167,13 @@ def discover_streams(eng, child, mother, father, ref, k, min_child_count=3,
     if partitioned is None:
         partitioned = child_capacity is None
     stats = eng.new_stats()
-    d_child = _on_device(eng, child, True)
-    d_ref = _on_device(eng, ref, False)
-    d_mother = _on_device(eng, mother, False)
-    d_father = _on_device(eng, father, False)
+    up = _Uploader(eng)
+    d_child, ev_child = up.put(child, True)
+    d_ref, ev_ref = up.put(ref, False)
+    d_mother, ev_mother = up.put(mother, False)
+    d_father, ev_father = up.put(father, False)
+    up.wait(ev_child)
+    up.wait(ev_ref)
 
     # Module 1 + reference subtraction: jellyfish count -C ; dump -L ; query ref.jf
     if partitioned:
@@ -182,12 +217,14 @@ def discover_streams(eng, child, mother, father, ref, k, min_child_count=3,
     n_pu = 0
     if n_nonref:
         mt = _primed_table(eng, k, lo, hi, n_nonref)
+        up.wait(ev_mother)
         eng.count_stream(mt, d_mother, _engine.MODE_COUNT_IF_PRESENT, 0, 1, stats)
         n_am, lo, hi, _a, _b = eng.threshold_compact(mt, max0=parent_max_count)
         mt.close()
         out["after_mother"] = n_am
         if n_am:
             ft = _primed_table(eng, k, lo, hi, n_am)
+            up.wait(ev_father)
             eng.count_stream(ft, d_father, _engine.MODE_COUNT_IF_PRESENT, 0, 1, stats)
             n_pu, lo, hi, _a, _b = eng.threshold_compact(ft, max0=parent_max_count)
             ft.close()

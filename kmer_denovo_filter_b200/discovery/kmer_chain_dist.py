@@ -1,0 +1,227 @@
+"""The discovery k-mer chain across the GPUs of one node (one process per GPU,
+``torch.distributed``; NCCL over NVLink on the box, gloo in the CPU tests).
+
+The reference has no multi-device mode; this is how the path
+shards:
+
+* reads shard by rank — every rank holds 1/R of each sample's reads and one
+  slice of the reference;
+* the child k-mer table is partitioned by *owner rank* (``owner_of(hash)``,
+  independent of the bucket hash): K6 bins each rank's canonical k-mers by
+  owner, one all-to-all routes every k-mer to its owner, and the owner counts
+  what it received with the same L2-sliced partitioned count as on one GPU;
+  the reference slice takes the same route, so reference subtraction is local
+  to the owner;
+* what survives (count >= min_child_count, not in the reference) is small:
+  it is all-gathered and replicated, each rank probes its parent shards
+  against the replica, and the per-key parent counts are summed with one
+  all-reduce — in the fixed order of the gathered key list, so every rank
+  filters identically;
+* the per-read scan is purely data-parallel.
+"""
+
+import numpy as np
+
+from .. import engine as _engine
+from ..kmer_utils import KmerSet
+from . import kmer_chain as _kc
+
+
+# ---------------------------------------------------------------------------
+# collective plumbing (device-agnostic: tested under gloo with CPU tensors)
+# ---------------------------------------------------------------------------
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def exchange_equal(send, world):
+    """All-to-all of ``world`` equal segments of ``send`` → tensor of the same shape
+    whose segment r came from rank r."""
+    dist = _dist()
+    recv = send.new_empty(send.shape)
+    dist.all_to_all_single(recv, send)
+    return recv
+
+
+def allreduce(t, op="sum"):
+    dist = _dist()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MAX)
+    return t
+
+
+def allgather_varlen(torch, t, world):
+    """Concatenation over ranks (rank order) of 1-D tensors of different lengths."""
+    dist = _dist()
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=t.device) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(s.item()) for s in sizes]
+    m = max(sizes + [1])
+    pad = t.new_zeros(m)
+    pad[:t.shape[0]] = t
+    parts = [t.new_empty(m) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    return torch.cat([p[:s] for p, s in zip(parts, sizes)])
+
+
+# ---------------------------------------------------------------------------
+# stages
+# ---------------------------------------------------------------------------
+
+def route_to_owners(eng, streams, k, world):
+    """K6 + all-to-all: the canonical k-mers of this rank's ``streams`` go to their
+    owner ranks.  Returns ``(recv, recv_counts, bin_cap, windows)``: ``recv`` holds
+    ``world`` segments of ``bin_cap`` keys (u64, or {lo, hi} pairs for k > 32),
+    segment r = keys sent by rank r of which the first ``recv_counts[r]`` are valid."""
+    torch = eng.torch
+    n_max = sum(s.n_bases for s in streams)
+    cap = torch.tensor([_kc._bin_capacity(max(n_max, 1), world)], dtype=torch.int64, device=eng.device)
+    allreduce(cap, "max")          # every rank must use the same segment size
+    bin_cap = (int(cap.item()) + 3) & ~3
+    while True:
+        bins = eng.new_bins(k, world, bin_cap, by_owner=True)
+        st = eng.new_stats()
+        for s in streams:
+            eng.bin_stream(bins, s, st)
+        need = torch.stack([bins.cursors.max() if world else bins.cursors.new_zeros(()),
+                            bins.overflow[0]]).to(torch.int64)
+        allreduce(need, "max")
+        if int(need[1].item()) == 0:
+            break
+        bin_cap = (int(need[0].item()) + 4 + 3) & ~3     # exact size, agreed by all ranks
+        del bins
+    send_counts = torch.minimum(bins.cursors, torch.full_like(bins.cursors, bin_cap))
+    recv_counts = exchange_equal(send_counts, world)
+    recv = exchange_equal(bins.data, world)
+    return recv, recv_counts.cpu().numpy().astype(np.int64), bins.bin_cap, eng.read_stats(st)["windows"]
+
+
+def _segments(recv, counts, bin_cap, kw):
+    for r, n in enumerate(counts.tolist()):
+        if n:
+            yield recv[r * bin_cap * kw:(r * bin_cap + n) * kw], int(n)
+
+
+def count_child_dist(eng, child_streams, ref_streams, k, min_child_count, world):
+    """Module 1 + reference subtraction with the table partitioned by owner rank.
+    Returns dict(child_windows, ref_windows, child_distinct, candidates, non_ref — all
+    LOCAL to this rank — and lo, hi: this owner's non-reference candidates)."""
+    kw = eng.lib.kdf_key_words(k)
+    c_recv, c_counts, c_cap, c_win = route_to_owners(eng, child_streams, k, world)
+    r_recv, r_counts, r_cap, r_win = route_to_owners(eng, ref_streams, k, world)
+    n_child = int(c_counts.sum())
+    n_ref = int(r_counts.sum())
+    n_parts, slice_capacity = _kc.plan_partitions(max(n_child, 1))
+    bin_cap = _kc._bin_capacity(max(n_child, 1), n_parts)
+    ref_cap = _kc._bin_capacity(max(n_ref, 1), n_parts)
+    while True:
+        cb = eng.new_bins(k, n_parts, bin_cap)
+        rb = eng.new_bins(k, n_parts, ref_cap)
+        for seg, n in _segments(c_recv, c_counts, c_cap, kw):
+            eng.bin_keys(cb, seg, None, n)
+        for seg, n in _segments(r_recv, r_counts, r_cap, kw):
+            eng.bin_keys(rb, seg, None, n)
+        oc, orf = cb.overflowed(), rb.overflowed()
+        if not oc and not orf:
+            break
+        if oc:
+            bin_cap = int(cb.counts().max()) + 4
+        if orf:
+            ref_cap = int(rb.counts().max()) + 4
+        del cb, rb
+    del c_recv, r_recv
+    out_cap = max(1 << 16, n_child // 64)
+    while True:
+        res = eng.count_bins(cb, rb, slice_capacity, min0=min_child_count, max1=0,
+                             count_min0=min_child_count, out_cap=out_cap)
+        if res["full"]:
+            if slice_capacity >= 2 * bin_cap:
+                raise _engine.KdfError("child k-mer table slice full at %d slots" % slice_capacity)
+            slice_capacity = min(slice_capacity * 4, 2 * bin_cap + 4)
+            continue
+        if res["n_out"] > out_cap:
+            out_cap = res["n_out"]
+            continue
+        break
+    return {"child_windows": c_win, "ref_windows": r_win, "child_distinct": res["distinct"],
+            "candidates": res["n_count"], "non_ref": res["n_out"], "lo": res["lo"], "hi": res["hi"]}
+
+
+def filter_parent_dist(eng, parent_stream, k, lo, hi, parent_max_count, world, stats):
+    """``count --if`` of this rank's parent shard against the replicated key list,
+    all-reduce of the per-key counts (list order), threshold.  → (lo, hi) survivors,
+    identical on every rank."""
+    n = int(lo.shape[0])
+    table = _kc._primed_table(eng, k, lo, hi, n)
+    eng.count_stream(table, parent_stream, _engine.MODE_COUNT_IF_PRESENT, 0, 1, stats)
+    _found, p0, _p1 = eng.lookup_keys(table, lo, hi)
+    table.close()
+    total = p0.to(eng.torch.int64)
+    allreduce(total, "sum")
+    keep = total <= parent_max_count
+    return lo[keep].contiguous(), (hi[keep].contiguous() if hi is not None else None)
+
+
+def discover_streams_dist(eng, child, mother, father, ref, k, min_child_count=3,
+                          parent_max_count=0, min_distinct_kmers_per_read=None, fetch=False):
+    """Multi-GPU form of :func:`kmer_chain.discover_streams`; every argument is this
+    rank's shard.  Stage sizes in the result are GLOBAL (identical on all ranks);
+    ``units`` and the per-read records are this rank's own."""
+    dist = _dist()
+    torch = eng.torch
+    world = dist.get_world_size()
+    if min_distinct_kmers_per_read is None:
+        min_distinct_kmers_per_read = max(1, k // 4)
+    stats = eng.new_stats()
+    up = _kc._Uploader(eng)
+    d_child, ev_child = up.put(child, True)
+    d_ref, ev_ref = up.put(ref, False)
+    d_mother, ev_mother = up.put(mother, False)
+    d_father, ev_father = up.put(father, False)
+    up.wait(ev_child)
+    up.wait(ev_ref)
+
+    c = count_child_dist(eng, [d_child], [d_ref], k, min_child_count, world)
+    tot = torch.tensor([c["candidates"], c["child_distinct"]], dtype=torch.int64, device=eng.device)
+    allreduce(tot, "sum")
+    lo = allgather_varlen(torch, c["lo"], world)
+    hi = allgather_varlen(torch, c["hi"], world) if c["hi"] is not None else None
+    out = {"child_windows": c["child_windows"], "child_distinct": int(tot[1].item()),
+           "candidates": int(tot[0].item()), "non_ref": int(lo.shape[0]), "after_mother": 0,
+           "proband_unique": 0, "pu": None, "ndistinct": None, "nhits": None,
+           "informative_reads": 0, "reads": None, "hits": None}
+    units = c["child_windows"] + c["ref_windows"]
+
+    n_pu = 0
+    if out["non_ref"]:
+        up.wait(ev_mother)
+        lo, hi = filter_parent_dist(eng, d_mother, k, lo, hi, parent_max_count, world, stats)
+        out["after_mother"] = int(lo.shape[0])
+        if out["after_mother"]:
+            up.wait(ev_father)
+            lo, hi = filter_parent_dist(eng, d_father, k, lo, hi, parent_max_count, world, stats)
+            n_pu = int(lo.shape[0])
+    out["proband_unique"] = n_pu
+
+    local_inf = 0
+    if n_pu:
+        out["pu"] = KmerSet(eng, k, lo, hi)
+        pt = _kc._primed_table(eng, k, lo, hi, n_pu)
+        sp = eng.scan_reads_sparse(pt, d_child, stats=stats)
+        pt.close()
+        out["reads"] = sp
+        local_inf = int((sp["ndistinct"] >= min_distinct_kmers_per_read).sum())
+        if fetch:
+            nd = np.zeros(d_child.n_reads, dtype=np.uint32)
+            nh = np.zeros(d_child.n_reads, dtype=np.uint32)
+            nd[sp["read"].astype(np.int64)] = sp["ndistinct"]
+            nh[sp["read"].astype(np.int64)] = sp["nhits"]
+            out["ndistinct"], out["nhits"] = nd, nh
+    inf = torch.tensor([local_inf], dtype=torch.int64, device=eng.device)
+    allreduce(inf, "sum")
+    out["informative_reads"] = int(inf.item())
+    out["informative_reads_local"] = local_inf
+    out["units"] = eng.read_stats(stats)["windows"] + units
+    return out

@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkdf_sm100.so")
+LIB_PATH = os.environ.get("KDF_LIB") or os.path.join(_HERE, "libkdf_sm100.so")
 
 KDF_OK = 0
 MODE_INSERT_COUNT = 0

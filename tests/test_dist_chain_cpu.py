@@ -1,0 +1,140 @@
+"""The multi-GPU chain's host logic under gloo, world_size 2, on CPU: owner
+routing + all-to-all, owner-local count and reference subtraction, replicated
+parent filtering with all-reduced counts — against a single-process oracle
+count of the union of both ranks' shards."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+K = 31
+GENOME = 60_000
+DEPTH = 12
+WORLD = 2
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dev_stream(s):
+    from kmer_denovo_filter_b200 import engine
+    return engine.DeviceStream(s["codes"], s["valid"], s["n_bases"], s["read_starts"], s["read_lens"])
+
+
+def _shards(rank):
+    from kmer_denovo_filter_b200 import synth
+    return synth.make_trio(torch, torch.device("cpu"), GENOME, depth=DEPTH, read_len=100,
+                           n_denovo=12, rank=rank, world=WORLD)
+
+
+def _worker(rank, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        from fake_engine import FakeEngine
+        from kmer_denovo_filter_b200.discovery import kmer_chain_dist
+        trio = _shards(rank)
+        eng = FakeEngine()
+        res = kmer_chain_dist.discover_streams_dist(
+            eng, _dev_stream(trio["child"]), _dev_stream(trio["mother"]),
+            _dev_stream(trio["father"]), _dev_stream(trio["ref"]), K)
+        pu = sorted(res["pu"].lo.numpy().view(np.uint64).tolist()) if res["pu"] is not None else []
+        q.put((rank, {x: res[x] for x in ("candidates", "non_ref", "after_mother", "proband_unique",
+                                          "child_distinct", "informative_reads", "units")}, pu,
+               res["informative_reads_local"]))
+    finally:
+        dist.destroy_process_group()
+
+
+def _expected():
+    """Single-process oracle over the union of the shards."""
+    import collections
+    from fake_engine import stream_keys, unpack_stream
+    from kmer_denovo_filter_b200 import synth
+    from oracle import kmers
+    tot = {w: collections.Counter() for w in ("child", "mother", "father")}
+    units = 0
+    child_streams = []
+    for r in range(WORLD):
+        trio = _shards(r)
+        for w in tot:
+            ds = _dev_stream(trio[w])
+            lo, hi, ok = stream_keys(ds, K)
+            units += int(ok.sum()) * (2 if w == "child" else 1)   # child: binned + scanned
+            tot[w].update(lo[ok].tolist())
+            if w == "child":
+                child_streams.append(ds)
+        lo, hi, ok = stream_keys(_dev_stream(trio["ref"]), K)
+        units += int(ok.sum())
+    full = synth.make_trio(torch, torch.device("cpu"), GENOME, depth=0.1, read_len=100, n_denovo=12)
+    rlo, _rhi, rok = stream_keys(_dev_stream(full["ref"]), K)
+    ref = set(rlo[rok].tolist())
+    cand = {x for x, c in tot["child"].items() if c >= 3}
+    nonref = cand - ref
+    am = {x for x in nonref if tot["mother"].get(x, 0) == 0}
+    pu = {x for x in am if tot["father"].get(x, 0) == 0}
+    inf = 0
+    for ds in child_streams:
+        lo, hi, ok = stream_keys(ds, K)
+        starts = ds.read_starts.numpy().astype(np.int64)
+        lens = ds.read_lens.numpy().astype(np.int64)
+        hit = ok & np.isin(lo, np.fromiter(pu, dtype=np.uint64, count=len(pu)))
+        for s, l in zip(starts.tolist(), lens.tolist()):
+            seg = lo[s:s + max(0, l - K + 1)][hit[s:s + max(0, l - K + 1)]]
+            if np.unique(seg).shape[0] >= K // 4:
+                inf += 1
+    return {"candidates": len(cand), "non_ref": len(nonref), "after_mother": len(am),
+            "proband_unique": len(pu), "child_distinct": len(tot["child"]),
+            "informative_reads": inf}, sorted(pu), units
+
+
+def test_distributed_chain_world2_gloo():
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    if here not in sys.path:
+        sys.path.insert(0, here)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, port, q)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want, want_pu, want_units = _expected()
+    assert want["proband_unique"] > 0 and want["informative_reads"] > 0
+    for rank, sizes, pu, _loc in got:
+        for key, v in want.items():
+            assert sizes[key] == v, (rank, key, sizes[key], v)
+        assert pu == want_pu
+    assert sum(g[3] for g in got) == want["informative_reads"]
+    # duplicated reference windows in the 64-base shard overlap are the only slack
+    assert 0 <= sum(g[1]["units"] for g in got) - want_units <= 64 * WORLD
+
+
+def test_collective_helpers_single_process():
+    """allgather_varlen / exchange_equal with world_size 1 (gloo)."""
+    import torch.distributed as dist
+    from kmer_denovo_filter_b200.discovery import kmer_chain_dist as D
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(_free_port())
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        t = torch.arange(7, dtype=torch.int64)
+        assert torch.equal(D.allgather_varlen(torch, t, 1), t)
+        assert torch.equal(D.exchange_equal(t, 1), t)
+        assert torch.equal(D.allgather_varlen(torch, t[:0], 1), t[:0])
+    finally:
+        dist.destroy_process_group()
