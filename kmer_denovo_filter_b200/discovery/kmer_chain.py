@@ -38,15 +38,12 @@ class _Uploader:
             return s, None
         torch = self.torch
         if self.side is None:
-            self.side = torch.cuda.Stream(device=self.eng.device)
-        main = torch.cuda.current_stream(self.eng.device)
-        with torch.cuda.stream(self.side):
-            d = self.eng.upload(s, non_blocking=True, with_reads=with_reads)
-            ev = torch.cuda.Event()
-            ev.record(self.side)
-        for t in (d.codes, d.valid, d.read_starts, d.read_lens):
-            if t is not None:
-                t.record_stream(main)
+            self.side = getattr(self.eng, "_copy_stream", None)
+            if self.side is None:
+                self.side = self.eng._copy_stream = torch.cuda.Stream(device=self.eng.device)
+        d = self.eng.upload(s, with_reads=with_reads, copy_stream=self.side)
+        ev = torch.cuda.Event()
+        ev.record(self.side)
         return d, ev
 
     def wait(self, ev):

@@ -374,20 +374,32 @@ class CudaEngine:
                 "hits": int(v[STAT_HITS]), "new": int(v[STAT_NEW])}
 
     # -- data movement -----------------------------------------------------
-    def upload(self, hs, non_blocking=False, with_reads=True):
-        """HostStream → DeviceStream (H2D copies on the current stream)."""
+    def upload(self, hs, non_blocking=False, with_reads=True, copy_stream=None):
+        """HostStream → DeviceStream.  Device buffers are allocated on the current
+        stream; the H2D copies run on it too, or on ``copy_stream`` (which first
+        waits for the current stream, so a recycled buffer is never overwritten
+        while earlier kernels still read it) — the caller then orders consumers
+        after the copies with an event."""
         torch = self.torch
-        codes = torch.from_numpy(np.ascontiguousarray(hs.codes).view(np.int64))
-        valid = torch.from_numpy(np.ascontiguousarray(hs.valid).view(np.int32))
-        rs = rl = None
+        main = torch.cuda.current_stream(self.device)
+
+        def host(a, dt):
+            return torch.from_numpy(np.ascontiguousarray(a).view(dt))
+
+        src = [host(hs.codes, np.int64), host(hs.valid, np.int32)]
         if with_reads and hs.read_lens is not None:
-            rs = torch.from_numpy(np.ascontiguousarray(hs.read_starts).view(np.int64)).to(
-                self.device, non_blocking=non_blocking)
-            rl = torch.from_numpy(np.ascontiguousarray(hs.read_lens).view(np.int32)).to(
-                self.device, non_blocking=non_blocking)
-        return DeviceStream(codes.to(self.device, non_blocking=non_blocking),
-                            valid.to(self.device, non_blocking=non_blocking),
-                            hs.n_bases, rs, rl)
+            src += [host(hs.read_starts, np.int64), host(hs.read_lens, np.int32)]
+        dst = [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in src]
+        if copy_stream is not None:
+            copy_stream.wait_stream(main)
+            with torch.cuda.stream(copy_stream):
+                for d, h in zip(dst, src):
+                    d.copy_(h, non_blocking=True)
+        else:
+            for d, h in zip(dst, src):
+                d.copy_(h, non_blocking=non_blocking)
+        rs, rl = (dst[2], dst[3]) if len(dst) == 4 else (None, None)
+        return DeviceStream(dst[0], dst[1], hs.n_bases, rs, rl)
 
     def keys_to_device(self, keys, key_words):
         """Python ints / numpy → (lo, hi) int64 device tensors."""
