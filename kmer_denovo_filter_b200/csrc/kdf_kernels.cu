@@ -827,10 +827,29 @@ struct BinStage {
     for (int i = threadIdx.x; i < P; i += blockDim.x) cnt[i] = 0;
   }
   static size_t bytes(int P, int Q) { return (size_t)P * 8 + (size_t)P * Q * KW * 8 + (size_t)P * 4; }
-  // append a key; queue overflow falls back to a direct global append
-  __device__ __forceinline__ void push(u32 p, const Key<KW>& key, u64* bins, u64 bin_cap, u64* cursors,
-                                       u64* overflow) {
-    u32 o = atomicAdd(&cnt[p], 1u);
+  // Append a key (all lanes of the warp call this together; `ok` says whether
+  // the lane has one).  Queue overflow falls back to a direct global append.
+  // With few bins (owner binning at 2..8 ranks) every lane would hit the same
+  // few shared counters, so the warp aggregates: one atomic per bin per warp.
+  __device__ __forceinline__ void push(bool ok, u32 p, const Key<KW>& key, u64* bins, u64 bin_cap,
+                                       u64* cursors, u64* overflow) {
+    u32 o = 0;
+    if (n_parts <= 8) {
+      const unsigned lane = threadIdx.x & 31;
+      for (int b = 0; b < n_parts; ++b) {
+        unsigned m = __ballot_sync(0xffffffffu, ok && p == (u32)b);
+        if (m) {
+          int leader = __ffs(m) - 1;
+          u32 base = 0;
+          if ((int)lane == leader) base = atomicAdd(&cnt[b], (u32)__popc(m));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          if (ok && p == (u32)b) o = base + __popc(m & ((1u << lane) - 1));
+        }
+      }
+    } else if (ok) {
+      o = atomicAdd(&cnt[p], 1u);
+    }
+    if (!ok) return;
     if (o < (u32)qcap) {
       u64* q = queue + ((size_t)p * qcap + o) * KW;
       q[0] = key.lo;
@@ -850,12 +869,16 @@ struct BinStage {
       gbase[p] = c ? atomicAdd(cursors + p, (u64)c) : 0ull;
     }
     __syncthreads();
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    for (int p = warp; p < n_parts; p += n_warps) {
+    // many bins: a warp per bin; few bins: the whole block per bin
+    const bool wide = n_parts <= 8;
+    const unsigned lane = wide ? threadIdx.x : (threadIdx.x & 31);
+    const unsigned step = wide ? blockDim.x : 32;
+    const unsigned first = wide ? 0 : (threadIdx.x >> 5), n_warps = wide ? 1 : (blockDim.x >> 5);
+    for (int p = first; p < n_parts; p += n_warps) {
       u32 c = cnt[p];
       if (c > (u32)qcap) c = qcap;
       u64 g0 = gbase[p];
-      for (u32 i = lane; i < c; i += 32) {
+      for (u32 i = lane; i < c; i += step) {
         u64 g = g0 + i;
         const u64* q = queue + ((size_t)p * qcap + i) * KW;
         if (g < bin_cap) {
@@ -906,11 +929,9 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_stream(StreamView s, int k,
         bool ok = it.ok();
         Key<KW> key = it.canonical();
         it.advance();
-        if (ok) {
-          windows++;
-          stage.push(bin_of<KW, BY_OWNER>(key, log2_parts, n_parts), key, bins, bin_cap, cursors,
-                     overflow);
-        }
+        windows += ok ? 1u : 0u;
+        stage.push(ok, bin_of<KW, BY_OWNER>(key, log2_parts, n_parts), key, bins, bin_cap, cursors,
+                   overflow);
       }
       stage.flush(bins, bin_cap, cursors, overflow);
     }
@@ -937,11 +958,10 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_keys(const u64* lo, const u
 #pragma unroll 4
     for (int j = 0; j < BIN_WPR; ++j) {
       u64 i = base + (u64)j * blockDim.x;
-      if (i < n) {
-        Key<KW> key = ld_key_stream<KW>(lo, hi, i);
-        stage.push(bin_of<KW, BY_OWNER>(key, log2_parts, n_parts), key, bins, bin_cap, cursors,
-                   overflow);
-      }
+      bool ok = i < n;
+      Key<KW> key = ld_key_stream<KW>(lo, hi, ok ? i : 0);
+      stage.push(ok, bin_of<KW, BY_OWNER>(key, log2_parts, n_parts), key, bins, bin_cap, cursors,
+                 overflow);
     }
     stage.flush(bins, bin_cap, cursors, overflow);
   }
@@ -1389,8 +1409,10 @@ int kdf_reduce_hits(const uint64_t* hit_pos, const uint32_t* hit_slot, uint64_t 
 // ---- binning -------------------------------------------------------------
 static int bin_qcap(int n_parts, int kw) {
   // ~64 KB of queues per CTA -> 3 CTAs per SM
+  // a round offers 256 threads x 16 windows = 4096 keys, 4096 / n_parts per queue
   int q = (64 * 1024) / (n_parts * 8 * kw);
-  if (q > 96) q = 96;
+  int want = 2 * (BIN_THREADS * BIN_WPR / n_parts) + 32;
+  if (q > want) q = want;
   if (q < 8) q = 8;
   return q;
 }

@@ -79,8 +79,14 @@ def plan_partitions(n_windows_max, slots_needed=None):
 
 
 def _bin_capacity(n_keys_max, n_parts):
+    """Slots per bin for ``n_keys_max`` k-mer INSTANCES spread over ``n_parts``
+    hash ranges.  All copies of a k-mer share a bin, so the spread of a bin's
+    size is that of ~mean/depth keys of weight ~depth, not of ``mean`` unit
+    keys: 4 % + 64 sqrt(mean) covers depths into the hundreds.  A bin that is
+    still too small is reported by the kernel and the caller re-bins with the
+    exact sizes."""
     mean = n_keys_max / n_parts
-    return int(mean + 8 * (mean ** 0.5) + 64)
+    return int(mean * 1.04 + 64 * (mean ** 0.5) + 1024)
 
 
 def count_child_partitioned(eng, child_streams, ref_streams, k, min_child_count,

@@ -5,6 +5,7 @@ rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr = rows[0]
+units = rows[1]
 want = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
         'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem',
@@ -25,7 +26,7 @@ for r in rows[2:]:
     print('---')
     for w in want:
         if w in hdr:
-            print("  %-75s %s" % (w, r[hdr.index(w)][:90]))
+            print("  %-75s %s %s" % (w, r[hdr.index(w)][:90], units[hdr.index(w)]))
     st = sorted(((float(r[hdr.index(h)] or 0), h) for h in stall), reverse=True)[:6]
     for v, h in st:
         print("  stall %-69s %.2f" % (h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''), v))
