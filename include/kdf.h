@@ -287,7 +287,9 @@ uint64_t kdf_pack_sequences(const char* seqs, const uint64_t* offsets,
  *   KDF_BAM_SCAN  : drop secondary (0x100) and duplicate (0x400) records only.
  *   KDF_BAM_ALL   : every record.
  * A batch owns its host memory until kdf_bam_batch_free.  Metadata arrays are
- * filled only when want_meta != 0.  max_bases == 0 reads to end of file.     */
+ * filled only when want_meta != 0, base qualities only when want_meta >= 2
+ * (VCF-mode child reads, vcf/pipeline.py:671-690).  max_bases == 0 reads to
+ * end of file.                                                               */
 #define KDF_BAM_FASTA 0
 #define KDF_BAM_SCAN 1
 #define KDF_BAM_ALL 2
@@ -315,6 +317,8 @@ typedef struct kdf_bam_batch {
   const uint32_t* cigar_blob;    /* BAM encoding: len<<4 | op                 */
   const uint64_t* sa_off;        /* n_reads+1 offsets into sa_blob (SA:Z)     */
   const char* sa_blob;
+  const uint64_t* qual_off;      /* n_reads+1 offsets into qual_blob (want_meta >= 2) */
+  const uint8_t* qual_blob;      /* Phred base qualities (0xFF = absent)     */
   int at_eof;
 } kdf_bam_batch;
 

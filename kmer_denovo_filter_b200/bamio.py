@@ -29,7 +29,7 @@ class _Batch(ctypes.Structure):
         ("rec_index", _vp), ("ref_id", _vp), ("pos", _vp), ("next_ref_id", _vp),
         ("next_pos", _vp), ("flag", _vp), ("mapq", _vp), ("qname_off", _vp),
         ("qname_blob", _vp), ("cigar_off", _vp), ("cigar_blob", _vp),
-        ("sa_off", _vp), ("sa_blob", _vp), ("at_eof", _i),
+        ("sa_off", _vp), ("sa_blob", _vp), ("qual_off", _vp), ("qual_blob", _vp), ("at_eof", _i),
     ]
 
 
@@ -120,7 +120,10 @@ class Record:
         return bytes(b.sa_blob[int(b.sa_off[self.i]):int(b.sa_off[self.i + 1])]).decode()
 
     def get_aligned_pairs(self, matches_only=True):
-        """(query_pos, ref_pos) for M/=/X columns (``core/bam_scanner.py:111``)."""
+        """pysam ``get_aligned_pairs``: (query_pos, ref_pos) per CIGAR column;
+        with ``matches_only=False`` insertions / soft clips give (q, None) and
+        deletions / skips (None, r) (``core/bam_scanner.py:111``,
+        ``vcf/pipeline.py:683``)."""
         pairs = []
         q = 0
         r = self.reference_start
@@ -130,10 +133,33 @@ class Record:
                 q += ln
                 r += ln
             elif op in (1, 4):
+                if not matches_only:
+                    pairs.extend((q + j, None) for j in range(ln))
                 q += ln
             elif op in (2, 3):
+                if not matches_only:
+                    pairs.extend((None, r + j) for j in range(ln))
                 r += ln
         return pairs
+
+    def get_reference_positions(self, full_length=False):
+        if full_length:
+            out = [None] * self.query_length
+            for q, r in self.get_aligned_pairs(matches_only=True):
+                out[q] = r
+            return out
+        return [r for _q, r in self.get_aligned_pairs(matches_only=True)]
+
+    @property
+    def query_qualities(self):
+        """Phred qualities as a list, or None when absent (needs want_meta=2)."""
+        b = self.batch
+        if not getattr(b, "has_quals", False):
+            raise _engine.KdfError("batch was decoded without base qualities")
+        q = b.qual_blob[int(b.qual_off[self.i]):int(b.qual_off[self.i + 1])]
+        if q.shape[0] == 0 or int(q[0]) == 0xFF:
+            return None
+        return q.tolist()
 
     @property
     def query_sequence(self):
@@ -179,6 +205,10 @@ class HostBatch(_engine.HostStream):
             self.cigar_blob = _arr(raw.cigar_blob, int(self.cigar_off[-1]) if n else 0, np.uint32)
             self.sa_off = _arr(raw.sa_off, n + 1, np.uint64)
             self.sa_blob = _arr(raw.sa_blob, int(self.sa_off[-1]) if n else 0, np.uint8)
+            self.has_quals = int(want_meta) >= 2
+            if self.has_quals:
+                self.qual_off = _arr(raw.qual_off, n + 1, np.uint64)
+                self.qual_blob = _arr(raw.qual_blob, int(self.qual_off[-1]) if n else 0, np.uint8)
 
     def record(self, i):
         if not self.has_meta:
@@ -224,7 +254,7 @@ class BamReader:
 
     def next_batch(self, mode, max_bases=0, want_meta=False):
         raw = _Batch()
-        rc = self.lib.kdf_bam_next_batch(self.handle, mode, int(max_bases), 1 if want_meta else 0,
+        rc = self.lib.kdf_bam_next_batch(self.handle, mode, int(max_bases), int(want_meta),
                                          ctypes.byref(raw))
         if rc != 0:
             raise _engine.KdfError("BAM decode failed for %s: %s" % (

@@ -242,6 +242,8 @@ struct kdf_bam_batch_impl {
   std::vector<uint64_t> qname_off, cigar_off, sa_off;  // n+1 each
   std::vector<char> qname_blob, sa_blob;
   std::vector<uint32_t> cigar_blob;
+  std::vector<uint64_t> qual_off;   // n+1 (want_meta >= 2)
+  std::vector<uint8_t> qual_blob;   // Phred base qualities, l_seq bytes per read
   uint64_t n_bases = 0;
 };
 
@@ -409,6 +411,7 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
     im->qname_off.assign(n + 1, 0);
     im->cigar_off.assign(n + 1, 0);
     im->sa_off.assign(n + 1, 0);
+    if (want_meta >= 2) im->qual_off.assign(n + 1, 0);
     for (size_t i = 0; i < n; ++i) {
       const uint8_t* r = buf.data() + kept[i].off;
       int32_t bs = rd_i32(r - 4);
@@ -431,6 +434,11 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
         im->cigar_blob.push_back(v);
       }
       im->cigar_off[i + 1] = im->cigar_blob.size();
+      if (want_meta >= 2) {
+        const uint8_t* q = cg + 4 * (size_t)n_cig + (l_seq + 1) / 2;
+        im->qual_blob.insert(im->qual_blob.end(), q, q + l_seq);
+        im->qual_off[i + 1] = im->qual_blob.size();
+      }
       // walk aux tags for SA:Z
       const uint8_t* t = cg + 4 * (size_t)n_cig + (l_seq + 1) / 2 + l_seq;
       const uint8_t* end = r + bs;
@@ -491,6 +499,10 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
     out->cigar_blob = im->cigar_blob.data();
     out->sa_off = im->sa_off.data();
     out->sa_blob = im->sa_blob.data();
+    if (want_meta >= 2) {
+      out->qual_off = im->qual_off.data();
+      out->qual_blob = im->qual_blob.data();
+    }
   }
   out->at_eof = (b->eof && b->carry.empty()) ? 1 : 0;
   return KDF_OK;

@@ -48,6 +48,80 @@ def _is_symbolic(allele):
     return allele[0] == "<" or allele == "*" or "[" in allele or "]" in allele
 
 
+# ---- VCF-mode read helpers (CPU: a few dozen reads per variant) ------------
+
+def read_supports_alt(read, variant_pos, ref, alt, min_baseq=0, *, aligned_pairs=None, seq=None,
+                      quals=None):
+    """True iff the read carries exactly ``alt`` over the reference span of the
+    variant (reference ``kmer_utils.py:1037-1099``)."""
+    if alt is None or _is_symbolic(alt):
+        return False
+    if seq is None:
+        seq = read.query_sequence
+    if seq is None:
+        return False
+    if min_baseq > 0 and quals is None:
+        quals = read.query_qualities
+    if aligned_pairs is None:
+        aligned_pairs = read.get_aligned_pairs(matches_only=False)
+    extracted = []
+    in_region = False
+    end = variant_pos + len(ref)
+    for qpos, rpos in aligned_pairs:
+        if rpos is not None and rpos >= end:
+            break
+        if rpos == variant_pos:
+            in_region = True
+        if in_region and qpos is not None:
+            if min_baseq > 0 and quals is not None and quals[qpos] < min_baseq:
+                return False
+            extracted.append(seq[qpos])
+    if not in_region:
+        return False
+    return "".join(extracted).upper() == alt.upper()
+
+
+def extract_variant_spanning_kmers(read, variant_pos, k, min_baseq=0, ref=None, alt=None, *,
+                                   aligned_pairs=None, seq=None, quals=None):
+    """Canonical k-mers of the read that cover the variant, skipping windows with an
+    N or a base below ``min_baseq`` (reference ``kmer_utils.py:1102-1172``)."""
+    try:
+        rp = read.get_reference_positions(full_length=True).index(variant_pos)
+    except ValueError:
+        return set()
+    if seq is None:
+        seq = read.query_sequence
+    if seq is None:
+        return set()
+    if quals is None:
+        quals = read.query_qualities
+    alt_len = len(alt) if alt and not _is_symbolic(alt) else 1
+    start_min = max(0, rp - k + 1)
+    start_max = min(len(seq) - k, rp + alt_len - 1)
+    window_end = start_max + k
+    if window_end <= start_min:
+        return set()
+    up = seq[start_min:window_end].upper()
+    bad = bytearray(len(up))
+    for i, ch in enumerate(up):
+        if ch == "N":
+            bad[i] = 1
+    if quals is not None and min_baseq > 0:
+        for i in range(len(up)):
+            if quals[start_min + i] < min_baseq:
+                bad[i] = 1
+    out = set()
+    bad_count = sum(bad[:min(k, len(bad))])
+    for s in range(start_min, start_max + 1):
+        off = s - start_min
+        if off > 0:
+            bad_count += bad[off + k - 1] - bad[off - 1]
+        if bad_count:
+            continue
+        out.add(canonicalize(seq[s:s + k]))
+    return out
+
+
 # ---- integer keys ---------------------------------------------------------
 
 def key_of(kmer):
