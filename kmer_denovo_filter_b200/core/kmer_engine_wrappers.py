@@ -129,6 +129,26 @@ class RefIndex:
         self.keys = keys          # (lo u64, hi u64) numpy or None
         self.source = source
 
+    def to_bins(self, eng, n_parts):
+        """The reference's canonical k-mers in ``n_parts`` hash-range bins (the input
+        of ``kdf_count_bins``), with an exact-size retry if a range is skewed."""
+        from ..discovery import kmer_chain
+        if self.host_stream is not None:
+            n_max = self.host_stream.n_bases
+        else:
+            n_max = int(self.keys[0].shape[0])
+        cap = kmer_chain._bin_capacity(max(n_max, 1), n_parts)
+        while True:
+            bins = eng.new_bins(self.k, n_parts, cap)
+            if self.host_stream is not None:
+                eng.bin_stream(bins, eng.upload(self.host_stream, with_reads=False))
+            else:
+                lo, hi = eng.keys_to_device(self.keys, bins.key_words)
+                eng.bin_keys(bins, lo, hi)
+            if not bins.overflowed():
+                return bins
+            cap = int(bins.counts().max()) + 4
+
     def mark_present(self, eng, table, plane, stats=None):
         """OR 1 into ``plane`` of every table key that occurs in the reference."""
         if self.host_stream is not None:

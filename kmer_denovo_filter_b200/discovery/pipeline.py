@@ -35,6 +35,7 @@ from ..core.kmer_engine_wrappers import (  # noqa: F401  (re-exported like the r
     get_engine,
 )
 from ..kmer_utils import KmerSet, canonicalize
+from . import kmer_chain
 
 logger = logging.getLogger(__name__)
 
@@ -42,20 +43,75 @@ REF_PLANE = 1  # plane 1 of the child table holds the "in reference" flag
 
 
 class ChildCandidates:
-    """Module-1 handle: the child count table (plane 0 = count) and the
-    ``min_child_count`` threshold; replaces ``child_candidates.fa``."""
+    """Module-1 handle: the child's canonical k-mers in hash-range bins (HBM) plus
+    the counts of the first pass; replaces ``child.jf`` / ``child_candidates.fa``.
+    The count table itself never exists in HBM: every pass re-counts the bins in
+    an L2-resident slice (``kdf_count_bins``)."""
 
-    def __init__(self, eng, table, min_child_count, n_candidates, stats):
+    def __init__(self, eng, bins, slice_capacity, min_child_count, n_candidates, stats):
         self.engine = eng
-        self.table = table
+        self.bins = bins
+        self.slice_capacity = slice_capacity
         self.min_child_count = min_child_count
         self.n_candidates = n_candidates
-        self.stats = stats
+        self.stats = stats          # windows (k-mer instances), new (distinct), reads, bases
+        self.k = bins.k
+
+    def count(self, ref_bins=None, out_cap=1, **thresholds):
+        """One counting pass over the bins → ``eng.count_bins`` result; the slice is
+        enlarged (and the pass redone) when a bin holds more distinct k-mers than it."""
+        eng = self.engine
+        while True:
+            res = eng.count_bins(self.bins, ref_bins, self.slice_capacity, out_cap=out_cap,
+                                 count_min0=self.min_child_count, **thresholds)
+            if res["full"]:
+                if self.slice_capacity >= 2 * self.bins.bin_cap:
+                    raise _engine.KdfError("k-mer table slice full at %d slots" % self.slice_capacity)
+                self.slice_capacity = min(self.slice_capacity * 4, 2 * self.bins.bin_cap + 4)
+                logger.info("  growing the table slice to %d slots", self.slice_capacity)
+                continue
+            if res["n_out"] > out_cap and out_cap > 1:
+                out_cap = res["n_out"]
+                continue
+            return res
+
+    def dump(self, **thresholds):
+        """All (key, count, in-reference flag) that pass the thresholds — what
+        ``jellyfish dump -c`` would print; used by the tests."""
+        res = self.count(out_cap=max(self.stats["new"], 2), want_planes=True, **thresholds)
+        return res
 
     def close(self):
-        if self.table is not None:
-            self.table.close()
-            self.table = None
+        self.bins = None
+
+
+def bin_bam(eng, bam_path, kmer_size, threads, mode=bamio.MODE_FASTA, batch_bases=kw.BATCH_BASES):
+    """Decode a BAM (``samtools fasta -F 0xD00`` semantics) and append every valid
+    canonical k-mer to hash-range bins.  The packed batches are held in host memory
+    until the bins are known to be large enough (a skewed hash range triggers one
+    exact-size retry).  → (bins, slice_capacity, stats)."""
+    batches = []
+    with bamio.BamReader(bam_path, threads=threads) as rd:
+        for batch in rd.batches(mode, max_bases=batch_bases):
+            batches.append(batch)
+    n_max = sum(b.n_bases for b in batches)
+    tot = {"reads": sum(b.n_reads for b in batches), "bases": n_max}
+    n_parts, slice_capacity = kmer_chain.plan_partitions(max(n_max, 1))
+    bin_cap = kmer_chain._bin_capacity(max(n_max, 1), n_parts)
+    while True:
+        bins = eng.new_bins(kmer_size, n_parts, bin_cap)
+        st = eng.new_stats()
+        for b in batches:
+            ds = eng.upload(b, with_reads=False)
+            eng.bin_stream(bins, ds, st)
+        if not bins.overflowed():
+            break
+        bin_cap = int(bins.counts().max()) + 4
+        logger.info("  hash ranges are skewed: re-binning with %d slots per bin", bin_cap)
+    for b in batches:
+        b.close()
+    tot["windows"] = eng.read_stats(st)["windows"]
+    return bins, slice_capacity, tot
 
 
 # ── Module 1 ───────────────────────────────────────────────────────
@@ -66,49 +122,48 @@ def _extract_child_kmers_discovery(child_bam, ref_fasta, kmer_size, min_child_co
 
     Returns ``(ChildCandidates, n_candidates)``; the reference returns the
     path of a FASTA holding the same set (``dump -c -L min_child_count``).
+    ``jf_hash_size`` (Jellyfish ``-s``) is accepted and used as the total slot
+    budget of the table slices when given.
     """
     eng = get_engine(engine)
-    kwds = eng.lib.kdf_key_words(kmer_size)
-    if not kwds:
+    if not eng.lib.kdf_key_words(kmer_size):
         raise _engine.KdfError(
             "k=%d is outside the GPU engine's range (k <= 63; 64-bit keys for k <= 32, "
             "128-bit above)" % kmer_size)
-    slot_bytes = 16 if kwds == 1 else 32
-    free_b, _tot = eng.torch.cuda.mem_get_info(eng.device)
-    n_keys = kw._parse_hash_size(jf_hash_size)
-    if n_keys is None:
-        n_keys = kw._estimate_table_keys(child_bam, free_b, slot_bytes)
-    else:
-        n_keys = min(n_keys, int(free_b * 0.8 / slot_bytes))
     t0 = time.monotonic()
-    table = eng.new_table(kmer_size, capacity=max(eng.capacity_for(n_keys // 2), 1024))
-    logger.info("Extracting child k-mers from BAM (k=%d, table slots=%d)…", kmer_size,
-                table.capacity)
-    table, tot = kw.count_bam_into_table(eng, child_bam, table, _engine.MODE_INSERT_COUNT, 0,
-                                         threads, grow=True)
-    n_candidates = eng.threshold_count(table, min0=min_child_count)
+    logger.info("Extracting child k-mers from BAM (k=%d)…", kmer_size)
+    bins, slice_capacity, tot = bin_bam(eng, child_bam, kmer_size, threads)
+    n_keys = kw._parse_hash_size(jf_hash_size)
+    if n_keys:
+        slice_capacity = max(slice_capacity, (n_keys // bins.n_parts + 3) & ~3)
+    cand = ChildCandidates(eng, bins, slice_capacity, min_child_count, 0, tot)
+    res = cand.count(min0=min_child_count)
+    tot["new"] = res["distinct"]
+    tot["hits"] = res["hits"]
+    cand.n_candidates = n_candidates = res["n_count"]
     logger.info("Child k-mer counting complete (%.1fs): %d reads, %d k-mer instances, "
-                "%d distinct", time.monotonic() - t0, tot["reads"], tot["windows"], tot["new"])
+                "%d distinct (%d hash ranges x %d slots)", time.monotonic() - t0, tot["reads"],
+                tot["windows"], tot["new"], bins.n_parts, cand.slice_capacity)
     logger.info("Child candidate k-mers (count >= %d): %d", min_child_count, n_candidates)
-    return ChildCandidates(eng, table, min_child_count, n_candidates, tot), n_candidates
+    return cand, n_candidates
 
 
 def _subtract_reference_kmers(ref_jf, child_candidates_fa, tmpdir):
     """Remove candidates that occur in the reference → ``(KmerSet, n_non_ref)``.
 
     The reference queries every candidate against ``ref.jf`` and keeps count
-    == 0; here the reference sequence is streamed against the child table
-    (mark-if-present) and the survivors are compacted.  The candidates handle
-    is released afterwards, as the reference deletes its input FASTA."""
+    == 0; here the reference k-mers are binned by the same hash ranges and
+    marked inside the counting pass, and the survivors are emitted from the
+    L2-resident slice.  The candidates handle is released afterwards, as the
+    reference deletes its input FASTA."""
     cand = child_candidates_fa
     eng = cand.engine
-    eng.clear_plane(cand.table, REF_PLANE)
-    ref_jf.mark_present(eng, cand.table, REF_PLANE)
-    n, lo, hi, _p0, _p1 = eng.threshold_compact(cand.table, min0=cand.min_child_count, max1=0)
-    k = cand.table.k
+    ref_bins = ref_jf.to_bins(eng, cand.bins.n_parts)
+    res = cand.count(ref_bins, out_cap=max(cand.n_candidates, 2), min0=cand.min_child_count, max1=0)
+    k = cand.k
     cand.close()
-    logger.info("Non-reference child k-mers after subtraction: %d", n)
-    return KmerSet(eng, k, lo, hi), n
+    logger.info("Non-reference child k-mers after subtraction: %d", res["n_out"])
+    return KmerSet(eng, k, res["lo"], res["hi"]), res["n_out"]
 
 
 # ── Module 2 ───────────────────────────────────────────────────────
@@ -202,27 +257,27 @@ def scan_child_reads(eng, child_bam, table, kmer_size, min_distinct_kmers_per_re
     with bamio.BamReader(child_bam, threads=threads) as rd:
         for batch in rd.batches(bamio.MODE_SCAN, max_bases=batch_bases, want_meta=True):
             ds = eng.upload(batch)
-            res = eng.scan_reads(table, ds, min_distinct=max(1, min_distinct_kmers_per_read))
-            nd = res["ndistinct"].cpu().numpy().view(np.uint32)
-            nh = res["nhits"].cpu().numpy().view(np.uint32)
-            if res["n_hits"]:
-                pos = res["hit_pos"].cpu().numpy().view(np.uint64)
-                slot = res["hit_slot"].cpu().numpy().view(np.uint32)
-                order = np.argsort(pos, kind="stable")
-                pos = pos[order]
-                slot = slot[order]
+            # sparse form: a streaming probe emits the (rare) hit windows, the device
+            # reduces them per read; dense per-read arrays are rebuilt here for the
+            # CPU cluster / anchor step
+            sp = eng.scan_reads_sparse(table, ds)
+            nd = np.zeros(batch.n_reads, dtype=np.uint32)
+            nh = np.zeros(batch.n_reads, dtype=np.uint32)
+            rr = sp["read"].astype(np.int64)
+            nd[rr] = sp["ndistinct"]
+            nh[rr] = sp["nhits"]
+            thr = max(1, min_distinct_kmers_per_read)
+            pos = sp["hit_pos"]
+            slot = sp["hit_slot"]
+            if pos.shape[0]:
                 ridx = np.searchsorted(batch.read_starts, pos, side="right") - 1
+                keep = nd[ridx] >= thr
+                pos, slot, ridx = pos[keep], slot[keep], ridx[keep]
                 off = (pos - batch.read_starts[ridx]).astype(np.int64)
             else:
                 ridx = np.zeros(0, dtype=np.int64)
                 off = np.zeros(0, dtype=np.int64)
                 slot = np.zeros(0, dtype=np.uint32)
-            # finish the rare overflow reads (> 1024 hit windows) from the slot list
-            ov = np.flatnonzero(nd == _engine.NDISTINCT_OVERFLOW)
-            if ov.size:
-                nd = nd.copy()
-                for r in ov.tolist():
-                    nd[r] = np.unique(slot[ridx == r]).shape[0]
             yield batch, nd, nh, ridx, off, slot
 
 

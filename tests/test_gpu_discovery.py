@@ -35,12 +35,13 @@ def test_discovery_chain_stage_sets(eng, giab_paths):
     assert n_cand == exp["candidates"] == 51125
     assert cand.stats["new"] == exp["child_distinct"]
     assert cand.stats["windows"] == exp["child_total"]
-    n, lo, hi, p0, _p1 = eng.threshold_compact(cand.table, want_planes=True)
-    keys = eng.keys_to_pyints(lo, hi)
-    counts = p0.cpu().numpy().view(np.uint32).tolist()
+    d = cand.dump()
+    keys = eng.keys_to_pyints(d["lo"], d["hi"])
+    counts = d["p0"].cpu().numpy().view(np.uint32).tolist()
+    assert d["n_out"] == exp["child_distinct"]
     assert _digest([(key << 32) | c for key, c in zip(keys, counts)]) == exp["child_counts_digest"]
-    n, lo, hi, _a, _b = eng.threshold_compact(cand.table, min0=3)
-    assert _digest(eng.keys_to_pyints(lo, hi)) == exp["candidates_digest"]
+    d = cand.dump(min0=3)
+    assert _digest(eng.keys_to_pyints(d["lo"], d["hi"])) == exp["candidates_digest"]
     non_ref, n_non_ref = P._subtract_reference_kmers(ref, cand, None)
     assert n_non_ref == exp["non_ref"] == 6679
     assert _digest(non_ref.to_pyints()) == exp["non_ref_digest"]
