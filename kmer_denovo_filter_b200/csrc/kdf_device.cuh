@@ -169,30 +169,46 @@ KDF_HD u32 ld_valid(const StreamView& s, u64 w) {
 // validity shift registers move 2 / 1 bits per step.
 template <int KW> struct WindowIter;
 
+// bit (63 - j) of the result: bases j .. j+k-1 of the 64-base validity register
+// are all valid (runs of k ones, by doubling: k = sum of powers of two)
+KDF_HD u64 runs_of_k(u64 vv, int k) {
+  u64 p = vv, res = ~0ull;
+  int off = 0;
+  for (int b = 0; (1 << b) <= k; ++b) {
+    if (k & (1 << b)) {
+      res &= (p << off);
+      off += 1 << b;
+    }
+    p &= (b < 6) ? (p << (1 << b)) : 0ull;
+  }
+  return res;
+}
+
 template <> struct WindowIter<1> {
   u64 b0, b1;   // base shift register (b0 holds the current window at its top)
-  u64 vv;       // validity shift register (MSB = current start)
+  u32 okm;      // window validity of the 32 starts of this word (MSB = current start)
   Key<1> rc;
   int k;
   KDF_HD WindowIter(const StreamView& s, u64 w, int k_) : k(k_) {
     b0 = ld_code(s, w);
     b1 = ld_code(s, w + 1);
-    vv = ((u64)ld_valid(s, w) << 32) | (u64)ld_valid(s, w + 1);
+    u64 vv = ((u64)ld_valid(s, w) << 32) | (u64)ld_valid(s, w + 1);
+    okm = (u32)(runs_of_k(vv, k) >> 32);
     Key<1> f = fwd();
     rc = revcomp(f, k);
   }
-  KDF_HD bool any_valid() const { return vv != 0; }
+  KDF_HD bool any_valid() const { return okm != 0; }
   KDF_HD Key<1> fwd() const {
     Key<1> f;
     f.lo = b0 >> (64 - 2 * k);
     return f;
   }
-  KDF_HD bool ok() const { return ((~vv) >> (64 - k)) == 0; }
+  KDF_HD bool ok() const { return (okm >> 31) != 0; }
   KDF_HD Key<1> canonical() const { return kmin(fwd(), rc); }
   KDF_HD void advance() {
     b0 = (b0 << 2) | (b1 >> 62);
     b1 <<= 2;
-    vv <<= 1;
+    okm <<= 1;
     u64 nb = (b0 >> (64 - 2 * k)) & 3ull;  // newest base of the new window
     rc.lo = (rc.lo >> 2) | ((3ull - nb) << (2 * (k - 1)));
   }
@@ -200,18 +216,24 @@ template <> struct WindowIter<1> {
 
 template <> struct WindowIter<2> {
   u64 b0, b1, b2;
-  u64 v0, v1;  // 96 validity bits: v0 = words w,w+1 ; v1 = word w+2 in its top half
+  u32 okm;     // window validity of the 32 starts of this word (MSB = current start)
   Key<2> rc;
   int k;
   KDF_HD WindowIter(const StreamView& s, u64 w, int k_) : k(k_) {
     b0 = ld_code(s, w);
     b1 = ld_code(s, w + 1);
     b2 = ld_code(s, w + 2);
-    v0 = ((u64)ld_valid(s, w) << 32) | (u64)ld_valid(s, w + 1);
-    v1 = ((u64)ld_valid(s, w + 2) << 32);
+    // 96 validity bits: v0 = words w, w+1 ; v1 = word w+2 in its top half.  A window
+    // of k <= 64 bases starting in word w needs run(start, 32) & run(start+32, k-32)
+    // for k > 32: both runs lie inside the 64-bit views below.
+    u64 v0 = ((u64)ld_valid(s, w) << 32) | (u64)ld_valid(s, w + 1);
+    u64 v1 = ((u64)ld_valid(s, w + 1) << 32) | (u64)ld_valid(s, w + 2);
+    u64 r = runs_of_k(v0, k < 32 ? k : 32);
+    if (k > 32) r &= runs_of_k(v1, k - 32);
+    okm = (u32)(r >> 32);
     rc = revcomp(fwd(), k);
   }
-  KDF_HD bool any_valid() const { return (v0 | v1) != 0; }
+  KDF_HD bool any_valid() const { return okm != 0; }
   KDF_HD Key<2> fwd() const {
     int sh = 128 - 2 * k;  // 0..62
     Key<2> f;
@@ -224,14 +246,13 @@ template <> struct WindowIter<2> {
     }
     return f;
   }
-  KDF_HD bool ok() const { return k == 64 ? (~v0 == 0) : (((~v0) >> (64 - k)) == 0); }
+  KDF_HD bool ok() const { return (okm >> 31) != 0; }
   KDF_HD Key<2> canonical() const { return kmin(fwd(), rc); }
   KDF_HD void advance() {
     b0 = (b0 << 2) | (b1 >> 62);
     b1 = (b1 << 2) | (b2 >> 62);
     b2 <<= 2;
-    v0 = (v0 << 1) | (v1 >> 63);
-    v1 <<= 1;
+    okm <<= 1;
     // newest base = last base of the new window = bits just above the cut
     int sh = 128 - 2 * k;
     u64 nb = (sh == 0 ? b1 : (b1 >> sh)) & 3ull;

@@ -66,6 +66,7 @@ template <int KW> struct TableView {
   u32* p1;
   u32 n_buckets;
   int log2_parts;
+  bool fast_empty;  // k % 32 != 0 (see has_empty)
 };
 template <int KW> struct SPB { static constexpr int v = 4 / KW; };  // slots per bucket
 
@@ -77,6 +78,7 @@ static TableView<KW> view_of_table(const kdf_table* t) {
   v.p1 = v.p0 + t->capacity;
   v.n_buckets = (u32)(t->capacity / SPB<KW>::v);
   v.log2_parts = t->log2_parts;
+  v.fast_empty = (t->k % 32) != 0;
   return v;
 }
 
@@ -117,10 +119,22 @@ __device__ __forceinline__ int match_in(const Bucket& b, const Key<2>& key) {
   if (b.q[0] == key.lo && b.q[1] == key.hi) j = 0;
   return j;
 }
-__device__ __forceinline__ bool has_empty(const Bucket& b, Key<1>) {
+// `fast`: k is not a multiple of 32, so the top 32 bits of a stored key's most
+// significant word are never all ones and testing them alone identifies an empty slot
+__device__ __forceinline__ bool has_empty(const Bucket& b, Key<1>, bool fast) {
+  if (fast) {
+    // a slot is empty iff its high half is all ones: max over the four high halves
+    u32 h0 = (u32)(b.q[0] >> 32), h1 = (u32)(b.q[1] >> 32), h2 = (u32)(b.q[2] >> 32), h3 = (u32)(b.q[3] >> 32);
+    u32 mx = max(max(h0, h1), max(h2, h3));
+    return mx == 0xffffffffu;
+  }
   return b.q[0] == EMPTY || b.q[1] == EMPTY || b.q[2] == EMPTY || b.q[3] == EMPTY;
 }
-__device__ __forceinline__ bool has_empty(const Bucket& b, Key<2>) {
+__device__ __forceinline__ bool has_empty(const Bucket& b, Key<2>, bool fast) {
+  if (fast) {
+    u32 h0 = (u32)(b.q[1] >> 32), h1 = (u32)(b.q[3] >> 32);
+    return max(h0, h1) == 0xffffffffu;
+  }
   return (b.q[0] == EMPTY && b.q[1] == EMPTY) || (b.q[2] == EMPTY && b.q[3] == EMPTY);
 }
 // slot j of the bucket may be (a possibly torn view of) an empty slot
@@ -220,7 +234,7 @@ __device__ __forceinline__ u32 resolve_from(const TableView<KW>& t, u32 b, const
         }
       }
     } else {
-      if (has_empty(bk, key)) return R_MISS;
+      if (has_empty(bk, key, t.fast_empty)) return R_MISS;
     }
     b = (b + 1 == t.n_buckets) ? 0 : b + 1;
   }
@@ -415,7 +429,7 @@ __global__ void __launch_bounds__(SMEM ? 512 : 256, SMEM ? KDF_SMEM_BLOCKS : KDF
             on_found<OP, KW>(t, (u64)bidx[u] * S + j, plane, arg, pos0 + u, sink);
           } else if (kInsert) {  // new key (or full bucket): CAS path, queued
             tally(st, sq_push_or_resolve<KW, OP>(q, t, bidx[u], keys[u], plane, arg, pos0 + u, sink));
-          } else if (!has_empty(bk[u], keys[u])) {  // full bucket: look further, queued
+          } else if (!has_empty(bk[u], keys[u], t.fast_empty)) {  // full bucket: look further, queued
             u32 nb = (bidx[u] + 1 == t.n_buckets) ? 0 : bidx[u] + 1;
             tally(st, sq_push_or_resolve<KW, OP>(q, t, nb, keys[u], plane, arg, pos0 + u, sink));
           }
@@ -503,7 +517,7 @@ __global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_update_keys(TableView<
           on_found<OP, KW>(t, (u64)bidx[u] * S + j, plane, arg, 0, sink);
         } else if (kInsert) {
           tally(st, sq_push_or_resolve<KW, OP>(q, t, bidx[u], keys[u], plane, arg, 0, sink));
-        } else if (!has_empty(bk[u], keys[u])) {
+        } else if (!has_empty(bk[u], keys[u], t.fast_empty)) {
           u32 nb = (bidx[u] + 1 == t.n_buckets) ? 0 : bidx[u] + 1;
           tally(st, sq_push_or_resolve<KW, OP>(q, t, nb, keys[u], plane, arg, 0, sink));
         }
@@ -586,7 +600,7 @@ __device__ __forceinline__ bool find_slot(const TableView<KW>& t, const Key<KW>&
       idx_out = (u64)b * S + j;
       return true;
     }
-    if (has_empty(bk, key)) return false;
+    if (has_empty(bk, key, t.fast_empty)) return false;
     b = (b + 1 == t.n_buckets) ? 0 : b + 1;
   }
   return false;

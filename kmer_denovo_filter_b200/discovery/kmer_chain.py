@@ -145,9 +145,13 @@ def count_child_partitioned(eng, child_streams, ref_streams, k, min_child_count,
 def _primed_table(eng, k, lo, hi, n):
     # small sets get load 0.25: they stay within the shared-memory budget of the
     # stream kernels and almost no probe has to look past its home bucket
+    # larger read-only sets get load 0.33: a third as many probes meet a full home
+    # bucket (4.6 % instead of 14 %), which is worth more than the extra L2 footprint
     n_keys = max(n, 1)
     if n_keys * 4 * 8 * eng.lib.kdf_key_words(k) <= SMEM_TABLE_BYTES:
         n_keys *= 2
+    else:
+        n_keys = n_keys * 3 // 2
     t = eng.new_table(k, n_keys=n_keys)
     eng.update_keys(t, lo, hi, _engine.MODE_INSERT_ONLY, 0, 0)
     return t
