@@ -588,6 +588,95 @@ __global__ void __launch_bounds__(256) k_threshold_compact(TableView<KW> t, u64 
   }
 }
 
+// Bucket-wise form used by kdf_count_bins: one thread per 32-byte bucket (4 or 2
+// slots, three wide loads), same predicate and compaction as above, and the slice
+// is cleared on the way out (CLEAR) so that the next bin needs no fill pass.
+template <int KW, bool CLEAR>
+__global__ void __launch_bounds__(256) k_emit_buckets(TableView<KW> t, u32 min0, u32 max0, u32 min1,
+                                                      u32 max1, u64* out_lo, u64* out_hi,
+                                                      u32* out_p0, u32* out_p1, u64 cap, u64* n_out,
+                                                      u32 count_min0, u64* n_count, u64* n_occupied) {
+  constexpr int S = SPB<KW>::v;
+  u64 stride = (u64)gridDim.x * blockDim.x;
+  u64 first = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  u64 rounds = ((u64)t.n_buckets + stride - 1) / stride;
+  unsigned lane = threadIdx.x & 31;
+  u32 cnt_ge = 0, cnt_occ = 0;
+  for (u64 r = 0; r < rounds; ++r) {
+    u64 b = first + r * stride;
+    bool inb = b < t.n_buckets;
+    Bucket bk;
+    bk.q[0] = bk.q[1] = bk.q[2] = bk.q[3] = EMPTY;
+    u32 p0[S], p1[S];
+#pragma unroll
+    for (int j = 0; j < S; ++j) p0[j] = p1[j] = 0;
+    bool any = false;
+    if (inb) {
+      bk = ld_bucket(t.keys + b * 4);
+      any = (KW == 1) ? !(bk.q[0] == EMPTY && bk.q[1] == EMPTY && bk.q[2] == EMPTY && bk.q[3] == EMPTY)
+                      : !(bk.q[1] == EMPTY && bk.q[3] == EMPTY && bk.q[0] == EMPTY && bk.q[2] == EMPTY);
+      if (any) {
+        if constexpr (KW == 1) {
+          uint4 a = __ldcg(reinterpret_cast<const uint4*>(t.p0 + b * 4));
+          uint4 c = __ldcg(reinterpret_cast<const uint4*>(t.p1 + b * 4));
+          p0[0] = a.x; p0[1] = a.y; p0[2] = a.z; p0[3] = a.w;
+          p1[0] = c.x; p1[1] = c.y; p1[2] = c.z; p1[3] = c.w;
+        } else {
+          uint2 a = __ldcg(reinterpret_cast<const uint2*>(t.p0 + b * 2));
+          uint2 c = __ldcg(reinterpret_cast<const uint2*>(t.p1 + b * 2));
+          p0[0] = a.x; p0[1] = a.y;
+          p1[0] = c.x; p1[1] = c.y;
+        }
+        if (CLEAR) {
+          asm volatile("st.global.cg.v4.u64 [%0], {%1,%1,%1,%1};" ::"l"(t.keys + b * 4), "l"(EMPTY) : "memory");
+          if (KW == 1) {
+            *reinterpret_cast<uint4*>(t.p0 + b * 4) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(t.p1 + b * 4) = make_uint4(0, 0, 0, 0);
+          } else {
+            *reinterpret_cast<uint2*>(t.p0 + b * 2) = make_uint2(0, 0);
+            *reinterpret_cast<uint2*>(t.p1 + b * 2) = make_uint2(0, 0);
+          }
+        }
+      }
+    }
+    if (!__any_sync(0xffffffffu, any)) continue;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      Key<KW> key;
+      key.lo = bk.q[j * KW];
+      if (KW == 2) ((u64*)&key)[KW - 1] = bk.q[j * KW + (KW - 1)];
+      bool occ = any && !is_empty_key(key);
+      bool keep = occ && p0[j] >= min0 && p0[j] <= max0 && p1[j] >= min1 && p1[j] <= max1;
+      cnt_occ += occ ? 1u : 0u;
+      cnt_ge += (occ && p0[j] >= count_min0) ? 1u : 0u;
+      unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (m) {
+        u64 base = 0;
+        int leader = __ffs(m) - 1;
+        if ((int)lane == leader) base = atomicAdd(n_out, (u64)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (keep) {
+          u64 o = base + __popc(m & ((1u << lane) - 1));
+          if (o < cap) {
+            if (out_lo) out_lo[o] = key.lo;
+            if (KW == 2 && out_hi) out_hi[o] = ((const u64*)&key)[KW - 1];
+            if (out_p0) out_p0[o] = p0[j];
+            if (out_p1) out_p1[o] = p1[j];
+          }
+        }
+      }
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    cnt_ge += __shfl_xor_sync(0xffffffffu, cnt_ge, o);
+    cnt_occ += __shfl_xor_sync(0xffffffffu, cnt_occ, o);
+  }
+  if (lane == 0) {
+    if (n_count && cnt_ge) atomicAdd(n_count, (u64)cnt_ge);
+    if (n_occupied && cnt_occ) atomicAdd(n_occupied, (u64)cnt_occ);
+  }
+}
+
 // ------------------------------------------------------------- K4 ---------
 template <int KW>
 __device__ __forceinline__ bool find_slot(const TableView<KW>& t, const Key<KW>& key, u64& idx_out) {
@@ -1136,6 +1225,18 @@ static int launch_threshold(const kdf_table* t, u32 min0, u32 max0, u32 min1, u3
   return KDF_OK;
 }
 
+template <int KW>
+static int launch_emit_buckets(const kdf_table* t, u32 min0, u32 max0, u32 min1, u32 max1, u64* out_lo,
+                               u64* out_hi, u32* out_p0, u32* out_p1, u64 cap, u64* n_out,
+                               u32 count_min0, u64* n_count, u64* n_occ, cudaStream_t st) {
+  TableView<KW> tv = view_of_table<KW>(t);
+  int g = grid_for((const void*)k_emit_buckets<KW, true>, 256, 0, tv.n_buckets, t->sm_count);
+  k_emit_buckets<KW, true><<<g, 256, 0, st>>>(tv, min0, max0, min1, max1, out_lo, out_hi, out_p0, out_p1,
+                                              cap, n_out, count_min0, n_count, n_occ);
+  CUDA_TRY(cudaGetLastError());
+  return KDF_OK;
+}
+
 static int check_table_args(int k, uint64_t capacity, const void* slots, const char* who) {
   int kw = kdf_key_words(k);
   if (!kw) return fail(KDF_ERR_ARG, std::string(who) + ": k must be in 1..64");
@@ -1529,9 +1630,9 @@ int kdf_count_bins(int k, int n_parts, const uint64_t* child_bins, uint64_t chil
   cudaStream_t st = (cudaStream_t)stream;
   u64* ctr = (u64*)counters;  // [0..3] = stats block (windows = keys applied, full, hits, new), [4] = #(p0 >= count_min0), [5] = #occupied
   const int kw = t.key_words;
+  rc = clear_table_async(&t, st);  // once: every emit pass leaves the slice clean
+  if (rc != KDF_OK) return rc;
   for (int p = 0; p < n_parts; ++p) {
-    rc = clear_table_async(&t, st);
-    if (rc != KDF_OK) return rc;
     const u64* cb = (const u64*)child_bins + (u64)p * child_bin_cap * kw;
     if (kw == 1)
       rc = launch_update_keys<1, OP_INSERT_COUNT>(&t, cb, nullptr, child_bin_cap, (const u64*)child_cursors + p, 0, 1, ctr, st);
@@ -1547,11 +1648,11 @@ int kdf_count_bins(int k, int n_parts, const uint64_t* child_bins, uint64_t chil
       if (rc != KDF_OK) return rc;
     }
     if (kw == 1)
-      rc = launch_threshold<1>(&t, min0, max0, min1, max1, (u64*)out_lo, (u64*)out_hi, out_p0, out_p1, out_cap,
-                               (u64*)n_out, count_min0, ctr + 4, ctr + 5, st);
+      rc = launch_emit_buckets<1>(&t, min0, max0, min1, max1, (u64*)out_lo, (u64*)out_hi, out_p0, out_p1,
+                                  out_cap, (u64*)n_out, count_min0, ctr + 4, ctr + 5, st);
     else
-      rc = launch_threshold<2>(&t, min0, max0, min1, max1, (u64*)out_lo, (u64*)out_hi, out_p0, out_p1, out_cap,
-                               (u64*)n_out, count_min0, ctr + 4, ctr + 5, st);
+      rc = launch_emit_buckets<2>(&t, min0, max0, min1, max1, (u64*)out_lo, (u64*)out_hi, out_p0, out_p1,
+                                  out_cap, (u64*)n_out, count_min0, ctr + 4, ctr + 5, st);
     if (rc != KDF_OK) return rc;
   }
   return KDF_OK;

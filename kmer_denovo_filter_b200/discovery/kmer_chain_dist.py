@@ -113,7 +113,7 @@ def count_child_dist(eng, child_streams, ref_streams, k, min_child_count, world)
     r_recv, r_counts, r_cap, r_win = route_to_owners(eng, ref_streams, k, world)
     n_child = int(c_counts.sum())
     n_ref = int(r_counts.sum())
-    n_parts, slice_capacity = _kc.plan_partitions(max(n_child, 1))
+    n_parts, slice_capacity = _kc.plan_partitions(max(n_child, 1), key_words=kw)
     bin_cap = _kc._bin_capacity(max(n_child, 1), n_parts)
     ref_cap = _kc._bin_capacity(max(n_ref, 1), n_parts)
     while True:

@@ -96,7 +96,7 @@ def bin_bam(eng, bam_path, kmer_size, threads, mode=bamio.MODE_FASTA, batch_base
             batches.append(batch)
     n_max = sum(b.n_bases for b in batches)
     tot = {"reads": sum(b.n_reads for b in batches), "bases": n_max}
-    n_parts, slice_capacity = kmer_chain.plan_partitions(max(n_max, 1))
+    n_parts, slice_capacity = kmer_chain.plan_partitions(max(n_max, 1), key_words=eng.lib.kdf_key_words(kmer_size))
     bin_cap = kmer_chain._bin_capacity(max(n_max, 1), n_parts)
     while True:
         bins = eng.new_bins(kmer_size, n_parts, bin_cap)

@@ -689,7 +689,7 @@ class CudaEngine:
             p0.data_ptr() if p0 is not None else None, p1.data_ptr() if p1 is not None else None,
             out_cap, n_out.data_ptr(), count_min0, ctr.data_ptr(), self.stream_ptr()))
         self._t1("count_bins/kw%d" % kw, ev)
-        self.launches += child_bins.n_parts * (4 + (1 if ref_bins is not None else 0))
+        self.launches += 2 + child_bins.n_parts * (2 + (1 if ref_bins is not None else 0))
         c = ctr.cpu().numpy().view(np.uint64)
         n = int(n_out.item())
         m = min(n, out_cap)
