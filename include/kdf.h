@@ -239,6 +239,17 @@ int kdf_reduce_hits(const uint64_t* hit_pos /*DEV*/, const uint32_t* hit_slot /*
 int kdf_bin_stream(const kdf_stream* s, int k, int by_owner, int n_parts,
                    uint64_t* bins /*DEV*/, uint64_t bin_cap, uint64_t* cursors /*DEV*/,
                    uint64_t* overflow /*DEV*/, uint64_t* stats /*DEV or NULL*/, void* stream);
+/* The same kernel with one base pointer per bin (bin_ptrs: DEV array of n_parts
+ * device pointers, each to bin_cap keys).  The pointers may address PEER memory
+ * mapped over NVLink / NVSwitch: with by_owner == 1 and bin r placed in rank r's
+ * receive buffer, the shared-memory-staged flush of the binning kernel is the
+ * all-to-all itself — compute and transfer in one kernel, no send buffer, no
+ * NCCL call.  cursors / overflow stay local to the sender (each (sender, owner)
+ * pair has its own region), the sender publishes min(cursors, bin_cap) afterwards. */
+int kdf_bin_stream_to(const kdf_stream* s, int k, int by_owner, int n_parts,
+                      uint64_t* const* bin_ptrs /*DEV*/, uint64_t bin_cap,
+                      uint64_t* cursors /*DEV*/, uint64_t* overflow /*DEV*/,
+                      uint64_t* stats /*DEV or NULL*/, void* stream);
 int kdf_bin_keys(const uint64_t* lo /*DEV*/, const uint64_t* hi /*DEV or NULL*/, uint64_t n,
                  int k, int by_owner, int n_parts, uint64_t* bins /*DEV*/, uint64_t bin_cap,
                  uint64_t* cursors /*DEV*/, uint64_t* overflow /*DEV*/, void* stream);

@@ -913,6 +913,18 @@ template <> __device__ __forceinline__ void st_key<2>(u64* bins, u64 idx, const 
   reinterpret_cast<ulonglong2*>(bins)[idx] = make_ulonglong2(key.lo, key.hi);
 }
 
+// Where bin p lives: a region of one local array (ptrs == NULL), or its own base
+// pointer — which may be PEER memory mapped over NVLink: then the queue flush below
+// IS the transfer of the multi-GPU all-to-all (kdf_bin_stream_to).
+struct BinDest {
+  u64* base;
+  u64* const* ptrs;
+  u64 cap;
+  __device__ __forceinline__ u64* of(u32 p, int kw) const {
+    return ptrs ? ptrs[p] : base + (u64)p * cap * kw;
+  }
+};
+
 template <int KW>
 struct BinStage {
   // dynamic shared memory layout: cnt[P] u32 | gbase[P] u64 | queue[P][QCAP] keys
@@ -934,7 +946,7 @@ struct BinStage {
   // the lane has one).  Queue overflow falls back to a direct global append.
   // With few bins (owner binning at 2..8 ranks) every lane would hit the same
   // few shared counters, so the warp aggregates: one atomic per bin per warp.
-  __device__ __forceinline__ void push(bool ok, u32 p, const Key<KW>& key, u64* bins, u64 bin_cap,
+  __device__ __forceinline__ void push(bool ok, u32 p, const Key<KW>& key, const BinDest& dst,
                                        u64* cursors, u64* overflow) {
     u32 o = 0;
     if (n_parts <= 8) {
@@ -959,12 +971,12 @@ struct BinStage {
       if (KW == 2) q[1] = ((const u64*)&key)[KW - 1];
     } else {
       u64 g = atomicAdd(cursors + p, 1ull);
-      if (g < bin_cap) st_key<KW>(bins, (u64)p * bin_cap + g, key);
+      if (g < dst.cap) st_key<KW>(dst.of(p, KW), g, key);
       else atomicOr(overflow, 1ull);
     }
   }
   // all threads: write every queue to its bin and reset the counters
-  __device__ void flush(u64* bins, u64 bin_cap, u64* cursors, u64* overflow) {
+  __device__ void flush(const BinDest& dst, u64* cursors, u64* overflow) {
     __syncthreads();
     for (int p = threadIdx.x; p < n_parts; p += blockDim.x) {
       u32 c = cnt[p];
@@ -981,14 +993,15 @@ struct BinStage {
       u32 c = cnt[p];
       if (c > (u32)qcap) c = qcap;
       u64 g0 = gbase[p];
+      u64* out = dst.of(p, KW);
       for (u32 i = lane; i < c; i += step) {
         u64 g = g0 + i;
         const u64* q = queue + ((size_t)p * qcap + i) * KW;
-        if (g < bin_cap) {
+        if (g < dst.cap) {
           Key<KW> key;
           key.lo = q[0];
           if (KW == 2) ((u64*)&key)[KW - 1] = q[1];
-          st_key<KW>(bins, (u64)p * bin_cap + g, key);
+          st_key<KW>(out, g, key);
         } else {
           atomicOr(overflow, 1ull);
         }
@@ -1011,8 +1024,8 @@ constexpr int BIN_WPR = 16;
 
 template <int KW, bool BY_OWNER>
 __global__ void __launch_bounds__(BIN_THREADS) k_bin_stream(StreamView s, int k, int log2_parts,
-                                                            u32 n_parts, int qcap, u64* bins,
-                                                            u64 bin_cap, u64* cursors, u64* overflow,
+                                                            u32 n_parts, int qcap, BinDest dst,
+                                                            u64* cursors, u64* overflow,
                                                             u64* stats) {
   extern __shared__ __align__(16) unsigned char bin_smem[];
   BinStage<KW> stage;
@@ -1033,10 +1046,9 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_stream(StreamView s, int k,
         Key<KW> key = it.canonical();
         it.advance();
         windows += ok ? 1u : 0u;
-        stage.push(ok, bin_of<KW, BY_OWNER>(key, log2_parts, n_parts), key, bins, bin_cap, cursors,
-                   overflow);
+        stage.push(ok, bin_of<KW, BY_OWNER>(key, log2_parts, n_parts), key, dst, cursors, overflow);
       }
-      stage.flush(bins, bin_cap, cursors, overflow);
+      stage.flush(dst, cursors, overflow);
     }
   }
   if (stats) {
@@ -1048,7 +1060,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_stream(StreamView s, int k,
 template <int KW, bool BY_OWNER>
 __global__ void __launch_bounds__(BIN_THREADS) k_bin_keys(const u64* lo, const u64* hi, u64 n,
                                                           int log2_parts, u32 n_parts, int qcap,
-                                                          u64* bins, u64 bin_cap, u64* cursors,
+                                                          BinDest dst, u64* cursors,
                                                           u64* overflow) {
   extern __shared__ __align__(16) unsigned char bin_smem[];
   BinStage<KW> stage;
@@ -1063,10 +1075,9 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_keys(const u64* lo, const u
       u64 i = base + (u64)j * blockDim.x;
       bool ok = i < n;
       Key<KW> key = ld_key_stream<KW>(lo, hi, ok ? i : 0);
-      stage.push(ok, bin_of<KW, BY_OWNER>(key, log2_parts, n_parts), key, bins, bin_cap, cursors,
-                 overflow);
+      stage.push(ok, bin_of<KW, BY_OWNER>(key, log2_parts, n_parts), key, dst, cursors, overflow);
     }
-    stage.flush(bins, bin_cap, cursors, overflow);
+    stage.flush(dst, cursors, overflow);
   }
 }
 
@@ -1532,10 +1543,28 @@ static int bin_qcap(int n_parts, int kw) {
   return q;
 }
 
+static int bin_stream_impl(const kdf_stream* s, int k, int by_owner, int n_parts, BinDest dst,
+                           uint64_t* cursors, uint64_t* overflow, uint64_t* stats, void* stream);
+
 int kdf_bin_stream(const kdf_stream* s, int k, int by_owner, int n_parts, uint64_t* bins,
                    uint64_t bin_cap, uint64_t* cursors, uint64_t* overflow, uint64_t* stats,
                    void* stream) {
   if (!s || !bins || !cursors || !overflow) return fail(KDF_ERR_ARG, "kdf_bin_stream: NULL argument");
+  BinDest dst = {(u64*)bins, nullptr, bin_cap};
+  return bin_stream_impl(s, k, by_owner, n_parts, dst, cursors, overflow, stats, stream);
+}
+
+int kdf_bin_stream_to(const kdf_stream* s, int k, int by_owner, int n_parts,
+                      uint64_t* const* bin_ptrs, uint64_t bin_cap, uint64_t* cursors,
+                      uint64_t* overflow, uint64_t* stats, void* stream) {
+  if (!s || !bin_ptrs || !cursors || !overflow)
+    return fail(KDF_ERR_ARG, "kdf_bin_stream_to: NULL argument");
+  BinDest dst = {nullptr, (u64* const*)bin_ptrs, bin_cap};
+  return bin_stream_impl(s, k, by_owner, n_parts, dst, cursors, overflow, stats, stream);
+}
+
+static int bin_stream_impl(const kdf_stream* s, int k, int by_owner, int n_parts, BinDest dst,
+                           uint64_t* cursors, uint64_t* overflow, uint64_t* stats, void* stream) {
   int kw = kdf_key_words(k);
   if (!kw) return fail(KDF_ERR_ARG, "kdf_bin_stream: k must be in 1..64");
   if (n_parts < 1 || n_parts > BIN_MAX_PARTS) return fail(KDF_ERR_ARG, "kdf_bin_stream: n_parts must be 1..256");
@@ -1555,8 +1584,8 @@ int kdf_bin_stream(const kdf_stream* s, int k, int by_owner, int n_parts, uint64
     const void* fn = (const void*)k_bin_stream<KW, OWN>;                                          \
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
     int g = grid_for(fn, BIN_THREADS, smem, v.n_words, sm);                                       \
-    k_bin_stream<KW, OWN><<<g, BIN_THREADS, smem, st>>>(v, k, log2p, (u32)n_parts, qcap, (u64*)bins, \
-                                                        bin_cap, (u64*)cursors, (u64*)overflow,   \
+    k_bin_stream<KW, OWN><<<g, BIN_THREADS, smem, st>>>(v, k, log2p, (u32)n_parts, qcap, dst,     \
+                                                        (u64*)cursors, (u64*)overflow,            \
                                                         (u64*)stats);                             \
   }
   if (kw == 1) {
@@ -1578,6 +1607,7 @@ int kdf_bin_keys(const uint64_t* lo, const uint64_t* hi, uint64_t n, int k, int 
   if (n == 0) return KDF_OK;
   if (!lo) return fail(KDF_ERR_ARG, "kdf_bin_keys: NULL key array");
   if (n_parts < 1 || n_parts > BIN_MAX_PARTS) return fail(KDF_ERR_ARG, "kdf_bin_keys: n_parts must be 1..256");
+  BinDest dst = {(u64*)bins, nullptr, bin_cap};
   int log2p = 0;
   if (!by_owner) {
     while ((1 << log2p) < n_parts) ++log2p;
@@ -1593,7 +1623,7 @@ int kdf_bin_keys(const uint64_t* lo, const uint64_t* hi, uint64_t n, int k, int 
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
     int g = grid_for(fn, BIN_THREADS, smem, (n + BIN_WPR - 1) / BIN_WPR, sm);                     \
     k_bin_keys<KW, OWN><<<g, BIN_THREADS, smem, st>>>((const u64*)lo, (const u64*)hi, n, log2p,   \
-                                                      (u32)n_parts, qcap, (u64*)bins, bin_cap,    \
+                                                      (u32)n_parts, qcap, dst,                    \
                                                       (u64*)cursors, (u64*)overflow);             \
   }
   if (kw == 1) {

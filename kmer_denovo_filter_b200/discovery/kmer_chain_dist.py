@@ -98,6 +98,76 @@ def route_to_owners(eng, streams, k, world):
     return recv, recv_counts.cpu().numpy().astype(np.int64), bins.bin_cap, eng.read_stats(st)["windows"]
 
 
+# symmetric receive buffers are expensive to set up (handle exchange between the
+# ranks): cached per (role, bytes) for the life of the process
+_symm_cache = {}
+
+
+def peer_memory_available(eng):
+    """True when the ranks can map each other's memory (NCCL backend on CUDA with
+    torch symmetric memory); the gloo / CPU tests take the all-to-all route."""
+    if getattr(eng, "peer_bins", True) is False:
+        return False
+    dist = _dist()
+    try:
+        if dist.get_backend() != "nccl" or eng.device.type != "cuda":
+            return False
+        import torch.distributed._symmetric_memory as symm_mem  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+def _symm_buffer(eng, role, n_words):
+    import torch.distributed._symmetric_memory as symm_mem
+    dist = _dist()
+    key = (role, int(n_words))
+    hit = _symm_cache.get(key)
+    if hit is None:
+        # drop smaller buffers of the same role (a retry with larger segments)
+        for old in [k2 for k2 in _symm_cache if k2[0] == role]:
+            del _symm_cache[old]
+        t = symm_mem.empty(int(n_words), dtype=eng.torch.int64, device=eng.device)
+        hdl = symm_mem.rendezvous(t, dist.group.WORLD)
+        hit = _symm_cache[key] = (t, hdl)
+    return hit
+
+
+def route_to_owners_p2p(eng, streams, k, world, role):
+    """K6 fused with the exchange: each rank's binning kernel writes the k-mers of
+    owner r straight into rank r's receive buffer through NVLink peer pointers
+    (``kdf_bin_stream_to``); no send buffer and no NCCL data movement.  Same return
+    value as :func:`route_to_owners`."""
+    torch = eng.torch
+    dist = _dist()
+    rank = dist.get_rank()
+    kw = eng.lib.kdf_key_words(k)
+    n_max = sum(s.n_bases for s in streams)
+    cap = torch.tensor([_kc._bin_capacity(max(n_max, 1), world)], dtype=torch.int64, device=eng.device)
+    allreduce(cap, "max")
+    seg_cap = (int(cap.item()) + 3) & ~3
+    while True:
+        recv, hdl = _symm_buffer(eng, role, world * seg_cap * kw)
+        # segment [rank] of every peer's buffer is this rank's to fill
+        ptrs = torch.tensor([int(hdl.buffer_ptrs[o]) + rank * seg_cap * kw * 8 for o in range(world)],
+                            dtype=torch.int64, device=eng.device)
+        cursors = torch.zeros(world, dtype=torch.int64, device=eng.device)
+        overflow = torch.zeros(1, dtype=torch.int64, device=eng.device)
+        st = eng.new_stats()
+        hdl.barrier(channel=0)          # every peer is done reading its buffer from the last use
+        for s in streams:
+            eng.bin_stream_to(s, k, ptrs, seg_cap, cursors, overflow, by_owner=True, stats=st)
+        hdl.barrier(channel=1)          # every peer's writes into this rank's buffer have landed
+        need = torch.stack([cursors.max(), overflow[0]]).to(torch.int64)
+        allreduce(need, "max")
+        if int(need[1].item()) == 0:
+            break
+        seg_cap = (int(need[0].item()) + 4 + 3) & ~3
+    send_counts = torch.minimum(cursors, torch.full_like(cursors, seg_cap))
+    recv_counts = exchange_equal(send_counts, world)      # 8 bytes per peer
+    return recv, recv_counts.cpu().numpy().astype(np.int64), seg_cap, eng.read_stats(st)["windows"]
+
+
 def _segments(recv, counts, bin_cap, kw):
     for r, n in enumerate(counts.tolist()):
         if n:
@@ -109,8 +179,12 @@ def count_child_dist(eng, child_streams, ref_streams, k, min_child_count, world)
     Returns dict(child_windows, ref_windows, child_distinct, candidates, non_ref — all
     LOCAL to this rank — and lo, hi: this owner's non-reference candidates)."""
     kw = eng.lib.kdf_key_words(k)
-    c_recv, c_counts, c_cap, c_win = route_to_owners(eng, child_streams, k, world)
-    r_recv, r_counts, r_cap, r_win = route_to_owners(eng, ref_streams, k, world)
+    if peer_memory_available(eng):
+        c_recv, c_counts, c_cap, c_win = route_to_owners_p2p(eng, child_streams, k, world, "child")
+        r_recv, r_counts, r_cap, r_win = route_to_owners_p2p(eng, ref_streams, k, world, "ref")
+    else:
+        c_recv, c_counts, c_cap, c_win = route_to_owners(eng, child_streams, k, world)
+        r_recv, r_counts, r_cap, r_win = route_to_owners(eng, ref_streams, k, world)
     n_child = int(c_counts.sum())
     n_ref = int(r_counts.sum())
     n_parts, slice_capacity = _kc.plan_partitions(max(n_child, 1), key_words=kw)

@@ -72,6 +72,7 @@ _SIGNATURES = {
     "kdf_reduce_hits": (_i, [_vp, _vp, _u64, _vp, _u64, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp, _vp,
                              _vp, _vp, _vp]),
     "kdf_bin_stream": (_i, [ctypes.POINTER(_Stream), _i, _i, _i, _vp, _u64, _vp, _vp, _vp, _vp]),
+    "kdf_bin_stream_to": (_i, [ctypes.POINTER(_Stream), _i, _i, _i, _vp, _u64, _vp, _vp, _vp, _vp]),
     "kdf_bin_keys": (_i, [_vp, _vp, _u64, _i, _i, _i, _vp, _u64, _vp, _vp, _vp]),
     "kdf_count_bins": (_i, [_i, _i, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _u64, _u32, _u32, _u32, _u32,
                             _vp, _vp, _vp, _vp, _u64, _vp, _u32, _vp, _vp]),
@@ -647,6 +648,17 @@ class CudaEngine:
             bins.bin_cap, bins.cursors.data_ptr(), bins.overflow.data_ptr(),
             stats.data_ptr() if stats is not None else None, self.stream_ptr()))
         self._t1("bin_stream/kw%d" % bins.key_words, ev)
+        self.launches += 1
+
+    def bin_stream_to(self, ds, k, bin_ptrs, bin_cap, cursors, overflow, by_owner=True, stats=None):
+        """K6 fused with the transfer: bin p goes to ``bin_ptrs[p]`` (device int64
+        tensor of raw pointers, possibly peer memory over NVLink)."""
+        ev = self._t0()
+        self._check(self.lib.kdf_bin_stream_to(
+            ds.c(), int(k), 1 if by_owner else 0, int(bin_ptrs.shape[0]), bin_ptrs.data_ptr(),
+            int(bin_cap), cursors.data_ptr(), overflow.data_ptr(),
+            stats.data_ptr() if stats is not None else None, self.stream_ptr()))
+        self._t1("bin_stream_to_peers/kw%d" % self.lib.kdf_key_words(int(k)), ev)
         self.launches += 1
 
     def bin_keys(self, bins, lo, hi=None, n=None):

@@ -36,7 +36,7 @@ def _union(torch, a, b):
             "read_lens": torch.cat([a["read_lens"], b["read_lens"]])}
 
 
-def _worker(rank, world, port, k, q):
+def _worker(rank, world, port, k, q, peer=True):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -47,6 +47,8 @@ def _worker(rank, world, port, k, q):
         from kmer_denovo_filter_b200 import engine, synth
         from kmer_denovo_filter_b200.discovery import kmer_chain, kmer_chain_dist
         eng = engine.CudaEngine(dev)
+        eng.peer_bins = peer     # True: NVLink peer-memory route; False: NCCL all-to-all route
+        assert kmer_chain_dist.peer_memory_available(eng) == peer
         trio = synth.make_trio(torch, dev, GENOME, depth=DEPTH, n_denovo=20, rank=rank, world=world)
         res = kmer_chain_dist.discover_streams_dist(
             eng, _dev(engine, trio["child"]), _dev(engine, trio["mother"]),
@@ -74,15 +76,16 @@ def _worker(rank, world, port, k, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("peer", [True, False])
 @pytest.mark.parametrize("k", [31, 47])
-def test_dist_chain_equals_single_gpu(k):
+def test_dist_chain_equals_single_gpu(k, peer):
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, k, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, k, q, peer)) for r in range(world)]
     for p in procs:
         p.start()
     got = [q.get(timeout=600) for _ in procs]
