@@ -230,12 +230,15 @@ int kdf_reduce_hits(const uint64_t* hit_pos /*DEV*/, const uint32_t* hit_slot /*
  * streams can be appended.  A key that does not fit sets *overflow != 0 and is
  * dropped: the caller must check it and retry with larger bins.
  *   by_owner == 0 : bin = hash range (top log2(n_parts) bits of the bucket
- *                   hash; n_parts a power of two <= 256) — input of
+ *                   hash; n_parts a power of two <= 512) — input of
  *                   kdf_count_bins; replaces nothing in the reference, it is
  *                   how `jellyfish count` (discovery/pipeline.py:114-122) is
  *                   kept out of DRAM-random-access territory on the GPU;
- *   by_owner == 1 : bin = owner rank of a multi-GPU run (any n_parts <= 256),
- *                   in front of the all-to-all.                              */
+ *   by_owner == 1 : bin = owner rank of a multi-GPU run (any n_parts <= 512),
+ *                   in front of the all-to-all;
+ *   by_owner == R >= 2 : composite, bin = owner * (n_parts / R) + hash range, for R
+ *                   owner ranks (n_parts / R a power of two): what a rank receives is
+ *                   already binned for kdf_count_bins_multi.                  */
 int kdf_bin_stream(const kdf_stream* s, int k, int by_owner, int n_parts,
                    uint64_t* bins /*DEV*/, uint64_t bin_cap, uint64_t* cursors /*DEV*/,
                    uint64_t* overflow /*DEV*/, uint64_t* stats /*DEV or NULL*/, void* stream);
@@ -276,6 +279,19 @@ int kdf_count_bins(int k, int n_parts, const uint64_t* child_bins /*DEV*/,
                    uint32_t* out_p0 /*DEV*/, uint32_t* out_p1 /*DEV*/, uint64_t out_cap,
                    uint64_t* n_out /*DEV*/, uint32_t count_min0, uint64_t* counters /*DEV*/,
                    void* stream);
+
+/* The same with the bins of n_src sources (multi-GPU: one region per sending
+ * rank, filled by kdf_bin_stream_to): bins are laid out [source][hash range]
+ * [bin_cap] and cursors [source][hash range].                                 */
+int kdf_count_bins_multi(int k, int n_parts, int n_src, const uint64_t* child_bins /*DEV*/,
+                         uint64_t child_bin_cap, const uint64_t* child_cursors /*DEV*/,
+                         const uint64_t* ref_bins /*DEV or NULL*/, uint64_t ref_bin_cap,
+                         const uint64_t* ref_cursors /*DEV or NULL*/, void* slice /*DEV*/,
+                         uint64_t slice_capacity, uint32_t min0, uint32_t max0, uint32_t min1,
+                         uint32_t max1, uint64_t* out_lo /*DEV*/, uint64_t* out_hi /*DEV*/,
+                         uint32_t* out_p0 /*DEV*/, uint32_t* out_p1 /*DEV*/, uint64_t out_cap,
+                         uint64_t* n_out /*DEV*/, uint32_t count_min0, uint64_t* counters /*DEV*/,
+                         void* stream);
 
 /* ---- host helpers (CPU, no device) --------------------------------------
  * Pack ASCII sequences into the stream layout.  seqs: concatenated bytes,

@@ -902,7 +902,7 @@ __global__ void __launch_bounds__(128) k_reduce_hits(const u64* pos, const u32* 
 // that global writes are contiguous runs.  A bin that overflows sets
 // *overflow and drops the key: the caller must size bins or retry.
 constexpr int BIN_THREADS = 256;
-constexpr int BIN_MAX_PARTS = 256;
+constexpr int BIN_MAX_PARTS = 512;
 
 template <int KW>
 __device__ __forceinline__ void st_key(u64* bins, u64 idx, const Key<KW>& key);
@@ -1013,18 +1013,22 @@ struct BinStage {
   }
 };
 
-template <int KW, bool BY_OWNER>
-__device__ __forceinline__ u32 bin_of(const Key<KW>& key, int log2_parts, u32 n_parts) {
+// BMODE 0: hash range (part_of); 1: owner rank; 2: composite owner x hash range —
+// bin = owner * n_local + part, n_parts = n_owners * n_local, log2_parts = log2(n_local)
+template <int KW, int BMODE>
+__device__ __forceinline__ u32 bin_of(const Key<KW>& key, int log2_parts, u32 n_parts, u32 n_owners) {
   u64 h = hash_key(key);
-  return BY_OWNER ? owner_of(h, n_parts) : part_of(h, log2_parts);
+  if (BMODE == 0) return part_of(h, log2_parts);
+  if (BMODE == 1) return owner_of(h, n_parts);
+  return owner_of(h, n_owners) * (n_parts / n_owners) + part_of(h, log2_parts);
 }
 
 // windows handled per thread between two flushes
 constexpr int BIN_WPR = 16;
 
-template <int KW, bool BY_OWNER>
+template <int KW, int BMODE>
 __global__ void __launch_bounds__(BIN_THREADS) k_bin_stream(StreamView s, int k, int log2_parts,
-                                                            u32 n_parts, int qcap, BinDest dst,
+                                                            u32 n_parts, u32 n_owners, int qcap, BinDest dst,
                                                             u64* cursors, u64* overflow,
                                                             u64* stats) {
   extern __shared__ __align__(16) unsigned char bin_smem[];
@@ -1046,7 +1050,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_stream(StreamView s, int k,
         Key<KW> key = it.canonical();
         it.advance();
         windows += ok ? 1u : 0u;
-        stage.push(ok, bin_of<KW, BY_OWNER>(key, log2_parts, n_parts), key, dst, cursors, overflow);
+        stage.push(ok, bin_of<KW, BMODE>(key, log2_parts, n_parts, n_owners), key, dst, cursors, overflow);
       }
       stage.flush(dst, cursors, overflow);
     }
@@ -1057,7 +1061,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_stream(StreamView s, int k,
   }
 }
 
-template <int KW, bool BY_OWNER>
+template <int KW, int BMODE>
 __global__ void __launch_bounds__(BIN_THREADS) k_bin_keys(const u64* lo, const u64* hi, u64 n,
                                                           int log2_parts, u32 n_parts, int qcap,
                                                           BinDest dst, u64* cursors,
@@ -1075,7 +1079,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_keys(const u64* lo, const u
       u64 i = base + (u64)j * blockDim.x;
       bool ok = i < n;
       Key<KW> key = ld_key_stream<KW>(lo, hi, ok ? i : 0);
-      stage.push(ok, bin_of<KW, BY_OWNER>(key, log2_parts, n_parts), key, dst, cursors, overflow);
+      stage.push(ok, bin_of<KW, BMODE>(key, log2_parts, n_parts, 1), key, dst, cursors, overflow);
     }
     stage.flush(dst, cursors, overflow);
   }
@@ -1537,6 +1541,7 @@ static int bin_qcap(int n_parts, int kw) {
   // ~64 KB of queues per CTA -> 3 CTAs per SM
   // a round offers 256 threads x 16 windows = 4096 keys, 4096 / n_parts per queue
   int q = (64 * 1024) / (n_parts * 8 * kw);
+  if (q < 16) q = (128 * 1024) / (n_parts * 8 * kw);  // many wide bins: fewer CTAs per SM, deeper queues
   int want = 2 * (BIN_THREADS * BIN_WPR / n_parts) + 32;
   if (q > want) q = want;
   if (q < 8) q = 8;
@@ -1567,31 +1572,37 @@ static int bin_stream_impl(const kdf_stream* s, int k, int by_owner, int n_parts
                            uint64_t* cursors, uint64_t* overflow, uint64_t* stats, void* stream) {
   int kw = kdf_key_words(k);
   if (!kw) return fail(KDF_ERR_ARG, "kdf_bin_stream: k must be in 1..64");
-  if (n_parts < 1 || n_parts > BIN_MAX_PARTS) return fail(KDF_ERR_ARG, "kdf_bin_stream: n_parts must be 1..256");
+  if (n_parts < 1 || n_parts > BIN_MAX_PARTS) return fail(KDF_ERR_ARG, "kdf_bin_stream: n_parts must be 1..512");
+  // by_owner: 0 = hash ranges, 1 = owner ranks, R >= 2 = composite (R owners x n_parts/R ranges)
   int log2p = 0;
-  if (!by_owner) {
-    while ((1 << log2p) < n_parts) ++log2p;
-    if ((1 << log2p) != n_parts) return fail(KDF_ERR_ARG, "kdf_bin_stream: hash-range bins need a power-of-two count");
+  int n_owners = 1;
+  int bmode = by_owner == 0 ? 0 : (by_owner == 1 ? 1 : 2);
+  if (bmode != 1) {
+    n_owners = bmode == 2 ? by_owner : 1;
+    if (n_parts % n_owners) return fail(KDF_ERR_ARG, "kdf_bin_stream: n_parts must be a multiple of the owner count");
+    int n_local = n_parts / n_owners;
+    while ((1 << log2p) < n_local) ++log2p;
+    if ((1 << log2p) != n_local) return fail(KDF_ERR_ARG, "kdf_bin_stream: hash-range bins need a power-of-two count");
   }
   StreamView v = view_of(s);
   if (v.n_words == 0) return KDF_OK;
   int sm = current_sm_count();
   cudaStream_t st = (cudaStream_t)stream;
   int qcap = bin_qcap(n_parts, kw);
-#define KDF_BIN(KW, OWN)                                                                          \
+#define KDF_BIN(KW, BM)                                                                           \
   {                                                                                               \
     size_t smem = BinStage<KW>::bytes(n_parts, qcap);                                             \
-    const void* fn = (const void*)k_bin_stream<KW, OWN>;                                          \
+    const void* fn = (const void*)k_bin_stream<KW, BM>;                                           \
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
     int g = grid_for(fn, BIN_THREADS, smem, v.n_words, sm);                                       \
-    k_bin_stream<KW, OWN><<<g, BIN_THREADS, smem, st>>>(v, k, log2p, (u32)n_parts, qcap, dst,     \
-                                                        (u64*)cursors, (u64*)overflow,            \
-                                                        (u64*)stats);                             \
+    k_bin_stream<KW, BM><<<g, BIN_THREADS, smem, st>>>(v, k, log2p, (u32)n_parts, (u32)n_owners,  \
+                                                       qcap, dst, (u64*)cursors, (u64*)overflow,  \
+                                                       (u64*)stats);                              \
   }
   if (kw == 1) {
-    if (by_owner) KDF_BIN(1, true) else KDF_BIN(1, false)
+    if (bmode == 0) KDF_BIN(1, 0) else if (bmode == 1) KDF_BIN(1, 1) else KDF_BIN(1, 2)
   } else {
-    if (by_owner) KDF_BIN(2, true) else KDF_BIN(2, false)
+    if (bmode == 0) KDF_BIN(2, 0) else if (bmode == 1) KDF_BIN(2, 1) else KDF_BIN(2, 2)
   }
 #undef KDF_BIN
   CUDA_TRY(cudaGetLastError());
@@ -1606,7 +1617,7 @@ int kdf_bin_keys(const uint64_t* lo, const uint64_t* hi, uint64_t n, int k, int 
   if (!kw) return fail(KDF_ERR_ARG, "kdf_bin_keys: k must be in 1..64");
   if (n == 0) return KDF_OK;
   if (!lo) return fail(KDF_ERR_ARG, "kdf_bin_keys: NULL key array");
-  if (n_parts < 1 || n_parts > BIN_MAX_PARTS) return fail(KDF_ERR_ARG, "kdf_bin_keys: n_parts must be 1..256");
+  if (n_parts < 1 || n_parts > BIN_MAX_PARTS) return fail(KDF_ERR_ARG, "kdf_bin_keys: n_parts must be 1..512");
   BinDest dst = {(u64*)bins, nullptr, bin_cap};
   int log2p = 0;
   if (!by_owner) {
@@ -1627,9 +1638,9 @@ int kdf_bin_keys(const uint64_t* lo, const uint64_t* hi, uint64_t n, int k, int 
                                                       (u64*)cursors, (u64*)overflow);             \
   }
   if (kw == 1) {
-    if (by_owner) KDF_BINK(1, true) else KDF_BINK(1, false)
+    if (by_owner) KDF_BINK(1, 1) else KDF_BINK(1, 0)
   } else {
-    if (by_owner) KDF_BINK(2, true) else KDF_BINK(2, false)
+    if (by_owner) KDF_BINK(2, 1) else KDF_BINK(2, 0)
   }
 #undef KDF_BINK
   CUDA_TRY(cudaGetLastError());
@@ -1642,14 +1653,28 @@ int kdf_count_bins(int k, int n_parts, const uint64_t* child_bins, uint64_t chil
                    uint32_t min0, uint32_t max0, uint32_t min1, uint32_t max1, uint64_t* out_lo,
                    uint64_t* out_hi, uint32_t* out_p0, uint32_t* out_p1, uint64_t out_cap,
                    uint64_t* n_out, uint32_t count_min0, uint64_t* counters, void* stream) {
+  return kdf_count_bins_multi(k, n_parts, 1, child_bins, child_bin_cap, child_cursors, ref_bins,
+                              ref_bin_cap, ref_cursors, slice, slice_capacity, min0, max0, min1, max1,
+                              out_lo, out_hi, out_p0, out_p1, out_cap, n_out, count_min0, counters,
+                              stream);
+}
+
+int kdf_count_bins_multi(int k, int n_parts, int n_src, const uint64_t* child_bins,
+                         uint64_t child_bin_cap, const uint64_t* child_cursors,
+                         const uint64_t* ref_bins, uint64_t ref_bin_cap, const uint64_t* ref_cursors,
+                         void* slice, uint64_t slice_capacity, uint32_t min0, uint32_t max0,
+                         uint32_t min1, uint32_t max1, uint64_t* out_lo, uint64_t* out_hi,
+                         uint32_t* out_p0, uint32_t* out_p1, uint64_t out_cap, uint64_t* n_out,
+                         uint32_t count_min0, uint64_t* counters, void* stream) {
   if (!child_bins || !child_cursors || !slice || !n_out || !counters)
     return fail(KDF_ERR_ARG, "kdf_count_bins: NULL argument");
+  if (n_src < 1) return fail(KDF_ERR_ARG, "kdf_count_bins: n_src must be >= 1");
   int rc = check_table_args(k, slice_capacity, slice, "kdf_count_bins");
   if (rc != KDF_OK) return rc;
   int log2p = 0;
   while ((1 << log2p) < n_parts) ++log2p;
   if (n_parts < 1 || n_parts > BIN_MAX_PARTS || (1 << log2p) != n_parts)
-    return fail(KDF_ERR_ARG, "kdf_count_bins: n_parts must be a power of two <= 256");
+    return fail(KDF_ERR_ARG, "kdf_count_bins: n_parts must be a power of two <= 512");
   kdf_table t;
   t.k = k;
   t.key_words = kdf_key_words(k);
@@ -1663,19 +1688,26 @@ int kdf_count_bins(int k, int n_parts, const uint64_t* child_bins, uint64_t chil
   rc = clear_table_async(&t, st);  // once: every emit pass leaves the slice clean
   if (rc != KDF_OK) return rc;
   for (int p = 0; p < n_parts; ++p) {
-    const u64* cb = (const u64*)child_bins + (u64)p * child_bin_cap * kw;
-    if (kw == 1)
-      rc = launch_update_keys<1, OP_INSERT_COUNT>(&t, cb, nullptr, child_bin_cap, (const u64*)child_cursors + p, 0, 1, ctr, st);
-    else
-      rc = launch_update_keys<2, OP_INSERT_COUNT>(&t, cb, nullptr, child_bin_cap, (const u64*)child_cursors + p, 0, 1, ctr, st);
-    if (rc != KDF_OK) return rc;
-    if (ref_bins && ref_cursors) {
-      const u64* rb = (const u64*)ref_bins + (u64)p * ref_bin_cap * kw;
+    // bins are laid out [source][hash range][bin_cap]: one insert pass per source
+    for (int sidx = 0; sidx < n_src; ++sidx) {
+      u64 b = (u64)sidx * n_parts + p;
+      const u64* cb = (const u64*)child_bins + b * child_bin_cap * kw;
       if (kw == 1)
-        rc = launch_update_keys<1, OP_MARK_IF_PRESENT>(&t, rb, nullptr, ref_bin_cap, (const u64*)ref_cursors + p, 1, 1, nullptr, st);
+        rc = launch_update_keys<1, OP_INSERT_COUNT>(&t, cb, nullptr, child_bin_cap, (const u64*)child_cursors + b, 0, 1, ctr, st);
       else
-        rc = launch_update_keys<2, OP_MARK_IF_PRESENT>(&t, rb, nullptr, ref_bin_cap, (const u64*)ref_cursors + p, 1, 1, nullptr, st);
+        rc = launch_update_keys<2, OP_INSERT_COUNT>(&t, cb, nullptr, child_bin_cap, (const u64*)child_cursors + b, 0, 1, ctr, st);
       if (rc != KDF_OK) return rc;
+    }
+    if (ref_bins && ref_cursors) {
+      for (int sidx = 0; sidx < n_src; ++sidx) {
+        u64 b = (u64)sidx * n_parts + p;
+        const u64* rb = (const u64*)ref_bins + b * ref_bin_cap * kw;
+        if (kw == 1)
+          rc = launch_update_keys<1, OP_MARK_IF_PRESENT>(&t, rb, nullptr, ref_bin_cap, (const u64*)ref_cursors + b, 1, 1, nullptr, st);
+        else
+          rc = launch_update_keys<2, OP_MARK_IF_PRESENT>(&t, rb, nullptr, ref_bin_cap, (const u64*)ref_cursors + b, 1, 1, nullptr, st);
+        if (rc != KDF_OK) return rc;
+      }
     }
     if (kw == 1)
       rc = launch_emit_buckets<1>(&t, min0, max0, min1, max1, (u64*)out_lo, (u64*)out_hi, out_p0, out_p1,

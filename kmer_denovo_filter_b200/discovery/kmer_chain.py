@@ -19,6 +19,7 @@ from .. import engine as _engine
 from ..kmer_utils import KmerSet
 
 REF_PLANE = 1
+L2_TABLE_BYTES = 100 << 20      # keys of a read-only table that can stay L2-resident next to the stream
 SMEM_TABLE_BYTES = 160 * 1024   # keys of a read-only table that the stream kernels copy to shared memory
 
 
@@ -155,8 +156,8 @@ def _primed_table(eng, k, lo, hi, n):
     n_keys = max(n, 1)
     if n_keys * 4 * 8 * eng.lib.kdf_key_words(k) <= SMEM_TABLE_BYTES:
         n_keys *= 2
-    else:
-        n_keys = n_keys * 3 // 2
+    elif n_keys * 3 * 8 * eng.lib.kdf_key_words(k) <= L2_TABLE_BYTES:
+        n_keys = n_keys * 3 // 2     # still L2-resident at load 0.33
     t = eng.new_table(k, n_keys=n_keys)
     eng.update_keys(t, lo, hi, _engine.MODE_INSERT_ONLY, 0, 0)
     return t

@@ -133,39 +133,51 @@ def _symm_buffer(eng, role, n_words):
     return hit
 
 
-def route_to_owners_p2p(eng, streams, k, world, role):
-    """K6 fused with the exchange: each rank's binning kernel writes the k-mers of
-    owner r straight into rank r's receive buffer through NVLink peer pointers
-    (``kdf_bin_stream_to``); no send buffer and no NCCL data movement.  Same return
-    value as :func:`route_to_owners`."""
+class RecvBins:
+    """What a rank received through the fused route, seen as the input of
+    ``kdf_count_bins_multi``: ``n_src`` x ``n_parts`` bins of ``bin_cap`` keys in the
+    (symmetric) receive buffer, with the senders' counts as cursors."""
+
+    def __init__(self, k, key_words, n_parts, n_src, bin_cap, data, cursors):
+        self.k, self.key_words = k, key_words
+        self.n_parts, self.n_src, self.bin_cap = n_parts, n_src, bin_cap
+        self.data, self.cursors = data, cursors
+
+
+def route_composite_p2p(eng, streams, k, world, role, n_local, n_expected):
+    """K6 fused with the exchange AND with the owner's hash-range binning: one kernel
+    per rank extracts its k-mers, picks (owner, hash range) and writes each key into
+    bin [this rank][range] of the owner's receive buffer through NVLink peer pointers
+    (``kdf_bin_stream_to``).  No send buffer, no NCCL data movement, no second
+    binning pass on the receiver.  → (RecvBins, windows of this rank's streams)."""
     torch = eng.torch
     dist = _dist()
     rank = dist.get_rank()
     kw = eng.lib.kdf_key_words(k)
-    n_max = sum(s.n_bases for s in streams)
-    cap = torch.tensor([_kc._bin_capacity(max(n_max, 1), world)], dtype=torch.int64, device=eng.device)
-    allreduce(cap, "max")
-    seg_cap = (int(cap.item()) + 3) & ~3
+    n_bins = world * n_local
+    seg_cap = (_kc._bin_capacity(max(n_expected, 1), n_bins) + 3) & ~3
     while True:
-        recv, hdl = _symm_buffer(eng, role, world * seg_cap * kw)
-        # segment [rank] of every peer's buffer is this rank's to fill
-        ptrs = torch.tensor([int(hdl.buffer_ptrs[o]) + rank * seg_cap * kw * 8 for o in range(world)],
+        recv, hdl = _symm_buffer(eng, role, n_bins * seg_cap * kw)
+        base = [int(hdl.buffer_ptrs[o]) for o in range(world)]
+        ptrs = torch.tensor([base[o] + (rank * n_local + p) * seg_cap * kw * 8
+                             for o in range(world) for p in range(n_local)],
                             dtype=torch.int64, device=eng.device)
-        cursors = torch.zeros(world, dtype=torch.int64, device=eng.device)
+        cursors = torch.zeros(n_bins, dtype=torch.int64, device=eng.device)
         overflow = torch.zeros(1, dtype=torch.int64, device=eng.device)
         st = eng.new_stats()
         hdl.barrier(channel=0)          # every peer is done reading its buffer from the last use
         for s in streams:
-            eng.bin_stream_to(s, k, ptrs, seg_cap, cursors, overflow, by_owner=True, stats=st)
+            eng.bin_stream_to(s, k, ptrs, seg_cap, cursors, overflow, by_owner=world, stats=st)
         hdl.barrier(channel=1)          # every peer's writes into this rank's buffer have landed
         need = torch.stack([cursors.max(), overflow[0]]).to(torch.int64)
         allreduce(need, "max")
         if int(need[1].item()) == 0:
             break
-        seg_cap = (int(need[0].item()) + 4 + 3) & ~3
+        seg_cap = (int(need[0].item()) + 4 + 3) & ~3      # exact size, agreed by all ranks
     send_counts = torch.minimum(cursors, torch.full_like(cursors, seg_cap))
-    recv_counts = exchange_equal(send_counts, world)      # 8 bytes per peer
-    return recv, recv_counts.cpu().numpy().astype(np.int64), seg_cap, eng.read_stats(st)["windows"]
+    recv_counts = exchange_equal(send_counts, world)      # [source][range], 8 bytes each
+    return (RecvBins(k, kw, n_local, world, seg_cap, recv, recv_counts),
+            eng.read_stats(st)["windows"])
 
 
 def _segments(recv, counts, bin_cap, kw):
@@ -180,11 +192,9 @@ def count_child_dist(eng, child_streams, ref_streams, k, min_child_count, world)
     LOCAL to this rank — and lo, hi: this owner's non-reference candidates)."""
     kw = eng.lib.kdf_key_words(k)
     if peer_memory_available(eng):
-        c_recv, c_counts, c_cap, c_win = route_to_owners_p2p(eng, child_streams, k, world, "child")
-        r_recv, r_counts, r_cap, r_win = route_to_owners_p2p(eng, ref_streams, k, world, "ref")
-    else:
-        c_recv, c_counts, c_cap, c_win = route_to_owners(eng, child_streams, k, world)
-        r_recv, r_counts, r_cap, r_win = route_to_owners(eng, ref_streams, k, world)
+        return _count_child_fused(eng, child_streams, ref_streams, k, min_child_count, world, kw)
+    c_recv, c_counts, c_cap, c_win = route_to_owners(eng, child_streams, k, world)
+    r_recv, r_counts, r_cap, r_win = route_to_owners(eng, ref_streams, k, world)
     n_child = int(c_counts.sum())
     n_ref = int(r_counts.sum())
     n_parts, slice_capacity = _kc.plan_partitions(max(n_child, 1), key_words=kw)
@@ -214,6 +224,36 @@ def count_child_dist(eng, child_streams, ref_streams, k, min_child_count, world)
             if slice_capacity >= 2 * bin_cap:
                 raise _engine.KdfError("child k-mer table slice full at %d slots" % slice_capacity)
             slice_capacity = min(slice_capacity * 4, 2 * bin_cap + 4)
+            continue
+        if res["n_out"] > out_cap:
+            out_cap = res["n_out"]
+            continue
+        break
+    return {"child_windows": c_win, "ref_windows": r_win, "child_distinct": res["distinct"],
+            "candidates": res["n_count"], "non_ref": res["n_out"], "lo": res["lo"], "hi": res["hi"]}
+
+
+def _count_child_fused(eng, child_streams, ref_streams, k, min_child_count, world, kw):
+    """count_child_dist over NVLink peer memory (see route_composite_p2p)."""
+    torch = eng.torch
+    n_exp = torch.tensor([sum(s.n_bases for s in child_streams), sum(s.n_bases for s in ref_streams)],
+                         dtype=torch.int64, device=eng.device)
+    allreduce(n_exp, "max")              # weak scaling: a rank receives about what it sends
+    n_child_exp, n_ref_exp = int(n_exp[0].item()), int(n_exp[1].item())
+    n_local, slice_capacity = _kc.plan_partitions(max(n_child_exp, 1), key_words=kw)
+    n_local = max(1, min(n_local, 512 // _kc._pow2_at_least(world)))
+    slice_capacity = max(slice_capacity, ((max(n_child_exp, 1) // 8 + n_local - 1) // n_local + 3) & ~3)
+    cb, c_win = route_composite_p2p(eng, child_streams, k, world, "child", n_local, n_child_exp)
+    rb, r_win = route_composite_p2p(eng, ref_streams, k, world, "ref", n_local, n_ref_exp)
+    n_child = int(cb.cursors.sum().item())
+    out_cap = max(1 << 16, n_child // 64)
+    while True:
+        res = eng.count_bins(cb, rb, slice_capacity, min0=min_child_count, max1=0,
+                             count_min0=min_child_count, out_cap=out_cap)
+        if res["full"]:
+            if slice_capacity >= 2 * cb.bin_cap * world:
+                raise _engine.KdfError("child k-mer table slice full at %d slots" % slice_capacity)
+            slice_capacity = min(slice_capacity * 4, 2 * cb.bin_cap * world + 4)
             continue
         if res["n_out"] > out_cap:
             out_cap = res["n_out"]

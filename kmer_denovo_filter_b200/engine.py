@@ -76,6 +76,8 @@ _SIGNATURES = {
     "kdf_bin_keys": (_i, [_vp, _vp, _u64, _i, _i, _i, _vp, _u64, _vp, _vp, _vp]),
     "kdf_count_bins": (_i, [_i, _i, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _u64, _u32, _u32, _u32, _u32,
                             _vp, _vp, _vp, _vp, _u64, _vp, _u32, _vp, _vp]),
+    "kdf_count_bins_multi": (_i, [_i, _i, _i, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _u64, _u32, _u32, _u32,
+                                  _u32, _vp, _vp, _vp, _vp, _u64, _vp, _u32, _vp, _vp]),
     "kdf_debug_hash_host": (_i, [_vp, _vp, _u64, _i, _i, _u32, _u32, _vp, _vp, _vp]),
     "kdf_pack_sequences": (_u64, [_vp, _vp, _u64, _vp, _vp, _vp]),
     "kdf_debug_extract_host": (_i, [_vp, _vp, _u64, _i, _i, _vp, _vp, _vp]),
@@ -650,12 +652,13 @@ class CudaEngine:
         self._t1("bin_stream/kw%d" % bins.key_words, ev)
         self.launches += 1
 
-    def bin_stream_to(self, ds, k, bin_ptrs, bin_cap, cursors, overflow, by_owner=True, stats=None):
+    def bin_stream_to(self, ds, k, bin_ptrs, bin_cap, cursors, overflow, by_owner=1, stats=None):
         """K6 fused with the transfer: bin p goes to ``bin_ptrs[p]`` (device int64
-        tensor of raw pointers, possibly peer memory over NVLink)."""
+        tensor of raw pointers, possibly peer memory over NVLink).  ``by_owner``: 1 =
+        one bin per owner rank, R >= 2 = composite R owners x hash ranges."""
         ev = self._t0()
         self._check(self.lib.kdf_bin_stream_to(
-            ds.c(), int(k), 1 if by_owner else 0, int(bin_ptrs.shape[0]), bin_ptrs.data_ptr(),
+            ds.c(), int(k), int(by_owner), int(bin_ptrs.shape[0]), bin_ptrs.data_ptr(),
             int(bin_cap), cursors.data_ptr(), overflow.data_ptr(),
             stats.data_ptr() if stats is not None else None, self.stream_ptr()))
         self._t1("bin_stream_to_peers/kw%d" % self.lib.kdf_key_words(int(k)), ev)
@@ -690,8 +693,11 @@ class CudaEngine:
         n_out = self.zeros(1, torch.int64)
         ctr = self.zeros(6, torch.int64)
         ev = self._t0()
-        self._check(self.lib.kdf_count_bins(
-            k, child_bins.n_parts, child_bins.data.data_ptr(), child_bins.bin_cap,
+        n_src = getattr(child_bins, "n_src", 1)
+        if ref_bins is not None and getattr(ref_bins, "n_src", 1) != n_src:
+            raise KdfError("count_bins: child and reference bins must have the same sources")
+        self._check(self.lib.kdf_count_bins_multi(
+            k, child_bins.n_parts, n_src, child_bins.data.data_ptr(), child_bins.bin_cap,
             child_bins.cursors.data_ptr(),
             ref_bins.data.data_ptr() if ref_bins is not None else None,
             ref_bins.bin_cap if ref_bins is not None else 0,
@@ -701,7 +707,7 @@ class CudaEngine:
             p0.data_ptr() if p0 is not None else None, p1.data_ptr() if p1 is not None else None,
             out_cap, n_out.data_ptr(), count_min0, ctr.data_ptr(), self.stream_ptr()))
         self._t1("count_bins/kw%d" % kw, ev)
-        self.launches += 2 + child_bins.n_parts * (2 + (1 if ref_bins is not None else 0))
+        self.launches += 2 + child_bins.n_parts * (1 + n_src * (1 + (1 if ref_bins is not None else 0)))
         c = ctr.cpu().numpy().view(np.uint64)
         n = int(n_out.item())
         m = min(n, out_cap)
