@@ -105,3 +105,67 @@ def test_chain_properties_at_scale(eng):
         assert eng.read_stats(st)["hits"] == 0
         tp.close()
     assert res["informative_reads"] >= 20
+
+
+def _pack_dev(eng, seqs):
+    from kmer_denovo_filter_b200 import engine
+    return eng.upload(engine.pack_sequences(seqs))
+
+
+def test_partitioned_count_survives_skew_and_small_slices(eng):
+    """One k-mer repeated 200 000 times lands in one hash range: the bins overflow
+    and are re-made with exact sizes; a slice far too small is grown.  Counts stay
+    exact (the reference's analogue is Jellyfish spilling to .jf_N files)."""
+    import random
+    from kmer_denovo_filter_b200.discovery import kmer_chain
+    from oracle import kmers
+    rng = random.Random(5)
+    k = 31
+    g = "".join(rng.choice("ACGT") for _ in range(3000))
+    poly = "A" * 100
+    reads = [poly] * 3000 + [g[i:i + 100] for i in range(0, 2900, 7)] * 3
+    want = kmers.count_sequences(reads, k)
+    ref = kmers.count_sequences([g[:1500]], k)
+    res = kmer_chain.count_child_partitioned(eng, [_pack_dev(eng, reads)], [_pack_dev(eng, [g[:1500]])],
+                                             k, 3, n_parts=16, slice_capacity=64)
+    assert res["child_windows"] == sum(want.values())
+    assert res["child_distinct"] == len(want)
+    assert res["candidates"] == sum(1 for c in want.values() if c >= 3)
+    got = set(eng.keys_to_pyints(res["lo"], res["hi"]))
+    assert got == {x for x, c in want.items() if c >= 3 and x not in ref}
+    assert 0 in want and want[0] == 3000 * 70          # poly-A canonical key
+
+
+@pytest.mark.parametrize("reads", [[], [""], ["ACGT"], ["N" * 200], ["ACGTN" * 40]])
+def test_chain_on_degenerate_children(eng, reads):
+    """Empty input, reads shorter than k, all-N reads: no k-mers, no crash."""
+    import random
+    from kmer_denovo_filter_b200.discovery import kmer_chain
+    rng = random.Random(1)
+    g = "".join(rng.choice("ACGT") for _ in range(500))
+    parents = [g[i:i + 100] for i in range(0, 400, 10)]
+    res = kmer_chain.discover_streams(eng, _pack_dev(eng, reads), _pack_dev(eng, parents),
+                                      _pack_dev(eng, parents), _pack_dev(eng, [g]), 31)
+    assert res["child_windows"] == 0 and res["candidates"] == 0 and res["proband_unique"] == 0
+    assert res["pu"] is None and res["informative_reads"] == 0
+    assert res["units"] == 2 * (100 - 30) * 0 + (500 - 30)     # only the reference was streamed
+
+
+def test_child_only_kmers_are_all_proband_unique(eng):
+    """Parents that share nothing with the child: every child k-mer with count >= 3
+    that is not in the reference survives both filters; ragged read lengths."""
+    import random
+    from kmer_denovo_filter_b200.discovery import kmer_chain
+    from oracle import kmers
+    rng = random.Random(9)
+    k = 21
+    gc = "".join(rng.choice("ACGT") for _ in range(2000))
+    gp = "".join(rng.choice("ACGT") for _ in range(2000))
+    child = [gc[s:s + rng.randint(15, 140)] for s in [rng.randrange(0, 1850) for _ in range(900)]]
+    parents = [gp[i:i + 90] for i in range(0, 1900, 5)]
+    want = {x for x, c in kmers.count_sequences(child, k).items() if c >= 3}
+    want -= set(kmers.count_sequences(parents, k)) | set(kmers.count_sequences([gp], k))
+    res = kmer_chain.discover_streams(eng, _pack_dev(eng, child), _pack_dev(eng, parents),
+                                      _pack_dev(eng, parents), _pack_dev(eng, [gp]), k)
+    assert set(res["pu"].to_pyints()) == want and len(want) > 500
+    assert res["after_mother"] == res["proband_unique"] == len(want)
