@@ -242,6 +242,13 @@ int kdf_reduce_hits(const uint64_t* hit_pos /*DEV*/, const uint32_t* hit_slot /*
 int kdf_bin_stream(const kdf_stream* s, int k, int by_owner, int n_parts,
                    uint64_t* bins /*DEV*/, uint64_t bin_cap, uint64_t* cursors /*DEV*/,
                    uint64_t* overflow /*DEV*/, uint64_t* stats /*DEV or NULL*/, void* stream);
+/* The same for the window starts of words [first_word, first_word + n_words) only
+ * (bases of later words are still read for the windows that span them), so that a
+ * stream can be binned chunk by chunk while its tail is still being copied in.  */
+int kdf_bin_stream_range(const kdf_stream* s, uint64_t first_word, uint64_t n_words, int k,
+                         int by_owner, int n_parts, uint64_t* bins /*DEV*/, uint64_t bin_cap,
+                         uint64_t* cursors /*DEV*/, uint64_t* overflow /*DEV*/,
+                         uint64_t* stats /*DEV or NULL*/, void* stream);
 /* The same kernel with one base pointer per bin (bin_ptrs: DEV array of n_parts
  * device pointers, each to bin_cap keys).  The pointers may address PEER memory
  * mapped over NVLink / NVSwitch: with by_owner == 1 and bin r placed in rank r's

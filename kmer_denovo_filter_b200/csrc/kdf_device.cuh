@@ -147,6 +147,7 @@ struct StreamView {
   const u32* valid;
   u64 n_bases;
   u64 n_words;
+  u64 w_begin, w_end;  // words whose window starts a kernel processes (default: all)
 };
 
 KDF_HD u64 ld_code(const StreamView& s, u64 w) {

@@ -1037,16 +1037,17 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_stream(StreamView s, int k,
   __syncthreads();
   u32 windows = 0;
   u64 stride = (u64)gridDim.x * blockDim.x;
-  u64 n_iter = (s.n_words + stride - 1) / stride;
-  u64 w0 = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  u64 n_iter = (s.w_end - s.w_begin + stride - 1) / stride;
+  u64 w0 = s.w_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x;
   for (u64 itn = 0; itn < n_iter; ++itn) {
     u64 w = w0 + itn * stride;
     WindowIter<KW> it(s, w, k);  // loads beyond n_words read as invalid
+    const bool in_range = w < s.w_end;  // window starts of later words belong to another launch
 #pragma unroll 1
     for (int c = 0; c < 32 / BIN_WPR; ++c) {
 #pragma unroll 4
       for (int j = 0; j < BIN_WPR; ++j) {
-        bool ok = it.ok();
+        bool ok = in_range && it.ok();
         Key<KW> key = it.canonical();
         it.advance();
         windows += ok ? 1u : 0u;
@@ -1143,6 +1144,8 @@ static StreamView view_of(const kdf_stream* s) {
   v.valid = s->valid;
   v.n_bases = s->n_bases;
   v.n_words = (s->n_bases + 31) / 32;
+  v.w_begin = 0;
+  v.w_end = v.n_words;
   return v;
 }
 
@@ -1549,7 +1552,8 @@ static int bin_qcap(int n_parts, int kw) {
 }
 
 static int bin_stream_impl(const kdf_stream* s, int k, int by_owner, int n_parts, BinDest dst,
-                           uint64_t* cursors, uint64_t* overflow, uint64_t* stats, void* stream);
+                           uint64_t* cursors, uint64_t* overflow, uint64_t* stats, void* stream,
+                           uint64_t first_word = 0, uint64_t n_range_words = ~0ull);
 
 int kdf_bin_stream(const kdf_stream* s, int k, int by_owner, int n_parts, uint64_t* bins,
                    uint64_t bin_cap, uint64_t* cursors, uint64_t* overflow, uint64_t* stats,
@@ -1568,8 +1572,19 @@ int kdf_bin_stream_to(const kdf_stream* s, int k, int by_owner, int n_parts,
   return bin_stream_impl(s, k, by_owner, n_parts, dst, cursors, overflow, stats, stream);
 }
 
+int kdf_bin_stream_range(const kdf_stream* s, uint64_t first_word, uint64_t n_words, int k,
+                         int by_owner, int n_parts, uint64_t* bins, uint64_t bin_cap,
+                         uint64_t* cursors, uint64_t* overflow, uint64_t* stats, void* stream) {
+  if (!s || !bins || !cursors || !overflow)
+    return fail(KDF_ERR_ARG, "kdf_bin_stream_range: NULL argument");
+  BinDest dst = {(u64*)bins, nullptr, bin_cap};
+  return bin_stream_impl(s, k, by_owner, n_parts, dst, cursors, overflow, stats, stream, first_word,
+                         n_words);
+}
+
 static int bin_stream_impl(const kdf_stream* s, int k, int by_owner, int n_parts, BinDest dst,
-                           uint64_t* cursors, uint64_t* overflow, uint64_t* stats, void* stream) {
+                           uint64_t* cursors, uint64_t* overflow, uint64_t* stats, void* stream,
+                           uint64_t first_word, uint64_t n_range_words) {
   int kw = kdf_key_words(k);
   if (!kw) return fail(KDF_ERR_ARG, "kdf_bin_stream: k must be in 1..64");
   if (n_parts < 1 || n_parts > BIN_MAX_PARTS) return fail(KDF_ERR_ARG, "kdf_bin_stream: n_parts must be 1..512");
@@ -1585,7 +1600,10 @@ static int bin_stream_impl(const kdf_stream* s, int k, int by_owner, int n_parts
     if ((1 << log2p) != n_local) return fail(KDF_ERR_ARG, "kdf_bin_stream: hash-range bins need a power-of-two count");
   }
   StreamView v = view_of(s);
-  if (v.n_words == 0) return KDF_OK;
+  if (first_word > v.n_words) first_word = v.n_words;
+  v.w_begin = first_word;
+  v.w_end = (n_range_words > v.n_words - first_word) ? v.n_words : first_word + n_range_words;
+  if (v.w_end == v.w_begin) return KDF_OK;
   int sm = current_sm_count();
   cudaStream_t st = (cudaStream_t)stream;
   int qcap = bin_qcap(n_parts, kw);
@@ -1594,7 +1612,7 @@ static int bin_stream_impl(const kdf_stream* s, int k, int by_owner, int n_parts
     size_t smem = BinStage<KW>::bytes(n_parts, qcap);                                             \
     const void* fn = (const void*)k_bin_stream<KW, BM>;                                           \
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    int g = grid_for(fn, BIN_THREADS, smem, v.n_words, sm);                                       \
+    int g = grid_for(fn, BIN_THREADS, smem, v.w_end - v.w_begin, sm);                             \
     k_bin_stream<KW, BM><<<g, BIN_THREADS, smem, st>>>(v, k, log2p, (u32)n_parts, (u32)n_owners,  \
                                                        qcap, dst, (u64*)cursors, (u64*)overflow,  \
                                                        (u64*)stats);                              \
@@ -1787,6 +1805,8 @@ int kdf_debug_extract_host(const uint64_t* codes, const uint32_t* valid, uint64_
   v.valid = valid;
   v.n_bases = n_bases;
   v.n_words = (n_bases + 31) / 32;
+  v.w_begin = 0;
+  v.w_end = v.n_words;
   for (u64 w = 0; w < v.n_words; ++w) {
     if (kw == 1) {
       WindowIter<1> it(v, w, k);

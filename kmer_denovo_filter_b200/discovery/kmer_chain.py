@@ -45,7 +45,28 @@ class _Uploader:
         d = self.eng.upload(s, with_reads=with_reads, copy_stream=self.side)
         ev = torch.cuda.Event()
         ev.record(self.side)
+        d.ready = ev
         return d, ev
+
+    def put_chunked(self, s, with_reads):
+        """Like :meth:`put`, but the stream is copied in chunks and can be consumed
+        chunk by chunk (``DeviceStream.chunks``); the returned event covers all of it."""
+        if isinstance(s, _engine.DeviceStream):
+            return s, None
+        torch = self.torch
+        if self.side is None:
+            self.side = getattr(self.eng, "_copy_stream", None)
+            if self.side is None:
+                self.side = self.eng._copy_stream = torch.cuda.Stream(device=self.eng.device)
+        d, ev = self.eng.upload_chunked(s, self.side, with_reads=with_reads)
+        d.ready = ev
+        return d, ev
+
+    def put_read_index(self, d, s):
+        """read_starts / read_lens of host stream ``s`` onto ``d`` → event (or None)."""
+        if isinstance(s, _engine.DeviceStream) or s.read_lens is None:
+            return None
+        return self.eng.upload_read_index(d, s, self.side)
 
     def wait(self, ev):
         if ev is not None:
@@ -116,8 +137,18 @@ def count_child_partitioned(eng, child_streams, ref_streams, k, min_child_count,
         rb = eng.new_bins(k, n_parts, ref_cap) if ref_streams else None
         st_c, st_r = eng.new_stats(), eng.new_stats()
         for s in child_streams:
-            eng.bin_stream(cb, s, st_c)
+            if getattr(s, "chunks", None):
+                main = eng.torch.cuda.current_stream(eng.device)
+                for first, n, ev in s.chunks:      # bin a chunk as soon as it has landed
+                    main.wait_event(ev)
+                    eng.bin_stream(cb, s, st_c, word_range=(first, n))
+            else:
+                if getattr(s, "ready", None) is not None:
+                    eng.torch.cuda.current_stream(eng.device).wait_event(s.ready)
+                eng.bin_stream(cb, s, st_c)
         for s in ref_streams:
+            if getattr(s, "ready", None) is not None:
+                eng.torch.cuda.current_stream(eng.device).wait_event(s.ready)
             eng.bin_stream(rb, s, st_r)
         over_c = cb.overflowed()
         over_r = rb.overflowed() if rb is not None else False
@@ -181,12 +212,20 @@ def discover_streams(eng, child, mother, father, ref, k, min_child_count=3,
         partitioned = child_capacity is None
     stats = eng.new_stats()
     up = _Uploader(eng)
-    d_child, ev_child = up.put(child, True)
-    d_ref, ev_ref = up.put(ref, False)
+    # copy order = consumption order: child (in chunks, binned as they land), ref,
+    # the child's read index (needed by the scan only), mother, father
+    if partitioned:
+        d_child, ev_child = up.put_chunked(child, False)
+        d_ref, ev_ref = up.put(ref, False)
+        ev_reads = up.put_read_index(d_child, child)
+    else:
+        d_child, ev_child = up.put(child, True)
+        d_ref, ev_ref = up.put(ref, False)
+        ev_reads = None
+        up.wait(ev_child)
+        up.wait(ev_ref)
     d_mother, ev_mother = up.put(mother, False)
     d_father, ev_father = up.put(father, False)
-    up.wait(ev_child)
-    up.wait(ev_ref)
 
     # Module 1 + reference subtraction: jellyfish count -C ; dump -L ; query ref.jf
     if partitioned:
@@ -247,6 +286,8 @@ def discover_streams(eng, child, mother, father, ref, k, min_child_count=3,
     if n_pu:
         out["pu"] = KmerSet(eng, k, lo, hi)
         pt = _primed_table(eng, k, lo, hi, n_pu)
+        up.wait(ev_child)
+        up.wait(ev_reads)
         if sparse_scan:
             # hits are rare: emit them from a streaming probe, reduce per read on the
             # device, return one record per read that has hits

@@ -72,6 +72,8 @@ _SIGNATURES = {
     "kdf_reduce_hits": (_i, [_vp, _vp, _u64, _vp, _u64, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp, _vp,
                              _vp, _vp, _vp]),
     "kdf_bin_stream": (_i, [ctypes.POINTER(_Stream), _i, _i, _i, _vp, _u64, _vp, _vp, _vp, _vp]),
+    "kdf_bin_stream_range": (_i, [ctypes.POINTER(_Stream), _u64, _u64, _i, _i, _i, _vp, _u64, _vp, _vp,
+                                  _vp, _vp]),
     "kdf_bin_stream_to": (_i, [ctypes.POINTER(_Stream), _i, _i, _i, _vp, _u64, _vp, _vp, _vp, _vp]),
     "kdf_bin_keys": (_i, [_vp, _vp, _u64, _i, _i, _i, _vp, _u64, _vp, _vp, _vp]),
     "kdf_count_bins": (_i, [_i, _i, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _u64, _u32, _u32, _u32, _u32,
@@ -202,7 +204,7 @@ def debug_extract_host(hs, k, random_access=False):
 class DeviceStream:
     """A packed stream resident in HBM (torch tensors as raw buffers)."""
 
-    __slots__ = ("codes", "valid", "n_bases", "read_starts", "read_lens", "_c")
+    __slots__ = ("codes", "valid", "n_bases", "read_starts", "read_lens", "_c", "chunks", "ready")
 
     def __init__(self, codes, valid, n_bases, read_starts=None, read_lens=None):
         self.codes = codes          # torch.int64 (bit pattern of u64)
@@ -211,6 +213,10 @@ class DeviceStream:
         self.read_starts = read_starts  # torch.int64 or None
         self.read_lens = read_lens      # torch.int32 or None
         self._c = _Stream(codes.data_ptr(), valid.data_ptr(), self.n_bases)
+        # optional upload schedule [(first_word, n_words, ready_event)]: the words of a
+        # chunk (and the few after it that its windows span) are valid once the event fires
+        self.chunks = None
+        self.ready = None   # event after which the whole stream is in HBM (None = already)
 
     @property
     def n_reads(self):
@@ -403,6 +409,61 @@ class CudaEngine:
                 d.copy_(h, non_blocking=non_blocking)
         rs, rl = (dst[2], dst[3]) if len(dst) == 4 else (None, None)
         return DeviceStream(dst[0], dst[1], hs.n_bases, rs, rl)
+
+    def upload_chunked(self, hs, copy_stream, n_chunks=8, with_reads=True):
+        """HostStream → DeviceStream copied chunk by chunk on ``copy_stream``; the
+        result carries ``chunks`` so that a consumer can start on the first words
+        while the rest is still in flight (``bin_stream(word_range=...)``).  A
+        chunk's event is recorded after the NEXT chunk's copy, because the windows
+        starting in its last words read the first words of the next one."""
+        torch = self.torch
+        main = torch.cuda.current_stream(self.device)
+        n_words = (hs.n_bases + 31) // 32
+        codes_h = torch.from_numpy(np.ascontiguousarray(hs.codes).view(np.int64))
+        valid_h = torch.from_numpy(np.ascontiguousarray(hs.valid).view(np.int32))
+        codes = torch.empty(codes_h.shape, dtype=torch.int64, device=self.device)
+        valid = torch.empty(valid_h.shape, dtype=torch.int32, device=self.device)
+        rs = rl = None
+        step = max((n_words + n_chunks - 1) // n_chunks, 1)
+        bounds = [(a, min(a + step, n_words)) for a in range(0, n_words, step)]
+        copy_stream.wait_stream(main)
+        events = []
+        with torch.cuda.stream(copy_stream):
+            for a, b in bounds:
+                codes[a:b].copy_(codes_h[a:b], non_blocking=True)
+                valid[a:b].copy_(valid_h[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                events.append(ev)
+            if with_reads and hs.read_lens is not None:
+                rs_h = torch.from_numpy(np.ascontiguousarray(hs.read_starts).view(np.int64))
+                rl_h = torch.from_numpy(np.ascontiguousarray(hs.read_lens).view(np.int32))
+                rs = torch.empty(rs_h.shape, dtype=torch.int64, device=self.device)
+                rl = torch.empty(rl_h.shape, dtype=torch.int32, device=self.device)
+                rs.copy_(rs_h, non_blocking=True)
+                rl.copy_(rl_h, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(copy_stream)
+        ds = DeviceStream(codes, valid, hs.n_bases, rs, rl)
+        ds.chunks = [(a, b - a, events[min(i + 1, len(events) - 1)]) for i, (a, b) in enumerate(bounds)]
+        return ds, done
+
+    def upload_read_index(self, ds, hs, copy_stream):
+        """Copy ``read_starts`` / ``read_lens`` of ``hs`` onto ``ds`` (copy stream);
+        → event."""
+        torch = self.torch
+        main = torch.cuda.current_stream(self.device)
+        rs_h = torch.from_numpy(np.ascontiguousarray(hs.read_starts).view(np.int64))
+        rl_h = torch.from_numpy(np.ascontiguousarray(hs.read_lens).view(np.int32))
+        ds.read_starts = torch.empty(rs_h.shape, dtype=torch.int64, device=self.device)
+        ds.read_lens = torch.empty(rl_h.shape, dtype=torch.int32, device=self.device)
+        copy_stream.wait_stream(main)
+        with torch.cuda.stream(copy_stream):
+            ds.read_starts.copy_(rs_h, non_blocking=True)
+            ds.read_lens.copy_(rl_h, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
 
     def keys_to_device(self, keys, key_words):
         """Python ints / numpy → (lo, hi) int64 device tensors."""
@@ -642,12 +703,14 @@ class CudaEngine:
     def new_bins(self, k, n_parts, bin_cap, by_owner=False):
         return KeyBins(self, k, n_parts, bin_cap, by_owner)
 
-    def bin_stream(self, bins, ds, stats=None):
-        """K2p / K6: append the canonical k-mers of a stream to hash-range (or owner) bins."""
+    def bin_stream(self, bins, ds, stats=None, word_range=None):
+        """K2p / K6: append the canonical k-mers of a stream to hash-range (or owner)
+        bins; ``word_range=(first, n)`` restricts the window starts to those words."""
         ev = self._t0()
-        self._check(self.lib.kdf_bin_stream(
-            ds.c(), bins.k, 1 if bins.by_owner else 0, bins.n_parts, bins.data.data_ptr(),
-            bins.bin_cap, bins.cursors.data_ptr(), bins.overflow.data_ptr(),
+        first, n = word_range if word_range is not None else (0, (ds.n_bases + 31) // 32)
+        self._check(self.lib.kdf_bin_stream_range(
+            ds.c(), int(first), int(n), bins.k, 1 if bins.by_owner else 0, bins.n_parts,
+            bins.data.data_ptr(), bins.bin_cap, bins.cursors.data_ptr(), bins.overflow.data_ptr(),
             stats.data_ptr() if stats is not None else None, self.stream_ptr()))
         self._t1("bin_stream/kw%d" % bins.key_words, ev)
         self.launches += 1
