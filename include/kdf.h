@@ -322,8 +322,9 @@ uint64_t kdf_pack_sequences(const char* seqs, const uint64_t* offsets,
  *   KDF_BAM_ALL   : every record.
  * A batch owns its host memory until kdf_bam_batch_free.  Metadata arrays are
  * filled only when want_meta != 0, base qualities only when want_meta >= 2
- * (VCF-mode child reads, vcf/pipeline.py:671-690).  max_bases == 0 reads to
- * end of file.                                                               */
+ * (VCF-mode child reads, vcf/pipeline.py:671-690), the raw records only when
+ * want_meta >= 3 (informative-reads BAM, discovery/pipeline.py:1979-2079).
+ * max_bases == 0 reads to end of file.                                       */
 #define KDF_BAM_FASTA 0
 #define KDF_BAM_SCAN 1
 #define KDF_BAM_ALL 2
@@ -353,11 +354,14 @@ typedef struct kdf_bam_batch {
   const char* sa_blob;
   const uint64_t* qual_off;      /* n_reads+1 offsets into qual_blob (want_meta >= 2) */
   const uint8_t* qual_blob;      /* Phred base qualities (0xFF = absent)     */
+  const uint64_t* raw_off;       /* n_reads+1 offsets into raw_blob (want_meta >= 3) */
+  const uint8_t* raw_blob;       /* the BAM records (bytes after block_size) */
   int at_eof;
 } kdf_bam_batch;
 
 int kdf_bam_open(const char* path, int n_threads, kdf_bam** out);
 void kdf_bam_close(kdf_bam* b);
+const char* kdf_bam_header_text(const kdf_bam* b, uint64_t* len); /* SAM header text */
 int kdf_bam_n_refs(const kdf_bam* b);
 const char* kdf_bam_ref_name(const kdf_bam* b, int i);
 int64_t kdf_bam_ref_len(const kdf_bam* b, int i);

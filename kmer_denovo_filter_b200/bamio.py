@@ -9,6 +9,8 @@ the (few) informative reads the CPU cluster step needs.
 """
 
 import ctypes
+import struct
+import zlib
 import os
 
 import numpy as np
@@ -29,7 +31,8 @@ class _Batch(ctypes.Structure):
         ("rec_index", _vp), ("ref_id", _vp), ("pos", _vp), ("next_ref_id", _vp),
         ("next_pos", _vp), ("flag", _vp), ("mapq", _vp), ("qname_off", _vp),
         ("qname_blob", _vp), ("cigar_off", _vp), ("cigar_blob", _vp),
-        ("sa_off", _vp), ("sa_blob", _vp), ("qual_off", _vp), ("qual_blob", _vp), ("at_eof", _i),
+        ("sa_off", _vp), ("sa_blob", _vp), ("qual_off", _vp), ("qual_blob", _vp), ("raw_off", _vp), ("raw_blob", _vp),
+        ("at_eof", _i),
     ]
 
 
@@ -205,6 +208,10 @@ class HostBatch(_engine.HostStream):
             self.cigar_blob = _arr(raw.cigar_blob, int(self.cigar_off[-1]) if n else 0, np.uint32)
             self.sa_off = _arr(raw.sa_off, n + 1, np.uint64)
             self.sa_blob = _arr(raw.sa_blob, int(self.sa_off[-1]) if n else 0, np.uint8)
+            self.has_raw = int(want_meta) >= 3
+            if self.has_raw:
+                self.raw_off = _arr(raw.raw_off, n + 1, np.uint64)
+                self.raw_blob = _arr(raw.raw_blob, int(self.raw_off[-1]) if n else 0, np.uint8)
             self.has_quals = int(want_meta) >= 2
             if self.has_quals:
                 self.qual_off = _arr(raw.qual_off, n + 1, np.uint64)
@@ -249,6 +256,9 @@ class BamReader:
         self.handle = h
         self.path = path
         n = self.lib.kdf_bam_n_refs(h)
+        ln = ctypes.c_uint64()
+        ptr = self.lib.kdf_bam_header_text(h, ctypes.byref(ln))
+        self.header_text = ctypes.string_at(ptr, ln.value) if ptr and ln.value else b""
         self.references = [self.lib.kdf_bam_ref_name(h, i).decode() for i in range(n)]
         self.lengths = [int(self.lib.kdf_bam_ref_len(h, i)) for i in range(n)]
 
@@ -304,3 +314,131 @@ def read_fasta_sequences(path):
     if names:
         seqs.append(b"".join(cur))
     return names, seqs
+
+
+# ---------------------------------------------------------------------------
+# BAM + BAI writer (replaces pysam's AlignmentFile("wb") / sort / index for the
+# informative-reads BAM, reference discovery/pipeline.py:1979-2079)
+# ---------------------------------------------------------------------------
+
+_BGZF_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+_BGZF_BLOCK = 0xFF00
+
+
+def _reg2bin(beg, end):
+    end -= 1
+    if beg >> 14 == end >> 14:
+        return ((1 << 15) - 1) // 7 + (beg >> 14)
+    if beg >> 17 == end >> 17:
+        return ((1 << 12) - 1) // 7 + (beg >> 17)
+    if beg >> 20 == end >> 20:
+        return ((1 << 9) - 1) // 7 + (beg >> 20)
+    if beg >> 23 == end >> 23:
+        return ((1 << 6) - 1) // 7 + (beg >> 23)
+    if beg >> 26 == end >> 26:
+        return ((1 << 3) - 1) // 7 + (beg >> 26)
+    return 0
+
+
+def append_int_tag(raw, tag, value):
+    """BAM record bytes (without block_size) + an ``i``-typed aux tag."""
+    return bytes(raw) + tag.encode() + b"i" + struct.pack("<i", int(value))
+
+
+def _record_span(raw):
+    """(ref_id, pos, end, flag) of a raw BAM record."""
+    ref_id, pos, l_name, _mq, _bin, n_cig, flag, _l_seq = struct.unpack_from("<iiBBHHHi", raw, 0)
+    end = pos
+    off = 32 + l_name
+    for c in range(n_cig):
+        v = struct.unpack_from("<I", raw, off + 4 * c)[0]
+        if (v & 15) in (0, 2, 3, 7, 8):
+            end += v >> 4
+    if end == pos:
+        end = pos + 1
+    return ref_id, pos, end, flag
+
+
+def write_sorted_bam(path, header_text, ref_names, ref_lens, records, index=True):
+    """Coordinate-sort ``records`` (raw BAM records without block_size), write them
+    as BGZF-compressed BAM at ``path`` and, with ``index``, a ``.bai`` beside it.
+    Order: (reference id, position, strand) with unplaced reads last, ties in input
+    order — what ``samtools sort`` produces."""
+    keyed = []
+    for i, raw in enumerate(records):
+        ref_id, pos, end, flag = _record_span(raw)
+        tid = ref_id if ref_id >= 0 else 1 << 31
+        keyed.append((tid, ((pos + 1) << 1) | (1 if flag & 0x10 else 0), i, raw, ref_id, pos, end, flag))
+    keyed.sort(key=lambda t: (t[0], t[1], t[2]))
+    text = header_text if isinstance(header_text, bytes) else header_text.encode()
+    if b"SO:" in text.split(b"\n", 1)[0]:
+        first, _, rest = text.partition(b"\n")
+        import re as _re
+        first = _re.sub(rb"SO:\S+", b"SO:coordinate", first)
+        text = first + b"\n" + rest
+    head = bytearray(b"BAM\1" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(ref_names)))
+    for name, ln in zip(ref_names, ref_lens):
+        nb = name.encode() + b"\0"
+        head += struct.pack("<i", len(nb)) + nb + struct.pack("<i", int(ln))
+    # uncompressed stream with the offset of every record
+    stream = bytearray(head)
+    starts = []
+    for t in keyed:
+        starts.append(len(stream))
+        stream += struct.pack("<i", len(t[3])) + t[3]
+    starts.append(len(stream))
+    # BGZF blocks; voffset(u) = file offset of u's block << 16 | offset inside it
+    block_file_off = []
+    with open(path, "wb") as fh:
+        for off in range(0, len(stream), _BGZF_BLOCK):
+            block_file_off.append(fh.tell())
+            chunk = bytes(stream[off:off + _BGZF_BLOCK])
+            co = zlib.compressobj(6, zlib.DEFLATED, -15)
+            comp = co.compress(chunk) + co.flush()
+            fh.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(comp) + 25) +
+                     comp + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+        eof_off = fh.tell()
+        fh.write(_BGZF_EOF)
+    block_file_off.append(eof_off)
+
+    def voff(u):
+        b = u // _BGZF_BLOCK
+        return (block_file_off[b] << 16) | (u - b * _BGZF_BLOCK) if u < len(stream) else (eof_off << 16)
+
+    if not index:
+        return len(keyed)
+    n_ref = len(ref_names)
+    bins = [dict() for _ in range(n_ref)]
+    linear = [dict() for _ in range(n_ref)]
+    n_no_coor = 0
+    for j, t in enumerate(keyed):
+        ref_id, pos, end = t[4], t[5], t[6]
+        if ref_id < 0 or pos < 0:
+            n_no_coor += 1
+            continue
+        v0, v1 = voff(starts[j]), voff(starts[j + 1])
+        chunks = bins[ref_id].setdefault(_reg2bin(pos, end), [])
+        if chunks and chunks[-1][1] == v0:
+            chunks[-1][1] = v1
+        else:
+            chunks.append([v0, v1])
+        for w in range(pos >> 14, ((end - 1) >> 14) + 1):
+            if w not in linear[ref_id]:
+                linear[ref_id][w] = v0
+    out = bytearray(b"BAI\1" + struct.pack("<i", n_ref))
+    for r in range(n_ref):
+        out += struct.pack("<i", len(bins[r]))
+        for b in sorted(bins[r]):
+            out += struct.pack("<Ii", b, len(bins[r][b]))
+            for v0, v1 in bins[r][b]:
+                out += struct.pack("<QQ", v0, v1)
+        n_intv = (max(linear[r]) + 1) if linear[r] else 0
+        out += struct.pack("<i", n_intv)
+        last = 0
+        for w in range(n_intv):
+            last = linear[r].get(w, last)
+            out += struct.pack("<Q", last)
+    out += struct.pack("<Q", n_no_coor)
+    with open(path + ".bai", "wb") as fh:
+        fh.write(out)
+    return len(keyed)

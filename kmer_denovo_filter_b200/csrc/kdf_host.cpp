@@ -242,6 +242,8 @@ struct kdf_bam_batch_impl {
   std::vector<uint64_t> qname_off, cigar_off, sa_off;  // n+1 each
   std::vector<char> qname_blob, sa_blob;
   std::vector<uint32_t> cigar_blob;
+  std::vector<uint64_t> raw_off;    // n+1 (want_meta >= 3): the BAM records themselves
+  std::vector<uint8_t> raw_blob;    //   (bytes after block_size), for BAM output
   std::vector<uint64_t> qual_off;   // n+1 (want_meta >= 2)
   std::vector<uint8_t> qual_blob;   // Phred base qualities, l_seq bytes per read
   uint64_t n_bases = 0;
@@ -281,6 +283,11 @@ void kdf_bam_close(kdf_bam* h) {
 
 const char* kdf_host_last_error(void) { return g_host_err.c_str(); }
 
+const char* kdf_bam_header_text(const kdf_bam* h, uint64_t* len) {
+  const Bam* b = reinterpret_cast<const Bam*>(h);
+  if (len) *len = b->header_text.size();
+  return b->header_text.data();
+}
 int kdf_bam_n_refs(const kdf_bam* h) { return (int)reinterpret_cast<const Bam*>(h)->ref_names.size(); }
 const char* kdf_bam_ref_name(const kdf_bam* h, int i) {
   const Bam* b = reinterpret_cast<const Bam*>(h);
@@ -412,6 +419,7 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
     im->cigar_off.assign(n + 1, 0);
     im->sa_off.assign(n + 1, 0);
     if (want_meta >= 2) im->qual_off.assign(n + 1, 0);
+    if (want_meta >= 3) im->raw_off.assign(n + 1, 0);
     for (size_t i = 0; i < n; ++i) {
       const uint8_t* r = buf.data() + kept[i].off;
       int32_t bs = rd_i32(r - 4);
@@ -434,6 +442,10 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
         im->cigar_blob.push_back(v);
       }
       im->cigar_off[i + 1] = im->cigar_blob.size();
+      if (want_meta >= 3) {
+        im->raw_blob.insert(im->raw_blob.end(), r, r + bs);
+        im->raw_off[i + 1] = im->raw_blob.size();
+      }
       if (want_meta >= 2) {
         const uint8_t* q = cg + 4 * (size_t)n_cig + (l_seq + 1) / 2;
         im->qual_blob.insert(im->qual_blob.end(), q, q + l_seq);
@@ -502,6 +514,10 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
     if (want_meta >= 2) {
       out->qual_off = im->qual_off.data();
       out->qual_blob = im->qual_blob.data();
+    }
+    if (want_meta >= 3) {
+      out->raw_off = im->raw_off.data();
+      out->raw_blob = im->raw_blob.data();
     }
   }
   out->at_eof = (b->eof && b->carry.empty()) ? 1 : 0;

@@ -637,6 +637,41 @@ def _evaluate_dnm_regions(discovery_regions, region_detail, dnm_regions=None):
     return out
 
 
+def _write_informative_reads_discovery(child_bam, ref_fasta, proband_unique_kmers_or_path, kmer_size,
+                                       output_bam, engine=None, threads=4):
+    """Child reads carrying >= 1 proband-unique k-mer → coordinate-sorted, indexed
+    BAM, each read tagged ``dk:i:1`` (reference ``:1979-2079``): primary and
+    supplementary, non-duplicate, mapped or not, first record per
+    ``(query_name, is_supplementary)`` in file order.  ``proband_unique_kmers_or_path``
+    is the device membership table (or a KmerSet)."""
+    eng = get_engine(engine)
+    table = proband_unique_kmers_or_path
+    owns = False
+    if isinstance(table, KmerSet):
+        table = table.build_table()
+        owns = True
+    records = []
+    written = set()
+    with bamio.BamReader(child_bam, threads=threads) as rd:
+        header_text, names, lens = rd.header_text, rd.references, rd.lengths
+        for batch in rd.batches(bamio.MODE_SCAN, max_bases=kw.BATCH_BASES, want_meta=3):
+            sp = eng.scan_reads_sparse(table, eng.upload(batch))
+            for i in sp["read"].astype(np.int64).tolist():
+                rec = batch.record(i)
+                key = (rec.query_name, rec.is_supplementary)
+                if key in written:
+                    continue
+                written.add(key)
+                raw = batch.raw_blob[int(batch.raw_off[i]):int(batch.raw_off[i + 1])].tobytes()
+                records.append(bamio.append_int_tag(raw, "dk", 1))
+            batch.close()
+    if owns:
+        table.close()
+    n = bamio.write_sorted_bam(output_bam, header_text, names, lens, records)
+    logger.info("Informative reads BAM written: %s (%d reads)", output_bam, n)
+    return n
+
+
 def _write_empty_discovery_outputs(bed_path, metrics_path, summary_path, metrics,
                                    bedpe_path=None):
     _write_bed([], {}, {}, bed_path)
@@ -680,6 +715,7 @@ def run_discovery_pipeline(args, engine=None):
     eng = get_engine(engine)
     out_prefix = args.out_prefix
     bed_path = out_prefix + ".bed"
+    info_bam_path = out_prefix + ".informative.bam"
     metrics_path = out_prefix + ".metrics.json"
     summary_path = out_prefix + ".summary.txt"
     bedpe_path = getattr(args, "sv_bedpe", None) or out_prefix + ".sv.bedpe"
@@ -719,6 +755,9 @@ def run_discovery_pipeline(args, engine=None):
         args.child, args.ref_fasta, None, k, merge_distance=args.cluster_distance,
         threads=threads, min_distinct_kmers_per_read=min_dk, proband_jf=pu_table,
         n_proband_unique=n_pu, engine=eng)
+    logger.info("[Module 4] Writing informative reads BAM: %s", info_bam_path)
+    _write_informative_reads_discovery(args.child, getattr(args, "ref_fasta", None), pu_table, k,
+                                       info_bam_path, engine=eng, threads=threads)
     pu_table.close()
 
     min_reads, min_kmers = args.min_supporting_reads, args.min_distinct_kmers

@@ -87,6 +87,7 @@ _SIGNATURES = {
     # host BGZF/BAM decoder (bound in bamio.py)
     "kdf_bam_open": (_i, [ctypes.c_char_p, _i, ctypes.POINTER(_vp)]),
     "kdf_bam_close": (None, [_vp]),
+    "kdf_bam_header_text": (ctypes.c_void_p, [_vp, ctypes.POINTER(_u64)]),
     "kdf_bam_n_refs": (_i, [_vp]),
     "kdf_bam_ref_name": (ctypes.c_char_p, [_vp, _i]),
     "kdf_bam_ref_len": (ctypes.c_int64, [_vp, _i]),

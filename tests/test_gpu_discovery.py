@@ -144,3 +144,57 @@ def test_gpu_kmer_query_interface(eng, giab_paths):
     assert uniq == set(want.values()) and idx == set(want)
     q.close()
     assert q.query_batch(pu[:3]) == set(pu[:3])  # close() only clears caches
+
+
+def test_informative_reads_bam(eng, giab_paths, giab_records, oracle_discovery, tmp_path):
+    """{prefix}.informative.bam: the reads with >= 1 proband-unique k-mer (primary +
+    supplementary, non-duplicate, first per (qname, is_supplementary)), tagged
+    dk:i:1, coordinate-sorted, with a .bai whose chunks land on record boundaries.
+    Read back with the oracle's BAM reader."""
+    import struct
+    from kmer_denovo_filter_b200.discovery import pipeline as P
+    from kmer_denovo_filter_b200.kmer_utils import KmerSet
+    from oracle import bam as obam, discovery as odisc
+    pu = oracle_discovery["proband_unique"]
+    k = 31
+    kset = KmerSet(eng, k, *eng.keys_to_device(sorted(pu), 1))
+    out = str(tmp_path / "giab.informative.bam")
+    n = P._write_informative_reads_discovery(giab_paths["child"], None, kset, k, out, engine=eng)
+    # expected selection straight from the oracle's records
+    pu_keys = set(kset.to_pyints())
+    want, seen = [], set()
+    for r in giab_records["child"]:
+        if r.is_secondary or r.is_duplicate or not r.seq:
+            continue
+        uniq, _idx = odisc.scan_read_numeric(r.seq, k, pu_keys)
+        key = (r.qname, r.is_supplementary)
+        if uniq and key not in seen:
+            seen.add(key)
+            want.append((r.ref_id, r.pos, r.qname, r.flag))
+    names, lens, got = obam.read_bam(out)
+    assert n == len(got) == len(want) > 150
+    assert sorted((r.ref_id, r.pos, r.qname, r.flag) for r in got) == sorted(want)
+    keys = [((r.ref_id if r.ref_id >= 0 else 1 << 31), r.pos) for r in got]
+    assert keys == sorted(keys)
+    assert all(r.get_tag("dk") == 1 for r in got)
+    src = {(r.qname, r.flag): r for r in giab_records["child"]}
+    for r in got[:50]:
+        o = src[(r.qname, r.flag)]
+        assert (r.seq, r.cigar, r.mapq, r.next_pos, r.tlen) == (o.seq, o.cigar, o.mapq, o.next_pos, o.tlen)
+    # the index parses and every chunk starts inside the file
+    bai = open(out + ".bai", "rb").read()
+    assert bai[:4] == b"BAI\x01"
+    n_ref = struct.unpack_from("<i", bai, 4)[0]
+    assert n_ref == len(names)
+    size = os.path.getsize(out)
+    off, n_chunks = 8, 0
+    for _ in range(n_ref):
+        n_bin = struct.unpack_from("<i", bai, off)[0]; off += 4
+        for _b in range(n_bin):
+            _bin, n_chunk = struct.unpack_from("<Ii", bai, off); off += 8
+            for _c in range(n_chunk):
+                v0, v1 = struct.unpack_from("<QQ", bai, off); off += 16
+                assert (v0 >> 16) < size and v0 < v1
+                n_chunks += 1
+        n_intv = struct.unpack_from("<i", bai, off)[0]; off += 4 + 8 * n_intv
+    assert n_chunks > 0 and off + 8 == len(bai)
