@@ -28,11 +28,12 @@
  *   Both arrays hold n_words = ceil(n_bases/32) words; bits past n_bases must
  *   be 0.  A window (k-mer) starting at p is counted iff valid[p..p+k) are all 1.
  *
- *   Table: open addressing over 32-byte buckets, linear probing by bucket; the
+ *   Table: open addressing over 4-slot buckets, linear probing by bucket; the
  *   caller provides one 32-byte-aligned device buffer of kdf_table_bytes():
- *     keys  : capacity slots of key_words u64 each (k <= 32: 4 keys per bucket;
- *             k <= 64: 2 {lo, hi} keys per bucket); empty = all-ones words
- *             (never a canonical k-mer); a probe reads one whole bucket;
+ *     keys  : capacity slots of key_words u64 each (k <= 32: a bucket is 32
+ *             bytes = one sector; k <= 64: 4 {lo, hi} keys = 64 bytes = two
+ *             sectors of one line); empty = all-ones words (never a canonical
+ *             k-mer); a probe reads one whole bucket with 256-bit loads;
  *     plane0: u32[capacity], plane1: u32[capacity] — two independent value
  *             planes (child count, parent count, reference flag ...), touched
  *             only when a key is found.

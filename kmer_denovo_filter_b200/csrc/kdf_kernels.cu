@@ -68,7 +68,7 @@ template <int KW> struct TableView {
   int log2_parts;
   bool fast_empty;  // k % 32 != 0 (see has_empty)
 };
-template <int KW> struct SPB { static constexpr int v = 4 / KW; };  // slots per bucket
+template <int KW> struct SPB { static constexpr int v = 4; };  // slots per bucket
 
 template <int KW>
 static TableView<KW> view_of_table(const kdf_table* t) {
@@ -83,29 +83,38 @@ static TableView<KW> view_of_table(const kdf_table* t) {
 }
 
 // ----------------------------------------------------- bucket primitives --
-struct Bucket {
-  u64 q[4];
+// A bucket is 4 slots for either key width: 32 bytes (one sector, one 256-bit
+// load) of 64-bit keys, 64 bytes (two sectors of one line, two 256-bit loads) of
+// 128-bit keys.  Four slots keep "home bucket full" rare at load 0.3-0.5 (5-14 %);
+// with two 128-bit slots per bucket it was 14-26 % and every such probe pays a
+// second, dependent round trip.
+template <int KW> struct Bucket {
+  u64 q[4 * KW];
 };
-__device__ __forceinline__ Bucket ld_bucket(const u64* p) {
-  Bucket b;
+__device__ __forceinline__ void ld256(const u64* p, u64& a, u64& b, u64& c, u64& d) {
   asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
-               : "=l"(b.q[0]), "=l"(b.q[1]), "=l"(b.q[2]), "=l"(b.q[3])
+               : "=l"(a), "=l"(b), "=l"(c), "=l"(d)
                : "l"(p)
                : "memory");
+}
+template <int KW> __device__ __forceinline__ Bucket<KW> ld_bucket(const u64* p) {
+  Bucket<KW> b;
+  ld256(p, b.q[0], b.q[1], b.q[2], b.q[3]);
+  if (KW == 2) ld256(p + 4, b.q[4 * (KW - 1)], b.q[4 * (KW - 1) + 1], b.q[4 * (KW - 1) + 2], b.q[4 * (KW - 1) + 3]);
   return b;
 }
-__device__ __forceinline__ Bucket lds_bucket(const u64* p) {
-  Bucket b;
-  ulonglong2 a = *reinterpret_cast<const ulonglong2*>(p);
-  ulonglong2 c = *reinterpret_cast<const ulonglong2*>(p + 2);
-  b.q[0] = a.x;
-  b.q[1] = a.y;
-  b.q[2] = c.x;
-  b.q[3] = c.y;
+template <int KW> __device__ __forceinline__ Bucket<KW> lds_bucket(const u64* p) {
+  Bucket<KW> b;
+#pragma unroll
+  for (int i = 0; i < 2 * KW; ++i) {
+    ulonglong2 a = *reinterpret_cast<const ulonglong2*>(p + 2 * i);
+    b.q[2 * i] = a.x;
+    b.q[2 * i + 1] = a.y;
+  }
   return b;
 }
 // index of the slot holding `key` in the bucket, or -1
-__device__ __forceinline__ int match_in(const Bucket& b, const Key<1>& key) {
+__device__ __forceinline__ int match_in(const Bucket<1>& b, const Key<1>& key) {
   int j = -1;
   if (b.q[3] == key.lo) j = 3;
   if (b.q[2] == key.lo) j = 2;
@@ -113,15 +122,17 @@ __device__ __forceinline__ int match_in(const Bucket& b, const Key<1>& key) {
   if (b.q[0] == key.lo) j = 0;
   return j;
 }
-__device__ __forceinline__ int match_in(const Bucket& b, const Key<2>& key) {
+__device__ __forceinline__ int match_in(const Bucket<2>& b, const Key<2>& key) {
   int j = -1;
+  if (b.q[6] == key.lo && b.q[7] == key.hi) j = 3;
+  if (b.q[4] == key.lo && b.q[5] == key.hi) j = 2;
   if (b.q[2] == key.lo && b.q[3] == key.hi) j = 1;
   if (b.q[0] == key.lo && b.q[1] == key.hi) j = 0;
   return j;
 }
 // `fast`: k is not a multiple of 32, so the top 32 bits of a stored key's most
 // significant word are never all ones and testing them alone identifies an empty slot
-__device__ __forceinline__ bool has_empty(const Bucket& b, Key<1>, bool fast) {
+__device__ __forceinline__ bool has_empty(const Bucket<1>& b, Key<1>, bool fast) {
   if (fast) {
     // a slot is empty iff its high half is all ones: max over the four high halves
     u32 h0 = (u32)(b.q[0] >> 32), h1 = (u32)(b.q[1] >> 32), h2 = (u32)(b.q[2] >> 32), h3 = (u32)(b.q[3] >> 32);
@@ -130,16 +141,17 @@ __device__ __forceinline__ bool has_empty(const Bucket& b, Key<1>, bool fast) {
   }
   return b.q[0] == EMPTY || b.q[1] == EMPTY || b.q[2] == EMPTY || b.q[3] == EMPTY;
 }
-__device__ __forceinline__ bool has_empty(const Bucket& b, Key<2>, bool fast) {
+__device__ __forceinline__ bool has_empty(const Bucket<2>& b, Key<2>, bool fast) {
   if (fast) {
-    u32 h0 = (u32)(b.q[1] >> 32), h1 = (u32)(b.q[3] >> 32);
-    return max(h0, h1) == 0xffffffffu;
+    u32 h0 = (u32)(b.q[1] >> 32), h1 = (u32)(b.q[3] >> 32), h2 = (u32)(b.q[5] >> 32), h3 = (u32)(b.q[7] >> 32);
+    return max(max(h0, h1), max(h2, h3)) == 0xffffffffu;
   }
-  return (b.q[0] == EMPTY && b.q[1] == EMPTY) || (b.q[2] == EMPTY && b.q[3] == EMPTY);
+  return (b.q[0] == EMPTY && b.q[1] == EMPTY) || (b.q[2] == EMPTY && b.q[3] == EMPTY) ||
+         (b.q[4] == EMPTY && b.q[5] == EMPTY) || (b.q[6] == EMPTY && b.q[7] == EMPTY);
 }
 // slot j of the bucket may be (a possibly torn view of) an empty slot
-__device__ __forceinline__ bool maybe_empty(const Bucket& b, int j, Key<1>) { return b.q[j] == EMPTY; }
-__device__ __forceinline__ bool maybe_empty(const Bucket& b, int j, Key<2>) {
+__device__ __forceinline__ bool maybe_empty(const Bucket<1>& b, int j, Key<1>) { return b.q[j] == EMPTY; }
+__device__ __forceinline__ bool maybe_empty(const Bucket<2>& b, int j, Key<2>) {
   return b.q[2 * j] == EMPTY || b.q[2 * j + 1] == EMPTY;
 }
 
@@ -211,7 +223,7 @@ __device__ __forceinline__ u32 resolve_from(const TableView<KW>& t, u32 b, const
   constexpr bool kInsert = (OP == OP_INSERT_COUNT || OP == OP_INSERT_ONLY);
   constexpr int S = SPB<KW>::v;
   for (u32 n = 0; n < t.n_buckets; ++n) {
-    Bucket bk = ld_bucket(t.keys + (u64)b * 4);
+    Bucket<KW> bk = ld_bucket<KW>(t.keys + (u64)b * 4 * KW);
     int j = match_in(bk, key);
     if (j >= 0) {
       on_found<OP, KW>(t, (u64)b * S + j, plane, arg, pos, sink);
@@ -375,14 +387,14 @@ __global__ void __launch_bounds__(256) k_extract(StreamView s, int k, u64* out_l
 // ops "bucket holds the key" (the common case at sequencing depth).  Anything
 // else is queued per warp and resolved 32 items at a time.
 template <int KW, int OP, bool SMEM, int CHUNK>
-__global__ void __launch_bounds__(SMEM ? 512 : 256, SMEM ? KDF_SMEM_BLOCKS : KDF_STREAM_BLOCKS)
+__global__ void __launch_bounds__(SMEM ? 512 : 256, SMEM ? KDF_SMEM_BLOCKS : (KW == 2 ? 2 : KDF_STREAM_BLOCKS))
     k_stream(TableView<KW> t, StreamView s, int k, int plane, u32 arg, u64* stats, HitSink sink) {
   extern __shared__ __align__(32) u64 sm_keys[];
   constexpr bool kInsert = (OP == OP_INSERT_COUNT || OP == OP_INSERT_ONLY);
   constexpr int S = SPB<KW>::v;
   static_assert(!(SMEM && kInsert), "shared-memory tables are read-only");
   if (SMEM) {
-    u32 n = t.n_buckets * 4;
+    u32 n = t.n_buckets * 4 * KW;
     for (u32 i = threadIdx.x; i < n; i += blockDim.x) sm_keys[i] = __ldg(t.keys + i);
     __syncthreads();
   }
@@ -404,7 +416,7 @@ __global__ void __launch_bounds__(SMEM ? 512 : 256, SMEM ? KDF_SMEM_BLOCKS : KDF
 #pragma unroll 1
     for (int c = 0; c < 32 / CHUNK; ++c) {
       Key<KW> keys[CHUNK];
-      Bucket bk[CHUNK];
+      Bucket<KW> bk[CHUNK];
       u32 bidx[CHUNK];
       u32 okm = 0;
 #pragma unroll
@@ -415,7 +427,7 @@ __global__ void __launch_bounds__(SMEM ? 512 : 256, SMEM ? KDF_SMEM_BLOCKS : KDF
         bidx[u] = bucket_of(hash_key(keys[u]), t.log2_parts, t.n_buckets);
         if (ok) {
           okm |= 1u << u;
-          bk[u] = SMEM ? lds_bucket(sm_keys + (u64)bidx[u] * 4) : ld_bucket(t.keys + (u64)bidx[u] * 4);
+          bk[u] = SMEM ? lds_bucket<KW>(sm_keys + (u64)bidx[u] * 4 * KW) : ld_bucket<KW>(t.keys + (u64)bidx[u] * 4 * KW);
         }
       }
       st.windows += __popc(okm);
@@ -489,7 +501,7 @@ __global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_update_keys(TableView<
   for (u64 itn = 0; itn < n_iter; ++itn) {
     u64 i0 = first + itn * stride * CHUNK;
     Key<KW> keys[CHUNK];
-    Bucket bk[CHUNK];
+    Bucket<KW> bk[CHUNK];
     u32 bidx[CHUNK];
     u32 okm = 0;
 #pragma unroll
@@ -504,7 +516,7 @@ __global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_update_keys(TableView<
     for (int u = 0; u < CHUNK; ++u) {
       if (okm & (1u << u)) {
         bidx[u] = bucket_of(hash_key(keys[u]), t.log2_parts, t.n_buckets);
-        bk[u] = ld_bucket(t.keys + (u64)bidx[u] * 4);
+        bk[u] = ld_bucket<KW>(t.keys + (u64)bidx[u] * 4 * KW);
       }
     }
     st.windows += __popc(okm);
@@ -605,37 +617,28 @@ __global__ void __launch_bounds__(256) k_emit_buckets(TableView<KW> t, u32 min0,
   for (u64 r = 0; r < rounds; ++r) {
     u64 b = first + r * stride;
     bool inb = b < t.n_buckets;
-    Bucket bk;
-    bk.q[0] = bk.q[1] = bk.q[2] = bk.q[3] = EMPTY;
+    Bucket<KW> bk;
+#pragma unroll
+    for (int i = 0; i < 4 * KW; ++i) bk.q[i] = EMPTY;
     u32 p0[S], p1[S];
 #pragma unroll
     for (int j = 0; j < S; ++j) p0[j] = p1[j] = 0;
     bool any = false;
     if (inb) {
-      bk = ld_bucket(t.keys + b * 4);
-      any = (KW == 1) ? !(bk.q[0] == EMPTY && bk.q[1] == EMPTY && bk.q[2] == EMPTY && bk.q[3] == EMPTY)
-                      : !(bk.q[1] == EMPTY && bk.q[3] == EMPTY && bk.q[0] == EMPTY && bk.q[2] == EMPTY);
+      bk = ld_bucket<KW>(t.keys + b * 4 * KW);
+#pragma unroll
+      for (int i = 0; i < 4 * KW; ++i) any = any || bk.q[i] != EMPTY;
       if (any) {
-        if constexpr (KW == 1) {
-          uint4 a = __ldcg(reinterpret_cast<const uint4*>(t.p0 + b * 4));
-          uint4 c = __ldcg(reinterpret_cast<const uint4*>(t.p1 + b * 4));
-          p0[0] = a.x; p0[1] = a.y; p0[2] = a.z; p0[3] = a.w;
-          p1[0] = c.x; p1[1] = c.y; p1[2] = c.z; p1[3] = c.w;
-        } else {
-          uint2 a = __ldcg(reinterpret_cast<const uint2*>(t.p0 + b * 2));
-          uint2 c = __ldcg(reinterpret_cast<const uint2*>(t.p1 + b * 2));
-          p0[0] = a.x; p0[1] = a.y;
-          p1[0] = c.x; p1[1] = c.y;
-        }
+        uint4 a = __ldcg(reinterpret_cast<const uint4*>(t.p0 + b * 4));
+        uint4 c = __ldcg(reinterpret_cast<const uint4*>(t.p1 + b * 4));
+        p0[0] = a.x; p0[1] = a.y; p0[2] = a.z; p0[3] = a.w;
+        p1[0] = c.x; p1[1] = c.y; p1[2] = c.z; p1[3] = c.w;
         if (CLEAR) {
-          asm volatile("st.global.cg.v4.u64 [%0], {%1,%1,%1,%1};" ::"l"(t.keys + b * 4), "l"(EMPTY) : "memory");
-          if (KW == 1) {
-            *reinterpret_cast<uint4*>(t.p0 + b * 4) = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(t.p1 + b * 4) = make_uint4(0, 0, 0, 0);
-          } else {
-            *reinterpret_cast<uint2*>(t.p0 + b * 2) = make_uint2(0, 0);
-            *reinterpret_cast<uint2*>(t.p1 + b * 2) = make_uint2(0, 0);
-          }
+          asm volatile("st.global.cg.v4.u64 [%0], {%1,%1,%1,%1};" ::"l"(t.keys + b * 4 * KW), "l"(EMPTY) : "memory");
+          if (KW == 2)
+            asm volatile("st.global.cg.v4.u64 [%0], {%1,%1,%1,%1};" ::"l"(t.keys + b * 4 * KW + 4), "l"(EMPTY) : "memory");
+          *reinterpret_cast<uint4*>(t.p0 + b * 4) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(t.p1 + b * 4) = make_uint4(0, 0, 0, 0);
         }
       }
     }
@@ -683,7 +686,7 @@ __device__ __forceinline__ bool find_slot(const TableView<KW>& t, const Key<KW>&
   constexpr int S = SPB<KW>::v;
   u32 b = bucket_of(hash_key(key), t.log2_parts, t.n_buckets);
   for (u32 n = 0; n < t.n_buckets; ++n) {
-    Bucket bk = ld_bucket(t.keys + (u64)b * 4);
+    Bucket<KW> bk = ld_bucket<KW>(t.keys + (u64)b * 4 * KW);
     int j = match_in(bk, key);
     if (j >= 0) {
       idx_out = (u64)b * S + j;
@@ -1157,7 +1160,7 @@ static int launch_stream(const kdf_table* t, const StreamView& v, int plane, u32
                          const HitSink& sink, cudaStream_t st) {
   TableView<KW> tv = view_of_table<KW>(t);
   const void* fn = (const void*)k_stream<KW, OP, SMEM, CHUNK>;
-  size_t smem = SMEM ? (size_t)tv.n_buckets * 32 : 0;
+  size_t smem = SMEM ? (size_t)tv.n_buckets * 32 * KW : 0;
   int block = SMEM ? 512 : 256;
   if (SMEM) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int g = grid_for(fn, block, smem, v.n_words, t->sm_count);
@@ -1169,7 +1172,7 @@ static int launch_stream(const kdf_table* t, const StreamView& v, int plane, u32
 template <int KW>
 static int dispatch_stream(const kdf_table* t, const StreamView& v, int op, int plane, u32 arg,
                            u64* stats, const HitSink& sink, cudaStream_t st) {
-  bool small = (size_t)(t->capacity / SPB<KW>::v) * 32 <= SMEM_TABLE_MAX && t->log2_parts == 0;
+  bool small = (size_t)(t->capacity / SPB<KW>::v) * 32 * KW <= SMEM_TABLE_MAX && t->log2_parts == 0;
   switch (op) {
     case OP_INSERT_COUNT:
       return launch_stream<KW, OP_INSERT_COUNT, false, KDF_STREAM_CHUNK>(t, v, plane, arg, stats, sink, st);
@@ -1260,7 +1263,7 @@ static int check_table_args(int k, uint64_t capacity, const void* slots, const c
   if (!kw) return fail(KDF_ERR_ARG, std::string(who) + ": k must be in 1..64");
   if (capacity < 4 || (capacity & 3))
     return fail(KDF_ERR_ARG, std::string(who) + ": capacity must be a multiple of 4, >= 4");
-  if (capacity / (4 / kw) > 0xffffffffull)
+  if (capacity / 4 > 0xffffffffull)
     return fail(KDF_ERR_ARG, std::string(who) + ": capacity exceeds 2^32 buckets");
   if (((uintptr_t)slots & 31) != 0)
     return fail(KDF_ERR_ARG, std::string(who) + ": table memory must be 32-byte aligned");
