@@ -12,8 +12,8 @@ Reference map (``vcf/pipeline.py``):
   _parse_vcf_variants :747       _write_annotated_vcf :813
   _write_summary :1360           run_pipeline :1454 (parent scans :1587-1609,
                                  annotate :1662-1728, metrics :1925-1951)
-Not restated: Kraken2 contamination fractions, the HTML report and the
-informative-reads BAM (SURVEY §2 rows 12, 16, 17 — out of scope).
+Not restated: Kraken2 contamination fractions, the HTML report and VCF mode's
+DV-tagged informative-reads BAM (SURVEY §2 rows 12, 16, 17 — out of scope).
 """
 
 import collections
@@ -265,16 +265,72 @@ def _annotate_variants(variants, variant_read_kmers, parent_found_kmers):
 # ── Step 5: writers ────────────────────────────────────────────────
 
 def _bgzf_write(path, data):
-    """bgzip-compatible output (64 KiB BGZF blocks + EOF block)."""
+    """bgzip-compatible output (64 KiB BGZF blocks + EOF block).  → file offset of
+    every block (for virtual offsets)."""
+    offs = []
     with open(path, "wb") as fh:
         for off in range(0, len(data), 0xFF00):
+            offs.append(fh.tell())
             chunk = data[off:off + 0xFF00]
             co = zlib.compressobj(6, zlib.DEFLATED, -15)
             comp = co.compress(chunk) + co.flush()
             fh.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" +
                      struct.pack("<H", len(comp) + 25) + comp +
                      struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+        offs.append(fh.tell())
         fh.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+    return offs
+
+
+def _write_tabix_index(vcf_gz, data, block_offs):
+    """``.tbi`` for a bgzipped VCF whose uncompressed bytes are ``data`` (what
+    ``pysam.tabix_index(preset="vcf")`` writes; reference ``:1302``): the BAI
+    binning scheme over (CHROM, POS-1, POS-1+len(REF)), BGZF-compressed."""
+    def voff(u):
+        if u >= len(data):
+            return block_offs[-1] << 16          # the EOF block
+        b = u // 0xFF00
+        return (block_offs[b] << 16) | (u - b * 0xFF00)
+
+    names, bins, linear = [], [], []
+    pos = 0
+    for line in data.split(b"\n"):
+        start, pos = pos, pos + len(line) + 1
+        if not line or line[:1] == b"#":
+            continue
+        f = line.split(b"\t", 5)
+        chrom = f[0].decode()
+        if chrom not in names:
+            names.append(chrom)
+            bins.append({})
+            linear.append({})
+        t = names.index(chrom)
+        beg = int(f[1]) - 1
+        end = beg + max(len(f[3]), 1)
+        v0, v1 = voff(start), voff(min(pos, len(data)))
+        chunks = bins[t].setdefault(bamio._reg2bin(beg, end), [])
+        if chunks and chunks[-1][1] == v0:
+            chunks[-1][1] = v1
+        else:
+            chunks.append([v0, v1])
+        for w in range(beg >> 14, ((end - 1) >> 14) + 1):
+            linear[t].setdefault(w, v0)
+    nm = b"".join(n.encode() + b"\0" for n in names)
+    out = bytearray(b"TBI\1" + struct.pack("<iiiiiii", len(names), 2, 1, 2, 0, ord("#"), 0) +
+                    struct.pack("<i", len(nm)) + nm)
+    for t in range(len(names)):
+        out += struct.pack("<i", len(bins[t]))
+        for b in sorted(bins[t]):
+            out += struct.pack("<Ii", b, len(bins[t][b]))
+            for v0, v1 in bins[t][b]:
+                out += struct.pack("<QQ", v0, v1)
+        n_intv = (max(linear[t]) + 1) if linear[t] else 0
+        out += struct.pack("<i", n_intv)
+        last = 0
+        for w in range(n_intv):
+            last = linear[t].get(w, last)
+            out += struct.pack("<Q", last)
+    _bgzf_write(vcf_gz + ".tbi", bytes(out))
 
 
 def _fmt_value(key, ann):
@@ -286,7 +342,7 @@ def _write_annotated_vcf(input_vcf, output_vcf, annotations, proband_id=None):
     """Annotated VCF, bgzip-compressed (reference ``:813-1304``).  FORMAT fields on
     the proband's sample when it is in the VCF, INFO fields otherwise.  Records
     and header are passed through textually; the new header lines go last, as
-    htslib appends them.  (No tabix index is written: there is no htslib here.)"""
+    htslib appends them; a ``.tbi`` tabix index is written beside the output."""
     samples = _vcf_samples(input_vcf)
     use_format = proband_id is not None and proband_id in samples
     if proband_id is not None and not use_format:
@@ -326,7 +382,8 @@ def _write_annotated_vcf(input_vcf, output_vcf, annotations, proband_id=None):
             out.append("\t".join(f))
     if not output_vcf.endswith(".gz"):
         output_vcf += ".gz"
-    _bgzf_write(output_vcf, ("\n".join(out) + "\n").encode())
+    data = ("\n".join(out) + "\n").encode()
+    _write_tabix_index(output_vcf, data, _bgzf_write(output_vcf, data))
     return output_vcf
 
 

@@ -125,3 +125,41 @@ def test_read_helpers_known_answers():
     dele = MockRead("ACGTAGTAC", 100, [(0, 5), (2, 1), (0, 4)])
     assert read_supports_alt(dele, 104, "AC", "A") and not read_supports_alt(dele, 104, "AC", "AC")
     assert not read_supports_alt(lowq, 104, "A", "A", min_baseq=20)
+
+
+def test_tabix_index_structure(oracle_run, giab_paths, tmp_path):
+    """The .tbi beside the annotated VCF: header fields of the VCF preset, one
+    sequence entry per contig in file order, chunks that start at record lines."""
+    import struct
+    variants, ann, _m, _f = oracle_run
+    out = P._write_annotated_vcf(giab_paths["vcf"], str(tmp_path / "a.vcf.gz"), ann, "HG002")
+    tbi = gzip.open(out + ".tbi", "rb").read()
+    assert tbi[:4] == b"TBI\x01"
+    n_ref, fmt, col_seq, col_beg, col_end, meta, skip, l_nm = struct.unpack_from("<8i", tbi, 4)
+    assert (fmt, col_seq, col_beg, col_end, meta, skip) == (2, 1, 2, 0, ord("#"), 0)
+    names = tbi[36:36 + l_nm].split(b"\0")[:-1]
+    want_names = []
+    for v in variants:
+        if v["chrom"].encode() not in want_names:
+            want_names.append(v["chrom"].encode())
+    assert names == want_names and n_ref == len(names)
+    # walk the index: every chunk's virtual offset points at the start of a record line
+    raw = open(out, "rb").read()
+    text = gzip.open(out, "rb").read()
+    off = 36 + l_nm
+    n_chunks = 0
+    import zlib
+    for _ in range(n_ref):
+        n_bin = struct.unpack_from("<i", tbi, off)[0]; off += 4
+        for _b in range(n_bin):
+            _bin, n_chunk = struct.unpack_from("<Ii", tbi, off); off += 8
+            for _c in range(n_chunk):
+                v0, v1 = struct.unpack_from("<QQ", tbi, off); off += 16
+                blk, within = v0 >> 16, v0 & 0xFFFF
+                bsize = struct.unpack_from("<H", raw, blk + 16)[0] + 1
+                payload = zlib.decompress(raw[blk + 18:blk + bsize - 8], -15)
+                assert payload[within:within + 3] == b"chr" and v0 < v1
+                n_chunks += 1
+        n_intv = struct.unpack_from("<i", tbi, off)[0]; off += 4 + 8 * n_intv
+    assert n_chunks >= n_ref and off == len(tbi)
+    assert text.count(b"\nchr") == len(variants)
