@@ -261,6 +261,11 @@ int kdf_bin_stream_to(const kdf_stream* s, int k, int by_owner, int n_parts,
                       uint64_t* const* bin_ptrs /*DEV*/, uint64_t bin_cap,
                       uint64_t* cursors /*DEV*/, uint64_t* overflow /*DEV*/,
                       uint64_t* stats /*DEV or NULL*/, void* stream);
+int kdf_bin_stream_to_range(const kdf_stream* s, uint64_t first_word, uint64_t n_words, int k,
+                            int by_owner, int n_parts, uint64_t* const* bin_ptrs /*DEV*/,
+                            uint64_t bin_cap, uint64_t* cursors /*DEV*/,
+                            uint64_t* overflow /*DEV*/, uint64_t* stats /*DEV or NULL*/,
+                            void* stream);
 int kdf_bin_keys(const uint64_t* lo /*DEV*/, const uint64_t* hi /*DEV or NULL*/, uint64_t n,
                  int k, int by_owner, int n_parts, uint64_t* bins /*DEV*/, uint64_t bin_cap,
                  uint64_t* cursors /*DEV*/, uint64_t* overflow /*DEV*/, void* stream);

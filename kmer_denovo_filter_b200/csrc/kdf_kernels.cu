@@ -1569,10 +1569,18 @@ int kdf_bin_stream(const kdf_stream* s, int k, int by_owner, int n_parts, uint64
 int kdf_bin_stream_to(const kdf_stream* s, int k, int by_owner, int n_parts,
                       uint64_t* const* bin_ptrs, uint64_t bin_cap, uint64_t* cursors,
                       uint64_t* overflow, uint64_t* stats, void* stream) {
+  return kdf_bin_stream_to_range(s, 0, ~0ull, k, by_owner, n_parts, bin_ptrs, bin_cap, cursors,
+                                 overflow, stats, stream);
+}
+
+int kdf_bin_stream_to_range(const kdf_stream* s, uint64_t first_word, uint64_t n_words, int k,
+                            int by_owner, int n_parts, uint64_t* const* bin_ptrs, uint64_t bin_cap,
+                            uint64_t* cursors, uint64_t* overflow, uint64_t* stats, void* stream) {
   if (!s || !bin_ptrs || !cursors || !overflow)
     return fail(KDF_ERR_ARG, "kdf_bin_stream_to: NULL argument");
   BinDest dst = {nullptr, (u64* const*)bin_ptrs, bin_cap};
-  return bin_stream_impl(s, k, by_owner, n_parts, dst, cursors, overflow, stats, stream);
+  return bin_stream_impl(s, k, by_owner, n_parts, dst, cursors, overflow, stats, stream, first_word,
+                         n_words);
 }
 
 int kdf_bin_stream_range(const kdf_stream* s, uint64_t first_word, uint64_t n_words, int k,

@@ -166,8 +166,17 @@ def route_composite_p2p(eng, streams, k, world, role, n_local, n_expected):
         overflow = torch.zeros(1, dtype=torch.int64, device=eng.device)
         st = eng.new_stats()
         hdl.barrier(channel=0)          # every peer is done reading its buffer from the last use
+        main = torch.cuda.current_stream(eng.device)
         for s in streams:
-            eng.bin_stream_to(s, k, ptrs, seg_cap, cursors, overflow, by_owner=world, stats=st)
+            if getattr(s, "chunks", None):           # bin each chunk as soon as it has landed
+                for first, n, ev in s.chunks:
+                    main.wait_event(ev)
+                    eng.bin_stream_to(s, k, ptrs, seg_cap, cursors, overflow, by_owner=world,
+                                      stats=st, word_range=(first, n))
+            else:
+                if getattr(s, "ready", None) is not None:
+                    main.wait_event(s.ready)
+                eng.bin_stream_to(s, k, ptrs, seg_cap, cursors, overflow, by_owner=world, stats=st)
         hdl.barrier(channel=1)          # every peer's writes into this rank's buffer have landed
         need = torch.stack([cursors.max(), overflow[0]]).to(torch.int64)
         allreduce(need, "max")
@@ -290,12 +299,19 @@ def discover_streams_dist(eng, child, mother, father, ref, k, min_child_count=3,
         min_distinct_kmers_per_read = max(1, k // 4)
     stats = eng.new_stats()
     up = _kc._Uploader(eng)
-    d_child, ev_child = up.put(child, True)
-    d_ref, ev_ref = up.put(ref, False)
+    if peer_memory_available(eng):
+        # fused route: the child is copied in chunks and binned (= sent) as it lands
+        d_child, ev_child = up.put_chunked(child, False)
+        d_ref, ev_ref = up.put(ref, False)
+        ev_reads = up.put_read_index(d_child, child)
+    else:
+        d_child, ev_child = up.put(child, True)
+        d_ref, ev_ref = up.put(ref, False)
+        ev_reads = None
+        up.wait(ev_child)
+        up.wait(ev_ref)
     d_mother, ev_mother = up.put(mother, False)
     d_father, ev_father = up.put(father, False)
-    up.wait(ev_child)
-    up.wait(ev_ref)
 
     c = count_child_dist(eng, [d_child], [d_ref], k, min_child_count, world)
     tot = torch.tensor([c["candidates"], c["child_distinct"]], dtype=torch.int64, device=eng.device)
@@ -323,6 +339,8 @@ def discover_streams_dist(eng, child, mother, father, ref, k, min_child_count=3,
     if n_pu:
         out["pu"] = KmerSet(eng, k, lo, hi)
         pt = _kc._primed_table(eng, k, lo, hi, n_pu)
+        up.wait(ev_child)
+        up.wait(ev_reads)
         sp = eng.scan_reads_sparse(pt, d_child, stats=stats)
         pt.close()
         out["reads"] = sp

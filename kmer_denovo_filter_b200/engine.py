@@ -74,6 +74,8 @@ _SIGNATURES = {
     "kdf_bin_stream": (_i, [ctypes.POINTER(_Stream), _i, _i, _i, _vp, _u64, _vp, _vp, _vp, _vp]),
     "kdf_bin_stream_range": (_i, [ctypes.POINTER(_Stream), _u64, _u64, _i, _i, _i, _vp, _u64, _vp, _vp,
                                   _vp, _vp]),
+    "kdf_bin_stream_to_range": (_i, [ctypes.POINTER(_Stream), _u64, _u64, _i, _i, _i, _vp, _u64, _vp,
+                                     _vp, _vp, _vp]),
     "kdf_bin_stream_to": (_i, [ctypes.POINTER(_Stream), _i, _i, _i, _vp, _u64, _vp, _vp, _vp, _vp]),
     "kdf_bin_keys": (_i, [_vp, _vp, _u64, _i, _i, _i, _vp, _u64, _vp, _vp, _vp]),
     "kdf_count_bins": (_i, [_i, _i, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _u64, _u32, _u32, _u32, _u32,
@@ -716,13 +718,16 @@ class CudaEngine:
         self._t1("bin_stream/kw%d" % bins.key_words, ev)
         self.launches += 1
 
-    def bin_stream_to(self, ds, k, bin_ptrs, bin_cap, cursors, overflow, by_owner=1, stats=None):
+    def bin_stream_to(self, ds, k, bin_ptrs, bin_cap, cursors, overflow, by_owner=1, stats=None,
+                      word_range=None):
         """K6 fused with the transfer: bin p goes to ``bin_ptrs[p]`` (device int64
         tensor of raw pointers, possibly peer memory over NVLink).  ``by_owner``: 1 =
         one bin per owner rank, R >= 2 = composite R owners x hash ranges."""
         ev = self._t0()
-        self._check(self.lib.kdf_bin_stream_to(
-            ds.c(), int(k), int(by_owner), int(bin_ptrs.shape[0]), bin_ptrs.data_ptr(),
+        first, n = word_range if word_range is not None else (0, (ds.n_bases + 31) // 32)
+        self._check(self.lib.kdf_bin_stream_to_range(
+            ds.c(), int(first), int(n), int(k), int(by_owner), int(bin_ptrs.shape[0]),
+            bin_ptrs.data_ptr(),
             int(bin_cap), cursors.data_ptr(), overflow.data_ptr(),
             stats.data_ptr() if stats is not None else None, self.stream_ptr()))
         self._t1("bin_stream_to_peers/kw%d" % self.lib.kdf_key_words(int(k)), ev)
