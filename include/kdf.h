@@ -295,8 +295,11 @@ int kdf_count_bins(int k, int n_parts, const uint64_t* child_bins /*DEV*/,
 
 /* The same with the bins of n_src sources (multi-GPU: one region per sending
  * rank, filled by kdf_bin_stream_to): bins are laid out [source][hash range]
- * [bin_cap] and cursors [source][hash range].                                 */
-int kdf_count_bins_multi(int k, int n_parts, int n_src, const uint64_t* child_bins /*DEV*/,
+ * [bin_cap] and cursors [source][hash range].  sub_split (a power of two) counts
+ * every bin in that many passes, each over one sub-range of its hashes, so that the
+ * table slice can stay L2-sized when there are few, large bins.                */
+int kdf_count_bins_multi(int k, int n_parts, int n_src, int sub_split,
+                         const uint64_t* child_bins /*DEV*/,
                          uint64_t child_bin_cap, const uint64_t* child_cursors /*DEV*/,
                          const uint64_t* ref_bins /*DEV or NULL*/, uint64_t ref_bin_cap,
                          const uint64_t* ref_cursors /*DEV or NULL*/, void* slice /*DEV*/,

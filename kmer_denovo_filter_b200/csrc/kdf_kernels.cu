@@ -477,10 +477,12 @@ template <> __device__ __forceinline__ Key<2> ld_key_stream<2>(const u64* lo, co
   return k;
 }
 
-template <int KW, int OP>
+template <int KW, int OP, bool FILT>
 __global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_update_keys(TableView<KW> t, const u64* lo, const u64* hi,
                                                      u64 n_max, const u64* n_dev, int plane, u32 arg,
-                                                     u64* stats) {
+                                                     u64* stats, int filt_log2, u32 filt_val) {
+  // filt_log2 > 0: only keys of hash range filt_val (of 2^filt_log2) are applied — a
+  // bin that spans several table slices is streamed once per slice
   constexpr int CHUNK = KDF_KEYS_CHUNK;
   constexpr bool kInsert = (OP == OP_INSERT_COUNT || OP == OP_INSERT_ONLY);
   constexpr int S = SPB<KW>::v;
@@ -515,8 +517,13 @@ __global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_update_keys(TableView<
 #pragma unroll
     for (int u = 0; u < CHUNK; ++u) {
       if (okm & (1u << u)) {
-        bidx[u] = bucket_of(hash_key(keys[u]), t.log2_parts, t.n_buckets);
-        bk[u] = ld_bucket<KW>(t.keys + (u64)bidx[u] * 4 * KW);
+        u64 h = hash_key(keys[u]);
+        if (FILT && part_of(h, filt_log2) != filt_val) {
+          okm &= ~(1u << u);
+        } else {
+          bidx[u] = bucket_of(h, t.log2_parts, t.n_buckets);
+          bk[u] = ld_bucket<KW>(t.keys + (u64)bidx[u] * 4 * KW);
+        }
       }
     }
     st.windows += __popc(okm);
@@ -1194,10 +1201,17 @@ static int dispatch_stream(const kdf_table* t, const StreamView& v, int op, int 
 
 template <int KW, int OP>
 static int launch_update_keys(const kdf_table* t, const u64* lo, const u64* hi, u64 n_max,
-                              const u64* n_dev, int plane, u32 arg, u64* stats, cudaStream_t st) {
+                              const u64* n_dev, int plane, u32 arg, u64* stats, cudaStream_t st,
+                              int filt_log2 = 0, u32 filt_val = 0) {
   TableView<KW> tv = view_of_table<KW>(t);
-  int g = grid_for((const void*)k_update_keys<KW, OP>, 256, 0, (n_max + KDF_KEYS_CHUNK - 1) / KDF_KEYS_CHUNK, t->sm_count);
-  k_update_keys<KW, OP><<<g, 256, 0, st>>>(tv, lo, hi, n_max, n_dev, plane, arg, stats);
+  if (filt_log2 > 0) {
+    int g = grid_for((const void*)k_update_keys<KW, OP, true>, 256, 0, (n_max + KDF_KEYS_CHUNK - 1) / KDF_KEYS_CHUNK, t->sm_count);
+    k_update_keys<KW, OP, true><<<g, 256, 0, st>>>(tv, lo, hi, n_max, n_dev, plane, arg, stats, filt_log2,
+                                                   filt_val);
+  } else {
+    int g = grid_for((const void*)k_update_keys<KW, OP, false>, 256, 0, (n_max + KDF_KEYS_CHUNK - 1) / KDF_KEYS_CHUNK, t->sm_count);
+    k_update_keys<KW, OP, false><<<g, 256, 0, st>>>(tv, lo, hi, n_max, n_dev, plane, arg, stats, 0, 0);
+  }
   CUDA_TRY(cudaGetLastError());
   return KDF_OK;
 }
@@ -1682,13 +1696,13 @@ int kdf_count_bins(int k, int n_parts, const uint64_t* child_bins, uint64_t chil
                    uint32_t min0, uint32_t max0, uint32_t min1, uint32_t max1, uint64_t* out_lo,
                    uint64_t* out_hi, uint32_t* out_p0, uint32_t* out_p1, uint64_t out_cap,
                    uint64_t* n_out, uint32_t count_min0, uint64_t* counters, void* stream) {
-  return kdf_count_bins_multi(k, n_parts, 1, child_bins, child_bin_cap, child_cursors, ref_bins,
+  return kdf_count_bins_multi(k, n_parts, 1, 1, child_bins, child_bin_cap, child_cursors, ref_bins,
                               ref_bin_cap, ref_cursors, slice, slice_capacity, min0, max0, min1, max1,
                               out_lo, out_hi, out_p0, out_p1, out_cap, n_out, count_min0, counters,
                               stream);
 }
 
-int kdf_count_bins_multi(int k, int n_parts, int n_src, const uint64_t* child_bins,
+int kdf_count_bins_multi(int k, int n_parts, int n_src, int sub_split, const uint64_t* child_bins,
                          uint64_t child_bin_cap, const uint64_t* child_cursors,
                          const uint64_t* ref_bins, uint64_t ref_bin_cap, const uint64_t* ref_cursors,
                          void* slice, uint64_t slice_capacity, uint32_t min0, uint32_t max0,
@@ -1698,6 +1712,10 @@ int kdf_count_bins_multi(int k, int n_parts, int n_src, const uint64_t* child_bi
   if (!child_bins || !child_cursors || !slice || !n_out || !counters)
     return fail(KDF_ERR_ARG, "kdf_count_bins: NULL argument");
   if (n_src < 1) return fail(KDF_ERR_ARG, "kdf_count_bins: n_src must be >= 1");
+  int log2s = 0;
+  while ((1 << log2s) < sub_split) ++log2s;
+  if (sub_split < 1 || sub_split > 64 || (1 << log2s) != sub_split)
+    return fail(KDF_ERR_ARG, "kdf_count_bins: sub_split must be a power of two <= 64");
   int rc = check_table_args(k, slice_capacity, slice, "kdf_count_bins");
   if (rc != KDF_OK) return rc;
   int log2p = 0;
@@ -1710,21 +1728,23 @@ int kdf_count_bins_multi(int k, int n_parts, int n_src, const uint64_t* child_bi
   t.capacity = slice_capacity;
   t.base = slice;
   t.sm_count = current_sm_count();
-  t.log2_parts = log2p;
+  t.log2_parts = log2p + log2s;  // a slice covers one of n_parts * sub_split hash ranges
+  const int filt_log2 = sub_split > 1 ? log2p + log2s : 0;
   cudaStream_t st = (cudaStream_t)stream;
   u64* ctr = (u64*)counters;  // [0..3] = stats block (windows = keys applied, full, hits, new), [4] = #(p0 >= count_min0), [5] = #occupied
   const int kw = t.key_words;
   rc = clear_table_async(&t, st);  // once: every emit pass leaves the slice clean
   if (rc != KDF_OK) return rc;
-  for (int p = 0; p < n_parts; ++p) {
+  for (int pf = 0; pf < n_parts * sub_split; ++pf) {
+    const int p = pf / sub_split;   // the bin; pf = the slice's hash range
     // bins are laid out [source][hash range][bin_cap]: one insert pass per source
     for (int sidx = 0; sidx < n_src; ++sidx) {
       u64 b = (u64)sidx * n_parts + p;
       const u64* cb = (const u64*)child_bins + b * child_bin_cap * kw;
       if (kw == 1)
-        rc = launch_update_keys<1, OP_INSERT_COUNT>(&t, cb, nullptr, child_bin_cap, (const u64*)child_cursors + b, 0, 1, ctr, st);
+        rc = launch_update_keys<1, OP_INSERT_COUNT>(&t, cb, nullptr, child_bin_cap, (const u64*)child_cursors + b, 0, 1, ctr, st, filt_log2, (u32)pf);
       else
-        rc = launch_update_keys<2, OP_INSERT_COUNT>(&t, cb, nullptr, child_bin_cap, (const u64*)child_cursors + b, 0, 1, ctr, st);
+        rc = launch_update_keys<2, OP_INSERT_COUNT>(&t, cb, nullptr, child_bin_cap, (const u64*)child_cursors + b, 0, 1, ctr, st, filt_log2, (u32)pf);
       if (rc != KDF_OK) return rc;
     }
     if (ref_bins && ref_cursors) {
@@ -1732,9 +1752,9 @@ int kdf_count_bins_multi(int k, int n_parts, int n_src, const uint64_t* child_bi
         u64 b = (u64)sidx * n_parts + p;
         const u64* rb = (const u64*)ref_bins + b * ref_bin_cap * kw;
         if (kw == 1)
-          rc = launch_update_keys<1, OP_MARK_IF_PRESENT>(&t, rb, nullptr, ref_bin_cap, (const u64*)ref_cursors + b, 1, 1, nullptr, st);
+          rc = launch_update_keys<1, OP_MARK_IF_PRESENT>(&t, rb, nullptr, ref_bin_cap, (const u64*)ref_cursors + b, 1, 1, nullptr, st, filt_log2, (u32)pf);
         else
-          rc = launch_update_keys<2, OP_MARK_IF_PRESENT>(&t, rb, nullptr, ref_bin_cap, (const u64*)ref_cursors + b, 1, 1, nullptr, st);
+          rc = launch_update_keys<2, OP_MARK_IF_PRESENT>(&t, rb, nullptr, ref_bin_cap, (const u64*)ref_cursors + b, 1, 1, nullptr, st, filt_log2, (u32)pf);
         if (rc != KDF_OK) return rc;
       }
     }

@@ -249,16 +249,19 @@ def _count_child_fused(eng, child_streams, ref_streams, k, min_child_count, worl
                          dtype=torch.int64, device=eng.device)
     allreduce(n_exp, "max")              # weak scaling: a rank receives about what it sends
     n_child_exp, n_ref_exp = int(n_exp[0].item()), int(n_exp[1].item())
-    n_local, slice_capacity = _kc.plan_partitions(max(n_child_exp, 1), key_words=kw)
-    n_local = max(1, min(n_local, 512 // _kc._pow2_at_least(world)))
-    slice_capacity = max(slice_capacity, ((max(n_child_exp, 1) // 8 + n_local - 1) // n_local + 3) & ~3)
+    # L2-sized slices want n_plan hash ranges; the binning kernel is fastest with at
+    # most 256 (owner x range) bins, so with many ranks a bin spans `sub` slices and
+    # is counted in `sub` passes (kdf_count_bins_multi sub_split)
+    n_plan, slice_capacity = _kc.plan_partitions(max(n_child_exp, 1), key_words=kw)
+    n_local = max(1, min(n_plan, 256 // _kc._pow2_at_least(world)))
+    sub = max(1, n_plan // n_local)
     cb, c_win = route_composite_p2p(eng, child_streams, k, world, "child", n_local, n_child_exp)
     rb, r_win = route_composite_p2p(eng, ref_streams, k, world, "ref", n_local, n_ref_exp)
     n_child = int(cb.cursors.sum().item())
     out_cap = max(1 << 16, n_child // 64)
     while True:
         res = eng.count_bins(cb, rb, slice_capacity, min0=min_child_count, max1=0,
-                             count_min0=min_child_count, out_cap=out_cap)
+                             count_min0=min_child_count, out_cap=out_cap, sub_split=sub)
         if res["full"]:
             if slice_capacity >= 2 * cb.bin_cap * world:
                 raise _engine.KdfError("child k-mer table slice full at %d slots" % slice_capacity)

@@ -80,7 +80,7 @@ _SIGNATURES = {
     "kdf_bin_keys": (_i, [_vp, _vp, _u64, _i, _i, _i, _vp, _u64, _vp, _vp, _vp]),
     "kdf_count_bins": (_i, [_i, _i, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _u64, _u32, _u32, _u32, _u32,
                             _vp, _vp, _vp, _vp, _u64, _vp, _u32, _vp, _vp]),
-    "kdf_count_bins_multi": (_i, [_i, _i, _i, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _u64, _u32, _u32, _u32,
+    "kdf_count_bins_multi": (_i, [_i, _i, _i, _i, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _u64, _u32, _u32, _u32,
                                   _u32, _vp, _vp, _vp, _vp, _u64, _vp, _u32, _vp, _vp]),
     "kdf_debug_hash_host": (_i, [_vp, _vp, _u64, _i, _i, _u32, _u32, _vp, _vp, _vp]),
     "kdf_pack_sequences": (_u64, [_vp, _vp, _u64, _vp, _vp, _vp]),
@@ -746,7 +746,7 @@ class CudaEngine:
         self.launches += 1
 
     def count_bins(self, child_bins, ref_bins, slice_capacity, min0=0, max0=U32_MAX, min1=0,
-                   max1=U32_MAX, count_min0=0, out_cap=1 << 20, want_planes=False):
+                   max1=U32_MAX, count_min0=0, out_cap=1 << 20, want_planes=False, sub_split=1):
         """Count every bin in an L2-resident slice and emit (see include/kdf.h).
         Returns dict(n_out, lo, hi, p0, p1, keys, full, hits, distinct, n_count, occupied);
         lo/hi/p0/p1 hold min(n_out, out_cap) entries."""
@@ -766,7 +766,8 @@ class CudaEngine:
         if ref_bins is not None and getattr(ref_bins, "n_src", 1) != n_src:
             raise KdfError("count_bins: child and reference bins must have the same sources")
         self._check(self.lib.kdf_count_bins_multi(
-            k, child_bins.n_parts, n_src, child_bins.data.data_ptr(), child_bins.bin_cap,
+            k, child_bins.n_parts, n_src, int(sub_split), child_bins.data.data_ptr(),
+            child_bins.bin_cap,
             child_bins.cursors.data_ptr(),
             ref_bins.data.data_ptr() if ref_bins is not None else None,
             ref_bins.bin_cap if ref_bins is not None else 0,
@@ -776,7 +777,8 @@ class CudaEngine:
             p0.data_ptr() if p0 is not None else None, p1.data_ptr() if p1 is not None else None,
             out_cap, n_out.data_ptr(), count_min0, ctr.data_ptr(), self.stream_ptr()))
         self._t1("count_bins/kw%d" % kw, ev)
-        self.launches += 2 + child_bins.n_parts * (1 + n_src * (1 + (1 if ref_bins is not None else 0)))
+        self.launches += 2 + child_bins.n_parts * int(sub_split) * (
+            1 + n_src * (1 + (1 if ref_bins is not None else 0)))
         c = ctr.cpu().numpy().view(np.uint64)
         n = int(n_out.item())
         m = min(n, out_cap)

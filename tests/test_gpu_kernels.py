@@ -350,6 +350,16 @@ def test_count_bins_equals_direct_table(eng, k, n_parts):
     p1 = res["p1"].cpu().numpy().view(np.uint32).tolist()
     assert dict(zip(keys, p0)) == want
     assert {key for key, f in zip(keys, p1) if f} == set(want) & set(refk)
+    # the same bins counted in sub-range passes (a bin spanning several table slices)
+    if n_parts == 8:
+        for sub in (2, 8):
+            rs = eng.count_bins(cb, rb, slice_capacity=2 * len(want) // (n_parts * sub) + 64,
+                                want_planes=True, count_min0=3, out_cap=len(want) + 10, sub_split=sub)
+            assert rs["full"] == 0 and rs["keys"] == n_win and rs["distinct"] == len(want)
+            ks = eng.keys_to_pyints(rs["lo"], rs["hi"])
+            assert dict(zip(ks, rs["p0"].cpu().numpy().view(np.uint32).tolist())) == want
+            assert {key for key, f in zip(ks, rs["p1"].cpu().numpy().view(np.uint32).tolist()) if f} == \
+                set(want) & set(refk)
     # thresholded emit: count >= 3 and not in the reference; undersized output is reported
     res2 = eng.count_bins(cb, rb, slice_capacity=2 * len(want) // n_parts + 64, min0=3, max1=0,
                           out_cap=len(want) + 10)
