@@ -249,11 +249,12 @@ def _count_child_fused(eng, child_streams, ref_streams, k, min_child_count, worl
                          dtype=torch.int64, device=eng.device)
     allreduce(n_exp, "max")              # weak scaling: a rank receives about what it sends
     n_child_exp, n_ref_exp = int(n_exp[0].item()), int(n_exp[1].item())
-    # L2-sized slices want n_plan hash ranges; the binning kernel is fastest with at
-    # most 256 (owner x range) bins, so with many ranks a bin spans `sub` slices and
-    # is counted in `sub` passes (kdf_count_bins_multi sub_split)
+    # L2-sized slices want n_plan hash ranges; the binning kernel takes at most 512
+    # (owner x range) bins, so beyond 8 ranks a bin spans `sub` slices and is counted
+    # in `sub` passes (kdf_count_bins_multi sub_split).  Measured at 8 ranks: 512 bins
+    # (bin + send 43.5 ms, count 33.8 ms) and 256 bins x 2 passes (31.2 + 48.1 ms) tie.
     n_plan, slice_capacity = _kc.plan_partitions(max(n_child_exp, 1), key_words=kw)
-    n_local = max(1, min(n_plan, 256 // _kc._pow2_at_least(world)))
+    n_local = max(1, min(n_plan, 512 // _kc._pow2_at_least(world)))
     sub = max(1, n_plan // n_local)
     cb, c_win = route_composite_p2p(eng, child_streams, k, world, "child", n_local, n_child_exp)
     rb, r_win = route_composite_p2p(eng, ref_streams, k, world, "ref", n_local, n_ref_exp)
