@@ -58,46 +58,13 @@ def _parse_hash_size(text):
     return int(float(t) * mult)
 
 
-def _estimate_table_keys(bam_path, hbm_free_bytes, slot_bytes):
-    """Initial distinct-k-mer estimate for a BAM: ~4 bases per compressed byte,
-    one distinct k-mer per 4 bases, floor 1M; capped so the table uses at most
-    60 % of free HBM.  The count loop grows the table when this is too small."""
-    try:
-        size = os.path.getsize(bam_path)
-    except OSError:
-        size = 1 << 28
-    est = max(size, 1_000_000)
-    cap = int(hbm_free_bytes * 0.6 / slot_bytes / 2)
-    return max(min(est, cap), 1024)
-
-
-def _rehash(eng, table, new_capacity):
-    """Grow a table (Jellyfish's analogue: spill to ``.jf_N`` + ``merge``,
-    reference ``:59-70, 335-366``; here nothing is ever spilled or dropped)."""
-    n, lo, hi, p0, p1 = eng.threshold_compact(table, want_planes=True)
-    big = eng.new_table(table.k, capacity=new_capacity)
-    st = eng.new_stats()
-    eng.update_keys(big, lo, hi, _engine.MODE_INSERT_ONLY, 0, 0, st)
-    eng.add_planes(big, lo, hi, p0, p1)
-    eng.check_not_full(st)
-    table.close()
-    return big
-
-
-def count_bam_into_table(eng, bam_path, table, mode, plane, threads, grow=False,
-                         batch_bases=BATCH_BASES):
-    """Stream ``samtools fasta -F 0xD00``-equivalent reads of a BAM through
-    K1+K2.  Returns ``(table, stats dict)``; with ``grow`` the table is
-    re-hashed into a larger one before any batch could overfill it."""
+def count_bam_into_table(eng, bam_path, table, mode, plane, threads, batch_bases=BATCH_BASES):
+    """Stream ``samtools fasta -F 0xD00``-equivalent reads of a BAM through K1+K2
+    against ``table`` (filtered parent counts: the table is primed with the filter
+    set and never grows).  Returns ``(table, stats dict)``."""
     total = {"windows": 0, "hits": 0, "new": 0, "reads": 0, "bases": 0}
     with bamio.BamReader(bam_path, threads=threads) as rd:
         for batch in rd.batches(bamio.MODE_FASTA, max_bases=batch_bases):
-            if grow:
-                worst = total["new"] + batch.window_count_upper_bound(table.k)
-                if worst > 0.85 * table.capacity:
-                    new_cap = eng.capacity_for(worst)
-                    logger.info("  growing k-mer table %d -> %d slots", table.capacity, new_cap)
-                    table = _rehash(eng, table, new_cap)
             ds = eng.upload(batch, with_reads=False)
             st = eng.new_stats()
             eng.count_stream(table, ds, mode, plane, 1, st)
@@ -148,15 +115,6 @@ class RefIndex:
             if not bins.overflowed():
                 return bins
             cap = int(bins.counts().max()) + 4
-
-    def mark_present(self, eng, table, plane, stats=None):
-        """OR 1 into ``plane`` of every table key that occurs in the reference."""
-        if self.host_stream is not None:
-            ds = eng.upload(self.host_stream, with_reads=False)
-            eng.count_stream(table, ds, _engine.MODE_MARK_IF_PRESENT, plane, 1, stats)
-        else:
-            lo, hi = eng.keys_to_device(self.keys, table.key_words)
-            eng.update_keys(table, lo, hi, _engine.MODE_MARK_IF_PRESENT, plane, 1, stats)
 
 
 def read_jf_binary_sorted(path):

@@ -6,7 +6,6 @@ import os
 import socket
 
 import numpy as np
-import pytest
 import torch
 import torch.multiprocessing as mp
 
@@ -59,9 +58,8 @@ def _worker(rank, port, q):
 def _expected():
     """Single-process oracle over the union of the shards."""
     import collections
-    from fake_engine import stream_keys, unpack_stream
+    from fake_engine import stream_keys
     from kmer_denovo_filter_b200 import synth
-    from oracle import kmers
     tot = {w: collections.Counter() for w in ("child", "mother", "father")}
     units = 0
     child_streams = []

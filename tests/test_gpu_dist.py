@@ -4,7 +4,6 @@ host logic is covered on CPU by test_dist_chain_cpu.py."""
 import os
 import socket
 
-import numpy as np
 import pytest
 import torch
 import torch.multiprocessing as mp

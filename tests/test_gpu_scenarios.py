@@ -7,7 +7,7 @@ import os
 
 import pytest
 
-from helpers import create_bam, create_ref_fasta, create_vcf, simple_bam
+from helpers import create_ref_fasta, create_vcf, simple_bam
 
 pytestmark = pytest.mark.gpu
 

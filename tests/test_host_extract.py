@@ -2,7 +2,6 @@
 templates instantiated on the host (``kdf_debug_extract_host``): packing layout,
 rolling canonical k-mers (64- and 128-bit), random-access extraction, validity.
 No GPU needed; the oracle is the checker."""
-import ctypes
 import random
 import re
 

@@ -2,12 +2,11 @@
 import json
 import random
 
-import numpy as np
 import pytest
 
 from kmer_denovo_filter_b200 import engine
 from oracle import bam as obam
-from oracle import ckdf, discovery, kmers
+from oracle import ckdf, kmers
 
 
 def _pack(seqs):

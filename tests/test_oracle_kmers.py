@@ -6,7 +6,6 @@ Vectors follow the reference's own unit tests (reference
 """
 import random
 
-import numpy as np
 import pytest
 
 from oracle import kmers

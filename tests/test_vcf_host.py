@@ -2,7 +2,6 @@
 the oracle's, and its writers reproduce the reference's golden files when fed
 the (golden-pinned) oracle annotations."""
 import gzip
-import json
 import os
 
 import pytest
