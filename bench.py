@@ -56,7 +56,7 @@ def kernel_class(name):
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--k", type=int, default=31)
@@ -98,6 +98,11 @@ class ClockSampler:
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                  "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=self.fh, stderr=subprocess.DEVNULL)
+            # nvidia-smi takes a moment to print its first sample; the timed region
+            # may last only a few hundred ms, so wait until the sampler is running
+            t0 = time.time()
+            while time.time() - t0 < 15.0 and os.path.getsize(self.path) == 0:
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 

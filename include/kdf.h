@@ -282,7 +282,21 @@ int kdf_bin_keys(const uint64_t* lo /*DEV*/, const uint64_t* hi /*DEV or NULL*/,
  * counters: DEV u64[6], caller zeroes: [0] keys applied, [1] != 0 slice full
  * (results invalid: retry with a larger slice), [2] instances that found their
  * key, [3] distinct keys, [4] keys with plane0 >= count_min0, [5] occupied
- * slots seen by the emit pass.  n_out as in kdf_threshold_compact.           */
+ * slots seen by the emit pass.  n_out as in kdf_threshold_compact.
+ *
+ * Packed form.  The discovery chain discards the counts after thresholding
+ * (discovery/pipeline.py:207-226 keeps only the k-mer column of `dump -c -L`),
+ * and k is odd (utils.py:299-311), so a key leaves >= 2 spare bits in its most
+ * significant word.  When the call asks only for "plane0 >= min0" (max0 ==
+ * UINT32_MAX, out_p0 == out_p1 == NULL, min0 >= 1 fits the spare bits, min1 == 0,
+ * max1 in {0, UINT32_MAX}, count_min0 <= 1 or == min0) the slice holds keys only:
+ * a counter saturating at min0 lives in the spare bits, so every copy of a k-mer
+ * after the min0-th is a plain bucket read (no atomic, no plane traffic), and
+ * "in the reference" is one more state of that field.  Same outputs and counters;
+ * keys must be canonical (the all-T key doubles as the empty marker).
+ * kdf_count_bins_packed() says whether a call takes this form.               */
+int kdf_count_bins_packed(int k, uint32_t min0, uint32_t max0, uint32_t min1, uint32_t max1,
+                          uint32_t count_min0, int want_planes);
 int kdf_count_bins(int k, int n_parts, const uint64_t* child_bins /*DEV*/,
                    uint64_t child_bin_cap, const uint64_t* child_cursors /*DEV*/,
                    const uint64_t* ref_bins /*DEV or NULL*/, uint64_t ref_bin_cap,

@@ -26,9 +26,11 @@
 // load; CHUNK probes are issued back to back before the first is resolved.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
+#include <type_traits>
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -175,6 +177,27 @@ __device__ __forceinline__ Key<2> cas_key(u64* p, const Key<2>& val) {
       : "memory");
   return old;
 }
+// compare-and-swap of a whole slot with an explicit expected value
+__device__ __forceinline__ Key<1> cas_slot(u64* p, const Key<1>& expect, const Key<1>& val) {
+  Key<1> old;
+  old.lo = atomicCAS(p, expect.lo, val.lo);
+  return old;
+}
+__device__ __forceinline__ Key<2> cas_slot(u64* p, const Key<2>& expect, const Key<2>& val) {
+  Key<2> old;
+  asm volatile(
+      "{\n\t"
+      ".reg .b128 c, v, o;\n\t"
+      "mov.b128 c, {%2, %3};\n\t"
+      "mov.b128 v, {%4, %5};\n\t"
+      "atom.relaxed.gpu.global.cas.b128 o, [%6], c, v;\n\t"
+      "mov.b128 {%0, %1}, o;\n\t"
+      "}\n"
+      : "=l"(old.lo), "=l"(old.hi)
+      : "l"(expect.lo), "l"(expect.hi), "l"(val.lo), "l"(val.hi), "l"(p)
+      : "memory");
+  return old;
+}
 __device__ __forceinline__ bool is_empty_key(const Key<1>& k) { return k.lo == EMPTY; }
 __device__ __forceinline__ bool is_empty_key(const Key<2>& k) { return k.lo == EMPTY && k.hi == EMPTY; }
 
@@ -184,6 +207,8 @@ constexpr int OP_INSERT_ONLY = KDF_MODE_INSERT_ONLY;
 constexpr int OP_COUNT_IF_PRESENT = KDF_MODE_COUNT_IF_PRESENT;
 constexpr int OP_MARK_IF_PRESENT = KDF_MODE_MARK_IF_PRESENT;
 constexpr int OP_EMIT_HITS = 4;
+constexpr int OP_PACKED_COUNT = 5;  // packed counting (K2c below): plane = state shift, arg = sat
+constexpr int OP_PACKED_MARK = 6;
 
 struct HitSink {
   u64* pos;
@@ -215,11 +240,20 @@ __device__ __forceinline__ void on_found(const TableView<KW>& t, u64 slot, int p
   }
 }
 
+template <int KW>
+__device__ __forceinline__ u32 resolve_packed_count(const TableView<KW>& t, u32 b, const Key<KW>& key,
+                                                    int sh, u32 sat);
+template <int KW>
+__device__ __forceinline__ u32 resolve_packed_mark(const TableView<KW>& t, u32 b, const Key<KW>& key,
+                                                   int sh, u32 sat);
+
 // Finish a probe starting at bucket `b` (the rare path: a new key, a full
 // bucket, or a probing op that has to look past a full bucket).
 template <int KW, int OP>
 __device__ __forceinline__ u32 resolve_from(const TableView<KW>& t, u32 b, const Key<KW>& key,
                                             int plane, u32 arg, u64 pos, const HitSink& sink) {
+  if constexpr (OP == OP_PACKED_COUNT) return resolve_packed_count<KW>(t, b, key, plane, arg);
+  if constexpr (OP == OP_PACKED_MARK) return resolve_packed_mark<KW>(t, b, key, plane, arg);
   constexpr bool kInsert = (OP == OP_INSERT_COUNT || OP == OP_INSERT_ONLY);
   constexpr int S = SPB<KW>::v;
   for (u32 n = 0; n < t.n_buckets; ++n) {
@@ -547,6 +581,472 @@ __global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_update_keys(TableView<
   }
   tally_packed(st, sq_drain<KW, OP>(&q, t, plane, arg, sink, true));
   flush_stats(st, stats);
+}
+
+// ------------------------------------------------ K2c: packed counting -----
+// kdf_count_bins only has to answer "count >= min_child_count ?" and "in the
+// reference ?" (the counts themselves are discarded, discovery/pipeline.py:
+// 207-226), and k is odd, so a key leaves >= 2 spare bits at the top of its most
+// significant word.  The packed form keeps a SATURATING counter there and drops
+// the value planes: a slot is one word (pair), and once a k-mer has been seen
+// `sat` times every further copy is a plain bucket read — no atomic, no plane
+// sector.  At 30x that is ~21 of every 24 copies.  States of the field:
+// 1..sat = copies seen (saturating), 0 = "reached sat, then found in the
+// reference" (an occupied slot always has count >= 1, so 0 is free).  The all-ones
+// word stays the empty marker: it would be the all-T key, which is never canonical.
+// slot of the bucket holding `key` under `mask` (key bits of the most significant
+// word), or -1; `ms` receives that slot's most significant word
+__device__ __forceinline__ int match_packed(const Bucket<1>& b, const Key<1>& key, u64 mask, u64& ms) {
+  int j = -1;
+#pragma unroll
+  for (int c = 3; c >= 0; --c)
+    if ((b.q[c] & mask) == key.lo) {
+      j = c;
+      ms = b.q[c];
+    }
+  return j;
+}
+__device__ __forceinline__ int match_packed(const Bucket<2>& b, const Key<2>& key, u64 mask, u64& ms) {
+  int j = -1;
+#pragma unroll
+  for (int c = 3; c >= 0; --c)
+    if (b.q[2 * c] == key.lo && (b.q[2 * c + 1] & mask) == key.hi) {
+      j = c;
+      ms = b.q[2 * c + 1];
+    }
+  return j;
+}
+__device__ __forceinline__ bool same_packed(const Key<1>& stored, const Key<1>& key, u64 mask) {
+  return (stored.lo & mask) == key.lo;
+}
+__device__ __forceinline__ bool same_packed(const Key<2>& stored, const Key<2>& key, u64 mask) {
+  return stored.lo == key.lo && (stored.hi & mask) == key.hi;
+}
+// saturating +1 on the state field; `cur` is a (possibly stale) view of the word
+__device__ __forceinline__ void packed_bump(u64* pms, u64 cur, int sh, u32 sat) {
+  for (;;) {
+    if ((u32)(cur >> sh) >= sat) return;
+    u64 old = atomicCAS(pms, cur, cur + (1ull << sh));
+    if (old == cur) return;
+    cur = old;
+  }
+}
+
+template <int KW>
+__device__ __forceinline__ u32 resolve_packed_count(const TableView<KW>& t, u32 b, const Key<KW>& key,
+                                                    int sh, u32 sat) {
+  constexpr int S = SPB<KW>::v;
+  const u64 mask = (1ull << sh) - 1;
+  Key<KW> val = key;
+  ((u64*)&val)[KW - 1] |= 1ull << sh;  // state 1
+  for (u32 n = 0; n < t.n_buckets; ++n) {
+    Bucket<KW> bk = ld_bucket<KW>(t.keys + (u64)b * 4 * KW);
+    u64 ms = 0;
+    int j = match_packed(bk, key, mask, ms);
+    if (j >= 0) {
+      packed_bump(t.keys + ((u64)b * S + j) * KW + (KW - 1), ms, sh, sat);
+      return R_HIT;
+    }
+#pragma unroll
+    for (int c = 0; c < S; ++c) {
+      if (maybe_empty(bk, c, key)) {
+        u64 slot = (u64)b * S + c;
+        Key<KW> old = cas_key(t.keys + slot * KW, val);
+        if (is_empty_key(old)) return R_NEW;
+        if (same_packed(old, key, mask)) {  // inserted by another thread since the load
+          packed_bump(t.keys + slot * KW + (KW - 1), ((const u64*)&old)[KW - 1], sh, sat);
+          return R_HIT;
+        }
+      }
+    }
+    b = (b + 1 == t.n_buckets) ? 0 : b + 1;
+  }
+  return R_FULL;
+}
+
+template <int KW>
+__device__ __forceinline__ u32 resolve_packed_mark(const TableView<KW>& t, u32 b, const Key<KW>& key,
+                                                   int sh, u32 sat) {
+  constexpr int S = SPB<KW>::v;
+  const u64 mask = (1ull << sh) - 1;
+  for (u32 n = 0; n < t.n_buckets; ++n) {
+    Bucket<KW> bk = ld_bucket<KW>(t.keys + (u64)b * 4 * KW);
+    u64 ms = 0;
+    int j = match_packed(bk, key, mask, ms);
+    if (j >= 0) {
+      if ((u32)(ms >> sh) == sat) atomicAnd(t.keys + ((u64)b * S + j) * KW + (KW - 1), mask);
+      return R_HIT;
+    }
+    if (has_empty(bk, key, false)) return R_MISS;
+    b = (b + 1 == t.n_buckets) ? 0 : b + 1;
+  }
+  return R_FULL;
+}
+
+// k_update_keys for the packed form: OP_PACKED_COUNT inserts / bumps the child's
+// keys, OP_PACKED_MARK turns "saturated" into "saturated, in the reference".
+//
+// The grid fills the machine once, so a thread walks ~80 chunks one after the other
+// and the latencies of a chunk would add up: key load (DRAM) -> bucket load (L2) ->
+// CAS.  The loop is therefore software-pipelined three deep: while chunk A is
+// resolved, the bucket loads of chunk B and the key loads of chunk C are in flight.
+template <int KW> __device__ __forceinline__ Key<KW> ld_key_pinned(const u64* lo, u64 i);
+template <> __device__ __forceinline__ Key<1> ld_key_pinned<1>(const u64* lo, u64 i) {
+  Key<1> k;
+  asm volatile("ld.global.cs.u64 %0, [%1];" : "=l"(k.lo) : "l"(lo + i) : "memory");
+  return k;
+}
+template <> __device__ __forceinline__ Key<2> ld_key_pinned<2>(const u64* lo, u64 i) {
+  Key<2> k;  // interleaved {lo, hi} pairs (bins)
+  asm volatile("ld.global.cs.v2.u64 {%0,%1}, [%2];" : "=l"(k.lo), "=l"(k.hi) : "l"(lo + 2 * i) : "memory");
+  return k;
+}
+
+// Per-warp queue of the atomics a packed count still owes.  In the stream of a bin
+// only ~1 key in 6 needs one (a new key, or a copy that has not saturated yet), so
+// done in place they would run with a handful of lanes and the warp would sit out a
+// full L2 round trip for each of them.  Lanes queue them instead — with everything
+// the first attempt needs, so no bucket is read again — and the warp drains the queue
+// 128 at a time: four compare-and-swaps per lane in flight together (one instruction
+// site for bumps and inserts alike, so no result is waited for before the last one is
+// issued), results checked afterwards.  What the first attempt cannot settle (the slot
+// was taken meanwhile, the home bucket was full) goes to the SlowQueue, whose drain
+// probes from scratch with every lane busy.
+constexpr int PQ_CAP = 256;
+constexpr int PQ_DRAIN = 128;
+template <int KW> struct PackedQueue {
+  u64 lo[PQ_CAP];
+  u64 hi[KW == 2 ? PQ_CAP : 1];
+  u64 expect[PQ_CAP];  // bump: the state word as read; insert: unused
+  u32 b[PQ_CAP];       // home bucket
+  u32 info[PQ_CAP];    // kind (1 bump, 2 insert) | slot << 2
+  u32 count;
+};
+template <int KW> struct PackedQueues {
+  PackedQueue<KW> fast;
+  SlowQueue<KW> slow;
+};
+
+template <int KW>
+__device__ __forceinline__ bool pq_push(PackedQueue<KW>& q, const Key<KW>& key, u32 b, u32 info, u64 expect) {
+  u32 o = atomicAdd(&q.count, 1u);
+  if (o >= (u32)PQ_CAP) return false;  // full: the caller resolves in place
+  q.lo[o] = key.lo;
+  if (KW == 2) q.hi[o] = ((const u64*)&key)[KW - 1];
+  q.expect[o] = expect;
+  q.b[o] = b;
+  q.info[o] = info;
+  return true;
+}
+
+// all lanes of the warp: drain batches of PQ_DRAIN (or everything when `all`);
+// returns fresh << 10 | full << 20 | hits (the tallies of the resolved items)
+template <int KW>
+__device__ __noinline__ u32 pq_drain(PackedQueues<KW>* qp, TableView<KW> t, int sh, u32 sat, bool all) {
+  constexpr int S = SPB<KW>::v;
+  constexpr int R = PQ_DRAIN / 32;
+  PackedQueue<KW>& q = qp->fast;
+  const unsigned lane = threadIdx.x & 31;
+  const u64 one = 1ull << sh;
+  const HitSink sink = {nullptr, nullptr, 0, nullptr};
+  __syncwarp();
+  u32 n = q.count;
+  if (n > (u32)PQ_CAP) n = PQ_CAP;
+  u32 packed = 0;
+  while (n >= (u32)PQ_DRAIN || (all && n > 0)) {
+    const u32 take = n >= (u32)PQ_DRAIN ? (u32)PQ_DRAIN : n;
+    const u32 base = n - take;
+    Key<KW> want[R], got[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {  // issue: nothing below looks at a result
+      const u32 idx = base + r * 32 + lane;
+      want[r].lo = EMPTY;
+      if (KW == 2) ((u64*)&want[r])[KW - 1] = EMPTY;
+      got[r] = want[r];
+      if (r * 32 + lane < take) {
+        const u32 info = q.info[idx];
+        Key<KW> key;
+        key.lo = q.lo[idx];
+        if (KW == 2) ((u64*)&key)[KW - 1] = q.hi[idx];
+        Key<KW> val = key;
+        if ((info & 3u) == 1) {  // bump: expect the slot as read, write state + 1
+          ((u64*)&want[r])[KW - 1] = q.expect[idx];
+          if (KW == 2) want[r].lo = key.lo;
+          ((u64*)&val)[KW - 1] = q.expect[idx] + one;
+        } else {                 // insert: expect the empty slot, write the key in state 1
+          ((u64*)&val)[KW - 1] |= one;
+        }
+        got[r] = cas_slot(t.keys + ((u64)q.b[idx] * S + (info >> 2)) * KW, want[r], val);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {  // check
+      const u32 idx = base + r * 32 + lane;
+      if (r * 32 + lane < take) {
+        const u32 info = q.info[idx];
+        const bool won = got[r] == want[r];
+        if ((info & 3u) == 1) {
+          if (!won)  // bumped by someone else in between: go on from the new value
+            packed_bump(t.keys + ((u64)q.b[idx] * S + (info >> 2)) * KW + (KW - 1),
+                        ((const u64*)&got[r])[KW - 1], sh, sat);
+        } else if (won) {
+          packed += 1u << 10;
+        } else {     // the slot was taken meanwhile: probe from scratch, with the other such cases
+          Key<KW> key;
+          key.lo = q.lo[idx];
+          if (KW == 2) ((u64*)&key)[KW - 1] = q.hi[idx];
+          u32 code = sq_push_or_resolve<KW, OP_PACKED_COUNT>(qp->slow, t, q.b[idx], key, sh, sat, 0, sink);
+          packed += (code == R_HIT ? 1u : 0u) + (code == R_NEW ? (1u << 10) : 0u);
+          packed |= (code == R_FULL ? (1u << 20) : 0u);
+        }
+      }
+    }
+    n = base;
+    __syncwarp();
+  }
+  if (lane == 0) q.count = n;
+  __syncwarp();
+  return packed;
+}
+
+template <int KW, int OP>
+using PackedKeysQueue = typename std::conditional<OP == OP_PACKED_COUNT, PackedQueues<KW>, SlowQueue<KW>>::type;
+
+template <int KW, int OP, bool FILT>
+__global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_packed_keys(TableView<KW> t, const u64* lo, u64 n_max,
+                                                     const u64* n_dev, int sh, u32 sat, u64* stats,
+                                                     int filt_log2, u32 filt_val) {
+  constexpr int CHUNK = KW == 2 ? 2 : KDF_KEYS_CHUNK;   // two bucket sets live in registers
+  constexpr int S = SPB<KW>::v;
+  const u64 mask = (1ull << sh) - 1;
+  u64 n = n_max;
+  if (n_dev) {
+    u64 nd = *n_dev;
+    n = nd < n_max ? nd : n_max;
+  }
+  using Queue = PackedKeysQueue<KW, OP>;
+  extern __shared__ __align__(16) unsigned char pk_smem[];   // one queue per warp
+  Queue& q = reinterpret_cast<Queue*>(pk_smem)[threadIdx.x >> 5];
+  if ((threadIdx.x & 31) == 0) {
+    if constexpr (OP == OP_PACKED_COUNT) {
+      q.fast.count = 0;
+      q.slow.count = 0;
+    } else {
+      q.count = 0;
+    }
+  }
+  __syncwarp();
+  LocalStats st = {0, 0, 0, 0};
+  HitSink sink = {nullptr, nullptr, 0, nullptr};
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  const u64 n_iter = (n + stride * CHUNK - 1) / (stride * CHUNK);   // warp-uniform (see k_stream)
+  const u64 first = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+
+  Key<KW> kA[CHUNK], kB[CHUNK], kC[CHUNK];
+  Bucket<KW> bA[CHUNK], bB[CHUNK];
+  u32 iA[CHUNK], iB[CHUNK];
+  u32 mA = 0, mB = 0, mC = 0;
+
+  // stage 1: the chunk's keys (mask of the in-range ones)
+  auto load_keys = [&](u64 itn, Key<KW>* keys) -> u32 {
+    u32 okm = 0;
+    u64 i0 = first + itn * stride * CHUNK;
+#pragma unroll
+    for (int u = 0; u < CHUNK; ++u) {
+      u64 i = i0 + (u64)u * stride;
+      if (itn < n_iter && i < n) {
+        okm |= 1u << u;
+        keys[u] = ld_key_pinned<KW>(lo, i);
+      }
+    }
+    return okm;
+  };
+  // stage 2: hash, home bucket loads
+  auto load_buckets = [&](const Key<KW>* keys, u32& okm, u32* bidx, Bucket<KW>* bk) {
+#pragma unroll
+    for (int u = 0; u < CHUNK; ++u) {
+      if (okm & (1u << u)) {
+        u64 h = hash_key(keys[u]);
+        if (FILT && part_of(h, filt_log2) != filt_val) {
+          okm &= ~(1u << u);
+        } else {
+          bidx[u] = bucket_of(h, t.log2_parts, t.n_buckets);
+          bk[u] = ld_bucket<KW>(t.keys + (u64)bidx[u] * 4 * KW);
+        }
+      }
+    }
+  };
+  // stage 3: resolve.  A saturated copy is done once its bucket has been read; a
+  // copy that needs an atomic is queued (see PackedQueue).
+  auto resolve = [&](const Key<KW>* keys, u32 okm, const u32* bidx, const Bucket<KW>* bk) {
+    st.windows += __popc(okm);
+    if constexpr (OP == OP_PACKED_COUNT) {
+#pragma unroll
+      for (int u = 0; u < CHUNK; ++u) {
+        if (okm & (1u << u)) {
+          u64 ms = 0;
+          int j = match_packed(bk[u], keys[u], mask, ms);
+          if (j >= 0) {
+            st.hits++;
+#ifndef KDF_DBG_NO_BUMP
+            if ((u32)(ms >> sh) < sat && !pq_push<KW>(q.fast, keys[u], bidx[u], 1u | ((u32)j << 2), ms))
+              packed_bump(t.keys + ((u64)bidx[u] * S + j) * KW + (KW - 1), ms, sh, sat);
+#endif
+          } else {
+#ifndef KDF_DBG_NO_INSERT
+            int c = -1;
+#pragma unroll
+            for (int cc = S - 1; cc >= 0; --cc)
+              if (maybe_empty(bk[u], cc, keys[u])) c = cc;
+            if (c < 0) {  // home bucket full: probe on from the next one
+              u32 nb = (bidx[u] + 1 == t.n_buckets) ? 0 : bidx[u] + 1;
+              tally(st, sq_push_or_resolve<KW, OP>(q.slow, t, nb, keys[u], sh, sat, 0, sink));
+            } else if (!pq_push<KW>(q.fast, keys[u], bidx[u], 2u | ((u32)c << 2), 0ull)) {
+              tally(st, resolve_packed_count<KW>(t, bidx[u], keys[u], sh, sat));
+            }
+#endif
+          }
+        }
+      }
+      __syncwarp();
+      if (q.fast.count >= (u32)PQ_DRAIN) tally_packed(st, pq_drain<KW>(&q, t, sh, sat, false));
+      if (q.slow.count >= 32) tally_packed(st, sq_drain<KW, OP>(&q.slow, t, sh, sat, sink, false));
+    } else {
+#pragma unroll
+      for (int u = 0; u < CHUNK; ++u) {
+        if (okm & (1u << u)) {
+          u64 ms = 0;
+          int j = match_packed(bk[u], keys[u], mask, ms);
+          if (j >= 0) {
+            st.hits++;
+            if ((u32)(ms >> sh) == sat) atomicAnd(t.keys + ((u64)bidx[u] * S + j) * KW + (KW - 1), mask);
+          } else if (!has_empty(bk[u], keys[u], false)) {  // full bucket: look further, queued
+            u32 nb = (bidx[u] + 1 == t.n_buckets) ? 0 : bidx[u] + 1;
+            tally(st, sq_push_or_resolve<KW, OP>(q, t, nb, keys[u], sh, sat, 0, sink));
+          }
+        }
+      }
+      __syncwarp();
+      if (q.count >= 32) tally_packed(st, sq_drain<KW, OP>(&q, t, sh, sat, sink, false));
+    }
+  };
+
+  mA = load_keys(0, kA);
+  mB = load_keys(1, kB);
+  load_buckets(kA, mA, iA, bA);
+  for (u64 itn = 0; itn < n_iter; ++itn) {
+    mC = load_keys(itn + 2, kC);
+    load_buckets(kB, mB, iB, bB);
+    resolve(kA, mA, iA, bA);
+#pragma unroll
+    for (int u = 0; u < CHUNK; ++u) {
+      kA[u] = kB[u];
+      bA[u] = bB[u];
+      iA[u] = iB[u];
+      kB[u] = kC[u];
+    }
+    mA = mB;
+    mB = mC;
+  }
+  if constexpr (OP == OP_PACKED_COUNT) {
+    tally_packed(st, pq_drain<KW>(&q, t, sh, sat, true));
+    tally_packed(st, sq_drain<KW, OP>(&q.slow, t, sh, sat, sink, true));
+  } else {
+    tally_packed(st, sq_drain<KW, OP>(&q, t, sh, sat, sink, true));
+  }
+  flush_stats(st, stats);
+}
+
+// Emit + clear of a packed slice.  keep = "reached sat" (and, unless ignore_ref,
+// "not found in the reference"); n_count counts the slots that reached sat whether
+// or not the reference holds them (count_all: every occupied slot).  Emitted keys
+// have the state field cleared.  A thread takes U buckets per round with all loads
+// in flight, and a warp reserves its output range with ONE atomic per round (lane
+// counts -> shuffle scan), so the pass is not a chain of same-address atomics.
+template <int KW>
+__global__ void __launch_bounds__(256) k_emit_packed(TableView<KW> t, int sh, u32 sat, int ignore_ref,
+                                                     int count_all, u64* out_lo, u64* out_hi, u64 cap,
+                                                     u64* n_out, u64* n_count, u64* n_occupied) {
+  constexpr int S = SPB<KW>::v;
+  constexpr int U = KW == 2 ? 2 : 4;
+  const u64 mask = (1ull << sh) - 1;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  const u64 first = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 rounds = ((u64)t.n_buckets + stride * U - 1) / (stride * U);
+  const unsigned lane = threadIdx.x & 31;
+  u32 cnt_ge = 0, cnt_occ = 0;
+  for (u64 r = 0; r < rounds; ++r) {
+    Bucket<KW> bk[U];
+    u32 keepm = 0;   // bit u * S + j: slot j of bucket u is emitted
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      u64 b = first + (r * U + u) * stride;
+#pragma unroll
+      for (int i = 0; i < 4 * KW; ++i) bk[u].q[i] = EMPTY;
+      if (b < t.n_buckets) bk[u] = ld_bucket<KW>(t.keys + b * 4 * KW);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      u64 b = first + (r * U + u) * stride;
+      bool any = false;
+#pragma unroll
+      for (int i = 0; i < 4 * KW; ++i) any = any || bk[u].q[i] != EMPTY;
+      if (any) {
+        asm volatile("st.global.cg.v4.u64 [%0], {%1,%1,%1,%1};" ::"l"(t.keys + b * 4 * KW), "l"(EMPTY) : "memory");
+        if (KW == 2)
+          asm volatile("st.global.cg.v4.u64 [%0], {%1,%1,%1,%1};" ::"l"(t.keys + b * 4 * KW + 4), "l"(EMPTY) : "memory");
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+          u64 ms = bk[u].q[j * KW + (KW - 1)];
+          bool occ = !(ms == EMPTY && bk[u].q[j * KW] == EMPTY);
+          u32 state = (u32)(ms >> sh);
+          bool reached = state >= sat || state == 0;
+          bool keep = occ && (ignore_ref ? reached : state >= sat);
+          cnt_occ += occ ? 1u : 0u;
+          cnt_ge += (occ && (count_all || reached)) ? 1u : 0u;
+          keepm |= (keep ? 1u : 0u) << (u * S + j);
+        }
+      }
+    }
+    // warp-wide exclusive scan of the per-lane counts, one reservation per warp
+    u32 mine = __popc(keepm), incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      u32 v = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((int)lane >= o) incl += v;
+    }
+    u32 total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) continue;
+    u64 base = 0;
+    if (lane == 0) base = atomicAdd(n_out, (u64)total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    u64 o = base + (incl - mine);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int j = 0; j < S; ++j) {
+        if (keepm & (1u << (u * S + j))) {
+          if (o < cap) {
+            if (KW == 1) {
+              if (out_lo) out_lo[o] = bk[u].q[j] & mask;
+            } else {
+              if (out_lo) out_lo[o] = bk[u].q[j * KW];
+              if (out_hi) out_hi[o] = bk[u].q[j * KW + (KW - 1)] & mask;
+            }
+          }
+          ++o;
+        }
+      }
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    cnt_ge += __shfl_xor_sync(0xffffffffu, cnt_ge, o);
+    cnt_occ += __shfl_xor_sync(0xffffffffu, cnt_occ, o);
+  }
+  if (lane == 0) {
+    if (n_count && cnt_ge) atomicAdd(n_count, (u64)cnt_ge);
+    if (n_occupied && cnt_occ) atomicAdd(n_occupied, (u64)cnt_occ);
+  }
 }
 
 // ------------------------------------------------------------- K3 ---------
@@ -1104,28 +1604,59 @@ __global__ void __launch_bounds__(256) k_fill_u64x2(ulonglong2* p, u64 n_units, 
 }
 
 // ---------------------------------------------- random-access roofline ----
+// mode 0: 32-byte-sector reads; 1: read + RED.ADD.32 on the sector (the two figures
+// bench.py reports).  Modes >= 2 time other read-modify-write flavours on the same
+// access pattern (profiles/r1d_atomics.txt); every CAS below succeeds unless raced:
+// 2 ATOM.ADD.32 (result used), 3 CAS.32, 4 CAS.64, 5 RED.ADD.64, 6 RED.AND.64,
+// 7 ATOM.EXCH.64, 8 RED.ADD.32 without the read, 10 one 256-bit load per op,
+// 11 256-bit load + CAS.64 on one op in six (the mix of a packed count).
 __global__ void __launch_bounds__(256) k_bench_random(u32* buf, u64 n_sectors, u64 n_ops, int atomic,
                                                       u64* sink) {
   constexpr int CHUNK = 8;
   u64 stride = (u64)gridDim.x * blockDim.x;
-  u32 acc = 0;
+  u64 acc = 0;
   for (u64 i0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_ops; i0 += stride * CHUNK) {
-    u32 v[CHUNK];
+    u64 v[CHUNK];
     u64 sidx[CHUNK];
 #pragma unroll
     for (int u = 0; u < CHUNK; ++u) {
       u64 i = i0 + (u64)u * stride;
       sidx[u] = mulhi64(mix64(i + 0x1234567ull), n_sectors);
-      v[u] = (i < n_ops) ? __ldcg(buf + sidx[u] * 8) : 0u;
+      v[u] = 0;
+      if (i < n_ops && atomic != 8) {
+        if (atomic == 10 || atomic == 11) {
+          u64 a, b, c, d;
+          ld256(reinterpret_cast<const u64*>(buf + sidx[u] * 8), a, b, c, d);
+          v[u] = b;
+          acc += a ^ c ^ d;
+        } else if (atomic == 4 || atomic == 5 || atomic == 6 || atomic == 7) {
+          v[u] = __ldcg(reinterpret_cast<const u64*>(buf + sidx[u] * 8 + 2));
+        } else {
+          v[u] = __ldcg(buf + sidx[u] * 8 + 2);
+        }
+      }
     }
 #pragma unroll
     for (int u = 0; u < CHUNK; ++u) {
       u64 i = i0 + (u64)u * stride;
       acc += v[u];
-      if (atomic && i < n_ops) atomicAdd(buf + sidx[u] * 8 + 2, 1u);
+      if (i >= n_ops) continue;
+      u32* p32 = buf + sidx[u] * 8 + 2;
+      u64* p64 = reinterpret_cast<u64*>(buf + sidx[u] * 8 + 2);
+      switch (atomic) {
+        case 1: case 8: atomicAdd(p32, 1u); break;
+        case 2: acc += atomicAdd(p32, 1u); break;
+        case 3: acc += atomicCAS(p32, (u32)v[u], (u32)v[u] + 1u); break;
+        case 4: acc += atomicCAS(p64, v[u], v[u] + 1ull); break;
+        case 5: atomicAdd(p64, 1ull); break;
+        case 6: atomicAnd(p64, ~(u64)(i & 1)); break;
+        case 7: acc += atomicExch(p64, i); break;
+        case 11: if ((sidx[u] % 6) == 0) acc += atomicCAS(p64, v[u], v[u] + 1ull); break;
+        default: break;
+      }
     }
   }
-  if (acc == 0xdeadbeefu) *sink = acc;
+  if (acc == 0xdeadbeefdeadbeefull) *sink = acc;
 }
 
 // ------------------------------------------------------------ host side ---
@@ -1268,6 +1799,39 @@ static int launch_emit_buckets(const kdf_table* t, u32 min0, u32 max0, u32 min1,
   int g = grid_for((const void*)k_emit_buckets<KW, true>, 256, 0, tv.n_buckets, t->sm_count);
   k_emit_buckets<KW, true><<<g, 256, 0, st>>>(tv, min0, max0, min1, max1, out_lo, out_hi, out_p0, out_p1,
                                               cap, n_out, count_min0, n_count, n_occ);
+  CUDA_TRY(cudaGetLastError());
+  return KDF_OK;
+}
+
+template <int KW, int OP>
+static int launch_packed_keys(const kdf_table* t, const u64* lo, u64 n_max, const u64* n_dev, int sh,
+                              u32 sat, u64* stats, cudaStream_t st, int filt_log2, u32 filt_val) {
+  TableView<KW> tv = view_of_table<KW>(t);
+  const size_t smem = sizeof(PackedKeysQueue<KW, OP>) * (256 / 32);
+  const u64 items = (n_max + KDF_KEYS_CHUNK - 1) / KDF_KEYS_CHUNK;
+  if (filt_log2 > 0) {
+    const void* fn = (const void*)k_packed_keys<KW, OP, true>;
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int g = grid_for(fn, 256, smem, items, t->sm_count);
+    k_packed_keys<KW, OP, true><<<g, 256, smem, st>>>(tv, lo, n_max, n_dev, sh, sat, stats, filt_log2, filt_val);
+  } else {
+    const void* fn = (const void*)k_packed_keys<KW, OP, false>;
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int g = grid_for(fn, 256, smem, items, t->sm_count);
+    k_packed_keys<KW, OP, false><<<g, 256, smem, st>>>(tv, lo, n_max, n_dev, sh, sat, stats, 0, 0);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return KDF_OK;
+}
+
+template <int KW>
+static int launch_emit_packed(const kdf_table* t, int sh, u32 sat, int ignore_ref, int count_all,
+                              u64* out_lo, u64* out_hi, u64 cap, u64* n_out, u64* n_count, u64* n_occ,
+                              cudaStream_t st) {
+  TableView<KW> tv = view_of_table<KW>(t);
+  int g = grid_for((const void*)k_emit_packed<KW>, 256, 0, (tv.n_buckets + 3) / 4, t->sm_count);
+  k_emit_packed<KW><<<g, 256, 0, st>>>(tv, sh, sat, ignore_ref, count_all, out_lo, out_hi, cap, n_out,
+                                       n_count, n_occ);
   CUDA_TRY(cudaGetLastError());
   return KDF_OK;
 }
@@ -1690,6 +2254,21 @@ int kdf_bin_keys(const uint64_t* lo, const uint64_t* hi, uint64_t n, int k, int 
   return KDF_OK;
 }
 
+int kdf_count_bins_packed(int k, uint32_t min0, uint32_t max0, uint32_t min1, uint32_t max1,
+                          uint32_t count_min0, int want_planes) {
+  int kw = kdf_key_words(k);
+  if (!kw || want_planes) return 0;
+  const char* off = getenv("KDF_COUNT_BINS_PLANES");   // A/B switch: force the plane form
+  if (off && off[0] == '1') return 0;
+  int free_bits = 64 * kw - 2 * k;   // spare bits above the key in its most significant word
+  if (free_bits < 2) return 0;
+  if (min0 < 1 || max0 != 0xffffffffu || min1 != 0 || (max1 != 0 && max1 != 0xffffffffu)) return 0;
+  if (!(count_min0 <= 1 || count_min0 == min0)) return 0;
+  if (free_bits < 31 && min0 > (1u << free_bits) - 1) return 0;
+  if (min0 > 0x7fffffffu) return 0;
+  return 1;
+}
+
 int kdf_count_bins(int k, int n_parts, const uint64_t* child_bins, uint64_t child_bin_cap,
                    const uint64_t* child_cursors, const uint64_t* ref_bins, uint64_t ref_bin_cap,
                    const uint64_t* ref_cursors, void* slice, uint64_t slice_capacity,
@@ -1733,6 +2312,48 @@ int kdf_count_bins_multi(int k, int n_parts, int n_src, int sub_split, const uin
   cudaStream_t st = (cudaStream_t)stream;
   u64* ctr = (u64*)counters;  // [0..3] = stats block (windows = keys applied, full, hits, new), [4] = #(p0 >= count_min0), [5] = #occupied
   const int kw = t.key_words;
+  if (kdf_count_bins_packed(k, min0, max0, min1, max1, count_min0, out_p0 || out_p1)) {
+    // packed form (K2c): the slice is keys only, the counter saturates at min0
+    const int sh = 2 * k - 64 * (kw - 1);
+    const u32 sat = min0;
+    const int ignore_ref = (max1 != 0) ? 1 : 0;
+    const int count_all = (count_min0 <= 1) ? 1 : 0;
+    {
+      u64 key_units = t.capacity * 8ull * kw / 16;
+      int g = grid_for((const void*)k_fill_u64x2, 256, 0, key_units, t.sm_count);
+      k_fill_u64x2<<<g, 256, 0, st>>>((ulonglong2*)t.base, key_units, EMPTY);
+      CUDA_TRY(cudaGetLastError());
+    }
+    for (int pf = 0; pf < n_parts * sub_split; ++pf) {
+      const int p = pf / sub_split;
+      for (int sidx = 0; sidx < n_src; ++sidx) {
+        u64 b = (u64)sidx * n_parts + p;
+        const u64* cb = (const u64*)child_bins + b * child_bin_cap * kw;
+        if (kw == 1)
+          rc = launch_packed_keys<1, OP_PACKED_COUNT>(&t, cb, child_bin_cap, (const u64*)child_cursors + b, sh, sat, ctr, st, filt_log2, (u32)pf);
+        else
+          rc = launch_packed_keys<2, OP_PACKED_COUNT>(&t, cb, child_bin_cap, (const u64*)child_cursors + b, sh, sat, ctr, st, filt_log2, (u32)pf);
+        if (rc != KDF_OK) return rc;
+      }
+      if (ref_bins && ref_cursors && !ignore_ref) {
+        for (int sidx = 0; sidx < n_src; ++sidx) {
+          u64 b = (u64)sidx * n_parts + p;
+          const u64* rb = (const u64*)ref_bins + b * ref_bin_cap * kw;
+          if (kw == 1)
+            rc = launch_packed_keys<1, OP_PACKED_MARK>(&t, rb, ref_bin_cap, (const u64*)ref_cursors + b, sh, sat, nullptr, st, filt_log2, (u32)pf);
+          else
+            rc = launch_packed_keys<2, OP_PACKED_MARK>(&t, rb, ref_bin_cap, (const u64*)ref_cursors + b, sh, sat, nullptr, st, filt_log2, (u32)pf);
+          if (rc != KDF_OK) return rc;
+        }
+      }
+      if (kw == 1)
+        rc = launch_emit_packed<1>(&t, sh, sat, ignore_ref, count_all, (u64*)out_lo, (u64*)out_hi, out_cap, (u64*)n_out, ctr + 4, ctr + 5, st);
+      else
+        rc = launch_emit_packed<2>(&t, sh, sat, ignore_ref, count_all, (u64*)out_lo, (u64*)out_hi, out_cap, (u64*)n_out, ctr + 4, ctr + 5, st);
+      if (rc != KDF_OK) return rc;
+    }
+    return KDF_OK;
+  }
   rc = clear_table_async(&t, st);  // once: every emit pass leaves the slice clean
   if (rc != KDF_OK) return rc;
   for (int pf = 0; pf < n_parts * sub_split; ++pf) {

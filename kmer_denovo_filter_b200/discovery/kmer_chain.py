@@ -13,6 +13,8 @@ samples, either resident in HBM (``DeviceStream``) or in host memory
 (``HostStream`` — uploaded here, inside the caller's timed region).
 """
 
+import os
+
 import numpy as np
 
 from .. import engine as _engine
@@ -82,7 +84,7 @@ def default_child_capacity(eng, n_bases):
 # it with evict-first loads.  Measured on the 64 Mbp x 30x trio (k = 31): 32 MB
 # slices (256 bins) 43.8 ms for bin + count, 64 MB (128 bins) 37.9 ms, 64 MB at
 # load 0.56 (64 bins) 32.6 ms, 128 MB 44 ms (the slice no longer fits).
-SLICE_BYTES = 64 << 20
+SLICE_BYTES = int(os.environ.get("KDF_SLICE_MB", "64")) << 20
 MAX_PARTS = 256
 
 
@@ -93,13 +95,15 @@ def _pow2_at_least(x):
     return p
 
 
-def plan_partitions(n_windows_max, slots_needed=None, key_words=1):
+def plan_partitions(n_windows_max, slots_needed=None, key_words=1, packed=False):
     """(n_parts, slice_capacity) for about ``slots_needed`` table slots in total.
     Default sizing: 8 bases per distinct k-mer (30x data holds ~14); a slice that
-    turns out too small is reported by the kernel and the pass is redone."""
+    turns out too small is reported by the kernel and the pass is redone.
+    ``packed``: the slice holds keys only (``CudaEngine.count_bins_packed``), so the
+    same L2 budget covers twice the slots and half as many bins are needed."""
     if slots_needed is None:
         slots_needed = max(n_windows_max // 8, 1024)
-    slice_slots = SLICE_BYTES // (8 * key_words + 8)
+    slice_slots = SLICE_BYTES // (8 * key_words + (0 if packed else 8))
     n_parts = min(MAX_PARTS, _pow2_at_least((slots_needed + slice_slots - 1) // slice_slots))
     slice_cap = max(1024, (slots_needed + n_parts - 1) // n_parts)
     return n_parts, (slice_cap + 3) & ~3
@@ -127,7 +131,8 @@ def count_child_partitioned(eng, child_streams, ref_streams, k, min_child_count,
     child_windows, ref_windows, child_distinct, candidates, non_ref, lo, hi."""
     n_max = sum(s.n_bases for s in child_streams)
     r_max = sum(s.n_bases for s in ref_streams)
-    p_auto, s_auto = plan_partitions(n_max, key_words=eng.lib.kdf_key_words(k))
+    p_auto, s_auto = plan_partitions(n_max, key_words=eng.lib.kdf_key_words(k),
+                                     packed=eng.count_bins_packed(k, min_child_count))
     n_parts = n_parts or p_auto
     slice_capacity = slice_capacity or s_auto
     bin_cap = _bin_capacity(n_max, n_parts)

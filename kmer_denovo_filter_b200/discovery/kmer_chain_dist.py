@@ -206,7 +206,8 @@ def count_child_dist(eng, child_streams, ref_streams, k, min_child_count, world)
     r_recv, r_counts, r_cap, r_win = route_to_owners(eng, ref_streams, k, world)
     n_child = int(c_counts.sum())
     n_ref = int(r_counts.sum())
-    n_parts, slice_capacity = _kc.plan_partitions(max(n_child, 1), key_words=kw)
+    n_parts, slice_capacity = _kc.plan_partitions(max(n_child, 1), key_words=kw,
+                                                  packed=eng.count_bins_packed(k, min_child_count))
     bin_cap = _kc._bin_capacity(max(n_child, 1), n_parts)
     ref_cap = _kc._bin_capacity(max(n_ref, 1), n_parts)
     while True:
@@ -253,7 +254,8 @@ def _count_child_fused(eng, child_streams, ref_streams, k, min_child_count, worl
     # (owner x range) bins, so beyond 8 ranks a bin spans `sub` slices and is counted
     # in `sub` passes (kdf_count_bins_multi sub_split).  Measured at 8 ranks: 512 bins
     # (bin + send 43.5 ms, count 33.8 ms) and 256 bins x 2 passes (31.2 + 48.1 ms) tie.
-    n_plan, slice_capacity = _kc.plan_partitions(max(n_child_exp, 1), key_words=kw)
+    n_plan, slice_capacity = _kc.plan_partitions(max(n_child_exp, 1), key_words=kw,
+                                                 packed=eng.count_bins_packed(k, min_child_count))
     n_local = max(1, min(n_plan, 512 // _kc._pow2_at_least(world)))
     sub = max(1, n_plan // n_local)
     cb, c_win = route_composite_p2p(eng, child_streams, k, world, "child", n_local, n_child_exp)

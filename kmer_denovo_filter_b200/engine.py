@@ -78,6 +78,7 @@ _SIGNATURES = {
                                      _vp, _vp, _vp]),
     "kdf_bin_stream_to": (_i, [ctypes.POINTER(_Stream), _i, _i, _i, _vp, _u64, _vp, _vp, _vp, _vp]),
     "kdf_bin_keys": (_i, [_vp, _vp, _u64, _i, _i, _i, _vp, _u64, _vp, _vp, _vp]),
+    "kdf_count_bins_packed": (_i, [_i, _u32, _u32, _u32, _u32, _u32, _i]),
     "kdf_count_bins": (_i, [_i, _i, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _u64, _u32, _u32, _u32, _u32,
                             _vp, _vp, _vp, _vp, _u64, _vp, _u32, _vp, _vp]),
     "kdf_count_bins_multi": (_i, [_i, _i, _i, _i, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _u64, _u32, _u32, _u32,
@@ -745,6 +746,13 @@ class CudaEngine:
         self._t1("bin_keys/kw%d" % bins.key_words, ev)
         self.launches += 1
 
+    def count_bins_packed(self, k, min_child_count):
+        """True when the discovery chain's count_bins call (count >= min_child_count,
+        not in the reference, no count planes wanted) takes the packed form of
+        include/kdf.h: the table slice then holds keys only."""
+        return bool(self.lib.kdf_count_bins_packed(k, min_child_count, U32_MAX, 0, 0,
+                                                   min_child_count, 0))
+
     def count_bins(self, child_bins, ref_bins, slice_capacity, min0=0, max0=U32_MAX, min1=0,
                    max1=U32_MAX, count_min0=0, out_cap=1 << 20, want_planes=False, sub_split=1):
         """Count every bin in an L2-resident slice and emit (see include/kdf.h).
@@ -793,6 +801,6 @@ class CudaEngine:
     def bench_random_access(self, buf, n_ops, atomic):
         sink = self.zeros(1, self.torch.int64)
         self._check(self.lib.kdf_bench_random_access(
-            buf.data_ptr(), buf.numel() * buf.element_size(), n_ops, 1 if atomic else 0,
+            buf.data_ptr(), buf.numel() * buf.element_size(), n_ops, int(atomic),
             sink.data_ptr(), self.stream_ptr()))
         self.launches += 1

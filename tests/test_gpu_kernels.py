@@ -373,6 +373,82 @@ def test_count_bins_equals_direct_table(eng, k, n_parts):
     assert res4["full"] == 1
 
 
+@pytest.mark.parametrize("k", [21, 31, 47, 63])
+@pytest.mark.parametrize("n_parts", [1, 8])
+def test_count_bins_packed_form(eng, k, n_parts):
+    """The packed form of kdf_count_bins (keys-only slice, saturating counter in the
+    key's spare bits, include/kdf.h) answers threshold + reference subtraction exactly
+    like the oracle, for every threshold that fits the spare bits, with and without a
+    reference, in sub-range passes, and reports a full slice."""
+    from kmer_denovo_filter_b200 import engine
+    g, child = _genome_reads(191 + k, glen=9000, n=1500)
+    ref = [g[:6000]]
+    want = kmers.count_sequences(child, k)
+    refk = set(kmers.count_sequences(ref, k))
+    dc = eng.upload(engine.pack_sequences(child))
+    dr = eng.upload(engine.pack_sequences(ref))
+    n_win = sum(want.values())
+    cb = eng.new_bins(k, n_parts, bin_cap=n_win // n_parts * 2 + 512)
+    rb = eng.new_bins(k, n_parts, bin_cap=6000 // n_parts * 2 + 512)
+    eng.bin_stream(cb, dc)
+    eng.bin_stream(rb, dr)
+    cap = 2 * len(want) // n_parts + 64
+    free_bits = 64 * cb.key_words - 2 * k
+    for m in (1, 2, 3, 5):
+        packed = bool(eng.lib.kdf_count_bins_packed(k, m, engine.U32_MAX, 0, 0, m, 0))
+        assert packed == (m <= (1 << min(free_bits, 31)) - 1)
+        assert eng.count_bins_packed(k, m) == packed
+        # count >= m and not in the reference (the discovery chain's call)
+        res = eng.count_bins(cb, rb, slice_capacity=cap, min0=m, max1=0, count_min0=m,
+                             out_cap=len(want) + 10)
+        cand = {key for key, c in want.items() if c >= m}
+        assert res["full"] == 0 and res["keys"] == n_win
+        assert res["distinct"] == len(want) == res["occupied"]
+        assert res["hits"] + res["distinct"] == n_win
+        assert res["n_count"] == len(cand)
+        got = eng.keys_to_pyints(res["lo"], res["hi"])
+        assert len(got) == res["n_out"] == len(set(got))
+        assert set(got) == cand - refk
+        # no reference bins: every candidate comes out
+        res = eng.count_bins(cb, None, slice_capacity=cap, min0=m, max1=0, count_min0=m,
+                             out_cap=len(want) + 10)
+        assert set(eng.keys_to_pyints(res["lo"], res["hi"])) == cand and res["n_count"] == len(cand)
+        # reference marks ignored (max1 open), n_count over all occupied slots (count_min0 = 0)
+        res = eng.count_bins(cb, rb, slice_capacity=cap, min0=m, out_cap=len(want) + 10)
+        assert set(eng.keys_to_pyints(res["lo"], res["hi"])) == cand and res["n_count"] == len(want)
+    # sub-range passes over the same bins, and an undersized output / slice
+    for sub in (2, 8):
+        rs = eng.count_bins(cb, rb, slice_capacity=2 * len(want) // (n_parts * sub) + 64, min0=3,
+                            max1=0, count_min0=3, out_cap=len(want) + 10, sub_split=sub)
+        assert rs["full"] == 0 and rs["keys"] == n_win and rs["distinct"] == len(want)
+        assert set(eng.keys_to_pyints(rs["lo"], rs["hi"])) == \
+            {key for key, c in want.items() if c >= 3} - refk
+    small = eng.count_bins(cb, rb, slice_capacity=cap, min0=3, max1=0, count_min0=3, out_cap=5)
+    assert small["n_out"] == len({key for key, c in want.items() if c >= 3} - refk)
+    assert small["lo"].shape[0] == 5
+    full = eng.count_bins(cb, None, slice_capacity=max(4, len(want) // n_parts // 2), min0=3, max1=0,
+                          count_min0=3, out_cap=4)
+    assert full["full"] == 1
+
+
+def test_count_bins_packed_heavy_duplicates(eng):
+    """Many concurrent copies of few keys (the saturating CAS under contention) and
+    keys whose top bases are all T (state bits next to an all-ones key prefix)."""
+    from kmer_denovo_filter_b200 import engine
+    k = 31
+    seqs = ["T" * 15 + "C" + "A" * 15] * 3000 + ["ACGTTGCAAGGCTTAACCGGATATCGCGATTAGC"] * 5000 + \
+           ["T" * 20 + "G" + "C" * 12] * 2 + ["G" * 31]
+    want = kmers.count_sequences(seqs, k)
+    dc = eng.upload(engine.pack_sequences(seqs))
+    n_win = sum(want.values())
+    cb = eng.new_bins(k, 4, bin_cap=n_win + 64)
+    eng.bin_stream(cb, dc)
+    for m in (1, 2, 3):
+        res = eng.count_bins(cb, None, slice_capacity=1024, min0=m, max1=0, count_min0=m, out_cap=64)
+        assert res["full"] == 0 and res["keys"] == n_win and res["distinct"] == len(want)
+        assert set(eng.keys_to_pyints(res["lo"], res["hi"])) == {x for x, c in want.items() if c >= m}
+
+
 @pytest.mark.parametrize("k", [31, 47])
 @pytest.mark.parametrize("big_table", [False, True])
 def test_scan_sparse_equals_dense(eng, k, big_table):
