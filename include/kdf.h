@@ -270,6 +270,18 @@ int kdf_bin_keys(const uint64_t* lo /*DEV*/, const uint64_t* hi /*DEV or NULL*/,
                  int k, int by_owner, int n_parts, uint64_t* bins /*DEV*/, uint64_t bin_cap,
                  uint64_t* cursors /*DEV*/, uint64_t* overflow /*DEV*/, void* stream);
 
+/* K2 on hash-range bins: apply `mode` (kdf_update_keys semantics) to the keys of
+ * every bin, bin after bin.  bins / cursors as written by kdf_bin_stream with
+ * by_owner == 0 (for 128-bit keys the {lo, hi} pairs of a bin are interleaved).
+ * The table's bucket index grows with the hash, so bin p only touches the p-th
+ * n_parts-th of the table: a read-only table far larger than L2 (the filter set of
+ * `jellyfish count --if`, discovery/pipeline.py:377-386, at whole-genome scale) is
+ * probed with L2-resident traffic after one streaming binning pass, instead of one
+ * random DRAM sector per k-mer.                                               */
+int kdf_update_bins(kdf_table* t, int n_parts, const uint64_t* bins /*DEV*/, uint64_t bin_cap,
+                    const uint64_t* cursors /*DEV*/, int mode, int plane, uint32_t arg,
+                    uint64_t* stats /*DEV or NULL*/, void* stream);
+
 /* Count every hash-range bin in an L2-resident table slice and emit.
  * For each bin p: clear `slice` (a table of slice_capacity slots in caller
  * memory of kdf_table_bytes(slice_capacity, key_words)); insert+count the child

@@ -712,8 +712,11 @@ template <> __device__ __forceinline__ Key<2> ld_key_pinned<2>(const u64* lo, u6
 // issued), results checked afterwards.  What the first attempt cannot settle (the slot
 // was taken meanwhile, the home bucket was full) goes to the SlowQueue, whose drain
 // probes from scratch with every lane busy.
-constexpr int PQ_CAP = 256;
-constexpr int PQ_DRAIN = 128;
+#ifndef KDF_PQ_DRAIN
+#define KDF_PQ_DRAIN 128
+#endif
+constexpr int PQ_DRAIN = KDF_PQ_DRAIN;
+constexpr int PQ_CAP = PQ_DRAIN + 128;   // a chunk adds at most 128 items per warp
 template <int KW> struct PackedQueue {
   u64 lo[PQ_CAP];
   u64 hi[KW == 2 ? PQ_CAP : 1];
@@ -912,15 +915,29 @@ __global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_packed_keys(TableView<
       if (q.fast.count >= (u32)PQ_DRAIN) tally_packed(st, pq_drain<KW>(&q, t, sh, sat, false));
       if (q.slow.count >= 32) tally_packed(st, sq_drain<KW, OP>(&q.slow, t, sh, sat, sink, false));
     } else {
+      // probing ops: OP_PACKED_MARK on a packed slice, or COUNT_IF_PRESENT /
+      // MARK_IF_PRESENT on a table with value planes (then sh = plane, sat = arg)
 #pragma unroll
       for (int u = 0; u < CHUNK; ++u) {
         if (okm & (1u << u)) {
-          u64 ms = 0;
-          int j = match_packed(bk[u], keys[u], mask, ms);
-          if (j >= 0) {
-            st.hits++;
-            if ((u32)(ms >> sh) == sat) atomicAnd(t.keys + ((u64)bidx[u] * S + j) * KW + (KW - 1), mask);
-          } else if (!has_empty(bk[u], keys[u], false)) {  // full bucket: look further, queued
+          bool full;
+          if constexpr (OP == OP_PACKED_MARK) {
+            u64 ms = 0;
+            int j = match_packed(bk[u], keys[u], mask, ms);
+            if (j >= 0) {
+              st.hits++;
+              if ((u32)(ms >> sh) == sat) atomicAnd(t.keys + ((u64)bidx[u] * S + j) * KW + (KW - 1), mask);
+            }
+            full = j < 0 && !has_empty(bk[u], keys[u], false);
+          } else {
+            int j = match_in(bk[u], keys[u]);
+            if (j >= 0) {
+              st.hits++;
+              on_found<OP, KW>(t, (u64)bidx[u] * S + j, sh, sat, 0, sink);
+            }
+            full = j < 0 && !has_empty(bk[u], keys[u], t.fast_empty);
+          }
+          if (full) {  // full bucket: look further, queued
             u32 nb = (bidx[u] + 1 == t.n_buckets) ? 0 : bidx[u] + 1;
             tally(st, sq_push_or_resolve<KW, OP>(q, t, nb, keys[u], sh, sat, 0, sink));
           }
@@ -1998,6 +2015,36 @@ int kdf_update_keys(kdf_table* t, const uint64_t* lo, const uint64_t* hi, uint64
                                    (u64*)stats, st);
   return dispatch_update_keys<2>(t, (const u64*)lo, (const u64*)hi, n, nullptr, mode, plane, arg,
                                  (u64*)stats, st);
+}
+
+int kdf_update_bins(kdf_table* t, int n_parts, const uint64_t* bins, uint64_t bin_cap,
+                    const uint64_t* cursors, int mode, int plane, uint32_t arg, uint64_t* stats,
+                    void* stream) {
+  if (!t || !bins || !cursors) return fail(KDF_ERR_ARG, "kdf_update_bins: NULL argument");
+  if (n_parts < 1 || n_parts > BIN_MAX_PARTS) return fail(KDF_ERR_ARG, "kdf_update_bins: n_parts must be 1..512");
+  if (plane != 0 && plane != 1) return fail(KDF_ERR_ARG, "kdf_update_bins: plane must be 0 or 1");
+  if (mode < 0 || mode > KDF_MODE_MARK_IF_PRESENT) return fail(KDF_ERR_ARG, "kdf_update_bins: unknown mode");
+  if (bin_cap == 0) return KDF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int kw = t->key_words;
+  // one launch per bin, in hash order: the bucket index grows with the hash, so the
+  // keys of bin p only touch the p-th n_parts-th of the table, which stays in L2
+  for (int p = 0; p < n_parts; ++p) {
+    const u64* b = (const u64*)bins + (u64)p * bin_cap * kw;
+    const u64* n_dev = (const u64*)cursors + p;
+    int rc;
+    if (mode == KDF_MODE_COUNT_IF_PRESENT)   // the probing ops take the software-pipelined kernel
+      rc = kw == 1 ? launch_packed_keys<1, OP_COUNT_IF_PRESENT>(t, b, bin_cap, n_dev, plane, arg, (u64*)stats, st, 0, 0)
+                   : launch_packed_keys<2, OP_COUNT_IF_PRESENT>(t, b, bin_cap, n_dev, plane, arg, (u64*)stats, st, 0, 0);
+    else if (mode == KDF_MODE_MARK_IF_PRESENT)
+      rc = kw == 1 ? launch_packed_keys<1, OP_MARK_IF_PRESENT>(t, b, bin_cap, n_dev, plane, arg, (u64*)stats, st, 0, 0)
+                   : launch_packed_keys<2, OP_MARK_IF_PRESENT>(t, b, bin_cap, n_dev, plane, arg, (u64*)stats, st, 0, 0);
+    else
+      rc = kw == 1 ? dispatch_update_keys<1>(t, b, nullptr, bin_cap, n_dev, mode, plane, arg, (u64*)stats, st)
+                   : dispatch_update_keys<2>(t, b, nullptr, bin_cap, n_dev, mode, plane, arg, (u64*)stats, st);
+    if (rc != KDF_OK) return rc;
+  }
+  return KDF_OK;
 }
 
 int kdf_threshold_compact(const kdf_table* t, uint32_t min0, uint32_t max0, uint32_t min1,

@@ -184,6 +184,42 @@ def count_child_partitioned(eng, child_streams, ref_streams, k, min_child_count,
             "n_parts": n_parts, "slice_capacity": slice_capacity}
 
 
+# A parent stream is probed against a read-only table (``count --if``).  While the
+# table's keys fit L2 the stream kernel probes it directly; past that every probe
+# would be a random DRAM sector (measured 37 G/s against ~150 G/s from L2), so the
+# parent's k-mers are first binned by hash range — a streaming pass — and the bins are
+# applied one after the other, each touching only its own L2-sized share of the table.
+PROBE_DIRECT_BYTES = int(os.environ.get("KDF_PROBE_DIRECT_MB", "128")) << 20   # keys of a table probed straight from the stream
+PROBE_SLICE_BYTES = 48 << 20
+PROBE_CHUNK_BASES = 1 << 30      # bins of one chunk: <= 8.6 GB (64-bit keys)
+
+
+def count_if_present(eng, table, d_stream, stats, plane=0, arg=1):
+    """``jellyfish count --if`` of one parent stream (discovery/pipeline.py:377-386)."""
+    key_bytes = table.capacity * 8 * table.key_words
+    if key_bytes <= PROBE_DIRECT_BYTES or os.environ.get("KDF_PROBE_DIRECT") == "1":
+        eng.count_stream(table, d_stream, _engine.MODE_COUNT_IF_PRESENT, plane, arg, stats)
+        return
+    # at least 16 bins: with <= 8 the binning kernel takes its owner-routing form
+    n_parts = min(MAX_PARTS, max(16, _pow2_at_least((key_bytes + PROBE_SLICE_BYTES - 1) // PROBE_SLICE_BYTES)))
+    n_words = (d_stream.n_bases + 31) // 32
+    chunk_words = PROBE_CHUNK_BASES // 32
+    bin_cap = _bin_capacity(min(d_stream.n_bases, PROBE_CHUNK_BASES), n_parts)
+    first = 0
+    while first < n_words:
+        n = min(chunk_words, n_words - first)
+        while True:   # a skewed hash range: retry this chunk with the exact size
+            bins = eng.new_bins(table.k, n_parts, bin_cap)
+            eng.bin_stream(bins, d_stream, None, word_range=(first, n))
+            if not bins.overflowed():
+                break
+            bin_cap = int(bins.counts().max()) + 4
+            del bins
+        eng.update_bins(table, bins, _engine.MODE_COUNT_IF_PRESENT, plane, arg, stats)
+        del bins
+        first += n
+
+
 def _primed_table(eng, k, lo, hi, n):
     # small sets get load 0.25: they stay within the shared-memory budget of the
     # stream kernels and almost no probe has to look past its home bucket
@@ -194,6 +230,8 @@ def _primed_table(eng, k, lo, hi, n):
         n_keys *= 2
     elif n_keys * 3 * 8 * eng.lib.kdf_key_words(k) <= L2_TABLE_BYTES:
         n_keys = n_keys * 3 // 2     # still L2-resident at load 0.33
+    elif n_keys * 2 * 8 * eng.lib.kdf_key_words(k) > PROBE_DIRECT_BYTES:
+        n_keys = n_keys * 3 // 2     # probed bin by bin (count_if_present): its size is free
     t = eng.new_table(k, n_keys=n_keys)
     eng.update_keys(t, lo, hi, _engine.MODE_INSERT_ONLY, 0, 0)
     return t
@@ -275,14 +313,14 @@ def discover_streams(eng, child, mother, father, ref, k, min_child_count=3,
     if n_nonref:
         mt = _primed_table(eng, k, lo, hi, n_nonref)
         up.wait(ev_mother)
-        eng.count_stream(mt, d_mother, _engine.MODE_COUNT_IF_PRESENT, 0, 1, stats)
+        count_if_present(eng, mt, d_mother, stats)
         n_am, lo, hi, _a, _b = eng.threshold_compact(mt, max0=parent_max_count)
         mt.close()
         out["after_mother"] = n_am
         if n_am:
             ft = _primed_table(eng, k, lo, hi, n_am)
             up.wait(ev_father)
-            eng.count_stream(ft, d_father, _engine.MODE_COUNT_IF_PRESENT, 0, 1, stats)
+            count_if_present(eng, ft, d_father, stats)
             n_pu, lo, hi, _a, _b = eng.threshold_compact(ft, max0=parent_max_count)
             ft.close()
     out["proband_unique"] = n_pu

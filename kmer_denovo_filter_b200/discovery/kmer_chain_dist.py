@@ -284,7 +284,7 @@ def filter_parent_dist(eng, parent_stream, k, lo, hi, parent_max_count, world, s
     identical on every rank."""
     n = int(lo.shape[0])
     table = _kc._primed_table(eng, k, lo, hi, n)
-    eng.count_stream(table, parent_stream, _engine.MODE_COUNT_IF_PRESENT, 0, 1, stats)
+    _kc.count_if_present(eng, table, parent_stream, stats)
     _found, p0, _p1 = eng.lookup_keys(table, lo, hi)
     table.close()
     total = p0.to(eng.torch.int64)

@@ -78,6 +78,7 @@ _SIGNATURES = {
                                      _vp, _vp, _vp]),
     "kdf_bin_stream_to": (_i, [ctypes.POINTER(_Stream), _i, _i, _i, _vp, _u64, _vp, _vp, _vp, _vp]),
     "kdf_bin_keys": (_i, [_vp, _vp, _u64, _i, _i, _i, _vp, _u64, _vp, _vp, _vp]),
+    "kdf_update_bins": (_i, [_vp, _i, _vp, _u64, _vp, _i, _i, _u32, _vp, _vp]),
     "kdf_count_bins_packed": (_i, [_i, _u32, _u32, _u32, _u32, _u32, _i]),
     "kdf_count_bins": (_i, [_i, _i, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _u64, _u32, _u32, _u32, _u32,
                             _vp, _vp, _vp, _vp, _u64, _vp, _u32, _vp, _vp]),
@@ -745,6 +746,18 @@ class CudaEngine:
             bins.cursors.data_ptr(), bins.overflow.data_ptr(), self.stream_ptr()))
         self._t1("bin_keys/kw%d" % bins.key_words, ev)
         self.launches += 1
+
+    def update_bins(self, table, bins, mode=MODE_COUNT_IF_PRESENT, plane=0, arg=1, stats=None):
+        """K2 over hash-range bins, bin after bin (``kdf_update_bins``): each bin only
+        touches its own share of the table, which therefore stays in L2."""
+        if bins.by_owner:
+            raise KdfError("update_bins needs hash-range bins")
+        ev = self._t0()
+        self._check(self.lib.kdf_update_bins(
+            table.handle, bins.n_parts, bins.data.data_ptr(), bins.bin_cap, bins.cursors.data_ptr(),
+            mode, plane, arg, stats.data_ptr() if stats is not None else None, self.stream_ptr()))
+        self._t1("update_bins/mode%d/kw%d" % (mode, bins.key_words), ev)
+        self.launches += bins.n_parts
 
     def count_bins_packed(self, k, min_child_count):
         """True when the discovery chain's count_bins call (count >= min_child_count,

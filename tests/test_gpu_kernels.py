@@ -431,6 +431,52 @@ def test_count_bins_packed_form(eng, k, n_parts):
     assert full["full"] == 1
 
 
+@pytest.mark.parametrize("k", [31, 47])
+def test_update_bins_equals_count_stream(eng, k, monkeypatch):
+    """`count --if` applied bin after bin (kdf_update_bins, the route for filter tables
+    larger than L2) gives the same per-key counts as the direct stream probe and the
+    oracle; the chain helper takes that route in chunks once the table is 'large'."""
+    from kmer_denovo_filter_b200 import engine
+    from kmer_denovo_filter_b200.discovery import kmer_chain
+    g, parent = _genome_reads(301 + k, glen=8000, n=1300)
+    parent = parent + ["", "ACGTN", g[:k]]
+    filt = sorted(kmers.count_sequences([g[1000:5000]], k))[::2]
+    want = kmers.count_sequences(parent, k)
+    ds = eng.upload(engine.pack_sequences(parent))
+    n_win = sum(want.values())
+
+    def fresh():
+        t = eng.new_table(k, n_keys=len(filt))
+        lo, hi = eng.keys_to_device(filt, t.key_words)
+        eng.update_keys(t, lo, hi, engine.MODE_INSERT_ONLY, 0, 0)
+        return t, lo, hi
+
+    t0, lo, hi = fresh()
+    eng.count_stream(t0, ds, engine.MODE_COUNT_IF_PRESENT, 0, 1, None)
+    direct = eng.lookup_keys(t0, lo, hi)[1].cpu().numpy().view(np.uint32)
+    assert direct.tolist() == [want.get(x, 0) for x in filt]
+    for n_parts in (1, 16):
+        t1, lo, hi = fresh()
+        bins = eng.new_bins(k, n_parts, bin_cap=n_win + 64)
+        eng.bin_stream(bins, ds)
+        st = eng.new_stats()
+        eng.update_bins(t1, bins, engine.MODE_COUNT_IF_PRESENT, 0, 1, st)
+        got = eng.lookup_keys(t1, lo, hi)[1].cpu().numpy().view(np.uint32)
+        assert np.array_equal(got, direct)
+        assert eng.read_stats(st)["windows"] == n_win
+    # the chain helper: force the binned route, in several chunks, with a bin retry
+    monkeypatch.setattr(kmer_chain, "PROBE_DIRECT_BYTES", 0)
+    monkeypatch.setattr(kmer_chain, "PROBE_SLICE_BYTES", 4096)
+    monkeypatch.setattr(kmer_chain, "PROBE_CHUNK_BASES", 32 * 1024)
+    monkeypatch.setattr(kmer_chain, "_bin_capacity", lambda n, p: 64)
+    t2, lo, hi = fresh()
+    st = eng.new_stats()
+    kmer_chain.count_if_present(eng, t2, ds, st)
+    got = eng.lookup_keys(t2, lo, hi)[1].cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, direct)
+    assert eng.read_stats(st)["windows"] == n_win
+
+
 def test_count_bins_packed_heavy_duplicates(eng):
     """Many concurrent copies of few keys (the saturating CAS under contention) and
     keys whose top bases are all T (state bits next to an all-ones key prefix)."""
