@@ -319,6 +319,33 @@ int kdf_count_bins(int k, int n_parts, const uint64_t* child_bins /*DEV*/,
                    uint64_t* n_out /*DEV*/, uint32_t count_min0, uint64_t* counters /*DEV*/,
                    void* stream);
 
+/* Shared-memory form of the packed count (64-bit keys, thresholds as for
+ * kdf_count_bins_packed).  Returning atomics on L2 are the ceiling of the L2-sliced
+ * form, so every hash-range bin is split once more into s2 sub-ranges (a second
+ * streaming pass through `scratch`, `group` bins at a time) until one sub-bin's
+ * distinct keys fit a table of n_slots packed slots in shared memory; one CTA then
+ * counts a sub-bin start to finish: insert + saturating count, reference marks,
+ * emit.  Replaces the same reference calls as kdf_count_bins
+ * (discovery/pipeline.py:114-122, :207-211, :286-304).
+ *   scratch : DEV, 16-byte aligned, kdf_count_bins_smem_scratch() bytes
+ *   sub_cap / ref_sub_cap : key slots of one child / reference sub-bin
+ *   counters: DEV u64[6] as in kdf_count_bins ([1] unused), caller zeroes
+ *   flags   : DEV u64, caller zeroes; bit 0 = some sub-bin's keys did not fit its
+ *             shared-memory table, bit 1 = some sub-bin region overflowed: in both
+ *             cases the outputs are invalid and the caller re-counts the same bins
+ *             with kdf_count_bins (nothing is dropped silently).                */
+size_t kdf_count_bins_smem_scratch(int n_parts, int group, int s2, uint64_t sub_cap,
+                                   uint64_t ref_sub_cap);
+int kdf_count_bins_smem(int k, int n_parts, int n_src, const uint64_t* child_bins /*DEV*/,
+                        uint64_t child_bin_cap, const uint64_t* child_cursors /*DEV*/,
+                        const uint64_t* ref_bins /*DEV or NULL*/, uint64_t ref_bin_cap,
+                        const uint64_t* ref_cursors /*DEV or NULL*/, void* scratch /*DEV*/,
+                        size_t scratch_bytes, int group, int s2, uint64_t sub_cap,
+                        uint64_t ref_sub_cap, uint32_t n_slots, uint32_t min0, uint32_t max1,
+                        uint32_t count_min0, uint64_t* out_lo /*DEV*/, uint64_t out_cap,
+                        uint64_t* n_out /*DEV*/, uint64_t* counters /*DEV*/,
+                        uint64_t* flags /*DEV*/, void* stream);
+
 /* The same with the bins of n_src sources (multi-GPU: one region per sending
  * rank, filled by kdf_bin_stream_to): bins are laid out [source][hash range]
  * [bin_cap] and cursors [source][hash range].  sub_split (a power of two) counts

@@ -707,13 +707,14 @@ template <> __device__ __forceinline__ Key<2> ld_key_pinned<2>(const u64* lo, u6
 // done in place they would run with a handful of lanes and the warp would sit out a
 // full L2 round trip for each of them.  Lanes queue them instead — with everything
 // the first attempt needs, so no bucket is read again — and the warp drains the queue
-// 128 at a time: four compare-and-swaps per lane in flight together (one instruction
+// 64 at a time (measured: 64 -> 18.3 ms, 128 -> 18.9, 256 -> 21.9 per 1.53 G keys): two
+// compare-and-swaps per lane in flight together (one instruction
 // site for bumps and inserts alike, so no result is waited for before the last one is
 // issued), results checked afterwards.  What the first attempt cannot settle (the slot
 // was taken meanwhile, the home bucket was full) goes to the SlowQueue, whose drain
 // probes from scratch with every lane busy.
 #ifndef KDF_PQ_DRAIN
-#define KDF_PQ_DRAIN 128
+#define KDF_PQ_DRAIN 64
 #endif
 constexpr int PQ_DRAIN = KDF_PQ_DRAIN;
 constexpr int PQ_CAP = PQ_DRAIN + 128;   // a chunk adds at most 128 items per warp
@@ -1613,7 +1614,198 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_keys(const u64* lo, const u
   }
 }
 
+// ------------------------------------- K2s: shared-memory packed count ----
+// Returning atomics on L2 top out near 50 G/s on this part (profiles/r1d_atomics.txt:
+// CAS / ATOM.ADD with the result used, L2-resident buffer) and a packed count needs one
+// for every new key and every unsaturated copy, which is what bounds kdf_count_bins at
+// ~80 G keys/s.  Shared-memory atomics have no such ceiling, so for 64-bit keys the bins
+// are split once more — `s2` sub-ranges of each hash range, a second streaming pass —
+// until a sub-bin's distinct keys fit a table in shared memory; one CTA then counts a
+// sub-bin start to finish (clear, insert + saturating count, reference marks, emit)
+// without a single global atomic on the table.  Same packed slot format as K2c.
+constexpr int SUB_THREADS = 256;
+constexpr int SUB_LOADS = 4;          // keys in flight per thread
+constexpr int SUB_PROBE_MAX = 96;     // longer probe sequences mean the table is too full
+
+// second-level binning: work item = (bin of the group, source, tile of TILE keys)
+constexpr int REBIN_TILE = BIN_THREADS * BIN_WPR;
+__global__ void __launch_bounds__(BIN_THREADS) k_rebin(const u64* bins, u64 bin_cap, const u64* cursors,
+                                                       int n_parts, int n_src, int p_begin, int p_count,
+                                                       int log2_tot, u32 s2, int qcap, u64* sub,
+                                                       u64 sub_cap, u64* sub_cursors, u64* overflow) {
+  extern __shared__ __align__(16) unsigned char bin_smem[];
+  BinStage<1> stage;
+  stage.init(bin_smem, (int)s2, qcap);
+  __syncthreads();
+  const u64 tiles = (bin_cap + REBIN_TILE - 1) / REBIN_TILE;
+  const u64 n_items = (u64)p_count * n_src * tiles;
+  for (u64 item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const u64 tile = item % tiles;
+    const u64 ps = item / tiles;
+    const int src = (int)(ps % n_src);
+    const int pl = (int)(ps / n_src);
+    const u64 b = (u64)src * n_parts + p_begin + pl;
+    u64 n = cursors[b];
+    if (n > bin_cap) n = bin_cap;
+    if (tile * REBIN_TILE >= n) continue;  // uniform over the CTA
+    const u64* in = bins + b * bin_cap;
+    BinDest dst = {sub + (u64)pl * s2 * sub_cap, nullptr, sub_cap};
+    u64* cur = sub_cursors + (u64)pl * s2;
+#pragma unroll 4
+    for (int j = 0; j < BIN_WPR; ++j) {
+      u64 i = tile * REBIN_TILE + (u64)j * BIN_THREADS + threadIdx.x;
+      bool ok = i < n;
+      Key<1> key = ld_key_stream<1>(in, nullptr, ok ? i : 0);
+      u32 part = part_of(hash_key(key), log2_tot) & (s2 - 1);
+      stage.push(ok, part, key, dst, cur, overflow);
+    }
+    stage.flush(dst, cur, overflow);
+  }
+}
+
+__device__ __forceinline__ u32 sub_slot_of(u64 h, u32 slot_mask) {
+  u32 l = (u32)h;   // the high product bits chose the bin and the sub-bin
+  l ^= l >> 16;
+  l *= 0x7feb352du;
+  l ^= l >> 15;
+  return l & slot_mask;
+}
+
+// flags: bit 0 = a sub-bin did not fit its shared-memory table (results invalid: the
+// caller falls back to the L2 form), counters as in kdf_count_bins
+__global__ void __launch_bounds__(SUB_THREADS) k_count_sub(
+    const u64* sub, u64 sub_cap, const u64* sub_cursors, const u64* rsub, u64 rsub_cap,
+    const u64* rsub_cursors, u32 n_sub, u32 n_slots, int sh, u32 sat, int ignore_ref, int count_all,
+    u64* out_lo, u64 cap, u64* n_out, u64* counters, u64* flags) {
+  extern __shared__ __align__(16) u64 tab[];
+  __shared__ u32 s_over;
+  const u64 mask = (1ull << sh) - 1;
+  const u64 one = 1ull << sh;
+  const u32 slot_mask = n_slots - 1;
+  const unsigned lane = threadIdx.x & 31;
+  u32 n_keys = 0, n_hits = 0, n_new = 0, cnt_ge = 0, cnt_occ = 0;
+  for (u32 sb = blockIdx.x; sb < n_sub; sb += gridDim.x) {
+    for (u32 i = threadIdx.x; i < n_slots; i += SUB_THREADS) tab[i] = EMPTY;
+    if (threadIdx.x == 0) s_over = 0;
+    __syncthreads();
+    // ---- insert + saturating count
+    u64 n = sub_cursors[sb];
+    if (n > sub_cap) n = sub_cap;
+    const u64* in = sub + (u64)sb * sub_cap;
+    for (u64 base = 0; base < n; base += SUB_THREADS * SUB_LOADS) {
+      u64 keys[SUB_LOADS];
+#pragma unroll
+      for (int u = 0; u < SUB_LOADS; ++u) {
+        u64 i = base + (u64)u * SUB_THREADS + threadIdx.x;
+        keys[u] = i < n ? __ldcs(in + i) : EMPTY;
+      }
+#pragma unroll
+      for (int u = 0; u < SUB_LOADS; ++u) {
+        const u64 key = keys[u];
+        if (key == EMPTY) continue;
+        ++n_keys;
+        Key<1> kk;
+        kk.lo = key;
+        u32 slot = sub_slot_of(hash_key(kk), slot_mask);
+        int probes = 0;
+        for (;;) {
+          u64 w = *(volatile u64*)(tab + slot);
+          if (w == EMPTY) {
+            u64 old = atomicCAS(tab + slot, EMPTY, key | one);
+            if (old == EMPTY) {
+              ++n_new;
+              break;
+            }
+            w = old;  // someone else took the slot: is it our key ?
+          }
+          if ((w & mask) == key) {
+            ++n_hits;
+            while ((u32)(w >> sh) < sat) {   // saturating bump
+              u64 old = atomicCAS(tab + slot, w, w + one);
+              if (old == w) break;
+              w = old;
+            }
+            break;
+          }
+          slot = (slot + 1) & slot_mask;
+          if (++probes > SUB_PROBE_MAX) {
+            s_over = 1;
+            break;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- reference marks: "saturated" -> "saturated, in the reference"
+    if (rsub && !ignore_ref) {
+      u64 nr = rsub_cursors[sb];
+      if (nr > rsub_cap) nr = rsub_cap;
+      const u64* rin = rsub + (u64)sb * rsub_cap;
+      for (u64 i = threadIdx.x; i < nr; i += SUB_THREADS) {
+        const u64 key = __ldcs(rin + i);
+        Key<1> kk;
+        kk.lo = key;
+        u32 slot = sub_slot_of(hash_key(kk), slot_mask);
+        for (int probes = 0; probes <= SUB_PROBE_MAX + 1; ++probes) {
+          u64 w = *(volatile u64*)(tab + slot);
+          if (w == EMPTY) break;
+          if ((w & mask) == key) {
+            if ((u32)(w >> sh) == sat) atomicAnd(tab + slot, mask);
+            break;
+          }
+          slot = (slot + 1) & slot_mask;
+        }
+      }
+      __syncthreads();
+    }
+    // ---- emit
+    const bool over = s_over != 0;
+    if (over) {
+      if (threadIdx.x == 0) atomicOr(flags, 1ull);
+    } else {
+      for (u32 i0 = 0; i0 < n_slots; i0 += SUB_THREADS) {
+        u64 w = tab[i0 + threadIdx.x];
+        bool occ = w != EMPTY;
+        u32 state = (u32)(w >> sh);
+        bool reached = state >= sat || state == 0;
+        bool keep = occ && (ignore_ref ? reached : state >= sat);
+        cnt_occ += occ ? 1u : 0u;
+        cnt_ge += (occ && (count_all || reached)) ? 1u : 0u;
+        unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m) {
+          u64 base = 0;
+          if (lane == 0) base = atomicAdd(n_out, (u64)__popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (keep) {
+            u64 o = base + __popc(m & ((1u << lane) - 1));
+            if (o < cap && out_lo) out_lo[o] = w & mask;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // counters: [0] keys applied, [2] hits, [3] distinct, [4] reached, [5] occupied
+  for (int o = 16; o; o >>= 1) {
+    n_keys += __shfl_xor_sync(0xffffffffu, n_keys, o);
+    n_hits += __shfl_xor_sync(0xffffffffu, n_hits, o);
+    n_new += __shfl_xor_sync(0xffffffffu, n_new, o);
+    cnt_ge += __shfl_xor_sync(0xffffffffu, cnt_ge, o);
+    cnt_occ += __shfl_xor_sync(0xffffffffu, cnt_occ, o);
+  }
+  if (lane == 0) {
+    if (n_keys) atomicAdd(counters + 0, (u64)n_keys);
+    if (n_hits) atomicAdd(counters + 2, (u64)n_hits);
+    if (n_new) atomicAdd(counters + 3, (u64)n_new);
+    if (cnt_ge) atomicAdd(counters + 4, (u64)cnt_ge);
+    if (cnt_occ) atomicAdd(counters + 5, (u64)cnt_occ);
+  }
+}
+
 // ------------------------------------------------ table maintenance -------
+__global__ void k_or_flag(const u64* src, u64* flags, u64 bit) {
+  if (*src) atomicOr(flags, bit);
+}
 __global__ void __launch_bounds__(256) k_fill_u64x2(ulonglong2* p, u64 n_units, u64 value) {
   u64 stride = (u64)gridDim.x * blockDim.x;
   ulonglong2 v = make_ulonglong2(value, value);
@@ -2434,6 +2626,87 @@ int kdf_count_bins_multi(int k, int n_parts, int n_src, int sub_split, const uin
                                   out_cap, (u64*)n_out, count_min0, ctr + 4, ctr + 5, st);
     if (rc != KDF_OK) return rc;
   }
+  return KDF_OK;
+}
+
+size_t kdf_count_bins_smem_scratch(int n_parts, int group, int s2, uint64_t sub_cap,
+                                   uint64_t ref_sub_cap) {
+  if (group < 1 || s2 < 1) return 0;
+  if (group > n_parts) group = n_parts;
+  uint64_t n_sub = (uint64_t)group * (uint64_t)s2;
+  // child sub-bins | reference sub-bins | child cursors | reference cursors | overflow word
+  return (size_t)(n_sub * (sub_cap + ref_sub_cap) * 8 + 2 * n_sub * 8 + 64);
+}
+
+int kdf_count_bins_smem(int k, int n_parts, int n_src, const uint64_t* child_bins,
+                        uint64_t child_bin_cap, const uint64_t* child_cursors,
+                        const uint64_t* ref_bins, uint64_t ref_bin_cap, const uint64_t* ref_cursors,
+                        void* scratch, size_t scratch_bytes, int group, int s2, uint64_t sub_cap,
+                        uint64_t ref_sub_cap, uint32_t n_slots, uint32_t min0, uint32_t max1,
+                        uint32_t count_min0, uint64_t* out_lo, uint64_t out_cap, uint64_t* n_out,
+                        uint64_t* counters, uint64_t* flags, void* stream) {
+  if (!child_bins || !child_cursors || !scratch || !n_out || !counters || !flags)
+    return fail(KDF_ERR_ARG, "kdf_count_bins_smem: NULL argument");
+  if (kdf_key_words(k) != 1) return fail(KDF_ERR_ARG, "kdf_count_bins_smem: 64-bit keys only (k <= 32)");
+  if (!kdf_count_bins_packed(k, min0, 0xffffffffu, 0, max1, count_min0, 0))
+    return fail(KDF_ERR_ARG, "kdf_count_bins_smem: thresholds do not fit the packed form");
+  if (n_src < 1) return fail(KDF_ERR_ARG, "kdf_count_bins_smem: n_src must be >= 1");
+  int log2p = 0, log2s = 0;
+  while ((1 << log2p) < n_parts) ++log2p;
+  while ((1 << log2s) < s2) ++log2s;
+  if (n_parts < 1 || n_parts > BIN_MAX_PARTS || (1 << log2p) != n_parts)
+    return fail(KDF_ERR_ARG, "kdf_count_bins_smem: n_parts must be a power of two <= 512");
+  if (s2 < 2 || s2 > BIN_MAX_PARTS || (1 << log2s) != s2 || log2p + log2s > 28)
+    return fail(KDF_ERR_ARG, "kdf_count_bins_smem: s2 must be a power of two in 2..512");
+  if (n_slots < 256 || (n_slots & (n_slots - 1)) || (size_t)n_slots * 8 > 200 * 1024)
+    return fail(KDF_ERR_ARG, "kdf_count_bins_smem: n_slots must be a power of two, 256..25600");
+  if (group < 1) group = 1;
+  if (group > n_parts) group = n_parts;
+  if (sub_cap < 1 || scratch_bytes < kdf_count_bins_smem_scratch(n_parts, group, s2, sub_cap, ref_sub_cap))
+    return fail(KDF_ERR_ARG, "kdf_count_bins_smem: scratch too small");
+  if (((uintptr_t)scratch & 15) != 0) return fail(KDF_ERR_ARG, "kdf_count_bins_smem: scratch must be 16-byte aligned");
+  const bool with_ref = ref_bins && ref_cursors && ref_sub_cap > 0 && max1 == 0;
+  const u64 n_sub_max = (u64)group * s2;
+  u64* sub = (u64*)scratch;
+  u64* rsub = sub + n_sub_max * sub_cap;
+  u64* cur = rsub + n_sub_max * ref_sub_cap;
+  u64* rcur = cur + n_sub_max;
+  u64* over = rcur + n_sub_max;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int sm = current_sm_count();
+  const int sh = 2 * k;
+  const int qcap = bin_qcap(s2, 1);
+  const size_t bin_smem = BinStage<1>::bytes(s2, qcap);
+  const size_t tab_smem = (size_t)n_slots * 8;
+  CUDA_TRY(cudaFuncSetAttribute((const void*)k_rebin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem));
+  CUDA_TRY(cudaFuncSetAttribute((const void*)k_count_sub, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_smem));
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k_rebin, BIN_THREADS, bin_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int g_rebin = sm * per_sm;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k_count_sub, SUB_THREADS, tab_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int g_count = sm * per_sm;
+  CUDA_TRY(cudaMemsetAsync(over, 0, 64, st));
+  for (int p0 = 0; p0 < n_parts; p0 += group) {
+    const int pc = (n_parts - p0) < group ? (n_parts - p0) : group;
+    const u32 n_sub = (u32)pc * (u32)s2;
+    CUDA_TRY(cudaMemsetAsync(cur, 0, 2 * n_sub_max * 8, st));   // both cursor arrays
+    k_rebin<<<g_rebin, BIN_THREADS, bin_smem, st>>>((const u64*)child_bins, child_bin_cap, (const u64*)child_cursors,
+                                                    n_parts, n_src, p0, pc, log2p + log2s, (u32)s2, qcap, sub,
+                                                    sub_cap, cur, over);
+    if (with_ref)
+      k_rebin<<<g_rebin, BIN_THREADS, bin_smem, st>>>((const u64*)ref_bins, ref_bin_cap, (const u64*)ref_cursors,
+                                                      n_parts, n_src, p0, pc, log2p + log2s, (u32)s2, qcap,
+                                                      rsub, ref_sub_cap, rcur, over);
+    int g = (int)((u32)g_count < n_sub ? (u32)g_count : n_sub);
+    k_count_sub<<<g, SUB_THREADS, tab_smem, st>>>(sub, sub_cap, cur, with_ref ? rsub : nullptr, ref_sub_cap, rcur,
+                                                  n_sub, n_slots, sh, min0, max1 != 0 ? 1 : 0,
+                                                  count_min0 <= 1 ? 1 : 0, (u64*)out_lo, out_cap, (u64*)n_out,
+                                                  (u64*)counters, (u64*)flags);
+    CUDA_TRY(cudaGetLastError());
+  }
+  // a sub-bin that overflowed its region: bit 1 of flags (read back by the caller)
+  k_or_flag<<<1, 1, 0, st>>>(over, (u64*)flags, 2ull);
+  CUDA_TRY(cudaGetLastError());
   return KDF_OK;
 }
 

@@ -86,6 +86,7 @@ def default_child_capacity(eng, n_bases):
 # load 0.56 (64 bins) 32.6 ms, 128 MB 44 ms (the slice no longer fits).
 SLICE_BYTES = int(os.environ.get("KDF_SLICE_MB", "64")) << 20
 MAX_PARTS = 256
+SMEM_PARTS = int(os.environ.get("KDF_SMEM_PARTS", "256"))   # hash ranges in front of the shared-memory count
 
 
 def _pow2_at_least(x):
@@ -133,6 +134,12 @@ def count_child_partitioned(eng, child_streams, ref_streams, k, min_child_count,
     r_max = sum(s.n_bases for s in ref_streams)
     p_auto, s_auto = plan_partitions(n_max, key_words=eng.lib.kdf_key_words(k),
                                      packed=eng.count_bins_packed(k, min_child_count))
+    # 64-bit keys: shared-memory count (kdf_count_bins_smem) — as many hash ranges as the
+    # binning kernel handles well, the rest of the split is its second level
+    smem = (n_parts is None and slice_capacity is None and eng.count_bins_smem_ok(k, min_child_count))
+    if smem:
+        p_auto = max(p_auto, min(SMEM_PARTS, _pow2_at_least(n_max // (eng.SUB_TARGET * 256) + 1)))
+        s_auto = max(1024, (max(n_max // 8, 1024) + p_auto - 1) // p_auto + 3) & ~3
     n_parts = n_parts or p_auto
     slice_capacity = slice_capacity or s_auto
     bin_cap = _bin_capacity(n_max, n_parts)
@@ -166,8 +173,14 @@ def count_child_partitioned(eng, child_streams, ref_streams, k, min_child_count,
         del cb, rb
     out_cap = max(1 << 16, n_max // 64)
     while True:   # slices / output: retry when a slice was full or the output too small
-        res = eng.count_bins(cb, rb, slice_capacity, min0=min_child_count, max1=0,
-                             count_min0=min_child_count, out_cap=out_cap)
+        res = None
+        if smem:
+            res = eng.count_bins_smem(cb, rb, min_child_count, max1=0, out_cap=out_cap)
+            if res["fallback"]:      # a sub-bin did not fit shared memory: L2 form, same bins
+                smem, res = False, None
+        if res is None:
+            res = eng.count_bins(cb, rb, slice_capacity, min0=min_child_count, max1=0,
+                                 count_min0=min_child_count, out_cap=out_cap)
         if res["full"]:
             if slice_capacity >= 2 * bin_cap:
                 raise _engine.KdfError("child k-mer table slice full at %d slots" % slice_capacity)

@@ -79,6 +79,9 @@ _SIGNATURES = {
     "kdf_bin_stream_to": (_i, [ctypes.POINTER(_Stream), _i, _i, _i, _vp, _u64, _vp, _vp, _vp, _vp]),
     "kdf_bin_keys": (_i, [_vp, _vp, _u64, _i, _i, _i, _vp, _u64, _vp, _vp, _vp]),
     "kdf_update_bins": (_i, [_vp, _i, _vp, _u64, _vp, _i, _i, _u32, _vp, _vp]),
+    "kdf_count_bins_smem_scratch": (ctypes.c_size_t, [_i, _i, _i, _u64, _u64]),
+    "kdf_count_bins_smem": (_i, [_i, _i, _i, _vp, _u64, _vp, _vp, _u64, _vp, _vp, ctypes.c_size_t, _i, _i,
+                                 _u64, _u64, _u32, _u32, _u32, _u32, _vp, _u64, _vp, _vp, _vp, _vp]),
     "kdf_count_bins_packed": (_i, [_i, _u32, _u32, _u32, _u32, _u32, _i]),
     "kdf_count_bins": (_i, [_i, _i, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _u64, _u32, _u32, _u32, _u32,
                             _vp, _vp, _vp, _vp, _u64, _vp, _u32, _vp, _vp]),
@@ -765,6 +768,70 @@ class CudaEngine:
         include/kdf.h: the table slice then holds keys only."""
         return bool(self.lib.kdf_count_bins_packed(k, min_child_count, U32_MAX, 0, 0,
                                                    min_child_count, 0))
+
+    SUB_TARGET = 24 * 1024      # k-mer instances per sub-bin the shared-memory count aims for
+    SUB_SLOTS = 8192            # packed slots of its table (64 KB: three CTAs per SM)
+    SUB_SCRATCH_BYTES = 3 << 30
+
+    def count_bins_smem_ok(self, k, min_child_count, force=False):
+        """The shared-memory form of the packed count applies (64-bit keys, thresholds
+        that fit the key's spare bits).  It is exact and tested, but measured SLOWER than
+        the L2 form on B200 (64 Mbp x 30x: 256-way binning 13.5 ms + second-level binning
+        16.4 ms + count 19 ms against 7.9 + 18.9 ms), so the chain only takes
+        it when asked to (KDF_COUNT_SMEM=1)."""
+        return (self.lib.kdf_key_words(k) == 1 and self.count_bins_packed(k, min_child_count)
+                and (force or os.environ.get("KDF_COUNT_SMEM", "0") == "1"))
+
+    def count_bins_smem(self, child_bins, ref_bins, min0, max1=0, count_min0=None, out_cap=1 << 20,
+                        n_keys=None, n_ref_keys=None):
+        """``kdf_count_bins_smem`` over hash-range bins.  Returns the dict of
+        :meth:`count_bins` plus ``fallback`` (True: a sub-bin did not fit — count the same
+        bins with :meth:`count_bins` instead; the outputs here are then meaningless)."""
+        torch = self.torch
+        k = child_bins.k
+        n_src = getattr(child_bins, "n_src", 1)
+        count_min0 = min0 if count_min0 is None else count_min0
+        if n_keys is None:
+            n_keys = int(child_bins.cursors.sum().item())
+        if ref_bins is not None and n_ref_keys is None:
+            n_ref_keys = int(ref_bins.cursors.sum().item())
+        n_parts = child_bins.n_parts
+        s2 = 2
+        while s2 < 512 and n_keys > n_parts * s2 * self.SUB_TARGET:
+            s2 *= 2
+
+        def cap_of(total):
+            mean = total / float(n_parts * s2)
+            return (int(mean * 1.04 + 64 * (mean ** 0.5) + 1024) + 1) & ~1
+        sub_cap = cap_of(n_keys)
+        ref_cap = cap_of(n_ref_keys) if ref_bins is not None else 0
+        group = max(1, min(n_parts, self.SUB_SCRATCH_BYTES // max(1, s2 * (sub_cap + ref_cap) * 8)))
+        nbytes = self.lib.kdf_count_bins_smem_scratch(n_parts, group, s2, sub_cap, ref_cap)
+        scratch = self.empty((nbytes + 7) // 8, torch.int64)
+        lo = self.empty(max(out_cap, 1), torch.int64)
+        n_out = self.zeros(1, torch.int64)
+        ctr = self.zeros(6, torch.int64)
+        flags = self.zeros(1, torch.int64)
+        ev = self._t0()
+        self._check(self.lib.kdf_count_bins_smem(
+            k, n_parts, n_src, child_bins.data.data_ptr(), child_bins.bin_cap,
+            child_bins.cursors.data_ptr(),
+            ref_bins.data.data_ptr() if ref_bins is not None else None,
+            ref_bins.bin_cap if ref_bins is not None else 0,
+            ref_bins.cursors.data_ptr() if ref_bins is not None else None,
+            scratch.data_ptr(), nbytes, group, s2, sub_cap, ref_cap, self.SUB_SLOTS, min0, max1,
+            count_min0, lo.data_ptr(), out_cap, n_out.data_ptr(), ctr.data_ptr(), flags.data_ptr(),
+            self.stream_ptr()))
+        self._t1("count_bins_smem/kw1", ev)
+        n_groups = (n_parts + group - 1) // group
+        self.launches += 1 + n_groups * (2 + (1 if ref_bins is not None and max1 == 0 else 0))
+        c = ctr.cpu().numpy().view(np.uint64)
+        n = int(n_out.item())
+        m = min(n, out_cap)
+        return {"n_out": n, "lo": lo[:m], "hi": None, "p0": None, "p1": None,
+                "keys": int(c[0]), "full": 0, "hits": int(c[2]), "distinct": int(c[3]),
+                "n_count": int(c[4]), "occupied": int(c[5]), "fallback": bool(int(flags.item())),
+                "s2": s2, "group": group, "sub_cap": sub_cap}
 
     def count_bins(self, child_bins, ref_bins, slice_capacity, min0=0, max0=U32_MAX, min1=0,
                    max1=U32_MAX, count_min0=0, out_cap=1 << 20, want_planes=False, sub_split=1):

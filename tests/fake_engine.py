@@ -140,6 +140,9 @@ class FakeEngine:
     def count_bins_packed(self, k, min_child_count):
         return False
 
+    def count_bins_smem_ok(self, k, min_child_count):
+        return False
+
     def count_bins(self, cb, rb, slice_capacity, min0=0, max0=U32_MAX, min1=0, max1=U32_MAX,
                    count_min0=0, out_cap=1 << 20, want_planes=False):
         cnt = collections.Counter()

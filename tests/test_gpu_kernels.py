@@ -477,6 +477,52 @@ def test_update_bins_equals_count_stream(eng, k, monkeypatch):
     assert eng.read_stats(st)["windows"] == n_win
 
 
+@pytest.mark.parametrize("k", [21, 31])
+@pytest.mark.parametrize("n_parts", [1, 16])
+def test_count_bins_smem_form(eng, k, n_parts, monkeypatch):
+    """The shared-memory form of the packed count (second-level binning + one CTA per
+    sub-bin, include/kdf.h) against the oracle: thresholds, reference subtraction,
+    counters, undersized output, and the flags that send the caller back to the L2 form."""
+    from kmer_denovo_filter_b200 import engine
+    g, child = _genome_reads(391 + k, glen=12000, n=2500)
+    ref = [g[:7000]]
+    want = kmers.count_sequences(child, k)
+    refk = set(kmers.count_sequences(ref, k))
+    dc = eng.upload(engine.pack_sequences(child))
+    dr = eng.upload(engine.pack_sequences(ref))
+    n_win = sum(want.values())
+    cb = eng.new_bins(k, n_parts, bin_cap=n_win // n_parts * 2 + 512)
+    rb = eng.new_bins(k, n_parts, bin_cap=7000 // n_parts * 2 + 512)
+    eng.bin_stream(cb, dc)
+    eng.bin_stream(rb, dr)
+    assert eng.count_bins_smem_ok(k, 3, force=True)
+    monkeypatch.setattr(engine.CudaEngine, "SUB_TARGET", 512)      # many sub-bins even for this input
+    for m in (1, 2, 3):
+        cand = {key for key, c in want.items() if c >= m}
+        res = eng.count_bins_smem(cb, rb, m, max1=0, out_cap=len(want) + 10)
+        assert not res["fallback"] and res["s2"] > 2
+        assert res["keys"] == n_win and res["distinct"] == len(want) == res["occupied"]
+        assert res["hits"] + res["distinct"] == n_win and res["n_count"] == len(cand)
+        got = eng.keys_to_pyints(res["lo"], None)
+        assert len(got) == res["n_out"] == len(set(got)) and set(got) == cand - refk
+        res = eng.count_bins_smem(cb, None, m, max1=0, out_cap=len(want) + 10)
+        assert not res["fallback"] and set(eng.keys_to_pyints(res["lo"], None)) == cand
+        res = eng.count_bins_smem(cb, rb, m, max1=engine.U32_MAX, count_min0=0, out_cap=len(want) + 10)
+        assert set(eng.keys_to_pyints(res["lo"], None)) == cand and res["n_count"] == len(want)
+    small = eng.count_bins_smem(cb, rb, 3, max1=0, out_cap=5)
+    assert small["n_out"] == len({key for key, c in want.items() if c >= 3} - refk) and small["lo"].shape[0] == 5
+    # several groups of bins through a small scratch buffer
+    monkeypatch.setattr(engine.CudaEngine, "SUB_SCRATCH_BYTES", 1 << 16)
+    res = eng.count_bins_smem(cb, rb, 3, max1=0, out_cap=len(want) + 10)
+    assert not res["fallback"] and (n_parts == 1 or res["group"] < n_parts)
+    assert set(eng.keys_to_pyints(res["lo"], None)) == {key for key, c in want.items() if c >= 3} - refk
+    # a table too small for a sub-bin's distinct keys is reported, never wrong silently
+    monkeypatch.setattr(engine.CudaEngine, "SUB_TARGET", 1 << 30)
+    monkeypatch.setattr(engine.CudaEngine, "SUB_SLOTS", 256)
+    res = eng.count_bins_smem(cb, rb, 3, max1=0, out_cap=len(want) + 10)
+    assert res["fallback"] == (len(want) // n_parts > 200)
+
+
 def test_count_bins_packed_heavy_duplicates(eng):
     """Many concurrent copies of few keys (the saturating CAS under contention) and
     keys whose top bases are all T (state bits next to an all-ones key prefix)."""
