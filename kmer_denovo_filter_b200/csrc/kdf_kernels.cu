@@ -415,6 +415,17 @@ __global__ void __launch_bounds__(256) k_extract(StreamView s, int k, u64* out_l
   }
 }
 
+// two filter bits of a key inside one 32-bit word (low product bits: independent of
+// the bucket index, which comes from the high ones)
+constexpr int PF_WORDS = 4096;
+__device__ __forceinline__ void pf_bits(u64 h, u32& word, u32& bits) {
+  u32 l = (u32)h;
+  l ^= l >> 15;
+  l *= 0x2C1B3C6Du;
+  word = l & (u32)(PF_WORDS - 1);
+  bits = (1u << (l >> 27)) | (1u << ((l >> 22) & 31u));
+}
+
 // ------------------------------------------------------------- K2 ---------
 // One fast-path decision per probe: for probing ops "bucket has an empty slot
 // and no match" (a miss, the common case against a filter set), for inserting
@@ -427,9 +438,27 @@ __global__ void __launch_bounds__(SMEM ? 512 : 256, SMEM ? KDF_SMEM_BLOCKS : (KW
   constexpr bool kInsert = (OP == OP_INSERT_COUNT || OP == OP_INSERT_ONLY);
   constexpr int S = SPB<KW>::v;
   static_assert(!(SMEM && kInsert), "shared-memory tables are read-only");
+  // Shared-memory tables are small read-only sets (the proband-unique k-mers, VCF-mode
+  // filter sets) that almost no window hits, and a bucket probe from shared memory costs
+  // two 128-bit loads with bank conflicts plus the compares: the ncu profile of the scan
+  // showed l1tex at 78 %.  A 16 KB two-bit filter built next to the table answers
+  // "certainly absent" for > 99 % of the windows with one 32-bit load.
+  u32* pf = reinterpret_cast<u32*>(sm_keys + (SMEM ? (size_t)t.n_buckets * 4 * KW : 0));
   if (SMEM) {
     u32 n = t.n_buckets * 4 * KW;
     for (u32 i = threadIdx.x; i < n; i += blockDim.x) sm_keys[i] = __ldg(t.keys + i);
+    for (u32 i = threadIdx.x; i < (u32)PF_WORDS; i += blockDim.x) pf[i] = 0;
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < t.n_buckets * S; i += blockDim.x) {
+      Key<KW> key;
+      key.lo = sm_keys[(size_t)i * KW];
+      if (KW == 2) ((u64*)&key)[KW - 1] = sm_keys[(size_t)i * KW + (KW - 1)];
+      if (!is_empty_key(key)) {
+        u32 word, bits;
+        pf_bits(hash_key(key), word, bits);
+        atomicOr(pf + word, bits);
+      }
+    }
     __syncthreads();
   }
   __shared__ SlowQueue<KW> sq[(SMEM ? 512 : 256) / 32];
@@ -452,23 +481,34 @@ __global__ void __launch_bounds__(SMEM ? 512 : 256, SMEM ? KDF_SMEM_BLOCKS : (KW
       Key<KW> keys[CHUNK];
       Bucket<KW> bk[CHUNK];
       u32 bidx[CHUNK];
-      u32 okm = 0;
+      u32 okm = 0, probe = 0;
 #pragma unroll
       for (int u = 0; u < CHUNK; ++u) {
         bool ok = it.ok();
         keys[u] = it.canonical();
         it.advance();
-        bidx[u] = bucket_of(hash_key(keys[u]), t.log2_parts, t.n_buckets);
+        const u64 h = hash_key(keys[u]);
+        bidx[u] = bucket_of(h, t.log2_parts, t.n_buckets);
         if (ok) {
           okm |= 1u << u;
-          bk[u] = SMEM ? lds_bucket<KW>(sm_keys + (u64)bidx[u] * 4 * KW) : ld_bucket<KW>(t.keys + (u64)bidx[u] * 4 * KW);
+          if (SMEM) {
+            u32 word, bits;
+            pf_bits(h, word, bits);
+            if ((pf[word] & bits) == bits) {
+              probe |= 1u << u;
+              bk[u] = lds_bucket<KW>(sm_keys + (u64)bidx[u] * 4 * KW);
+            }
+          } else {
+            probe |= 1u << u;
+            bk[u] = ld_bucket<KW>(t.keys + (u64)bidx[u] * 4 * KW);
+          }
         }
       }
       st.windows += __popc(okm);
       u64 pos0 = (w << 5) + c * CHUNK;
 #pragma unroll
       for (int u = 0; u < CHUNK; ++u) {
-        if (okm & (1u << u)) {
+        if (probe & (1u << u)) {
           int j = match_in(bk[u], keys[u]);
           if (j >= 0) {  // found in the home bucket
             st.hits++;
@@ -1907,7 +1947,7 @@ static int launch_stream(const kdf_table* t, const StreamView& v, int plane, u32
                          const HitSink& sink, cudaStream_t st) {
   TableView<KW> tv = view_of_table<KW>(t);
   const void* fn = (const void*)k_stream<KW, OP, SMEM, CHUNK>;
-  size_t smem = SMEM ? (size_t)tv.n_buckets * 32 * KW : 0;
+  size_t smem = SMEM ? (size_t)tv.n_buckets * 32 * KW + (size_t)PF_WORDS * 4 : 0;
   int block = SMEM ? 512 : 256;
   if (SMEM) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int g = grid_for(fn, block, smem, v.n_words, t->sm_count);
