@@ -362,6 +362,33 @@ int kdf_count_bins_multi(int k, int n_parts, int n_src, int sub_split,
                          uint64_t* n_out /*DEV*/, uint32_t count_min0, uint64_t* counters /*DEV*/,
                          void* stream);
 
+/* ---- K7: coverage of the reference by hit k-mers -------------------------
+ * Replaces _collect_kmer_ref_positions (core/bam_scanner.py:97-117) and the
+ * per-contig Counter merges of _anchor_and_cluster (discovery/pipeline.py:851-855)
+ * for the informative reads of one batch.  Hits are (read index into the arrays
+ * below, window start inside the read), sorted by (read, start).  Per read:
+ * contig id, 0-based reference start, and BAM CIGAR words (len << 4 | op) at
+ * cigar[read_cig_off[r] .. read_cig_off[r+1]).  Output: n_out runs of
+ *   key   = contig << 40 | ref_pos << 1 | first      (sorted ascending)
+ *   count = hit k-mers covering ref_pos with that `first` flag
+ * `first` = 1 for the keys of a (read, position) seen for the first time in that read,
+ * so sum(count) over both flags is the k-mer coverage and sum over first == 1 the number
+ * of reads (the reference's read_coverage).  The last run may be the all-ones padding
+ * key: ignore it.  out_keys / out_counts need n_hits * k entries.             */
+size_t kdf_hit_coverage_scratch_bytes(uint64_t n_hits, int k);
+int kdf_hit_coverage(const uint32_t* hit_read /*DEV*/, const uint32_t* hit_off /*DEV*/,
+                     uint64_t n_hits, int k, const int32_t* read_contig /*DEV*/,
+                     const int64_t* read_ref_start /*DEV*/, const uint64_t* read_cig_off /*DEV*/,
+                     const uint32_t* cigar /*DEV*/, void* scratch /*DEV*/, size_t scratch_bytes,
+                     uint64_t* out_keys /*DEV*/, uint32_t* out_counts /*DEV*/,
+                     uint64_t* n_out /*DEV*/, void* stream);
+/* the same expansion on the host (test hook, host pointers): keys[n_hits * k],
+ * unused entries all ones, unsorted                                          */
+int kdf_debug_hit_coverage_host(const uint32_t* hit_read, const uint32_t* hit_off, uint64_t n_hits,
+                                int k, const int32_t* read_contig, const int64_t* read_ref_start,
+                                const uint64_t* read_cig_off, const uint32_t* cigar,
+                                uint64_t* keys);
+
 /* ---- host helpers (CPU, no device) --------------------------------------
  * Pack ASCII sequences into the stream layout.  seqs: concatenated bytes,
  * offsets[n_seqs+1].  Returns the stream length in bases (sum of lengths +

@@ -307,4 +307,39 @@ template <> struct WindowAt<2> {
   }
 };
 
+// ---------------------------------------------------- K7: hit coverage ----
+// Reference positions under one hit window (core/bam_scanner.py:97-117
+// _collect_kmer_ref_positions): query positions off .. off+k-1 that a CIGAR M / = / X
+// operation aligns.  One key per covered base, (contig << 40) | (ref_pos << 1) | first,
+// where `first` says that no earlier hit of the same read covers the base (hits of a
+// read come sorted by offset, so that is "query position >= prev_end"): counting all
+// keys of a position gives the k-mer coverage, counting the `first` ones the number of
+// reads.  cigar words are BAM's (len << 4 | op).  Returns the number of keys written.
+KDF_HD int expand_hit(const u32* cigar, u64 n_ops, long long ref_start, u32 off, int k, u32 prev_end,
+                      u64 contig, u64* out) {
+  int n = 0;
+  u64 q = 0;
+  long long r = ref_start;
+  const u64 lo = off, hi = (u64)off + (u64)k;
+  for (u64 i = 0; i < n_ops && q < hi; ++i) {
+    const u32 op = cigar[i] & 15u;
+    const u64 len = cigar[i] >> 4;
+    if (op == 0 || op == 7 || op == 8) {
+      const u64 a = q > lo ? q : lo;
+      const u64 b = (q + len) < hi ? (q + len) : hi;
+      for (u64 qq = a; qq < b; ++qq) {
+        const long long rp = r + (long long)(qq - q);
+        out[n++] = (contig << 40) | (((u64)rp & 0x7fffffffffull) << 1) | (qq >= prev_end ? 1ull : 0ull);
+      }
+      q += len;
+      r += (long long)len;
+    } else if (op == 1 || op == 4) {
+      q += len;
+    } else if (op == 2 || op == 3) {
+      r += (long long)len;
+    }
+  }
+  return n;
+}
+
 }  // namespace kdf

@@ -33,6 +33,7 @@
 #include <type_traits>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_run_length_encode.cuh>
 
 #include "../../include/kdf.h"
 #include "kdf_device.cuh"
@@ -1842,6 +1843,24 @@ __global__ void __launch_bounds__(SUB_THREADS) k_count_sub(
   }
 }
 
+// ------------------------------------------------------------- K7 ---------
+// One thread per hit: the keys of its covered reference bases into keys[h * k ..),
+// unused slots padded with all ones (they sort last).  Hits are sorted by (read, offset).
+__global__ void __launch_bounds__(128) k_hit_coverage(const u32* hit_read, const u32* hit_off, u64 n_hits,
+                                                      int k, const int* read_contig,
+                                                      const long long* read_ref_start,
+                                                      const u64* read_cig_off, const u32* cigar, u64* keys) {
+  u64 h = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n_hits) return;
+  const u32 r = hit_read[h];
+  const u32 off = hit_off[h];
+  const u32 prev_end = (h > 0 && hit_read[h - 1] == r) ? hit_off[h - 1] + (u32)k : 0u;
+  u64* out = keys + h * (u64)k;
+  const u64 c0 = read_cig_off[r], c1 = read_cig_off[r + 1];
+  int n = expand_hit(cigar + c0, c1 - c0, read_ref_start[r], off, k, prev_end, (u64)(u32)read_contig[r], out);
+  for (int j = n; j < k; ++j) out[j] = ~0ull;
+}
+
 // ------------------------------------------------ table maintenance -------
 __global__ void k_or_flag(const u64* src, u64* flags, u64 bit) {
   if (*src) atomicOr(flags, bit);
@@ -2396,6 +2415,66 @@ int kdf_reduce_hits(const uint64_t* hit_pos, const uint32_t* hit_slot, uint64_t 
   k_reduce_hits<<<g, 128, 0, st>>>(spos, sslot, n_hits, (const u64*)read_starts, n_reads, (u64*)rec_read,
                                    rec_ndistinct, rec_nhits, (u64*)rec_first, (u64*)n_recs);
   CUDA_TRY(cudaGetLastError());
+  return KDF_OK;
+}
+
+// ---- K7: coverage of the reference by hit k-mers ---------------------------
+size_t kdf_hit_coverage_scratch_bytes(uint64_t n_hits, int k) {
+  uint64_t n = n_hits * (uint64_t)(k > 0 ? k : 0);
+  size_t t1 = 0, t2 = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, t1, (const u64*)nullptr, (u64*)nullptr, (int)n);
+  cub::DeviceRunLengthEncode::Encode(nullptr, t2, (const u64*)nullptr, (u64*)nullptr, (u32*)nullptr,
+                                     (u64*)nullptr, (int)n);
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  return 2 * al(n * 8) + al(t1 > t2 ? t1 : t2) + 256;
+}
+
+int kdf_hit_coverage(const uint32_t* hit_read, const uint32_t* hit_off, uint64_t n_hits, int k,
+                     const int32_t* read_contig, const int64_t* read_ref_start,
+                     const uint64_t* read_cig_off, const uint32_t* cigar, void* scratch,
+                     size_t scratch_bytes, uint64_t* out_keys, uint32_t* out_counts, uint64_t* n_out,
+                     void* stream) {
+  if (n_hits == 0) return KDF_OK;
+  if (!hit_read || !hit_off || !read_contig || !read_ref_start || !read_cig_off || !cigar || !scratch ||
+      !out_keys || !out_counts || !n_out)
+    return fail(KDF_ERR_ARG, "kdf_hit_coverage: NULL argument");
+  if (k < 1 || k > 64) return fail(KDF_ERR_ARG, "kdf_hit_coverage: k must be in 1..64");
+  const u64 n = n_hits * (u64)k;
+  if (n > 0x7fffffffull) return fail(KDF_ERR_ARG, "kdf_hit_coverage: too many hits for one call");
+  if (scratch_bytes < kdf_hit_coverage_scratch_bytes(n_hits, k))
+    return fail(KDF_ERR_CAPACITY, "kdf_hit_coverage: scratch too small");
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  char* p = (char*)(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+  u64* keys = (u64*)p;
+  p += al(n * 8);
+  u64* sorted = (u64*)p;
+  p += al(n * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  int g = (int)((n_hits + 127) / 128);
+  k_hit_coverage<<<g, 128, 0, st>>>(hit_read, hit_off, n_hits, k, (const int*)read_contig,
+                                    (const long long*)read_ref_start, (const u64*)read_cig_off, cigar, keys);
+  CUDA_TRY(cudaGetLastError());
+  size_t t1 = 0, t2 = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, t1, (const u64*)keys, sorted, (int)n);
+  CUDA_TRY(cub::DeviceRadixSort::SortKeys(p, t1, (const u64*)keys, sorted, (int)n, 0, 64, st));
+  cub::DeviceRunLengthEncode::Encode(nullptr, t2, (const u64*)sorted, (u64*)out_keys, out_counts, (u64*)n_out, (int)n);
+  CUDA_TRY(cub::DeviceRunLengthEncode::Encode(p, t2, (const u64*)sorted, (u64*)out_keys, out_counts,
+                                              (u64*)n_out, (int)n, st));
+  return KDF_OK;
+}
+
+int kdf_debug_hit_coverage_host(const uint32_t* hit_read, const uint32_t* hit_off, uint64_t n_hits, int k,
+                                const int32_t* read_contig, const int64_t* read_ref_start,
+                                const uint64_t* read_cig_off, const uint32_t* cigar, uint64_t* keys) {
+  if (k < 1 || k > 64) return fail(KDF_ERR_ARG, "kdf_debug_hit_coverage_host: k must be in 1..64");
+  for (uint64_t h = 0; h < n_hits; ++h) {
+    const uint32_t r = hit_read[h];
+    const uint32_t prev_end = (h > 0 && hit_read[h - 1] == r) ? hit_off[h - 1] + (uint32_t)k : 0u;
+    u64* out = (u64*)keys + h * (u64)k;
+    int n = expand_hit(cigar + read_cig_off[r], read_cig_off[r + 1] - read_cig_off[r],
+                       (long long)read_ref_start[r], hit_off[h], k, prev_end, (u64)(uint32_t)read_contig[r], out);
+    for (int j = n; j < k; ++j) out[j] = ~0ull;
+  }
   return KDF_OK;
 }
 

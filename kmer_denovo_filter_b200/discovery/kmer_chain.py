@@ -21,7 +21,7 @@ from .. import engine as _engine
 from ..kmer_utils import KmerSet
 
 REF_PLANE = 1
-L2_TABLE_BYTES = 100 << 20      # keys of a read-only table that can stay L2-resident next to the stream
+L2_TABLE_BYTES = int(os.environ.get("KDF_L2_TABLE_MB", "100")) << 20   # keys of a read-only table that can stay L2-resident next to the stream
 SMEM_TABLE_BYTES = 160 * 1024   # keys of a read-only table that the stream kernels copy to shared memory
 
 

@@ -247,6 +247,39 @@ def _collect_kmer_ref_positions(read, kmer_hit_indices, kmer_size):
     return cov
 
 
+def _accumulate_coverage(eng, batch, reads, hit_slices, off, kmer_size, kmer_coverage, read_coverage):
+    """Per-position k-mer and read coverage of the kept reads of one batch, on the
+    device (``kdf_hit_coverage``, K7): what the reference computes read by read with
+    ``_collect_kmer_ref_positions`` and merges with ``Counter.update``
+    (``core/bam_scanner.py:97-117``, ``discovery/pipeline.py:851-855``)."""
+    if not reads:
+        return
+    rr = np.asarray(reads, dtype=np.int64)
+    c0 = batch.cigar_off[rr].astype(np.int64)
+    c1 = batch.cigar_off[rr + 1].astype(np.int64)
+    n_ops = c1 - c0
+    cig_off = np.zeros(rr.shape[0] + 1, dtype=np.uint64)
+    cig_off[1:] = np.cumsum(n_ops)
+    if int(cig_off[-1]):
+        idx = np.repeat(c0 - cig_off[:-1].astype(np.int64), n_ops) + np.arange(int(cig_off[-1]))
+        cigar = batch.cigar_blob[idx]
+    else:
+        cigar = np.zeros(0, dtype=np.uint32)
+    n_hits = np.asarray([b - a for a, b in hit_slices], dtype=np.int64)
+    hit_read = np.repeat(np.arange(rr.shape[0], dtype=np.uint32), n_hits)
+    hit_off = np.concatenate([off[a:b] for a, b in hit_slices]).astype(np.uint32) if n_hits.sum() else \
+        np.zeros(0, dtype=np.uint32)
+    contig, pos, kc, rc = eng.hit_coverage(hit_read, hit_off, kmer_size, batch.ref_id[rr],
+                                           batch.pos[rr].astype(np.int64), cig_off, cigar)
+    for c in np.unique(contig).tolist():
+        sel = contig == c
+        name = batch.ref_names[c]
+        kcov, rcov = kmer_coverage[name], read_coverage[name]
+        for p, a, b in zip(pos[sel].tolist(), kc[sel].tolist(), rc[sel].tolist()):
+            kcov[p] += a
+            rcov[p] += b
+
+
 def scan_child_reads(eng, child_bam, table, kmer_size, min_distinct_kmers_per_read, threads,
                      batch_bases=kw.BATCH_BASES):
     """GPU part of Module 3: per-read distinct / hit counts for every scanned
@@ -348,6 +381,7 @@ def _anchor_and_cluster(child_bam, ref_fasta, proband_unique_kmers, kmer_size,
         informative = np.flatnonzero(nd >= max(1, min_distinct_kmers_per_read))
         lo_i = np.searchsorted(ridx, informative, side="left")
         hi_i = np.searchsorted(ridx, informative, side="right")
+        cov_reads, cov_hits = [], []   # kept reads of this batch and their hit slices (K7 input)
         for r, a, b in zip(informative.tolist(), lo_i.tolist(), hi_i.tolist()):
             read = batch.record(r)
             dedup_key = (read.query_name, read.is_supplementary)
@@ -363,11 +397,8 @@ def _anchor_and_cluster(child_bam, ref_fasta, proband_unique_kmers, kmer_size,
             chrom = read.reference_name
             read_hits.append((chrom, read.reference_start, read.reference_end,
                               dedup_key[0], unique_in_read, dedup_key[1]))
-            cov = _collect_kmer_ref_positions(read, hit_idx, kmer_size)
-            kmer_coverage[chrom] += cov
-            rc = read_coverage[chrom]
-            for pos in cov:
-                rc[pos] += 1
+            cov_reads.append(r)
+            cov_hits.append((a, b))
             max_clip = 0
             for op, ln in read.cigartuples or ():
                 if op == 4 and ln > max_clip:
@@ -381,6 +412,8 @@ def _anchor_and_cluster(child_bam, ref_fasta, proband_unique_kmers, kmer_size,
                 "mate_is_unmapped": read.mate_is_unmapped if read.is_paired else False,
                 "max_clip": max_clip,
             }
+        _accumulate_coverage(eng, batch, cov_reads, cov_hits, off, kmer_size, kmer_coverage,
+                             read_coverage)
         batch.close()
     if owns:
         table.close()

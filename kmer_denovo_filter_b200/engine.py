@@ -78,6 +78,9 @@ _SIGNATURES = {
                                      _vp, _vp, _vp]),
     "kdf_bin_stream_to": (_i, [ctypes.POINTER(_Stream), _i, _i, _i, _vp, _u64, _vp, _vp, _vp, _vp]),
     "kdf_bin_keys": (_i, [_vp, _vp, _u64, _i, _i, _i, _vp, _u64, _vp, _vp, _vp]),
+    "kdf_hit_coverage_scratch_bytes": (ctypes.c_size_t, [_u64, _i]),
+    "kdf_hit_coverage": (_i, [_vp, _vp, _u64, _i, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp]),
+    "kdf_debug_hit_coverage_host": (_i, [_vp, _vp, _u64, _i, _vp, _vp, _vp, _vp, _vp]),
     "kdf_update_bins": (_i, [_vp, _i, _vp, _u64, _vp, _i, _i, _u32, _vp, _vp]),
     "kdf_count_bins_smem_scratch": (ctypes.c_size_t, [_i, _i, _i, _u64, _u64]),
     "kdf_count_bins_smem": (_i, [_i, _i, _i, _vp, _u64, _vp, _vp, _u64, _vp, _vp, ctypes.c_size_t, _i, _i,
@@ -306,6 +309,46 @@ class KeyBins:
             return seg, None
         pair = seg.view(-1, 2)
         return pair[:, 0].contiguous(), pair[:, 1].contiguous()
+
+
+def _fold_coverage(keys, counts):
+    """Runs of ``kdf_hit_coverage`` (key = contig << 40 | pos << 1 | first) →
+    (contig, pos, k-mer count, read count) per position."""
+    keep = keys != np.uint64(0xFFFFFFFFFFFFFFFF)
+    keys, counts = keys[keep], counts[keep].astype(np.int64)
+    pos_key = keys >> np.uint64(1)
+    first = (keys & np.uint64(1)).astype(bool)
+    u, inv = np.unique(pos_key, return_inverse=True)
+    kc = np.zeros(u.shape[0], dtype=np.int64)
+    rc = np.zeros(u.shape[0], dtype=np.int64)
+    np.add.at(kc, inv, counts)
+    np.add.at(rc, inv[first], counts[first])
+    return ((u >> np.uint64(39)).astype(np.int64), (u & np.uint64((1 << 39) - 1)).astype(np.int64),
+            kc, rc)
+
+
+def debug_hit_coverage_host(hit_read, hit_off, k, read_contig, read_ref_start, read_cig_off, cigar):
+    """The K7 expansion run on the host by the same code the kernel uses (test hook);
+    same return value as :meth:`CudaEngine.hit_coverage`."""
+    lib = load_library()
+    hr = np.ascontiguousarray(hit_read, dtype=np.uint32)
+    ho = np.ascontiguousarray(hit_off, dtype=np.uint32)
+    rc = np.ascontiguousarray(read_contig, dtype=np.int32)
+    rs = np.ascontiguousarray(read_ref_start, dtype=np.int64)
+    co = np.ascontiguousarray(read_cig_off, dtype=np.uint64)
+    cg = np.ascontiguousarray(cigar, dtype=np.uint32)
+    if cg.shape[0] == 0:
+        cg = np.zeros(1, np.uint32)
+    n = hr.shape[0]
+    keys = np.zeros(max(n * k, 1), np.uint64)
+    if n:
+        r = lib.kdf_debug_hit_coverage_host(_np_ptr(hr), _np_ptr(ho), n, int(k), _np_ptr(rc), _np_ptr(rs),
+                                            _np_ptr(co), _np_ptr(cg), _np_ptr(keys))
+        if r != KDF_OK:
+            raise KdfError(lib.kdf_last_error().decode())
+    keys = np.sort(keys[:n * k])
+    u, c = np.unique(keys, return_counts=True)
+    return _fold_coverage(u, c.astype(np.uint32))
 
 
 def debug_hash_host(lo, hi, key_words, log2_parts, n_buckets, n_ranks):
@@ -749,6 +792,43 @@ class CudaEngine:
             bins.cursors.data_ptr(), bins.overflow.data_ptr(), self.stream_ptr()))
         self._t1("bin_keys/kw%d" % bins.key_words, ev)
         self.launches += 1
+
+    def hit_coverage(self, hit_read, hit_off, k, read_contig, read_ref_start, read_cig_off, cigar):
+        """K7 (``kdf_hit_coverage``): reference positions covered by hit k-mers.
+        Inputs are numpy arrays (hits sorted by (read, offset); per-read contig id,
+        reference start, CIGAR offsets; BAM CIGAR words).  Returns numpy
+        ``(contig i64[], pos i64[], kmer_count i64[], read_count i64[])``, one entry
+        per covered position, sorted by (contig, pos)."""
+        torch = self.torch
+        n_hits = int(len(hit_read))
+        if n_hits == 0:
+            z = np.zeros(0, dtype=np.int64)
+            return z, z, z, z
+
+        def dev(a, dt):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(self.device)
+        d_hr, d_ho = dev(hit_read, np.uint32).view(torch.int32), dev(hit_off, np.uint32).view(torch.int32)
+        d_rc, d_rs = dev(read_contig, np.int32), dev(read_ref_start, np.int64)
+        d_co = dev(np.asarray(read_cig_off, dtype=np.uint64).view(np.int64), np.int64)
+        d_cg = dev(np.asarray(cigar, dtype=np.uint32).view(np.int32), np.int32)
+        if d_cg.numel() == 0:
+            d_cg = self.zeros(1, torch.int32)
+        n = n_hits * int(k)
+        nbytes = self.lib.kdf_hit_coverage_scratch_bytes(n_hits, int(k))
+        scratch = self.empty((nbytes + 7) // 8, torch.int64)
+        keys = self.empty(n, torch.int64)
+        counts = self.empty(n, torch.int32)
+        n_out = self.zeros(1, torch.int64)
+        ev = self._t0()
+        self._check(self.lib.kdf_hit_coverage(
+            d_hr.data_ptr(), d_ho.data_ptr(), n_hits, int(k), d_rc.data_ptr(), d_rs.data_ptr(),
+            d_co.data_ptr(), d_cg.data_ptr(), scratch.data_ptr(), nbytes, keys.data_ptr(),
+            counts.data_ptr(), n_out.data_ptr(), self.stream_ptr()))
+        self._t1("hit_coverage", ev)
+        self.launches += 3
+        m = int(n_out.item())
+        return _fold_coverage(keys[:m].cpu().numpy().view(np.uint64),
+                              counts[:m].cpu().numpy().view(np.uint32))
 
     def update_bins(self, table, bins, mode=MODE_COUNT_IF_PRESENT, plane=0, arg=1, stats=None):
         """K2 over hash-range bins, bin after bin (``kdf_update_bins``): each bin only

@@ -523,6 +523,25 @@ def test_count_bins_smem_form(eng, k, n_parts, monkeypatch):
     assert res["fallback"] == (len(want) // n_parts > 200)
 
 
+def test_hit_coverage_device_equals_host(eng):
+    """K7 on the device (expand + radix sort + run-length encode) == the same expansion
+    on the host, which the CPU suite pins against the reference-named helper."""
+    from kmer_denovo_filter_b200 import engine
+    from test_postprocess_cpu import _random_alignments
+    for seed, k in ((11, 9), (12, 31), (13, 63)):
+        contig, start, cig_off, cigar, hr, ho, _recs = _random_alignments(seed, n_reads=400, k=k)
+        want = engine.debug_hit_coverage_host(hr, ho, k, contig, start, cig_off, cigar)
+        got = eng.hit_coverage(np.asarray(hr, np.uint32), np.asarray(ho, np.uint32), k,
+                               np.asarray(contig, np.int32), np.asarray(start, np.int64),
+                               np.asarray(cig_off, np.uint64), np.asarray(cigar, np.uint32))
+        assert len(want[0]) > 100
+        for a, b in zip(want, got):
+            assert np.array_equal(a, b)
+    empty = eng.hit_coverage(np.zeros(0, np.uint32), np.zeros(0, np.uint32), 31, np.zeros(1, np.int32),
+                             np.zeros(1, np.int64), np.zeros(2, np.uint64), np.zeros(0, np.uint32))
+    assert all(a.shape[0] == 0 for a in empty)
+
+
 def test_count_bins_packed_heavy_duplicates(eng):
     """Many concurrent copies of few keys (the saturating CAS under contention) and
     keys whose top bases are all T (state bits next to an all-ones key prefix)."""

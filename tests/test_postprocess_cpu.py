@@ -54,6 +54,68 @@ def test_kmer_ref_positions_with_insertion():
     assert dict(P._collect_kmer_ref_positions(R, [], 5)) == {}
 
 
+def _random_alignments(seed, n_reads=60, k=7):
+    """Reads with random CIGARs (all op kinds) and sorted random hit offsets."""
+    import random
+    rng = random.Random(seed)
+    contig, start, cig_off, cigar, hr, ho, recs = [], [], [0], [], [], [], []
+    for r in range(n_reads):
+        ops = []
+        if rng.random() < 0.3:
+            ops.append((5, rng.randint(1, 9)))
+        if rng.random() < 0.5:
+            ops.append((4, rng.randint(1, 12)))
+        for _ in range(rng.randint(1, 6)):
+            ops.append((rng.choice([0, 0, 0, 7, 8]), rng.randint(1, 30)))
+            if rng.random() < 0.6:
+                ops.append((rng.choice([1, 2, 3, 6]), rng.randint(1, 8)))
+        if rng.random() < 0.4:
+            ops.append((4, rng.randint(1, 12)))
+        qlen = sum(ln for op, ln in ops if op in (0, 1, 4, 7, 8))
+        c = rng.randint(0, 3)
+        st = rng.randint(0, 5000)
+        offs = sorted(rng.sample(range(0, max(qlen - k + 1, 1)), min(rng.randint(0, 6), max(qlen - k + 1, 1))))
+        contig.append(c)
+        start.append(st)
+        cigar += [(ln << 4) | op for op, ln in ops]
+        cig_off.append(len(cigar))
+        hr += [r] * len(offs)
+        ho += offs
+        recs.append((c, st, ops, offs))
+    return contig, start, cig_off, cigar, hr, ho, recs
+
+
+def test_hit_coverage_host_matches_reference_helper():
+    """K7 (kdf_hit_coverage): the device function, instantiated on the host, against the
+    reference-named per-read helper and its Counter merges (core/bam_scanner.py:97-117,
+    discovery/pipeline.py:851-855), on random CIGARs with clips, insertions, deletions,
+    skips and padding."""
+    import collections
+    from kmer_denovo_filter_b200 import engine
+    for seed, k in ((1, 7), (2, 31), (3, 1)):
+        contig, start, cig_off, cigar, hr, ho, recs = _random_alignments(seed, k=k)
+        kc = collections.defaultdict(collections.Counter)
+        rc = collections.defaultdict(collections.Counter)
+        for c, st, ops, offs in recs:
+            class R:
+                reference_start = st
+                cigartuples = ops
+            cov = P._collect_kmer_ref_positions(R, offs, k)
+            kc[c] += cov
+            for p in cov:
+                rc[c][p] += 1
+        gc, gp, gk, gr = engine.debug_hit_coverage_host(hr, ho, k, contig, start, cig_off, cigar)
+        got_k = collections.defaultdict(dict)
+        got_r = collections.defaultdict(dict)
+        for c, p, a, b in zip(gc.tolist(), gp.tolist(), gk.tolist(), gr.tolist()):
+            got_k[c][p] = a
+            got_r[c][p] = b
+        assert {c: dict(v) for c, v in kc.items() if v} == dict(got_k)
+        assert {c: dict(v) for c, v in rc.items() if v} == dict(got_r)
+    z = engine.debug_hit_coverage_host([], [], 31, [0], [0], [0, 0], [])
+    assert all(a.shape[0] == 0 for a in z)
+
+
 def test_sv_linking_and_classes():
     regions = [("chr1", 100, 300), ("chr1", 5000, 5200), ("chr2", 10, 90)]
     rreads = {regions[0]: {"a", "b"}, regions[1]: {"a"}, regions[2]: {"c"}}
