@@ -50,6 +50,8 @@ def kernel_class(name):
         return "count", False
     if name.startswith("bin_stream"):
         return "bin", True
+    if name.startswith("update_bins"):
+        return "probe", False
     return "probe", True
 
 
@@ -364,10 +366,17 @@ def main():
     def kmers_per_launch(name):
         """valid k-mer instances one launch of this (timed) call processes, averaged
         over its launches in the step"""
-        if name.startswith("count_stream/mode2"):
-            return (windows["mother"] + windows["father"]) / 2.0
+        if name.startswith(("count_stream/mode2", "update_bins/mode2")):
+            binned = name.startswith("update_bins")
+            sel = [w for w, b in zip(("mother", "father"), res.get("parents_binned", [False, False]))
+                   if bool(b) == binned] or ["mother", "father"]
+            return sum(windows[w] for w in sel) / max(per_kernel[name]["launches"] / float(args.steps), 1.0)
         if name.startswith("bin_stream"):
-            return (windows["child"] + windows["ref"]) / 2.0
+            # child + reference, and the parents that took the binned route (filter table > L2)
+            tot = windows["child"] + windows["ref"]
+            for who, b in zip(("mother", "father"), res.get("parents_binned", [])):
+                tot += windows[who] if b else 0
+            return tot / max(per_kernel[name]["launches"] / float(args.steps), 1.0)
         if name.startswith("count_bins"):
             return float(windows["child"])
         if name.startswith(("scan_stream_hits", "scan_reads", "count_stream/mode0")):

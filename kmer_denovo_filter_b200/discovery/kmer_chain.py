@@ -208,11 +208,12 @@ PROBE_CHUNK_BASES = 1 << 30      # bins of one chunk: <= 8.6 GB (64-bit keys)
 
 
 def count_if_present(eng, table, d_stream, stats, plane=0, arg=1):
-    """``jellyfish count --if`` of one parent stream (discovery/pipeline.py:377-386)."""
+    """``jellyfish count --if`` of one parent stream (discovery/pipeline.py:377-386).
+    → True when the stream was binned first (the large-table route)."""
     key_bytes = table.capacity * 8 * table.key_words
     if key_bytes <= PROBE_DIRECT_BYTES or os.environ.get("KDF_PROBE_DIRECT") == "1":
         eng.count_stream(table, d_stream, _engine.MODE_COUNT_IF_PRESENT, plane, arg, stats)
-        return
+        return False
     # at least 16 bins: with <= 8 the binning kernel takes its owner-routing form
     n_parts = min(MAX_PARTS, max(16, _pow2_at_least((key_bytes + PROBE_SLICE_BYTES - 1) // PROBE_SLICE_BYTES)))
     n_words = (d_stream.n_bases + 31) // 32
@@ -231,6 +232,7 @@ def count_if_present(eng, table, d_stream, stats, plane=0, arg=1):
         eng.update_bins(table, bins, _engine.MODE_COUNT_IF_PRESENT, plane, arg, stats)
         del bins
         first += n
+    return True
 
 
 def _primed_table(eng, k, lo, hi, n):
@@ -319,21 +321,21 @@ def discover_streams(eng, child, mother, father, ref, k, min_child_count=3,
            "child_capacity": child_capacity, "candidates": n_cand,
            "non_ref": n_nonref, "after_mother": 0, "proband_unique": 0,
            "pu": None, "ndistinct": None, "nhits": None, "informative_reads": 0, "hits": None,
-           "reads": None}
+           "reads": None, "parents_binned": []}
 
     # Module 2: count --if against mother, then father
     n_pu = 0
     if n_nonref:
         mt = _primed_table(eng, k, lo, hi, n_nonref)
         up.wait(ev_mother)
-        count_if_present(eng, mt, d_mother, stats)
+        out["parents_binned"].append(count_if_present(eng, mt, d_mother, stats))
         n_am, lo, hi, _a, _b = eng.threshold_compact(mt, max0=parent_max_count)
         mt.close()
         out["after_mother"] = n_am
         if n_am:
             ft = _primed_table(eng, k, lo, hi, n_am)
             up.wait(ev_father)
-            count_if_present(eng, ft, d_father, stats)
+            out["parents_binned"].append(count_if_present(eng, ft, d_father, stats))
             n_pu, lo, hi, _a, _b = eng.threshold_compact(ft, max0=parent_max_count)
             ft.close()
     out["proband_unique"] = n_pu

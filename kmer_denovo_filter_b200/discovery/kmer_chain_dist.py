@@ -284,13 +284,13 @@ def filter_parent_dist(eng, parent_stream, k, lo, hi, parent_max_count, world, s
     identical on every rank."""
     n = int(lo.shape[0])
     table = _kc._primed_table(eng, k, lo, hi, n)
-    _kc.count_if_present(eng, table, parent_stream, stats)
+    binned = _kc.count_if_present(eng, table, parent_stream, stats)
     _found, p0, _p1 = eng.lookup_keys(table, lo, hi)
     table.close()
     total = p0.to(eng.torch.int64)
     allreduce(total, "sum")
     keep = total <= parent_max_count
-    return lo[keep].contiguous(), (hi[keep].contiguous() if hi is not None else None)
+    return lo[keep].contiguous(), (hi[keep].contiguous() if hi is not None else None), binned
 
 
 def discover_streams_dist(eng, child, mother, father, ref, k, min_child_count=3,
@@ -327,17 +327,19 @@ def discover_streams_dist(eng, child, mother, father, ref, k, min_child_count=3,
     out = {"child_windows": c["child_windows"], "child_distinct": int(tot[1].item()),
            "candidates": int(tot[0].item()), "non_ref": int(lo.shape[0]), "after_mother": 0,
            "proband_unique": 0, "pu": None, "ndistinct": None, "nhits": None,
-           "informative_reads": 0, "reads": None, "hits": None}
+           "informative_reads": 0, "reads": None, "hits": None, "parents_binned": []}
     units = c["child_windows"] + c["ref_windows"]
 
     n_pu = 0
     if out["non_ref"]:
         up.wait(ev_mother)
-        lo, hi = filter_parent_dist(eng, d_mother, k, lo, hi, parent_max_count, world, stats)
+        lo, hi, b = filter_parent_dist(eng, d_mother, k, lo, hi, parent_max_count, world, stats)
+        out["parents_binned"].append(b)
         out["after_mother"] = int(lo.shape[0])
         if out["after_mother"]:
             up.wait(ev_father)
-            lo, hi = filter_parent_dist(eng, d_father, k, lo, hi, parent_max_count, world, stats)
+            lo, hi, b = filter_parent_dist(eng, d_father, k, lo, hi, parent_max_count, world, stats)
+            out["parents_binned"].append(b)
             n_pu = int(lo.shape[0])
     out["proband_unique"] = n_pu
 
