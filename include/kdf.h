@@ -110,6 +110,16 @@ uint64_t kdf_table_capacity_for(uint64_t n_keys);
 int kdf_table_create(kdf_table** out, int k, uint64_t capacity,
                      void* slots /*DEV*/, void* stream);
 int kdf_table_destroy(kdf_table* t);
+/* Attach a two-bit membership filter to a table whose keys are final (the primed
+ * filter set of `count --if`, the proband-unique set): `words` is DEV memory of
+ * n_words (a power of two) u32 owned by the caller and must outlive the table's use.
+ * The probing stream ops (COUNT_IF_PRESENT, MARK_IF_PRESENT, the hit scan) then read
+ * ONE 32-bit word per window — a filter of 4 bytes per key stays L2-resident where the
+ * table does not — and only the windows it cannot rule out (the hits plus < 1 % false
+ * positives) probe the table, in the queue drain with every lane busy.  Exact: a filter
+ * has no false negatives.  Any inserting call or kdf_table_clear detaches it;
+ * words == NULL detaches it explicitly.                                        */
+int kdf_table_build_filter(kdf_table* t, uint32_t* words /*DEV*/, uint64_t n_words, void* stream);
 int kdf_table_clear(kdf_table* t, void* stream);                 /* all slots -> empty */
 int kdf_table_clear_plane(kdf_table* t, int plane, void* stream); /* one value plane -> 0 */
 int kdf_table_info(const kdf_table* t, int* k, int* key_words, uint64_t* capacity);

@@ -60,6 +60,8 @@ struct kdf_table {
   void* base;
   int sm_count;
   int log2_parts;  // hash bits consumed above the bucket bits (table slices)
+  u32* filter = nullptr;   // optional two-bit membership filter over the keys (kdf_table_build_filter)
+  u32 filter_mask = 0;     // number of 32-bit filter words - 1 (a power of two)
 };
 
 // SoA table: keys[capacity] (KW words each, 32-byte buckets), p0[capacity], p1[capacity]
@@ -70,6 +72,8 @@ template <int KW> struct TableView {
   u32 n_buckets;
   int log2_parts;
   bool fast_empty;  // k % 32 != 0 (see has_empty)
+  const u32* filter;  // two-bit membership filter or NULL
+  u32 filter_mask;
 };
 template <int KW> struct SPB { static constexpr int v = 4; };  // slots per bucket
 
@@ -82,6 +86,8 @@ static TableView<KW> view_of_table(const kdf_table* t) {
   v.n_buckets = (u32)(t->capacity / SPB<KW>::v);
   v.log2_parts = t->log2_parts;
   v.fast_empty = (t->k % 32) != 0;
+  v.filter = t->filter;
+  v.filter_mask = t->filter_mask;
   return v;
 }
 
@@ -427,18 +433,44 @@ __device__ __forceinline__ void pf_bits(u64 h, u32& word, u32& bits) {
   bits = (1u << (l >> 27)) | (1u << ((l >> 22) & 31u));
 }
 
+// the same for a filter in global memory (kdf_table_build_filter): any power-of-two
+// number of words
+__device__ __forceinline__ void gf_bits(u64 h, u32 mask, u32& word, u32& bits) {
+  u32 l = (u32)h;
+  l ^= l >> 15;
+  l *= 0x2C1B3C6Du;
+  word = (l ^ (u32)(h >> 32)) & mask;
+  bits = (1u << (l >> 27)) | (1u << ((l >> 22) & 31u));
+}
+
+template <int KW>
+__global__ void __launch_bounds__(256) k_build_filter(TableView<KW> t, u64 capacity, u32* words, u32 mask) {
+  u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < capacity; i += stride) {
+    Key<KW> key;
+    key.lo = __ldcg(t.keys + i * KW);
+    if (KW == 2) ((u64*)&key)[KW - 1] = __ldcg(t.keys + i * KW + (KW - 1));
+    if (!is_empty_key(key)) {
+      u32 word, bits;
+      gf_bits(hash_key(key), mask, word, bits);
+      atomicOr(words + word, bits);
+    }
+  }
+}
+
 // ------------------------------------------------------------- K2 ---------
 // One fast-path decision per probe: for probing ops "bucket has an empty slot
 // and no match" (a miss, the common case against a filter set), for inserting
 // ops "bucket holds the key" (the common case at sequencing depth).  Anything
 // else is queued per warp and resolved 32 items at a time.
-template <int KW, int OP, bool SMEM, int CHUNK>
+template <int KW, int OP, bool SMEM, int CHUNK, bool FILT = false>
 __global__ void __launch_bounds__(SMEM ? 512 : 256, SMEM ? KDF_SMEM_BLOCKS : (KW == 2 ? 2 : KDF_STREAM_BLOCKS))
     k_stream(TableView<KW> t, StreamView s, int k, int plane, u32 arg, u64* stats, HitSink sink) {
   extern __shared__ __align__(32) u64 sm_keys[];
   constexpr bool kInsert = (OP == OP_INSERT_COUNT || OP == OP_INSERT_ONLY);
   constexpr int S = SPB<KW>::v;
   static_assert(!(SMEM && kInsert), "shared-memory tables are read-only");
+  static_assert(!(FILT && (SMEM || kInsert)), "a filter fronts read-only tables in global memory");
   // Shared-memory tables are small read-only sets (the proband-unique k-mers, VCF-mode
   // filter sets) that almost no window hits, and a bucket probe from shared memory costs
   // two 128-bit loads with bank conflicts plus the compares: the ncu profile of the scan
@@ -482,7 +514,7 @@ __global__ void __launch_bounds__(SMEM ? 512 : 256, SMEM ? KDF_SMEM_BLOCKS : (KW
       Key<KW> keys[CHUNK];
       Bucket<KW> bk[CHUNK];
       u32 bidx[CHUNK];
-      u32 okm = 0, probe = 0;
+      u32 okm = 0, probe = 0, cand = 0;
 #pragma unroll
       for (int u = 0; u < CHUNK; ++u) {
         bool ok = it.ok();
@@ -492,7 +524,13 @@ __global__ void __launch_bounds__(SMEM ? 512 : 256, SMEM ? KDF_SMEM_BLOCKS : (KW
         bidx[u] = bucket_of(h, t.log2_parts, t.n_buckets);
         if (ok) {
           okm |= 1u << u;
-          if (SMEM) {
+          if (FILT) {
+            // filtered table: one 32-bit load says "certainly absent" for almost every
+            // window; the few candidates are probed by the queue drain, all lanes busy
+            u32 word, bits;
+            gf_bits(h, t.filter_mask, word, bits);
+            if ((__ldg(t.filter + word) & bits) == bits) cand |= 1u << u;
+          } else if (SMEM) {
             u32 word, bits;
             pf_bits(h, word, bits);
             if ((pf[word] & bits) == bits) {
@@ -507,6 +545,12 @@ __global__ void __launch_bounds__(SMEM ? 512 : 256, SMEM ? KDF_SMEM_BLOCKS : (KW
       }
       st.windows += __popc(okm);
       u64 pos0 = (w << 5) + c * CHUNK;
+      if (FILT) {
+#pragma unroll
+        for (int u = 0; u < CHUNK; ++u)
+          if (cand & (1u << u))
+            tally(st, sq_push_or_resolve<KW, OP>(q, t, bidx[u], keys[u], plane, arg, pos0 + u, sink));
+      }
 #pragma unroll
       for (int u = 0; u < CHUNK; ++u) {
         if (probe & (1u << u)) {
@@ -1961,16 +2005,16 @@ static StreamView view_of(const kdf_stream* s) {
 // shared-memory budget for a read-only table copy (keys only)
 static const size_t SMEM_TABLE_MAX = 160 * 1024;
 
-template <int KW, int OP, bool SMEM, int CHUNK>
+template <int KW, int OP, bool SMEM, int CHUNK, bool FILT = false>
 static int launch_stream(const kdf_table* t, const StreamView& v, int plane, u32 arg, u64* stats,
                          const HitSink& sink, cudaStream_t st) {
   TableView<KW> tv = view_of_table<KW>(t);
-  const void* fn = (const void*)k_stream<KW, OP, SMEM, CHUNK>;
+  const void* fn = (const void*)k_stream<KW, OP, SMEM, CHUNK, FILT>;
   size_t smem = SMEM ? (size_t)tv.n_buckets * 32 * KW + (size_t)PF_WORDS * 4 : 0;
   int block = SMEM ? 512 : 256;
   if (SMEM) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int g = grid_for(fn, block, smem, v.n_words, t->sm_count);
-  k_stream<KW, OP, SMEM, CHUNK><<<g, block, smem, st>>>(tv, v, t->k, plane, arg, stats, sink);
+  k_stream<KW, OP, SMEM, CHUNK, FILT><<<g, block, smem, st>>>(tv, v, t->k, plane, arg, stats, sink);
   CUDA_TRY(cudaGetLastError());
   return KDF_OK;
 }
@@ -1979,20 +2023,24 @@ template <int KW>
 static int dispatch_stream(const kdf_table* t, const StreamView& v, int op, int plane, u32 arg,
                            u64* stats, const HitSink& sink, cudaStream_t st) {
   bool small = (size_t)(t->capacity / SPB<KW>::v) * 32 * KW <= SMEM_TABLE_MAX && t->log2_parts == 0;
+  bool filt = t->filter != nullptr;
   switch (op) {
     case OP_INSERT_COUNT:
       return launch_stream<KW, OP_INSERT_COUNT, false, KDF_STREAM_CHUNK>(t, v, plane, arg, stats, sink, st);
     case OP_INSERT_ONLY:
       return launch_stream<KW, OP_INSERT_ONLY, false, KDF_STREAM_CHUNK>(t, v, plane, arg, stats, sink, st);
     case OP_COUNT_IF_PRESENT:
-      return small ? launch_stream<KW, OP_COUNT_IF_PRESENT, true, KDF_SMEM_CHUNK>(t, v, plane, arg, stats, sink, st)
-                   : launch_stream<KW, OP_COUNT_IF_PRESENT, false, KDF_STREAM_CHUNK>(t, v, plane, arg, stats, sink, st);
+      if (small) return launch_stream<KW, OP_COUNT_IF_PRESENT, true, KDF_SMEM_CHUNK>(t, v, plane, arg, stats, sink, st);
+      if (filt) return launch_stream<KW, OP_COUNT_IF_PRESENT, false, KDF_STREAM_CHUNK, true>(t, v, plane, arg, stats, sink, st);
+      return launch_stream<KW, OP_COUNT_IF_PRESENT, false, KDF_STREAM_CHUNK>(t, v, plane, arg, stats, sink, st);
     case OP_MARK_IF_PRESENT:
-      return small ? launch_stream<KW, OP_MARK_IF_PRESENT, true, KDF_SMEM_CHUNK>(t, v, plane, arg, stats, sink, st)
-                   : launch_stream<KW, OP_MARK_IF_PRESENT, false, KDF_STREAM_CHUNK>(t, v, plane, arg, stats, sink, st);
+      if (small) return launch_stream<KW, OP_MARK_IF_PRESENT, true, KDF_SMEM_CHUNK>(t, v, plane, arg, stats, sink, st);
+      if (filt) return launch_stream<KW, OP_MARK_IF_PRESENT, false, KDF_STREAM_CHUNK, true>(t, v, plane, arg, stats, sink, st);
+      return launch_stream<KW, OP_MARK_IF_PRESENT, false, KDF_STREAM_CHUNK>(t, v, plane, arg, stats, sink, st);
     case OP_EMIT_HITS:
-      return small ? launch_stream<KW, OP_EMIT_HITS, true, KDF_SMEM_CHUNK>(t, v, plane, arg, stats, sink, st)
-                   : launch_stream<KW, OP_EMIT_HITS, false, KDF_STREAM_CHUNK>(t, v, plane, arg, stats, sink, st);
+      if (small) return launch_stream<KW, OP_EMIT_HITS, true, KDF_SMEM_CHUNK>(t, v, plane, arg, stats, sink, st);
+      if (filt) return launch_stream<KW, OP_EMIT_HITS, false, KDF_STREAM_CHUNK, true>(t, v, plane, arg, stats, sink, st);
+      return launch_stream<KW, OP_EMIT_HITS, false, KDF_STREAM_CHUNK>(t, v, plane, arg, stats, sink, st);
     default:
       return fail(KDF_ERR_ARG, "unknown table operation");
   }
@@ -2158,6 +2206,8 @@ uint64_t kdf_table_capacity_for(uint64_t n_keys) {
 
 int kdf_table_clear(kdf_table* t, void* stream) {
   if (!t) return fail(KDF_ERR_ARG, "kdf_table_clear: table is NULL");
+  t->filter = nullptr;   // a filter describes the keys it was built from
+  t->filter_mask = 0;
   return clear_table_async(t, (cudaStream_t)stream);
 }
 
@@ -2181,6 +2231,30 @@ int kdf_table_create(kdf_table** out, int k, uint64_t capacity, void* slots, voi
     return rc;
   }
   *out = t;
+  return KDF_OK;
+}
+
+int kdf_table_build_filter(kdf_table* t, uint32_t* words, uint64_t n_words, void* stream) {
+  if (!t) return fail(KDF_ERR_ARG, "kdf_table_build_filter: table is NULL");
+  if (!words || n_words == 0) {   // detach
+    t->filter = nullptr;
+    t->filter_mask = 0;
+    return KDF_OK;
+  }
+  if ((n_words & (n_words - 1)) || n_words > (1ull << 30))
+    return fail(KDF_ERR_ARG, "kdf_table_build_filter: n_words must be a power of two <= 2^30");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(words, 0, n_words * 4, st));
+  if (t->key_words == 1) {
+    int g = grid_for((const void*)k_build_filter<1>, 256, 0, t->capacity, t->sm_count);
+    k_build_filter<1><<<g, 256, 0, st>>>(view_of_table<1>(t), t->capacity, words, (u32)(n_words - 1));
+  } else {
+    int g = grid_for((const void*)k_build_filter<2>, 256, 0, t->capacity, t->sm_count);
+    k_build_filter<2><<<g, 256, 0, st>>>(view_of_table<2>(t), t->capacity, words, (u32)(n_words - 1));
+  }
+  CUDA_TRY(cudaGetLastError());
+  t->filter = words;
+  t->filter_mask = (u32)(n_words - 1);
   return KDF_OK;
 }
 
@@ -2232,6 +2306,10 @@ int kdf_count_stream(kdf_table* t, const kdf_stream* s, int mode, int plane, uin
   if (mode < 0 || mode > KDF_MODE_MARK_IF_PRESENT) return fail(KDF_ERR_ARG, "kdf_count_stream: unknown mode");
   StreamView v = view_of(s);
   if (v.n_words == 0) return KDF_OK;
+  if (mode == KDF_MODE_INSERT_COUNT || mode == KDF_MODE_INSERT_ONLY) {
+    t->filter = nullptr;   // new keys: a filter built earlier no longer covers the table
+    t->filter_mask = 0;
+  }
   HitSink sink = {nullptr, nullptr, 0, nullptr};
   if (t->key_words == 1)
     return dispatch_stream<1>(t, v, mode, plane, arg, (u64*)stats, sink, (cudaStream_t)stream);
@@ -2260,6 +2338,10 @@ int kdf_update_keys(kdf_table* t, const uint64_t* lo, const uint64_t* hi, uint64
   if (!lo || (t->key_words == 2 && !hi)) return fail(KDF_ERR_ARG, "kdf_update_keys: NULL key array");
   if (plane != 0 && plane != 1) return fail(KDF_ERR_ARG, "kdf_update_keys: plane must be 0 or 1");
   if (mode < 0 || mode > KDF_MODE_MARK_IF_PRESENT) return fail(KDF_ERR_ARG, "kdf_update_keys: unknown mode");
+  if (mode == KDF_MODE_INSERT_COUNT || mode == KDF_MODE_INSERT_ONLY) {
+    t->filter = nullptr;
+    t->filter_mask = 0;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   if (t->key_words == 1)
     return dispatch_update_keys<1>(t, (const u64*)lo, (const u64*)hi, n, nullptr, mode, plane, arg,
@@ -2276,6 +2358,10 @@ int kdf_update_bins(kdf_table* t, int n_parts, const uint64_t* bins, uint64_t bi
   if (plane != 0 && plane != 1) return fail(KDF_ERR_ARG, "kdf_update_bins: plane must be 0 or 1");
   if (mode < 0 || mode > KDF_MODE_MARK_IF_PRESENT) return fail(KDF_ERR_ARG, "kdf_update_bins: unknown mode");
   if (bin_cap == 0) return KDF_OK;
+  if (mode == KDF_MODE_INSERT_COUNT || mode == KDF_MODE_INSERT_ONLY) {
+    t->filter = nullptr;
+    t->filter_mask = 0;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const int kw = t->key_words;
   // one launch per bin, in hash order: the bucket index grows with the hash, so the

@@ -249,6 +249,11 @@ def _primed_table(eng, k, lo, hi, n):
         n_keys = n_keys * 3 // 2     # probed bin by bin (count_if_present): its size is free
     t = eng.new_table(k, n_keys=n_keys)
     eng.update_keys(t, lo, hi, _engine.MODE_INSERT_ONLY, 0, 0)
+    # probed straight from the stream and too large for shared memory: put a two-bit
+    # filter (4 bytes per key, L2-resident) in front of it
+    key_bytes = t.capacity * 8 * t.key_words
+    if SMEM_TABLE_BYTES < key_bytes <= PROBE_DIRECT_BYTES and os.environ.get("KDF_TABLE_FILTER", "1") != "0":
+        eng.build_filter(t, max(n, 1))
     return t
 
 

@@ -58,6 +58,7 @@ _SIGNATURES = {
     "kdf_table_destroy": (_i, [_vp]),
     "kdf_table_clear": (_i, [_vp, _vp]),
     "kdf_table_clear_plane": (_i, [_vp, _i, _vp]),
+    "kdf_table_build_filter": (_i, [_vp, _vp, _u64, _vp]),
     "kdf_table_info": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_u64)]),
     "kdf_extract_canonical": (_i, [ctypes.POINTER(_Stream), _i, _vp, _vp, _vp, _vp]),
     "kdf_count_stream": (_i, [_vp, ctypes.POINTER(_Stream), _i, _i, _u32, _vp, _vp]),
@@ -256,6 +257,7 @@ class KmerTable:
         engine._check(lib.kdf_table_create(ctypes.byref(h), self.k, self.capacity,
                                            self.buf.data_ptr(), engine.stream_ptr()))
         self.handle = h
+        self.filter_buf = None
 
     @property
     def nbytes(self):
@@ -266,6 +268,7 @@ class KmerTable:
             self.engine.lib.kdf_table_destroy(self.handle)
             self.handle = None
             self.buf = None
+            self.filter_buf = None
 
     def __del__(self):
         try:
@@ -549,6 +552,18 @@ class CudaEngine:
         t = KmerTable(self, k, capacity)
         self._t1("table_clear", ev)
         return t
+
+    def build_filter(self, table, n_keys):
+        """Attach a two-bit membership filter (4 bytes per key, ``kdf_table_build_filter``)
+        to a table whose keys are final; the probing stream kernels then read one 32-bit
+        word per window and probe the table only for the few windows it cannot rule out."""
+        n_words = 1024
+        while n_words < n_keys and n_words < (1 << 28):
+            n_words *= 2
+        table.filter_buf = self.zeros(n_words, self.torch.int32)   # kept alive with the table
+        self._check(self.lib.kdf_table_build_filter(table.handle, table.filter_buf.data_ptr(), n_words,
+                                                    self.stream_ptr()))
+        self.launches += 1
 
     def clear_plane(self, table, plane):
         self._check(self.lib.kdf_table_clear_plane(table.handle, plane, self.stream_ptr()))

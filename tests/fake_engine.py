@@ -140,6 +140,9 @@ class FakeEngine:
     def count_bins_packed(self, k, min_child_count):
         return False
 
+    def build_filter(self, table, n_keys):
+        pass
+
     def count_bins_smem_ok(self, k, min_child_count):
         return False
 

@@ -542,6 +542,50 @@ def test_hit_coverage_device_equals_host(eng):
     assert all(a.shape[0] == 0 for a in empty)
 
 
+@pytest.mark.parametrize("k", [31, 47])
+def test_table_filter_keeps_results_exact(eng, k):
+    """A table behind its two-bit filter (kdf_table_build_filter) gives the same counts,
+    marks, hit list and stats as the unfiltered table and the oracle; an insert after
+    the build detaches the filter instead of producing false negatives."""
+    from kmer_denovo_filter_b200 import engine
+    g, parent = _genome_reads(501 + k, glen=9000, n=1500)
+    parent = parent + ["", "ACGTN", g[:k]]
+    filt = sorted(kmers.count_sequences([g[1000:6000]], k))[::2]
+    want = kmers.count_sequences(parent, k)
+    ds = eng.upload(engine.pack_sequences(parent))
+    n_win = sum(want.values())
+    res = []
+    for use_filter in (False, True, "tiny"):
+        t = eng.new_table(k, capacity=1 << 16)       # not shared-memory resident
+        lo, hi = eng.keys_to_device(filt, t.key_words)
+        eng.update_keys(t, lo, hi, engine.MODE_INSERT_ONLY, 0, 0)
+        if use_filter:
+            eng.build_filter(t, 1 if use_filter == "tiny" else len(filt))   # tiny: dense filter, many candidates
+        st = eng.new_stats()
+        eng.count_stream(t, ds, engine.MODE_COUNT_IF_PRESENT, 0, 1, st)
+        eng.count_stream(t, ds, engine.MODE_MARK_IF_PRESENT, 1, 1, st)
+        _f, p0, p1 = eng.lookup_keys(t, lo, hi)
+        sp = eng.scan_reads_sparse(t, ds)
+        res.append((p0.cpu().numpy().view(np.uint32).tolist(), p1.cpu().numpy().view(np.uint32).tolist(),
+                    sp["read"].tolist(), sp["ndistinct"].tolist(), sp["nhits"].tolist(),
+                    eng.read_stats(st)))
+        t.close()
+    assert res[0][0] == [want.get(x, 0) for x in filt]
+    assert res[0][1] == [1 if x in want else 0 for x in filt]
+    assert res[0][5]["windows"] == 2 * n_win and res[0][5]["hits"] == 2 * sum(want.get(x, 0) for x in filt)
+    assert res[1] == res[0] and res[2] == res[0]
+    # inserting after the build: the new key must be found
+    t = eng.new_table(k, capacity=1 << 16)
+    lo, hi = eng.keys_to_device(filt[:10], t.key_words)
+    eng.update_keys(t, lo, hi, engine.MODE_INSERT_ONLY, 0, 0)
+    eng.build_filter(t, 10)
+    lo2, hi2 = eng.keys_to_device(filt[10:], t.key_words)
+    eng.update_keys(t, lo2, hi2, engine.MODE_INSERT_ONLY, 0, 0)
+    eng.count_stream(t, ds, engine.MODE_COUNT_IF_PRESENT, 0, 1, None)
+    lo, hi = eng.keys_to_device(filt, t.key_words)
+    assert eng.lookup_keys(t, lo, hi)[1].cpu().numpy().view(np.uint32).tolist() == res[0][0]
+
+
 def test_count_bins_packed_heavy_duplicates(eng):
     """Many concurrent copies of few keys (the saturating CAS under contention) and
     keys whose top bases are all T (state bits next to an all-ones key prefix)."""
