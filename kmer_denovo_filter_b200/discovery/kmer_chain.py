@@ -211,7 +211,8 @@ def count_if_present(eng, table, d_stream, stats, plane=0, arg=1):
     """``jellyfish count --if`` of one parent stream (discovery/pipeline.py:377-386).
     → True when the stream was binned first (the large-table route)."""
     key_bytes = table.capacity * 8 * table.key_words
-    if key_bytes <= PROBE_DIRECT_BYTES or os.environ.get("KDF_PROBE_DIRECT") == "1":
+    if (key_bytes <= PROBE_DIRECT_BYTES or getattr(table, "filter_buf", None) is not None
+            or os.environ.get("KDF_PROBE_DIRECT") == "1"):
         eng.count_stream(table, d_stream, _engine.MODE_COUNT_IF_PRESENT, plane, arg, stats)
         return False
     # at least 16 bins: with <= 8 the binning kernel takes its owner-routing form
@@ -241,19 +242,21 @@ def _primed_table(eng, k, lo, hi, n):
     # larger read-only sets get load 0.33: a third as many probes meet a full home
     # bucket (4.6 % instead of 14 %), which is worth more than the extra L2 footprint
     n_keys = max(n, 1)
-    if n_keys * 4 * 8 * eng.lib.kdf_key_words(k) <= SMEM_TABLE_BYTES:
+    kw = eng.lib.kdf_key_words(k)
+    # a two-bit filter of 4 bytes per key (rounded up to a power of two) in front of the
+    # table keeps the stream probe L2-resident whatever the table's size — as long as the
+    # FILTER fits the ~64 MB of L2 that data shared by both dies can use
+    filtered = eng.filter_applies(k, n_keys)
+    if n_keys * 4 * 8 * kw <= SMEM_TABLE_BYTES:
         n_keys *= 2
-    elif n_keys * 3 * 8 * eng.lib.kdf_key_words(k) <= L2_TABLE_BYTES:
+    elif n_keys * 3 * 8 * kw <= L2_TABLE_BYTES:
         n_keys = n_keys * 3 // 2     # still L2-resident at load 0.33
-    elif n_keys * 2 * 8 * eng.lib.kdf_key_words(k) > PROBE_DIRECT_BYTES:
+    elif not filtered and n_keys * 2 * 8 * kw > PROBE_DIRECT_BYTES:
         n_keys = n_keys * 3 // 2     # probed bin by bin (count_if_present): its size is free
     t = eng.new_table(k, n_keys=n_keys)
     eng.update_keys(t, lo, hi, _engine.MODE_INSERT_ONLY, 0, 0)
-    # probed straight from the stream and too large for shared memory: put a two-bit
-    # filter (4 bytes per key, L2-resident) in front of it
-    key_bytes = t.capacity * 8 * t.key_words
-    if SMEM_TABLE_BYTES < key_bytes <= PROBE_DIRECT_BYTES and os.environ.get("KDF_TABLE_FILTER", "1") != "0":
-        eng.build_filter(t, max(n, 1))
+    if filtered:
+        eng.build_filter(t, max(n, 1), eng.FILTER_MAX_BYTES)
     return t
 
 

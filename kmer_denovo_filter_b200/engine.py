@@ -553,13 +553,36 @@ class CudaEngine:
         self._t1("table_clear", ev)
         return t
 
-    def build_filter(self, table, n_keys):
+    @staticmethod
+    def filter_words(n_keys, max_bytes):
+        """32-bit words of the filter for ``n_keys`` keys within ``max_bytes``: 32 bits per
+        key (false positives ~0.4 %) when that fits, else 16 (~1.5 %), else 0 (no filter)."""
+        for per_word in (1, 2):
+            n_words = 1024
+            while n_words * per_word < n_keys:
+                n_words *= 2
+            if n_words * 4 <= max_bytes:
+                return n_words
+        return 0
+
+    FILTER_MAX_BYTES = int(os.environ.get("KDF_FILTER_MAX_MB", "32")) << 20
+    SMEM_TABLE_BYTES = 160 * 1024
+
+    def filter_applies(self, k, n_keys):
+        """A table of ``n_keys`` final keys gets a filter: too large for the stream
+        kernels' shared-memory copy, and its filter fits the L2 budget."""
+        kw = self.lib.kdf_key_words(k)
+        return (max(n_keys, 1) * 4 * 8 * kw > self.SMEM_TABLE_BYTES
+                and self.filter_words(max(n_keys, 1), self.FILTER_MAX_BYTES) > 0
+                and os.environ.get("KDF_TABLE_FILTER", "1") != "0")
+
+    def build_filter(self, table, n_keys, max_bytes=1 << 30):
         """Attach a two-bit membership filter (4 bytes per key, ``kdf_table_build_filter``)
         to a table whose keys are final; the probing stream kernels then read one 32-bit
         word per window and probe the table only for the few windows it cannot rule out."""
-        n_words = 1024
-        while n_words < n_keys and n_words < (1 << 28):
-            n_words *= 2
+        n_words = self.filter_words(n_keys, max_bytes)
+        if not n_words:
+            raise KdfError("build_filter: %d keys do not fit a filter of %d bytes" % (n_keys, max_bytes))
         table.filter_buf = self.zeros(n_words, self.torch.int32)   # kept alive with the table
         self._check(self.lib.kdf_table_build_filter(table.handle, table.filter_buf.data_ptr(), n_words,
                                                     self.stream_ptr()))

@@ -201,6 +201,8 @@ class KmerSet:
         eng = self.engine
         t = eng.new_table(self.k, n_keys=max(len(self), n_min, 1))
         eng.update_keys(t, self.lo, self.hi, _engine.MODE_INSERT_ONLY, 0, 0)
+        if eng.filter_applies(self.k, len(self)):   # final keys: front the table with a filter
+            eng.build_filter(t, max(len(self), 1), eng.FILTER_MAX_BYTES)
         return t
 
 

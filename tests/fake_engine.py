@@ -140,7 +140,12 @@ class FakeEngine:
     def count_bins_packed(self, k, min_child_count):
         return False
 
-    def build_filter(self, table, n_keys):
+    FILTER_MAX_BYTES = 32 << 20
+
+    def filter_applies(self, k, n_keys):
+        return False
+
+    def build_filter(self, table, n_keys, max_bytes=1 << 30):
         pass
 
     def count_bins_smem_ok(self, k, min_child_count):
