@@ -157,8 +157,24 @@ def stream_to_host(torch, s, pin):
     hs = engine.HostStream(keep[0].numpy().view(np.uint64), keep[1].numpy().view(np.uint32),
                            s["n_bases"], keep[2].numpy().view(np.uint64),
                            keep[3].numpy().view(np.uint32))
-    hs_bytes = sum(t.numel() * t.element_size() for t in keep)
-    return hs, keep, hs_bytes
+    # the sparse form of the validity bitmap, as the BAM decoder emits it with every batch
+    # (kdf_bam_batch.invalid_pos): computed once here, outside any timed region
+    inv = engine.invalid_positions(hs.valid, hs.n_bases)
+    if inv is not None:
+        t = torch.empty(max(inv.shape[0], 1), dtype=torch.int32, pin_memory=pin)
+        t[:inv.shape[0]].copy_(torch.from_numpy(inv.view(np.int32)))
+        keep.append(t)
+        hs.invalid = t.numpy().view(np.uint32)[:inv.shape[0]]
+    return hs, keep, host_bytes(hs, True)
+
+
+def host_bytes(hs, with_reads):
+    """Bytes engine.upload copies for this stream (what crosses PCIe per step)."""
+    sparse = hs.invalid is not None and os.environ.get("KDF_SPARSE_VALID", "1") != "0"
+    n = hs.codes.nbytes + (hs.invalid.nbytes if sparse else hs.valid.nbytes)
+    if with_reads:
+        n += hs.read_starts.nbytes + hs.read_lens.nbytes
+    return n
 
 
 def to_device_stream(engine_mod, s):
@@ -459,10 +475,7 @@ def main():
             hs, kp, nb = stream_to_host(torch, trio[w], pin=True)
             hosts[w] = hs
             keep.append(kp)
-            if w == "child":
-                h2d += nb
-            else:
-                h2d += hs.codes.nbytes + hs.valid.nbytes
+            h2d += nb if w == "child" else host_bytes(hs, False)
         del d
         del trio
         torch.cuda.empty_cache()

@@ -399,6 +399,18 @@ int kdf_debug_hit_coverage_host(const uint32_t* hit_read, const uint32_t* hit_of
                                 const uint64_t* read_cig_off, const uint32_t* cigar,
                                 uint64_t* keys);
 
+/* ---- sparse validity ------------------------------------------------------
+ * The validity bitmap is all ones except one separator per read and the rare N /
+ * IUPAC base, so a stream can cross PCIe as codes + the ascending list of its invalid
+ * positions (kdf_bam_batch.invalid_pos, or kdf_invalid_positions on the host: returns
+ * the count, fills out[0 .. min(count, cap)); ~0 if n_bases > 2^32) and the bitmap be
+ * rebuilt on the device: valid[w] = all ones inside n_bases, then the listed bits
+ * cleared.  Same bitmap, a third less H2D traffic for the whole stream.          */
+uint64_t kdf_invalid_positions(const uint32_t* valid /*HOST*/, uint64_t n_bases, uint32_t* out /*HOST or NULL*/,
+                               uint64_t cap);
+int kdf_valid_from_invalid(uint32_t* valid /*DEV n_words*/, uint64_t n_bases,
+                           const uint32_t* invalid_pos /*DEV*/, uint64_t n_invalid, void* stream);
+
 /* ---- host helpers (CPU, no device) --------------------------------------
  * Pack ASCII sequences into the stream layout.  seqs: concatenated bytes,
  * offsets[n_seqs+1].  Returns the stream length in bases (sum of lengths +
@@ -456,6 +468,12 @@ typedef struct kdf_bam_batch {
   const uint64_t* raw_off;       /* n_reads+1 offsets into raw_blob (want_meta >= 3) */
   const uint8_t* raw_blob;       /* the BAM records (bytes after block_size) */
   int at_eof;
+  int has_invalid;               /* invalid_pos / n_invalid are set (n_bases <= 2^32) */
+  const uint32_t* invalid_pos;   /* HOST, ascending: positions of the invalid bases (separators,
+                                    N / IUPAC) — the sparse form of `valid`, a fifth of its size at
+                                    150-base reads; kdf_valid_from_invalid rebuilds the bitmap on
+                                    the device so that only codes + this list cross PCIe          */
+  uint64_t n_invalid;
 } kdf_bam_batch;
 
 int kdf_bam_open(const char* path, int n_threads, kdf_bam** out);

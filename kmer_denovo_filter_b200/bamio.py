@@ -32,7 +32,7 @@ class _Batch(ctypes.Structure):
         ("next_pos", _vp), ("flag", _vp), ("mapq", _vp), ("qname_off", _vp),
         ("qname_blob", _vp), ("cigar_off", _vp), ("cigar_blob", _vp),
         ("sa_off", _vp), ("sa_blob", _vp), ("qual_off", _vp), ("qual_blob", _vp), ("raw_off", _vp), ("raw_blob", _vp),
-        ("at_eof", _i),
+        ("at_eof", _i), ("has_invalid", _i), ("invalid_pos", _vp), ("n_invalid", _u64),
     ]
 
 
@@ -192,6 +192,8 @@ class HostBatch(_engine.HostStream):
                          raw.n_bases, _arr(raw.read_starts, n, np.uint64),
                          _arr(raw.read_lens, n, np.uint32))
         self.ref_names = ref_names
+        if raw.has_invalid:   # sparse form of `valid`: uploads send this list instead of the bitmap
+            self.invalid = _arr(raw.invalid_pos, int(raw.n_invalid), np.uint32)
         self.rec_index = _arr(raw.rec_index, n, np.uint64)
         self.at_eof = bool(raw.at_eof)
         self.has_meta = bool(want_meta)

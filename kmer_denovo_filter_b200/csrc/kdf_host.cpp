@@ -230,9 +230,27 @@ void pack_record(const uint8_t* nib, uint32_t l_seq, uint64_t start, uint64_t* c
 
 }  // namespace
 
+// positions of the invalid bases (0 bits) of a validity bitmap, ascending
+static uint64_t invalid_positions(const uint32_t* valid, uint64_t n_bases, uint32_t* out, uint64_t cap) {
+  uint64_t n = 0;
+  const uint64_t n_words = (n_bases + 31) / 32;
+  for (uint64_t w = 0; w < n_words; ++w) {
+    uint32_t inv = ~valid[w];
+    if (w == n_words - 1 && (n_bases & 31)) inv &= ~0u << (32 - (n_bases & 31));   // bits past the end are not bases
+    while (inv) {
+      int b = __builtin_clz(inv);          // base i of the word sits at bit 31 - i
+      if (out && n < cap) out[n] = (uint32_t)(w * 32 + (uint64_t)b);
+      ++n;
+      inv &= ~(0x80000000u >> b);
+    }
+  }
+  return n;
+}
+
 struct kdf_bam_batch_impl {
   std::vector<uint64_t> codes;
   std::vector<uint32_t> valid;
+  std::vector<uint32_t> invalid;   // positions of the invalid bases (sparse form of `valid`)
   std::vector<uint64_t> read_starts;
   std::vector<uint32_t> read_lens;
   std::vector<uint64_t> rec_index;
@@ -408,6 +426,12 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
     im->read_starts[i] = kept[i].start;
     im->read_lens[i] = kept[i].l_seq;
   }
+  if (n_bases <= 0xffffffffull) {   // sparse form of the validity bitmap (kdf_valid_from_invalid)
+    uint64_t n_inv = invalid_positions(im->valid.data(), n_bases, nullptr, 0);
+    im->invalid.resize(n_inv ? n_inv : 1);
+    invalid_positions(im->valid.data(), n_bases, im->invalid.data(), n_inv);
+    im->invalid.resize(n_inv);
+  }
   if (want_meta) {
     im->ref_id.resize(n);
     im->pos.resize(n);
@@ -521,7 +545,17 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
     }
   }
   out->at_eof = (b->eof && b->carry.empty()) ? 1 : 0;
+  if (n_bases <= 0xffffffffull) {
+    out->invalid_pos = im->invalid.data();
+    out->n_invalid = im->invalid.size();
+    out->has_invalid = 1;
+  }
   return KDF_OK;
+}
+
+uint64_t kdf_invalid_positions(const uint32_t* valid, uint64_t n_bases, uint32_t* out, uint64_t cap) {
+  if (!valid || n_bases > 0xffffffffull) return ~0ull;
+  return invalid_positions(valid, n_bases, out, cap);
 }
 
 void kdf_bam_batch_free(kdf_bam_batch* batch) {

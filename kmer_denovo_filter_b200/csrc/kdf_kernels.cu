@@ -1906,6 +1906,23 @@ __global__ void __launch_bounds__(128) k_hit_coverage(const u32* hit_read, const
 }
 
 // ------------------------------------------------ table maintenance -------
+// validity bitmap from its sparse form: all ones inside n_bases, listed positions cleared
+__global__ void __launch_bounds__(256) k_valid_fill(u32* valid, u64 n_words, u64 n_bases) {
+  u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+    u32 v = 0xffffffffu;
+    if (w == n_words - 1 && (n_bases & 31)) v <<= 32 - (u32)(n_bases & 31);
+    valid[w] = v;
+  }
+}
+__global__ void __launch_bounds__(256) k_valid_clear(u32* valid, u64 n_bases, const u32* pos, u64 n) {
+  u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    u32 p = pos[i];
+    if (p < n_bases) atomicAnd(valid + (p >> 5), ~(0x80000000u >> (p & 31)));
+  }
+}
+
 __global__ void k_or_flag(const u64* src, u64* flags, u64 bit) {
   if (*src) atomicOr(flags, bit);
 }
@@ -2911,6 +2928,24 @@ int kdf_count_bins_smem(int k, int n_parts, int n_src, const uint64_t* child_bin
   }
   // a sub-bin that overflowed its region: bit 1 of flags (read back by the caller)
   k_or_flag<<<1, 1, 0, st>>>(over, (u64*)flags, 2ull);
+  CUDA_TRY(cudaGetLastError());
+  return KDF_OK;
+}
+
+int kdf_valid_from_invalid(uint32_t* valid, uint64_t n_bases, const uint32_t* invalid_pos,
+                           uint64_t n_invalid, void* stream) {
+  if (n_bases == 0) return KDF_OK;
+  if (!valid || (n_invalid && !invalid_pos)) return fail(KDF_ERR_ARG, "kdf_valid_from_invalid: NULL argument");
+  if (n_bases > 0xffffffffull) return fail(KDF_ERR_ARG, "kdf_valid_from_invalid: stream longer than 2^32 bases");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int sm = current_sm_count();
+  const u64 n_words = (n_bases + 31) / 32;
+  int g = grid_for((const void*)k_valid_fill, 256, 0, n_words, sm);
+  k_valid_fill<<<g, 256, 0, st>>>(valid, n_words, n_bases);
+  if (n_invalid) {
+    g = grid_for((const void*)k_valid_clear, 256, 0, n_invalid, sm);
+    k_valid_clear<<<g, 256, 0, st>>>(valid, n_bases, invalid_pos, n_invalid);
+  }
   CUDA_TRY(cudaGetLastError());
   return KDF_OK;
 }

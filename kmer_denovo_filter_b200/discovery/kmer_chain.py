@@ -278,20 +278,20 @@ def discover_streams(eng, child, mother, father, ref, k, min_child_count=3,
         partitioned = child_capacity is None
     stats = eng.new_stats()
     up = _Uploader(eng)
-    # copy order = consumption order: child (in chunks, binned as they land), ref,
-    # the child's read index (needed by the scan only), mother, father
+    # copy order = consumption order: child (in chunks, binned as they land), ref, mother,
+    # father, and last the child's read index (12 bytes per read, needed by the scan only:
+    # ahead of the parents it delayed the father's arrival, which the chain waits for)
     if partitioned:
         d_child, ev_child = up.put_chunked(child, False)
         d_ref, ev_ref = up.put(ref, False)
-        ev_reads = up.put_read_index(d_child, child)
     else:
         d_child, ev_child = up.put(child, True)
         d_ref, ev_ref = up.put(ref, False)
-        ev_reads = None
         up.wait(ev_child)
         up.wait(ev_ref)
     d_mother, ev_mother = up.put(mother, False)
     d_father, ev_father = up.put(father, False)
+    ev_reads = up.put_read_index(d_child, child) if partitioned else None
 
     # Module 1 + reference subtraction: jellyfish count -C ; dump -L ; query ref.jf
     if partitioned:

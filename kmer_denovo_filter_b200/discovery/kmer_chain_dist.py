@@ -309,15 +309,16 @@ def discover_streams_dist(eng, child, mother, father, ref, k, min_child_count=3,
         # fused route: the child is copied in chunks and binned (= sent) as it lands
         d_child, ev_child = up.put_chunked(child, False)
         d_ref, ev_ref = up.put(ref, False)
-        ev_reads = up.put_read_index(d_child, child)
+        fused = True
     else:
         d_child, ev_child = up.put(child, True)
         d_ref, ev_ref = up.put(ref, False)
-        ev_reads = None
+        fused = False
         up.wait(ev_child)
         up.wait(ev_ref)
     d_mother, ev_mother = up.put(mother, False)
     d_father, ev_father = up.put(father, False)
+    ev_reads = up.put_read_index(d_child, child) if fused else None   # needed last: copied last
 
     c = count_child_dist(eng, [d_child], [d_ref], k, min_child_count, world)
     tot = torch.tensor([c["candidates"], c["child_distinct"]], dtype=torch.int64, device=eng.device)

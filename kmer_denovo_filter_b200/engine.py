@@ -93,6 +93,8 @@ _SIGNATURES = {
                                   _u32, _vp, _vp, _vp, _vp, _u64, _vp, _u32, _vp, _vp]),
     "kdf_debug_hash_host": (_i, [_vp, _vp, _u64, _i, _i, _u32, _u32, _vp, _vp, _vp]),
     "kdf_pack_sequences": (_u64, [_vp, _vp, _u64, _vp, _vp, _vp]),
+    "kdf_invalid_positions": (_u64, [_vp, _u64, _vp, _u64]),
+    "kdf_valid_from_invalid": (_i, [_vp, _u64, _vp, _u64, _vp]),
     "kdf_debug_extract_host": (_i, [_vp, _vp, _u64, _i, _i, _vp, _vp, _vp]),
     "kdf_bench_random_access": (_i, [_vp, _u64, _u64, _i, _vp, _vp]),
     # host BGZF/BAM decoder (bound in bamio.py)
@@ -145,16 +147,24 @@ def _np_ptr(a):
 
 class HostStream:
     """Packed stream in host memory (numpy): ``codes`` u64, ``valid`` u32,
-    ``n_bases``, ``read_starts`` u64, ``read_lens`` u32."""
+    ``n_bases``, ``read_starts`` u64, ``read_lens`` u32, and optionally ``invalid``
+    (u32, ascending positions of the invalid bases: the sparse form of ``valid`` —
+    when present, uploads send it instead of the bitmap, include/kdf.h)."""
 
-    __slots__ = ("codes", "valid", "n_bases", "read_starts", "read_lens")
+    __slots__ = ("codes", "valid", "n_bases", "read_starts", "read_lens", "invalid")
 
-    def __init__(self, codes, valid, n_bases, read_starts, read_lens):
+    def __init__(self, codes, valid, n_bases, read_starts, read_lens, invalid=None):
         self.codes = codes
         self.valid = valid
         self.n_bases = int(n_bases)
         self.read_starts = read_starts
         self.read_lens = read_lens
+        self.invalid = invalid
+
+    def with_sparse_validity(self):
+        """Compute ``invalid`` from ``valid`` (what the BAM decoder emits with a batch)."""
+        self.invalid = invalid_positions(self.valid, self.n_bases)
+        return self
 
     @property
     def n_reads(self):
@@ -167,6 +177,21 @@ class HostStream:
     def window_count_upper_bound(self, k):
         l = self.read_lens.astype(np.int64) - (k - 1)
         return int(np.clip(l, 0, None).sum())
+
+
+def invalid_positions(valid, n_bases):
+    """Ascending positions of the 0 bits of a validity bitmap (``kdf_invalid_positions``),
+    or None when the stream is longer than 2^32 bases."""
+    lib = load_library()
+    if n_bases > 0xFFFFFFFF:
+        return None
+    v = np.ascontiguousarray(valid, dtype=np.uint32)
+    if v.shape[0] == 0:
+        return np.zeros(0, dtype=np.uint32)
+    n = lib.kdf_invalid_positions(_np_ptr(v), int(n_bases), None, 0)
+    out = np.zeros(max(n, 1), dtype=np.uint32)
+    lib.kdf_invalid_positions(_np_ptr(v), int(n_bases), _np_ptr(out), n)
+    return out[:n]
 
 
 def pack_sequences(seqs):
@@ -188,7 +213,7 @@ def pack_sequences(seqs):
                                  _np_ptr(valid), _np_ptr(read_offsets))
     assert got == total
     return HostStream(codes[:n_words], valid[:n_words], total,
-                      read_offsets[:n].copy(), lens.astype(np.uint32))
+                      read_offsets[:n].copy(), lens.astype(np.uint32)).with_sparse_validity()
 
 
 def debug_extract_host(hs, k, random_access=False):
@@ -449,20 +474,40 @@ class CudaEngine:
         def host(a, dt):
             return torch.from_numpy(np.ascontiguousarray(a).view(dt))
 
-        src = [host(hs.codes, np.int64), host(hs.valid, np.int32)]
+        sparse = self._sparse(hs)
+        src = [host(hs.codes, np.int64), host(hs.invalid if sparse else hs.valid, np.int32)]
         if with_reads and hs.read_lens is not None:
             src += [host(hs.read_starts, np.int64), host(hs.read_lens, np.int32)]
         dst = [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in src]
+        valid = torch.empty((hs.n_bases + 31) // 32, dtype=torch.int32, device=self.device) if sparse else None
         if copy_stream is not None:
             copy_stream.wait_stream(main)
             with torch.cuda.stream(copy_stream):
                 for d, h in zip(dst, src):
                     d.copy_(h, non_blocking=True)
+                if sparse:
+                    self._valid_from_invalid(valid, hs.n_bases, dst[1], copy_stream)
         else:
             for d, h in zip(dst, src):
                 d.copy_(h, non_blocking=non_blocking)
+            if sparse:
+                self._valid_from_invalid(valid, hs.n_bases, dst[1], main)
         rs, rl = (dst[2], dst[3]) if len(dst) == 4 else (None, None)
-        return DeviceStream(dst[0], dst[1], hs.n_bases, rs, rl)
+        return DeviceStream(dst[0], valid if sparse else dst[1], hs.n_bases, rs, rl)
+
+    def _sparse(self, hs):
+        """Send the invalid-position list instead of the validity bitmap?"""
+        return (getattr(hs, "invalid", None) is not None and hs.n_bases > 0
+                and os.environ.get("KDF_SPARSE_VALID", "1") != "0")
+
+    def _valid_from_invalid(self, valid, n_bases, invalid_dev, stream):
+        """Rebuild the validity bitmap on ``stream`` from the uploaded list; the list
+        is kept alive by the stream-ordered allocator until the kernel has run."""
+        self._check(self.lib.kdf_valid_from_invalid(
+            valid.data_ptr(), int(n_bases), invalid_dev.data_ptr() if invalid_dev.numel() else None,
+            int(invalid_dev.numel()), ctypes.c_void_p(stream.cuda_stream)))
+        invalid_dev.record_stream(stream)
+        self.launches += 2
 
     def upload_chunked(self, hs, copy_stream, n_chunks=8, with_reads=True):
         """HostStream → DeviceStream copied chunk by chunk on ``copy_stream``; the
@@ -473,19 +518,25 @@ class CudaEngine:
         torch = self.torch
         main = torch.cuda.current_stream(self.device)
         n_words = (hs.n_bases + 31) // 32
+        sparse = self._sparse(hs)
         codes_h = torch.from_numpy(np.ascontiguousarray(hs.codes).view(np.int64))
-        valid_h = torch.from_numpy(np.ascontiguousarray(hs.valid).view(np.int32))
+        valid_h = torch.from_numpy(np.ascontiguousarray(hs.invalid if sparse else hs.valid).view(np.int32))
         codes = torch.empty(codes_h.shape, dtype=torch.int64, device=self.device)
-        valid = torch.empty(valid_h.shape, dtype=torch.int32, device=self.device)
+        valid = torch.empty(n_words, dtype=torch.int32, device=self.device)
         rs = rl = None
         step = max((n_words + n_chunks - 1) // n_chunks, 1)
         bounds = [(a, min(a + step, n_words)) for a in range(0, n_words, step)]
         copy_stream.wait_stream(main)
         events = []
         with torch.cuda.stream(copy_stream):
+            if sparse:   # the whole (small) list first, the bitmap rebuilt before the first chunk
+                inv = torch.empty(valid_h.shape, dtype=torch.int32, device=self.device)
+                inv.copy_(valid_h, non_blocking=True)
+                self._valid_from_invalid(valid, hs.n_bases, inv, copy_stream)
             for a, b in bounds:
                 codes[a:b].copy_(codes_h[a:b], non_blocking=True)
-                valid[a:b].copy_(valid_h[a:b], non_blocking=True)
+                if not sparse:
+                    valid[a:b].copy_(valid_h[a:b], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
                 events.append(ev)

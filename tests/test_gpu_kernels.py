@@ -586,6 +586,37 @@ def test_table_filter_keeps_results_exact(eng, k):
     assert eng.lookup_keys(t, lo, hi)[1].cpu().numpy().view(np.uint32).tolist() == res[0][0]
 
 
+def test_sparse_validity_upload_rebuilds_the_bitmap(eng, monkeypatch):
+    """Uploads send codes + the invalid-position list and rebuild the validity bitmap on
+    the device (kdf_valid_from_invalid): same bitmap as the dense upload, for plain,
+    copy-stream and chunked uploads, ragged ends and an empty stream."""
+    from kmer_denovo_filter_b200 import engine
+    import torch
+    _g, reads = _genome_reads(701, glen=5000, n=400)
+    reads = reads + ["", "N" * 40, "ACGTNNACGT", "A" * 33, "C"]
+    hs = engine.pack_sequences(reads)
+    assert hs.invalid is not None and hs.invalid.shape[0] >= len(reads) - 1
+    monkeypatch.setenv("KDF_SPARSE_VALID", "0")
+    dense = eng.upload(hs)
+    monkeypatch.setenv("KDF_SPARSE_VALID", "1")
+    side = torch.cuda.Stream(device=eng.device)
+    a = eng.upload(hs)
+    b = eng.upload(hs, copy_stream=side)
+    c, ev = eng.upload_chunked(hs, side, n_chunks=5)
+    torch.cuda.synchronize()
+    want = dense.valid.cpu().numpy()
+    assert np.array_equal(want.view(np.uint32), hs.valid)
+    for d in (a, b, c):
+        assert np.array_equal(d.valid.cpu().numpy(), want)
+        assert np.array_equal(d.codes.cpu().numpy(), dense.codes.cpu().numpy())
+    st = eng.new_stats()
+    t = eng.new_table(31, n_keys=16)
+    eng.count_stream(t, a, engine.MODE_COUNT_IF_PRESENT, 0, 1, st)
+    assert eng.read_stats(st)["windows"] == sum(kmers.count_sequences(reads, 31).values())
+    e = eng.upload(engine.pack_sequences([]))
+    assert e.n_bases == 0
+
+
 def test_count_bins_packed_heavy_duplicates(eng):
     """Many concurrent copies of few keys (the saturating CAS under contention) and
     keys whose top bases are all T (state bits next to an all-ones key prefix)."""

@@ -27,6 +27,7 @@ def test_fasta_stream_matches_oracle(giab_paths, giab_records, who):
     assert np.array_equal(b.codes, hs.codes) and np.array_equal(b.valid, hs.valid)
     assert np.array_equal(b.read_starts, hs.read_starts)
     assert np.array_equal(b.read_lens, hs.read_lens)
+    assert np.array_equal(b.invalid, hs.invalid)     # the decoder's sparse form of `valid`
 
 
 def test_scan_stream_and_metadata(giab_paths, giab_records):

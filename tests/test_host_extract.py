@@ -75,3 +75,23 @@ def test_engine_refuses_without_gpu():
         pytest.skip("GPU present")
     with pytest.raises(engine.KdfError):
         engine.CudaEngine()
+
+
+def test_invalid_positions_is_the_sparse_form_of_valid():
+    """kdf_invalid_positions (and the list the BAM decoder attaches to a batch) names
+    exactly the 0 bits of the validity bitmap inside n_bases, ascending: separators,
+    N / IUPAC bases, nothing past the end of the stream."""
+    for seed in range(6):
+        seqs = _rand_seqs(seed, n=40) + ["", "N", "ACGT" * 8, "A" * 31, "C" * 33]
+        hs = engine.pack_sequences(seqs)
+        bits = np.unpackbits(np.ascontiguousarray(hs.valid).view(np.uint8).reshape(-1, 4)[:, ::-1].reshape(-1))
+        want = np.flatnonzero(bits[:hs.n_bases] == 0).astype(np.uint32)
+        assert np.array_equal(hs.invalid, want)
+        assert np.array_equal(engine.invalid_positions(hs.valid, hs.n_bases), want)
+        # rebuilding the bitmap from the list (what kdf_valid_from_invalid does on the device)
+        rebuilt = np.ones(hs.n_words * 32, dtype=np.uint8)
+        rebuilt[hs.n_bases:] = 0
+        rebuilt[want] = 0
+        assert np.array_equal(np.packbits(rebuilt).view(">u4").astype(np.uint32), hs.valid)
+    empty = engine.pack_sequences([])
+    assert empty.invalid is not None and empty.invalid.shape[0] == 0
