@@ -64,3 +64,27 @@ def test_low_entropy_keys_do_not_collapse():
     _p, bucket, _o = engine.debug_hash_host(keys, None, 1, 0, 1 << 16, 1)
     # distinct keys spread: no bucket holds more than a handful
     assert np.bincount(bucket).max() <= 6
+
+
+def test_filter_words_and_partition_plans():
+    """Host-side sizing: the two-bit filter takes 32 bits per key, 16 when only that fits
+    the budget, none beyond; the packed count plans half as many hash ranges as the plane
+    form for the same L2 slice."""
+    from kmer_denovo_filter_b200.discovery import kmer_chain
+    fw = engine.CudaEngine.filter_words
+    mb = 1 << 20
+    assert fw(1, 32 * mb) == 1024
+    assert fw(3_893_677, 32 * mb) * 4 == 16 * mb          # 32 bits per key
+    assert fw(7_790_648, 32 * mb) * 4 == 32 * mb
+    assert fw(15_602_227, 32 * mb) * 4 == 32 * mb         # 16 bits per key
+    assert fw(31_243_893, 32 * mb) == 0                   # no filter: the binned route
+    for n in (1, 1000, 5_000_000):
+        w = fw(n, 1 << 30)
+        assert w & (w - 1) == 0 and w >= min(n, 1024)
+    n_win = 1_920_000_000
+    p_plane, c_plane = kmer_chain.plan_partitions(n_win, key_words=1, packed=False)
+    p_pack, c_pack = kmer_chain.plan_partitions(n_win, key_words=1, packed=True)
+    assert (p_plane, p_pack) == (64, 32)
+    assert c_pack * 8 <= kmer_chain.SLICE_BYTES and c_plane * 16 <= kmer_chain.SLICE_BYTES
+    assert p_pack * c_pack >= n_win // 8 and c_pack % 4 == 0
+    assert kmer_chain.plan_partitions(100, key_words=2, packed=True)[0] == 1
