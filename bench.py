@@ -10,8 +10,11 @@ child count -> threshold -> reference subtraction -> mother / father filtered
 counts -> proband-unique set -> per-read distinct-hit scan.  The metric is
 canonical k-mer instances counted + queried per second, summed over stages.
 At N > 1 every rank holds 1/N of each sample's reads of an N x 64 Mbp genome
-(weak scaling); the child table is partitioned by hash range and k-mers are
-routed to their owner with an NCCL all-to-all.
+(weak scaling); the child table is partitioned by owner rank and k-mers are
+routed to their owner by the binning kernel itself, over NVLink peer memory
+(NCCL all-to-all where peer memory is unavailable).
+`e2e` is the same call on pinned HOST buffers in the decoder's batch format
+(codes + the sparse validity list), H2D and D2H inside the timed region.
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 """
