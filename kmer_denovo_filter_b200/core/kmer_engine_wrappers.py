@@ -62,12 +62,18 @@ def count_bam_into_table(eng, bam_path, table, mode, plane, threads, batch_bases
     """Stream ``samtools fasta -F 0xD00``-equivalent reads of a BAM through K1+K2
     against ``table`` (filtered parent counts: the table is primed with the filter
     set and never grows).  Returns ``(table, stats dict)``."""
+    from ..discovery import kmer_chain as _kmer_chain   # (discovery imports this module)
     total = {"windows": 0, "hits": 0, "new": 0, "reads": 0, "bases": 0}
     with bamio.BamReader(bam_path, threads=threads) as rd:
         for batch in rd.batches(bamio.MODE_FASTA, max_bases=batch_bases):
             ds = eng.upload(batch, with_reads=False)
             st = eng.new_stats()
-            eng.count_stream(table, ds, mode, plane, 1, st)
+            if mode == _engine.MODE_COUNT_IF_PRESENT:
+                # direct probe (behind the table's filter when it has one), or — for a filter
+                # set far larger than L2 — bin the batch by hash range and apply the bins
+                _kmer_chain.count_if_present(eng, table, ds, st, plane)
+            else:
+                eng.count_stream(table, ds, mode, plane, 1, st)
             s = eng.read_stats(st)
             if s["full"]:
                 raise _engine.KdfError(
