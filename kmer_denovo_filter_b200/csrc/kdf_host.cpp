@@ -601,7 +601,47 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
     im->sa_off.assign(n + 1, 0);
     if (want_meta >= 2) im->qual_off.assign(n + 1, 0);
     if (want_meta >= 3) im->raw_off.assign(n + 1, 0);
-    for (size_t i = 0; i < n; ++i) {
+    // pass 1 (parallel): fixed fields, and the size of every variable-length piece
+    std::vector<const uint8_t*> sa_ptr(n, nullptr);
+    auto find_sa = [](const uint8_t* t, const uint8_t* end, size_t* len) -> const uint8_t* {
+      const uint8_t* found = nullptr;
+      *len = 0;
+      while (t + 3 <= end) {   // walk the aux tags up to the SA:Z tag (a record has one at most)
+        char t0 = (char)t[0], t1 = (char)t[1], ty = (char)t[2];
+        t += 3;
+        size_t adv = 0;
+        switch (ty) {
+          case 'A': case 'c': case 'C': adv = 1; break;
+          case 's': case 'S': adv = 2; break;
+          case 'i': case 'I': case 'f': adv = 4; break;
+          case 'Z': case 'H': {
+            const uint8_t* z = (const uint8_t*)memchr(t, 0, (size_t)(end - t));
+            if (!z) return found;
+            if (t0 == 'S' && t1 == 'A' && ty == 'Z') {
+              *len = (size_t)(z - t);
+              return t;
+            }
+            adv = (size_t)(z - t) + 1;
+            break;
+          }
+          case 'B': {
+            if (t + 5 > end) return found;
+            char sub = (char)t[0];
+            uint32_t cnt;
+            memcpy(&cnt, t + 1, 4);
+            size_t sz = (sub == 'c' || sub == 'C') ? 1 : ((sub == 's' || sub == 'S') ? 2 : 4);
+            adv = 5 + sz * cnt;
+            break;
+          }
+          default: return found;
+        }
+        if (t >= end) break;
+        t += adv;
+      }
+      return found;
+    };
+#pragma omp parallel for schedule(static) num_threads(b->threads)
+    for (long i = 0; i < (long)n; ++i) {
       const uint8_t* r = kept[i].rec;
       int32_t bs = rd_i32(r - 4);
       uint8_t l_name = r[8];
@@ -613,59 +653,49 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
       im->flag[i] = rd_u16(r + 14);
       im->next_ref_id[i] = rd_i32(r + 20);
       im->next_pos[i] = rd_i32(r + 24);
-      size_t ql = l_name ? (size_t)l_name - 1 : 0;
-      im->qname_blob.insert(im->qname_blob.end(), (const char*)r + 32, (const char*)r + 32 + ql);
-      im->qname_off[i + 1] = im->qname_blob.size();
+      im->qname_off[i + 1] = l_name ? (size_t)l_name - 1 : 0;
+      im->cigar_off[i + 1] = n_cig;
+      if (want_meta >= 3) im->raw_off[i + 1] = (uint64_t)bs;
+      if (want_meta >= 2) im->qual_off[i + 1] = l_seq;
+      const uint8_t* t = r + 32 + l_name + 4 * (size_t)n_cig + (l_seq + 1) / 2 + l_seq;
+      size_t sl = 0;
+      sa_ptr[i] = find_sa(t, r + bs, &sl);
+      im->sa_off[i + 1] = sl;
+    }
+    // offsets
+    for (size_t i = 0; i < n; ++i) {
+      im->qname_off[i + 1] += im->qname_off[i];
+      im->cigar_off[i + 1] += im->cigar_off[i];
+      im->sa_off[i + 1] += im->sa_off[i];
+      if (want_meta >= 2) im->qual_off[i + 1] += im->qual_off[i];
+      if (want_meta >= 3) im->raw_off[i + 1] += im->raw_off[i];
+    }
+    im->qname_blob.resize(im->qname_off[n]);
+    im->cigar_blob.resize(im->cigar_off[n]);
+    im->sa_blob.resize(im->sa_off[n]);
+    if (want_meta >= 2) im->qual_blob.resize(im->qual_off[n]);
+    if (want_meta >= 3) im->raw_blob.resize(im->raw_off[n]);
+    // pass 2 (parallel): copy the pieces to their places
+#pragma omp parallel for schedule(static) num_threads(b->threads)
+    for (long i = 0; i < (long)n; ++i) {
+      const uint8_t* r = kept[i].rec;
+      uint8_t l_name = r[8];
+      uint16_t n_cig = rd_u16(r + 12);
+      uint32_t l_seq = kept[i].l_seq;
+      size_t ql = im->qname_off[i + 1] - im->qname_off[i];
+      if (ql) memcpy(&im->qname_blob[im->qname_off[i]], r + 32, ql);
       const uint8_t* cg = r + 32 + l_name;
-      for (uint16_t c = 0; c < n_cig; ++c) {
-        uint32_t v;
-        memcpy(&v, cg + 4 * c, 4);
-        im->cigar_blob.push_back(v);
-      }
-      im->cigar_off[i + 1] = im->cigar_blob.size();
+      if (n_cig) memcpy(&im->cigar_blob[im->cigar_off[i]], cg, 4 * (size_t)n_cig);
       if (want_meta >= 3) {
-        im->raw_blob.insert(im->raw_blob.end(), r, r + bs);
-        im->raw_off[i + 1] = im->raw_blob.size();
+        size_t bs = im->raw_off[i + 1] - im->raw_off[i];
+        if (bs) memcpy(&im->raw_blob[im->raw_off[i]], r, bs);
       }
-      if (want_meta >= 2) {
+      if (want_meta >= 2 && l_seq) {
         const uint8_t* q = cg + 4 * (size_t)n_cig + (l_seq + 1) / 2;
-        im->qual_blob.insert(im->qual_blob.end(), q, q + l_seq);
-        im->qual_off[i + 1] = im->qual_blob.size();
+        memcpy(&im->qual_blob[im->qual_off[i]], q, l_seq);
       }
-      // walk aux tags for SA:Z
-      const uint8_t* t = cg + 4 * (size_t)n_cig + (l_seq + 1) / 2 + l_seq;
-      const uint8_t* end = r + bs;
-      while (t + 3 <= end) {
-        char t0 = (char)t[0], t1 = (char)t[1], ty = (char)t[2];
-        t += 3;
-        size_t adv = 0;
-        switch (ty) {
-          case 'A': case 'c': case 'C': adv = 1; break;
-          case 's': case 'S': adv = 2; break;
-          case 'i': case 'I': case 'f': adv = 4; break;
-          case 'Z': case 'H': {
-            const uint8_t* z = (const uint8_t*)memchr(t, 0, (size_t)(end - t));
-            if (!z) { t = end; adv = 0; break; }
-            if (t0 == 'S' && t1 == 'A' && ty == 'Z')
-              im->sa_blob.insert(im->sa_blob.end(), (const char*)t, (const char*)z);
-            adv = (size_t)(z - t) + 1;
-            break;
-          }
-          case 'B': {
-            if (t + 5 > end) { t = end; break; }
-            char sub = (char)t[0];
-            uint32_t cnt;
-            memcpy(&cnt, t + 1, 4);
-            size_t sz = (sub == 'c' || sub == 'C') ? 1 : ((sub == 's' || sub == 'S') ? 2 : 4);
-            adv = 5 + sz * cnt;
-            break;
-          }
-          default: t = end; break;
-        }
-        if (t >= end) break;
-        t += adv;
-      }
-      im->sa_off[i + 1] = im->sa_blob.size();
+      size_t sl = im->sa_off[i + 1] - im->sa_off[i];
+      if (sl) memcpy(&im->sa_blob[im->sa_off[i]], sa_ptr[i], sl);
     }
   }
   // keep undecoded tail for the next call

@@ -100,6 +100,16 @@ def test_synthetic_bam_roundtrip(tmp_path):
     assert s.record(3).get_tag("SA") == "chr1,5,+,4M,60,0;"
     assert s.record(3).is_supplementary and s.record(4).is_unmapped
     assert s.record(3).get_aligned_pairs() == [(2, 22), (3, 23)]
+    assert [s.record(i).has_tag("SA") for i in range(s.n_reads)] == [False] * 3 + [True, False, False]
+    # qualities (want_meta=2) and the raw records (want_meta=3), several decoder threads
+    with bamio.BamReader(p, threads=3) as rd:
+        a = rd.next_batch(bamio.MODE_ALL, want_meta=3)
+    assert a.n_reads == len(recs)
+    for i, raw in enumerate(recs):
+        assert bytes(a.raw_blob[int(a.raw_off[i]):int(a.raw_off[i + 1])]) == raw[4:]   # after block_size
+        l_seq = int(a.read_lens[i])
+        assert int(a.qual_off[i + 1] - a.qual_off[i]) == l_seq
+    assert [a.record(i).cigartuples for i in (0, 5, 6)] == [[(0, 7)], [(4, 2), (0, 2)], None]
 
 
 def test_not_a_bam(tmp_path):
