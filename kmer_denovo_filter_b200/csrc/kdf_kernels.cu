@@ -7,14 +7,24 @@
 //                           mark-if-present / emit-hits; table in L2/HBM or,
 //                           for small read-only sets, copied to shared memory
 //       k_update_keys       the same table ops on explicit key arrays
+//       k_stream<FILT>      the probing ops behind a two-bit filter in L2
+//                           (kdf_table_build_filter): one 32-bit load per window,
+//                           the table is probed only from the queue drain
 //   K2p k_bin_stream/_keys  hash-range binning of canonical k-mers (shared-memory
-//                           staged), feeding k_update_keys on an L2-resident
-//                           table slice per bin (kdf_count_bins)
+//                           staged), feeding the per-bin count of kdf_count_bins
+//   K2c k_packed_keys       the per-bin count in packed form (saturating counter in
+//                           the key's spare bits, keys-only L2 slice; queued
+//                           compare-and-swaps), and the probing ops of
+//                           kdf_update_bins; k_emit_packed = emit + clear
+//   K2s k_rebin/k_count_sub shared-memory variant of the packed count (off by default)
 //   K3  k_threshold_compact threshold + stream compaction (dump -L, == 0, <= pmc)
 //   K4  k_lookup_keys       batched membership / count lookup
 //   K5  k_scan_reads        dense per-read scan + distinct reduction
 //       k_reduce_hits       sparse per-read reduction of an emitted hit list
-//   K6  k_bin_stream<OWNER> owner binning in front of the NCCL all-to-all
+//   K6  k_bin_stream<OWNER> owner (x hash range) binning; with peer-mapped
+//                           destinations the flush IS the multi-GPU all-to-all
+//   K7  k_hit_coverage      reference positions under the hit windows (+ cub sort/RLE)
+//       k_valid_fill/_clear validity bitmap from its sparse form (PCIe format)
 //
 // Nothing here is a dense contraction, so there is no tensor-core code: the
 // work is bounded by L2 / HBM sector traffic and instruction issue.
