@@ -43,9 +43,26 @@ template <class T> struct NoInitAlloc : std::allocator<T> {
 };
 
 struct BlockRef {
-  uint64_t coff;   // offset of the block in the compressed file
+  uint64_t coff;   // offset of the block in the compressed bytes
   uint32_t csize;  // total block size
   uint32_t usize;  // uncompressed size (ISIZE)
+  uint64_t uoff;   // offset of its data in the inflated chunk
+};
+
+// compressed BGZF blocks of one chunk, read but not yet inflated
+struct CompBuf {
+  std::vector<uint8_t, NoInitAlloc<uint8_t>> bytes;
+  std::vector<BlockRef> blocks;
+  uint64_t total_u = 0;
+  bool valid = false;
+};
+
+// an inflated chunk: logical bytes data[begin .. size), `begin` leaves headroom for the
+// unparsed tail of the chunk before it
+struct Chunk {
+  uint8_t* data = nullptr;
+  size_t begin = 0, size = 0, cap = 0;
+  bool valid = false;
 };
 
 struct Bam {
@@ -63,8 +80,14 @@ struct Bam {
   // inflate buffers, recycled across chunks and batches: plain malloc memory (no
   // zero-fill, no growth copies) whose pages stay mapped once touched
   std::vector<std::pair<uint8_t*, size_t>> pool;
-  std::vector<uint8_t, NoInitAlloc<uint8_t>> comp;   // compressed bytes of the chunk being read
-  std::vector<uint8_t> pending;                       // read from the file, not yet taken as blocks
+  std::vector<uint8_t> pending;   // read from the file, not yet taken as blocks
+  bool file_eof = false;          // nothing left to read from the file
+  uint64_t chunk_bytes = 64ull << 20;   // data per pipeline chunk (KDF_BAM_CHUNK_KB: tests)
+  size_t gap = 1u << 20;                // headroom in front of a chunk (KDF_BAM_GAP: tests)
+  // the decode pipeline (kdf_bam_next_batch): the chunk being parsed, the inflated
+  // chunk after it, and the compressed bytes of the one after that
+  Chunk cur, next;
+  CompBuf ahead, ahead2;
   uint8_t* get_buf(size_t n, size_t* cap) {
     size_t best = pool.size();
     for (size_t i = 0; i < pool.size(); ++i)
@@ -95,6 +118,8 @@ struct Bam {
     pool.emplace_back(p, cap);
   }
   ~Bam() {
+    if (cur.valid) free(cur.data);
+    if (next.valid) free(next.data);
     for (auto& e : pool) free(e.first);
   }
 };
@@ -116,17 +141,16 @@ bool inflate_block(const uint8_t* src, uint32_t csize, uint8_t* dst, uint32_t us
   return rc == Z_STREAM_END && zs.total_out == usize;
 }
 
-// Read up to `want_bytes` of uncompressed data worth of BGZF blocks and inflate them in
-// parallel into a pooled buffer that starts with the `tail_len` bytes at `tail` (the
-// unparsed end of the previous chunk).  *out / *out_size / *out_cap describe the buffer
-// (the caller returns it with Bam::put_buf).
-bool read_chunk(Bam* b, uint64_t want_bytes, const uint8_t* tail, size_t tail_len, uint8_t** out,
-                size_t* out_size, size_t* out_cap) {
-  // The compressed bytes are read in large slabs and the BGZF block headers walked in
-  // memory (one fread per block cost a fifth of the decode time); what follows the last
-  // block taken stays in b->pending for the next call.
-  auto& comp = b->comp;
+// Stage 1 (serial): the compressed bytes of up to `want_bytes` of data.  The file is read
+// in large slabs and the BGZF block headers walked in memory (one fread per block cost a
+// fifth of the decode time); what follows the last block taken stays in b->pending.
+// Errors go to `err` (this may run on a worker thread; g_host_err is thread-local).
+bool read_comp(Bam* b, uint64_t want_bytes, CompBuf& cb, std::string& err) {
+  auto& comp = cb.bytes;
   comp.clear();
+  cb.blocks.clear();
+  cb.total_u = 0;
+  cb.valid = false;
   comp.insert(comp.end(), b->pending.begin(), b->pending.end());
   b->pending.clear();
   const size_t SLAB = 8u << 20;
@@ -137,28 +161,26 @@ bool read_chunk(Bam* b, uint64_t want_bytes, const uint8_t* tail, size_t tail_le
     comp.resize(at + got);
     return got > 0;
   };
-  std::vector<BlockRef> blocks;
-  uint64_t total_u = 0;
   size_t pos = 0;
-  while (total_u < want_bytes) {
+  while (cb.total_u < want_bytes) {
     if (comp.size() - pos < 18) {
       if (refill()) continue;
       if (comp.size() == pos) {
-        b->eof = true;
+        b->file_eof = true;
         break;
       }
-      g_host_err = "not a BGZF block (is this a BAM file?)";
+      err = "not a BGZF block (is this a BAM file?)";
       return false;
     }
     const uint8_t* hdr = comp.data() + pos;
     if (hdr[0] != 31 || hdr[1] != 139 || hdr[2] != 8 || !(hdr[3] & 4)) {
-      g_host_err = "not a BGZF block (is this a BAM file?)";
+      err = "not a BGZF block (is this a BAM file?)";
       return false;
     }
     uint16_t xlen = (uint16_t)(hdr[10] | (hdr[11] << 8));
     if (comp.size() - pos < (size_t)12 + xlen) {
       if (refill()) continue;
-      g_host_err = "truncated BGZF header";
+      err = "truncated BGZF header";
       return false;
     }
     // locate the BC subfield (normally the only one)
@@ -171,60 +193,78 @@ bool read_chunk(Bam* b, uint64_t want_bytes, const uint8_t* tail, size_t tail_le
       p += 4 + slen;
     }
     if (bsize < 0) {
-      g_host_err = "BGZF block without BC subfield";
+      err = "BGZF block without BC subfield";
       return false;
     }
     if (bsize < 12 + (int)xlen + 8) {
-      g_host_err = "corrupt BGZF block size";
+      err = "corrupt BGZF block size";
       return false;
     }
     if (comp.size() - pos < (size_t)bsize) {
       if (refill()) continue;
-      g_host_err = "truncated BGZF block";
+      err = "truncated BGZF block";
       return false;
     }
     const uint8_t* tl = comp.data() + pos + bsize - 4;
     uint32_t isize = tl[0] | (tl[1] << 8) | (tl[2] << 16) | ((uint32_t)tl[3] << 24);
-    blocks.push_back({(uint64_t)pos, (uint32_t)bsize, isize});
-    total_u += isize;
+    cb.blocks.push_back({(uint64_t)pos, (uint32_t)bsize, isize, cb.total_u});
+    cb.total_u += isize;
     pos += (size_t)bsize;
   }
   b->pending.assign(comp.begin() + (long)pos, comp.end());
-  size_t cap = 0;
-  uint8_t* dst = b->get_buf(tail_len + total_u + 1, &cap);
-  if (!dst) {
-    g_host_err = "out of memory";
-    return false;
-  }
-  if (tail_len) memcpy(dst, tail, tail_len);
-  std::vector<uint64_t> uoff(blocks.size() + 1, 0);
-  for (size_t i = 0; i < blocks.size(); ++i) uoff[i + 1] = uoff[i] + blocks[i].usize;
-  int bad = 0;
-#pragma omp parallel for schedule(dynamic, 8) num_threads(b->threads) reduction(| : bad)
-  for (long i = 0; i < (long)blocks.size(); ++i) {
-    if (blocks[i].usize == 0) continue;
-    if (!inflate_block(comp.data() + blocks[i].coff, blocks[i].csize, dst + tail_len + uoff[i],
-                       blocks[i].usize))
-      bad |= 1;
-  }
-  if (bad) {
-    b->put_buf(dst, cap);
-    g_host_err = "BGZF inflate failed";
-    return false;
-  }
-  *out = dst;
-  *out_size = tail_len + total_u;
-  *out_cap = cap;
+  cb.valid = !cb.blocks.empty();
   return true;
 }
 
-// the same, appended to a vector (header parsing)
+// a pooled buffer for the data of `cb` behind `gap` bytes of headroom
+bool alloc_chunk(Bam* b, const CompBuf& cb, size_t gap, Chunk& c) {
+  size_t cap = 0;
+  uint8_t* p = b->get_buf(gap + cb.total_u + 1, &cap);
+  if (!p) return false;
+  c.data = p;
+  c.begin = gap;
+  c.size = gap + cb.total_u;
+  c.cap = cap;
+  c.valid = false;   // until inflated
+  return true;
+}
+
+// Stage 2 (one block; any thread)
+inline bool inflate_one(const CompBuf& cb, size_t i, Chunk& c) {
+  const BlockRef& br = cb.blocks[i];
+  if (br.usize == 0) return true;
+  return inflate_block(cb.bytes.data() + br.coff, br.csize, c.data + c.begin + br.uoff, br.usize);
+}
+
+// read + inflate `want_bytes` more, appended to a vector (header parsing only)
 bool read_chunk(Bam* b, uint64_t want_bytes, std::vector<uint8_t>& out) {
-  uint8_t* p = nullptr;
-  size_t n = 0, cap = 0;
-  if (!read_chunk(b, want_bytes, nullptr, 0, &p, &n, &cap)) return false;
-  out.insert(out.end(), p, p + n);
-  b->put_buf(p, cap);
+  std::string err;
+  CompBuf& cb = b->ahead;
+  if (!read_comp(b, want_bytes, cb, err)) {
+    g_host_err = err;
+    return false;
+  }
+  if (!cb.valid) {
+    b->eof = true;
+    return true;
+  }
+  Chunk c;
+  if (!alloc_chunk(b, cb, 0, c)) {
+    g_host_err = "out of memory";
+    return false;
+  }
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic, 8) num_threads(b->threads) reduction(| : bad)
+  for (long i = 0; i < (long)cb.blocks.size(); ++i)
+    if (!inflate_one(cb, (size_t)i, c)) bad |= 1;
+  cb.valid = false;
+  if (bad) {
+    b->put_buf(c.data, c.cap);
+    g_host_err = "BGZF inflate failed";
+    return false;
+  }
+  out.insert(out.end(), c.data + c.begin, c.data + c.size);
+  b->put_buf(c.data, c.cap);
   return true;
 }
 
@@ -374,6 +414,14 @@ int kdf_bam_open(const char* path, int n_threads, kdf_bam** out) {
   Bam* b = new Bam;
   b->fh = fh;
   b->threads = n_threads > 0 ? n_threads : 1;
+  if (const char* e = getenv("KDF_BAM_CHUNK_KB")) {
+    long v = atol(e);
+    if (v > 0) b->chunk_bytes = (uint64_t)v << 10;
+  }
+  if (const char* e = getenv("KDF_BAM_GAP")) {
+    long v = atol(e);
+    if (v >= 0) b->gap = (size_t)v;
+  }
   g_host_err.clear();
   if (!parse_header(b)) {
     fclose(fh);
@@ -425,41 +473,53 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
     uint64_t start;
     uint32_t l_seq;
   };
-  struct Chunk {
-    uint8_t* data;
-    size_t size, cap;
-  };
   std::vector<Kept> kept;
   uint64_t n_bases = 0;
-  // Chunk buffers stay where they are until the batch is packed (kept records point
-  // into them); a record that straddles two chunks is completed by copying the
-  // unparsed tail of the old chunk to the front of the new one.
-  std::vector<Chunk> chunks;
-  auto release_chunks = [&]() {
-    for (auto& c : chunks) b->put_buf(c.data, c.cap);
-    chunks.clear();
+  // The decode is a three-stage pipeline over chunks of ~64 MB of records: while one
+  // thread walks the records of chunk C (a serial chain: every header is a cache miss),
+  // another reads the compressed bytes of chunk C+2 and the rest inflate chunk C+1.
+  // Chunks whose records were kept stay where they are until the batch is packed; a
+  // record that straddles two chunks is completed by copying the unparsed tail of the
+  // old chunk into the headroom in front of the new one.  What is not consumed (the rest
+  // of the current chunk, the look-ahead) stays in the reader for the next batch.
+  const uint64_t CHUNK_BYTES = b->chunk_bytes;
+  const size_t GAP = b->gap;
+  std::vector<Chunk> retired;
+  auto release_retired = [&]() {
+    for (auto& c : retired) b->put_buf(c.data, c.cap);
+    retired.clear();
   };
-  {
+  auto bail = [&](const std::string& msg) {
+    g_host_err = msg;
+    release_retired();
+    delete im;
+    return KDF_ERR_ARG;
+  };
+  if (!b->cur.valid) {   // first call: the bytes that followed the header
     size_t cap = 0;
     uint8_t* p = b->get_buf(b->carry.size() + 1, &cap);
+    if (!p) return bail("out of memory");
     if (!b->carry.empty()) memcpy(p, b->carry.data(), b->carry.size());
-    chunks.push_back({p, b->carry.size(), cap});
+    b->cur.data = p;
+    b->cur.begin = 0;
+    b->cur.size = b->carry.size();
+    b->cur.cap = cap;
+    b->cur.valid = true;
     b->carry.clear();
   }
-  const uint8_t* buf = chunks.back().data;
-  size_t buf_size = chunks.back().size;
-  size_t off = 0;
+  const uint8_t* buf = b->cur.data;
+  size_t buf_size = b->cur.size;
+  size_t off = b->cur.begin;
   bool done = false;
-  while (!done) {
-    // parse all complete records currently in the chunk
+  std::string perr, rerr;
+  // stage 3: parse all complete records currently in the chunk
+  auto parse = [&]() {
     while (true) {
       if (buf_size - off < 4) break;
       int32_t bs = rd_i32(buf + off);
       if (bs < 32) {
-        g_host_err = "corrupt BAM record";
-        release_chunks();
-        delete im;
-        return KDF_ERR_ARG;
+        perr = "corrupt BAM record";
+        return;
       }
       if (buf_size - off - 4 < (size_t)bs) break;
       const uint8_t* r = buf + off + 4;
@@ -500,21 +560,83 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
       b->record_index++;
       off += 4 + (size_t)bs;
     }
-    if (done) break;
-    if (b->eof) break;
-    // need more data: a new chunk that starts with the unparsed tail of this one
-    uint8_t* p = nullptr;
-    size_t n = 0, cap = 0;
-    if (!read_chunk(b, 64ull << 20, buf + off, buf_size - off, &p, &n, &cap)) {
-      release_chunks();
-      delete im;
-      return KDF_ERR_ARG;
+  };
+  while (true) {
+    // the compressed blocks of the next chunk must be at hand (read here only when the
+    // pipeline is cold: otherwise stage 1 of the previous round fetched them)
+    if (!b->next.valid && !b->ahead.valid && !b->file_eof) {
+      if (!read_comp(b, CHUNK_BYTES, b->ahead, rerr)) return bail(rerr);
     }
-    chunks.push_back({p, n, cap});
-    buf = p;
-    buf_size = n;
-    off = 0;
+    const bool do_inflate = !b->next.valid && b->ahead.valid;
+    Chunk nx;
+    if (do_inflate && !alloc_chunk(b, b->ahead, GAP, nx)) return bail("out of memory");
+    const bool do_read = !b->file_eof && (do_inflate || !b->ahead.valid);
+    b->ahead2.valid = false;
+    bool read_ok = true;
+    int bad = 0;
+    const long n_blk = do_inflate ? (long)b->ahead.blocks.size() : 0;
+#pragma omp parallel num_threads(b->threads) reduction(| : bad)
+    {
+#pragma omp single nowait
+      { parse(); }
+#pragma omp single nowait
+      {
+        if (do_read) read_ok = read_comp(b, CHUNK_BYTES, b->ahead2, rerr);
+      }
+#pragma omp for schedule(dynamic, 4) nowait
+      for (long i = 0; i < n_blk; ++i)
+        if (!inflate_one(b->ahead, (size_t)i, nx)) bad |= 1;
+    }
+    if (do_inflate) {
+      if (bad) {
+        b->put_buf(nx.data, nx.cap);
+        return bail("BGZF inflate failed");
+      }
+      nx.valid = true;
+      b->next = nx;
+      b->ahead.valid = false;
+    }
+    if (!read_ok) return bail(rerr);
+    if (!perr.empty()) return bail(perr);
+    if (do_read && b->ahead2.valid) {   // ahead is free by now (see do_read)
+      std::swap(b->ahead, b->ahead2);
+      b->ahead2.valid = false;
+    }
+    if (done) break;   // batch full: the rest of this chunk and the look-ahead wait in the reader
+    // this chunk is exhausted but for an incomplete record at its end
+    const size_t tail = buf_size - off;
+    if (!b->next.valid) {
+      if (b->file_eof && !b->ahead.valid) {
+        if (tail) return bail("truncated BAM file (incomplete record at the end)");
+        break;
+      }
+      continue;   // the look-ahead is still to be inflated: go round again
+    }
+    Chunk& nxt = b->next;
+    if (tail <= nxt.begin) {
+      if (tail) memcpy(nxt.data + nxt.begin - tail, buf + off, tail);
+      nxt.begin -= tail;
+    } else {   // a record longer than the headroom: rebuild the next chunk behind the tail
+      size_t cap = 0, n_next = nxt.size - nxt.begin;
+      uint8_t* p = b->get_buf(tail + n_next + 1, &cap);
+      if (!p) return bail("out of memory");
+      memcpy(p, buf + off, tail);
+      memcpy(p + tail, nxt.data + nxt.begin, n_next);
+      b->put_buf(nxt.data, nxt.cap);
+      nxt.data = p;
+      nxt.begin = 0;
+      nxt.size = tail + n_next;
+      nxt.cap = cap;
+    }
+    retired.push_back(b->cur);   // kept records point into it: released after packing
+    b->cur = nxt;
+    b->next = Chunk();
+    buf = b->cur.data;
+    buf_size = b->cur.size;
+    off = b->cur.begin;
   }
+  b->cur.begin = off;
+  b->eof = b->file_eof && !b->ahead.valid && !b->next.valid;
   // NOTE: when a batch limit stops us mid-buffer the collapse state already
   // reflects only the records consumed so far (the break precedes any update
   // for the postponed record? no — state was updated; undo by re-evaluating):
@@ -698,9 +820,7 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
       if (sl) memcpy(&im->sa_blob[im->sa_off[i]], sa_ptr[i], sl);
     }
   }
-  // keep undecoded tail for the next call
-  b->carry.assign(buf + off, buf + buf_size);
-  release_chunks();
+  release_retired();   // packed: nothing points into the retired chunks any more
   memset(out, 0, sizeof(*out));
   out->impl = im;
   out->n_reads = n;
@@ -732,7 +852,7 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
       out->raw_blob = im->raw_blob.data();
     }
   }
-  out->at_eof = (b->eof && b->carry.empty()) ? 1 : 0;
+  out->at_eof = (b->eof && b->cur.begin == b->cur.size) ? 1 : 0;
   if (n_bases <= 0xffffffffull) {
     out->invalid_pos = im->invalid.data();
     out->n_invalid = im->invalid.size();

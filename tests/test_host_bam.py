@@ -121,3 +121,41 @@ def test_not_a_bam(tmp_path):
         c = tmp_path / "x.cram"
         c.write_bytes(b"CRAM")
         bamio.BamReader(str(c))
+
+
+@pytest.mark.parametrize("chunk_kb,gap", [(64, 1 << 20), (64, 16), (200, 0)])
+def test_decoder_pipeline_chunking_is_invisible(giab_paths, monkeypatch, chunk_kb, gap):
+    """The decoder's read / inflate / parse pipeline works chunk by chunk; records that
+    straddle chunks are completed in the next chunk's headroom, or — when the unparsed
+    tail is larger than the headroom — by rebuilding that chunk.  Small chunks and tiny
+    headrooms exercise every transition on the fixture: same batches as the defaults."""
+    def decode(mode, max_bases):
+        out = []
+        with bamio.BamReader(giab_paths["child"], threads=3) as rd:
+            for b in rd.batches(mode, max_bases=max_bases, want_meta=True):
+                out.append((b.n_reads, b.n_bases, b.codes.copy(), b.valid.copy(), b.invalid.copy(),
+                            b.rec_index.copy(), b.pos.copy(), b.cigar_blob.copy(), bytes(b.qname_blob)))
+                b.close()
+        return out
+    want = {(m, mb): decode(m, mb) for m in (bamio.MODE_FASTA, bamio.MODE_SCAN) for mb in (0, 300_000)}
+    monkeypatch.setenv("KDF_BAM_CHUNK_KB", str(chunk_kb))
+    monkeypatch.setenv("KDF_BAM_GAP", str(gap))
+    for key, w in want.items():
+        got = decode(*key)
+        assert len(got) == len(w)
+        for a, b in zip(got, w):
+            assert a[0] == b[0] and a[1] == b[1] and a[8] == b[8]
+            for x, y in zip(a[2:8], b[2:8]):
+                assert np.array_equal(x, y)
+
+
+def test_truncated_bam_is_an_error(giab_paths, tmp_path):
+    """A file cut in the middle of a record (or of a BGZF block) is reported, not read
+    as a shorter file and not looped on."""
+    data = open(giab_paths["father"], "rb").read()
+    p = str(tmp_path / "cut.bam")
+    open(p, "wb").write(data[:len(data) // 2])
+    with pytest.raises(Exception):
+        with bamio.BamReader(p, threads=2) as rd:
+            for b in rd.batches(bamio.MODE_FASTA):
+                b.close()
