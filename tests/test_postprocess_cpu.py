@@ -3,6 +3,8 @@ classify, writers) fed with the oracle's read hits, against the goldens."""
 import json
 import os
 
+import numpy as np
+
 from kmer_denovo_filter_b200.discovery import pipeline as P
 from kmer_denovo_filter_b200.discovery import summary as S
 from oracle import discovery, kmers
@@ -114,6 +116,46 @@ def test_hit_coverage_host_matches_reference_helper():
         assert {c: dict(v) for c, v in rc.items() if v} == dict(got_r)
     z = engine.debug_hit_coverage_host([], [], 31, [0], [0], [0, 0], [])
     assert all(a.shape[0] == 0 for a in z)
+
+
+def test_accumulate_coverage_glue_on_fixture_reads(giab_paths):
+    """The pipeline's K7 glue (CIGAR gather, hit lists, Counter merges) on real records of
+    the fixture, with the device call replaced by the host instantiation of the same code:
+    equal to the reference-named helper applied read by read."""
+    import collections
+    from kmer_denovo_filter_b200 import bamio, engine
+
+    class HostK7:
+        def hit_coverage(self, *a):
+            return engine.debug_hit_coverage_host(*a)
+
+    k = 31
+    with bamio.BamReader(giab_paths["child"], threads=2) as rd:
+        batch = rd.next_batch(bamio.MODE_SCAN, want_meta=True)
+    reads, slices, off = [], [], []
+    for r in range(0, batch.n_reads, 23):
+        rec = batch.record(r)
+        if rec.is_unmapped or not rec.cigartuples or int(batch.read_lens[r]) < k + 40:
+            continue
+        offs = [3, 4, 20, int(batch.read_lens[r]) - k]
+        reads.append(r)
+        slices.append((len(off), len(off) + len(offs)))
+        off += offs
+    assert len(reads) > 100
+    kc = collections.defaultdict(collections.Counter)
+    rc = collections.defaultdict(collections.Counter)
+    P._accumulate_coverage(HostK7(), batch, reads, slices, np.asarray(off, dtype=np.int64), k, kc, rc)
+    want_k = collections.defaultdict(collections.Counter)
+    want_r = collections.defaultdict(collections.Counter)
+    for r, (a, b) in zip(reads, slices):
+        rec = batch.record(r)
+        cov = P._collect_kmer_ref_positions(rec, off[a:b], k)
+        want_k[rec.reference_name] += cov
+        for p in cov:
+            want_r[rec.reference_name][p] += 1
+    assert {c: dict(v) for c, v in kc.items()} == {c: dict(v) for c, v in want_k.items() if v}
+    assert {c: dict(v) for c, v in rc.items()} == {c: dict(v) for c, v in want_r.items() if v}
+    batch.close()
 
 
 def test_sv_linking_and_classes():
