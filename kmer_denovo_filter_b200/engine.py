@@ -1037,7 +1037,9 @@ class CudaEngine:
             p0.data_ptr() if p0 is not None else None, p1.data_ptr() if p1 is not None else None,
             out_cap, n_out.data_ptr(), count_min0, ctr.data_ptr(), self.stream_ptr()))
         self._t1("count_bins/kw%d" % kw, ev)
-        self.launches += 2 + child_bins.n_parts * int(sub_split) * (
+        packed = bool(self.lib.kdf_count_bins_packed(k, min0, max0, min1, max1, count_min0,
+                                                     1 if want_planes else 0))
+        self.launches += (1 if packed else 2) + child_bins.n_parts * int(sub_split) * (
             1 + n_src * (1 + (1 if ref_bins is not None else 0)))
         c = ctr.cpu().numpy().view(np.uint64)
         n = int(n_out.item())
