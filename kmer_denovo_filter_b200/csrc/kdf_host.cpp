@@ -523,6 +523,10 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
       }
       if (buf_size - off - 4 < (size_t)bs) break;
       const uint8_t* r = buf + off + 4;
+      // the walk is a chain of one cache miss per record header: pull the headers of the
+      // records a few hundred bytes ahead (the chunk buffer has slack past its end)
+      __builtin_prefetch(r + bs + 1024);
+      __builtin_prefetch(r + bs + 1088);
       uint16_t flag = rd_u16(r + 14);
       uint8_t l_name = r[8];
       uint32_t l_seq = (uint32_t)rd_i32(r + 16);
