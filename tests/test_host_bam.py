@@ -159,3 +159,38 @@ def test_truncated_bam_is_an_error(giab_paths, tmp_path):
         with bamio.BamReader(p, threads=2) as rd:
             for b in rd.batches(bamio.MODE_FASTA):
                 b.close()
+
+
+def test_count_bam_into_table_routes_probes_through_the_chain_helper(giab_paths):
+    """The pipeline's parent count (`samtools fasta | jellyfish count --if`,
+    core/jellyfish_wrappers.py:159-176) decodes batch by batch and applies every batch
+    with kmer_chain.count_if_present (direct / filtered / binned route); other modes
+    go straight to the stream kernel.  Host logic only: the engine is a recorder."""
+    from kmer_denovo_filter_b200.core import kmer_engine_wrappers as kw
+
+    class Table:
+        capacity, key_words, k, filter_buf = 1024, 1, 31, None
+
+    class Recorder:
+        def __init__(self):
+            self.calls = []
+
+        def upload(self, batch, with_reads=True):
+            return batch
+
+        def new_stats(self):
+            return {}
+
+        def count_stream(self, table, ds, mode, plane, arg, stats):
+            self.calls.append((mode, plane, arg, ds.n_bases))
+            stats["windows"] = ds.n_bases
+
+        def read_stats(self, st):
+            return {"windows": st["windows"], "full": 0, "hits": 0, "new": 0}
+
+    for mode in (engine.MODE_COUNT_IF_PRESENT, engine.MODE_INSERT_COUNT):
+        eng = Recorder()
+        _t, tot = kw.count_bam_into_table(eng, giab_paths["mother"], Table(), mode, 1, 2,
+                                          batch_bases=500_000)
+        assert len(eng.calls) > 3 and all(c[:3] == (mode, 1, 1) for c in eng.calls)
+        assert tot["windows"] == sum(c[3] for c in eng.calls) == tot["bases"]
