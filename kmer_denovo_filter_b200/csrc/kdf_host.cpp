@@ -331,33 +331,65 @@ inline void or_word32(uint32_t* w, uint32_t v, bool shared) {
     *w |= v;
 }
 
-// pack l_seq bases (BAM nibbles) at stream position `start`
+// two nibble bytes (4 bases) -> 8 code bits (first base most significant) | 4 validity
+// bits << 8; indexed by the two bytes as a little-endian u16
+struct NibLut {
+  uint16_t v[65536];
+  NibLut() {
+    for (unsigned i = 0; i < 65536; ++i) {
+      unsigned b0 = i & 255, b1 = i >> 8;
+      unsigned n[4] = {b0 >> 4, b0 & 15, b1 >> 4, b1 & 15};
+      unsigned c = 0, ok = 0;
+      for (int j = 0; j < 4; ++j) {
+        c = (c << 2) | NIB_CODE[n[j]];
+        ok = (ok << 1) | NIB_OK[n[j]];
+      }
+      v[i] = (uint16_t)(c | (ok << 8));
+    }
+  }
+};
+const NibLut NIB4;
+
+// pack l_seq bases (BAM nibbles) at stream position `start`: 32 bases at a time into an
+// aligned word (eight table look-ups of four bases each), shifted into place; the first
+// and the last stream word of a read are shared with its neighbours (atomic OR)
 void pack_record(const uint8_t* nib, uint32_t l_seq, uint64_t start, uint64_t* codes,
                  uint32_t* valid) {
   if (!l_seq) return;
-  uint64_t first_w = start >> 5, last_w = (start + l_seq - 1) >> 5;
-  uint64_t cw = 0;
-  uint32_t vw = 0;
+  const uint64_t first_w = start >> 5, last_w = (start + l_seq - 1) >> 5;
+  const unsigned s = (unsigned)(start & 31);
+  uint64_t carry_c = 0;
+  uint32_t carry_v = 0;
   uint64_t w = first_w;
-  for (uint32_t i = 0; i < l_seq; ++i) {
-    uint8_t byte = nib[i >> 1];
-    uint8_t n = (i & 1) ? (byte & 15) : (byte >> 4);
-    uint64_t p = start + i;
-    uint64_t pw = p >> 5;
-    if (pw != w) {
-      bool shared = (w == first_w) || (w == last_w);
-      or_word64(codes + w, cw, shared);
-      or_word32(valid + w, vw, shared);
-      cw = 0;
-      vw = 0;
-      w = pw;
+  for (uint32_t done = 0; done < l_seq; done += 32, ++w) {
+    const uint32_t nb = l_seq - done < 32 ? l_seq - done : 32;
+    const uint8_t* src = nib + (done >> 1);
+    uint64_t lw = 0;
+    uint32_t lv = 0;
+    const unsigned groups = (nb + 3) >> 2;
+    for (unsigned g = 0; g < groups; ++g) {
+      uint16_t two;
+      memcpy(&two, src + 2 * g, 2);   // past an odd end this reads into the qualities: masked below
+      const uint16_t e = NIB4.v[two];
+      lw |= (uint64_t)(e & 255) << (56 - 8 * g);
+      lv |= (uint32_t)(e >> 8) << (28 - 4 * g);
     }
-    unsigned sh = (unsigned)(p & 31);
-    cw |= (uint64_t)NIB_CODE[n] << (62 - 2 * sh);
-    vw |= (uint32_t)NIB_OK[n] << (31 - sh);
+    if (nb < 32) {
+      lw &= ~0ull << (64 - 2 * nb);
+      lv &= ~0u << (32 - nb);
+    }
+    uint64_t oc = carry_c | (lw >> (2 * s));
+    uint32_t ov = carry_v | (lv >> s);
+    carry_c = s ? lw << (64 - 2 * s) : 0;
+    carry_v = s ? lv << (32 - s) : 0;
+    const bool shared = (w == first_w) || (w == last_w);
+    or_word64(codes + w, oc, shared);
+    or_word32(valid + w, ov, shared);
   }
-  or_word64(codes + w, cw, true);
-  or_word32(valid + w, vw, true);
+  if (w <= last_w) {   // the shifted remainder spills into one more word
+    or_word64(codes + w, carry_c, true);
+    or_word32(valid + w, carry_v, true);
+  }
 }
 
 }  // namespace
