@@ -57,6 +57,13 @@ struct CompBuf {
   bool valid = false;
 };
 
+// a record taken into the batch being built
+struct Kept {
+  const uint8_t* rec;  // the record body (inside one of the chunk buffers)
+  uint64_t start;      // stream position of its first base
+  uint32_t l_seq;
+};
+
 // an inflated chunk: logical bytes data[begin .. size), `begin` leaves headroom for the
 // unparsed tail of the chunk before it
 struct Chunk {
@@ -88,6 +95,7 @@ struct Bam {
   // chunk after it, and the compressed bytes of the one after that
   Chunk cur, next;
   CompBuf ahead, ahead2;
+  std::vector<Kept> kept;   // records of the batch being built
   uint8_t* get_buf(size_t n, size_t* cap) {
     size_t best = pool.size();
     for (size_t i = 0; i < pool.size(); ++i)
@@ -500,12 +508,10 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
     return KDF_ERR_ARG;
   }
   kdf_bam_batch_impl* im = new kdf_bam_batch_impl;
-  struct Kept {
-    const uint8_t* rec;  // the record body (inside one of the chunk buffers)
-    uint64_t start;
-    uint32_t l_seq;
-  };
-  std::vector<Kept> kept;
+  // (the vector lives in the reader: its pages stay mapped from batch to batch, a fresh
+  // one cost a page fault per 128 records in the middle of the serial walk)
+  std::vector<Kept>& kept = b->kept;
+  kept.clear();
   uint64_t n_bases = 0;
   // The decode is a three-stage pipeline over chunks of ~64 MB of records: while one
   // thread walks the records of chunk C (a serial chain: every header is a cache miss),
@@ -539,6 +545,7 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
     b->cur.valid = true;
     b->carry.clear();
   }
+  im->rec_index.reserve(kept.capacity());
   const uint8_t* buf = b->cur.data;
   size_t buf_size = b->cur.size;
   size_t off = b->cur.begin;
