@@ -106,14 +106,17 @@ struct Bam {
       pool.erase(pool.begin() + (long)best);
       return p;
     }
-    // 2 MB-aligned and advised for transparent huge pages: a fresh 64 MB buffer is first
-    // touched by all inflate threads at once, and with 4 KB pages those faults serialise
-    // in the kernel (measured: 1.1 s instead of 0.16 s for 276 MB on 8 threads)
+    // 2 MB-aligned.  Fresh pages are touched by all inflate threads at once, which is slow
+    // (page faults serialise), but the pool makes that a one-off per reader.  Advising
+    // transparent huge pages (KDF_BAM_THP=1) removes most of those faults and measured ~5 %
+    // faster in steady state, at the price of an occasional compaction stall of a second
+    // on the first allocation: off by default.
     const size_t huge = 2u << 20;
     *cap = ((n < huge ? huge : n) + huge - 1) & ~(huge - 1);
     void* p = aligned_alloc(huge, *cap);
 #ifdef MADV_HUGEPAGE
-    if (p) madvise(p, *cap, MADV_HUGEPAGE);
+    static const bool thp = getenv("KDF_BAM_THP") != nullptr;
+    if (p && thp) madvise(p, *cap, MADV_HUGEPAGE);
 #endif
     return (uint8_t*)p;
   }
