@@ -280,6 +280,30 @@ int kdf_bin_keys(const uint64_t* lo /*DEV*/, const uint64_t* hi /*DEV or NULL*/,
                  int k, int by_owner, int n_parts, uint64_t* bins /*DEV*/, uint64_t bin_cap,
                  uint64_t* cursors /*DEV*/, uint64_t* overflow /*DEV*/, void* stream);
 
+/* Multi-pass binning — what the reference gets from Jellyfish's sized hash +
+ * spill-and-merge (core/jellyfish_wrappers.py:73-107, 335-366;
+ * discovery/pipeline.py:114-122, 186-189): the bins of a whole-genome sample
+ * (8 bytes x every k-mer instance) do not fit HBM, so the hash ranges are split into
+ * 2^pass_log2 groups by their TOP bits and the stream is re-extracted once per
+ * group: this call bins only the keys of group pass_val (0 <= pass_val <
+ * 2^pass_log2), into n_parts bins that are the group's own sub-ranges (by_owner 0 or
+ * R >= 2; with by_owner == 1 the pass only filters).  kdf_count_bins_pass with the
+ * same (pass_log2, pass_val) counts them: over all passes every key is counted
+ * exactly once, in slices that cover 1 / (2^pass_log2 * n_parts) of the hash space.
+ * Exactly one of bins / bin_ptrs is non-NULL (local regions, or one — possibly
+ * peer-mapped — pointer per bin as in kdf_bin_stream_to).  pass_log2 == 0 is
+ * kdf_bin_stream_range / kdf_bin_stream_to_range.                              */
+int kdf_bin_stream_pass(const kdf_stream* s, uint64_t first_word, uint64_t n_words, int k,
+                        int by_owner, int n_parts, uint64_t* bins /*DEV or NULL*/,
+                        uint64_t* const* bin_ptrs /*DEV or NULL*/, uint64_t bin_cap,
+                        uint64_t* cursors /*DEV*/, uint64_t* overflow /*DEV*/,
+                        uint64_t* stats /*DEV or NULL*/, int pass_log2, uint32_t pass_val,
+                        void* stream);
+int kdf_bin_keys_pass(const uint64_t* lo /*DEV*/, const uint64_t* hi /*DEV or NULL*/, uint64_t n,
+                      int k, int by_owner, int n_parts, int pass_log2, uint32_t pass_val,
+                      uint64_t* bins /*DEV*/, uint64_t bin_cap, uint64_t* cursors /*DEV*/,
+                      uint64_t* overflow /*DEV*/, void* stream);
+
 /* K2 on hash-range bins: apply `mode` (kdf_update_keys semantics) to the keys of
  * every bin, bin after bin.  bins / cursors as written by kdf_bin_stream with
  * by_owner == 0 (for 128-bit keys the {lo, hi} pairs of a bin are interleaved).
@@ -329,33 +353,6 @@ int kdf_count_bins(int k, int n_parts, const uint64_t* child_bins /*DEV*/,
                    uint64_t* n_out /*DEV*/, uint32_t count_min0, uint64_t* counters /*DEV*/,
                    void* stream);
 
-/* Shared-memory form of the packed count (64-bit keys, thresholds as for
- * kdf_count_bins_packed).  Returning atomics on L2 are the ceiling of the L2-sliced
- * form, so every hash-range bin is split once more into s2 sub-ranges (a second
- * streaming pass through `scratch`, `group` bins at a time) until one sub-bin's
- * distinct keys fit a table of n_slots packed slots in shared memory; one CTA then
- * counts a sub-bin start to finish: insert + saturating count, reference marks,
- * emit.  Replaces the same reference calls as kdf_count_bins
- * (discovery/pipeline.py:114-122, :207-211, :286-304).
- *   scratch : DEV, 16-byte aligned, kdf_count_bins_smem_scratch() bytes
- *   sub_cap / ref_sub_cap : key slots of one child / reference sub-bin
- *   counters: DEV u64[6] as in kdf_count_bins ([1] unused), caller zeroes
- *   flags   : DEV u64, caller zeroes; bit 0 = some sub-bin's keys did not fit its
- *             shared-memory table, bit 1 = some sub-bin region overflowed: in both
- *             cases the outputs are invalid and the caller re-counts the same bins
- *             with kdf_count_bins (nothing is dropped silently).                */
-size_t kdf_count_bins_smem_scratch(int n_parts, int group, int s2, uint64_t sub_cap,
-                                   uint64_t ref_sub_cap);
-int kdf_count_bins_smem(int k, int n_parts, int n_src, const uint64_t* child_bins /*DEV*/,
-                        uint64_t child_bin_cap, const uint64_t* child_cursors /*DEV*/,
-                        const uint64_t* ref_bins /*DEV or NULL*/, uint64_t ref_bin_cap,
-                        const uint64_t* ref_cursors /*DEV or NULL*/, void* scratch /*DEV*/,
-                        size_t scratch_bytes, int group, int s2, uint64_t sub_cap,
-                        uint64_t ref_sub_cap, uint32_t n_slots, uint32_t min0, uint32_t max1,
-                        uint32_t count_min0, uint64_t* out_lo /*DEV*/, uint64_t out_cap,
-                        uint64_t* n_out /*DEV*/, uint64_t* counters /*DEV*/,
-                        uint64_t* flags /*DEV*/, void* stream);
-
 /* The same with the bins of n_src sources (multi-GPU: one region per sending
  * rank, filled by kdf_bin_stream_to): bins are laid out [source][hash range]
  * [bin_cap] and cursors [source][hash range].  sub_split (a power of two) counts
@@ -371,6 +368,20 @@ int kdf_count_bins_multi(int k, int n_parts, int n_src, int sub_split,
                          uint32_t* out_p0 /*DEV*/, uint32_t* out_p1 /*DEV*/, uint64_t out_cap,
                          uint64_t* n_out /*DEV*/, uint32_t count_min0, uint64_t* counters /*DEV*/,
                          void* stream);
+/* ... and for the bins of one pass of a multi-pass count (kdf_bin_stream_pass):
+ * slice p of this call covers hash range (pass_val * n_parts + p) * sub_split .. of
+ * 2^pass_log2 * n_parts * sub_split.  Outputs (n_out, counters) accumulate over the
+ * passes when the caller does not zero them in between.                        */
+int kdf_count_bins_pass(int k, int n_parts, int n_src, int sub_split, int pass_log2,
+                        uint32_t pass_val, const uint64_t* child_bins /*DEV*/,
+                        uint64_t child_bin_cap, const uint64_t* child_cursors /*DEV*/,
+                        const uint64_t* ref_bins /*DEV or NULL*/, uint64_t ref_bin_cap,
+                        const uint64_t* ref_cursors /*DEV or NULL*/, void* slice /*DEV*/,
+                        uint64_t slice_capacity, uint32_t min0, uint32_t max0, uint32_t min1,
+                        uint32_t max1, uint64_t* out_lo /*DEV*/, uint64_t* out_hi /*DEV*/,
+                        uint32_t* out_p0 /*DEV*/, uint32_t* out_p1 /*DEV*/, uint64_t out_cap,
+                        uint64_t* n_out /*DEV*/, uint32_t count_min0, uint64_t* counters /*DEV*/,
+                        void* stream);
 
 /* ---- K7: coverage of the reference by hit k-mers -------------------------
  * Replaces _collect_kmer_ref_positions (core/bam_scanner.py:97-117) and the

@@ -262,6 +262,108 @@ template <> struct WindowIter<2> {
   }
 };
 
+// Chunked iterator over the 32 window starts of stream word `w` (the form the
+// stream kernels use).  WindowIter above rolls every register by one base per
+// window (~14 integer instructions of shifting per step); here the 64 (96) bases
+// a thread needs are laid out ONCE so that the window at offset u of the current
+// chunk is a fixed-distance funnel shift:
+//   forward:  (c0:c1[:c2]) = (b0:b1[:b2]) >> (64*KW - 2k); window u = the 64*KW-bit
+//             field at bit offset 2u, low 2k bits
+//   reverse:  (r0:r1[:r2]) = reverse complement of all the bases; window u =
+//             ((r..) >> 2u), low 2k bits
+// With u a compile-time constant (unrolled chunk loop) that is two SHF per 64 bits
+// and a mask; next<C>() moves the registers on by C bases once per chunk.
+template <int KW> struct WindowChunks;
+
+template <> struct WindowChunks<1> {
+  u64 c0, c1, r0, r1, kmask;
+  u32 okm;  // window validity of the remaining starts (MSB = offset 0 of the chunk)
+  KDF_HD WindowChunks(const StreamView& s, u64 w, int k) {
+    const u64 b0 = ld_code(s, w), b1 = ld_code(s, w + 1);
+    const u64 vv = ((u64)ld_valid(s, w) << 32) | (u64)ld_valid(s, w + 1);
+    okm = (u32)(runs_of_k(vv, k) >> 32);
+    const int t = 64 - 2 * k;  // 0..62
+    kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1);
+    if (t == 0) {
+      c0 = b0;
+      c1 = b1;
+    } else {
+      c0 = b0 >> t;
+      c1 = (b0 << (64 - t)) | (b1 >> t);
+    }
+    r0 = revcomp_word(b1);
+    r1 = revcomp_word(b0);
+  }
+  KDF_HD bool any_valid() const { return okm != 0; }
+  KDF_HD bool ok(int u) const { return ((okm >> (31 - u)) & 1u) != 0; }
+  KDF_HD Key<1> key(int u) const {  // canonical k-mer of the window at chunk offset u (0..31)
+    Key<1> f, r;
+    f.lo = (u == 0 ? c0 : ((c0 << (2 * u)) | (c1 >> (64 - 2 * u)))) & kmask;
+    r.lo = (u == 0 ? r1 : ((r1 >> (2 * u)) | (r0 << (64 - 2 * u)))) & kmask;
+    return kmin(f, r);
+  }
+  template <int C> KDF_HD void next() {  // C in 1..31
+    c0 = (c0 << (2 * C)) | (c1 >> (64 - 2 * C));
+    c1 <<= 2 * C;
+    r1 = (r1 >> (2 * C)) | (r0 << (64 - 2 * C));
+    r0 >>= 2 * C;
+    okm <<= C;
+  }
+};
+
+template <> struct WindowChunks<2> {
+  u64 c0, c1, c2, r0, r1, r2, kmask;  // kmask: key bits of the most significant word
+  u32 okm;
+  KDF_HD WindowChunks(const StreamView& s, u64 w, int k) {
+    const u64 b0 = ld_code(s, w), b1 = ld_code(s, w + 1), b2 = ld_code(s, w + 2);
+    const u64 v0 = ((u64)ld_valid(s, w) << 32) | (u64)ld_valid(s, w + 1);
+    const u64 v1 = ((u64)ld_valid(s, w + 1) << 32) | (u64)ld_valid(s, w + 2);
+    u64 r = runs_of_k(v0, k < 32 ? k : 32);
+    if (k > 32) r &= runs_of_k(v1, k - 32);
+    okm = (u32)(r >> 32);
+    const int t = 128 - 2 * k;  // 0..62
+    kmask = k == 64 ? ~0ull : ((1ull << (2 * k - 64)) - 1);
+    if (t == 0) {
+      c0 = b0;
+      c1 = b1;
+      c2 = b2;
+    } else {
+      c0 = b0 >> t;
+      c1 = (b0 << (64 - t)) | (b1 >> t);
+      c2 = (b1 << (64 - t)) | (b2 >> t);
+    }
+    r0 = revcomp_word(b2);
+    r1 = revcomp_word(b1);
+    r2 = revcomp_word(b0);
+  }
+  KDF_HD bool any_valid() const { return okm != 0; }
+  KDF_HD bool ok(int u) const { return ((okm >> (31 - u)) & 1u) != 0; }
+  KDF_HD Key<2> key(int u) const {
+    Key<2> f, r;
+    if (u == 0) {
+      f.hi = c0 & kmask;
+      f.lo = c1;
+      r.hi = r1 & kmask;
+      r.lo = r2;
+    } else {
+      f.hi = ((c0 << (2 * u)) | (c1 >> (64 - 2 * u))) & kmask;
+      f.lo = (c1 << (2 * u)) | (c2 >> (64 - 2 * u));
+      r.hi = ((r1 >> (2 * u)) | (r0 << (64 - 2 * u))) & kmask;
+      r.lo = (r2 >> (2 * u)) | (r1 << (64 - 2 * u));
+    }
+    return kmin(f, r);
+  }
+  template <int C> KDF_HD void next() {
+    c0 = (c0 << (2 * C)) | (c1 >> (64 - 2 * C));
+    c1 = (c1 << (2 * C)) | (c2 >> (64 - 2 * C));
+    c2 <<= 2 * C;
+    r2 = (r2 >> (2 * C)) | (r1 << (64 - 2 * C));
+    r1 = (r1 >> (2 * C)) | (r0 << (64 - 2 * C));
+    r0 >>= 2 * C;
+    okm <<= C;
+  }
+};
+
 // Random-access extraction of the window starting at stream position p
 // (used by the per-read scan, where lanes stride through one read).
 template <int KW> struct WindowAt;

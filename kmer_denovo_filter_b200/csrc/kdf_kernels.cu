@@ -16,7 +16,6 @@
 //                           the key's spare bits, keys-only L2 slice; queued
 //                           compare-and-swaps), and the probing ops of
 //                           kdf_update_bins; k_emit_packed = emit + clear
-//   K2s k_rebin/k_count_sub shared-memory variant of the packed count (off by default)
 //   K3  k_threshold_compact threshold + stream compaction (dump -L, == 0, <= pmc)
 //   K4  k_lookup_keys       batched membership / count lookup
 //   K5  k_scan_reads        dense per-read scan + distinct reduction
@@ -38,6 +37,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+
+#include <math.h>
 
 #include <string>
 #include <type_traits>
@@ -517,7 +518,7 @@ __global__ void __launch_bounds__(SMEM ? 512 : 256, SMEM ? KDF_SMEM_BLOCKS : (KW
   u64 w0 = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   for (u64 itn = 0; itn < n_iter; ++itn) {
     u64 w = w0 + itn * stride;
-    WindowIter<KW> it(s, w, k);
+    WindowChunks<KW> it(s, w, k);
     if (!__any_sync(0xffffffffu, it.any_valid())) continue;
 #pragma unroll 1
     for (int c = 0; c < 32 / CHUNK; ++c) {
@@ -527,11 +528,10 @@ __global__ void __launch_bounds__(SMEM ? 512 : 256, SMEM ? KDF_SMEM_BLOCKS : (KW
       u32 okm = 0, probe = 0, cand = 0;
 #pragma unroll
       for (int u = 0; u < CHUNK; ++u) {
-        bool ok = it.ok();
-        keys[u] = it.canonical();
-        it.advance();
+        bool ok = it.ok(u);
+        keys[u] = it.key(u);
         const u64 h = hash_key(keys[u]);
-        bidx[u] = bucket_of(h, t.log2_parts, t.n_buckets);
+        if (!FILT) bidx[u] = bucket_of(h, t.log2_parts, t.n_buckets);   // FILT: only candidates need it
         if (ok) {
           okm |= 1u << u;
           if (FILT) {
@@ -553,13 +553,15 @@ __global__ void __launch_bounds__(SMEM ? 512 : 256, SMEM ? KDF_SMEM_BLOCKS : (KW
           }
         }
       }
+      it.template next<CHUNK>();
       st.windows += __popc(okm);
       u64 pos0 = (w << 5) + c * CHUNK;
       if (FILT) {
 #pragma unroll
         for (int u = 0; u < CHUNK; ++u)
           if (cand & (1u << u))
-            tally(st, sq_push_or_resolve<KW, OP>(q, t, bidx[u], keys[u], plane, arg, pos0 + u, sink));
+            tally(st, sq_push_or_resolve<KW, OP>(q, t, bucket_of(hash_key(keys[u]), t.log2_parts, t.n_buckets),
+                                                 keys[u], plane, arg, pos0 + u, sink));
       }
 #pragma unroll
       for (int u = 0; u < CHUNK; ++u) {
@@ -908,10 +910,125 @@ __device__ __noinline__ u32 pq_drain(PackedQueues<KW>* qp, TableView<KW> t, int 
   return packed;
 }
 
-template <int KW, int OP>
-using PackedKeysQueue = typename std::conditional<OP == OP_PACKED_COUNT, PackedQueues<KW>, SlowQueue<KW>>::type;
+// Split-phase form of the same queue (KDF_PQ_SPLIT, default on): a RING, drained oldest
+// first.  A drain ISSUES the compare-and-swaps of a batch and returns; their results
+// stay in registers, untouched, while the warp goes on with the next chunks, and are
+// checked ("retired") at the start of the next drain — ~3 chunks later, when the L2
+// round trip has long completed.  The entries of the batch in flight stay in the ring
+// (head is only moved when they retire), so a loser still finds its key and bucket.
+// Capacity: < 64 undrained + 64 in flight + <= 128 pushed by one chunk = 256.
+constexpr int PQ_RING = 256;
+template <int KW> struct PackedRing {
+  u64 lo[PQ_RING];
+  u64 hi[KW == 2 ? PQ_RING : 1];
+  u64 expect[PQ_RING];
+  u32 b[PQ_RING];
+  u32 info[PQ_RING];
+  u32 count;  // tail: items pushed so far (monotonic)
+  u32 head;   // first item not yet retired
+};
+template <int KW> struct PackedRings {
+  PackedRing<KW> fast;
+  SlowQueue<KW> slow;
+};
+template <int KW> struct PendingCas {
+  Key<KW> got[PQ_DRAIN / 32];
+  u32 n;  // items of the batch in flight (0: none)
+};
 
-template <int KW, int OP, bool FILT>
+template <int KW>
+__device__ __forceinline__ bool pr_push(PackedRing<KW>& q, const Key<KW>& key, u32 b, u32 info, u64 expect) {
+  // lanes race on this check, so leave a warp's worth of room
+  if (q.count - q.head >= (u32)(PQ_RING - 32)) return false;
+  const u32 o = atomicAdd(&q.count, 1u) & (u32)(PQ_RING - 1);
+  q.lo[o] = key.lo;
+  if (KW == 2) q.hi[o] = ((const u64*)&key)[KW - 1];
+  q.expect[o] = expect;
+  q.b[o] = b;
+  q.info[o] = info;
+  return true;
+}
+
+// all lanes: retire the batch in flight, then issue the next one (when `all`: until the
+// ring is empty, every batch retired).  Returns the tallies of the retired items.
+template <int KW>
+__device__ __forceinline__ u32 pr_drain(PackedRings<KW>* qp, PendingCas<KW>& pend, const TableView<KW>& t,
+                                        int sh, u32 sat, bool all) {
+  constexpr int S = SPB<KW>::v;
+  constexpr int R = PQ_DRAIN / 32;
+  PackedRing<KW>& q = qp->fast;
+  const unsigned lane = threadIdx.x & 31;
+  const u64 one = 1ull << sh;
+  const HitSink sink = {nullptr, nullptr, 0, nullptr};
+  __syncwarp();
+  const u32 tail = q.count;
+  u32 head = q.head;
+  u32 packed = 0;
+  for (;;) {
+    if (pend.n) {  // retire
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if ((u32)(r * 32) + lane < pend.n) {
+          const u32 idx = (head + r * 32 + lane) & (u32)(PQ_RING - 1);
+          const u32 info = q.info[idx];
+          if ((info & 3u) == 1) {
+            if (((const u64*)&pend.got[r])[KW - 1] != q.expect[idx] || (KW == 2 && pend.got[r].lo != q.lo[idx]))
+              packed_bump(t.keys + ((u64)q.b[idx] * S + (info >> 2)) * KW + (KW - 1),
+                          ((const u64*)&pend.got[r])[KW - 1], sh, sat);
+          } else if (is_empty_key(pend.got[r])) {
+            packed += 1u << 10;
+          } else {  // the slot was taken meanwhile: probe from scratch, with the other such cases
+            Key<KW> key;
+            key.lo = q.lo[idx];
+            if (KW == 2) ((u64*)&key)[KW - 1] = q.hi[idx];
+            u32 code = sq_push_or_resolve<KW, OP_PACKED_COUNT>(qp->slow, t, q.b[idx], key, sh, sat, 0, sink);
+            packed += (code == R_HIT ? 1u : 0u) + (code == R_NEW ? (1u << 10) : 0u);
+            packed |= (code == R_FULL ? (1u << 20) : 0u);
+          }
+        }
+      }
+      head += pend.n;
+      pend.n = 0;
+      __syncwarp();
+    }
+    const u32 avail = tail - head;
+    if (!(avail >= (u32)PQ_DRAIN || (all && avail > 0))) break;
+    const u32 take = avail >= (u32)PQ_DRAIN ? (u32)PQ_DRAIN : avail;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {  // issue: nothing below looks at a result
+      if ((u32)(r * 32) + lane < take) {
+        const u32 idx = (head + r * 32 + lane) & (u32)(PQ_RING - 1);
+        const u32 info = q.info[idx];
+        Key<KW> key, want;
+        key.lo = q.lo[idx];
+        if (KW == 2) ((u64*)&key)[KW - 1] = q.hi[idx];
+        Key<KW> val = key;
+        want.lo = EMPTY;
+        if (KW == 2) ((u64*)&want)[KW - 1] = EMPTY;
+        if ((info & 3u) == 1) {  // bump: expect the slot as read, write state + 1
+          ((u64*)&want)[KW - 1] = q.expect[idx];
+          if (KW == 2) want.lo = key.lo;
+          ((u64*)&val)[KW - 1] = q.expect[idx] + one;
+        } else {                 // insert: expect the empty slot, write the key in state 1
+          ((u64*)&val)[KW - 1] |= one;
+        }
+        pend.got[r] = cas_slot(t.keys + ((u64)q.b[idx] * S + (info >> 2)) * KW, want, val);
+      }
+    }
+    pend.n = take;
+    if (!all) break;
+  }
+  if (lane == 0) q.head = head;
+  __syncwarp();
+  return packed;
+}
+
+template <int KW, int OP, bool SPLIT = false>
+using PackedKeysQueue = typename std::conditional<
+    OP == OP_PACKED_COUNT, typename std::conditional<SPLIT, PackedRings<KW>, PackedQueues<KW>>::type,
+    SlowQueue<KW>>::type;
+
+template <int KW, int OP, bool FILT, bool SPLIT = false>
 __global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_packed_keys(TableView<KW> t, const u64* lo, u64 n_max,
                                                      const u64* n_dev, int sh, u32 sat, u64* stats,
                                                      int filt_log2, u32 filt_val) {
@@ -923,12 +1040,15 @@ __global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_packed_keys(TableView<
     u64 nd = *n_dev;
     n = nd < n_max ? nd : n_max;
   }
-  using Queue = PackedKeysQueue<KW, OP>;
+  using Queue = PackedKeysQueue<KW, OP, SPLIT>;
   extern __shared__ __align__(16) unsigned char pk_smem[];   // one queue per warp
   Queue& q = reinterpret_cast<Queue*>(pk_smem)[threadIdx.x >> 5];
+  PendingCas<KW> pend;
+  pend.n = 0;
   if ((threadIdx.x & 31) == 0) {
     if constexpr (OP == OP_PACKED_COUNT) {
       q.fast.count = 0;
+      if constexpr (SPLIT) q.fast.head = 0;
       q.slow.count = 0;
     } else {
       q.count = 0;
@@ -988,8 +1108,12 @@ __global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_packed_keys(TableView<
           if (j >= 0) {
             st.hits++;
 #ifndef KDF_DBG_NO_BUMP
-            if ((u32)(ms >> sh) < sat && !pq_push<KW>(q.fast, keys[u], bidx[u], 1u | ((u32)j << 2), ms))
-              packed_bump(t.keys + ((u64)bidx[u] * S + j) * KW + (KW - 1), ms, sh, sat);
+            if ((u32)(ms >> sh) < sat) {
+              bool queued;
+              if constexpr (SPLIT) queued = pr_push<KW>(q.fast, keys[u], bidx[u], 1u | ((u32)j << 2), ms);
+              else queued = pq_push<KW>(q.fast, keys[u], bidx[u], 1u | ((u32)j << 2), ms);
+              if (!queued) packed_bump(t.keys + ((u64)bidx[u] * S + j) * KW + (KW - 1), ms, sh, sat);
+            }
 #endif
           } else {
 #ifndef KDF_DBG_NO_INSERT
@@ -1000,15 +1124,23 @@ __global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_packed_keys(TableView<
             if (c < 0) {  // home bucket full: probe on from the next one
               u32 nb = (bidx[u] + 1 == t.n_buckets) ? 0 : bidx[u] + 1;
               tally(st, sq_push_or_resolve<KW, OP>(q.slow, t, nb, keys[u], sh, sat, 0, sink));
-            } else if (!pq_push<KW>(q.fast, keys[u], bidx[u], 2u | ((u32)c << 2), 0ull)) {
-              tally(st, resolve_packed_count<KW>(t, bidx[u], keys[u], sh, sat));
+            } else {
+              bool queued;
+              if constexpr (SPLIT) queued = pr_push<KW>(q.fast, keys[u], bidx[u], 2u | ((u32)c << 2), 0ull);
+              else queued = pq_push<KW>(q.fast, keys[u], bidx[u], 2u | ((u32)c << 2), 0ull);
+              if (!queued) tally(st, resolve_packed_count<KW>(t, bidx[u], keys[u], sh, sat));
             }
 #endif
           }
         }
       }
       __syncwarp();
-      if (q.fast.count >= (u32)PQ_DRAIN) tally_packed(st, pq_drain<KW>(&q, t, sh, sat, false));
+      if constexpr (SPLIT) {
+        // 64 items beyond the batch in flight: retire that batch, issue the next
+        if (q.fast.count - q.fast.head >= pend.n + (u32)PQ_DRAIN) tally_packed(st, pr_drain<KW>(&q, pend, t, sh, sat, false));
+      } else {
+        if (q.fast.count >= (u32)PQ_DRAIN) tally_packed(st, pq_drain<KW>(&q, t, sh, sat, false));
+      }
       if (q.slow.count >= 32) tally_packed(st, sq_drain<KW, OP>(&q.slow, t, sh, sat, sink, false));
     } else {
       // probing ops: OP_PACKED_MARK on a packed slice, or COUNT_IF_PRESENT /
@@ -1062,7 +1194,8 @@ __global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_packed_keys(TableView<
     mB = mC;
   }
   if constexpr (OP == OP_PACKED_COUNT) {
-    tally_packed(st, pq_drain<KW>(&q, t, sh, sat, true));
+    if constexpr (SPLIT) tally_packed(st, pr_drain<KW>(&q, pend, t, sh, sat, true));
+    else tally_packed(st, pq_drain<KW>(&q, t, sh, sat, true));
     tally_packed(st, sq_drain<KW, OP>(&q.slow, t, sh, sat, sink, true));
   } else {
     tally_packed(st, sq_drain<KW, OP>(&q, t, sh, sat, sink, true));
@@ -1474,47 +1607,56 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan_reads(
   }
 }
 
-// Sparse form: hits (stream position, slot) sorted by position -> one record
-// per read that has hits.  A hit is the first of its read iff the previous
-// hit lies before the read's start; each thread owning a first hit walks its
-// read's run (<= read length entries) and counts distinct slots.
-__global__ void __launch_bounds__(128) k_reduce_hits(const u64* pos, const u32* slot, u64 n_hits,
-                                                     const u64* read_starts, u64 n_reads,
-                                                     u64* rec_read, u32* rec_ndistinct,
-                                                     u32* rec_nhits, u64* rec_first, u64* n_recs) {
+// Sparse form: hits (stream position, slot) sorted by position -> one record per read
+// that has hits.  Distinct slots per read are counted by SORTING: k_hit_read_keys turns
+// every hit into (read << 32 | slot), a second radix sort groups equal (read, slot)
+// pairs, and the thread that owns the first entry of a read walks its run once,
+// counting the entries that differ from their predecessor — linear in the run length
+// (the first version compared every hit with all earlier ones of its read: quadratic
+// on a long read full of hits).
+__global__ void __launch_bounds__(256) k_hit_read_keys(const u64* pos, const u32* slot, u64 n_hits,
+                                                       const u64* read_starts, u64 n_reads, u64* rkey) {
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_hits) return;
   u64 p = pos[i];
-  // r = last read with read_starts[r] <= p
-  u64 lo = 0, hi = n_reads;
+  u64 lo = 0, hi = n_reads;  // r = last read with read_starts[r] <= p
   while (hi - lo > 1) {
     u64 mid = (lo + hi) >> 1;
     if (read_starts[mid] <= p) lo = mid; else hi = mid;
   }
-  u64 r = lo;
-  u64 rs = read_starts[r];
-  if (i > 0 && pos[i - 1] >= rs) return;  // not the first hit of this read
-  u64 rend = (r + 1 < n_reads) ? read_starts[r + 1] : ~0ull;
-  u64 j = i;
+  rkey[i] = (lo << 32) | (u64)slot[i];
+}
+
+__global__ void __launch_bounds__(128) k_reduce_hits(const u64* rkey, u64 n_hits, const u64* pos,
+                                                     const u64* read_starts, u64* rec_read,
+                                                     u32* rec_ndistinct, u32* rec_nhits, u64* rec_first,
+                                                     u64* n_recs) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_hits) return;
+  const u64 key = rkey[i];
+  const u64 r = key >> 32;
+  if (i > 0 && (rkey[i - 1] >> 32) == r) return;  // not the first entry of this read
   u32 nh = 0, nd = 0;
-  while (j < n_hits && pos[j] < rend) {
-    u32 sj = slot[j];
-    bool dup = false;
-    for (u64 q = i; q < j; ++q) {
-      if (slot[q] == sj) {
-        dup = true;
-        break;
-      }
-    }
-    nd += dup ? 0u : 1u;
+  u64 prev = ~key;
+  for (u64 j = i; j < n_hits; ++j) {
+    const u64 kj = rkey[j];
+    if ((kj >> 32) != r) break;
+    nd += kj != prev ? 1u : 0u;
+    prev = kj;
     ++nh;
-    ++j;
+  }
+  // index of the read's first hit in the position-sorted list
+  const u64 rs = read_starts[r];
+  u64 lo = 0, hi = n_hits;
+  while (lo < hi) {
+    u64 mid = (lo + hi) >> 1;
+    if (pos[mid] < rs) lo = mid + 1; else hi = mid;
   }
   u64 o = atomicAdd(n_recs, 1ull);
   rec_read[o] = r;
   rec_ndistinct[o] = nd;
   rec_nhits[o] = nh;
-  rec_first[o] = i;
+  rec_first[o] = lo;
 }
 
 // ----------------------------------------------------------- K2p / K6 -----
@@ -1637,46 +1779,140 @@ struct BinStage {
 };
 
 // BMODE 0: hash range (part_of); 1: owner rank; 2: composite owner x hash range —
-// bin = owner * n_local + part, n_parts = n_owners * n_local, log2_parts = log2(n_local)
+// bin = owner * n_local + part, n_parts = n_owners * n_local, log2_parts = log2(n_local).
+// pass_log2 > 0 (BMODE 0 / 2): the hash ranges are split into 2^pass_log2 groups by their
+// TOP bits and only the keys of group pass_val are binned — the multi-pass child count,
+// which bounds the bins' memory by re-extracting the stream once per group.  Returns
+// false for a key of another group.
 template <int KW, int BMODE>
-__device__ __forceinline__ u32 bin_of(const Key<KW>& key, int log2_parts, u32 n_parts, u32 n_owners) {
-  u64 h = hash_key(key);
-  if (BMODE == 0) return part_of(h, log2_parts);
-  if (BMODE == 1) return owner_of(h, n_parts);
-  return owner_of(h, n_owners) * (n_parts / n_owners) + part_of(h, log2_parts);
+__device__ __forceinline__ bool bin_of(const Key<KW>& key, int log2_parts, u32 n_parts, u32 n_owners,
+                                       int pass_log2, u32 pass_val, u32& bin) {
+  const u64 h = hash_key(key);
+  if (BMODE == 1) {
+    if (pass_log2 && part_of(h, pass_log2) != pass_val) return false;
+    bin = owner_of(h, n_parts);
+    return true;
+  }
+  const u32 tot = part_of(h, pass_log2 + log2_parts);
+  if (pass_log2 && (tot >> log2_parts) != pass_val) return false;
+  const u32 local = tot & ((1u << log2_parts) - 1u);
+  bin = BMODE == 0 ? local : owner_of(h, n_owners) * (n_parts / n_owners) + local;
+  return true;
 }
 
-// windows handled per thread between two flushes
+// windows handled per thread between two flushes of BinStage (k_bin_keys)
 constexpr int BIN_WPR = 16;
 
+// K2p / K6, stream form.  A CTA stages the keys of a whole ROUND (threads x wpr
+// windows: 8192 keys) in per-bin shared-memory queues and writes them out as one
+// contiguous run per bin.  Against the first version (4096-key rounds, one warp per
+// bin in the flush): runs twice as long — 64 keys = 512 bytes at 128 bins, which is
+// what the NVLink peer route needs — and a flush whose cost does not grow with the
+// number of bins: with short queues the copy-out is FLAT (thread i takes queue slot i
+// of all bins, ~8 instructions per slot) instead of a loop per bin whose fixed cost was
+// paid for 16 keys.  Few bins (< 32) are spread over `rep` virtual bins each so that
+// the lanes of a warp do not serialise on a handful of shared counters.  The window
+// loop uses WindowChunks (fixed-distance funnel shifts).
+struct BinPlan {
+  int threads, wpr, qcap, rep_log2, flat;
+  size_t smem;
+};
+
 template <int KW, int BMODE>
-__global__ void __launch_bounds__(BIN_THREADS) k_bin_stream(StreamView s, int k, int log2_parts,
-                                                            u32 n_parts, u32 n_owners, int qcap, BinDest dst,
-                                                            u64* cursors, u64* overflow,
-                                                            u64* stats) {
+__global__ void __launch_bounds__(1024, 1) k_bin_stream(StreamView s, int k, int log2_parts, u32 n_parts,
+                                                        u32 n_owners, int pass_log2, u32 pass_val, int wpr,
+                                                        int qcap, u32 qinv, int rep_log2, int flat,
+                                                        BinDest dst, u64* cursors, u64* overflow, u64* stats) {
   extern __shared__ __align__(16) unsigned char bin_smem[];
-  BinStage<KW> stage;
-  stage.init(bin_smem, (int)n_parts, qcap);
+  const u32 nv = n_parts << rep_log2;   // virtual bins
+  // layout: queue[nv][qcap] keys | gptr[nv] u64* | ceff[nv] u32 | cnt[2][nv] u32
+  u64* queue = reinterpret_cast<u64*>(bin_smem);
+  u64** gptr = reinterpret_cast<u64**>(queue + (size_t)nv * qcap * KW);
+  u32* ceff = reinterpret_cast<u32*>(gptr + nv);
+  u32* cnt0 = ceff + nv;
+  const u32 tid = threadIdx.x, nthr = blockDim.x;
+  const u32 lane_rep = tid & ((1u << rep_log2) - 1u);
+  for (u32 i = tid; i < 2 * nv; i += nthr) cnt0[i] = 0;
   __syncthreads();
+  u32 round = 0;
   u32 windows = 0;
-  u64 stride = (u64)gridDim.x * blockDim.x;
-  u64 n_iter = (s.w_end - s.w_begin + stride - 1) / stride;
-  u64 w0 = s.w_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 stride = (u64)gridDim.x * nthr;
+  const u64 n_iter = (s.w_end - s.w_begin + stride - 1) / stride;
+  const u64 w0 = s.w_begin + (u64)blockIdx.x * nthr + tid;
   for (u64 itn = 0; itn < n_iter; ++itn) {
-    u64 w = w0 + itn * stride;
-    WindowIter<KW> it(s, w, k);  // loads beyond n_words read as invalid
+    const u64 w = w0 + itn * stride;
+    WindowChunks<KW> it(s, w, k);  // loads beyond n_words read as invalid
     const bool in_range = w < s.w_end;  // window starts of later words belong to another launch
 #pragma unroll 1
-    for (int c = 0; c < 32 / BIN_WPR; ++c) {
-#pragma unroll 4
-      for (int j = 0; j < BIN_WPR; ++j) {
-        bool ok = in_range && it.ok();
-        Key<KW> key = it.canonical();
-        it.advance();
-        windows += ok ? 1u : 0u;
-        stage.push(ok, bin_of<KW, BMODE>(key, log2_parts, n_parts, n_owners), key, dst, cursors, overflow);
+    for (int c = 0; c < 8; ++c) {
+      u32* cnt = cnt0 + (round & 1u) * nv;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const Key<KW> key = it.key(u);
+        u32 p;
+        if (in_range && it.ok(u) && bin_of<KW, BMODE>(key, log2_parts, n_parts, n_owners, pass_log2, pass_val, p)) {
+          ++windows;
+          const u32 v = (p << rep_log2) | lane_rep;
+          const u32 o = atomicAdd(&cnt[v], 1u);
+          if (o < (u32)qcap) {
+            u64* q = queue + ((size_t)v * qcap + o) * KW;
+            q[0] = key.lo;
+            if (KW == 2) q[1] = ((const u64*)&key)[KW - 1];
+          } else {  // queue full (a skewed round): append directly
+            const u64 g = atomicAdd(cursors + p, 1ull);
+            if (g < dst.cap) st_key<KW>(dst.of(p, KW), g, key);
+            else atomicOr(overflow, 1ull);
+          }
+        }
       }
-      stage.flush(dst, cursors, overflow);
+      it.template next<4>();
+      if ((((c + 1) * 4) % wpr) != 0) continue;
+      // ---- flush: reserve one run per (virtual) bin, copy out, next round
+      __syncthreads();
+      u32* cnt_next = cnt0 + ((round + 1) & 1u) * nv;
+      for (u32 v = tid; v < nv; v += nthr) {
+        u32 cc = cnt[v];
+        if (cc > (u32)qcap) cc = qcap;
+        const u32 p = v >> rep_log2;
+        u64 g0 = 0;
+        if (cc) {
+          g0 = atomicAdd(cursors + p, (u64)cc);
+          if (g0 + cc > dst.cap) {
+            atomicOr(overflow, 1ull);
+            cc = g0 < dst.cap ? (u32)(dst.cap - g0) : 0u;
+          }
+        }
+        ceff[v] = cc;
+        gptr[v] = dst.of(p, KW) + g0 * KW;
+        cnt_next[v] = 0;
+      }
+      __syncthreads();
+      if (flat) {
+        const u32 n_slots = nv * (u32)qcap;
+        for (u32 i = tid; i < n_slots; i += nthr) {
+          const u32 v = __umulhi(i, qinv);
+          const u32 o = i - v * (u32)qcap;
+          if (o < ceff[v]) {
+            const u64* q = queue + (size_t)i * KW;
+            u64* out = gptr[v] + (size_t)o * KW;
+            if (KW == 1) out[0] = q[0];
+            else *reinterpret_cast<ulonglong2*>(out) = *reinterpret_cast<const ulonglong2*>(q);
+          }
+        }
+      } else {
+        const u32 lane = tid & 31u, n_warps = nthr >> 5;
+        for (u32 v = tid >> 5; v < nv; v += n_warps) {
+          const u32 cc = ceff[v];
+          u64* out = gptr[v];
+          const u64* q = queue + (size_t)v * qcap * KW;
+          for (u32 o = lane; o < cc; o += 32) {
+            if (KW == 1) out[o] = q[o];
+            else reinterpret_cast<ulonglong2*>(out)[o] = reinterpret_cast<const ulonglong2*>(q)[o];
+          }
+        }
+      }
+      __syncthreads();
+      ++round;
     }
   }
   if (stats) {
@@ -1687,8 +1923,8 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_stream(StreamView s, int k,
 
 template <int KW, int BMODE>
 __global__ void __launch_bounds__(BIN_THREADS) k_bin_keys(const u64* lo, const u64* hi, u64 n,
-                                                          int log2_parts, u32 n_parts, int qcap,
-                                                          BinDest dst, u64* cursors,
+                                                          int log2_parts, u32 n_parts, int pass_log2,
+                                                          u32 pass_val, int qcap, BinDest dst, u64* cursors,
                                                           u64* overflow) {
   extern __shared__ __align__(16) unsigned char bin_smem[];
   BinStage<KW> stage;
@@ -1703,197 +1939,12 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_keys(const u64* lo, const u
       u64 i = base + (u64)j * blockDim.x;
       bool ok = i < n;
       Key<KW> key = ld_key_stream<KW>(lo, hi, ok ? i : 0);
-      stage.push(ok, bin_of<KW, BMODE>(key, log2_parts, n_parts, 1), key, dst, cursors, overflow);
+      u32 p = 0;
+      // log2_parts = ALL hash-range bits (pass groups on top), n_parts local bins
+      ok = ok && bin_of<KW, BMODE>(key, log2_parts - pass_log2, n_parts, 1, pass_log2, pass_val, p);
+      stage.push(ok, p, key, dst, cursors, overflow);
     }
     stage.flush(dst, cursors, overflow);
-  }
-}
-
-// ------------------------------------- K2s: shared-memory packed count ----
-// Returning atomics on L2 top out near 50 G/s on this part (profiles/r1d_atomics.txt:
-// CAS / ATOM.ADD with the result used, L2-resident buffer) and a packed count needs one
-// for every new key and every unsaturated copy, which is what bounds kdf_count_bins at
-// ~80 G keys/s.  Shared-memory atomics have no such ceiling, so for 64-bit keys the bins
-// are split once more — `s2` sub-ranges of each hash range, a second streaming pass —
-// until a sub-bin's distinct keys fit a table in shared memory; one CTA then counts a
-// sub-bin start to finish (clear, insert + saturating count, reference marks, emit)
-// without a single global atomic on the table.  Same packed slot format as K2c.
-constexpr int SUB_THREADS = 256;
-constexpr int SUB_LOADS = 4;          // keys in flight per thread
-constexpr int SUB_PROBE_MAX = 96;     // longer probe sequences mean the table is too full
-
-// second-level binning: work item = (bin of the group, source, tile of TILE keys)
-constexpr int REBIN_TILE = BIN_THREADS * BIN_WPR;
-__global__ void __launch_bounds__(BIN_THREADS) k_rebin(const u64* bins, u64 bin_cap, const u64* cursors,
-                                                       int n_parts, int n_src, int p_begin, int p_count,
-                                                       int log2_tot, u32 s2, int qcap, u64* sub,
-                                                       u64 sub_cap, u64* sub_cursors, u64* overflow) {
-  extern __shared__ __align__(16) unsigned char bin_smem[];
-  BinStage<1> stage;
-  stage.init(bin_smem, (int)s2, qcap);
-  __syncthreads();
-  const u64 tiles = (bin_cap + REBIN_TILE - 1) / REBIN_TILE;
-  const u64 n_items = (u64)p_count * n_src * tiles;
-  for (u64 item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const u64 tile = item % tiles;
-    const u64 ps = item / tiles;
-    const int src = (int)(ps % n_src);
-    const int pl = (int)(ps / n_src);
-    const u64 b = (u64)src * n_parts + p_begin + pl;
-    u64 n = cursors[b];
-    if (n > bin_cap) n = bin_cap;
-    if (tile * REBIN_TILE >= n) continue;  // uniform over the CTA
-    const u64* in = bins + b * bin_cap;
-    BinDest dst = {sub + (u64)pl * s2 * sub_cap, nullptr, sub_cap};
-    u64* cur = sub_cursors + (u64)pl * s2;
-#pragma unroll 4
-    for (int j = 0; j < BIN_WPR; ++j) {
-      u64 i = tile * REBIN_TILE + (u64)j * BIN_THREADS + threadIdx.x;
-      bool ok = i < n;
-      Key<1> key = ld_key_stream<1>(in, nullptr, ok ? i : 0);
-      u32 part = part_of(hash_key(key), log2_tot) & (s2 - 1);
-      stage.push(ok, part, key, dst, cur, overflow);
-    }
-    stage.flush(dst, cur, overflow);
-  }
-}
-
-__device__ __forceinline__ u32 sub_slot_of(u64 h, u32 slot_mask) {
-  u32 l = (u32)h;   // the high product bits chose the bin and the sub-bin
-  l ^= l >> 16;
-  l *= 0x7feb352du;
-  l ^= l >> 15;
-  return l & slot_mask;
-}
-
-// flags: bit 0 = a sub-bin did not fit its shared-memory table (results invalid: the
-// caller falls back to the L2 form), counters as in kdf_count_bins
-__global__ void __launch_bounds__(SUB_THREADS) k_count_sub(
-    const u64* sub, u64 sub_cap, const u64* sub_cursors, const u64* rsub, u64 rsub_cap,
-    const u64* rsub_cursors, u32 n_sub, u32 n_slots, int sh, u32 sat, int ignore_ref, int count_all,
-    u64* out_lo, u64 cap, u64* n_out, u64* counters, u64* flags) {
-  extern __shared__ __align__(16) u64 tab[];
-  __shared__ u32 s_over;
-  const u64 mask = (1ull << sh) - 1;
-  const u64 one = 1ull << sh;
-  const u32 slot_mask = n_slots - 1;
-  const unsigned lane = threadIdx.x & 31;
-  u32 n_keys = 0, n_hits = 0, n_new = 0, cnt_ge = 0, cnt_occ = 0;
-  for (u32 sb = blockIdx.x; sb < n_sub; sb += gridDim.x) {
-    for (u32 i = threadIdx.x; i < n_slots; i += SUB_THREADS) tab[i] = EMPTY;
-    if (threadIdx.x == 0) s_over = 0;
-    __syncthreads();
-    // ---- insert + saturating count
-    u64 n = sub_cursors[sb];
-    if (n > sub_cap) n = sub_cap;
-    const u64* in = sub + (u64)sb * sub_cap;
-    for (u64 base = 0; base < n; base += SUB_THREADS * SUB_LOADS) {
-      u64 keys[SUB_LOADS];
-#pragma unroll
-      for (int u = 0; u < SUB_LOADS; ++u) {
-        u64 i = base + (u64)u * SUB_THREADS + threadIdx.x;
-        keys[u] = i < n ? __ldcs(in + i) : EMPTY;
-      }
-#pragma unroll
-      for (int u = 0; u < SUB_LOADS; ++u) {
-        const u64 key = keys[u];
-        if (key == EMPTY) continue;
-        ++n_keys;
-        Key<1> kk;
-        kk.lo = key;
-        u32 slot = sub_slot_of(hash_key(kk), slot_mask);
-        int probes = 0;
-        for (;;) {
-          u64 w = *(volatile u64*)(tab + slot);
-          if (w == EMPTY) {
-            u64 old = atomicCAS(tab + slot, EMPTY, key | one);
-            if (old == EMPTY) {
-              ++n_new;
-              break;
-            }
-            w = old;  // someone else took the slot: is it our key ?
-          }
-          if ((w & mask) == key) {
-            ++n_hits;
-            while ((u32)(w >> sh) < sat) {   // saturating bump
-              u64 old = atomicCAS(tab + slot, w, w + one);
-              if (old == w) break;
-              w = old;
-            }
-            break;
-          }
-          slot = (slot + 1) & slot_mask;
-          if (++probes > SUB_PROBE_MAX) {
-            s_over = 1;
-            break;
-          }
-        }
-      }
-    }
-    __syncthreads();
-    // ---- reference marks: "saturated" -> "saturated, in the reference"
-    if (rsub && !ignore_ref) {
-      u64 nr = rsub_cursors[sb];
-      if (nr > rsub_cap) nr = rsub_cap;
-      const u64* rin = rsub + (u64)sb * rsub_cap;
-      for (u64 i = threadIdx.x; i < nr; i += SUB_THREADS) {
-        const u64 key = __ldcs(rin + i);
-        Key<1> kk;
-        kk.lo = key;
-        u32 slot = sub_slot_of(hash_key(kk), slot_mask);
-        for (int probes = 0; probes <= SUB_PROBE_MAX + 1; ++probes) {
-          u64 w = *(volatile u64*)(tab + slot);
-          if (w == EMPTY) break;
-          if ((w & mask) == key) {
-            if ((u32)(w >> sh) == sat) atomicAnd(tab + slot, mask);
-            break;
-          }
-          slot = (slot + 1) & slot_mask;
-        }
-      }
-      __syncthreads();
-    }
-    // ---- emit
-    const bool over = s_over != 0;
-    if (over) {
-      if (threadIdx.x == 0) atomicOr(flags, 1ull);
-    } else {
-      for (u32 i0 = 0; i0 < n_slots; i0 += SUB_THREADS) {
-        u64 w = tab[i0 + threadIdx.x];
-        bool occ = w != EMPTY;
-        u32 state = (u32)(w >> sh);
-        bool reached = state >= sat || state == 0;
-        bool keep = occ && (ignore_ref ? reached : state >= sat);
-        cnt_occ += occ ? 1u : 0u;
-        cnt_ge += (occ && (count_all || reached)) ? 1u : 0u;
-        unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (m) {
-          u64 base = 0;
-          if (lane == 0) base = atomicAdd(n_out, (u64)__popc(m));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (keep) {
-            u64 o = base + __popc(m & ((1u << lane) - 1));
-            if (o < cap && out_lo) out_lo[o] = w & mask;
-          }
-        }
-      }
-    }
-    __syncthreads();
-  }
-  // counters: [0] keys applied, [2] hits, [3] distinct, [4] reached, [5] occupied
-  for (int o = 16; o; o >>= 1) {
-    n_keys += __shfl_xor_sync(0xffffffffu, n_keys, o);
-    n_hits += __shfl_xor_sync(0xffffffffu, n_hits, o);
-    n_new += __shfl_xor_sync(0xffffffffu, n_new, o);
-    cnt_ge += __shfl_xor_sync(0xffffffffu, cnt_ge, o);
-    cnt_occ += __shfl_xor_sync(0xffffffffu, cnt_occ, o);
-  }
-  if (lane == 0) {
-    if (n_keys) atomicAdd(counters + 0, (u64)n_keys);
-    if (n_hits) atomicAdd(counters + 2, (u64)n_hits);
-    if (n_new) atomicAdd(counters + 3, (u64)n_new);
-    if (cnt_ge) atomicAdd(counters + 4, (u64)cnt_ge);
-    if (cnt_occ) atomicAdd(counters + 5, (u64)cnt_occ);
   }
 }
 
@@ -1999,6 +2050,10 @@ __global__ void __launch_bounds__(256) k_bench_random(u32* buf, u64 n_sectors, u
 }
 
 // ------------------------------------------------------------ host side ---
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
 static int grid_for(const void* func, int block, size_t smem, u64 work_items, int sm_count) {
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, block, smem) != cudaSuccess ||
@@ -2146,25 +2201,38 @@ static int launch_emit_buckets(const kdf_table* t, u32 min0, u32 max0, u32 min1,
   return KDF_OK;
 }
 
+static bool pq_split_enabled() {
+  static const int v = env_int("KDF_PQ_SPLIT", 1);
+  return v != 0;
+}
+
+template <int KW, int OP, bool FILT, bool SPLIT>
+static int launch_packed_keys_impl(const kdf_table* t, const u64* lo, u64 n_max, const u64* n_dev, int sh,
+                                   u32 sat, u64* stats, cudaStream_t st, int filt_log2, u32 filt_val) {
+  TableView<KW> tv = view_of_table<KW>(t);
+  const size_t smem = sizeof(PackedKeysQueue<KW, OP, SPLIT>) * (256 / 32);
+  const u64 items = (n_max + KDF_KEYS_CHUNK - 1) / KDF_KEYS_CHUNK;
+  const void* fn = (const void*)k_packed_keys<KW, OP, FILT, SPLIT>;
+  CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int g = grid_for(fn, 256, smem, items, t->sm_count);
+  k_packed_keys<KW, OP, FILT, SPLIT><<<g, 256, smem, st>>>(tv, lo, n_max, n_dev, sh, sat, stats, filt_log2, filt_val);
+  CUDA_TRY(cudaGetLastError());
+  return KDF_OK;
+}
+
 template <int KW, int OP>
 static int launch_packed_keys(const kdf_table* t, const u64* lo, u64 n_max, const u64* n_dev, int sh,
                               u32 sat, u64* stats, cudaStream_t st, int filt_log2, u32 filt_val) {
-  TableView<KW> tv = view_of_table<KW>(t);
-  const size_t smem = sizeof(PackedKeysQueue<KW, OP>) * (256 / 32);
-  const u64 items = (n_max + KDF_KEYS_CHUNK - 1) / KDF_KEYS_CHUNK;
-  if (filt_log2 > 0) {
-    const void* fn = (const void*)k_packed_keys<KW, OP, true>;
-    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int g = grid_for(fn, 256, smem, items, t->sm_count);
-    k_packed_keys<KW, OP, true><<<g, 256, smem, st>>>(tv, lo, n_max, n_dev, sh, sat, stats, filt_log2, filt_val);
-  } else {
-    const void* fn = (const void*)k_packed_keys<KW, OP, false>;
-    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int g = grid_for(fn, 256, smem, items, t->sm_count);
-    k_packed_keys<KW, OP, false><<<g, 256, smem, st>>>(tv, lo, n_max, n_dev, sh, sat, stats, 0, 0);
+  if constexpr (OP == OP_PACKED_COUNT) {
+    if (pq_split_enabled()) {
+      if (filt_log2 > 0)
+        return launch_packed_keys_impl<KW, OP, true, true>(t, lo, n_max, n_dev, sh, sat, stats, st, filt_log2, filt_val);
+      return launch_packed_keys_impl<KW, OP, false, true>(t, lo, n_max, n_dev, sh, sat, stats, st, 0, 0);
+    }
   }
-  CUDA_TRY(cudaGetLastError());
-  return KDF_OK;
+  if (filt_log2 > 0)
+    return launch_packed_keys_impl<KW, OP, true, false>(t, lo, n_max, n_dev, sh, sat, stats, st, filt_log2, filt_val);
+  return launch_packed_keys_impl<KW, OP, false, false>(t, lo, n_max, n_dev, sh, sat, stats, st, 0, 0);
 }
 
 template <int KW>
@@ -2493,12 +2561,14 @@ int kdf_scan_reads(const kdf_table* t, const kdf_stream* s, const uint64_t* read
 }
 
 size_t kdf_reduce_hits_scratch_bytes(uint64_t n_hits) {
-  size_t tmp = 0;
+  size_t tmp = 0, tmp2 = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const u64*)nullptr, (u64*)nullptr,
                                   (const u32*)nullptr, (u32*)nullptr, (int)n_hits);
-  // sorted pos + sorted slot + cub temp, each 256-byte aligned
+  cub::DeviceRadixSort::SortKeys(nullptr, tmp2, (const u64*)nullptr, (u64*)nullptr, (int)n_hits);
+  if (tmp2 > tmp) tmp = tmp2;
+  // sorted pos + sorted slot + two (read, slot) key arrays + cub temp, each 256-byte aligned
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  return al(n_hits * 8) + al(n_hits * 4) + al(tmp) + 256;
+  return 3 * al(n_hits * 8) + al(n_hits * 4) + al(tmp) + 256;
 }
 
 int kdf_reduce_hits(const uint64_t* hit_pos, const uint32_t* hit_slot, uint64_t n_hits,
@@ -2511,6 +2581,7 @@ int kdf_reduce_hits(const uint64_t* hit_pos, const uint32_t* hit_slot, uint64_t 
       !rec_nhits || !rec_first || !n_recs)
     return fail(KDF_ERR_ARG, "kdf_reduce_hits: NULL argument");
   if (n_hits > 0x7fffffffull) return fail(KDF_ERR_ARG, "kdf_reduce_hits: too many hits for one call");
+  if (n_reads > 0xffffffffull) return fail(KDF_ERR_ARG, "kdf_reduce_hits: more than 2^32 reads in one stream");
   if (scratch_bytes < kdf_reduce_hits_scratch_bytes(n_hits))
     return fail(KDF_ERR_CAPACITY, "kdf_reduce_hits: scratch too small");
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -2519,13 +2590,22 @@ int kdf_reduce_hits(const uint64_t* hit_pos, const uint32_t* hit_slot, uint64_t 
   p += al(n_hits * 8);
   u32* sslot = sorted_slot_out ? sorted_slot_out : (u32*)p;
   p += al(n_hits * 4);
-  size_t tmp = 0;
+  u64* rkey = (u64*)p;
+  p += al(n_hits * 8);
+  u64* rkey_sorted = (u64*)p;
+  p += al(n_hits * 8);
+  size_t tmp = 0, tmp2 = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const u64*)hit_pos, spos, hit_slot, sslot, (int)n_hits);
+  cub::DeviceRadixSort::SortKeys(nullptr, tmp2, (const u64*)rkey, rkey_sorted, (int)n_hits);
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(p, tmp, (const u64*)hit_pos, spos, hit_slot, sslot,
                                            (int)n_hits, 0, 64, st));
+  k_hit_read_keys<<<(int)((n_hits + 255) / 256), 256, 0, st>>>(spos, sslot, n_hits, (const u64*)read_starts,
+                                                              n_reads, rkey);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cub::DeviceRadixSort::SortKeys(p, tmp2, (const u64*)rkey, rkey_sorted, (int)n_hits, 0, 64, st));
   int g = (int)((n_hits + 127) / 128);
-  k_reduce_hits<<<g, 128, 0, st>>>(spos, sslot, n_hits, (const u64*)read_starts, n_reads, (u64*)rec_read,
+  k_reduce_hits<<<g, 128, 0, st>>>(rkey_sorted, n_hits, spos, (const u64*)read_starts, (u64*)rec_read,
                                    rec_ndistinct, rec_nhits, (u64*)rec_first, (u64*)n_recs);
   CUDA_TRY(cudaGetLastError());
   return KDF_OK;
@@ -2603,16 +2683,107 @@ static int bin_qcap(int n_parts, int kw) {
   return q;
 }
 
+// Launch shape of k_bin_stream for n_parts bins (see the kernel's comment).  A round is
+// 8192 / kw keys.  Two CTAs of 512 threads per SM while the queues fit ~108 KB; with
+// many bins the slack a short queue needs (mean + 5 sigma) makes them larger, and one
+// CTA of 1024 threads takes the same round.  KDF_BIN_THREADS / KDF_BIN_WPR override.
+static BinPlan bin_plan(int n_parts, int kw) {
+  BinPlan pl;
+  pl.rep_log2 = 0;
+  while ((n_parts << pl.rep_log2) < 32) ++pl.rep_log2;
+  const int nv = n_parts << pl.rep_log2;
+  const int round_keys = 8192 / kw;
+  auto qcap_for = [&](int keys) {
+    double mean = (double)keys / nv;
+    return (int)(mean + 5.0 * sqrt(mean) + 8.0);
+  };
+  auto smem_for = [&](int qcap) { return (size_t)nv * qcap * 8 * kw + (size_t)nv * (8 + 4 + 8); };
+  pl.threads = env_int("KDF_BIN_THREADS", 0);
+  pl.wpr = env_int("KDF_BIN_WPR", 0);
+  if (pl.threads != 512 && pl.threads != 1024 && pl.threads != 256) pl.threads = 0;
+  if (pl.wpr != 4 && pl.wpr != 8 && pl.wpr != 16 && pl.wpr != 32) pl.wpr = 0;
+  if (!pl.threads) pl.threads = smem_for(qcap_for(round_keys)) <= 108 * 1024 ? 512 : 1024;
+  if (!pl.wpr) {
+    pl.wpr = round_keys / pl.threads;
+    if (pl.wpr < 4) pl.wpr = 4;
+    if (pl.wpr > 32) pl.wpr = 32;
+  }
+  const int keys = pl.threads * pl.wpr;
+  pl.qcap = qcap_for(keys);
+  const size_t budget = 220 * 1024;
+  if (smem_for(pl.qcap) > budget) pl.qcap = (int)((budget - (size_t)nv * 20) / ((size_t)nv * 8 * kw));
+  if (pl.qcap < 4) pl.qcap = 4;
+  pl.smem = smem_for(pl.qcap);
+  pl.flat = (keys / nv) < 128 ? 1 : 0;
+  return pl;
+}
+
 static int bin_stream_impl(const kdf_stream* s, int k, int by_owner, int n_parts, BinDest dst,
                            uint64_t* cursors, uint64_t* overflow, uint64_t* stats, void* stream,
-                           uint64_t first_word = 0, uint64_t n_range_words = ~0ull);
+                           uint64_t first_word, uint64_t n_range_words, int pass_log2, uint32_t pass_val) {
+  int kw = kdf_key_words(k);
+  if (!kw) return fail(KDF_ERR_ARG, "kdf_bin_stream: k must be in 1..64");
+  if (n_parts < 1 || n_parts > BIN_MAX_PARTS) return fail(KDF_ERR_ARG, "kdf_bin_stream: n_parts must be 1..512");
+  if (pass_log2 < 0 || pass_log2 > 16 || (pass_val >> pass_log2) != 0)
+    return fail(KDF_ERR_ARG, "kdf_bin_stream: pass_val must be < 2^pass_log2, pass_log2 <= 16");
+  // by_owner: 0 = hash ranges, 1 = owner ranks, R >= 2 = composite (R owners x n_parts/R ranges)
+  int log2p = 0;
+  int n_owners = 1;
+  int bmode = by_owner == 0 ? 0 : (by_owner == 1 ? 1 : 2);
+  if (bmode != 1) {
+    n_owners = bmode == 2 ? by_owner : 1;
+    if (n_parts % n_owners) return fail(KDF_ERR_ARG, "kdf_bin_stream: n_parts must be a multiple of the owner count");
+    int n_local = n_parts / n_owners;
+    while ((1 << log2p) < n_local) ++log2p;
+    if ((1 << log2p) != n_local) return fail(KDF_ERR_ARG, "kdf_bin_stream: hash-range bins need a power-of-two count");
+    if (log2p + pass_log2 > 28) return fail(KDF_ERR_ARG, "kdf_bin_stream: too many hash ranges");
+  }
+  StreamView v = view_of(s);
+  if (first_word > v.n_words) first_word = v.n_words;
+  v.w_begin = first_word;
+  v.w_end = (n_range_words > v.n_words - first_word) ? v.n_words : first_word + n_range_words;
+  if (v.w_end == v.w_begin) return KDF_OK;
+  int sm = current_sm_count();
+  cudaStream_t st = (cudaStream_t)stream;
+  const BinPlan pl = bin_plan(n_parts, kw);
+  const u32 qinv = (u32)((0x100000000ull + (u64)pl.qcap - 1) / (u64)pl.qcap);
+#define KDF_BIN(KW, BM)                                                                           \
+  {                                                                                               \
+    const void* fn = (const void*)k_bin_stream<KW, BM>;                                           \
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
+    int g = grid_for(fn, pl.threads, pl.smem, v.w_end - v.w_begin, sm);                           \
+    k_bin_stream<KW, BM><<<g, pl.threads, pl.smem, st>>>(v, k, log2p, (u32)n_parts, (u32)n_owners, \
+                                                         pass_log2, pass_val, pl.wpr, pl.qcap, qinv, \
+                                                         pl.rep_log2, pl.flat, dst, (u64*)cursors, \
+                                                         (u64*)overflow, (u64*)stats);            \
+  }
+  if (kw == 1) {
+    if (bmode == 0) KDF_BIN(1, 0) else if (bmode == 1) KDF_BIN(1, 1) else KDF_BIN(1, 2)
+  } else {
+    if (bmode == 0) KDF_BIN(2, 0) else if (bmode == 1) KDF_BIN(2, 1) else KDF_BIN(2, 2)
+  }
+#undef KDF_BIN
+  CUDA_TRY(cudaGetLastError());
+  return KDF_OK;
+}
+
+int kdf_bin_stream_pass(const kdf_stream* s, uint64_t first_word, uint64_t n_words, int k, int by_owner,
+                        int n_parts, uint64_t* bins, uint64_t* const* bin_ptrs, uint64_t bin_cap,
+                        uint64_t* cursors, uint64_t* overflow, uint64_t* stats, int pass_log2,
+                        uint32_t pass_val, void* stream) {
+  if (!s || (!bins && !bin_ptrs) || !cursors || !overflow)
+    return fail(KDF_ERR_ARG, "kdf_bin_stream_pass: NULL argument");
+  BinDest dst = {(u64*)bins, bins ? nullptr : (u64* const*)bin_ptrs, bin_cap};
+  return bin_stream_impl(s, k, by_owner, n_parts, dst, cursors, overflow, stats, stream, first_word,
+                         n_words, pass_log2, pass_val);
+}
 
 int kdf_bin_stream(const kdf_stream* s, int k, int by_owner, int n_parts, uint64_t* bins,
                    uint64_t bin_cap, uint64_t* cursors, uint64_t* overflow, uint64_t* stats,
                    void* stream) {
-  if (!s || !bins || !cursors || !overflow) return fail(KDF_ERR_ARG, "kdf_bin_stream: NULL argument");
-  BinDest dst = {(u64*)bins, nullptr, bin_cap};
-  return bin_stream_impl(s, k, by_owner, n_parts, dst, cursors, overflow, stats, stream);
+  if (!bins) return fail(KDF_ERR_ARG, "kdf_bin_stream: NULL argument");
+  return kdf_bin_stream_pass(s, 0, ~0ull, k, by_owner, n_parts, bins, nullptr, bin_cap, cursors, overflow,
+                             stats, 0, 0, stream);
 }
 
 int kdf_bin_stream_to(const kdf_stream* s, int k, int by_owner, int n_parts,
@@ -2625,77 +2796,30 @@ int kdf_bin_stream_to(const kdf_stream* s, int k, int by_owner, int n_parts,
 int kdf_bin_stream_to_range(const kdf_stream* s, uint64_t first_word, uint64_t n_words, int k,
                             int by_owner, int n_parts, uint64_t* const* bin_ptrs, uint64_t bin_cap,
                             uint64_t* cursors, uint64_t* overflow, uint64_t* stats, void* stream) {
-  if (!s || !bin_ptrs || !cursors || !overflow)
-    return fail(KDF_ERR_ARG, "kdf_bin_stream_to: NULL argument");
-  BinDest dst = {nullptr, (u64* const*)bin_ptrs, bin_cap};
-  return bin_stream_impl(s, k, by_owner, n_parts, dst, cursors, overflow, stats, stream, first_word,
-                         n_words);
+  if (!bin_ptrs) return fail(KDF_ERR_ARG, "kdf_bin_stream_to: NULL argument");
+  return kdf_bin_stream_pass(s, first_word, n_words, k, by_owner, n_parts, nullptr, bin_ptrs, bin_cap,
+                             cursors, overflow, stats, 0, 0, stream);
 }
 
 int kdf_bin_stream_range(const kdf_stream* s, uint64_t first_word, uint64_t n_words, int k,
                          int by_owner, int n_parts, uint64_t* bins, uint64_t bin_cap,
                          uint64_t* cursors, uint64_t* overflow, uint64_t* stats, void* stream) {
-  if (!s || !bins || !cursors || !overflow)
-    return fail(KDF_ERR_ARG, "kdf_bin_stream_range: NULL argument");
-  BinDest dst = {(u64*)bins, nullptr, bin_cap};
-  return bin_stream_impl(s, k, by_owner, n_parts, dst, cursors, overflow, stats, stream, first_word,
-                         n_words);
+  if (!bins) return fail(KDF_ERR_ARG, "kdf_bin_stream_range: NULL argument");
+  return kdf_bin_stream_pass(s, first_word, n_words, k, by_owner, n_parts, bins, nullptr, bin_cap, cursors,
+                             overflow, stats, 0, 0, stream);
 }
 
-static int bin_stream_impl(const kdf_stream* s, int k, int by_owner, int n_parts, BinDest dst,
-                           uint64_t* cursors, uint64_t* overflow, uint64_t* stats, void* stream,
-                           uint64_t first_word, uint64_t n_range_words) {
-  int kw = kdf_key_words(k);
-  if (!kw) return fail(KDF_ERR_ARG, "kdf_bin_stream: k must be in 1..64");
-  if (n_parts < 1 || n_parts > BIN_MAX_PARTS) return fail(KDF_ERR_ARG, "kdf_bin_stream: n_parts must be 1..512");
-  // by_owner: 0 = hash ranges, 1 = owner ranks, R >= 2 = composite (R owners x n_parts/R ranges)
-  int log2p = 0;
-  int n_owners = 1;
-  int bmode = by_owner == 0 ? 0 : (by_owner == 1 ? 1 : 2);
-  if (bmode != 1) {
-    n_owners = bmode == 2 ? by_owner : 1;
-    if (n_parts % n_owners) return fail(KDF_ERR_ARG, "kdf_bin_stream: n_parts must be a multiple of the owner count");
-    int n_local = n_parts / n_owners;
-    while ((1 << log2p) < n_local) ++log2p;
-    if ((1 << log2p) != n_local) return fail(KDF_ERR_ARG, "kdf_bin_stream: hash-range bins need a power-of-two count");
-  }
-  StreamView v = view_of(s);
-  if (first_word > v.n_words) first_word = v.n_words;
-  v.w_begin = first_word;
-  v.w_end = (n_range_words > v.n_words - first_word) ? v.n_words : first_word + n_range_words;
-  if (v.w_end == v.w_begin) return KDF_OK;
-  int sm = current_sm_count();
-  cudaStream_t st = (cudaStream_t)stream;
-  int qcap = bin_qcap(n_parts, kw);
-#define KDF_BIN(KW, BM)                                                                           \
-  {                                                                                               \
-    size_t smem = BinStage<KW>::bytes(n_parts, qcap);                                             \
-    const void* fn = (const void*)k_bin_stream<KW, BM>;                                           \
-    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    int g = grid_for(fn, BIN_THREADS, smem, v.w_end - v.w_begin, sm);                             \
-    k_bin_stream<KW, BM><<<g, BIN_THREADS, smem, st>>>(v, k, log2p, (u32)n_parts, (u32)n_owners,  \
-                                                       qcap, dst, (u64*)cursors, (u64*)overflow,  \
-                                                       (u64*)stats);                              \
-  }
-  if (kw == 1) {
-    if (bmode == 0) KDF_BIN(1, 0) else if (bmode == 1) KDF_BIN(1, 1) else KDF_BIN(1, 2)
-  } else {
-    if (bmode == 0) KDF_BIN(2, 0) else if (bmode == 1) KDF_BIN(2, 1) else KDF_BIN(2, 2)
-  }
-#undef KDF_BIN
-  CUDA_TRY(cudaGetLastError());
-  return KDF_OK;
-}
-
-int kdf_bin_keys(const uint64_t* lo, const uint64_t* hi, uint64_t n, int k, int by_owner,
-                 int n_parts, uint64_t* bins, uint64_t bin_cap, uint64_t* cursors,
-                 uint64_t* overflow, void* stream) {
+int kdf_bin_keys_pass(const uint64_t* lo, const uint64_t* hi, uint64_t n, int k, int by_owner,
+                      int n_parts, int pass_log2, uint32_t pass_val, uint64_t* bins, uint64_t bin_cap,
+                      uint64_t* cursors, uint64_t* overflow, void* stream) {
   if (!bins || !cursors || !overflow) return fail(KDF_ERR_ARG, "kdf_bin_keys: NULL argument");
   int kw = kdf_key_words(k);
   if (!kw) return fail(KDF_ERR_ARG, "kdf_bin_keys: k must be in 1..64");
   if (n == 0) return KDF_OK;
   if (!lo) return fail(KDF_ERR_ARG, "kdf_bin_keys: NULL key array");
   if (n_parts < 1 || n_parts > BIN_MAX_PARTS) return fail(KDF_ERR_ARG, "kdf_bin_keys: n_parts must be 1..512");
+  if (pass_log2 < 0 || pass_log2 > 16 || (pass_val >> pass_log2) != 0)
+    return fail(KDF_ERR_ARG, "kdf_bin_keys: pass_val must be < 2^pass_log2, pass_log2 <= 16");
   BinDest dst = {(u64*)bins, nullptr, bin_cap};
   int log2p = 0;
   if (!by_owner) {
@@ -2711,9 +2835,10 @@ int kdf_bin_keys(const uint64_t* lo, const uint64_t* hi, uint64_t n, int k, int 
     const void* fn = (const void*)k_bin_keys<KW, OWN>;                                            \
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
     int g = grid_for(fn, BIN_THREADS, smem, (n + BIN_WPR - 1) / BIN_WPR, sm);                     \
-    k_bin_keys<KW, OWN><<<g, BIN_THREADS, smem, st>>>((const u64*)lo, (const u64*)hi, n, log2p,   \
-                                                      (u32)n_parts, qcap, dst,                    \
-                                                      (u64*)cursors, (u64*)overflow);             \
+    k_bin_keys<KW, OWN><<<g, BIN_THREADS, smem, st>>>((const u64*)lo, (const u64*)hi, n,          \
+                                                      log2p + pass_log2, (u32)n_parts, pass_log2, \
+                                                      pass_val, qcap, dst, (u64*)cursors,         \
+                                                      (u64*)overflow);                            \
   }
   if (kw == 1) {
     if (by_owner) KDF_BINK(1, 1) else KDF_BINK(1, 0)
@@ -2723,6 +2848,12 @@ int kdf_bin_keys(const uint64_t* lo, const uint64_t* hi, uint64_t n, int k, int 
 #undef KDF_BINK
   CUDA_TRY(cudaGetLastError());
   return KDF_OK;
+}
+
+int kdf_bin_keys(const uint64_t* lo, const uint64_t* hi, uint64_t n, int k, int by_owner,
+                 int n_parts, uint64_t* bins, uint64_t bin_cap, uint64_t* cursors,
+                 uint64_t* overflow, void* stream) {
+  return kdf_bin_keys_pass(lo, hi, n, k, by_owner, n_parts, 0, 0, bins, bin_cap, cursors, overflow, stream);
 }
 
 int kdf_count_bins_packed(int k, uint32_t min0, uint32_t max0, uint32_t min1, uint32_t max1,
@@ -2759,6 +2890,21 @@ int kdf_count_bins_multi(int k, int n_parts, int n_src, int sub_split, const uin
                          uint32_t min1, uint32_t max1, uint64_t* out_lo, uint64_t* out_hi,
                          uint32_t* out_p0, uint32_t* out_p1, uint64_t out_cap, uint64_t* n_out,
                          uint32_t count_min0, uint64_t* counters, void* stream) {
+  return kdf_count_bins_pass(k, n_parts, n_src, sub_split, 0, 0, child_bins, child_bin_cap, child_cursors,
+                             ref_bins, ref_bin_cap, ref_cursors, slice, slice_capacity, min0, max0, min1,
+                             max1, out_lo, out_hi, out_p0, out_p1, out_cap, n_out, count_min0, counters,
+                             stream);
+}
+
+int kdf_count_bins_pass(int k, int n_parts, int n_src, int sub_split, int pass_log2, uint32_t pass_val,
+                        const uint64_t* child_bins, uint64_t child_bin_cap, const uint64_t* child_cursors,
+                        const uint64_t* ref_bins, uint64_t ref_bin_cap, const uint64_t* ref_cursors,
+                        void* slice, uint64_t slice_capacity, uint32_t min0, uint32_t max0,
+                        uint32_t min1, uint32_t max1, uint64_t* out_lo, uint64_t* out_hi,
+                        uint32_t* out_p0, uint32_t* out_p1, uint64_t out_cap, uint64_t* n_out,
+                        uint32_t count_min0, uint64_t* counters, void* stream) {
+  if (pass_log2 < 0 || pass_log2 > 16 || (pass_val >> pass_log2) != 0)
+    return fail(KDF_ERR_ARG, "kdf_count_bins: pass_val must be < 2^pass_log2, pass_log2 <= 16");
   if (!child_bins || !child_cursors || !slice || !n_out || !counters)
     return fail(KDF_ERR_ARG, "kdf_count_bins: NULL argument");
   if (n_src < 1) return fail(KDF_ERR_ARG, "kdf_count_bins: n_src must be >= 1");
@@ -2778,8 +2924,12 @@ int kdf_count_bins_multi(int k, int n_parts, int n_src, int sub_split, const uin
   t.capacity = slice_capacity;
   t.base = slice;
   t.sm_count = current_sm_count();
-  t.log2_parts = log2p + log2s;  // a slice covers one of n_parts * sub_split hash ranges
-  const int filt_log2 = sub_split > 1 ? log2p + log2s : 0;
+  // a slice covers one of 2^pass_log2 * n_parts * sub_split hash ranges: the bins hold the
+  // ranges of group pass_val (kdf_bin_stream_pass), slice pf of this call is range pass_base + pf
+  t.log2_parts = pass_log2 + log2p + log2s;
+  if (t.log2_parts > 28) return fail(KDF_ERR_ARG, "kdf_count_bins: too many hash ranges");
+  const int filt_log2 = sub_split > 1 ? t.log2_parts : 0;
+  const u32 pass_base = pass_val << (log2p + log2s);
   cudaStream_t st = (cudaStream_t)stream;
   u64* ctr = (u64*)counters;  // [0..3] = stats block (windows = keys applied, full, hits, new), [4] = #(p0 >= count_min0), [5] = #occupied
   const int kw = t.key_words;
@@ -2801,9 +2951,9 @@ int kdf_count_bins_multi(int k, int n_parts, int n_src, int sub_split, const uin
         u64 b = (u64)sidx * n_parts + p;
         const u64* cb = (const u64*)child_bins + b * child_bin_cap * kw;
         if (kw == 1)
-          rc = launch_packed_keys<1, OP_PACKED_COUNT>(&t, cb, child_bin_cap, (const u64*)child_cursors + b, sh, sat, ctr, st, filt_log2, (u32)pf);
+          rc = launch_packed_keys<1, OP_PACKED_COUNT>(&t, cb, child_bin_cap, (const u64*)child_cursors + b, sh, sat, ctr, st, filt_log2, pass_base + (u32)pf);
         else
-          rc = launch_packed_keys<2, OP_PACKED_COUNT>(&t, cb, child_bin_cap, (const u64*)child_cursors + b, sh, sat, ctr, st, filt_log2, (u32)pf);
+          rc = launch_packed_keys<2, OP_PACKED_COUNT>(&t, cb, child_bin_cap, (const u64*)child_cursors + b, sh, sat, ctr, st, filt_log2, pass_base + (u32)pf);
         if (rc != KDF_OK) return rc;
       }
       if (ref_bins && ref_cursors && !ignore_ref) {
@@ -2811,9 +2961,9 @@ int kdf_count_bins_multi(int k, int n_parts, int n_src, int sub_split, const uin
           u64 b = (u64)sidx * n_parts + p;
           const u64* rb = (const u64*)ref_bins + b * ref_bin_cap * kw;
           if (kw == 1)
-            rc = launch_packed_keys<1, OP_PACKED_MARK>(&t, rb, ref_bin_cap, (const u64*)ref_cursors + b, sh, sat, nullptr, st, filt_log2, (u32)pf);
+            rc = launch_packed_keys<1, OP_PACKED_MARK>(&t, rb, ref_bin_cap, (const u64*)ref_cursors + b, sh, sat, nullptr, st, filt_log2, pass_base + (u32)pf);
           else
-            rc = launch_packed_keys<2, OP_PACKED_MARK>(&t, rb, ref_bin_cap, (const u64*)ref_cursors + b, sh, sat, nullptr, st, filt_log2, (u32)pf);
+            rc = launch_packed_keys<2, OP_PACKED_MARK>(&t, rb, ref_bin_cap, (const u64*)ref_cursors + b, sh, sat, nullptr, st, filt_log2, pass_base + (u32)pf);
           if (rc != KDF_OK) return rc;
         }
       }
@@ -2834,9 +2984,9 @@ int kdf_count_bins_multi(int k, int n_parts, int n_src, int sub_split, const uin
       u64 b = (u64)sidx * n_parts + p;
       const u64* cb = (const u64*)child_bins + b * child_bin_cap * kw;
       if (kw == 1)
-        rc = launch_update_keys<1, OP_INSERT_COUNT>(&t, cb, nullptr, child_bin_cap, (const u64*)child_cursors + b, 0, 1, ctr, st, filt_log2, (u32)pf);
+        rc = launch_update_keys<1, OP_INSERT_COUNT>(&t, cb, nullptr, child_bin_cap, (const u64*)child_cursors + b, 0, 1, ctr, st, filt_log2, pass_base + (u32)pf);
       else
-        rc = launch_update_keys<2, OP_INSERT_COUNT>(&t, cb, nullptr, child_bin_cap, (const u64*)child_cursors + b, 0, 1, ctr, st, filt_log2, (u32)pf);
+        rc = launch_update_keys<2, OP_INSERT_COUNT>(&t, cb, nullptr, child_bin_cap, (const u64*)child_cursors + b, 0, 1, ctr, st, filt_log2, pass_base + (u32)pf);
       if (rc != KDF_OK) return rc;
     }
     if (ref_bins && ref_cursors) {
@@ -2844,9 +2994,9 @@ int kdf_count_bins_multi(int k, int n_parts, int n_src, int sub_split, const uin
         u64 b = (u64)sidx * n_parts + p;
         const u64* rb = (const u64*)ref_bins + b * ref_bin_cap * kw;
         if (kw == 1)
-          rc = launch_update_keys<1, OP_MARK_IF_PRESENT>(&t, rb, nullptr, ref_bin_cap, (const u64*)ref_cursors + b, 1, 1, nullptr, st, filt_log2, (u32)pf);
+          rc = launch_update_keys<1, OP_MARK_IF_PRESENT>(&t, rb, nullptr, ref_bin_cap, (const u64*)ref_cursors + b, 1, 1, nullptr, st, filt_log2, pass_base + (u32)pf);
         else
-          rc = launch_update_keys<2, OP_MARK_IF_PRESENT>(&t, rb, nullptr, ref_bin_cap, (const u64*)ref_cursors + b, 1, 1, nullptr, st, filt_log2, (u32)pf);
+          rc = launch_update_keys<2, OP_MARK_IF_PRESENT>(&t, rb, nullptr, ref_bin_cap, (const u64*)ref_cursors + b, 1, 1, nullptr, st, filt_log2, pass_base + (u32)pf);
         if (rc != KDF_OK) return rc;
       }
     }
@@ -2858,87 +3008,6 @@ int kdf_count_bins_multi(int k, int n_parts, int n_src, int sub_split, const uin
                                   out_cap, (u64*)n_out, count_min0, ctr + 4, ctr + 5, st);
     if (rc != KDF_OK) return rc;
   }
-  return KDF_OK;
-}
-
-size_t kdf_count_bins_smem_scratch(int n_parts, int group, int s2, uint64_t sub_cap,
-                                   uint64_t ref_sub_cap) {
-  if (group < 1 || s2 < 1) return 0;
-  if (group > n_parts) group = n_parts;
-  uint64_t n_sub = (uint64_t)group * (uint64_t)s2;
-  // child sub-bins | reference sub-bins | child cursors | reference cursors | overflow word
-  return (size_t)(n_sub * (sub_cap + ref_sub_cap) * 8 + 2 * n_sub * 8 + 64);
-}
-
-int kdf_count_bins_smem(int k, int n_parts, int n_src, const uint64_t* child_bins,
-                        uint64_t child_bin_cap, const uint64_t* child_cursors,
-                        const uint64_t* ref_bins, uint64_t ref_bin_cap, const uint64_t* ref_cursors,
-                        void* scratch, size_t scratch_bytes, int group, int s2, uint64_t sub_cap,
-                        uint64_t ref_sub_cap, uint32_t n_slots, uint32_t min0, uint32_t max1,
-                        uint32_t count_min0, uint64_t* out_lo, uint64_t out_cap, uint64_t* n_out,
-                        uint64_t* counters, uint64_t* flags, void* stream) {
-  if (!child_bins || !child_cursors || !scratch || !n_out || !counters || !flags)
-    return fail(KDF_ERR_ARG, "kdf_count_bins_smem: NULL argument");
-  if (kdf_key_words(k) != 1) return fail(KDF_ERR_ARG, "kdf_count_bins_smem: 64-bit keys only (k <= 32)");
-  if (!kdf_count_bins_packed(k, min0, 0xffffffffu, 0, max1, count_min0, 0))
-    return fail(KDF_ERR_ARG, "kdf_count_bins_smem: thresholds do not fit the packed form");
-  if (n_src < 1) return fail(KDF_ERR_ARG, "kdf_count_bins_smem: n_src must be >= 1");
-  int log2p = 0, log2s = 0;
-  while ((1 << log2p) < n_parts) ++log2p;
-  while ((1 << log2s) < s2) ++log2s;
-  if (n_parts < 1 || n_parts > BIN_MAX_PARTS || (1 << log2p) != n_parts)
-    return fail(KDF_ERR_ARG, "kdf_count_bins_smem: n_parts must be a power of two <= 512");
-  if (s2 < 2 || s2 > BIN_MAX_PARTS || (1 << log2s) != s2 || log2p + log2s > 28)
-    return fail(KDF_ERR_ARG, "kdf_count_bins_smem: s2 must be a power of two in 2..512");
-  if (n_slots < 256 || (n_slots & (n_slots - 1)) || (size_t)n_slots * 8 > 200 * 1024)
-    return fail(KDF_ERR_ARG, "kdf_count_bins_smem: n_slots must be a power of two, 256..25600");
-  if (group < 1) group = 1;
-  if (group > n_parts) group = n_parts;
-  if (sub_cap < 1 || scratch_bytes < kdf_count_bins_smem_scratch(n_parts, group, s2, sub_cap, ref_sub_cap))
-    return fail(KDF_ERR_ARG, "kdf_count_bins_smem: scratch too small");
-  if (((uintptr_t)scratch & 15) != 0) return fail(KDF_ERR_ARG, "kdf_count_bins_smem: scratch must be 16-byte aligned");
-  const bool with_ref = ref_bins && ref_cursors && ref_sub_cap > 0 && max1 == 0;
-  const u64 n_sub_max = (u64)group * s2;
-  u64* sub = (u64*)scratch;
-  u64* rsub = sub + n_sub_max * sub_cap;
-  u64* cur = rsub + n_sub_max * ref_sub_cap;
-  u64* rcur = cur + n_sub_max;
-  u64* over = rcur + n_sub_max;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int sm = current_sm_count();
-  const int sh = 2 * k;
-  const int qcap = bin_qcap(s2, 1);
-  const size_t bin_smem = BinStage<1>::bytes(s2, qcap);
-  const size_t tab_smem = (size_t)n_slots * 8;
-  CUDA_TRY(cudaFuncSetAttribute((const void*)k_rebin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem));
-  CUDA_TRY(cudaFuncSetAttribute((const void*)k_count_sub, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_smem));
-  int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k_rebin, BIN_THREADS, bin_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-  const int g_rebin = sm * per_sm;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k_count_sub, SUB_THREADS, tab_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-  const int g_count = sm * per_sm;
-  CUDA_TRY(cudaMemsetAsync(over, 0, 64, st));
-  for (int p0 = 0; p0 < n_parts; p0 += group) {
-    const int pc = (n_parts - p0) < group ? (n_parts - p0) : group;
-    const u32 n_sub = (u32)pc * (u32)s2;
-    CUDA_TRY(cudaMemsetAsync(cur, 0, 2 * n_sub_max * 8, st));   // both cursor arrays
-    k_rebin<<<g_rebin, BIN_THREADS, bin_smem, st>>>((const u64*)child_bins, child_bin_cap, (const u64*)child_cursors,
-                                                    n_parts, n_src, p0, pc, log2p + log2s, (u32)s2, qcap, sub,
-                                                    sub_cap, cur, over);
-    if (with_ref)
-      k_rebin<<<g_rebin, BIN_THREADS, bin_smem, st>>>((const u64*)ref_bins, ref_bin_cap, (const u64*)ref_cursors,
-                                                      n_parts, n_src, p0, pc, log2p + log2s, (u32)s2, qcap,
-                                                      rsub, ref_sub_cap, rcur, over);
-    int g = (int)((u32)g_count < n_sub ? (u32)g_count : n_sub);
-    k_count_sub<<<g, SUB_THREADS, tab_smem, st>>>(sub, sub_cap, cur, with_ref ? rsub : nullptr, ref_sub_cap, rcur,
-                                                  n_sub, n_slots, sh, min0, max1 != 0 ? 1 : 0,
-                                                  count_min0 <= 1 ? 1 : 0, (u64*)out_lo, out_cap, (u64*)n_out,
-                                                  (u64*)counters, (u64*)flags);
-    CUDA_TRY(cudaGetLastError());
-  }
-  // a sub-bin that overflowed its region: bit 1 of flags (read back by the caller)
-  k_or_flag<<<1, 1, 0, st>>>(over, (u64*)flags, 2ull);
-  CUDA_TRY(cudaGetLastError());
   return KDF_OK;
 }
 
@@ -3029,6 +3098,37 @@ int kdf_debug_extract_host(const uint64_t* codes, const uint32_t* valid, uint64_
   v.n_words = (n_bases + 31) / 32;
   v.w_begin = 0;
   v.w_end = v.n_words;
+  if (use_random_access >= 2) {
+    // the chunked iterator of the stream kernels: 2 = chunks of 4 windows, 3 = chunks of 16
+    for (u64 w = 0; w < v.n_words; ++w) {
+      auto run = [&](auto& it) {
+        for (int j0 = 0; j0 < 32;) {
+          const int cn = use_random_access == 2 ? 4 : 16;
+          for (int u = 0; u < cn; ++u) {
+            u64 p = (w << 5) + j0 + u;
+            auto c = it.key(u);
+            bool ok = it.ok(u);
+            if (p < n_bases) {
+              out_lo[p] = ok ? c.lo : 0;
+              if (out_hi) out_hi[p] = ok ? ((const u64*)&c)[sizeof(c) / 8 - 1] : 0;
+              out_ok[p] = ok;
+            }
+          }
+          if (cn == 4) it.template next<4>(); else it.template next<16>();
+          j0 += cn;
+        }
+      };
+      if (kw == 1) {
+        WindowChunks<1> it(v, w, k);
+        run(it);
+        if (out_hi) for (u64 p = w << 5; p < n_bases && p < (w << 5) + 32; ++p) out_hi[p] = 0;
+      } else {
+        WindowChunks<2> it(v, w, k);
+        run(it);
+      }
+    }
+    return KDF_OK;
+  }
   for (u64 w = 0; w < v.n_words; ++w) {
     if (kw == 1) {
       WindowIter<1> it(v, w, k);

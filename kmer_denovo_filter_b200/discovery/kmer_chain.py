@@ -86,7 +86,8 @@ def default_child_capacity(eng, n_bases):
 # load 0.56 (64 bins) 32.6 ms, 128 MB 44 ms (the slice no longer fits).
 SLICE_BYTES = int(os.environ.get("KDF_SLICE_MB", "64")) << 20
 MAX_PARTS = 256
-SMEM_PARTS = int(os.environ.get("KDF_SMEM_PARTS", "256"))   # hash ranges in front of the shared-memory count
+# table slots per k-mer instance: 30x data holds ~12 instances per distinct k-mer
+SLOTS_DIV = int(os.environ.get("KDF_COUNT_SLOTS_DIV", "8"))
 
 
 def _pow2_at_least(x):
@@ -96,16 +97,24 @@ def _pow2_at_least(x):
     return p
 
 
-def plan_partitions(n_windows_max, slots_needed=None, key_words=1, packed=False):
+def _as_list(x):
+    if x is None:
+        return []
+    return list(x) if isinstance(x, (list, tuple)) else [x]
+
+
+def plan_partitions(n_windows_max, slots_needed=None, key_words=1, packed=False, max_parts=MAX_PARTS):
     """(n_parts, slice_capacity) for about ``slots_needed`` table slots in total.
     Default sizing: 8 bases per distinct k-mer (30x data holds ~14); a slice that
     turns out too small is reported by the kernel and the pass is redone.
     ``packed``: the slice holds keys only (``CudaEngine.count_bins_packed``), so the
     same L2 budget covers twice the slots and half as many bins are needed."""
     if slots_needed is None:
-        slots_needed = max(n_windows_max // 8, 1024)
+        slots_needed = max(n_windows_max // SLOTS_DIV, 1024)
     slice_slots = SLICE_BYTES // (8 * key_words + (0 if packed else 8))
-    n_parts = min(MAX_PARTS, _pow2_at_least((slots_needed + slice_slots - 1) // slice_slots))
+    n_parts = _pow2_at_least((slots_needed + slice_slots - 1) // slice_slots)
+    if max_parts:
+        n_parts = min(max_parts, n_parts)
     slice_cap = max(1024, (slots_needed + n_parts - 1) // n_parts)
     return n_parts, (slice_cap + 3) & ~3
 
@@ -121,80 +130,141 @@ def _bin_capacity(n_keys_max, n_parts):
     return int(mean * 1.04 + 64 * (mean ** 0.5) + 1024)
 
 
+def bin_budget_bytes(eng):
+    """Device memory the bins of one counting pass may take: ``KDF_BIN_BUDGET_GB``, else
+    half of what is free on the device now (free + the allocator's cached blocks)."""
+    env = os.environ.get("KDF_BIN_BUDGET_GB")
+    if env:
+        return int(float(env) * (1 << 30))
+    fn = getattr(eng, "free_device_bytes", None)
+    return int(fn() * 0.5) if fn is not None else 1 << 62
+
+
+def plan_child_count(eng, n_child, n_ref, k, min_child_count, n_parts=None, slice_capacity=None,
+                     n_passes=None, max_local=MAX_PARTS):
+    """How the child count of ``n_child`` k-mer instances (+ ``n_ref`` reference ones) is
+    laid out: ``(n_passes, n_local, slice_capacity)``.  The hash space is cut into
+    ``n_passes * n_local`` ranges, each counted in one L2-sized table slice; a pass
+    re-extracts the streams and bins only its own ``n_local`` ranges, so the bins of a
+    pass hold ``1 / n_passes`` of the k-mers.  One pass when the bins of the whole sample
+    fit :func:`bin_budget_bytes` and ``max_local`` ranges are enough — which is what
+    Jellyfish's sized hash + spill/merge does for the reference
+    (``core/jellyfish_wrappers.py:73-107, 335-366``)."""
+    kw = eng.lib.kdf_key_words(k)
+    packed = eng.count_bins_packed(k, min_child_count)
+    n_total, s_auto = plan_partitions(n_child, key_words=kw, packed=packed, max_parts=0)
+    if n_parts is not None:
+        n_total = n_parts * (n_passes or 1)
+    if n_passes is None:
+        need = (n_child + n_ref) * 1.06 * 8 * kw
+        n_passes = _pow2_at_least(int(-(-need // max(bin_budget_bytes(eng), 1))))
+        n_passes = max(n_passes, n_total // max_local)
+    n_total = max(n_total, n_passes)
+    n_local = n_total // n_passes
+    if slice_capacity is None:
+        slots = max(n_child // SLOTS_DIV, 1024)
+        slice_capacity = (max(1024, -(-slots // n_total)) + 3) & ~3
+    return n_passes, n_local, slice_capacity
+
+
+def _wait_ready(eng, s):
+    if getattr(s, "ready", None) is not None:
+        eng.torch.cuda.current_stream(eng.device).wait_event(s.ready)
+
+
+def _bin_into(eng, bins, streams, stats, pass_):
+    for s in streams:
+        if getattr(s, "chunks", None):
+            main = eng.torch.cuda.current_stream(eng.device)
+            for first, n, ev in s.chunks:      # bin a chunk as soon as it has landed
+                main.wait_event(ev)
+                eng.bin_stream(bins, s, stats, word_range=(first, n), pass_=pass_)
+        else:
+            _wait_ready(eng, s)
+            eng.bin_stream(bins, s, stats, pass_=pass_)
+
+
 def count_child_partitioned(eng, child_streams, ref_streams, k, min_child_count,
-                            n_parts=None, slice_capacity=None):
+                            n_parts=None, slice_capacity=None, n_passes=None):
     """Module 1 + reference subtraction without a table in HBM: bin the child's
     (and the reference's) canonical k-mers by hash range, then count each bin in
     an L2-resident table slice and emit the keys with count >= min_child_count
-    that are not in the reference.
+    that are not in the reference.  When the bins of the whole sample would not fit
+    the device the hash ranges are taken in several passes (:func:`plan_child_count`).
 
     ``child_streams`` / ``ref_streams``: lists of DeviceStream.  Returns dict:
     child_windows, ref_windows, child_distinct, candidates, non_ref, lo, hi."""
+    torch = eng.torch
     n_max = sum(s.n_bases for s in child_streams)
     r_max = sum(s.n_bases for s in ref_streams)
-    p_auto, s_auto = plan_partitions(n_max, key_words=eng.lib.kdf_key_words(k),
-                                     packed=eng.count_bins_packed(k, min_child_count))
-    # 64-bit keys: shared-memory count (kdf_count_bins_smem) — as many hash ranges as the
-    # binning kernel handles well, the rest of the split is its second level
-    smem = (n_parts is None and slice_capacity is None and eng.count_bins_smem_ok(k, min_child_count))
-    if smem:
-        p_auto = max(p_auto, min(SMEM_PARTS, _pow2_at_least(n_max // (eng.SUB_TARGET * 256) + 1)))
-        s_auto = max(1024, (max(n_max // 8, 1024) + p_auto - 1) // p_auto + 3) & ~3
-    n_parts = n_parts or p_auto
-    slice_capacity = slice_capacity or s_auto
-    bin_cap = _bin_capacity(n_max, n_parts)
-    ref_cap = _bin_capacity(r_max, n_parts)
-    while True:   # bins: retry with exact sizes if the hash ranges are skewed
-        cb = eng.new_bins(k, n_parts, bin_cap)
-        rb = eng.new_bins(k, n_parts, ref_cap) if ref_streams else None
-        st_c, st_r = eng.new_stats(), eng.new_stats()
-        for s in child_streams:
-            if getattr(s, "chunks", None):
-                main = eng.torch.cuda.current_stream(eng.device)
-                for first, n, ev in s.chunks:      # bin a chunk as soon as it has landed
-                    main.wait_event(ev)
-                    eng.bin_stream(cb, s, st_c, word_range=(first, n))
+    n_passes, n_local, slice_capacity = plan_child_count(
+        eng, n_max, r_max, k, min_child_count, n_parts, slice_capacity, n_passes)
+    plog = n_passes.bit_length() - 1
+    if (1 << plog) != n_passes:
+        raise _engine.KdfError("the number of counting passes must be a power of two")
+    bin_cap = _bin_capacity(n_max / n_passes, n_local)
+    ref_cap = _bin_capacity(r_max / n_passes, n_local)
+    out_cap = max(1 << 16, n_max // 64 // n_passes)
+    st_c, st_r = eng.new_stats(), eng.new_stats()
+    cb = rb = None
+    tot = {"distinct": 0, "n_count": 0, "n_out": 0}
+    los, his = [], []
+    for p in range(n_passes):
+        pass_ = (plog, p) if n_passes > 1 else None
+        while True:   # bins: retry with exact sizes if the hash ranges are skewed
+            if cb is None:
+                cb = eng.new_bins(k, n_local, bin_cap)
+            if rb is None and ref_streams:
+                rb = eng.new_bins(k, n_local, ref_cap)
+            st_c1, st_r1 = eng.new_stats(), eng.new_stats()
+            _bin_into(eng, cb, child_streams, st_c1, pass_)
+            if rb is not None:
+                _bin_into(eng, rb, ref_streams, st_r1, pass_)
+            over_c = cb.overflowed()
+            over_r = rb.overflowed() if rb is not None else False
+            if not over_c and not over_r:
+                st_c += st_c1
+                st_r += st_r1
+                break
+            if over_c:
+                bin_cap = int(cb.counts().max()) + 4
+                cb = None
             else:
-                if getattr(s, "ready", None) is not None:
-                    eng.torch.cuda.current_stream(eng.device).wait_event(s.ready)
-                eng.bin_stream(cb, s, st_c)
-        for s in ref_streams:
-            if getattr(s, "ready", None) is not None:
-                eng.torch.cuda.current_stream(eng.device).wait_event(s.ready)
-            eng.bin_stream(rb, s, st_r)
-        over_c = cb.overflowed()
-        over_r = rb.overflowed() if rb is not None else False
-        if not over_c and not over_r:
-            break
-        if over_c:
-            bin_cap = int(cb.counts().max()) + 4
-        if over_r:
-            ref_cap = int(rb.counts().max()) + 4
-        del cb, rb
-    out_cap = max(1 << 16, n_max // 64)
-    while True:   # slices / output: retry when a slice was full or the output too small
-        res = None
-        if smem:
-            res = eng.count_bins_smem(cb, rb, min_child_count, max1=0, out_cap=out_cap)
-            if res["fallback"]:      # a sub-bin did not fit shared memory: L2 form, same bins
-                smem, res = False, None
-        if res is None:
+                cb.reset()
+            if over_r:
+                ref_cap = int(rb.counts().max()) + 4
+                rb = None
+            elif rb is not None:
+                rb.reset()
+        while True:   # slices / output: retry when a slice was full or the output too small
             res = eng.count_bins(cb, rb, slice_capacity, min0=min_child_count, max1=0,
-                                 count_min0=min_child_count, out_cap=out_cap)
-        if res["full"]:
-            if slice_capacity >= 2 * bin_cap:
-                raise _engine.KdfError("child k-mer table slice full at %d slots" % slice_capacity)
-            slice_capacity = min(slice_capacity * 4, 2 * bin_cap + 4)
-            continue
-        if res["n_out"] > out_cap:
-            out_cap = res["n_out"]
-            continue
-        break
+                                 count_min0=min_child_count, out_cap=out_cap, pass_=pass_)
+            if res["full"]:
+                if slice_capacity >= 2 * bin_cap:
+                    raise _engine.KdfError("child k-mer table slice full at %d slots" % slice_capacity)
+                slice_capacity = min(slice_capacity * 4, 2 * bin_cap + 4)
+                continue
+            if res["n_out"] > out_cap:
+                out_cap = res["n_out"]
+                continue
+            break
+        for key in tot:
+            tot[key] += res[key]
+        los.append(res["lo"])
+        if res["hi"] is not None:
+            his.append(res["hi"])
+        if p + 1 < n_passes:
+            cb.reset()
+            if rb is not None:
+                rb.reset()
+    del cb, rb
+    lo = los[0] if len(los) == 1 else torch.cat(los)
+    hi = (his[0] if len(his) == 1 else torch.cat(his)) if his else None
     return {"child_windows": eng.read_stats(st_c)["windows"],
             "ref_windows": eng.read_stats(st_r)["windows"] if ref_streams else 0,
-            "child_distinct": res["distinct"], "candidates": res["n_count"],
-            "non_ref": res["n_out"], "lo": res["lo"], "hi": res["hi"],
-            "n_parts": n_parts, "slice_capacity": slice_capacity}
+            "child_distinct": tot["distinct"], "candidates": tot["n_count"],
+            "non_ref": tot["n_out"], "lo": lo, "hi": hi,
+            "n_parts": n_local, "n_passes": n_passes, "slice_capacity": slice_capacity}
 
 
 # A parent stream is probed against a read-only table (``count --if``).  While the
@@ -208,8 +278,15 @@ PROBE_CHUNK_BASES = 1 << 30      # bins of one chunk: <= 8.6 GB (64-bit keys)
 
 
 def count_if_present(eng, table, d_stream, stats, plane=0, arg=1):
-    """``jellyfish count --if`` of one parent stream (discovery/pipeline.py:377-386).
+    """``jellyfish count --if`` of one parent stream, or of a list of streams that
+    together are the parent (discovery/pipeline.py:377-386).
     → True when the stream was binned first (the large-table route)."""
+    if isinstance(d_stream, (list, tuple)):
+        binned = False
+        for s in d_stream:
+            _wait_ready(eng, s)
+            binned = count_if_present(eng, table, s, stats, plane, arg) or binned
+        return binned
     key_bytes = table.capacity * 8 * table.key_words
     if (key_bytes <= PROBE_DIRECT_BYTES or getattr(table, "filter_buf", None) is not None
             or os.environ.get("KDF_PROBE_DIRECT") == "1"):
@@ -260,10 +337,30 @@ def _primed_table(eng, k, lo, hi, n):
     return t
 
 
+def merge_sparse_records(parts, streams):
+    """Per-read records of several streams of one sample (``scan_reads_sparse`` each) as
+    one record set: read indices, hit positions and ``first`` continue from one stream to
+    the next (stream i starts at read sum(n_reads[:i]), base sum(n_bases[:i]))."""
+    if len(parts) == 1:
+        return parts[0]
+    out = {key: [] for key in parts[0]}
+    r0 = b0 = h0 = 0
+    for sp, d in zip(parts, streams):
+        out["read"].append(sp["read"] + np.uint64(r0))
+        out["first"].append(sp["first"] + np.uint64(h0))
+        out["hit_pos"].append(sp["hit_pos"] + np.uint64(b0))
+        for key in ("ndistinct", "nhits", "hit_slot"):
+            out[key].append(sp[key])
+        r0 += d.n_reads
+        b0 += d.n_bases
+        h0 += int(sp["hit_pos"].shape[0])
+    return {key: np.concatenate(v) for key, v in out.items()}
+
+
 def discover_streams(eng, child, mother, father, ref, k, min_child_count=3,
                      parent_max_count=0, min_distinct_kmers_per_read=None,
                      child_capacity=None, want_hits=False, fetch=True, partitioned=None,
-                     sparse_scan=True):
+                     sparse_scan=True, n_passes=None):
     """Child count → threshold → reference subtraction → mother / father
     filtered counts → proband-unique set → per-read distinct-hit reduction.
 
@@ -278,27 +375,39 @@ def discover_streams(eng, child, mother, father, ref, k, min_child_count=3,
         partitioned = child_capacity is None
     stats = eng.new_stats()
     up = _Uploader(eng)
+    # a sample may come as a list of streams (a whole-genome sample exceeds the 2^32
+    # bases one stream's sparse validity list can address): lists take the partitioned,
+    # sparse-scan route
+    multi = any(isinstance(x, (list, tuple)) for x in (child, mother, father, ref))
+    if multi and not (partitioned and sparse_scan):
+        raise _engine.KdfError("lists of streams need partitioned=True and sparse_scan=True")
     # copy order = consumption order: child (in chunks, binned as they land), ref, mother,
     # father, and last the child's read index (12 bytes per read, needed by the scan only:
     # ahead of the parents it delayed the father's arrival, which the chain waits for)
     if partitioned:
-        d_child, ev_child = up.put_chunked(child, False)
-        d_ref, ev_ref = up.put(ref, False)
+        d_childs = [up.put_chunked(x, False)[0] for x in _as_list(child)]
+        d_refs = [up.put(x, False)[0] for x in _as_list(ref)]
+        d_child, d_ref = d_childs[0], (d_refs[0] if d_refs else None)
+        ev_child = None     # every stream carries its own `ready` event
     else:
         d_child, ev_child = up.put(child, True)
         d_ref, ev_ref = up.put(ref, False)
         up.wait(ev_child)
         up.wait(ev_ref)
-    d_mother, ev_mother = up.put(mother, False)
-    d_father, ev_father = up.put(father, False)
-    ev_reads = up.put_read_index(d_child, child) if partitioned else None
+        d_childs, d_refs = [d_child], [d_ref]
+    d_mothers = [up.put(x, False)[0] for x in _as_list(mother)]
+    d_fathers = [up.put(x, False)[0] for x in _as_list(father)]
+    d_mother, d_father = d_mothers, d_fathers
+    ev_mother = ev_father = None
+    ev_reads = ([up.put_read_index(d, h) for d, h in zip(d_childs, _as_list(child))]
+                if partitioned else [])
 
     # Module 1 + reference subtraction: jellyfish count -C ; dump -L ; query ref.jf
     if partitioned:
-        c = count_child_partitioned(eng, [d_child], [d_ref], k, min_child_count)
+        c = count_child_partitioned(eng, d_childs, d_refs, k, min_child_count, n_passes=n_passes)
         n_cand, n_nonref, lo, hi = c["candidates"], c["non_ref"], c["lo"], c["hi"]
         child_windows, child_distinct = c["child_windows"], c["child_distinct"]
-        child_capacity = c["n_parts"] * c["slice_capacity"]
+        child_capacity = c["n_passes"] * c["n_parts"] * c["slice_capacity"]
         units_binned = c["child_windows"] + c["ref_windows"]
     else:
         # direct form: one table in HBM, sized for 4 bases per distinct k-mer; when
@@ -327,6 +436,7 @@ def discover_streams(eng, child, mother, father, ref, k, min_child_count=3,
         table.close()
     out = {"child_windows": child_windows, "child_distinct": child_distinct,
            "child_capacity": child_capacity, "candidates": n_cand,
+           "n_passes": c["n_passes"] if partitioned else 1,
            "non_ref": n_nonref, "after_mother": 0, "proband_unique": 0,
            "pu": None, "ndistinct": None, "nhits": None, "informative_reads": 0, "hits": None,
            "reads": None, "parents_binned": []}
@@ -353,16 +463,22 @@ def discover_streams(eng, child, mother, father, ref, k, min_child_count=3,
         out["pu"] = KmerSet(eng, k, lo, hi)
         pt = _primed_table(eng, k, lo, hi, n_pu)
         up.wait(ev_child)
-        up.wait(ev_reads)
+        for ev in ev_reads:
+            up.wait(ev)
         if sparse_scan:
             # hits are rare: emit them from a streaming probe, reduce per read on the
             # device, return one record per read that has hits
-            sp = eng.scan_reads_sparse(pt, d_child, stats=stats)
+            parts = []
+            for d in d_childs:
+                _wait_ready(eng, d)
+                parts.append(eng.scan_reads_sparse(pt, d, stats=stats))
+            sp = merge_sparse_records(parts, d_childs)
             out["reads"] = sp
             out["informative_reads"] = int((sp["ndistinct"] >= min_distinct_kmers_per_read).sum())
             if fetch:
-                nd = np.zeros(d_child.n_reads, dtype=np.uint32)
-                nh = np.zeros(d_child.n_reads, dtype=np.uint32)
+                n_reads = sum(d.n_reads for d in d_childs)
+                nd = np.zeros(n_reads, dtype=np.uint32)
+                nh = np.zeros(n_reads, dtype=np.uint32)
                 nd[sp["read"].astype(np.int64)] = sp["ndistinct"]
                 nh[sp["read"].astype(np.int64)] = sp["nhits"]
                 out["ndistinct"], out["nhits"] = nd, nh

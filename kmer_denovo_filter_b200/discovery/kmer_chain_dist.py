@@ -70,21 +70,27 @@ def allgather_varlen(torch, t, world):
 # stages
 # ---------------------------------------------------------------------------
 
-def route_to_owners(eng, streams, k, world):
+def route_to_owners(eng, streams, k, world, pass_=None, n_passes=1):
     """K6 + all-to-all: the canonical k-mers of this rank's ``streams`` go to their
-    owner ranks.  Returns ``(recv, recv_counts, bin_cap, windows)``: ``recv`` holds
-    ``world`` segments of ``bin_cap`` keys (u64, or {lo, hi} pairs for k > 32),
-    segment r = keys sent by rank r of which the first ``recv_counts[r]`` are valid."""
+    owner ranks (with ``pass_`` only those of one hash-range group, see
+    ``kmer_chain.plan_child_count``).  Returns ``(recv, recv_counts, bin_cap, windows)``:
+    ``recv`` holds ``world`` segments of ``bin_cap`` keys (u64, or {lo, hi} pairs for
+    k > 32), segment r = keys sent by rank r of which the first ``recv_counts[r]`` are valid."""
     torch = eng.torch
     n_max = sum(s.n_bases for s in streams)
-    cap = torch.tensor([_kc._bin_capacity(max(n_max, 1), world)], dtype=torch.int64, device=eng.device)
+    cap = torch.tensor([_kc._bin_capacity(max(n_max, 1) / n_passes, world)], dtype=torch.int64,
+                       device=eng.device)
     allreduce(cap, "max")          # every rank must use the same segment size
     bin_cap = (int(cap.item()) + 3) & ~3
     while True:
         bins = eng.new_bins(k, world, bin_cap, by_owner=True)
         st = eng.new_stats()
         for s in streams:
-            eng.bin_stream(bins, s, st)
+            _kc._wait_ready(eng, s)
+            if pass_ is None:
+                eng.bin_stream(bins, s, st)
+            else:
+                eng.bin_stream(bins, s, st, pass_=pass_)
         need = torch.stack([bins.cursors.max() if world else bins.cursors.new_zeros(()),
                             bins.overflow[0]]).to(torch.int64)
         allreduce(need, "max")
@@ -144,7 +150,7 @@ class RecvBins:
         self.data, self.cursors = data, cursors
 
 
-def route_composite_p2p(eng, streams, k, world, role, n_local, n_expected):
+def route_composite_p2p(eng, streams, k, world, role, n_local, n_expected, pass_=None, seg_cap=None):
     """K6 fused with the exchange AND with the owner's hash-range binning: one kernel
     per rank extracts its k-mers, picks (owner, hash range) and writes each key into
     bin [this rank][range] of the owner's receive buffer through NVLink peer pointers
@@ -155,7 +161,8 @@ def route_composite_p2p(eng, streams, k, world, role, n_local, n_expected):
     rank = dist.get_rank()
     kw = eng.lib.kdf_key_words(k)
     n_bins = world * n_local
-    seg_cap = (_kc._bin_capacity(max(n_expected, 1), n_bins) + 3) & ~3
+    if seg_cap is None:
+        seg_cap = (_kc._bin_capacity(max(n_expected, 1), n_bins) + 3) & ~3
     while True:
         recv, hdl = _symm_buffer(eng, role, n_bins * seg_cap * kw)
         base = [int(hdl.buffer_ptrs[o]) for o in range(world)]
@@ -172,11 +179,12 @@ def route_composite_p2p(eng, streams, k, world, role, n_local, n_expected):
                 for first, n, ev in s.chunks:
                     main.wait_event(ev)
                     eng.bin_stream_to(s, k, ptrs, seg_cap, cursors, overflow, by_owner=world,
-                                      stats=st, word_range=(first, n))
+                                      stats=st, word_range=(first, n), pass_=pass_)
             else:
                 if getattr(s, "ready", None) is not None:
                     main.wait_event(s.ready)
-                eng.bin_stream_to(s, k, ptrs, seg_cap, cursors, overflow, by_owner=world, stats=st)
+                eng.bin_stream_to(s, k, ptrs, seg_cap, cursors, overflow, by_owner=world, stats=st,
+                                  pass_=pass_)
         hdl.barrier(channel=1)          # every peer's writes into this rank's buffer have landed
         need = torch.stack([cursors.max(), overflow[0]]).to(torch.int64)
         allreduce(need, "max")
@@ -195,87 +203,98 @@ def _segments(recv, counts, bin_cap, kw):
             yield recv[r * bin_cap * kw:(r * bin_cap + n) * kw], int(n)
 
 
-def count_child_dist(eng, child_streams, ref_streams, k, min_child_count, world):
+def _agree_max(eng, *vals):
+    t = eng.torch.tensor(list(vals), dtype=eng.torch.int64, device=eng.device)
+    allreduce(t, "max")
+    return [int(x) for x in t.tolist()]
+
+
+def count_child_dist(eng, child_streams, ref_streams, k, min_child_count, world, n_passes=None):
     """Module 1 + reference subtraction with the table partitioned by owner rank.
     Returns dict(child_windows, ref_windows, child_distinct, candidates, non_ref — all
-    LOCAL to this rank — and lo, hi: this owner's non-reference candidates)."""
+    LOCAL to this rank — and lo, hi: this owner's non-reference candidates).  The hash
+    ranges of an owner are taken in ``n_passes`` groups when what a rank would receive
+    in one go does not fit its memory (``kmer_chain.plan_child_count``; every rank
+    uses the same plan)."""
     kw = eng.lib.kdf_key_words(k)
-    if peer_memory_available(eng):
-        return _count_child_fused(eng, child_streams, ref_streams, k, min_child_count, world, kw)
-    c_recv, c_counts, c_cap, c_win = route_to_owners(eng, child_streams, k, world)
-    r_recv, r_counts, r_cap, r_win = route_to_owners(eng, ref_streams, k, world)
-    n_child = int(c_counts.sum())
-    n_ref = int(r_counts.sum())
-    n_parts, slice_capacity = _kc.plan_partitions(max(n_child, 1), key_words=kw,
-                                                  packed=eng.count_bins_packed(k, min_child_count))
-    bin_cap = _kc._bin_capacity(max(n_child, 1), n_parts)
-    ref_cap = _kc._bin_capacity(max(n_ref, 1), n_parts)
-    while True:
-        cb = eng.new_bins(k, n_parts, bin_cap)
-        rb = eng.new_bins(k, n_parts, ref_cap)
-        for seg, n in _segments(c_recv, c_counts, c_cap, kw):
-            eng.bin_keys(cb, seg, None, n)
-        for seg, n in _segments(r_recv, r_counts, r_cap, kw):
-            eng.bin_keys(rb, seg, None, n)
-        oc, orf = cb.overflowed(), rb.overflowed()
-        if not oc and not orf:
+    fused = peer_memory_available(eng)
+    n_child_exp, n_ref_exp = _agree_max(eng, sum(s.n_bases for s in child_streams),
+                                        sum(s.n_bases for s in ref_streams))
+    # weak scaling: a rank receives about what it sends.  The fused route takes at most
+    # 512 (owner x range) bins per pass
+    max_local = max(1, 512 // _kc._pow2_at_least(world)) if fused else _kc.MAX_PARTS
+    plan = _kc.plan_child_count(eng, max(n_child_exp, 1), n_ref_exp, k, min_child_count,
+                                n_passes=n_passes, max_local=max_local)
+    n_passes, n_local, slice_capacity = _agree_max(eng, *plan)
+    n_total = _kc._pow2_at_least(n_passes * n_local)
+    n_passes = _kc._pow2_at_least(n_passes)
+    n_local = max(1, n_total // n_passes)
+    plog = n_passes.bit_length() - 1
+    tot = {"distinct": 0, "n_count": 0, "n_out": 0}
+    c_win = r_win = 0
+    los, his = [], []
+    seg_c = seg_r = None
+    for p in range(n_passes):
+        pass_ = (plog, p) if n_passes > 1 else None
+        if fused:
+            cb, w1 = route_composite_p2p(eng, child_streams, k, world, "child", n_local,
+                                         n_child_exp // n_passes, pass_, seg_c)
+            rb, w2 = route_composite_p2p(eng, ref_streams, k, world, "ref", n_local,
+                                         n_ref_exp // n_passes, pass_, seg_r)
+            seg_c, seg_r = cb.bin_cap, rb.bin_cap       # sizes that worked: keep them
+            n_child = int(cb.cursors.sum().item())
+            cap_limit = 2 * cb.bin_cap * world
+        else:
+            c_recv, c_counts, c_cap, w1 = route_to_owners(eng, child_streams, k, world, pass_, n_passes)
+            r_recv, r_counts, r_cap, w2 = route_to_owners(eng, ref_streams, k, world, pass_, n_passes)
+            n_child = int(c_counts.sum())
+            n_ref = int(r_counts.sum())
+            bin_cap = _kc._bin_capacity(max(n_child, 1), n_local)
+            ref_cap = _kc._bin_capacity(max(n_ref, 1), n_local)
+            while True:
+                cb = eng.new_bins(k, n_local, bin_cap)
+                rb = eng.new_bins(k, n_local, ref_cap)
+                for seg, n in _segments(c_recv, c_counts, c_cap, kw):
+                    eng.bin_keys(cb, seg, None, n, pass_=pass_)
+                for seg, n in _segments(r_recv, r_counts, r_cap, kw):
+                    eng.bin_keys(rb, seg, None, n, pass_=pass_)
+                oc, orf = cb.overflowed(), rb.overflowed()
+                if not oc and not orf:
+                    break
+                if oc:
+                    bin_cap = int(cb.counts().max()) + 4
+                if orf:
+                    ref_cap = int(rb.counts().max()) + 4
+                del cb, rb
+            del c_recv, r_recv
+            cap_limit = 2 * bin_cap
+        c_win += w1
+        r_win += w2
+        out_cap = max(1 << 16, n_child // 64)
+        while True:
+            res = eng.count_bins(cb, rb, slice_capacity, min0=min_child_count, max1=0,
+                                 count_min0=min_child_count, out_cap=out_cap, pass_=pass_)
+            if res["full"]:
+                if slice_capacity >= cap_limit:
+                    raise _engine.KdfError("child k-mer table slice full at %d slots" % slice_capacity)
+                slice_capacity = min(slice_capacity * 4, cap_limit + 4)
+                continue
+            if res["n_out"] > out_cap:
+                out_cap = res["n_out"]
+                continue
             break
-        if oc:
-            bin_cap = int(cb.counts().max()) + 4
-        if orf:
-            ref_cap = int(rb.counts().max()) + 4
+        for key in tot:
+            tot[key] += res[key]
+        los.append(res["lo"])
+        if res["hi"] is not None:
+            his.append(res["hi"])
         del cb, rb
-    del c_recv, r_recv
-    out_cap = max(1 << 16, n_child // 64)
-    while True:
-        res = eng.count_bins(cb, rb, slice_capacity, min0=min_child_count, max1=0,
-                             count_min0=min_child_count, out_cap=out_cap)
-        if res["full"]:
-            if slice_capacity >= 2 * bin_cap:
-                raise _engine.KdfError("child k-mer table slice full at %d slots" % slice_capacity)
-            slice_capacity = min(slice_capacity * 4, 2 * bin_cap + 4)
-            continue
-        if res["n_out"] > out_cap:
-            out_cap = res["n_out"]
-            continue
-        break
-    return {"child_windows": c_win, "ref_windows": r_win, "child_distinct": res["distinct"],
-            "candidates": res["n_count"], "non_ref": res["n_out"], "lo": res["lo"], "hi": res["hi"]}
-
-
-def _count_child_fused(eng, child_streams, ref_streams, k, min_child_count, world, kw):
-    """count_child_dist over NVLink peer memory (see route_composite_p2p)."""
     torch = eng.torch
-    n_exp = torch.tensor([sum(s.n_bases for s in child_streams), sum(s.n_bases for s in ref_streams)],
-                         dtype=torch.int64, device=eng.device)
-    allreduce(n_exp, "max")              # weak scaling: a rank receives about what it sends
-    n_child_exp, n_ref_exp = int(n_exp[0].item()), int(n_exp[1].item())
-    # L2-sized slices want n_plan hash ranges; the binning kernel takes at most 512
-    # (owner x range) bins, so beyond 8 ranks a bin spans `sub` slices and is counted
-    # in `sub` passes (kdf_count_bins_multi sub_split).  Measured at 8 ranks: 512 bins
-    # (bin + send 43.5 ms, count 33.8 ms) and 256 bins x 2 passes (31.2 + 48.1 ms) tie.
-    n_plan, slice_capacity = _kc.plan_partitions(max(n_child_exp, 1), key_words=kw,
-                                                 packed=eng.count_bins_packed(k, min_child_count))
-    n_local = max(1, min(n_plan, 512 // _kc._pow2_at_least(world)))
-    sub = max(1, n_plan // n_local)
-    cb, c_win = route_composite_p2p(eng, child_streams, k, world, "child", n_local, n_child_exp)
-    rb, r_win = route_composite_p2p(eng, ref_streams, k, world, "ref", n_local, n_ref_exp)
-    n_child = int(cb.cursors.sum().item())
-    out_cap = max(1 << 16, n_child // 64)
-    while True:
-        res = eng.count_bins(cb, rb, slice_capacity, min0=min_child_count, max1=0,
-                             count_min0=min_child_count, out_cap=out_cap, sub_split=sub)
-        if res["full"]:
-            if slice_capacity >= 2 * cb.bin_cap * world:
-                raise _engine.KdfError("child k-mer table slice full at %d slots" % slice_capacity)
-            slice_capacity = min(slice_capacity * 4, 2 * cb.bin_cap * world + 4)
-            continue
-        if res["n_out"] > out_cap:
-            out_cap = res["n_out"]
-            continue
-        break
-    return {"child_windows": c_win, "ref_windows": r_win, "child_distinct": res["distinct"],
-            "candidates": res["n_count"], "non_ref": res["n_out"], "lo": res["lo"], "hi": res["hi"]}
+    lo = los[0] if len(los) == 1 else torch.cat(los)
+    hi = (his[0] if len(his) == 1 else torch.cat(his)) if his else None
+    return {"child_windows": c_win, "ref_windows": r_win, "child_distinct": tot["distinct"],
+            "candidates": tot["n_count"], "non_ref": tot["n_out"], "lo": lo, "hi": hi,
+            "n_passes": n_passes, "n_local": n_local}
 
 
 def filter_parent_dist(eng, parent_stream, k, lo, hi, parent_max_count, world, stats):
@@ -294,10 +313,11 @@ def filter_parent_dist(eng, parent_stream, k, lo, hi, parent_max_count, world, s
 
 
 def discover_streams_dist(eng, child, mother, father, ref, k, min_child_count=3,
-                          parent_max_count=0, min_distinct_kmers_per_read=None, fetch=False):
+                          parent_max_count=0, min_distinct_kmers_per_read=None, fetch=False,
+                          n_passes=None):
     """Multi-GPU form of :func:`kmer_chain.discover_streams`; every argument is this
-    rank's shard.  Stage sizes in the result are GLOBAL (identical on all ranks);
-    ``units`` and the per-read records are this rank's own."""
+    rank's shard (one stream, or a list of streams).  Stage sizes in the result are
+    GLOBAL (identical on all ranks); ``units`` and the per-read records are this rank's own."""
     dist = _dist()
     torch = eng.torch
     world = dist.get_world_size()
@@ -305,22 +325,22 @@ def discover_streams_dist(eng, child, mother, father, ref, k, min_child_count=3,
         min_distinct_kmers_per_read = max(1, k // 4)
     stats = eng.new_stats()
     up = _kc._Uploader(eng)
+    childs, refs = _kc._as_list(child), _kc._as_list(ref)
     if peer_memory_available(eng):
         # fused route: the child is copied in chunks and binned (= sent) as it lands
-        d_child, ev_child = up.put_chunked(child, False)
-        d_ref, ev_ref = up.put(ref, False)
+        d_childs = [up.put_chunked(x, False)[0] for x in childs]
+        d_refs = [up.put(x, False)[0] for x in refs]
         fused = True
     else:
-        d_child, ev_child = up.put(child, True)
-        d_ref, ev_ref = up.put(ref, False)
+        d_childs = [up.put(x, True)[0] for x in childs]
+        d_refs = [up.put(x, False)[0] for x in refs]
         fused = False
-        up.wait(ev_child)
-        up.wait(ev_ref)
-    d_mother, ev_mother = up.put(mother, False)
-    d_father, ev_father = up.put(father, False)
-    ev_reads = up.put_read_index(d_child, child) if fused else None   # needed last: copied last
+    d_mothers = [up.put(x, False)[0] for x in _kc._as_list(mother)]
+    d_fathers = [up.put(x, False)[0] for x in _kc._as_list(father)]
+    # needed last: copied last
+    ev_reads = [up.put_read_index(d, h) for d, h in zip(d_childs, childs)] if fused else []
 
-    c = count_child_dist(eng, [d_child], [d_ref], k, min_child_count, world)
+    c = count_child_dist(eng, d_childs, d_refs, k, min_child_count, world, n_passes=n_passes)
     tot = torch.tensor([c["candidates"], c["child_distinct"]], dtype=torch.int64, device=eng.device)
     allreduce(tot, "sum")
     lo = allgather_varlen(torch, c["lo"], world)
@@ -328,18 +348,17 @@ def discover_streams_dist(eng, child, mother, father, ref, k, min_child_count=3,
     out = {"child_windows": c["child_windows"], "child_distinct": int(tot[1].item()),
            "candidates": int(tot[0].item()), "non_ref": int(lo.shape[0]), "after_mother": 0,
            "proband_unique": 0, "pu": None, "ndistinct": None, "nhits": None,
-           "informative_reads": 0, "reads": None, "hits": None, "parents_binned": []}
+           "informative_reads": 0, "reads": None, "hits": None, "parents_binned": [],
+           "n_passes": c["n_passes"]}
     units = c["child_windows"] + c["ref_windows"]
 
     n_pu = 0
     if out["non_ref"]:
-        up.wait(ev_mother)
-        lo, hi, b = filter_parent_dist(eng, d_mother, k, lo, hi, parent_max_count, world, stats)
+        lo, hi, b = filter_parent_dist(eng, d_mothers, k, lo, hi, parent_max_count, world, stats)
         out["parents_binned"].append(b)
         out["after_mother"] = int(lo.shape[0])
         if out["after_mother"]:
-            up.wait(ev_father)
-            lo, hi, b = filter_parent_dist(eng, d_father, k, lo, hi, parent_max_count, world, stats)
+            lo, hi, b = filter_parent_dist(eng, d_fathers, k, lo, hi, parent_max_count, world, stats)
             out["parents_binned"].append(b)
             n_pu = int(lo.shape[0])
     out["proband_unique"] = n_pu
@@ -348,15 +367,20 @@ def discover_streams_dist(eng, child, mother, father, ref, k, min_child_count=3,
     if n_pu:
         out["pu"] = KmerSet(eng, k, lo, hi)
         pt = _kc._primed_table(eng, k, lo, hi, n_pu)
-        up.wait(ev_child)
-        up.wait(ev_reads)
-        sp = eng.scan_reads_sparse(pt, d_child, stats=stats)
+        for ev in ev_reads:
+            up.wait(ev)
+        parts = []
+        for d in d_childs:
+            _kc._wait_ready(eng, d)
+            parts.append(eng.scan_reads_sparse(pt, d, stats=stats))
         pt.close()
+        sp = _kc.merge_sparse_records(parts, d_childs)
         out["reads"] = sp
         local_inf = int((sp["ndistinct"] >= min_distinct_kmers_per_read).sum())
         if fetch:
-            nd = np.zeros(d_child.n_reads, dtype=np.uint32)
-            nh = np.zeros(d_child.n_reads, dtype=np.uint32)
+            n_reads = sum(d.n_reads for d in d_childs)
+            nd = np.zeros(n_reads, dtype=np.uint32)
+            nh = np.zeros(n_reads, dtype=np.uint32)
             nd[sp["read"].astype(np.int64)] = sp["ndistinct"]
             nh[sp["read"].astype(np.int64)] = sp["nhits"]
             out["ndistinct"], out["nhits"] = nd, nh

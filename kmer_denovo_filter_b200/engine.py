@@ -79,18 +79,20 @@ _SIGNATURES = {
                                      _vp, _vp, _vp]),
     "kdf_bin_stream_to": (_i, [ctypes.POINTER(_Stream), _i, _i, _i, _vp, _u64, _vp, _vp, _vp, _vp]),
     "kdf_bin_keys": (_i, [_vp, _vp, _u64, _i, _i, _i, _vp, _u64, _vp, _vp, _vp]),
+    "kdf_bin_stream_pass": (_i, [ctypes.POINTER(_Stream), _u64, _u64, _i, _i, _i, _vp, _vp, _u64, _vp, _vp,
+                                 _vp, _i, _u32, _vp]),
+    "kdf_bin_keys_pass": (_i, [_vp, _vp, _u64, _i, _i, _i, _i, _u32, _vp, _u64, _vp, _vp, _vp]),
     "kdf_hit_coverage_scratch_bytes": (ctypes.c_size_t, [_u64, _i]),
     "kdf_hit_coverage": (_i, [_vp, _vp, _u64, _i, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp]),
     "kdf_debug_hit_coverage_host": (_i, [_vp, _vp, _u64, _i, _vp, _vp, _vp, _vp, _vp]),
     "kdf_update_bins": (_i, [_vp, _i, _vp, _u64, _vp, _i, _i, _u32, _vp, _vp]),
-    "kdf_count_bins_smem_scratch": (ctypes.c_size_t, [_i, _i, _i, _u64, _u64]),
-    "kdf_count_bins_smem": (_i, [_i, _i, _i, _vp, _u64, _vp, _vp, _u64, _vp, _vp, ctypes.c_size_t, _i, _i,
-                                 _u64, _u64, _u32, _u32, _u32, _u32, _vp, _u64, _vp, _vp, _vp, _vp]),
     "kdf_count_bins_packed": (_i, [_i, _u32, _u32, _u32, _u32, _u32, _i]),
     "kdf_count_bins": (_i, [_i, _i, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _u64, _u32, _u32, _u32, _u32,
                             _vp, _vp, _vp, _vp, _u64, _vp, _u32, _vp, _vp]),
     "kdf_count_bins_multi": (_i, [_i, _i, _i, _i, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _u64, _u32, _u32, _u32,
                                   _u32, _vp, _vp, _vp, _vp, _u64, _vp, _u32, _vp, _vp]),
+    "kdf_count_bins_pass": (_i, [_i, _i, _i, _i, _i, _u32, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _u64, _u32,
+                                 _u32, _u32, _u32, _vp, _vp, _vp, _vp, _u64, _vp, _u32, _vp, _vp]),
     "kdf_debug_hash_host": (_i, [_vp, _vp, _u64, _i, _i, _u32, _u32, _vp, _vp, _vp]),
     "kdf_pack_sequences": (_u64, [_vp, _vp, _u64, _vp, _vp, _vp]),
     "kdf_invalid_positions": (_u64, [_vp, _u64, _vp, _u64]),
@@ -217,7 +219,9 @@ def pack_sequences(seqs):
 
 
 def debug_extract_host(hs, k, random_access=False):
-    """Run the device iterator templates on the CPU (test hook)."""
+    """Run the device iterator templates on the CPU (test hook).  ``random_access``:
+    False = rolling WindowIter, True = WindowAt, 2 / 3 = the chunked WindowChunks of the
+    stream kernels (chunks of 4 / 16 windows)."""
     lib = load_library()
     n = hs.n_bases
     lo = np.zeros(max(n, 1), dtype=np.uint64)
@@ -228,7 +232,7 @@ def debug_extract_host(hs, k, random_access=False):
     if codes.size == 0:
         return lo[:0], hi[:0], ok[:0].astype(bool)
     rc = lib.kdf_debug_extract_host(_np_ptr(codes), _np_ptr(valid), n, k,
-                                    1 if random_access else 0, _np_ptr(lo), _np_ptr(hi), _np_ptr(ok))
+                                    int(random_access), _np_ptr(lo), _np_ptr(hi), _np_ptr(ok))
     if rc != KDF_OK:
         raise KdfError(lib.kdf_last_error().decode())
     return lo[:n], hi[:n], ok[:n].astype(bool)
@@ -326,6 +330,11 @@ class KeyBins:
 
     def overflowed(self):
         return bool(int(self.overflow.item()))
+
+    def reset(self):
+        """Empty the bins (the next pass of a multi-pass count refills them)."""
+        self.cursors.zero_()
+        self.overflow.zero_()
 
     def bin_keys(self, b, count=None):
         """(lo, hi|None) device views of bin b."""
@@ -452,6 +461,14 @@ class CudaEngine:
 
     def empty(self, n, dtype):
         return self.torch.empty(n, dtype=dtype, device=self.device)
+
+    def free_device_bytes(self):
+        """Bytes a new allocation could take now: free on the device plus the blocks
+        torch's caching allocator holds without using them."""
+        torch = self.torch
+        free, _total = torch.cuda.mem_get_info(self.device)
+        cached = torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+        return int(free + max(cached, 0))
 
     def new_stats(self):
         return self.zeros(N_STATS, self.torch.int64)
@@ -846,42 +863,47 @@ class CudaEngine:
     def new_bins(self, k, n_parts, bin_cap, by_owner=False):
         return KeyBins(self, k, n_parts, bin_cap, by_owner)
 
-    def bin_stream(self, bins, ds, stats=None, word_range=None):
+    def bin_stream(self, bins, ds, stats=None, word_range=None, pass_=None):
         """K2p / K6: append the canonical k-mers of a stream to hash-range (or owner)
-        bins; ``word_range=(first, n)`` restricts the window starts to those words."""
+        bins; ``word_range=(first, n)`` restricts the window starts to those words;
+        ``pass_=(pass_log2, pass_val)`` bins only hash-range group ``pass_val`` of
+        ``2**pass_log2`` (``kdf_bin_stream_pass``: the multi-pass count)."""
         ev = self._t0()
         first, n = word_range if word_range is not None else (0, (ds.n_bases + 31) // 32)
-        self._check(self.lib.kdf_bin_stream_range(
+        plog, pval = pass_ if pass_ is not None else (0, 0)
+        self._check(self.lib.kdf_bin_stream_pass(
             ds.c(), int(first), int(n), bins.k, 1 if bins.by_owner else 0, bins.n_parts,
-            bins.data.data_ptr(), bins.bin_cap, bins.cursors.data_ptr(), bins.overflow.data_ptr(),
-            stats.data_ptr() if stats is not None else None, self.stream_ptr()))
+            bins.data.data_ptr(), None, bins.bin_cap, bins.cursors.data_ptr(), bins.overflow.data_ptr(),
+            stats.data_ptr() if stats is not None else None, int(plog), int(pval), self.stream_ptr()))
         self._t1("bin_stream/kw%d" % bins.key_words, ev)
         self.launches += 1
 
     def bin_stream_to(self, ds, k, bin_ptrs, bin_cap, cursors, overflow, by_owner=1, stats=None,
-                      word_range=None):
+                      word_range=None, pass_=None):
         """K6 fused with the transfer: bin p goes to ``bin_ptrs[p]`` (device int64
         tensor of raw pointers, possibly peer memory over NVLink).  ``by_owner``: 1 =
         one bin per owner rank, R >= 2 = composite R owners x hash ranges."""
         ev = self._t0()
         first, n = word_range if word_range is not None else (0, (ds.n_bases + 31) // 32)
-        self._check(self.lib.kdf_bin_stream_to_range(
+        plog, pval = pass_ if pass_ is not None else (0, 0)
+        self._check(self.lib.kdf_bin_stream_pass(
             ds.c(), int(first), int(n), int(k), int(by_owner), int(bin_ptrs.shape[0]),
-            bin_ptrs.data_ptr(),
+            None, bin_ptrs.data_ptr(),
             int(bin_cap), cursors.data_ptr(), overflow.data_ptr(),
-            stats.data_ptr() if stats is not None else None, self.stream_ptr()))
+            stats.data_ptr() if stats is not None else None, int(plog), int(pval), self.stream_ptr()))
         self._t1("bin_stream_to_peers/kw%d" % self.lib.kdf_key_words(int(k)), ev)
         self.launches += 1
 
-    def bin_keys(self, bins, lo, hi=None, n=None):
+    def bin_keys(self, bins, lo, hi=None, n=None, pass_=None):
         n = int(lo.shape[0]) if n is None else int(n)
         if not n:
             return
         ev = self._t0()
-        self._check(self.lib.kdf_bin_keys(
+        plog, pval = pass_ if pass_ is not None else (0, 0)
+        self._check(self.lib.kdf_bin_keys_pass(
             lo.data_ptr(), hi.data_ptr() if hi is not None else None, n, bins.k,
-            1 if bins.by_owner else 0, bins.n_parts, bins.data.data_ptr(), bins.bin_cap,
-            bins.cursors.data_ptr(), bins.overflow.data_ptr(), self.stream_ptr()))
+            1 if bins.by_owner else 0, bins.n_parts, int(plog), int(pval), bins.data.data_ptr(),
+            bins.bin_cap, bins.cursors.data_ptr(), bins.overflow.data_ptr(), self.stream_ptr()))
         self._t1("bin_keys/kw%d" % bins.key_words, ev)
         self.launches += 1
 
@@ -941,75 +963,13 @@ class CudaEngine:
         return bool(self.lib.kdf_count_bins_packed(k, min_child_count, U32_MAX, 0, 0,
                                                    min_child_count, 0))
 
-    SUB_TARGET = 24 * 1024      # k-mer instances per sub-bin the shared-memory count aims for
-    SUB_SLOTS = 8192            # packed slots of its table (64 KB: three CTAs per SM)
-    SUB_SCRATCH_BYTES = 3 << 30
-
-    def count_bins_smem_ok(self, k, min_child_count, force=False):
-        """The shared-memory form of the packed count applies (64-bit keys, thresholds
-        that fit the key's spare bits).  It is exact and tested, but measured SLOWER than
-        the L2 form on B200 (64 Mbp x 30x: 256-way binning 13.5 ms + second-level binning
-        16.4 ms + count 19 ms against 7.9 + 18.9 ms), so the chain only takes
-        it when asked to (KDF_COUNT_SMEM=1)."""
-        return (self.lib.kdf_key_words(k) == 1 and self.count_bins_packed(k, min_child_count)
-                and (force or os.environ.get("KDF_COUNT_SMEM", "0") == "1"))
-
-    def count_bins_smem(self, child_bins, ref_bins, min0, max1=0, count_min0=None, out_cap=1 << 20,
-                        n_keys=None, n_ref_keys=None):
-        """``kdf_count_bins_smem`` over hash-range bins.  Returns the dict of
-        :meth:`count_bins` plus ``fallback`` (True: a sub-bin did not fit — count the same
-        bins with :meth:`count_bins` instead; the outputs here are then meaningless)."""
-        torch = self.torch
-        k = child_bins.k
-        n_src = getattr(child_bins, "n_src", 1)
-        count_min0 = min0 if count_min0 is None else count_min0
-        if n_keys is None:
-            n_keys = int(child_bins.cursors.sum().item())
-        if ref_bins is not None and n_ref_keys is None:
-            n_ref_keys = int(ref_bins.cursors.sum().item())
-        n_parts = child_bins.n_parts
-        s2 = 2
-        while s2 < 512 and n_keys > n_parts * s2 * self.SUB_TARGET:
-            s2 *= 2
-
-        def cap_of(total):
-            mean = total / float(n_parts * s2)
-            return (int(mean * 1.04 + 64 * (mean ** 0.5) + 1024) + 1) & ~1
-        sub_cap = cap_of(n_keys)
-        ref_cap = cap_of(n_ref_keys) if ref_bins is not None else 0
-        group = max(1, min(n_parts, self.SUB_SCRATCH_BYTES // max(1, s2 * (sub_cap + ref_cap) * 8)))
-        nbytes = self.lib.kdf_count_bins_smem_scratch(n_parts, group, s2, sub_cap, ref_cap)
-        scratch = self.empty((nbytes + 7) // 8, torch.int64)
-        lo = self.empty(max(out_cap, 1), torch.int64)
-        n_out = self.zeros(1, torch.int64)
-        ctr = self.zeros(6, torch.int64)
-        flags = self.zeros(1, torch.int64)
-        ev = self._t0()
-        self._check(self.lib.kdf_count_bins_smem(
-            k, n_parts, n_src, child_bins.data.data_ptr(), child_bins.bin_cap,
-            child_bins.cursors.data_ptr(),
-            ref_bins.data.data_ptr() if ref_bins is not None else None,
-            ref_bins.bin_cap if ref_bins is not None else 0,
-            ref_bins.cursors.data_ptr() if ref_bins is not None else None,
-            scratch.data_ptr(), nbytes, group, s2, sub_cap, ref_cap, self.SUB_SLOTS, min0, max1,
-            count_min0, lo.data_ptr(), out_cap, n_out.data_ptr(), ctr.data_ptr(), flags.data_ptr(),
-            self.stream_ptr()))
-        self._t1("count_bins_smem/kw1", ev)
-        n_groups = (n_parts + group - 1) // group
-        self.launches += 1 + n_groups * (2 + (1 if ref_bins is not None and max1 == 0 else 0))
-        c = ctr.cpu().numpy().view(np.uint64)
-        n = int(n_out.item())
-        m = min(n, out_cap)
-        return {"n_out": n, "lo": lo[:m], "hi": None, "p0": None, "p1": None,
-                "keys": int(c[0]), "full": 0, "hits": int(c[2]), "distinct": int(c[3]),
-                "n_count": int(c[4]), "occupied": int(c[5]), "fallback": bool(int(flags.item())),
-                "s2": s2, "group": group, "sub_cap": sub_cap}
-
     def count_bins(self, child_bins, ref_bins, slice_capacity, min0=0, max0=U32_MAX, min1=0,
-                   max1=U32_MAX, count_min0=0, out_cap=1 << 20, want_planes=False, sub_split=1):
+                   max1=U32_MAX, count_min0=0, out_cap=1 << 20, want_planes=False, sub_split=1,
+                   pass_=None):
         """Count every bin in an L2-resident slice and emit (see include/kdf.h).
         Returns dict(n_out, lo, hi, p0, p1, keys, full, hits, distinct, n_count, occupied);
-        lo/hi/p0/p1 hold min(n_out, out_cap) entries."""
+        lo/hi/p0/p1 hold min(n_out, out_cap) entries.  ``pass_=(pass_log2, pass_val)``:
+        the bins are those of one pass of a multi-pass count (``bin_stream(pass_=...)``)."""
         torch = self.torch
         k = child_bins.k
         kw = child_bins.key_words
@@ -1025,8 +985,10 @@ class CudaEngine:
         n_src = getattr(child_bins, "n_src", 1)
         if ref_bins is not None and getattr(ref_bins, "n_src", 1) != n_src:
             raise KdfError("count_bins: child and reference bins must have the same sources")
-        self._check(self.lib.kdf_count_bins_multi(
-            k, child_bins.n_parts, n_src, int(sub_split), child_bins.data.data_ptr(),
+        plog, pval = pass_ if pass_ is not None else (0, 0)
+        self._check(self.lib.kdf_count_bins_pass(
+            k, child_bins.n_parts, n_src, int(sub_split), int(plog), int(pval),
+            child_bins.data.data_ptr(),
             child_bins.bin_cap,
             child_bins.cursors.data_ptr(),
             ref_bins.data.data_ptr() if ref_bins is not None else None,

@@ -98,16 +98,23 @@ class FakeEngine:
     def new_bins(self, k, n_parts, bin_cap, by_owner=False):
         return FakeBins(k, n_parts, bin_cap, by_owner)
 
-    def _append(self, bins, lo, hi):
+    def _append(self, bins, lo, hi, pass_=None):
         kw = bins.key_words
         log2p = bins.n_parts.bit_length() - 1
+        plog, pval = pass_ if pass_ is not None else (0, 0)
+        # hash ranges: the top plog bits pick the pass, the next log2p bits the local bin
         part, _b, owner = engine.debug_hash_host(lo, hi if kw == 2 else None, kw,
-                                                 0 if bins.by_owner else log2p, 1024,
+                                                 plog + (0 if bins.by_owner else log2p), 1024,
                                                  bins.n_parts if bins.by_owner else 1)
-        which = owner if bins.by_owner else part
+        if bins.by_owner:
+            in_pass = (part == pval) if plog else np.ones(lo.shape[0], dtype=bool)
+            which = owner
+        else:
+            in_pass = ((part >> log2p) == pval) if plog else np.ones(lo.shape[0], dtype=bool)
+            which = part & (bins.n_parts - 1)
         data = bins.data.numpy().view(np.uint64)
         for b in range(bins.n_parts):
-            sel = np.flatnonzero(which == b)
+            sel = np.flatnonzero((which == b) & in_pass)
             cur = int(bins.cursors[b])
             room = max(0, bins.bin_cap - cur)
             take = sel[:room]
@@ -120,22 +127,23 @@ class FakeEngine:
                 data[base:base + 2 * take.size:2] = lo[take]
                 data[base + 1:base + 2 * take.size:2] = hi[take]
             bins.cursors[b] = cur + sel.size
+        return int(in_pass.sum())
 
-    def bin_stream(self, bins, ds, stats=None):
+    def bin_stream(self, bins, ds, stats=None, word_range=None, pass_=None):
         lo, hi, ok = stream_keys(ds, bins.k)
+        n = self._append(bins, lo[ok], hi[ok], pass_)
         if stats is not None:
-            stats[0] += int(ok.sum())
-        self._append(bins, lo[ok], hi[ok])
+            stats[0] += n
 
-    def bin_keys(self, bins, lo, hi=None, n=None):
+    def bin_keys(self, bins, lo, hi=None, n=None, pass_=None):
         n = int(lo.shape[0]) if n is None else int(n)
         a = lo.numpy().view(np.uint64)
         if bins.key_words == 1:
-            self._append(bins, a[:n].copy(), np.zeros(n, np.uint64))
+            self._append(bins, a[:n].copy(), np.zeros(n, np.uint64), pass_)
         elif hi is None:
-            self._append(bins, a[0:2 * n:2].copy(), a[1:2 * n:2].copy())
+            self._append(bins, a[0:2 * n:2].copy(), a[1:2 * n:2].copy(), pass_)
         else:
-            self._append(bins, a[:n].copy(), hi.numpy().view(np.uint64)[:n].copy())
+            self._append(bins, a[:n].copy(), hi.numpy().view(np.uint64)[:n].copy(), pass_)
 
     def count_bins_packed(self, k, min_child_count):
         return False
@@ -148,11 +156,8 @@ class FakeEngine:
     def build_filter(self, table, n_keys, max_bytes=1 << 30):
         pass
 
-    def count_bins_smem_ok(self, k, min_child_count):
-        return False
-
     def count_bins(self, cb, rb, slice_capacity, min0=0, max0=U32_MAX, min1=0, max1=U32_MAX,
-                   count_min0=0, out_cap=1 << 20, want_planes=False):
+                   count_min0=0, out_cap=1 << 20, want_planes=False, sub_split=1, pass_=None):
         cnt = collections.Counter()
         n_keys = 0
         full = 0

@@ -28,13 +28,34 @@ def _dev_stream(s):
     return engine.DeviceStream(s["codes"], s["valid"], s["n_bases"], s["read_starts"], s["read_lens"])
 
 
+def _split_stream(ds):
+    """One stream as two (split at a read boundary, 32-base aligned: whole words)."""
+    from kmer_denovo_filter_b200 import engine
+    starts = ds.read_starts.numpy().astype(np.int64)
+    if starts.shape[0] < 2:
+        return [ds]
+    cand = np.flatnonzero(starts % 32 == 0)
+    cand = cand[cand > 0]
+    if cand.shape[0] == 0:
+        return [ds]
+    r = int(cand[cand.shape[0] // 2])
+    cut = int(starts[r])
+    w = cut // 32
+    # the separator before read r is the last base of the first part
+    a = engine.DeviceStream(ds.codes[:w].clone(), ds.valid[:w].clone(), cut - 1,
+                            ds.read_starts[:r].clone(), ds.read_lens[:r].clone())
+    b = engine.DeviceStream(ds.codes[w:].clone(), ds.valid[w:].clone(), ds.n_bases - cut,
+                            (ds.read_starts[r:] - cut).clone(), ds.read_lens[r:].clone())
+    return [a, b]
+
+
 def _shards(rank):
     from kmer_denovo_filter_b200 import synth
     return synth.make_trio(torch, torch.device("cpu"), GENOME, depth=DEPTH, read_len=100,
                            n_denovo=12, rank=rank, world=WORLD)
 
 
-def _worker(rank, port, q):
+def _worker(rank, port, q, n_passes=None, split=False):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -44,9 +65,12 @@ def _worker(rank, port, q):
         from kmer_denovo_filter_b200.discovery import kmer_chain_dist
         trio = _shards(rank)
         eng = FakeEngine()
+        streams = {w: _dev_stream(trio[w]) for w in ("child", "mother", "father", "ref")}
+        if split:     # every sample as a list of two streams (whole-genome samples exceed one)
+            streams = {w: _split_stream(s) for w, s in streams.items()}
         res = kmer_chain_dist.discover_streams_dist(
-            eng, _dev_stream(trio["child"]), _dev_stream(trio["mother"]),
-            _dev_stream(trio["father"]), _dev_stream(trio["ref"]), K)
+            eng, streams["child"], streams["mother"], streams["father"], streams["ref"], K,
+            n_passes=n_passes)
         pu = sorted(res["pu"].lo.numpy().view(np.uint64).tolist()) if res["pu"] is not None else []
         q.put((rank, {x: res[x] for x in ("candidates", "non_ref", "after_mother", "proband_unique",
                                           "child_distinct", "informative_reads", "units")}, pu,
@@ -96,7 +120,11 @@ def _expected():
             "informative_reads": inf}, sorted(pu), units
 
 
-def test_distributed_chain_world2_gloo():
+import pytest
+
+
+@pytest.mark.parametrize("n_passes,split", [(None, False), (2, True)])
+def test_distributed_chain_world2_gloo(n_passes, split):
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
     if here not in sys.path:
@@ -104,7 +132,7 @@ def test_distributed_chain_world2_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, port, q)) for r in range(WORLD)]
+    procs = [ctx.Process(target=_worker, args=(r, port, q, n_passes, split)) for r in range(WORLD)]
     for p in procs:
         p.start()
     got = [q.get(timeout=600) for _ in procs]

@@ -136,6 +136,81 @@ def test_partitioned_count_survives_skew_and_small_slices(eng):
     assert 0 in want and want[0] == 3000 * 70          # poly-A canonical key
 
 
+@pytest.mark.parametrize("k", [31, 47])
+@pytest.mark.parametrize("n_passes", [2, 8])
+def test_multi_pass_chain_equals_single_pass_and_oracle(eng, k, n_passes):
+    """The child count in several hash-range passes (what bounds the bins' memory for a
+    whole-genome sample) and with every sample given as a LIST of streams: identical
+    stage sizes, proband-unique set and per-read records."""
+    from kmer_denovo_filter_b200.discovery import kmer_chain
+    from oracle import ckdf
+    trio = _trio(eng, 250_000, 12)
+    h = {w: _host(trio[w]) for w in ("child", "mother", "father", "ref")}
+    want = ckdf.discovery_chain(h["child"], h["mother"][:3], h["father"][:3], h["ref"][:3], k, threads=4)
+    d = {w: _dev(trio[w]) for w in ("child", "mother", "father", "ref")}
+    got = kmer_chain.discover_streams(eng, d["child"], d["mother"], d["father"], d["ref"], k,
+                                      n_passes=n_passes)
+    assert got["n_passes"] == n_passes
+    for key in ("candidates", "non_ref", "after_mother", "proband_unique", "units"):
+        assert got[key] == want[key], key
+    assert sorted(got["pu"].to_pyints()) == _keys(want["pu_lo"], want["pu_hi"])
+    assert np.array_equal(got["ndistinct"], want["nd"]) and np.array_equal(got["nhits"], want["nh"])
+    # every sample as two streams
+    parts = {w: _split(d[w]) for w in d}
+    got2 = kmer_chain.discover_streams(eng, parts["child"], parts["mother"], parts["father"],
+                                       parts["ref"], k, n_passes=n_passes)
+    for key in ("candidates", "non_ref", "after_mother", "proband_unique"):
+        assert got2[key] == want[key], key
+    assert sorted(got2["pu"].to_pyints()) == _keys(want["pu_lo"], want["pu_hi"])
+    assert np.array_equal(got2["ndistinct"], want["nd"]) and np.array_equal(got2["nhits"], want["nh"])
+
+
+def _split(ds):
+    """One DeviceStream as two, cut at a read boundary that is word aligned."""
+    from kmer_denovo_filter_b200 import engine
+    starts = ds.read_starts.cpu().numpy().astype(np.int64)
+    cand = np.flatnonzero(starts % 32 == 0)
+    cand = cand[cand > 0]
+    if cand.shape[0] == 0:
+        return [ds]
+    r = int(cand[cand.shape[0] // 2])
+    cut = int(starts[r])
+    w = cut // 32
+    a = engine.DeviceStream(ds.codes[:w].clone(), ds.valid[:w].clone(), cut - 1,
+                            ds.read_starts[:r].clone(), ds.read_lens[:r].clone())
+    b = engine.DeviceStream(ds.codes[w:].clone(), ds.valid[w:].clone(), ds.n_bases - cut,
+                            (ds.read_starts[r:] - cut).clone(), ds.read_lens[r:].clone())
+    return [a, b]
+
+
+def test_bench_config_routes_equal_oracle(eng, monkeypatch):
+    """8 Mbp x 30x with the routes of the 64 Mbp bench configuration forced (32 hash-range
+    bins over L2-sized slices, the two-bit filter in front of the parent tables, and the
+    binned parent route): every stage size, the proband-unique keys and all per-read
+    (ndistinct, nhits) equal the CPU oracle's.  ~4 s of oracle time."""
+    from kmer_denovo_filter_b200.discovery import kmer_chain
+    from oracle import ckdf
+    k = 31
+    trio = _trio(eng, 8_000_000, 30)
+    h = {w: _host(trio[w]) for w in ("child", "mother", "father", "ref")}
+    want = ckdf.discovery_chain(h["child"], h["mother"][:3], h["father"][:3], h["ref"][:3], k,
+                                threads=ckdf.max_threads(),
+                                child_capacity=max(int(h["child"][2]) // 4, 1024))
+    d = {w: _dev(trio[w]) for w in ("child", "mother", "father", "ref")}
+    monkeypatch.setattr(kmer_chain, "SLICE_BYTES", kmer_chain.SLICE_BYTES // 8)
+    for route in ("filter", "binned"):
+        if route == "binned":
+            monkeypatch.setenv("KDF_TABLE_FILTER", "0")
+            monkeypatch.setattr(kmer_chain, "PROBE_DIRECT_BYTES", 0)
+            monkeypatch.setattr(kmer_chain, "L2_TABLE_BYTES", 0)
+        got = kmer_chain.discover_streams(eng, d["child"], d["mother"], d["father"], d["ref"], k)
+        for key in ("candidates", "non_ref", "after_mother", "proband_unique", "units"):
+            assert got[key] == want[key], (route, key)
+        assert got["parents_binned"] == [route == "binned"] * 2
+        assert sorted(got["pu"].to_pyints()) == _keys(want["pu_lo"], want["pu_hi"])
+        assert np.array_equal(got["ndistinct"], want["nd"]) and np.array_equal(got["nhits"], want["nh"])
+
+
 @pytest.mark.parametrize("reads", [[], [""], ["ACGT"], ["N" * 200], ["ACGTN" * 40]])
 def test_chain_on_degenerate_children(eng, reads):
     """Empty input, reads shorter than k, all-N reads: no k-mers, no crash."""

@@ -251,7 +251,8 @@ def test_scan_reads_overflow_path(eng):
 
 @pytest.mark.parametrize("k", [31, 47])
 @pytest.mark.parametrize("n_parts,by_owner", [(1, True), (2, True), (3, True), (8, True),
-                                              (1, False), (16, False), (256, False)])
+                                              (1, False), (16, False), (32, False), (128, False),
+                                              (256, False), (512, False)])
 def test_bin_stream(eng, k, n_parts, by_owner):
     """K2p / K6: every valid canonical k-mer lands in exactly one bin, the bin is
     the one the host-side hash predicts, equal keys share a bin."""
@@ -299,6 +300,134 @@ def test_bin_overflow_is_reported(eng):
     eng.bin_stream(bins, ds)
     assert bins.overflowed()
     assert bins.counts().sum() == kmers.canonical_windows(*kmers.encode_stream(reads)[:2], 31)[2].sum()
+
+
+@pytest.mark.parametrize("k", [31, 47])
+@pytest.mark.parametrize("threads,wpr", [(256, 4), (512, 16), (1024, 8), (1024, 32)])
+def test_bin_stream_launch_shapes(eng, k, threads, wpr, monkeypatch):
+    """Every launch shape of the binning kernel (round size, flat / per-bin copy-out,
+    queues that overflow into the direct path) bins the same multiset of keys."""
+    from kmer_denovo_filter_b200 import engine
+    monkeypatch.setenv("KDF_BIN_THREADS", str(threads))
+    monkeypatch.setenv("KDF_BIN_WPR", str(wpr))
+    _g, reads = _genome_reads(43 + k, glen=30000, n=6000)
+    reads = reads + ["A" * 150] * 300          # one key 36 000 times: its queue overflows
+    ds = eng.upload(engine.pack_sequences(reads))
+    codes, valid, _s, _l = kmers.encode_stream(reads)
+    ohi, olo, ook = kmers.canonical_windows(codes, valid, k)
+    want = sorted(kmers.to_pyints(ohi[ook], olo[ook]))
+    for n_parts in (4, 64, 512):
+        bins = eng.new_bins(k, n_parts, bin_cap=len(want))
+        st = eng.new_stats()
+        eng.bin_stream(bins, ds, st)
+        assert not bins.overflowed()
+        assert int(bins.counts().sum()) == len(want) == eng.read_stats(st)["windows"]
+        got = []
+        for b in range(n_parts):
+            got.extend(eng.keys_to_pyints(*bins.bin_keys(b)))
+        assert sorted(got) == want
+
+
+@pytest.mark.parametrize("k", [31, 47])
+@pytest.mark.parametrize("n_passes,n_parts", [(2, 8), (8, 64), (16, 1)])
+def test_bin_stream_passes_partition_the_keys(eng, k, n_passes, n_parts):
+    """Multi-pass binning (kdf_bin_stream_pass): pass p bins exactly the keys whose top
+    hash bits are p, into the bin the next bits name; over all passes every key appears
+    once; kdf_bin_keys_pass agrees; kdf_count_bins_pass over the passes equals the oracle."""
+    from kmer_denovo_filter_b200 import engine
+    g, reads = _genome_reads(61 + k, glen=6000, n=900)
+    ds = eng.upload(engine.pack_sequences(reads))
+    dr = eng.upload(engine.pack_sequences([g[:3000]]))
+    want = kmers.count_sequences(reads, k)
+    refk = set(kmers.count_sequences([g[:3000]], k))
+    kw = 1 if k <= 32 else 2
+    plog = n_passes.bit_length() - 1
+    log2p = n_parts.bit_length() - 1
+    n_win = sum(want.values())
+    lo_all, hi_all, ok = eng.extract_canonical(ds, k)
+    okb = np.unpackbits(ok.cpu().numpy().view(np.uint32).byteswap().view(np.uint8))[:ds.n_bases].astype(bool)
+    import torch
+    sel = torch.from_numpy(np.flatnonzero(okb)).to(eng.device)
+    klo = lo_all[sel].contiguous()
+    khi = hi_all[sel].contiguous() if hi_all is not None else None
+    seen = []
+    emitted, n_count, distinct = set(), 0, 0
+    for p in range(n_passes):
+        bins = eng.new_bins(k, n_parts, bin_cap=n_win + 64)
+        rb = eng.new_bins(k, n_parts, bin_cap=4000)
+        st = eng.new_stats()
+        eng.bin_stream(bins, ds, st, pass_=(plog, p))
+        eng.bin_stream(rb, dr, None, pass_=(plog, p))
+        b2 = eng.new_bins(k, n_parts, bin_cap=n_win + 64)
+        eng.bin_keys(b2, klo, khi, pass_=(plog, p))
+        assert (bins.counts() == b2.counts()).all()
+        assert int(bins.counts().sum()) == eng.read_stats(st)["windows"]
+        for b in range(n_parts):
+            keys = eng.keys_to_pyints(*bins.bin_keys(b))
+            assert sorted(keys) == sorted(eng.keys_to_pyints(*b2.bin_keys(b)))
+            seen.extend(keys)
+            if keys:
+                lo_np = np.array([x & 0xFFFFFFFFFFFFFFFF for x in keys], dtype=np.uint64)
+                hi_np = np.array([x >> 64 for x in keys], dtype=np.uint64)
+                part, _bk, _o = engine.debug_hash_host(lo_np, hi_np if kw == 2 else None, kw,
+                                                       plog + log2p, 1024, 1)
+                assert (part == p * n_parts + b).all()
+        res = eng.count_bins(bins, rb, slice_capacity=2 * len(want) // (n_passes * n_parts) + 256,
+                             min0=3, max1=0, count_min0=3, out_cap=len(want) + 10, pass_=(plog, p))
+        assert res["full"] == 0
+        got = eng.keys_to_pyints(res["lo"], res["hi"])
+        assert not (set(got) & emitted)
+        emitted |= set(got)
+        n_count += res["n_count"]
+        distinct += res["distinct"]
+    assert sorted(seen) == sorted(x for x, c in want.items() for _ in range(c))
+    assert emitted == {x for x, c in want.items() if c >= 3} - refk
+    assert n_count == sum(1 for c in want.values() if c >= 3) and distinct == len(want)
+
+
+@pytest.mark.parametrize("k", [31, 47])
+@pytest.mark.parametrize("owners,n_local,n_passes", [(2, 4, 1), (4, 16, 2), (8, 64, 4)])
+def test_bin_stream_to_composite_bins(eng, k, owners, n_local, n_passes):
+    """The fused multi-GPU route's binning (one pointer per (owner, hash range) bin,
+    kdf_bin_stream_pass with bin_ptrs) on local memory: bin = owner * n_local + range,
+    restricted to one pass group."""
+    import torch
+    from kmer_denovo_filter_b200 import engine
+    _g, reads = _genome_reads(71 + k, glen=6000, n=900)
+    ds = eng.upload(engine.pack_sequences(reads))
+    codes, valid, _s, _l = kmers.encode_stream(reads)
+    ohi, olo, ook = kmers.canonical_windows(codes, valid, k)
+    want = sorted(kmers.to_pyints(ohi[ook], olo[ook]))
+    kw = 1 if k <= 32 else 2
+    plog = n_passes.bit_length() - 1
+    log2l = n_local.bit_length() - 1
+    n_bins = owners * n_local
+    cap = len(want) + 8
+    got_all = []
+    for p in range(n_passes):
+        buf = torch.zeros(n_bins * cap * kw, dtype=torch.int64, device=eng.device)
+        ptrs = torch.tensor([buf.data_ptr() + b * cap * kw * 8 for b in range(n_bins)],
+                            dtype=torch.int64, device=eng.device)
+        cursors = torch.zeros(n_bins, dtype=torch.int64, device=eng.device)
+        overflow = torch.zeros(1, dtype=torch.int64, device=eng.device)
+        st = eng.new_stats()
+        eng.bin_stream_to(ds, k, ptrs, cap, cursors, overflow, by_owner=owners, stats=st,
+                          pass_=(plog, p) if n_passes > 1 else None)
+        assert int(overflow.item()) == 0
+        cnt = cursors.cpu().numpy()
+        assert int(cnt.sum()) == eng.read_stats(st)["windows"]
+        host = buf.cpu().numpy().view(np.uint64)
+        for b in range(n_bins):
+            seg = host[b * cap * kw:(b * cap + int(cnt[b])) * kw]
+            lo_np = seg if kw == 1 else seg[0::2]
+            hi_np = np.zeros_like(lo_np) if kw == 1 else seg[1::2]
+            got_all.extend(kmers.to_pyints(hi_np, lo_np))
+            if lo_np.shape[0]:
+                part, _bk, owner = engine.debug_hash_host(lo_np.copy(), hi_np.copy() if kw == 2 else None,
+                                                          kw, plog + log2l, 1024, owners)
+                assert (owner == b // n_local).all()
+                assert (part == p * n_local + b % n_local).all()
+    assert sorted(got_all) == want
 
 
 @pytest.mark.parametrize("k", [31, 47])
@@ -477,52 +606,6 @@ def test_update_bins_equals_count_stream(eng, k, monkeypatch):
     assert eng.read_stats(st)["windows"] == n_win
 
 
-@pytest.mark.parametrize("k", [21, 31])
-@pytest.mark.parametrize("n_parts", [1, 16])
-def test_count_bins_smem_form(eng, k, n_parts, monkeypatch):
-    """The shared-memory form of the packed count (second-level binning + one CTA per
-    sub-bin, include/kdf.h) against the oracle: thresholds, reference subtraction,
-    counters, undersized output, and the flags that send the caller back to the L2 form."""
-    from kmer_denovo_filter_b200 import engine
-    g, child = _genome_reads(391 + k, glen=12000, n=2500)
-    ref = [g[:7000]]
-    want = kmers.count_sequences(child, k)
-    refk = set(kmers.count_sequences(ref, k))
-    dc = eng.upload(engine.pack_sequences(child))
-    dr = eng.upload(engine.pack_sequences(ref))
-    n_win = sum(want.values())
-    cb = eng.new_bins(k, n_parts, bin_cap=n_win // n_parts * 2 + 512)
-    rb = eng.new_bins(k, n_parts, bin_cap=7000 // n_parts * 2 + 512)
-    eng.bin_stream(cb, dc)
-    eng.bin_stream(rb, dr)
-    assert eng.count_bins_smem_ok(k, 3, force=True)
-    monkeypatch.setattr(engine.CudaEngine, "SUB_TARGET", 512)      # many sub-bins even for this input
-    for m in (1, 2, 3):
-        cand = {key for key, c in want.items() if c >= m}
-        res = eng.count_bins_smem(cb, rb, m, max1=0, out_cap=len(want) + 10)
-        assert not res["fallback"] and res["s2"] > 2
-        assert res["keys"] == n_win and res["distinct"] == len(want) == res["occupied"]
-        assert res["hits"] + res["distinct"] == n_win and res["n_count"] == len(cand)
-        got = eng.keys_to_pyints(res["lo"], None)
-        assert len(got) == res["n_out"] == len(set(got)) and set(got) == cand - refk
-        res = eng.count_bins_smem(cb, None, m, max1=0, out_cap=len(want) + 10)
-        assert not res["fallback"] and set(eng.keys_to_pyints(res["lo"], None)) == cand
-        res = eng.count_bins_smem(cb, rb, m, max1=engine.U32_MAX, count_min0=0, out_cap=len(want) + 10)
-        assert set(eng.keys_to_pyints(res["lo"], None)) == cand and res["n_count"] == len(want)
-    small = eng.count_bins_smem(cb, rb, 3, max1=0, out_cap=5)
-    assert small["n_out"] == len({key for key, c in want.items() if c >= 3} - refk) and small["lo"].shape[0] == 5
-    # several groups of bins through a small scratch buffer
-    monkeypatch.setattr(engine.CudaEngine, "SUB_SCRATCH_BYTES", 1 << 16)
-    res = eng.count_bins_smem(cb, rb, 3, max1=0, out_cap=len(want) + 10)
-    assert not res["fallback"] and (n_parts == 1 or res["group"] < n_parts)
-    assert set(eng.keys_to_pyints(res["lo"], None)) == {key for key, c in want.items() if c >= 3} - refk
-    # a table too small for a sub-bin's distinct keys is reported, never wrong silently
-    monkeypatch.setattr(engine.CudaEngine, "SUB_TARGET", 1 << 30)
-    monkeypatch.setattr(engine.CudaEngine, "SUB_SLOTS", 256)
-    res = eng.count_bins_smem(cb, rb, 3, max1=0, out_cap=len(want) + 10)
-    assert res["fallback"] == (len(want) // n_parts > 200)
-
-
 def test_hit_coverage_device_equals_host(eng):
     """K7 on the device (expand + radix sort + run-length encode) == the same expansion
     on the host, which the CPU suite pins against the reference-named helper."""
@@ -667,6 +750,42 @@ def test_scan_sparse_equals_dense(eng, k, big_table):
         f = int(sp["first"][j])
         got_idx = sp["hit_pos"][f:f + len(idx)] - starts[r]
         assert sorted(got_idx.tolist()) == sorted(idx)
+
+
+@pytest.mark.parametrize("k", [31, 47])
+def test_scan_sparse_long_reads_full_of_hits(eng, k):
+    """Long reads (HiFi / ONT lengths) in which every window is a hit — a novel insertion:
+    > 10 000 hits per read, with repeats so that distinct < hits.  The per-read reduction
+    is sort based (linear in the run), so this finishes at once and stays exact."""
+    from kmer_denovo_filter_b200 import engine
+    rng = random.Random(7 + k)
+    unit = "".join(rng.choice("ACGT") for _ in range(6000))
+    reads = [unit * 3, unit[:3000] + unit[:3000] + unit, "ACGT" * 50, unit[100:400]]
+    pu = sorted(kmers.count_sequences([unit], k))
+    ds = eng.upload(engine.pack_sequences(reads))
+    t = eng.new_table(k, n_keys=len(pu))
+    lo, hi = eng.keys_to_device(pu, t.key_words)
+    eng.update_keys(t, lo, hi, engine.MODE_INSERT_ONLY, 0, 0)
+    sp = eng.scan_reads_sparse(t, ds)
+    want = {}
+    pus = set(pu)
+    for r, seq in enumerate(reads):
+        codes, valid, _s, _l = kmers.encode_stream([seq])
+        whi, wlo, wok = kmers.canonical_windows(codes, valid, k)
+        hits = [x for x in kmers.to_pyints(whi[wok], wlo[wok]) if x in pus]
+        if hits:
+            want[r] = (len(set(hits)), len(hits))
+    assert sp["read"].tolist() == sorted(want)
+    assert max(v[1] for v in want.values()) > 10000
+    for j, r in enumerate(sp["read"].tolist()):
+        assert (int(sp["ndistinct"][j]), int(sp["nhits"][j])) == want[r]
+    # `first` indexes the position-sorted hit list
+    starts = ds.read_starts.cpu().numpy().view(np.uint64)
+    for j, r in enumerate(sp["read"].tolist()):
+        f, n = int(sp["first"][j]), int(sp["nhits"][j])
+        seg = sp["hit_pos"][f:f + n]
+        assert seg.min() >= starts[r] and (np.diff(seg.astype(np.int64)) > 0).all()
+        assert seg.max() < starts[r] + len(reads[r])
 
 
 def test_empty_stream_is_a_noop(eng):

@@ -55,7 +55,7 @@ def test_pack_empty_inputs():
 
 
 @pytest.mark.parametrize("k", KS)
-@pytest.mark.parametrize("random_access", [False, True])
+@pytest.mark.parametrize("random_access", [False, True, 2, 3])
 def test_device_iterator_on_host_equals_oracle(k, random_access):
     seqs = _rand_seqs(100 + k)
     hs = engine.pack_sequences(seqs)
