@@ -12,13 +12,20 @@ canonical k-mer instances counted + queried per second, summed over stages.
 At N > 1 every rank holds 1/N of each sample's reads of an N x 64 Mbp genome
 (weak scaling); the child table is partitioned by owner rank and k-mers are
 routed to their owner by the binning kernel itself, over NVLink peer memory
-(NCCL all-to-all where peer memory is unavailable).
+(NCCL all-to-all where peer memory is unavailable).  `--total-genome-mbp 3000`
+is BASELINE config 4 (whole genome, table hash-partitioned across the GPUs): the
+genome is divided by N, samples come as lists of streams and the child count takes
+as many hash-range passes as the memory plan asks for.
 `e2e` is the same call on pinned HOST buffers in the decoder's batch format
 (codes + the sparse validity list), H2D and D2H inside the timed region.
+`parity_checked`: in the same run, the same chain (same N, same routes) on a bounded
+sample is compared with the CPU port — stage sizes, the proband-unique keys and
+every per-read (ndistinct, nhits) — and the run FAILS on any difference.
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -34,6 +41,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "canonical k-mers/s counted+queried (trio discovery k-mer path)"
 UNIT = "k-mers/s"
+SAMPLES = ("child", "mother", "father", "ref")
 # algorithmic bytes per k-mer instance (SURVEY §8d / DESIGN.md "Roofline")
 ALGO_BYTES = {
     # insert+count: key read + count read + count write
@@ -66,15 +74,27 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--k", type=int, default=31)
     ap.add_argument("--genome-mbp", type=float, default=64.0, help="genome size per GPU (Mbp)")
+    ap.add_argument("--total-genome-mbp", type=float, default=0.0,
+                    help="whole-job genome size (Mbp), divided by the number of GPUs (BASELINE config 4: 3000)")
     ap.add_argument("--depth", type=float, default=30.0)
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--denovo", type=int, default=100)
     ap.add_argument("--cpu-sample-mbp", type=float, default=8.0,
-                    help="genome size of the bounded CPU sample (same depth)")
+                    help="genome size of the bounded CPU / parity sample (same depth)")
+    ap.add_argument("--n-passes", type=int, default=0, help="hash-range passes of the child count (0: memory plan)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-random-bench", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-k-sweep", action="store_true")
+    ap.add_argument("--no-wall", action="store_true", help="skip the BAM -> BED discovery wall time")
+    ap.add_argument("--wall-mbp", type=float, default=0.0,
+                    help="genome size of the BAM trio of the wall-time leg (0: the bench genome)")
+    args = ap.parse_args()
+    if args.total_genome_mbp:
+        world = max(int(os.environ.get("WORLD_SIZE", "1")), 1)
+        args.genome_mbp = args.total_genome_mbp / world
+    return args
 
 
 # --------------------------------------------------------------------------
@@ -148,6 +168,14 @@ class ClockSampler:
                 "power_w_max": float(max(pw)), "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def as_list(x):
+    return list(x) if isinstance(x, (list, tuple)) else [x]
+
+
+def one_or_list(xs):
+    return xs[0] if len(xs) == 1 else xs
+
+
 def stream_to_host(torch, s, pin):
     """Device packed-stream dict -> HostStream on (pinned) host memory."""
     from kmer_denovo_filter_b200 import engine
@@ -168,7 +196,7 @@ def stream_to_host(torch, s, pin):
         t[:inv.shape[0]].copy_(torch.from_numpy(inv.view(np.int32)))
         keep.append(t)
         hs.invalid = t.numpy().view(np.uint32)[:inv.shape[0]]
-    return hs, keep, host_bytes(hs, True)
+    return hs, keep
 
 
 def host_bytes(hs, with_reads):
@@ -185,23 +213,26 @@ def to_device_stream(engine_mod, s):
                                    s["read_lens"])
 
 
-def make_host_sample(torch, genome_bp, depth, read_len, denovo):
-    """The bounded CPU sample: same generator, smaller genome, host numpy."""
-    from kmer_denovo_filter_b200 import synth
-    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() \
-        else torch.device("cpu")
-    trio = synth.make_trio(torch, dev, int(genome_bp), depth=depth, read_len=read_len,
-                           n_denovo=denovo)
-    out = {}
-    for who in ("child", "mother", "father", "ref"):
-        s = trio[who]
-        out[who] = (s["codes"].cpu().numpy().view(np.uint64), s["valid"].cpu().numpy().view(np.uint32),
-                    s["n_bases"], s["read_starts"].cpu().numpy().view(np.uint64),
-                    s["read_lens"].cpu().numpy().view(np.uint32))
-    del trio
-    if torch.cuda.is_available():
-        torch.cuda.empty_cache()
-    return out
+def stream_host_tuple(s):
+    return (s["codes"].cpu().numpy().view(np.uint64), s["valid"].cpu().numpy().view(np.uint32),
+            int(s["n_bases"]), s["read_starts"].cpu().numpy().view(np.uint64),
+            s["read_lens"].cpu().numpy().view(np.uint32))
+
+
+def concat_host(parts):
+    """Several host stream tuples as one: parts are laid word after word (the bits between
+    a part's n_bases and its last word are invalid, i.e. separators)."""
+    if len(parts) == 1:
+        return parts[0]
+    codes = np.concatenate([p[0] for p in parts])
+    valid = np.concatenate([p[1] for p in parts])
+    starts, lens, w = [], [], 0
+    for p in parts:
+        starts.append(p[3] + np.uint64(32 * w))
+        lens.append(p[4])
+        w += p[0].shape[0]
+    n_bases = 32 * (w - parts[-1][0].shape[0]) + parts[-1][2]
+    return codes, valid, int(n_bases), np.concatenate(starts), np.concatenate(lens)
 
 
 def cpu_chain(sample, k, threads):
@@ -215,10 +246,38 @@ def cpu_chain(sample, k, threads):
     return res, dt
 
 
+def make_host_sample(torch, dev, genome_bp, depth, read_len, denovo, world=1):
+    """The bounded CPU / parity sample on the host: the union of the `world` rank shards the
+    GPU arm runs (same generator, same seeds), the whole reference."""
+    from kmer_denovo_filter_b200 import synth
+    parts = {w: [] for w in ("child", "mother", "father")}
+    for r in range(world):
+        trio = synth.make_trio(torch, dev, int(genome_bp), depth=depth, read_len=read_len,
+                               n_denovo=denovo, rank=r, world=world)
+        for w in parts:
+            parts[w].append(stream_host_tuple(trio[w]))
+        del trio
+    out = {w: concat_host(v) for w, v in parts.items()}
+    out["child_read_counts"] = [int(p[3].shape[0]) for p in parts["child"]]
+    ref = synth.pack_sequence_tensor(torch, synth.make_reference(torch, dev, int(genome_bp)))
+    out["ref"] = stream_host_tuple(ref)
+    if dev.type == "cuda":
+        torch.cuda.empty_cache()
+    return out
+
+
 def sample_text(args):
     return ("1 pass of the same chain over a synthetic trio of a %.0f Mbp genome at %gx "
-            "(same generator, read length, error/variant rates; %.3g of the GPU step's k-mers)"
+            "(same generator, read length, error/variant rates; %.3g of one GPU's k-mers per step)"
             % (args.cpu_sample_mbp, args.depth, args.cpu_sample_mbp / args.genome_mbp))
+
+
+def digest(lo, hi):
+    """sha256 of the sorted key list (hi:lo), the form both arms can produce."""
+    lo = np.asarray(lo, dtype=np.uint64)
+    hi = np.asarray(hi, dtype=np.uint64) if hi is not None else np.zeros_like(lo)
+    order = np.lexsort((lo, hi))
+    return hashlib.sha256(np.stack([hi[order], lo[order]], axis=1).tobytes()).hexdigest()[:16]
 
 
 # --------------------------------------------------------------------------
@@ -231,8 +290,10 @@ def run_reference(args):
         return 0
     import torch
     from oracle import ckdf
-    threads = ckdf.max_threads()
-    sample = make_host_sample(torch, args.cpu_sample_mbp * 1e6, args.depth, args.read_len,
+    threads = ckdf.max_threads()     # every core of the box, whatever OMP_NUM_THREADS torchrun exported
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))) if torch.cuda.is_available() \
+        else torch.device("cpu")
+    sample = make_host_sample(torch, dev, args.cpu_sample_mbp * 1e6, args.depth, args.read_len,
                               min(args.denovo, 100))
     for _ in range(args.warmup):
         cpu_chain(sample, args.k, threads)
@@ -247,7 +308,11 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64" if args.k <= 32 else "u128", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, max(args.gpus, 1)),
+        # what a step of THIS arm actually ran: the bounded sample of that workload
+        "ran": {"genome_bp_total": int(args.cpu_sample_mbp * 1e6), "depth": args.depth,
+                "units_per_step": units // max(args.steps, 1), "host_threads": threads,
+                "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": sample_text(args),
                          "note": "jellyfish/samtools/pysam are absent from this image; this is "
@@ -269,7 +334,7 @@ def workload_config(args, world):
         "k": args.k, "min_child_count": 3, "parent_max_count": 0,
         "genome_bp_total": int(args.genome_mbp * 1e6) * world,
         "table": "hash-partitioned across %d GPU(s)" % world if world > 1 else "single GPU",
-        "l2_policy": "inputs (0.7 GB per sample) and the child table (GBs) are larger than L2; no flush",
+        "l2_policy": "inputs (0.7 GB per sample per 64 Mbp) and the child table (GBs) are larger than L2; no flush",
     }
 
 
@@ -297,33 +362,39 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     eng = engine.CudaEngine(dev)   # raises if the library or a GPU is missing: no fallback
+    n_passes = args.n_passes or None
 
     # ---- synthetic trio, resident in HBM ---------------------------------
     genome_bp = int(args.genome_mbp * 1e6) * world
+    t_gen = time.perf_counter()
     trio = synth.make_trio(torch, dev, genome_bp, depth=args.depth, read_len=args.read_len,
                            n_denovo=args.denovo, rank=rank, world=world)
-    d = {w: to_device_stream(engine, trio[w]) for w in ("child", "mother", "father", "ref")}
+    d = {w: one_or_list([to_device_stream(engine, s) for s in as_list(trio[w])]) for w in SAMPLES}
     torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    t_gen = time.perf_counter() - t_gen
 
     if world > 1:
         from kmer_denovo_filter_b200.discovery import kmer_chain_dist
-        def step(streams):
+
+        def step(streams, k=None):
             return kmer_chain_dist.discover_streams_dist(
                 eng, streams["child"], streams["mother"], streams["father"], streams["ref"],
-                args.k, fetch=False)
+                k or args.k, fetch=False, n_passes=n_passes)
     else:
-        def step(streams):
+        def step(streams, k=None):
             return kmer_chain.discover_streams(
                 eng, streams["child"], streams["mother"], streams["father"], streams["ref"],
-                args.k, fetch=False)
+                k or args.k, fetch=False, n_passes=n_passes)
 
     # valid k-mer instances of each resident stream (exact, measured once: a probe
     # pass against an empty table), for the per-kernel roofline arithmetic
     windows = {}
     tiny = eng.new_table(args.k, n_keys=16)
-    for wname in ("child", "mother", "father", "ref"):
+    for wname in SAMPLES:
         st0 = eng.new_stats()
-        eng.count_stream(tiny, d[wname], engine.MODE_COUNT_IF_PRESENT, 0, 1, st0)
+        for s in as_list(d[wname]):
+            eng.count_stream(tiny, s, engine.MODE_COUNT_IF_PRESENT, 0, 1, st0)
         windows[wname] = eng.read_stats(st0)["windows"]
     tiny.close()
 
@@ -332,7 +403,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_region(streams, n_steps):
+    def timed_region(streams, n_steps, k=None):
         """-> (device ms max over ranks, units summed over ranks, last result)."""
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
@@ -341,7 +412,7 @@ def main():
         units = 0
         res = None
         for _ in range(n_steps):
-            res = step(streams)
+            res = step(streams, k)
             units += res["units"]
         ev1.record()
         barrier()
@@ -358,6 +429,7 @@ def main():
     # ---- device-resident: warm-up, then K timed steps ---------------------
     for _ in range(args.warmup):
         step(d)
+    torch.cuda.reset_peak_memory_stats(dev)
     eng.timers = {}
     launches0 = eng.launches
     clocks = ClockSampler(local)
@@ -369,8 +441,9 @@ def main():
     ktimes = eng.kernel_times_ms()
     eng.timers = None
     value = units / (ms * 1e-3)
+    peak_hbm = int(torch.cuda.max_memory_allocated(dev))
 
-    # ---- roofline of the dominant kernel ---------------------------------
+    # ---- roofline of the dominant call -----------------------------------
     kw = 1 if args.k <= 32 else 2
     per_kernel = {n: {"launches": len(v), "ms_total": float(sum(v)), "ms_avg": float(np.mean(v))}
                   for n, v in ktimes.items()}
@@ -381,27 +454,30 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     in_bytes = args.read_len / (4.0 * (args.read_len - args.k + 1))
+    passes = int(res.get("n_passes", 1) or 1)
 
     def kmers_per_launch(name):
         """valid k-mer instances one launch of this (timed) call processes, averaged
-        over its launches in the step"""
+        over its launches in the step (a multi-pass count re-reads the stream once per
+        pass but bins every k-mer once: the algorithmic work is the k-mers)"""
+        per_step = max(per_kernel[name]["launches"] / float(args.steps), 1.0)
         if name.startswith(("count_stream/mode2", "update_bins/mode2")):
             binned = name.startswith("update_bins")
             sel = [w for w, b in zip(("mother", "father"), res.get("parents_binned", [False, False]))
                    if bool(b) == binned] or ["mother", "father"]
-            return sum(windows[w] for w in sel) / max(per_kernel[name]["launches"] / float(args.steps), 1.0)
+            return sum(windows[w] for w in sel) / per_step
         if name.startswith("bin_stream"):
             # child + reference, and the parents that took the binned route (filter table > L2)
             tot = windows["child"] + windows["ref"]
             for who, b in zip(("mother", "father"), res.get("parents_binned", [])):
                 tot += windows[who] if b else 0
-            return tot / max(per_kernel[name]["launches"] / float(args.steps), 1.0)
+            return tot / per_step
         if name.startswith("count_bins"):
-            return float(windows["child"])
+            return float(windows["child"]) / per_step
         if name.startswith(("scan_stream_hits", "scan_reads", "count_stream/mode0")):
-            return float(windows["child"])
+            return float(windows["child"]) / per_step
         if name.startswith("bin_keys"):
-            return float(windows["child"] + windows["ref"]) / max(world, 1) / 2.0
+            return float(windows["child"] + windows["ref"]) / per_step
         return None
 
     def roofline_of(name):
@@ -419,23 +495,23 @@ def main():
                 "kernel_ms_avg": per_kernel[name]["ms_avg"],
                 "kernel_share_of_step": per_kernel[name]["ms_total"] / ms, "traffic": None}
 
-    # count_bins is a C call that launches 5 kernels per table slice; the dominant
-    # KERNEL is picked among single-kernel calls, count_bins is listed beside it
-    single = [n for n in per_kernel if not n.startswith(("count_bins", "reduce_hits", "table_clear"))
-              and kmers_per_launch(n) is not None]
-    dom = max(single, key=lambda n: per_kernel[n]["ms_total"]) if single else None
+    # the dominant call is the one with the largest total time in the step, whatever it
+    # launches (count_bins is a C call that runs three kernels per table slice)
+    timed = [n for n in per_kernel if kmers_per_launch(n) is not None]
+    dom = max(timed, key=lambda n: per_kernel[n]["ms_total"]) if timed else None
     roofline = roofline_of(dom) if dom else None
     roofline_all = [r for r in (roofline_of(n) for n in per_kernel) if r is not None]
-    if roofline is not None:
-        prof = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
-        if os.path.isfile(prof):
-            try:
-                t = json.load(open(prof))
-                if t.get("kernel") == dom:
-                    roofline["traffic"] = t.get("dram_bytes_per_launch")
-                    roofline["traffic_source"] = t.get("source")
-            except Exception:
-                pass
+    prof = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.isfile(prof):
+        try:
+            traffic = json.load(open(prof))
+            for r in ([roofline] if roofline else []) + roofline_all:
+                t = traffic.get(r["kernel"])
+                if t:
+                    r["traffic"] = t.get("dram_bytes_per_launch")
+                    r["traffic_source"] = t.get("source")
+        except Exception:
+            pass
 
     # ---- sector-granular random-access roofline (same box, same run) ------
     random_access = None
@@ -470,15 +546,33 @@ def main():
     if world > 1:
         dist.barrier()
 
+    # ---- k sweep (BASELINE config 5) on the same resident trio ------------
+    k_sweep = None
+    if not args.no_k_sweep and world == 1 and not args.total_genome_mbp:
+        k_sweep = {}
+        for kk in (21, 31, 47, 63):
+            if kk == args.k:
+                k_sweep[str(kk)] = {"value": value, "ms_per_step": ms / args.steps}
+                continue
+            for _ in range(2):
+                step(d, kk)
+            sms, sunits, sres = timed_region(d, 3, kk)
+            k_sweep[str(kk)] = {"value": sunits / (sms * 1e-3), "ms_per_step": sms / 3,
+                                "key_bits": 64 if kk <= 32 else 128,
+                                "proband_unique": int(sres["proband_unique"])}
+
     # ---- end to end: host buffers, H2D + D2H inside the timed region ------
     e2e = None
     if not args.no_e2e:
         hosts, keep, h2d = {}, [], 0
-        for w in ("child", "mother", "father", "ref"):
-            hs, kp, nb = stream_to_host(torch, trio[w], pin=True)
-            hosts[w] = hs
-            keep.append(kp)
-            h2d += nb if w == "child" else host_bytes(hs, False)
+        for w in SAMPLES:
+            hs_list = []
+            for s in as_list(trio[w]):
+                hs, kp = stream_to_host(torch, s, pin=True)
+                hs_list.append(hs)
+                keep.append(kp)
+                h2d += host_bytes(hs, w == "child")
+            hosts[w] = one_or_list(hs_list)
         del d
         del trio
         torch.cuda.empty_cache()
@@ -494,17 +588,30 @@ def main():
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "api": "kmer_denovo_filter_b200.discovery.kmer_chain.discover_streams(HostStream...) "
                       "-> libkdf_sm100 C ABI; pinned host buffers"}
+        del hosts, keep
+    else:
+        del d
+        del trio
+    torch.cuda.empty_cache()
 
-    # ---- CPU baseline (rank 0, N = 1 only) -------------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import ckdf
-        threads = ckdf.max_threads()
-        sample = make_host_sample(torch, args.cpu_sample_mbp * 1e6, args.depth, args.read_len,
-                                  min(args.denovo, 100))
-        cres, dt = cpu_chain(sample, args.k, threads)
-        cpu = {"value": cres["units"] / dt, "unit": UNIT, "cores": threads, "kind": "port",
-               "seconds": dt, "sample": sample_text(args)}
+    # ---- parity (every N) + CPU baseline (rank 0, N = 1): the CPU port on a bounded sample,
+    #      the GPU chain on the same sample with the routes of the run above ------------------
+    cpu, parity = None, None
+    if not args.no_parity or (world == 1 and not args.no_cpu_baseline):
+        parity, cpu = parity_and_cpu(args, torch, dist, eng, engine, synth, kmer_chain, step, res,
+                                     rank, world, dev, genome_bp)
+        if args.no_cpu_baseline or world > 1:
+            cpu = None
+
+    # ---- discovery wall time: BAM trio -> candidate BED through the product pipeline ------
+    wall = None
+    if not args.no_wall and world == 1 and not args.total_genome_mbp:
+        try:
+            from kmer_denovo_filter_b200 import wallbench
+        except ImportError:
+            wallbench = None
+        if wallbench is not None:
+            wall = wallbench.discovery_wall(args, eng, rank)
 
     if rank == 0:
         line = {
@@ -516,14 +623,110 @@ def main():
             "units_per_step": units // args.steps,
             "stage_sizes": {x: int(res[x]) for x in ("candidates", "non_ref", "after_mother",
                                                       "proband_unique", "informative_reads")},
-            "roofline": roofline, "roofline_all": roofline_all, "kernels": per_kernel, "random_access": random_access,
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+            "count_passes": passes, "peak_hbm_bytes_rank0": peak_hbm, "synth_seconds": t_gen,
+            "roofline": roofline, "roofline_all": roofline_all, "kernels": per_kernel,
+            "random_access": random_access, "parity_checked": parity,
+            "cpu_baseline": cpu, "e2e": e2e, "k_sweep": k_sweep, "discovery_wall": wall,
+            "gpu_launches": launches, "clocks": clk,
             "device": eng.props["name"],
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def parity_and_cpu(args, torch, dist, eng, engine, synth, kmer_chain, step, main_res, rank, world, dev,
+                   genome_bp):
+    """Run the GPU chain (this N, the routes the timed run took) on the bounded sample and
+    compare it with the CPU port on the union of the shards.  → (parity dict, cpu dict).
+    Raises SystemExit on any difference: a bench line is only printed for equal results."""
+    sample_bp = int(args.cpu_sample_mbp * 1e6)
+    den = min(args.denovo, 100)
+    trio = synth.make_trio(torch, dev, sample_bp, depth=args.depth, read_len=args.read_len,
+                           n_denovo=den, rank=rank, world=world)
+    ds = {w: to_device_stream(engine, trio[w]) for w in SAMPLES}
+    # same routes as the timed run: table slices scaled with the genome so that the sample is
+    # cut into as many hash ranges, and the parent route (filter / binned) forced to match
+    saved = (kmer_chain.SLICE_BYTES, kmer_chain.PROBE_DIRECT_BYTES, kmer_chain.L2_TABLE_BYTES,
+             os.environ.get("KDF_TABLE_FILTER"))
+    scale = max(sample_bp / float(max(genome_bp, 1)), 1e-4)
+    kmer_chain.SLICE_BYTES = max(1 << 20, int(saved[0] * min(scale, 1.0)))
+    binned = bool(main_res.get("parents_binned")) and all(main_res["parents_binned"])
+    if binned:
+        kmer_chain.PROBE_DIRECT_BYTES = 0
+        kmer_chain.L2_TABLE_BYTES = 0
+        os.environ["KDF_TABLE_FILTER"] = "0"
+    try:
+        got = step(ds)
+    finally:
+        kmer_chain.SLICE_BYTES, kmer_chain.PROBE_DIRECT_BYTES, kmer_chain.L2_TABLE_BYTES = saved[:3]
+        if saved[3] is None:
+            os.environ.pop("KDF_TABLE_FILTER", None)
+        else:
+            os.environ["KDF_TABLE_FILTER"] = saved[3]
+    sp = got["reads"] or {"read": np.zeros(0, np.uint64), "ndistinct": np.zeros(0, np.uint32),
+                          "nhits": np.zeros(0, np.uint32)}
+    mine = {"read": sp["read"], "nd": sp["ndistinct"], "nh": sp["nhits"]}
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+    else:
+        gathered = [mine]
+    out = (None, None)
+    if rank == 0:
+        from oracle import ckdf
+        threads = ckdf.max_threads()
+        sample = make_host_sample(torch, dev, sample_bp, args.depth, args.read_len, den, world)
+        want, dt = cpu_chain(sample, args.k, threads)
+        diffs = []
+        for key in ("candidates", "non_ref", "after_mother", "proband_unique"):
+            if int(got[key]) != int(want[key]):
+                diffs.append("%s: gpu %d != cpu %d" % (key, got[key], want[key]))
+        pu = got["pu"]
+        g_lo = pu.lo.cpu().numpy().view(np.uint64) if pu is not None else np.zeros(0, np.uint64)
+        g_hi = (pu.hi.cpu().numpy().view(np.uint64) if (pu is not None and pu.hi is not None)
+                else np.zeros_like(g_lo))
+        dg, dw = digest(g_lo, g_hi), digest(want["pu_lo"], want["pu_hi"])
+        if dg != dw:
+            diffs.append("proband-unique key digest: gpu %s != cpu %s" % (dg, dw))
+        n_reads, off, n_with_hits = 0, 0, 0
+        nd_w = want["nd"] if want["nd"] is not None else np.zeros(sum(sample["child_read_counts"]), np.uint32)
+        nh_w = want["nh"] if want["nh"] is not None else np.zeros_like(nd_w)
+        for r, cnt in enumerate(sample["child_read_counts"]):
+            nd = np.zeros(cnt, np.uint32)
+            nh = np.zeros(cnt, np.uint32)
+            idx = gathered[r]["read"].astype(np.int64)
+            nd[idx] = gathered[r]["nd"]
+            nh[idx] = gathered[r]["nh"]
+            if not (np.array_equal(nd, nd_w[off:off + cnt]) and np.array_equal(nh, nh_w[off:off + cnt])):
+                diffs.append("per-read (ndistinct, nhits) of rank %d's shard differ" % r)
+            n_with_hits += int((nh > 0).sum())
+            off += cnt
+            n_reads += cnt
+        parity = {"ok": not diffs, "against": "oracle/kdf_oracle.c (CPU port), same run",
+                  "sample": "%.0f Mbp genome x %gx trio, %d shard(s): the union of what the %d rank(s) ran"
+                            % (args.cpu_sample_mbp, args.depth, world, world),
+                  "routes": {"hash_ranges_per_gpu": int(got.get("n_passes", 1) or 1) * int(got.get("n_local", 1) or 1),
+                             "parents": "binned + update_bins" if binned else "stream probe behind the L2 filter / shared-memory table",
+                             "count_passes": int(got.get("n_passes", 1) or 1)},
+                  "stage_sizes": {x: int(want[x]) for x in ("candidates", "non_ref", "after_mother",
+                                                             "proband_unique")},
+                  "pu_digest": dw, "reads_compared": n_reads, "reads_with_hits": n_with_hits,
+                  "differences": diffs}
+        cpu = {"value": want["units"] / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "seconds": dt, "sample": sample_text(args)}
+        out = (parity, cpu)
+        if diffs:
+            sys.stderr.write("PARITY FAILURE: " + "; ".join(diffs) + "\n")
+    flag = torch.tensor([0 if (out[0] is None or out[0]["ok"]) else 1], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if int(flag.item()):
+        raise SystemExit("bench.py: GPU results differ from the CPU port on the parity sample")
+    del trio, ds
+    torch.cuda.empty_cache()
+    return out
 
 
 if __name__ == "__main__":

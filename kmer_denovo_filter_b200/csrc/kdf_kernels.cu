@@ -317,6 +317,9 @@ __device__ __forceinline__ u32 resolve_from(const TableView<KW>& t, u32 b, const
 #ifndef KDF_SMEM_CHUNK
 #define KDF_SMEM_CHUNK 4
 #endif
+#ifndef KDF_FILT_CHUNK
+#define KDF_FILT_CHUNK 8   // filter loads in flight per thread (k_stream<FILT>)
+#endif
 #ifndef KDF_SMEM_BLOCKS
 #define KDF_SMEM_BLOCKS 1
 #endif
@@ -526,28 +529,51 @@ __global__ void __launch_bounds__(SMEM ? 512 : 256, SMEM ? KDF_SMEM_BLOCKS : (KW
       Bucket<KW> bk[CHUNK];
       u32 bidx[CHUNK];
       u32 okm = 0, probe = 0, cand = 0;
+      if constexpr (FILT || SMEM) {
+        // filtered tables: one 32-bit load says "certainly absent" for almost every
+        // window.  The CHUNK loads are issued UNCONDITIONALLY and back to back (an
+        // invalid window reads a valid filter word it then ignores) and tested
+        // afterwards: as `if (ok) { load; test }` ptxas built one divergent region per
+        // window with the load's consumer right behind it — one load in flight per
+        // thread, long_scoreboard the top stall (profiles/r2a_ncu_k_stream_filtered.txt).
+        u32 fval[CHUNK], fbits[CHUNK];
 #pragma unroll
-      for (int u = 0; u < CHUNK; ++u) {
-        bool ok = it.ok(u);
-        keys[u] = it.key(u);
-        const u64 h = hash_key(keys[u]);
-        if (!FILT) bidx[u] = bucket_of(h, t.log2_parts, t.n_buckets);   // FILT: only candidates need it
-        if (ok) {
-          okm |= 1u << u;
+        for (int u = 0; u < CHUNK; ++u) {
+          keys[u] = it.key(u);
+          const u64 h = hash_key(keys[u]);
+          u32 word;
           if (FILT) {
-            // filtered table: one 32-bit load says "certainly absent" for almost every
-            // window; the few candidates are probed by the queue drain, all lanes busy
-            u32 word, bits;
-            gf_bits(h, t.filter_mask, word, bits);
-            if ((__ldg(t.filter + word) & bits) == bits) cand |= 1u << u;
-          } else if (SMEM) {
-            u32 word, bits;
-            pf_bits(h, word, bits);
-            if ((pf[word] & bits) == bits) {
-              probe |= 1u << u;
+            gf_bits(h, t.filter_mask, word, fbits[u]);
+            fval[u] = __ldg(t.filter + word);
+          } else {
+            pf_bits(h, word, fbits[u]);
+            fval[u] = pf[word];
+          }
+          okm |= it.ok(u) ? (1u << u) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < CHUNK; ++u)
+          if ((fval[u] & fbits[u]) == fbits[u]) cand |= 1u << u;
+        cand &= okm;
+        if (SMEM && cand) {   // the few candidates probe the shared-memory table
+#pragma unroll
+          for (int u = 0; u < CHUNK; ++u) {
+            if (cand & (1u << u)) {
+              bidx[u] = bucket_of(hash_key(keys[u]), t.log2_parts, t.n_buckets);
               bk[u] = lds_bucket<KW>(sm_keys + (u64)bidx[u] * 4 * KW);
             }
-          } else {
+          }
+          probe = cand;
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < CHUNK; ++u) {
+          bool ok = it.ok(u);
+          keys[u] = it.key(u);
+          const u64 h = hash_key(keys[u]);
+          bidx[u] = bucket_of(h, t.log2_parts, t.n_buckets);
+          if (ok) {
+            okm |= 1u << u;
             probe |= 1u << u;
             bk[u] = ld_bucket<KW>(t.keys + (u64)bidx[u] * 4 * KW);
           }
@@ -910,125 +936,10 @@ __device__ __noinline__ u32 pq_drain(PackedQueues<KW>* qp, TableView<KW> t, int 
   return packed;
 }
 
-// Split-phase form of the same queue (KDF_PQ_SPLIT, default on): a RING, drained oldest
-// first.  A drain ISSUES the compare-and-swaps of a batch and returns; their results
-// stay in registers, untouched, while the warp goes on with the next chunks, and are
-// checked ("retired") at the start of the next drain — ~3 chunks later, when the L2
-// round trip has long completed.  The entries of the batch in flight stay in the ring
-// (head is only moved when they retire), so a loser still finds its key and bucket.
-// Capacity: < 64 undrained + 64 in flight + <= 128 pushed by one chunk = 256.
-constexpr int PQ_RING = 256;
-template <int KW> struct PackedRing {
-  u64 lo[PQ_RING];
-  u64 hi[KW == 2 ? PQ_RING : 1];
-  u64 expect[PQ_RING];
-  u32 b[PQ_RING];
-  u32 info[PQ_RING];
-  u32 count;  // tail: items pushed so far (monotonic)
-  u32 head;   // first item not yet retired
-};
-template <int KW> struct PackedRings {
-  PackedRing<KW> fast;
-  SlowQueue<KW> slow;
-};
-template <int KW> struct PendingCas {
-  Key<KW> got[PQ_DRAIN / 32];
-  u32 n;  // items of the batch in flight (0: none)
-};
+template <int KW, int OP>
+using PackedKeysQueue = typename std::conditional<OP == OP_PACKED_COUNT, PackedQueues<KW>, SlowQueue<KW>>::type;
 
-template <int KW>
-__device__ __forceinline__ bool pr_push(PackedRing<KW>& q, const Key<KW>& key, u32 b, u32 info, u64 expect) {
-  // lanes race on this check, so leave a warp's worth of room
-  if (q.count - q.head >= (u32)(PQ_RING - 32)) return false;
-  const u32 o = atomicAdd(&q.count, 1u) & (u32)(PQ_RING - 1);
-  q.lo[o] = key.lo;
-  if (KW == 2) q.hi[o] = ((const u64*)&key)[KW - 1];
-  q.expect[o] = expect;
-  q.b[o] = b;
-  q.info[o] = info;
-  return true;
-}
-
-// all lanes: retire the batch in flight, then issue the next one (when `all`: until the
-// ring is empty, every batch retired).  Returns the tallies of the retired items.
-template <int KW>
-__device__ __forceinline__ u32 pr_drain(PackedRings<KW>* qp, PendingCas<KW>& pend, const TableView<KW>& t,
-                                        int sh, u32 sat, bool all) {
-  constexpr int S = SPB<KW>::v;
-  constexpr int R = PQ_DRAIN / 32;
-  PackedRing<KW>& q = qp->fast;
-  const unsigned lane = threadIdx.x & 31;
-  const u64 one = 1ull << sh;
-  const HitSink sink = {nullptr, nullptr, 0, nullptr};
-  __syncwarp();
-  const u32 tail = q.count;
-  u32 head = q.head;
-  u32 packed = 0;
-  for (;;) {
-    if (pend.n) {  // retire
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        if ((u32)(r * 32) + lane < pend.n) {
-          const u32 idx = (head + r * 32 + lane) & (u32)(PQ_RING - 1);
-          const u32 info = q.info[idx];
-          if ((info & 3u) == 1) {
-            if (((const u64*)&pend.got[r])[KW - 1] != q.expect[idx] || (KW == 2 && pend.got[r].lo != q.lo[idx]))
-              packed_bump(t.keys + ((u64)q.b[idx] * S + (info >> 2)) * KW + (KW - 1),
-                          ((const u64*)&pend.got[r])[KW - 1], sh, sat);
-          } else if (is_empty_key(pend.got[r])) {
-            packed += 1u << 10;
-          } else {  // the slot was taken meanwhile: probe from scratch, with the other such cases
-            Key<KW> key;
-            key.lo = q.lo[idx];
-            if (KW == 2) ((u64*)&key)[KW - 1] = q.hi[idx];
-            u32 code = sq_push_or_resolve<KW, OP_PACKED_COUNT>(qp->slow, t, q.b[idx], key, sh, sat, 0, sink);
-            packed += (code == R_HIT ? 1u : 0u) + (code == R_NEW ? (1u << 10) : 0u);
-            packed |= (code == R_FULL ? (1u << 20) : 0u);
-          }
-        }
-      }
-      head += pend.n;
-      pend.n = 0;
-      __syncwarp();
-    }
-    const u32 avail = tail - head;
-    if (!(avail >= (u32)PQ_DRAIN || (all && avail > 0))) break;
-    const u32 take = avail >= (u32)PQ_DRAIN ? (u32)PQ_DRAIN : avail;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {  // issue: nothing below looks at a result
-      if ((u32)(r * 32) + lane < take) {
-        const u32 idx = (head + r * 32 + lane) & (u32)(PQ_RING - 1);
-        const u32 info = q.info[idx];
-        Key<KW> key, want;
-        key.lo = q.lo[idx];
-        if (KW == 2) ((u64*)&key)[KW - 1] = q.hi[idx];
-        Key<KW> val = key;
-        want.lo = EMPTY;
-        if (KW == 2) ((u64*)&want)[KW - 1] = EMPTY;
-        if ((info & 3u) == 1) {  // bump: expect the slot as read, write state + 1
-          ((u64*)&want)[KW - 1] = q.expect[idx];
-          if (KW == 2) want.lo = key.lo;
-          ((u64*)&val)[KW - 1] = q.expect[idx] + one;
-        } else {                 // insert: expect the empty slot, write the key in state 1
-          ((u64*)&val)[KW - 1] |= one;
-        }
-        pend.got[r] = cas_slot(t.keys + ((u64)q.b[idx] * S + (info >> 2)) * KW, want, val);
-      }
-    }
-    pend.n = take;
-    if (!all) break;
-  }
-  if (lane == 0) q.head = head;
-  __syncwarp();
-  return packed;
-}
-
-template <int KW, int OP, bool SPLIT = false>
-using PackedKeysQueue = typename std::conditional<
-    OP == OP_PACKED_COUNT, typename std::conditional<SPLIT, PackedRings<KW>, PackedQueues<KW>>::type,
-    SlowQueue<KW>>::type;
-
-template <int KW, int OP, bool FILT, bool SPLIT = false>
+template <int KW, int OP, bool FILT>
 __global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_packed_keys(TableView<KW> t, const u64* lo, u64 n_max,
                                                      const u64* n_dev, int sh, u32 sat, u64* stats,
                                                      int filt_log2, u32 filt_val) {
@@ -1040,15 +951,12 @@ __global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_packed_keys(TableView<
     u64 nd = *n_dev;
     n = nd < n_max ? nd : n_max;
   }
-  using Queue = PackedKeysQueue<KW, OP, SPLIT>;
+  using Queue = PackedKeysQueue<KW, OP>;
   extern __shared__ __align__(16) unsigned char pk_smem[];   // one queue per warp
   Queue& q = reinterpret_cast<Queue*>(pk_smem)[threadIdx.x >> 5];
-  PendingCas<KW> pend;
-  pend.n = 0;
   if ((threadIdx.x & 31) == 0) {
     if constexpr (OP == OP_PACKED_COUNT) {
       q.fast.count = 0;
-      if constexpr (SPLIT) q.fast.head = 0;
       q.slow.count = 0;
     } else {
       q.count = 0;
@@ -1096,7 +1004,9 @@ __global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_packed_keys(TableView<
     }
   };
   // stage 3: resolve.  A saturated copy is done once its bucket has been read; a
-  // copy that needs an atomic is queued (see PackedQueue).
+  // copy that needs an atomic is queued (see PackedQueue) — through ONE push site for
+  // bumps and inserts alike: what a key owes is first reduced to (kind, slot, expected
+  // word), so the queue code is executed once per chunk position, not once per kind.
   auto resolve = [&](const Key<KW>* keys, u32 okm, const u32* bidx, const Bucket<KW>* bk) {
     st.windows += __popc(okm);
     if constexpr (OP == OP_PACKED_COUNT) {
@@ -1104,16 +1014,12 @@ __global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_packed_keys(TableView<
       for (int u = 0; u < CHUNK; ++u) {
         if (okm & (1u << u)) {
           u64 ms = 0;
-          int j = match_packed(bk[u], keys[u], mask, ms);
+          const int j = match_packed(bk[u], keys[u], mask, ms);
+          u32 info = 0;   // kind (1 bump, 2 insert) | slot << 2; 0 = nothing owed
           if (j >= 0) {
             st.hits++;
 #ifndef KDF_DBG_NO_BUMP
-            if ((u32)(ms >> sh) < sat) {
-              bool queued;
-              if constexpr (SPLIT) queued = pr_push<KW>(q.fast, keys[u], bidx[u], 1u | ((u32)j << 2), ms);
-              else queued = pq_push<KW>(q.fast, keys[u], bidx[u], 1u | ((u32)j << 2), ms);
-              if (!queued) packed_bump(t.keys + ((u64)bidx[u] * S + j) * KW + (KW - 1), ms, sh, sat);
-            }
+            if ((u32)(ms >> sh) < sat) info = 1u | ((u32)j << 2);
 #endif
           } else {
 #ifndef KDF_DBG_NO_INSERT
@@ -1125,22 +1031,19 @@ __global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_packed_keys(TableView<
               u32 nb = (bidx[u] + 1 == t.n_buckets) ? 0 : bidx[u] + 1;
               tally(st, sq_push_or_resolve<KW, OP>(q.slow, t, nb, keys[u], sh, sat, 0, sink));
             } else {
-              bool queued;
-              if constexpr (SPLIT) queued = pr_push<KW>(q.fast, keys[u], bidx[u], 2u | ((u32)c << 2), 0ull);
-              else queued = pq_push<KW>(q.fast, keys[u], bidx[u], 2u | ((u32)c << 2), 0ull);
-              if (!queued) tally(st, resolve_packed_count<KW>(t, bidx[u], keys[u], sh, sat));
+              info = 2u | ((u32)c << 2);
+              ms = 0;
             }
 #endif
+          }
+          if (info && !pq_push<KW>(q.fast, keys[u], bidx[u], info, ms)) {   // queue full: in place
+            if ((info & 3u) == 1) packed_bump(t.keys + ((u64)bidx[u] * S + (info >> 2)) * KW + (KW - 1), ms, sh, sat);
+            else tally(st, resolve_packed_count<KW>(t, bidx[u], keys[u], sh, sat));
           }
         }
       }
       __syncwarp();
-      if constexpr (SPLIT) {
-        // 64 items beyond the batch in flight: retire that batch, issue the next
-        if (q.fast.count - q.fast.head >= pend.n + (u32)PQ_DRAIN) tally_packed(st, pr_drain<KW>(&q, pend, t, sh, sat, false));
-      } else {
-        if (q.fast.count >= (u32)PQ_DRAIN) tally_packed(st, pq_drain<KW>(&q, t, sh, sat, false));
-      }
+      if (q.fast.count >= (u32)PQ_DRAIN) tally_packed(st, pq_drain<KW>(&q, t, sh, sat, false));
       if (q.slow.count >= 32) tally_packed(st, sq_drain<KW, OP>(&q.slow, t, sh, sat, sink, false));
     } else {
       // probing ops: OP_PACKED_MARK on a packed slice, or COUNT_IF_PRESENT /
@@ -1194,8 +1097,7 @@ __global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_packed_keys(TableView<
     mB = mC;
   }
   if constexpr (OP == OP_PACKED_COUNT) {
-    if constexpr (SPLIT) tally_packed(st, pr_drain<KW>(&q, pend, t, sh, sat, true));
-    else tally_packed(st, pq_drain<KW>(&q, t, sh, sat, true));
+    tally_packed(st, pq_drain<KW>(&q, t, sh, sat, true));
     tally_packed(st, sq_drain<KW, OP>(&q.slow, t, sh, sat, sink, true));
   } else {
     tally_packed(st, sq_drain<KW, OP>(&q, t, sh, sat, sink, true));
@@ -2113,15 +2015,15 @@ static int dispatch_stream(const kdf_table* t, const StreamView& v, int op, int 
       return launch_stream<KW, OP_INSERT_ONLY, false, KDF_STREAM_CHUNK>(t, v, plane, arg, stats, sink, st);
     case OP_COUNT_IF_PRESENT:
       if (small) return launch_stream<KW, OP_COUNT_IF_PRESENT, true, KDF_SMEM_CHUNK>(t, v, plane, arg, stats, sink, st);
-      if (filt) return launch_stream<KW, OP_COUNT_IF_PRESENT, false, KDF_STREAM_CHUNK, true>(t, v, plane, arg, stats, sink, st);
+      if (filt) return launch_stream<KW, OP_COUNT_IF_PRESENT, false, KDF_FILT_CHUNK, true>(t, v, plane, arg, stats, sink, st);
       return launch_stream<KW, OP_COUNT_IF_PRESENT, false, KDF_STREAM_CHUNK>(t, v, plane, arg, stats, sink, st);
     case OP_MARK_IF_PRESENT:
       if (small) return launch_stream<KW, OP_MARK_IF_PRESENT, true, KDF_SMEM_CHUNK>(t, v, plane, arg, stats, sink, st);
-      if (filt) return launch_stream<KW, OP_MARK_IF_PRESENT, false, KDF_STREAM_CHUNK, true>(t, v, plane, arg, stats, sink, st);
+      if (filt) return launch_stream<KW, OP_MARK_IF_PRESENT, false, KDF_FILT_CHUNK, true>(t, v, plane, arg, stats, sink, st);
       return launch_stream<KW, OP_MARK_IF_PRESENT, false, KDF_STREAM_CHUNK>(t, v, plane, arg, stats, sink, st);
     case OP_EMIT_HITS:
       if (small) return launch_stream<KW, OP_EMIT_HITS, true, KDF_SMEM_CHUNK>(t, v, plane, arg, stats, sink, st);
-      if (filt) return launch_stream<KW, OP_EMIT_HITS, false, KDF_STREAM_CHUNK, true>(t, v, plane, arg, stats, sink, st);
+      if (filt) return launch_stream<KW, OP_EMIT_HITS, false, KDF_FILT_CHUNK, true>(t, v, plane, arg, stats, sink, st);
       return launch_stream<KW, OP_EMIT_HITS, false, KDF_STREAM_CHUNK>(t, v, plane, arg, stats, sink, st);
     default:
       return fail(KDF_ERR_ARG, "unknown table operation");
@@ -2201,38 +2103,25 @@ static int launch_emit_buckets(const kdf_table* t, u32 min0, u32 max0, u32 min1,
   return KDF_OK;
 }
 
-static bool pq_split_enabled() {
-  static const int v = env_int("KDF_PQ_SPLIT", 1);
-  return v != 0;
-}
-
-template <int KW, int OP, bool FILT, bool SPLIT>
-static int launch_packed_keys_impl(const kdf_table* t, const u64* lo, u64 n_max, const u64* n_dev, int sh,
-                                   u32 sat, u64* stats, cudaStream_t st, int filt_log2, u32 filt_val) {
-  TableView<KW> tv = view_of_table<KW>(t);
-  const size_t smem = sizeof(PackedKeysQueue<KW, OP, SPLIT>) * (256 / 32);
-  const u64 items = (n_max + KDF_KEYS_CHUNK - 1) / KDF_KEYS_CHUNK;
-  const void* fn = (const void*)k_packed_keys<KW, OP, FILT, SPLIT>;
-  CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int g = grid_for(fn, 256, smem, items, t->sm_count);
-  k_packed_keys<KW, OP, FILT, SPLIT><<<g, 256, smem, st>>>(tv, lo, n_max, n_dev, sh, sat, stats, filt_log2, filt_val);
-  CUDA_TRY(cudaGetLastError());
-  return KDF_OK;
-}
-
 template <int KW, int OP>
 static int launch_packed_keys(const kdf_table* t, const u64* lo, u64 n_max, const u64* n_dev, int sh,
                               u32 sat, u64* stats, cudaStream_t st, int filt_log2, u32 filt_val) {
-  if constexpr (OP == OP_PACKED_COUNT) {
-    if (pq_split_enabled()) {
-      if (filt_log2 > 0)
-        return launch_packed_keys_impl<KW, OP, true, true>(t, lo, n_max, n_dev, sh, sat, stats, st, filt_log2, filt_val);
-      return launch_packed_keys_impl<KW, OP, false, true>(t, lo, n_max, n_dev, sh, sat, stats, st, 0, 0);
-    }
+  TableView<KW> tv = view_of_table<KW>(t);
+  const size_t smem = sizeof(PackedKeysQueue<KW, OP>) * (256 / 32);
+  const u64 items = (n_max + KDF_KEYS_CHUNK - 1) / KDF_KEYS_CHUNK;
+  if (filt_log2 > 0) {
+    const void* fn = (const void*)k_packed_keys<KW, OP, true>;
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int g = grid_for(fn, 256, smem, items, t->sm_count);
+    k_packed_keys<KW, OP, true><<<g, 256, smem, st>>>(tv, lo, n_max, n_dev, sh, sat, stats, filt_log2, filt_val);
+  } else {
+    const void* fn = (const void*)k_packed_keys<KW, OP, false>;
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int g = grid_for(fn, 256, smem, items, t->sm_count);
+    k_packed_keys<KW, OP, false><<<g, 256, smem, st>>>(tv, lo, n_max, n_dev, sh, sat, stats, 0, 0);
   }
-  if (filt_log2 > 0)
-    return launch_packed_keys_impl<KW, OP, true, false>(t, lo, n_max, n_dev, sh, sat, stats, st, filt_log2, filt_val);
-  return launch_packed_keys_impl<KW, OP, false, false>(t, lo, n_max, n_dev, sh, sat, stats, st, 0, 0);
+  CUDA_TRY(cudaGetLastError());
+  return KDF_OK;
 }
 
 template <int KW>

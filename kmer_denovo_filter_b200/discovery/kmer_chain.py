@@ -137,7 +137,16 @@ def bin_budget_bytes(eng):
     if env:
         return int(float(env) * (1 << 30))
     fn = getattr(eng, "free_device_bytes", None)
-    return int(fn() * 0.5) if fn is not None else 1 << 62
+    if fn is None:
+        return 1 << 62
+    # cudaMemGetInfo takes the driver lock (measured: several ms per call while nvidia-smi
+    # polls the device, as bench.py's clock sampler does), so the answer is kept for a while
+    import time
+    now = time.monotonic()
+    cached = getattr(eng, "_bin_budget", None)
+    if cached is None or now - cached[0] > 30.0:
+        cached = eng._bin_budget = (now, int(fn() * 0.5))
+    return cached[1]
 
 
 def plan_child_count(eng, n_child, n_ref, k, min_child_count, n_parts=None, slice_capacity=None,
@@ -437,6 +446,7 @@ def discover_streams(eng, child, mother, father, ref, k, min_child_count=3,
     out = {"child_windows": child_windows, "child_distinct": child_distinct,
            "child_capacity": child_capacity, "candidates": n_cand,
            "n_passes": c["n_passes"] if partitioned else 1,
+           "n_local": c["n_parts"] if partitioned else 1,
            "non_ref": n_nonref, "after_mother": 0, "proband_unique": 0,
            "pu": None, "ndistinct": None, "nhits": None, "informative_reads": 0, "hits": None,
            "reads": None, "parents_binned": []}

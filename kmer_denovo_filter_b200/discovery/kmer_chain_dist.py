@@ -349,7 +349,7 @@ def discover_streams_dist(eng, child, mother, father, ref, k, min_child_count=3,
            "candidates": int(tot[0].item()), "non_ref": int(lo.shape[0]), "after_mother": 0,
            "proband_unique": 0, "pu": None, "ndistinct": None, "nhits": None,
            "informative_reads": 0, "reads": None, "hits": None, "parents_binned": [],
-           "n_passes": c["n_passes"]}
+           "n_passes": c["n_passes"], "n_local": c["n_local"]}
     units = c["child_windows"] + c["ref_windows"]
 
     n_pu = 0

@@ -158,11 +158,31 @@ def pack_sequence_tensor(torch, seq_codes):
             "read_lens": torch.tensor([min(n, 2**31 - 1)], dtype=torch.int32, device=seq_codes.device)}
 
 
+# one packed stream addresses its bases with 32 bits in the PCIe (sparse validity) format
+MAX_STREAM_BASES = 1 << 31
+
+
+def _reads_in_parts(torch, haps, pairs, read_len, seed, max_stream_bases):
+    """``make_reads``, as ONE stream dict when the reads fit ``max_stream_bases`` bases,
+    else as a list of stream dicts (a whole-genome sample on few GPUs)."""
+    per_part = max(16, (max_stream_bases // (2 * (read_len + 1))) // 16 * 16)
+    if pairs <= per_part:
+        return make_reads(torch, haps, pairs, read_len, seed)
+    parts, done, i = [], 0, 0
+    while done < pairs:
+        m = min(per_part, pairs - done)
+        parts.append(make_reads(torch, haps, m, read_len, seed + 100003 * (i + 1)))
+        done += m
+        i += 1
+    return parts
+
+
 def make_trio(torch, device, genome_bp, depth=30, read_len=150, n_denovo=100, rank=0, world=1,
-              seed=1000):
+              seed=1000, max_stream_bases=MAX_STREAM_BASES, keep_genomes=False):
     """Generate the trio; each rank gets 1/world of every sample's reads.
 
-    Returns dict(ref, child, mother, father: packed stream dicts; events; genome_bp)."""
+    Returns dict(ref, child, mother, father: packed stream dicts — or lists of them when a
+    sample exceeds ``max_stream_bases`` —; events; genome_bp)."""
     ref = make_reference(torch, device, genome_bp, seed)
     m0, m1 = make_haplotype(torch, ref, 2000), make_haplotype(torch, ref, 2001)
     f0, f1 = make_haplotype(torch, ref, 3000), make_haplotype(torch, ref, 3001)
@@ -171,12 +191,15 @@ def make_trio(torch, device, genome_bp, depth=30, read_len=150, n_denovo=100, ra
     pairs_total = int(depth * genome_bp / (2 * read_len))
     pairs = pairs_total // world
     out = {"genome_bp": genome_bp, "events": events}
-    out["child"] = make_reads(torch, [child_a, child_b], pairs, read_len, 5000 + 10 * rank)
-    out["mother"] = make_reads(torch, [m0, m1], pairs, read_len, 5001 + 10 * rank)
-    out["father"] = make_reads(torch, [f0, f1], pairs, read_len, 5002 + 10 * rank)
+    out["child"] = _reads_in_parts(torch, [child_a, child_b], pairs, read_len, 5000 + 10 * rank,
+                                   max_stream_bases)
+    out["mother"] = _reads_in_parts(torch, [m0, m1], pairs, read_len, 5001 + 10 * rank, max_stream_bases)
+    out["father"] = _reads_in_parts(torch, [f0, f1], pairs, read_len, 5002 + 10 * rank, max_stream_bases)
     # reference shard of this rank, overlapping the next shard by read_len bases
     lo = genome_bp * rank // world
     hi = min(genome_bp, genome_bp * (rank + 1) // world + 64)
     out["ref"] = pack_sequence_tensor(torch, ref[lo:hi])
     out["ref_full_bp"] = genome_bp
+    if keep_genomes:     # the BAM writer of the end-to-end benchmark needs them
+        out["genomes"] = {"ref": ref, "child": [child_a, child_b], "mother": [m0, m1], "father": [f0, f1]}
     return out

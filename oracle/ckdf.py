@@ -48,7 +48,14 @@ def _p(a):
 
 
 def max_threads():
-    return int(lib().okdf_max_threads())
+    """Host threads the timed CPU legs use: every core this process may run on.  NOT
+    ``omp_get_max_threads()``: torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    made the reference arm single-threaded (and time out) at N > 1 in round 1; the C
+    functions take their thread count as an argument (``num_threads(threads)``)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 class Table:

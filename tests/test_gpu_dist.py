@@ -35,7 +35,15 @@ def _union(torch, a, b):
             "read_lens": torch.cat([a["read_lens"], b["read_lens"]])}
 
 
-def _worker(rank, world, port, k, q, peer=True):
+def _host(s):
+    import numpy as np
+    return (s["codes"].cpu().numpy().view(np.uint64), s["valid"].cpu().numpy().view(np.uint32),
+            s["n_bases"], s["read_starts"].cpu().numpy().view(np.uint64),
+            s["read_lens"].cpu().numpy().view(np.uint32))
+
+
+def _worker(rank, world, port, k, q, peer=True, n_passes=None):
+    import numpy as np
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -44,18 +52,23 @@ def _worker(rank, world, port, k, q, peer=True):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         from kmer_denovo_filter_b200 import engine, synth
-        from kmer_denovo_filter_b200.discovery import kmer_chain, kmer_chain_dist
+        from kmer_denovo_filter_b200.discovery import kmer_chain_dist
         eng = engine.CudaEngine(dev)
         eng.peer_bins = peer     # True: NVLink peer-memory route; False: NCCL all-to-all route
         assert kmer_chain_dist.peer_memory_available(eng) == peer
         trio = synth.make_trio(torch, dev, GENOME, depth=DEPTH, n_denovo=20, rank=rank, world=world)
         res = kmer_chain_dist.discover_streams_dist(
             eng, _dev(engine, trio["child"]), _dev(engine, trio["mother"]),
-            _dev(engine, trio["father"]), _dev(engine, trio["ref"]), k)
+            _dev(engine, trio["father"]), _dev(engine, trio["ref"]), k, fetch=True, n_passes=n_passes)
+        if n_passes:
+            assert res["n_passes"] == n_passes
         sizes = {x: res[x] for x in ("candidates", "non_ref", "after_mother", "proband_unique",
-                                     "child_distinct", "informative_reads")}
+                                     "informative_reads")}
         pu = sorted(res["pu"].to_pyints())
+        per_read = (res["ndistinct"], res["nhits"])
         if rank == 0:
+            # the checker: the CPU oracle over the union of all ranks' shards
+            from oracle import ckdf
             shards = [trio] + [synth.make_trio(torch, dev, GENOME, depth=DEPTH, n_denovo=20,
                                                rank=r, world=world) for r in range(1, world)]
             u = {}
@@ -63,36 +76,49 @@ def _worker(rank, world, port, k, q, peer=True):
                 acc = shards[0][w]
                 for s in shards[1:]:
                     acc = _union(torch, acc, s[w])
-                u[w] = acc
-            full = synth.make_trio(torch, dev, GENOME, depth=0.2, n_denovo=20)
-            one = kmer_chain.discover_streams(eng, _dev(engine, u["child"]), _dev(engine, u["mother"]),
-                                              _dev(engine, u["father"]), _dev(engine, full["ref"]), k)
-            want = {x: one[x] for x in sizes}
-            q.put((rank, sizes, pu, want, sorted(one["pu"].to_pyints())))
+                u[w] = _host(acc)
+            ref = _host(synth.pack_sequence_tensor(torch, synth.make_reference(torch, dev, GENOME)))
+            want = ckdf.discovery_chain(u["child"], u["mother"][:3], u["father"][:3], ref[:3], k,
+                                        threads=ckdf.max_threads())
+            want_pu = sorted((int(h) << 64) | int(l) for l, h in
+                             zip(want["pu_lo"].tolist(), want["pu_hi"].tolist()))
+            k4 = max(1, k // 4)
+            want_sizes = {x: want[x] for x in ("candidates", "non_ref", "after_mother", "proband_unique")}
+            want_sizes["informative_reads"] = int((want["nd"] >= k4).sum())
+            counts = [int(s["child"]["read_starts"].shape[0]) for s in shards]
+            q.put((rank, sizes, pu, per_read, want_sizes, want_pu, (want["nd"], want["nh"], counts)))
         else:
-            q.put((rank, sizes, pu, None, None))
+            q.put((rank, sizes, pu, per_read, None, None, None))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("peer", [True, False])
+@pytest.mark.parametrize("peer,n_passes", [(True, None), (False, None), (True, 2), (False, 4)])
 @pytest.mark.parametrize("k", [31, 47])
-def test_dist_chain_equals_single_gpu(k, peer):
+def test_dist_chain_equals_oracle(k, peer, n_passes):
+    """The distributed chain (both routes, one and several hash-range passes) against the
+    CPU oracle over the union of the shards: stage sizes, proband-unique keys, and every
+    rank's per-read (ndistinct, nhits)."""
+    import numpy as np
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, k, q, peer)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, k, q, peer, n_passes)) for r in range(world)]
     for p in procs:
         p.start()
     got = [q.get(timeout=600) for _ in procs]
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    want = next(g for g in got if g[3] is not None)
-    assert want[3]["proband_unique"] > 0
-    for rank, sizes, pu, _w, _p in got:
-        assert sizes == want[3], (rank, sizes, want[3])
-        assert pu == want[4]
+    want = next(g for g in got if g[4] is not None)
+    assert want[4]["proband_unique"] > 0
+    nd_w, nh_w, counts = want[6]
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    for rank, sizes, pu, per_read, _w, _p, _r in got:
+        assert sizes == want[4], (rank, sizes, want[4])
+        assert pu == want[5]
+        assert np.array_equal(per_read[0], nd_w[offs[rank]:offs[rank + 1]])
+        assert np.array_equal(per_read[1], nh_w[offs[rank]:offs[rank + 1]])
