@@ -485,6 +485,11 @@ typedef struct kdf_bam_batch {
                                     150-base reads; kdf_valid_from_invalid rebuilds the bitmap on
                                     the device so that only codes + this list cross PCIe          */
   uint64_t n_invalid;
+  const uint64_t* rec_uoff;      /* HOST n_reads: offset of the record in the file's uncompressed
+                                    stream (argument of kdf_bam_fetch_records)                   */
+  const uint8_t* fasta_keep;     /* HOST n_reads: 1 = the record is part of the KDF_BAM_FASTA stream
+                                    (set in every mode: a scan-mode decode + this mask gives the
+                                    counting stream of the same file without a second pass)      */
 } kdf_bam_batch;
 
 int kdf_bam_open(const char* path, int n_threads, kdf_bam** out);
@@ -497,6 +502,23 @@ int kdf_bam_next_batch(kdf_bam* b, int mode, uint64_t max_bases, int want_meta,
                        kdf_bam_batch* out);
 void kdf_bam_batch_free(kdf_bam_batch* batch);
 const char* kdf_host_last_error(void);
+/* The raw BAM records (bytes after block_size) at the given uncompressed offsets
+ * (kdf_bam_batch.rec_uoff of records this reader has already decoded), by inflating
+ * only the blocks that hold them: what the informative-reads BAM writer needs
+ * (discovery/pipeline.py:1979-2079) without decoding the file once more.
+ * out_off[n+1] receives the record boundaries, *needed the total size; records are
+ * copied only while they fit out_cap (call again with a larger buffer).          */
+int kdf_bam_fetch_records(kdf_bam* b, const uint64_t* uoffs /*HOST*/, uint64_t n,
+                          uint8_t* out /*HOST or NULL*/, uint64_t out_cap,
+                          uint64_t* out_off /*HOST n+1*/, uint64_t* needed);
+/* `data` as a BGZF file (multi-threaded deflate + EOF marker): the container of the
+ * informative-reads BAM and of the bgzip'd annotated VCF (vcf/pipeline.py:1307-1357,
+ * :1640-1700; the reference writes them through pysam / bgzip).  block_coff (HOST,
+ * block_cap entries, may be NULL) receives the file offset of every block (and of the
+ * EOF block) for BAI / TBI virtual offsets; blocks hold 0xff00 input bytes each.    */
+int kdf_bgzf_write(const char* path, const uint8_t* data /*HOST*/, uint64_t n, int level,
+                   int n_threads, uint64_t* block_coff /*HOST or NULL*/, uint64_t block_cap,
+                   uint64_t* n_blocks);
 
 /* Test hook: runs the device window-iterator templates on the CPU (host
  * instantiation of the same code) so the bit manipulation can be verified

@@ -33,6 +33,7 @@ class _Batch(ctypes.Structure):
         ("qname_blob", _vp), ("cigar_off", _vp), ("cigar_blob", _vp),
         ("sa_off", _vp), ("sa_blob", _vp), ("qual_off", _vp), ("qual_blob", _vp), ("raw_off", _vp), ("raw_blob", _vp),
         ("at_eof", _i), ("has_invalid", _i), ("invalid_pos", _vp), ("n_invalid", _u64),
+        ("rec_uoff", _vp), ("fasta_keep", _vp),
     ]
 
 
@@ -195,6 +196,8 @@ class HostBatch(_engine.HostStream):
         if raw.has_invalid:   # sparse form of `valid`: uploads send this list instead of the bitmap
             self.invalid = _arr(raw.invalid_pos, int(raw.n_invalid), np.uint32)
         self.rec_index = _arr(raw.rec_index, n, np.uint64)
+        self.rec_uoff = _arr(raw.rec_uoff, n, np.uint64)       # kdf_bam_fetch_records keys
+        self.fasta_keep = _arr(raw.fasta_keep, n, np.uint8)    # member of the MODE_FASTA stream
         self.at_eof = bool(raw.at_eof)
         self.has_meta = bool(want_meta)
         if want_meta:

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/mman.h>
+#include <sys/types.h>
 #include <zlib.h>
 
 #include <memory>
@@ -54,6 +55,7 @@ struct CompBuf {
   std::vector<uint8_t, NoInitAlloc<uint8_t>> bytes;
   std::vector<BlockRef> blocks;
   uint64_t total_u = 0;
+  uint64_t ustart = 0;   // offset of its first byte in the file's uncompressed stream
   bool valid = false;
 };
 
@@ -61,7 +63,9 @@ struct CompBuf {
 struct Kept {
   const uint8_t* rec;  // the record body (inside one of the chunk buffers)
   uint64_t start;      // stream position of its first base
+  uint64_t uoff;       // offset of the record (its block_size word) in the uncompressed stream
   uint32_t l_seq;
+  uint8_t fasta_keep;  // KDF_BAM_FASTA would keep this record
 };
 
 // an inflated chunk: logical bytes data[begin .. size), `begin` leaves headroom for the
@@ -69,6 +73,8 @@ struct Kept {
 struct Chunk {
   uint8_t* data = nullptr;
   size_t begin = 0, size = 0, cap = 0;
+  size_t own = 0;        // where the chunk's own first byte sits (bytes before it: the previous chunk's tail)
+  uint64_t ustart = 0;   // uncompressed-stream offset of data[own]
   bool valid = false;
 };
 
@@ -80,7 +86,15 @@ struct Bam {
   std::string header_text;
   std::vector<uint8_t> carry;  // undecoded tail of the previous chunk
   bool eof = false;
+  bool verify_crc = true;     // check every block's CRC32 (KDF_BAM_CRC=0 switches it off)
   uint64_t record_index = 0;  // file-order index of the next record
+  // uncompressed / compressed bytes of all blocks taken so far, and the index of the
+  // blocks (uncompressed start -> file offset) that kdf_bam_fetch_records seeks with
+  uint64_t u_total = 0, c_total = 0;
+  std::vector<std::pair<uint64_t, uint64_t>> blk_index;
+  uint64_t first_rec_uoff = 0;   // uncompressed offset of the first record (= header size)
+  int last_set_part = -1;        // read-part bit the last parsed record set in seen_parts (-1: none)
+  std::string path;
   // collapse state of the FASTA stream (persists across batches)
   std::string cur_qname;
   unsigned seen_parts = 0;
@@ -135,7 +149,7 @@ struct Bam {
   }
 };
 
-bool inflate_block(const uint8_t* src, uint32_t csize, uint8_t* dst, uint32_t usize) {
+bool inflate_block(const uint8_t* src, uint32_t csize, uint8_t* dst, uint32_t usize, bool verify_crc = true) {
   // BGZF: 18-byte header (with BC subfield), deflate payload, crc32 + isize
   if (csize < 26) return false;
   uint16_t xlen = (uint16_t)(src[10] | (src[11] << 8));
@@ -149,7 +163,13 @@ bool inflate_block(const uint8_t* src, uint32_t csize, uint8_t* dst, uint32_t us
   zs.avail_out = usize;
   int rc = inflate(&zs, Z_FINISH);
   inflateEnd(&zs);
-  return rc == Z_STREAM_END && zs.total_out == usize;
+  if (!(rc == Z_STREAM_END && zs.total_out == usize)) return false;
+  if (verify_crc) {
+    const uint8_t* tl = src + csize - 8;
+    uint32_t want = tl[0] | (tl[1] << 8) | (tl[2] << 16) | ((uint32_t)tl[3] << 24);
+    if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, usize) != want) return false;
+  }
+  return true;
 }
 
 // Stage 1 (serial): the compressed bytes of up to `want_bytes` of data.  The file is read
@@ -161,6 +181,7 @@ bool read_comp(Bam* b, uint64_t want_bytes, CompBuf& cb, std::string& err) {
   comp.clear();
   cb.blocks.clear();
   cb.total_u = 0;
+  cb.ustart = b->u_total;
   cb.valid = false;
   comp.insert(comp.end(), b->pending.begin(), b->pending.end());
   b->pending.clear();
@@ -218,7 +239,14 @@ bool read_comp(Bam* b, uint64_t want_bytes, CompBuf& cb, std::string& err) {
     }
     const uint8_t* tl = comp.data() + pos + bsize - 4;
     uint32_t isize = tl[0] | (tl[1] << 8) | (tl[2] << 16) | ((uint32_t)tl[3] << 24);
+    if (isize > 65536) {
+      err = "corrupt BGZF block (ISIZE above 64 KiB)";
+      return false;
+    }
     cb.blocks.push_back({(uint64_t)pos, (uint32_t)bsize, isize, cb.total_u});
+    if (isize) b->blk_index.emplace_back(b->u_total, b->c_total);
+    b->u_total += isize;
+    b->c_total += (uint64_t)bsize;
     cb.total_u += isize;
     pos += (size_t)bsize;
   }
@@ -234,6 +262,8 @@ bool alloc_chunk(Bam* b, const CompBuf& cb, size_t gap, Chunk& c) {
   if (!p) return false;
   c.data = p;
   c.begin = gap;
+  c.own = gap;
+  c.ustart = cb.ustart;
   c.size = gap + cb.total_u;
   c.cap = cap;
   c.valid = false;   // until inflated
@@ -241,10 +271,10 @@ bool alloc_chunk(Bam* b, const CompBuf& cb, size_t gap, Chunk& c) {
 }
 
 // Stage 2 (one block; any thread)
-inline bool inflate_one(const CompBuf& cb, size_t i, Chunk& c) {
+inline bool inflate_one(const CompBuf& cb, size_t i, Chunk& c, bool verify_crc) {
   const BlockRef& br = cb.blocks[i];
   if (br.usize == 0) return true;
-  return inflate_block(cb.bytes.data() + br.coff, br.csize, c.data + c.begin + br.uoff, br.usize);
+  return inflate_block(cb.bytes.data() + br.coff, br.csize, c.data + c.own + br.uoff, br.usize, verify_crc);
 }
 
 // read + inflate `want_bytes` more, appended to a vector (header parsing only)
@@ -267,11 +297,11 @@ bool read_chunk(Bam* b, uint64_t want_bytes, std::vector<uint8_t>& out) {
   int bad = 0;
 #pragma omp parallel for schedule(dynamic, 8) num_threads(b->threads) reduction(| : bad)
   for (long i = 0; i < (long)cb.blocks.size(); ++i)
-    if (!inflate_one(cb, (size_t)i, c)) bad |= 1;
+    if (!inflate_one(cb, (size_t)i, c, b->verify_crc)) bad |= 1;
   cb.valid = false;
   if (bad) {
     b->put_buf(c.data, c.cap);
-    g_host_err = "BGZF inflate failed";
+    g_host_err = "BGZF inflate failed (corrupt block or CRC mismatch)";
     return false;
   }
   out.insert(out.end(), c.data + c.begin, c.data + c.size);
@@ -304,14 +334,26 @@ bool parse_header(Bam* b) {
     return false;
   }
   int32_t l_text = rd_i32(buf.data() + 4);
+  if (l_text < 0 || l_text > (1 << 30)) {
+    g_host_err = "corrupt BAM header (l_text)";
+    return false;
+  }
   if (!need(12 + (size_t)l_text)) return false;
   b->header_text.assign((const char*)buf.data() + 8, (size_t)l_text);
   size_t off = 8 + (size_t)l_text;
   int32_t n_ref = rd_i32(buf.data() + off);
+  if (n_ref < 0 || n_ref > (1 << 24)) {
+    g_host_err = "corrupt BAM header (n_ref)";
+    return false;
+  }
   off += 4;
   for (int32_t i = 0; i < n_ref; ++i) {
     if (!need(off + 4)) return false;
     int32_t l_name = rd_i32(buf.data() + off);
+    if (l_name < 1 || l_name > (1 << 16)) {
+      g_host_err = "corrupt BAM header (reference name length)";
+      return false;
+    }
     off += 4;
     if (!need(off + (size_t)l_name + 4)) return false;
     b->ref_names.emplace_back((const char*)buf.data() + off, (size_t)(l_name > 0 ? l_name - 1 : 0));
@@ -320,6 +362,7 @@ bool parse_header(Bam* b) {
     off += 4;
   }
   buf.erase(buf.begin(), buf.begin() + (long)off);
+  b->first_rec_uoff = off;
   return true;
 }
 
@@ -429,6 +472,8 @@ struct kdf_bam_batch_impl {
   std::vector<uint64_t> read_starts;
   std::vector<uint32_t> read_lens;
   std::vector<uint64_t> rec_index;
+  std::vector<uint64_t> rec_uoff;     // offset of every kept record in the uncompressed stream
+  std::vector<uint8_t> fasta_keep;    // the record is part of the KDF_BAM_FASTA stream
   std::vector<int32_t> ref_id, pos, next_ref_id, next_pos;
   std::vector<uint16_t> flag;
   std::vector<uint8_t> mapq;
@@ -454,9 +499,16 @@ int kdf_bam_open(const char* path, int n_threads, kdf_bam** out) {
     g_host_err = std::string("cannot open ") + path;
     return KDF_ERR_ARG;
   }
-  Bam* b = new Bam;
+  Bam* b = new (std::nothrow) Bam;
+  if (!b) {
+    fclose(fh);
+    g_host_err = "out of memory";
+    return KDF_ERR_ARG;
+  }
   b->fh = fh;
+  b->path = path;
   b->threads = n_threads > 0 ? n_threads : 1;
+  if (const char* e = getenv("KDF_BAM_CRC")) b->verify_crc = e[0] != '0';
   if (const char* e = getenv("KDF_BAM_CHUNK_KB")) {
     long v = atol(e);
     if (v > 0) b->chunk_bytes = (uint64_t)v << 10;
@@ -466,7 +518,13 @@ int kdf_bam_open(const char* path, int n_threads, kdf_bam** out) {
     if (v >= 0) b->gap = (size_t)v;
   }
   g_host_err.clear();
-  if (!parse_header(b)) {
+  bool ok = false;
+  try {
+    ok = parse_header(b);
+  } catch (const std::exception& e) {
+    g_host_err = std::string("cannot parse the BAM header: ") + e.what();
+  }
+  if (!ok) {
     fclose(fh);
     delete b;
     return KDF_ERR_ARG;
@@ -499,6 +557,9 @@ int64_t kdf_bam_ref_len(const kdf_bam* h, int i) {
   return (i >= 0 && i < (int)b->ref_lens.size()) ? b->ref_lens[i] : -1;
 }
 
+static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, kdf_bam_batch* out,
+                           kdf_bam_batch_impl* im);
+
 int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
                        kdf_bam_batch* out) {
   Bam* b = reinterpret_cast<Bam*>(h);
@@ -510,7 +571,26 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
     g_host_err = "kdf_bam_next_batch: bad mode";
     return KDF_ERR_ARG;
   }
-  kdf_bam_batch_impl* im = new kdf_bam_batch_impl;
+  // no C++ exception may cross the C ABI: an allocation failure (a huge or corrupt
+  // input) comes back as an error code
+  try {
+    std::unique_ptr<kdf_bam_batch_impl> im(new kdf_bam_batch_impl);
+    int rc = next_batch_impl(b, mode, max_bases, want_meta, out, im.get());
+    if (rc == KDF_OK) im.release();   // owned by *out until kdf_bam_batch_free
+    return rc;
+  } catch (const std::bad_alloc&) {
+    g_host_err = "out of memory while decoding the BAM";
+  } catch (const std::exception& e) {
+    g_host_err = std::string("BAM decode failed: ") + e.what();
+  } catch (...) {
+    g_host_err = "BAM decode failed";
+  }
+  memset(out, 0, sizeof(*out));
+  return KDF_ERR_ARG;
+}
+
+static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, kdf_bam_batch* out,
+                           kdf_bam_batch_impl* im) {
   // (the vector lives in the reader: its pages stay mapped from batch to batch, a fresh
   // one cost a page fault per 128 records in the middle of the serial walk)
   std::vector<Kept>& kept = b->kept;
@@ -533,7 +613,6 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
   auto bail = [&](const std::string& msg) {
     g_host_err = msg;
     release_retired();
-    delete im;
     return KDF_ERR_ARG;
   };
   if (!b->cur.valid) {   // first call: the bytes that followed the header
@@ -543,6 +622,8 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
     if (!b->carry.empty()) memcpy(p, b->carry.data(), b->carry.size());
     b->cur.data = p;
     b->cur.begin = 0;
+    b->cur.own = 0;
+    b->cur.ustart = b->first_rec_uoff;
     b->cur.size = b->carry.size();
     b->cur.cap = cap;
     b->cur.valid = true;
@@ -552,6 +633,8 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
   const uint8_t* buf = b->cur.data;
   size_t buf_size = b->cur.size;
   size_t off = b->cur.begin;
+  uint64_t cur_ustart = b->cur.ustart;
+  size_t cur_own = b->cur.own;
   bool done = false;
   std::string perr, rerr;
   // stage 3: parse all complete records currently in the chunk
@@ -559,8 +642,8 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
     while (true) {
       if (buf_size - off < 4) break;
       int32_t bs = rd_i32(buf + off);
-      if (bs < 32) {
-        perr = "corrupt BAM record";
+      if (bs < 32 || bs > (1 << 28)) {
+        perr = "corrupt BAM record (block_size out of range)";
         return;
       }
       if (buf_size - off - 4 < (size_t)bs) break;
@@ -571,25 +654,39 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
       __builtin_prefetch(r + bs + 1088);
       uint16_t flag = rd_u16(r + 14);
       uint8_t l_name = r[8];
-      uint32_t l_seq = (uint32_t)rd_i32(r + 16);
+      uint16_t n_cig_v = rd_u16(r + 12);
+      int32_t l_seq_s = rd_i32(r + 16);
+      // the variable-length fields must lie inside the record: a corrupt l_seq / n_cigar /
+      // l_read_name would otherwise send the packer (and the metadata pass) out of bounds
+      if (l_seq_s < 0 || 32ull + l_name + 4ull * n_cig_v + ((uint64_t)l_seq_s + 1) / 2 + (uint64_t)l_seq_s >
+                             (uint64_t)bs) {
+        perr = "corrupt BAM record (field sizes exceed the record)";
+        return;
+      }
+      uint32_t l_seq = (uint32_t)l_seq_s;
+      // membership of the `samtools fasta -F 0xD00` stream, tracked in every mode (the
+      // discovery pipeline decodes the child ONCE in scan mode and masks the counting
+      // stream with this flag)
+      bool fasta_keep = false;
+      b->last_set_part = -1;
+      if (!(flag & 0xD00)) {
+        const char* qn = (const char*)r + 32;
+        size_t ql = l_name ? (size_t)l_name - 1 : 0;
+        if (b->cur_qname.size() != ql || memcmp(b->cur_qname.data(), qn, ql) != 0) {
+          b->cur_qname.assign(qn, ql);
+          b->seen_parts = 0;
+        }
+        bool r1 = flag & 0x40, r2 = flag & 0x80;
+        unsigned part = (r1 && !r2) ? 1u : ((r2 && !r1) ? 2u : 0u);
+        if (!(b->seen_parts & (1u << part))) {
+          b->seen_parts |= 1u << part;
+          b->last_set_part = (int)part;
+          fasta_keep = true;
+        }
+      }
       bool keep = true;
       if (mode == KDF_BAM_FASTA) {
-        if (flag & 0xD00) {
-          keep = false;
-        } else {
-          const char* qn = (const char*)r + 32;
-          size_t ql = l_name ? (size_t)l_name - 1 : 0;
-          if (b->cur_qname.size() != ql || memcmp(b->cur_qname.data(), qn, ql) != 0) {
-            b->cur_qname.assign(qn, ql);
-            b->seen_parts = 0;
-          }
-          bool r1 = flag & 0x40, r2 = flag & 0x80;
-          unsigned part = (r1 && !r2) ? 1u : ((r2 && !r1) ? 2u : 0u);
-          if (b->seen_parts & (1u << part))
-            keep = false;
-          else
-            b->seen_parts |= 1u << part;
-        }
+        keep = fasta_keep;
       } else if (mode == KDF_BAM_SCAN) {
         if (flag & 0x500) keep = false;
       }
@@ -599,7 +696,8 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
           break;  // leave this record for the next batch
         }
         uint64_t start = kept.empty() ? 0 : n_bases + 1;
-        kept.push_back({buf + off + 4, start, l_seq});
+        const uint64_t uoff = cur_ustart + (uint64_t)off - (uint64_t)cur_own;   // off may lie in the tail before `own`
+        kept.push_back({buf + off + 4, start, uoff, l_seq, (uint8_t)(fasta_keep ? 1 : 0)});
         n_bases = start + l_seq;
         im->rec_index.push_back(b->record_index);
       }
@@ -631,12 +729,12 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
       }
 #pragma omp for schedule(dynamic, 4) nowait
       for (long i = 0; i < n_blk; ++i)
-        if (!inflate_one(b->ahead, (size_t)i, nx)) bad |= 1;
+        if (!inflate_one(b->ahead, (size_t)i, nx, b->verify_crc)) bad |= 1;
     }
     if (do_inflate) {
       if (bad) {
         b->put_buf(nx.data, nx.cap);
-        return bail("BGZF inflate failed");
+        return bail("BGZF inflate failed (corrupt block or CRC mismatch)");
       }
       nx.valid = true;
       b->next = nx;
@@ -669,6 +767,7 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
       memcpy(p, buf + off, tail);
       memcpy(p + tail, nxt.data + nxt.begin, n_next);
       b->put_buf(nxt.data, nxt.cap);
+      nxt.own = tail + (nxt.own - nxt.begin);
       nxt.data = p;
       nxt.begin = 0;
       nxt.size = tail + n_next;
@@ -680,21 +779,17 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
     buf = b->cur.data;
     buf_size = b->cur.size;
     off = b->cur.begin;
+    cur_ustart = b->cur.ustart;
+    cur_own = b->cur.own;
   }
   b->cur.begin = off;
   b->eof = b->file_eof && !b->ahead.valid && !b->next.valid;
-  // NOTE: when a batch limit stops us mid-buffer the collapse state already
-  // reflects only the records consumed so far (the break precedes any update
-  // for the postponed record? no — state was updated; undo by re-evaluating):
-  // to stay exact we re-derive the state on the next call from the carry, so
-  // roll the state back when the postponed record was a fresh keep.
-  if (done && mode == KDF_BAM_FASTA) {
-    // the postponed record set its part bit; clear it so it is kept next time
-    const uint8_t* r = buf + off + 4;
-    uint16_t flag = rd_u16(r + 14);
-    bool r1 = flag & 0x40, r2 = flag & 0x80;
-    unsigned part = (r1 && !r2) ? 1u : ((r2 && !r1) ? 2u : 0u);
-    b->seen_parts &= ~(1u << part);
+  // A batch limit postponed a record whose parse had already updated the collapse state:
+  // if it set a read-part bit, clear it, so that the record is kept when the next batch
+  // parses it again (its QNAME is then still the current one).
+  if (done && b->last_set_part >= 0) {
+    b->seen_parts &= ~(1u << b->last_set_part);
+    b->last_set_part = -1;
   }
   size_t n = kept.size();
   uint64_t n_words = (n_bases + 31) / 32;
@@ -723,6 +818,12 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
     pack_record(nib, kept[i].l_seq, kept[i].start, im->codes.data(), im->valid.data());
     im->read_starts[i] = kept[i].start;
     im->read_lens[i] = kept[i].l_seq;
+  }
+  im->rec_uoff.resize(n);
+  im->fasta_keep.resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    im->rec_uoff[i] = kept[i].uoff;
+    im->fasta_keep[i] = kept[i].fasta_keep;
   }
   if (n_bases <= 0xffffffffull) {   // sparse form of the validity bitmap (kdf_valid_from_invalid)
     // by word ranges: count, prefix, fill
@@ -876,6 +977,8 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
   out->read_starts = im->read_starts.data();
   out->read_lens = im->read_lens.data();
   out->rec_index = im->rec_index.data();
+  out->rec_uoff = im->rec_uoff.data();
+  out->fasta_keep = im->fasta_keep.data();
   if (want_meta) {
     out->ref_id = im->ref_id.data();
     out->pos = im->pos.data();
@@ -905,6 +1008,192 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
     out->has_invalid = 1;
   }
   return KDF_OK;
+}
+
+// ---- random access to records seen by the sequential decode ----------------
+// kdf_bam_batch.rec_uoff names a record by its offset in the file's uncompressed
+// stream; the reader remembers where every BGZF block it has walked starts (in both
+// coordinates), so a record can be fetched again by inflating just its block(s).
+int kdf_bam_fetch_records(kdf_bam* h, const uint64_t* uoffs, uint64_t n, uint8_t* out, uint64_t out_cap,
+                          uint64_t* out_off, uint64_t* needed) {
+  Bam* b = reinterpret_cast<Bam*>(h);
+  if (!b || (n && !uoffs) || !out_off || !needed) {
+    g_host_err = "kdf_bam_fetch_records: NULL argument";
+    return KDF_ERR_ARG;
+  }
+  try {
+    FILE* fh = fopen(b->path.c_str(), "rb");
+    if (!fh) {
+      g_host_err = "kdf_bam_fetch_records: cannot reopen " + b->path;
+      return KDF_ERR_ARG;
+    }
+    struct Closer {
+      FILE* f;
+      ~Closer() { fclose(f); }
+    } closer{fh};
+    const auto& idx = b->blk_index;
+    std::vector<uint8_t> comp(70000), cache;   // cache: inflated bytes from block `cache_first` on
+    size_t cache_first = (size_t)-1, cache_next = 0;
+    auto load_block = [&](size_t bi, std::vector<uint8_t>& dst) -> bool {   // append block bi to dst
+      if (bi >= idx.size()) return false;
+      if (fseeko(fh, (off_t)idx[bi].second, SEEK_SET) != 0) return false;
+      if (fread(comp.data(), 1, 18, fh) != 18) return false;
+      if (comp[0] != 31 || comp[1] != 139) return false;
+      uint16_t xlen = (uint16_t)(comp[10] | (comp[11] << 8));
+      if (xlen != 6) {   // the general case: re-read the whole extra field
+        if (comp.size() < (size_t)12 + xlen + 8) comp.resize((size_t)12 + xlen + 70000);
+        if (xlen > 6 && fread(comp.data() + 18, 1, (size_t)xlen - 6, fh) != (size_t)xlen - 6) return false;
+      }
+      int bsize = -1;
+      for (uint32_t p = 0; p + 4 <= xlen;) {
+        uint16_t slen = (uint16_t)(comp[12 + p + 2] | (comp[12 + p + 3] << 8));
+        if (comp[12 + p] == 'B' && comp[12 + p + 1] == 'C' && slen == 2 && p + 6 <= xlen)
+          bsize = (comp[12 + p + 4] | (comp[12 + p + 5] << 8)) + 1;
+        p += 4 + slen;
+      }
+      if (bsize < 12 + (int)xlen + 8) return false;
+      size_t have = (size_t)12 + xlen;
+      if (comp.size() < (size_t)bsize) comp.resize((size_t)bsize);
+      if (fread(comp.data() + have, 1, (size_t)bsize - have, fh) != (size_t)bsize - have) return false;
+      const uint8_t* tl = comp.data() + bsize - 4;
+      uint32_t isize = tl[0] | (tl[1] << 8) | (tl[2] << 16) | ((uint32_t)tl[3] << 24);
+      if (isize > 65536) return false;
+      size_t at = dst.size();
+      dst.resize(at + isize);
+      return isize == 0 || inflate_block(comp.data(), (uint32_t)bsize, dst.data() + at, isize, b->verify_crc);
+    };
+    uint64_t total = 0;
+    out_off[0] = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+      const uint64_t u = uoffs[i];
+      // block holding offset u: the last one that starts at or before it
+      size_t lo = 0, hi = idx.size();
+      while (lo < hi) {
+        size_t mid = (lo + hi) / 2;
+        if (idx[mid].first <= u) lo = mid + 1; else hi = mid;
+      }
+      if (lo == 0) {
+        g_host_err = "kdf_bam_fetch_records: offset precedes the blocks decoded so far";
+        return KDF_ERR_ARG;
+      }
+      const size_t bi = lo - 1;
+      if (cache_first != bi) {   // (records fetched in ascending order mostly share blocks)
+        cache.clear();
+        cache_first = bi;
+        cache_next = bi;
+      }
+      const size_t in_off = (size_t)(u - idx[bi].first);
+      auto ensure = [&](size_t need_bytes) -> bool {
+        while (cache.size() < need_bytes) {
+          if (!load_block(cache_next, cache)) return false;
+          ++cache_next;
+        }
+        return true;
+      };
+      if (!ensure(in_off + 4)) {
+        g_host_err = "kdf_bam_fetch_records: cannot read the record's block";
+        return KDF_ERR_ARG;
+      }
+      int32_t bs = rd_i32(cache.data() + in_off);
+      if (bs < 32 || bs > (1 << 28) || !ensure(in_off + 4 + (size_t)bs)) {
+        g_host_err = "kdf_bam_fetch_records: no BAM record at this offset";
+        return KDF_ERR_ARG;
+      }
+      if (out && total + (uint64_t)bs <= out_cap) memcpy(out + total, cache.data() + in_off + 4, (size_t)bs);
+      total += (uint64_t)bs;
+      out_off[i + 1] = total;
+    }
+    *needed = total;
+    return KDF_OK;
+  } catch (const std::exception& e) {
+    g_host_err = std::string("kdf_bam_fetch_records: ") + e.what();
+    return KDF_ERR_ARG;
+  }
+}
+
+// ---- BGZF writer -------------------------------------------------------------
+// `data` as a BGZF file (blocks of <= 0xff00 input bytes deflated by all threads,
+// written in order, then the EOF marker): the container of the BAM and bgzip-VCF
+// outputs.  block_coff (may be NULL) receives the file offset of every block, so that
+// the caller can turn uncompressed offsets into BAI / TBI virtual offsets.
+int kdf_bgzf_write(const char* path, const uint8_t* data, uint64_t n, int level, int n_threads,
+                   uint64_t* block_coff, uint64_t block_cap, uint64_t* n_blocks) {
+  if (!path || (n && !data)) {
+    g_host_err = "kdf_bgzf_write: NULL argument";
+    return KDF_ERR_ARG;
+  }
+  try {
+    const uint64_t BLK = 0xff00;
+    const uint64_t nb = (n + BLK - 1) / BLK;
+    if (n_blocks) *n_blocks = nb;
+    FILE* fh = fopen(path, "wb");
+    if (!fh) {
+      g_host_err = std::string("cannot create ") + path;
+      return KDF_ERR_ARG;
+    }
+    if (level < 0 || level > 9) level = 6;
+    if (n_threads < 1) n_threads = 1;
+    const uint64_t GROUP = 1024;   // blocks compressed per round (64 MB of input)
+    std::vector<std::vector<uint8_t>> outb(GROUP);
+    uint64_t coff = 0;
+    int bad = 0;
+    for (uint64_t g0 = 0; g0 < nb && !bad; g0 += GROUP) {
+      const long gn = (long)(nb - g0 < GROUP ? nb - g0 : GROUP);
+#pragma omp parallel for schedule(dynamic, 4) num_threads(n_threads) reduction(| : bad)
+      for (long j = 0; j < gn; ++j) {
+        const uint64_t bi = g0 + (uint64_t)j;
+        const uint8_t* src = data + bi * BLK;
+        const uint32_t len = (uint32_t)(n - bi * BLK < BLK ? n - bi * BLK : BLK);
+        std::vector<uint8_t>& ob = outb[(size_t)j];
+        ob.resize(18 + compressBound(len) + 8);
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) {
+          bad |= 1;
+          continue;
+        }
+        zs.next_in = const_cast<uint8_t*>(src);
+        zs.avail_in = len;
+        zs.next_out = ob.data() + 18;
+        zs.avail_out = (uInt)(ob.size() - 18 - 8);
+        int rc = deflate(&zs, Z_FINISH);
+        deflateEnd(&zs);
+        if (rc != Z_STREAM_END || 18 + zs.total_out + 8 > 65536) {
+          bad |= 1;   // (cannot happen for <= 0xff00 input bytes)
+          continue;
+        }
+        const uint32_t clen = (uint32_t)zs.total_out;
+        static const uint8_t HDR[16] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 'B', 'C', 2, 0};
+        memcpy(ob.data(), HDR, 16);
+        const uint16_t bsz = (uint16_t)(18 + clen + 8 - 1);
+        ob[16] = (uint8_t)(bsz & 255);
+        ob[17] = (uint8_t)(bsz >> 8);
+        const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), src, len);
+        uint8_t* tl = ob.data() + 18 + clen;
+        for (int q = 0; q < 4; ++q) tl[q] = (uint8_t)(crc >> (8 * q));
+        for (int q = 0; q < 4; ++q) tl[4 + q] = (uint8_t)(len >> (8 * q));
+        ob.resize(18 + clen + 8);
+      }
+      for (long j = 0; j < gn && !bad; ++j) {
+        if (block_coff && g0 + (uint64_t)j < block_cap) block_coff[g0 + (uint64_t)j] = coff;
+        if (fwrite(outb[(size_t)j].data(), 1, outb[(size_t)j].size(), fh) != outb[(size_t)j].size()) bad |= 2;
+        coff += outb[(size_t)j].size();
+      }
+    }
+    static const uint8_t EOF_BLOCK[28] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67,
+                                          2,  0,   27, 0, 3, 0, 0, 0, 0, 0, 0,   0, 0, 0};
+    if (!bad && fwrite(EOF_BLOCK, 1, 28, fh) != 28) bad |= 2;
+    if (block_coff && nb < block_cap) block_coff[nb] = coff;   // offset of the EOF block
+    if (fclose(fh) != 0) bad |= 2;
+    if (bad) {
+      g_host_err = (bad & 2) ? std::string("write failed: ") + path : "deflate failed";
+      return KDF_ERR_ARG;
+    }
+    return KDF_OK;
+  } catch (const std::exception& e) {
+    g_host_err = std::string("kdf_bgzf_write: ") + e.what();
+    return KDF_ERR_ARG;
+  }
 }
 
 uint64_t kdf_invalid_positions(const uint32_t* valid, uint64_t n_bases, uint32_t* out, uint64_t cap) {

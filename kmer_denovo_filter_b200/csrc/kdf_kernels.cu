@@ -447,6 +447,21 @@ __device__ __forceinline__ void pf_bits(u64 h, u32& word, u32& bits) {
   bits = (1u << (l >> 27)) | (1u << ((l >> 22) & 31u));
 }
 
+// 32-bit read-only load executed only when `on` (else 0): a predicated instruction, not a branch
+__device__ __forceinline__ u32 ldg_if(const u32* p, bool on) {
+  u32 v;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.u32 q, %2, 0;\n\t"
+      "mov.u32 %0, 0;\n\t"
+      "@q ld.global.nc.u32 %0, [%1];\n\t"
+      "}\n"
+      : "=r"(v)
+      : "l"(p), "r"((u32)on));
+  return v;
+}
+
 // the same for a filter in global memory (kdf_table_build_filter): any power-of-two
 // number of words
 __device__ __forceinline__ void gf_bits(u64 h, u32 mask, u32& word, u32& bits) {
@@ -531,11 +546,14 @@ __global__ void __launch_bounds__(SMEM ? 512 : 256, SMEM ? KDF_SMEM_BLOCKS : (KW
       u32 okm = 0, probe = 0, cand = 0;
       if constexpr (FILT || SMEM) {
         // filtered tables: one 32-bit load says "certainly absent" for almost every
-        // window.  The CHUNK loads are issued UNCONDITIONALLY and back to back (an
-        // invalid window reads a valid filter word it then ignores) and tested
-        // afterwards: as `if (ok) { load; test }` ptxas built one divergent region per
-        // window with the load's consumer right behind it — one load in flight per
-        // thread, long_scoreboard the top stall (profiles/r2a_ncu_k_stream_filtered.txt).
+        // window.  The CHUNK loads are issued back to back and tested afterwards.  Written
+        // as `if (ok) { load; test }` ptxas built one divergent region per window with the
+        // load's consumer right behind it — one load in flight per thread, long_scoreboard
+        // the top stall (profiles/r2a_ncu_k_stream_filtered.txt).  The global loads are
+        // PREDICATED on the window's validity (ldg_if: one PTX instruction, no branch): the
+        // kernel is bound by the L1/L2 request rate (l1tex 94 %), and loading for the 20 %
+        // of the positions that start no valid window cost exactly those 20 % (6.7 -> 7.3 ms,
+        // profiles/r2b_ncu_k_stream_filtered.txt).  Shared-memory filter reads are unconditional.
         u32 fval[CHUNK], fbits[CHUNK];
 #pragma unroll
         for (int u = 0; u < CHUNK; ++u) {
@@ -544,7 +562,7 @@ __global__ void __launch_bounds__(SMEM ? 512 : 256, SMEM ? KDF_SMEM_BLOCKS : (KW
           u32 word;
           if (FILT) {
             gf_bits(h, t.filter_mask, word, fbits[u]);
-            fval[u] = __ldg(t.filter + word);
+            fval[u] = ldg_if(t.filter + word, it.ok(u));
           } else {
             pf_bits(h, word, fbits[u]);
             fval[u] = pf[word];
@@ -1102,6 +1120,116 @@ __global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_packed_keys(TableView<
   } else {
     tally_packed(st, sq_drain<KW, OP>(&q, t, sh, sat, sink, true));
   }
+  flush_stats(st, stats);
+}
+
+// Lean form of the packed count (the default; KDF_COUNT_LEAN=0 takes the pipelined
+// kernel above).  ncu on the pipelined kernel (profiles/r2b_ncu_k_packed_keys.txt): 176
+// warp instructions per 32 keys — 27 % of them register moves, the rotation of a
+// three-stage software pipeline that needs 128 registers and therefore runs at 2 blocks
+// per SM (24 % of the warp slots), issue slots 44 % busy, long_scoreboard the top stall.
+// Here a thread takes LEAN_CHUNK keys per round with no software pipeline: keys -> hash ->
+// bucket loads -> resolve, the latencies hidden by occupancy instead (<= 64 registers:
+// 4 blocks of 256 threads per SM).  Same queues, same drain, same results.
+// the rare paths of the lean kernel, out of line so that they cost it no registers:
+// kind 0 = home bucket full (probe on from bucket b), 1 / 2 = the queue was full (bump /
+// insert in place).  Returns a resolve code for tally().
+template <int KW>
+__device__ __noinline__ u32 lean_rare(PackedQueues<KW>* qp, TableView<KW> t, Key<KW> key, u32 b, u32 info,
+                                      u64 ms, int sh, u32 sat) {
+  constexpr int S = SPB<KW>::v;
+  const HitSink sink = {nullptr, nullptr, 0, nullptr};
+  if ((info & 3u) == 0) return sq_push_or_resolve<KW, OP_PACKED_COUNT>(qp->slow, t, b, key, sh, sat, 0, sink);
+  if ((info & 3u) == 1) {
+    packed_bump(t.keys + ((u64)b * S + (info >> 2)) * KW + (KW - 1), ms, sh, sat);
+    return R_MISS;   // (the hit was tallied by the caller)
+  }
+  return resolve_packed_count<KW>(t, b, key, sh, sat);
+}
+
+template <int KW, bool FILT, int CHUNK, int BLOCKS>
+__global__ void __launch_bounds__(256, BLOCKS) k_packed_count_lean(
+    TableView<KW> t, const u64* lo, u64 n_max, const u64* n_dev, int sh, u32 sat, u64* stats, int filt_log2,
+    u32 filt_val) {
+  constexpr int S = SPB<KW>::v;
+  constexpr int OP = OP_PACKED_COUNT;
+  const u64 mask = (1ull << sh) - 1;
+  u64 n = n_max;
+  if (n_dev) {
+    u64 nd = *n_dev;
+    n = nd < n_max ? nd : n_max;
+  }
+  extern __shared__ __align__(16) unsigned char pk_smem[];   // one queue pair per warp
+  PackedQueues<KW>& q = reinterpret_cast<PackedQueues<KW>*>(pk_smem)[threadIdx.x >> 5];
+  if ((threadIdx.x & 31) == 0) {
+    q.fast.count = 0;
+    q.slow.count = 0;
+  }
+  __syncwarp();
+  LocalStats st = {0, 0, 0, 0};
+  const HitSink sink = {nullptr, nullptr, 0, nullptr};
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  const u64 n_iter = (n + stride * CHUNK - 1) / (stride * CHUNK);   // warp-uniform
+  const u64 first = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  for (u64 itn = 0; itn < n_iter; ++itn) {
+    Key<KW> keys[CHUNK];
+    Bucket<KW> bk[CHUNK];
+    u32 bidx[CHUNK];
+    u32 okm = 0;
+    const u64 i0 = first + itn * stride * CHUNK;
+#pragma unroll
+    for (int u = 0; u < CHUNK; ++u) {
+      const u64 i = i0 + (u64)u * stride;
+      if (i < n) {
+        okm |= 1u << u;
+        keys[u] = ld_key_pinned<KW>(lo, i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < CHUNK; ++u) {
+      if (okm & (1u << u)) {
+        const u64 h = hash_key(keys[u]);
+        if (FILT && part_of(h, filt_log2) != filt_val) {
+          okm &= ~(1u << u);
+        } else {
+          bidx[u] = bucket_of(h, t.log2_parts, t.n_buckets);
+          bk[u] = ld_bucket<KW>(t.keys + (u64)bidx[u] * 4 * KW);
+        }
+      }
+    }
+    st.windows += __popc(okm);
+#pragma unroll
+    for (int u = 0; u < CHUNK; ++u) {
+      if (okm & (1u << u)) {
+        u64 ms = 0;
+        const int j = match_packed(bk[u], keys[u], mask, ms);
+        u32 info = 0;   // kind (1 bump, 2 insert) | slot << 2; 0 = nothing owed
+        if (j >= 0) {
+          st.hits++;
+          if ((u32)(ms >> sh) < sat) info = 1u | ((u32)j << 2);
+        } else {
+          int c = -1;
+#pragma unroll
+          for (int cc = S - 1; cc >= 0; --cc)
+            if (maybe_empty(bk[u], cc, keys[u])) c = cc;
+          if (c < 0) {  // home bucket full: probe on from the next one
+            u32 nb = (bidx[u] + 1 == t.n_buckets) ? 0 : bidx[u] + 1;
+            tally(st, lean_rare<KW>(&q, t, keys[u], nb, 0u, 0ull, sh, sat));
+          } else {
+            info = 2u | ((u32)c << 2);
+            ms = 0;
+          }
+        }
+        if (info && !pq_push<KW>(q.fast, keys[u], bidx[u], info, ms))   // queue full: in place
+          tally(st, lean_rare<KW>(&q, t, keys[u], bidx[u], info, ms, sh, sat));
+      }
+    }
+    __syncwarp();
+    if (q.fast.count >= (u32)PQ_DRAIN) tally_packed(st, pq_drain<KW>(&q, t, sh, sat, false));
+    if (q.slow.count >= 32) tally_packed(st, sq_drain<KW, OP>(&q.slow, t, sh, sat, sink, false));
+  }
+  tally_packed(st, pq_drain<KW>(&q, t, sh, sat, true));
+  tally_packed(st, sq_drain<KW, OP>(&q.slow, t, sh, sat, sink, true));
   flush_stats(st, stats);
 }
 
@@ -1720,12 +1848,29 @@ struct BinPlan {
   size_t smem;
 };
 
-template <int KW, int BMODE>
+// shared-memory accesses by 32-bit shared-window address (the generic-pointer forms made
+// ptxas rebuild the window base — S2R SR_CgaCtaId, MOV, LEA — in front of every store)
+__device__ __forceinline__ u32 smem_inc(u32 addr) {
+  u32 old;
+  asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(addr) : "memory");
+  return old;
+}
+__device__ __forceinline__ void smem_st_key(u32 addr, const Key<1>& key) {
+  asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(key.lo) : "memory");
+}
+__device__ __forceinline__ void smem_st_key(u32 addr, const Key<2>& key) {
+  asm volatile("st.shared.v2.u64 [%0], {%1, %2};" ::"r"(addr), "l"(key.lo), "l"(key.hi) : "memory");
+}
+
+// PASS: pass_log2 > 0 (multi-pass count); REP: fewer than 32 bins, spread over virtual bins
+template <int KW, int BMODE, bool PASS, bool REP>
 __global__ void __launch_bounds__(1024, 1) k_bin_stream(StreamView s, int k, int log2_parts, u32 n_parts,
-                                                        u32 n_owners, int pass_log2, u32 pass_val, int wpr,
-                                                        int qcap, u32 qinv, int rep_log2, int flat,
+                                                        u32 n_owners, int pass_log2_arg, u32 pass_val, int wpr,
+                                                        int qcap, u32 qinv, int rep_log2_arg, int flat,
                                                         BinDest dst, u64* cursors, u64* overflow, u64* stats) {
   extern __shared__ __align__(16) unsigned char bin_smem[];
+  const int pass_log2 = PASS ? pass_log2_arg : 0;
+  const int rep_log2 = REP ? rep_log2_arg : 0;
   const u32 nv = n_parts << rep_log2;   // virtual bins
   // layout: queue[nv][qcap] keys | gptr[nv] u64* | ceff[nv] u32 | cnt[2][nv] u32
   u64* queue = reinterpret_cast<u64*>(bin_smem);
@@ -1733,7 +1878,9 @@ __global__ void __launch_bounds__(1024, 1) k_bin_stream(StreamView s, int k, int
   u32* ceff = reinterpret_cast<u32*>(gptr + nv);
   u32* cnt0 = ceff + nv;
   const u32 tid = threadIdx.x, nthr = blockDim.x;
-  const u32 lane_rep = tid & ((1u << rep_log2) - 1u);
+  const u32 lane_rep = REP ? (tid & ((1u << rep_log2) - 1u)) : 0u;
+  const u32 queue_s = (u32)__cvta_generic_to_shared(queue);
+  const u32 cnt0_s = (u32)__cvta_generic_to_shared(cnt0);
   for (u32 i = tid; i < 2 * nv; i += nthr) cnt0[i] = 0;
   __syncthreads();
   u32 round = 0;
@@ -1748,18 +1895,18 @@ __global__ void __launch_bounds__(1024, 1) k_bin_stream(StreamView s, int k, int
 #pragma unroll 1
     for (int c = 0; c < 8; ++c) {
       u32* cnt = cnt0 + (round & 1u) * nv;
+      const u32 cnt_s = cnt0_s + (round & 1u) * nv * 4u;
+      u32 pushed = 0;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const Key<KW> key = it.key(u);
         u32 p;
         if (in_range && it.ok(u) && bin_of<KW, BMODE>(key, log2_parts, n_parts, n_owners, pass_log2, pass_val, p)) {
-          ++windows;
-          const u32 v = (p << rep_log2) | lane_rep;
-          const u32 o = atomicAdd(&cnt[v], 1u);
+          pushed |= 1u << u;
+          const u32 v = REP ? ((p << rep_log2) | lane_rep) : p;
+          const u32 o = smem_inc(cnt_s + v * 4u);
           if (o < (u32)qcap) {
-            u64* q = queue + ((size_t)v * qcap + o) * KW;
-            q[0] = key.lo;
-            if (KW == 2) q[1] = ((const u64*)&key)[KW - 1];
+            smem_st_key(queue_s + (v * (u32)qcap + o) * (8u * KW), key);
           } else {  // queue full (a skewed round): append directly
             const u64 g = atomicAdd(cursors + p, 1ull);
             if (g < dst.cap) st_key<KW>(dst.of(p, KW), g, key);
@@ -1767,6 +1914,7 @@ __global__ void __launch_bounds__(1024, 1) k_bin_stream(StreamView s, int k, int
           }
         }
       }
+      windows += __popc(pushed);
       it.template next<4>();
       if ((((c + 1) * 4) % wpr) != 0) continue;
       // ---- flush: reserve one run per (virtual) bin, copy out, next round
@@ -2103,10 +2251,42 @@ static int launch_emit_buckets(const kdf_table* t, u32 min0, u32 max0, u32 min1,
   return KDF_OK;
 }
 
+// shape of the lean count kernel: KDF_COUNT_LEAN = 0 (pipelined kernel) or "<chunk><blocks>"
+// with chunk in {2, 4} keys per thread per round and blocks in {2, 3, 4} per SM
+static int count_lean_shape() {
+  static const int v = env_int("KDF_COUNT_LEAN", 23);
+  return v;
+}
+
+template <int KW, bool FILT, int CHUNK, int BLOCKS>
+static int launch_count_lean(const TableView<KW>& tv, const kdf_table* t, const u64* lo, u64 n_max,
+                             const u64* n_dev, int sh, u32 sat, u64* stats, cudaStream_t st, int filt_log2,
+                             u32 filt_val) {
+  const size_t smem = sizeof(PackedQueues<KW>) * (256 / 32);
+  const u64 items = (n_max + CHUNK - 1) / CHUNK;
+  const void* fn = (const void*)k_packed_count_lean<KW, FILT, CHUNK, BLOCKS>;
+  CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int g = grid_for(fn, 256, smem, items, t->sm_count);
+  k_packed_count_lean<KW, FILT, CHUNK, BLOCKS><<<g, 256, smem, st>>>(tv, lo, n_max, n_dev, sh, sat, stats,
+                                                                   filt_log2, filt_val);
+  CUDA_TRY(cudaGetLastError());
+  return KDF_OK;
+}
+
 template <int KW, int OP>
 static int launch_packed_keys(const kdf_table* t, const u64* lo, u64 n_max, const u64* n_dev, int sh,
                               u32 sat, u64* stats, cudaStream_t st, int filt_log2, u32 filt_val) {
   TableView<KW> tv = view_of_table<KW>(t);
+  if constexpr (OP == OP_PACKED_COUNT) {
+    const int shape = count_lean_shape();
+#define KDF_LEAN(C, B)                                                                                  \
+  if (shape == C * 10 + B)                                                                              \
+    return filt_log2 > 0 ? launch_count_lean<KW, true, C, B>(tv, t, lo, n_max, n_dev, sh, sat, stats, st, \
+                                                             filt_log2, filt_val)                        \
+                         : launch_count_lean<KW, false, C, B>(tv, t, lo, n_max, n_dev, sh, sat, stats, st, 0, 0);
+    KDF_LEAN(2, 3) KDF_LEAN(2, 4) KDF_LEAN(4, 3) KDF_LEAN(4, 2)
+#undef KDF_LEAN
+  }
   const size_t smem = sizeof(PackedKeysQueue<KW, OP>) * (256 / 32);
   const u64 items = (n_max + KDF_KEYS_CHUNK - 1) / KDF_KEYS_CHUNK;
   if (filt_log2 > 0) {
@@ -2636,22 +2816,25 @@ static int bin_stream_impl(const kdf_stream* s, int k, int by_owner, int n_parts
   cudaStream_t st = (cudaStream_t)stream;
   const BinPlan pl = bin_plan(n_parts, kw);
   const u32 qinv = (u32)((0x100000000ull + (u64)pl.qcap - 1) / (u64)pl.qcap);
-#define KDF_BIN(KW, BM)                                                                           \
+#define KDF_BIN2(KW, BM, PS, RP)                                                                  \
   {                                                                                               \
-    const void* fn = (const void*)k_bin_stream<KW, BM>;                                           \
+    const void* fn = (const void*)k_bin_stream<KW, BM, PS, RP>;                                   \
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
     int g = grid_for(fn, pl.threads, pl.smem, v.w_end - v.w_begin, sm);                           \
-    k_bin_stream<KW, BM><<<g, pl.threads, pl.smem, st>>>(v, k, log2p, (u32)n_parts, (u32)n_owners, \
-                                                         pass_log2, pass_val, pl.wpr, pl.qcap, qinv, \
-                                                         pl.rep_log2, pl.flat, dst, (u64*)cursors, \
-                                                         (u64*)overflow, (u64*)stats);            \
+    k_bin_stream<KW, BM, PS, RP><<<g, pl.threads, pl.smem, st>>>(                                 \
+        v, k, log2p, (u32)n_parts, (u32)n_owners, pass_log2, pass_val, pl.wpr, pl.qcap, qinv,     \
+        pl.rep_log2, pl.flat, dst, (u64*)cursors, (u64*)overflow, (u64*)stats);                   \
   }
-  if (kw == 1) {
-    if (bmode == 0) KDF_BIN(1, 0) else if (bmode == 1) KDF_BIN(1, 1) else KDF_BIN(1, 2)
-  } else {
-    if (bmode == 0) KDF_BIN(2, 0) else if (bmode == 1) KDF_BIN(2, 1) else KDF_BIN(2, 2)
+#define KDF_BIN(KW, BM)                                                                           \
+  {                                                                                               \
+    if (pass_log2 > 0) {                                                                          \
+      if (pl.rep_log2 > 0) KDF_BIN2(KW, BM, true, true) else KDF_BIN2(KW, BM, true, false)        \
+    } else {                                                                                      \
+      if (pl.rep_log2 > 0) KDF_BIN2(KW, BM, false, true) else KDF_BIN2(KW, BM, false, false)      \
+    }                                                                                             \
   }
 #undef KDF_BIN
+#undef KDF_BIN2
   CUDA_TRY(cudaGetLastError());
   return KDF_OK;
 }
