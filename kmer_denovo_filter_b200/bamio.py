@@ -284,6 +284,31 @@ class BamReader:
             if b.at_eof:
                 break
 
+    def fetch_records(self, uoffs):
+        """Raw BAM records (bytes after block_size) at uncompressed offsets ``uoffs``
+        (``HostBatch.rec_uoff`` of records this reader has decoded): only the BGZF blocks
+        that hold them are inflated (``kdf_bam_fetch_records``).  → list of bytes."""
+        u = np.ascontiguousarray(uoffs, dtype=np.uint64)
+        n = int(u.shape[0])
+        if n == 0:
+            return []
+        off = np.zeros(n + 1, dtype=np.uint64)
+        need = ctypes.c_uint64(0)
+        cap = max(1024, 512 * n)
+        while True:
+            buf = np.empty(cap, dtype=np.uint8)
+            rc = self.lib.kdf_bam_fetch_records(self.handle, u.ctypes.data_as(_vp), n,
+                                                buf.ctypes.data_as(_vp), cap, off.ctypes.data_as(_vp),
+                                                ctypes.byref(need))
+            if rc != 0:
+                raise _engine.KdfError("cannot fetch records from %s: %s" % (
+                    self.path, self.lib.kdf_host_last_error().decode()))
+            if need.value <= cap:
+                break
+            cap = int(need.value)
+        o = off.astype(np.int64)
+        return [buf[o[i]:o[i + 1]].tobytes() for i in range(n)]
+
     def close(self):
         if self.handle is not None:
             self.lib.kdf_bam_close(self.handle)
@@ -300,6 +325,55 @@ class BamReader:
             self.close()
         except Exception:
             pass
+
+
+def counting_view(batch):
+    """The ``samtools fasta -F 0xD00`` stream of a batch decoded in scan mode: the same
+    packed codes with the bases of the records outside that stream (supplementary reads,
+    later records of a QNAME run: ``fasta_keep == 0``) marked invalid, so that they start
+    no k-mer window.  → ``HostStream`` sharing the batch's code words (the batch must
+    outlive it)."""
+    drop = np.flatnonzero(batch.fasta_keep == 0)
+    if drop.shape[0] == 0:
+        hs = _engine.HostStream(batch.codes, batch.valid, batch.n_bases, batch.read_starts,
+                                batch.read_lens, invalid=getattr(batch, "invalid", None))
+        return hs
+    valid = np.array(batch.valid, dtype=np.uint32, copy=True)
+    extra = []
+    for r in drop.tolist():
+        s, ln = int(batch.read_starts[r]), int(batch.read_lens[r])
+        if ln == 0:
+            continue
+        pos = np.arange(s, s + ln, dtype=np.uint64)
+        np.bitwise_and.at(valid, (pos >> np.uint64(5)).astype(np.int64),
+                          ~(np.uint32(0x80000000) >> (pos & np.uint64(31)).astype(np.uint32)))
+        extra.append(pos.astype(np.uint32))
+    invalid = getattr(batch, "invalid", None)
+    if invalid is not None:
+        invalid = np.union1d(invalid, np.concatenate(extra)) if extra else invalid
+    return _engine.HostStream(batch.codes, valid, batch.n_bases, batch.read_starts, batch.read_lens,
+                              invalid=invalid)
+
+
+def bgzf_write(path, data, level=6, threads=None):
+    """``data`` (bytes-like) as a BGZF file + EOF marker (``kdf_bgzf_write``: every thread
+    deflates blocks).  → uint64 array with the file offset of every 0xff00-byte block and
+    of the EOF block (BAI / TBI virtual offsets: ``block_offset << 16 | offset in block``)."""
+    lib = _engine.load_library()
+    buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
+    n = int(buf.shape[0])
+    nb = (n + BGZF_WRITE_BLOCK - 1) // BGZF_WRITE_BLOCK
+    coff = np.zeros(nb + 1, dtype=np.uint64)
+    got = ctypes.c_uint64(0)
+    rc = lib.kdf_bgzf_write(os.fsencode(path), buf.ctypes.data_as(_vp) if n else None, n, int(level),
+                            int(threads or os.cpu_count() or 1), coff.ctypes.data_as(_vp), nb + 1,
+                            ctypes.byref(got))
+    if rc != 0:
+        raise _engine.KdfError("cannot write %s: %s" % (path, lib.kdf_host_last_error().decode()))
+    return coff
+
+
+BGZF_WRITE_BLOCK = 0xff00
 
 
 def read_fasta_sequences(path):

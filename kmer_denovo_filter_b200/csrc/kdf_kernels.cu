@@ -2833,6 +2833,11 @@ static int bin_stream_impl(const kdf_stream* s, int k, int by_owner, int n_parts
       if (pl.rep_log2 > 0) KDF_BIN2(KW, BM, false, true) else KDF_BIN2(KW, BM, false, false)      \
     }                                                                                             \
   }
+  if (kw == 1) {
+    if (bmode == 0) KDF_BIN(1, 0) else if (bmode == 1) KDF_BIN(1, 1) else KDF_BIN(1, 2)
+  } else {
+    if (bmode == 0) KDF_BIN(2, 0) else if (bmode == 1) KDF_BIN(2, 1) else KDF_BIN(2, 2)
+  }
 #undef KDF_BIN
 #undef KDF_BIN2
   CUDA_TRY(cudaGetLastError());
