@@ -58,14 +58,116 @@ def _parse_hash_size(text):
     return int(float(t) * mult)
 
 
+# ---------------------------------------------------------------------------
+# decode ahead of the GPU
+# ---------------------------------------------------------------------------
+
+# wall-clock accounting of the last pipeline run (seconds): time the decoder threads
+# spent inside kdf_bam_next_batch, and time the consumer waited for a batch
+TIMES = {"decode_s": 0.0, "decode_wait_s": 0.0}
+
+
+def reset_times():
+    for key in list(TIMES):
+        TIMES[key] = 0.0
+
+
+class BamPrefetcher:
+    """Decode a BAM on a background thread, ``depth`` batches ahead of the consumer
+    (the C++ decoder runs without the GIL, so batch i + 1 is inflated and packed while
+    batch i is uploaded and processed on the GPU; started early, a parent is decoded
+    while the child is still being counted).  Iterate it like ``BamReader.batches``;
+    ``reader`` stays open until :meth:`close` (``fetch_records`` needs it)."""
+
+    def __init__(self, path, mode, threads, want_meta=False, batch_bases=BATCH_BASES, depth=2):
+        import queue
+        import threading
+        self.path = path
+        self.reader = bamio.BamReader(path, threads=threads)
+        self._q = queue.Queue(maxsize=max(1, depth))
+        self._err = None
+        self._stop = False
+
+        def work():
+            import time
+            try:
+                while not self._stop:
+                    t0 = time.perf_counter()
+                    b = self.reader.next_batch(mode, batch_bases, want_meta)
+                    TIMES["decode_s"] += time.perf_counter() - t0
+                    last = b.at_eof
+                    if b.n_reads:
+                        self._q.put(b)
+                    else:
+                        b.close()
+                    if last:
+                        break
+            except BaseException as e:      # surfaced in the consumer
+                self._err = e
+            self._q.put(None)
+        self._t = threading.Thread(target=work, name="kdf-decode", daemon=True)
+        self._t.start()
+
+    def __iter__(self):
+        import time
+        while True:
+            t0 = time.perf_counter()
+            b = self._q.get()
+            TIMES["decode_wait_s"] += time.perf_counter() - t0
+            if b is None:
+                if self._err is not None:
+                    raise self._err
+                return
+            yield b
+
+    def close(self):
+        self._stop = True
+        try:
+            while self._t.is_alive():
+                try:
+                    b = self._q.get(timeout=0.05)
+                    if b is not None:
+                        b.close()
+                except Exception:
+                    pass
+        finally:
+            self.reader.close()
+
+
+# prefetchers started ahead of their consumer, by BAM path (run_discovery_pipeline starts the
+# parents' decode before the child has been counted)
+_PREFETCH = {}
+
+
+def start_prefetch(path, mode, threads, want_meta=False, batch_bases=BATCH_BASES, depth=2):
+    pf = _PREFETCH.get((path, mode))
+    if pf is None:
+        pf = _PREFETCH[(path, mode)] = BamPrefetcher(path, mode, threads, want_meta, batch_bases, depth)
+    return pf
+
+
+def take_prefetch(path, mode, threads, want_meta=False, batch_bases=BATCH_BASES):
+    """The prefetcher started for (path, mode), or a new one."""
+    pf = _PREFETCH.pop((path, mode), None)
+    if pf is None:
+        pf = BamPrefetcher(path, mode, threads, want_meta, batch_bases)
+    return pf
+
+
+def drop_prefetch():
+    for key in list(_PREFETCH):
+        _PREFETCH.pop(key).close()
+
+
 def count_bam_into_table(eng, bam_path, table, mode, plane, threads, batch_bases=BATCH_BASES):
     """Stream ``samtools fasta -F 0xD00``-equivalent reads of a BAM through K1+K2
     against ``table`` (filtered parent counts: the table is primed with the filter
     set and never grows).  Returns ``(table, stats dict)``."""
     from ..discovery import kmer_chain as _kmer_chain   # (discovery imports this module)
     total = {"windows": 0, "hits": 0, "new": 0, "reads": 0, "bases": 0}
-    with bamio.BamReader(bam_path, threads=threads) as rd:
-        for batch in rd.batches(bamio.MODE_FASTA, max_bases=batch_bases):
+    pf = take_prefetch(bam_path, bamio.MODE_FASTA, threads, False, batch_bases)
+    try:
+        for batch in pf:
             ds = eng.upload(batch, with_reads=False)
             st = eng.new_stats()
             if mode == _engine.MODE_COUNT_IF_PRESENT:
@@ -84,6 +186,8 @@ def count_bam_into_table(eng, bam_path, table, mode, plane, threads, batch_bases
             total["reads"] += batch.n_reads
             total["bases"] += batch.n_bases
             batch.close()
+    finally:
+        pf.close()
     return table, total
 
 
@@ -102,22 +206,24 @@ class RefIndex:
         self.keys = keys          # (lo u64, hi u64) numpy or None
         self.source = source
 
-    def to_bins(self, eng, n_parts):
+    def to_bins(self, eng, n_parts, pass_=None):
         """The reference's canonical k-mers in ``n_parts`` hash-range bins (the input
-        of ``kdf_count_bins``), with an exact-size retry if a range is skewed."""
+        of ``kdf_count_bins``; with ``pass_`` only those of one group of a multi-pass
+        count), with an exact-size retry if a range is skewed."""
         from ..discovery import kmer_chain
         if self.host_stream is not None:
             n_max = self.host_stream.n_bases
         else:
             n_max = int(self.keys[0].shape[0])
-        cap = kmer_chain._bin_capacity(max(n_max, 1), n_parts)
+        groups = (1 << pass_[0]) if pass_ else 1
+        cap = kmer_chain._bin_capacity(max(n_max, 1) / groups, n_parts)
         while True:
             bins = eng.new_bins(self.k, n_parts, cap)
             if self.host_stream is not None:
-                eng.bin_stream(bins, eng.upload(self.host_stream, with_reads=False))
+                eng.bin_stream(bins, eng.upload(self.host_stream, with_reads=False), pass_=pass_)
             else:
                 lo, hi = eng.keys_to_device(self.keys, bins.key_words)
-                eng.bin_keys(bins, lo, hi)
+                eng.bin_keys(bins, lo, hi, pass_=pass_)
             if not bins.overflowed():
                 return bins
             cap = int(bins.counts().max()) + 4

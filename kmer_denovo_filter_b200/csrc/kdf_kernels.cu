@@ -824,6 +824,13 @@ __device__ __forceinline__ u32 resolve_packed_mark(const TableView<KW>& t, u32 b
   return R_FULL;
 }
 
+// What bounds this kernel (round 2, profiles/r2c_count_variants.md): a lean variant
+// without the software pipeline (80 registers, 3 blocks per SM, a third fewer
+// instructions) and a split-phase variant (compare-and-swaps issued in one drain,
+// checked in the next) were built and measured: 18.8 / 20.9 ms against 18.8 ms for this
+// kernel.  Occupancy, instruction count and exposed atomic latency are not what limits it;
+// the L2's rate for the mix "one 32-byte read per key + a returning compare-and-swap for one
+// key in six" is (microbenchmark: 95 G ops/s = 16.1 ms for the 1.53 G keys of the bench).
 // k_update_keys for the packed form: OP_PACKED_COUNT inserts / bumps the child's
 // keys, OP_PACKED_MARK turns "saturated" into "saturated, in the reference".
 //
@@ -1120,116 +1127,6 @@ __global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_packed_keys(TableView<
   } else {
     tally_packed(st, sq_drain<KW, OP>(&q, t, sh, sat, sink, true));
   }
-  flush_stats(st, stats);
-}
-
-// Lean form of the packed count (the default; KDF_COUNT_LEAN=0 takes the pipelined
-// kernel above).  ncu on the pipelined kernel (profiles/r2b_ncu_k_packed_keys.txt): 176
-// warp instructions per 32 keys — 27 % of them register moves, the rotation of a
-// three-stage software pipeline that needs 128 registers and therefore runs at 2 blocks
-// per SM (24 % of the warp slots), issue slots 44 % busy, long_scoreboard the top stall.
-// Here a thread takes LEAN_CHUNK keys per round with no software pipeline: keys -> hash ->
-// bucket loads -> resolve, the latencies hidden by occupancy instead (<= 64 registers:
-// 4 blocks of 256 threads per SM).  Same queues, same drain, same results.
-// the rare paths of the lean kernel, out of line so that they cost it no registers:
-// kind 0 = home bucket full (probe on from bucket b), 1 / 2 = the queue was full (bump /
-// insert in place).  Returns a resolve code for tally().
-template <int KW>
-__device__ __noinline__ u32 lean_rare(PackedQueues<KW>* qp, TableView<KW> t, Key<KW> key, u32 b, u32 info,
-                                      u64 ms, int sh, u32 sat) {
-  constexpr int S = SPB<KW>::v;
-  const HitSink sink = {nullptr, nullptr, 0, nullptr};
-  if ((info & 3u) == 0) return sq_push_or_resolve<KW, OP_PACKED_COUNT>(qp->slow, t, b, key, sh, sat, 0, sink);
-  if ((info & 3u) == 1) {
-    packed_bump(t.keys + ((u64)b * S + (info >> 2)) * KW + (KW - 1), ms, sh, sat);
-    return R_MISS;   // (the hit was tallied by the caller)
-  }
-  return resolve_packed_count<KW>(t, b, key, sh, sat);
-}
-
-template <int KW, bool FILT, int CHUNK, int BLOCKS>
-__global__ void __launch_bounds__(256, BLOCKS) k_packed_count_lean(
-    TableView<KW> t, const u64* lo, u64 n_max, const u64* n_dev, int sh, u32 sat, u64* stats, int filt_log2,
-    u32 filt_val) {
-  constexpr int S = SPB<KW>::v;
-  constexpr int OP = OP_PACKED_COUNT;
-  const u64 mask = (1ull << sh) - 1;
-  u64 n = n_max;
-  if (n_dev) {
-    u64 nd = *n_dev;
-    n = nd < n_max ? nd : n_max;
-  }
-  extern __shared__ __align__(16) unsigned char pk_smem[];   // one queue pair per warp
-  PackedQueues<KW>& q = reinterpret_cast<PackedQueues<KW>*>(pk_smem)[threadIdx.x >> 5];
-  if ((threadIdx.x & 31) == 0) {
-    q.fast.count = 0;
-    q.slow.count = 0;
-  }
-  __syncwarp();
-  LocalStats st = {0, 0, 0, 0};
-  const HitSink sink = {nullptr, nullptr, 0, nullptr};
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  const u64 n_iter = (n + stride * CHUNK - 1) / (stride * CHUNK);   // warp-uniform
-  const u64 first = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  for (u64 itn = 0; itn < n_iter; ++itn) {
-    Key<KW> keys[CHUNK];
-    Bucket<KW> bk[CHUNK];
-    u32 bidx[CHUNK];
-    u32 okm = 0;
-    const u64 i0 = first + itn * stride * CHUNK;
-#pragma unroll
-    for (int u = 0; u < CHUNK; ++u) {
-      const u64 i = i0 + (u64)u * stride;
-      if (i < n) {
-        okm |= 1u << u;
-        keys[u] = ld_key_pinned<KW>(lo, i);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < CHUNK; ++u) {
-      if (okm & (1u << u)) {
-        const u64 h = hash_key(keys[u]);
-        if (FILT && part_of(h, filt_log2) != filt_val) {
-          okm &= ~(1u << u);
-        } else {
-          bidx[u] = bucket_of(h, t.log2_parts, t.n_buckets);
-          bk[u] = ld_bucket<KW>(t.keys + (u64)bidx[u] * 4 * KW);
-        }
-      }
-    }
-    st.windows += __popc(okm);
-#pragma unroll
-    for (int u = 0; u < CHUNK; ++u) {
-      if (okm & (1u << u)) {
-        u64 ms = 0;
-        const int j = match_packed(bk[u], keys[u], mask, ms);
-        u32 info = 0;   // kind (1 bump, 2 insert) | slot << 2; 0 = nothing owed
-        if (j >= 0) {
-          st.hits++;
-          if ((u32)(ms >> sh) < sat) info = 1u | ((u32)j << 2);
-        } else {
-          int c = -1;
-#pragma unroll
-          for (int cc = S - 1; cc >= 0; --cc)
-            if (maybe_empty(bk[u], cc, keys[u])) c = cc;
-          if (c < 0) {  // home bucket full: probe on from the next one
-            u32 nb = (bidx[u] + 1 == t.n_buckets) ? 0 : bidx[u] + 1;
-            tally(st, lean_rare<KW>(&q, t, keys[u], nb, 0u, 0ull, sh, sat));
-          } else {
-            info = 2u | ((u32)c << 2);
-            ms = 0;
-          }
-        }
-        if (info && !pq_push<KW>(q.fast, keys[u], bidx[u], info, ms))   // queue full: in place
-          tally(st, lean_rare<KW>(&q, t, keys[u], bidx[u], info, ms, sh, sat));
-      }
-    }
-    __syncwarp();
-    if (q.fast.count >= (u32)PQ_DRAIN) tally_packed(st, pq_drain<KW>(&q, t, sh, sat, false));
-    if (q.slow.count >= 32) tally_packed(st, sq_drain<KW, OP>(&q.slow, t, sh, sat, sink, false));
-  }
-  tally_packed(st, pq_drain<KW>(&q, t, sh, sat, true));
-  tally_packed(st, sq_drain<KW, OP>(&q.slow, t, sh, sat, sink, true));
   flush_stats(st, stats);
 }
 
@@ -2251,42 +2148,10 @@ static int launch_emit_buckets(const kdf_table* t, u32 min0, u32 max0, u32 min1,
   return KDF_OK;
 }
 
-// shape of the lean count kernel: KDF_COUNT_LEAN = 0 (pipelined kernel) or "<chunk><blocks>"
-// with chunk in {2, 4} keys per thread per round and blocks in {2, 3, 4} per SM
-static int count_lean_shape() {
-  static const int v = env_int("KDF_COUNT_LEAN", 23);
-  return v;
-}
-
-template <int KW, bool FILT, int CHUNK, int BLOCKS>
-static int launch_count_lean(const TableView<KW>& tv, const kdf_table* t, const u64* lo, u64 n_max,
-                             const u64* n_dev, int sh, u32 sat, u64* stats, cudaStream_t st, int filt_log2,
-                             u32 filt_val) {
-  const size_t smem = sizeof(PackedQueues<KW>) * (256 / 32);
-  const u64 items = (n_max + CHUNK - 1) / CHUNK;
-  const void* fn = (const void*)k_packed_count_lean<KW, FILT, CHUNK, BLOCKS>;
-  CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int g = grid_for(fn, 256, smem, items, t->sm_count);
-  k_packed_count_lean<KW, FILT, CHUNK, BLOCKS><<<g, 256, smem, st>>>(tv, lo, n_max, n_dev, sh, sat, stats,
-                                                                   filt_log2, filt_val);
-  CUDA_TRY(cudaGetLastError());
-  return KDF_OK;
-}
-
 template <int KW, int OP>
 static int launch_packed_keys(const kdf_table* t, const u64* lo, u64 n_max, const u64* n_dev, int sh,
                               u32 sat, u64* stats, cudaStream_t st, int filt_log2, u32 filt_val) {
   TableView<KW> tv = view_of_table<KW>(t);
-  if constexpr (OP == OP_PACKED_COUNT) {
-    const int shape = count_lean_shape();
-#define KDF_LEAN(C, B)                                                                                  \
-  if (shape == C * 10 + B)                                                                              \
-    return filt_log2 > 0 ? launch_count_lean<KW, true, C, B>(tv, t, lo, n_max, n_dev, sh, sat, stats, st, \
-                                                             filt_log2, filt_val)                        \
-                         : launch_count_lean<KW, false, C, B>(tv, t, lo, n_max, n_dev, sh, sat, stats, st, 0, 0);
-    KDF_LEAN(2, 3) KDF_LEAN(2, 4) KDF_LEAN(4, 3) KDF_LEAN(4, 2)
-#undef KDF_LEAN
-  }
   const size_t smem = sizeof(PackedKeysQueue<KW, OP>) * (256 / 32);
   const u64 items = (n_max + KDF_KEYS_CHUNK - 1) / KDF_KEYS_CHUNK;
   if (filt_log2 > 0) {

@@ -42,76 +42,193 @@ logger = logging.getLogger(__name__)
 REF_PLANE = 1  # plane 1 of the child table holds the "in reference" flag
 
 
+class ChildScanCache:
+    """The child BAM decoded ONCE.  The reference reads it three times (``samtools fasta``
+    for the count, the pysam scan of Module 3, the informative-reads writer); here one
+    scan-mode decode (with metadata) feeds all three: the counting stream is the same
+    packed codes behind the ``fasta_keep`` mask (``bamio.counting_view``), the batches stay
+    in host memory for the per-read scan (and for the later passes of a multi-pass
+    count), and the writer fetches the few informative records back by their offsets
+    (``kdf_bam_fetch_records``).  ``KDF_CHILD_CACHE_GB`` bounds the host memory (default
+    64; 0 disables the cache); past it the batches are dropped and every later consumer
+    decodes the file again, as the reference does."""
+
+    def __init__(self, path, threads, batch_bases=kw.BATCH_BASES):
+        self.path = path
+        self.threads = threads
+        self.batch_bases = batch_bases
+        self.pf = kw.take_prefetch(path, bamio.MODE_SCAN, threads, True, batch_bases)
+        self.reader = self.pf.reader
+        self.batches = []
+        self.nbytes = 0
+        self.limit = int(float(os.environ.get("KDF_CHILD_CACHE_GB", "64")) * (1 << 30))
+        self.complete = False      # every batch of the file is held in `batches`
+        self.decoded = False       # the first pass over the file is over
+        self.reads = self.bases = 0
+        self.hit_reads = []        # (uncompressed offset, qname, is_supplementary) of reads with hits
+
+    @staticmethod
+    def _batch_bytes(b):
+        n = b.codes.nbytes + b.valid.nbytes + b.read_starts.nbytes + b.read_lens.nbytes
+        for name in ("qname_blob", "cigar_blob", "sa_blob", "invalid"):
+            a = getattr(b, name, None)
+            n += a.nbytes if a is not None else 0
+        return n + 64 * b.n_reads
+
+    def stream(self):
+        """The scan-mode batches of the file: the first call decodes it (keeping the
+        batches while they fit), later calls replay the kept batches or decode again.
+        The caller must not close what it gets."""
+        if self.complete:
+            for b in self.batches:
+                yield b
+            return
+        if self.decoded:       # the batches did not fit: another pass over the file
+            pf = kw.BamPrefetcher(self.path, bamio.MODE_SCAN, self.threads, True, self.batch_bases)
+            try:
+                for b in pf:
+                    yield b
+                    b.close()
+            finally:
+                pf.close()
+            return
+        keep = self.limit > 0
+        for b in self.pf:
+            self.reads += b.n_reads
+            self.bases += b.n_bases
+            if keep:
+                self.nbytes += self._batch_bytes(b)
+                if self.nbytes > self.limit:
+                    logger.info("  child batches exceed KDF_CHILD_CACHE_GB: later stages decode %s again",
+                                self.path)
+                    keep = False
+                    for old in self.batches:
+                        old.close()
+                    self.batches = []
+            if keep:
+                self.batches.append(b)
+            yield b
+            if not keep:
+                b.close()
+        self.decoded = True
+        self.complete = keep
+
+    def release_batches(self):
+        """The per-read scan is done: only the hit list and the reader are still needed."""
+        for b in self.batches:
+            b.close()
+        self.batches = []
+        self.complete = False
+
+    def note_hit(self, batch, r):
+        rec = batch.record(r)
+        self.hit_reads.append((int(batch.rec_uoff[r]), rec.query_name, rec.is_supplementary))
+
+    def close(self):
+        self.release_batches()
+        self.pf.close()
+
+
+_CHILD_CACHE = {}
+
+
+def child_cache(path):
+    return _CHILD_CACHE.get(path)
+
+
+def drop_child_caches():
+    for key in list(_CHILD_CACHE):
+        _CHILD_CACHE.pop(key).close()
+
+
 class ChildCandidates:
     """Module-1 handle: the child's canonical k-mers in hash-range bins (HBM) plus
     the counts of the first pass; replaces ``child.jf`` / ``child_candidates.fa``.
     The count table itself never exists in HBM: every pass re-counts the bins in
-    an L2-resident slice (``kdf_count_bins``)."""
+    an L2-resident slice (``kdf_count_bins``).  When the bins of the whole sample would
+    not fit the device (``kmer_chain.plan_child_count``: a whole-genome child is 8 bytes
+    x 9e10 k-mer instances) the hash ranges are taken in ``n_passes`` groups: each pass
+    re-bins the packed batches (from host memory, or by decoding the file again) and
+    counts only its own ranges — the analogue of Jellyfish's sized hash with spill files
+    (``core/jellyfish_wrappers.py:73-107, 335-366``)."""
 
-    def __init__(self, eng, bins, slice_capacity, min_child_count, n_candidates, stats):
+    def __init__(self, eng, k, source, n_passes, n_local, slice_capacity, min_child_count, stats,
+                 bins0=None, bin_cap=None):
         self.engine = eng
-        self.bins = bins
+        self.k = k
+        self.source = source            # ChildScanCache
+        self.n_passes = n_passes
+        self.n_local = n_local
         self.slice_capacity = slice_capacity
         self.min_child_count = min_child_count
-        self.n_candidates = n_candidates
-        self.stats = stats          # windows (k-mer instances), new (distinct), reads, bases
-        self.k = bins.k
+        self.n_candidates = 0
+        self.stats = stats              # windows (k-mer instances), new (distinct), reads, bases
+        self.bins = bins0               # the bins of pass 0 (the only pass, usually): kept
+        self.bin_cap = bin_cap
 
-    def count(self, ref_bins=None, out_cap=1, **thresholds):
-        """One counting pass over the bins → ``eng.count_bins`` result; the slice is
-        enlarged (and the pass redone) when a bin holds more distinct k-mers than it."""
+    def _pass(self, p):
+        return (self.n_passes.bit_length() - 1, p) if self.n_passes > 1 else None
+
+    def _bins_of_pass(self, p):
+        """Hash-range bins of pass ``p``: the kept ones, or re-binned from the batches."""
         eng = self.engine
+        if p == 0 and self.bins is not None:
+            return self.bins
         while True:
-            res = eng.count_bins(self.bins, ref_bins, self.slice_capacity, out_cap=out_cap,
-                                 count_min0=self.min_child_count, **thresholds)
-            if res["full"]:
-                if self.slice_capacity >= 2 * self.bins.bin_cap:
-                    raise _engine.KdfError("k-mer table slice full at %d slots" % self.slice_capacity)
-                self.slice_capacity = min(self.slice_capacity * 4, 2 * self.bins.bin_cap + 4)
-                logger.info("  growing the table slice to %d slots", self.slice_capacity)
-                continue
-            if res["n_out"] > out_cap and out_cap > 1:
-                out_cap = res["n_out"]
-                continue
-            return res
+            bins = eng.new_bins(self.k, self.n_local, self.bin_cap)
+            for b in self.source.stream():
+                eng.bin_stream(bins, eng.upload(bamio.counting_view(b), with_reads=False), None,
+                               pass_=self._pass(p))
+            if not bins.overflowed():
+                return bins
+            self.bin_cap = int(bins.counts().max()) + 4
+            logger.info("  hash ranges are skewed: re-binning with %d slots per bin", self.bin_cap)
+
+    def count(self, ref_index=None, out_cap=1, want_planes=False, **thresholds):
+        """One counting pass over all hash ranges → the ``eng.count_bins`` result (summed
+        over the passes); a slice that turns out too small is enlarged and redone."""
+        eng = self.engine
+        torch = eng.torch
+        tot = {"n_out": 0, "keys": 0, "hits": 0, "distinct": 0, "n_count": 0, "occupied": 0}
+        parts = {"lo": [], "hi": [], "p0": [], "p1": []}
+        for p in range(self.n_passes):
+            bins = self._bins_of_pass(p)
+            ref_bins = ref_index.to_bins(eng, self.n_local, self._pass(p)) if ref_index is not None else None
+            cap = out_cap
+            while True:
+                res = eng.count_bins(bins, ref_bins, self.slice_capacity, out_cap=cap,
+                                     count_min0=self.min_child_count, want_planes=want_planes,
+                                     pass_=self._pass(p), **thresholds)
+                if res["full"]:
+                    if self.slice_capacity >= 2 * bins.bin_cap:
+                        raise _engine.KdfError("k-mer table slice full at %d slots" % self.slice_capacity)
+                    self.slice_capacity = min(self.slice_capacity * 4, 2 * bins.bin_cap + 4)
+                    logger.info("  growing the table slice to %d slots", self.slice_capacity)
+                    continue
+                if res["n_out"] > cap and cap > 1:
+                    cap = res["n_out"]
+                    continue
+                break
+            for key in tot:
+                tot[key] += res[key]
+            for key in parts:
+                if res.get(key) is not None:
+                    parts[key].append(res[key])
+            if not (p == 0 and bins is self.bins):
+                del bins
+        out = dict(tot)
+        out["full"] = 0
+        for key, v in parts.items():
+            out[key] = (v[0] if len(v) == 1 else torch.cat(v)) if v else None
+        return out
 
     def dump(self, **thresholds):
         """All (key, count, in-reference flag) that pass the thresholds — what
         ``jellyfish dump -c`` would print; used by the tests."""
-        res = self.count(out_cap=max(self.stats["new"], 2), want_planes=True, **thresholds)
-        return res
+        return self.count(out_cap=max(self.stats["new"], 2), want_planes=True, **thresholds)
 
     def close(self):
         self.bins = None
-
-
-def bin_bam(eng, bam_path, kmer_size, threads, mode=bamio.MODE_FASTA, batch_bases=kw.BATCH_BASES):
-    """Decode a BAM (``samtools fasta -F 0xD00`` semantics) and append every valid
-    canonical k-mer to hash-range bins.  The packed batches are held in host memory
-    until the bins are known to be large enough (a skewed hash range triggers one
-    exact-size retry).  → (bins, slice_capacity, stats)."""
-    batches = []
-    with bamio.BamReader(bam_path, threads=threads) as rd:
-        for batch in rd.batches(mode, max_bases=batch_bases):
-            batches.append(batch)
-    n_max = sum(b.n_bases for b in batches)
-    tot = {"reads": sum(b.n_reads for b in batches), "bases": n_max}
-    n_parts, slice_capacity = kmer_chain.plan_partitions(max(n_max, 1), key_words=eng.lib.kdf_key_words(kmer_size))
-    bin_cap = kmer_chain._bin_capacity(max(n_max, 1), n_parts)
-    while True:
-        bins = eng.new_bins(kmer_size, n_parts, bin_cap)
-        st = eng.new_stats()
-        for b in batches:
-            ds = eng.upload(b, with_reads=False)
-            eng.bin_stream(bins, ds, st)
-        if not bins.overflowed():
-            break
-        bin_cap = int(bins.counts().max()) + 4
-        logger.info("  hash ranges are skewed: re-binning with %d slots per bin", bin_cap)
-    for b in batches:
-        b.close()
-    tot["windows"] = eng.read_stats(st)["windows"]
-    return bins, slice_capacity, tot
 
 
 # ── Module 1 ───────────────────────────────────────────────────────
@@ -132,18 +249,48 @@ def _extract_child_kmers_discovery(child_bam, ref_fasta, kmer_size, min_child_co
             "128-bit above)" % kmer_size)
     t0 = time.monotonic()
     logger.info("Extracting child k-mers from BAM (k=%d)…", kmer_size)
-    bins, slice_capacity, tot = bin_bam(eng, child_bam, kmer_size, threads)
+    old = _CHILD_CACHE.pop(child_bam, None)
+    if old is not None:
+        old.close()
+    cache = _CHILD_CACHE[child_bam] = ChildScanCache(child_bam, threads)
+    # The layout of the count is planned before the file has been read, from its size: a BAM
+    # holds at most ~4 bases per compressed byte.  Too few bases guessed → the bins overflow
+    # and the pass is redone with exact sizes; too many → bins larger than needed.
+    est = max(int(os.path.getsize(child_bam) * 4), 1 << 16)
+    n_passes, n_local, slice_capacity = kmer_chain.plan_child_count(eng, est, 0, kmer_size, min_child_count)
+    bin_cap = kmer_chain._bin_capacity(est / n_passes, n_local)
+    pass0 = (n_passes.bit_length() - 1, 0) if n_passes > 1 else None
+    bins = eng.new_bins(kmer_size, n_local, bin_cap)
+    st = eng.new_stats()
+    for b in cache.stream():        # decode + bin pass 0, batch by batch
+        eng.bin_stream(bins, eng.upload(bamio.counting_view(b), with_reads=False), st, pass_=pass0)
+    tot = {"reads": cache.reads, "bases": cache.bases}
+    # now that the size is known: the real plan
+    n_max = max(cache.bases, 1)
+    real = kmer_chain.plan_child_count(eng, n_max, 0, kmer_size, min_child_count)
+    keep0 = (not bins.overflowed()) and real[0] <= n_passes
+    if keep0:
+        # fewer hash ranges would have done, but these are already binned: keep the layout,
+        # size the slices for the real number of k-mers
+        slice_capacity = (max(1024, -(-max(n_max // kmer_chain.SLOTS_DIV, 1024) // (n_passes * n_local))) + 3) & ~3
+    else:
+        logger.info("  the size estimate was off (%d bases): re-binning with %d pass(es)", n_max, real[0])
+        n_passes, n_local, slice_capacity = real
+        bins = None
+        bin_cap = kmer_chain._bin_capacity(n_max / n_passes, n_local)
     n_keys = kw._parse_hash_size(jf_hash_size)
     if n_keys:
-        slice_capacity = max(slice_capacity, (n_keys // bins.n_parts + 3) & ~3)
-    cand = ChildCandidates(eng, bins, slice_capacity, min_child_count, 0, tot)
+        slice_capacity = max(slice_capacity, (n_keys // (n_passes * n_local) + 3) & ~3)
+    cand = ChildCandidates(eng, kmer_size, cache, n_passes, n_local, slice_capacity, min_child_count, tot,
+                           bins0=bins, bin_cap=bins.bin_cap if bins is not None else bin_cap)
     res = cand.count(min0=min_child_count)
+    tot["windows"] = res["keys"]
     tot["new"] = res["distinct"]
     tot["hits"] = res["hits"]
     cand.n_candidates = n_candidates = res["n_count"]
     logger.info("Child k-mer counting complete (%.1fs): %d reads, %d k-mer instances, "
-                "%d distinct (%d hash ranges x %d slots)", time.monotonic() - t0, tot["reads"],
-                tot["windows"], tot["new"], bins.n_parts, cand.slice_capacity)
+                "%d distinct (%d pass(es) x %d hash ranges x %d slots)", time.monotonic() - t0,
+                tot["reads"], tot["windows"], tot["new"], n_passes, n_local, cand.slice_capacity)
     logger.info("Child candidate k-mers (count >= %d): %d", min_child_count, n_candidates)
     return cand, n_candidates
 
@@ -158,8 +305,7 @@ def _subtract_reference_kmers(ref_jf, child_candidates_fa, tmpdir):
     reference deletes its input FASTA."""
     cand = child_candidates_fa
     eng = cand.engine
-    ref_bins = ref_jf.to_bins(eng, cand.bins.n_parts)
-    res = cand.count(ref_bins, out_cap=max(cand.n_candidates, 2), min0=cand.min_child_count, max1=0)
+    res = cand.count(ref_jf, out_cap=max(cand.n_candidates, 2), min0=cand.min_child_count, max1=0)
     k = cand.k
     cand.close()
     logger.info("Non-reference child k-mers after subtraction: %d", res["n_out"])
@@ -287,8 +433,14 @@ def scan_child_reads(eng, child_bam, table, kmer_size, min_distinct_kmers_per_re
 
     Yields ``(batch, ndistinct u32[], nhits u32[], hit_read_idx, hit_offset)``
     per batch, hits sorted by (read, offset)."""
-    with bamio.BamReader(child_bam, threads=threads) as rd:
-        for batch in rd.batches(bamio.MODE_SCAN, max_bases=batch_bases, want_meta=True):
+    cache = child_cache(child_bam)
+    if cache is not None:
+        source, owned = cache.batches, False          # decoded once, in Module 1
+    else:
+        pf = kw.take_prefetch(child_bam, bamio.MODE_SCAN, threads, True, batch_bases)
+        source, owned = pf, True
+    try:
+        for batch in source:
             ds = eng.upload(batch)
             # sparse form: a streaming probe emits the (rare) hit windows, the device
             # reduces them per read; dense per-read arrays are rebuilt here for the
@@ -312,6 +464,11 @@ def scan_child_reads(eng, child_bam, table, kmer_size, min_distinct_kmers_per_re
                 off = np.zeros(0, dtype=np.int64)
                 slot = np.zeros(0, dtype=np.uint32)
             yield batch, nd, nh, ridx, off, slot
+            if owned:
+                batch.close()
+    finally:
+        if owned:
+            pf.close()
 
 
 def _cluster_hits(read_hits, merge_distance):

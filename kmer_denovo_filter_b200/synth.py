@@ -91,15 +91,19 @@ def _pack_chunk(torch, bases, valid):
 
 
 def make_reads(torch, haps, n_pairs, read_len=150, seed=5000, insert_mean=400.0, insert_sd=50.0,
-               chunk_pairs=1 << 19):
+               chunk_pairs=1 << 19, table=None):
     """Paired reads from a list of haplotypes → packed stream tensors on the device.
 
-    Returns dict(codes int64, valid int32, n_bases, read_starts int64, read_lens int32)."""
+    Returns dict(codes int64, valid int32, n_bases, read_starts int64, read_lens int32).
+    ``table`` (a dict) additionally receives the reads themselves, for writing them as an
+    aligned BAM: ``bases`` uint8 (2 n_pairs, read_len) with N = 4, as sequenced; ``hap``
+    (which haplotype), ``start`` / ``insert`` per pair (haplotype coordinates)."""
     dev = haps[0].device
     g = _gen(torch, dev, seed)
     L = read_len
     n_pairs = (n_pairs + 15) // 16 * 16          # 2*n_pairs reads, multiple of 32
     codes_out, valid_out = [], []
+    t_bases, t_hap, t_start, t_ins = [], [], [], []
     ar = torch.arange(L, device=dev, dtype=torch.int64)
     done = 0
     while done < n_pairs:
@@ -108,12 +112,14 @@ def make_reads(torch, haps, n_pairs, read_len=150, seed=5000, insert_mean=400.0,
         ins = torch.clamp((torch.randn(m, device=dev, generator=g) * insert_sd + insert_mean).round(),
                           L, 4 * insert_mean).to(torch.int64)
         bases = torch.zeros((2 * m, L + 1), dtype=torch.uint8, device=dev)
+        starts_all = torch.zeros(m, dtype=torch.int64, device=dev)
         for h, hap in enumerate(haps):
             sel = torch.nonzero(which == h).squeeze(1)
             if sel.numel() == 0:
                 continue
             span = hap.shape[0] - ins[sel]
             start = (torch.rand(sel.numel(), device=dev, generator=g, dtype=torch.float64) * span).to(torch.int64)
+            starts_all[sel] = start
             r1 = hap[start[:, None] + ar[None, :]]
             r2i = (start + ins[sel] - 1)[:, None] - ar[None, :]
             r2 = 3 - hap[r2i]
@@ -125,12 +131,20 @@ def make_reads(torch, haps, n_pairs, read_len=150, seed=5000, insert_mean=400.0,
         valid = torch.ones((2 * m, L + 1), dtype=torch.uint8, device=dev)
         valid[:, :L] = (torch.rand((2 * m, L), device=dev, generator=g) >= N_RATE).to(torch.uint8)
         valid[:, L] = 0
+        if table is not None:
+            t_bases.append(torch.where(valid[:, :L] != 0, bases[:, :L], torch.full_like(bases[:, :L], 4)).cpu())
+            t_hap.append(which.cpu())
+            t_start.append(starts_all.cpu())
+            t_ins.append(ins.cpu())
         c, v = _pack_chunk(torch, bases, valid)
         codes_out.append(c)
         valid_out.append(v)
         done += m
     n_reads = 2 * n_pairs
     n_bases = n_reads * (L + 1) - 1
+    if table is not None:
+        table.update({"bases": torch.cat(t_bases).numpy(), "hap": torch.cat(t_hap).numpy(),
+                      "start": torch.cat(t_start).numpy(), "insert": torch.cat(t_ins).numpy()})
     codes = torch.cat(codes_out)
     valid = torch.cat(valid_out)
     n_words = (n_bases + 31) // 32

@@ -194,3 +194,147 @@ def test_count_bam_into_table_routes_probes_through_the_chain_helper(giab_paths)
                                           batch_bases=500_000)
         assert len(eng.calls) > 3 and all(c[:3] == (mode, 1, 1) for c in eng.calls)
         assert tot["windows"] == sum(c[3] for c in eng.calls) == tot["bases"]
+
+
+# ---------------------------------------------------------------------------
+# round 2: one decode for the counting stream and the scan, random access to
+# records, the BGZF writer, corrupt input
+# ---------------------------------------------------------------------------
+
+def _kmer_multiset(hs, k=21):
+    lo, hi, ok = engine.debug_extract_host(hs, k)
+    return np.sort(lo[ok])
+
+
+@pytest.mark.parametrize("who", ["child", "mother"])
+def test_fasta_keep_mask_gives_the_counting_stream(giab_paths, who):
+    """A scan-mode decode + the fasta_keep mask = the `samtools fasta -F 0xD00` stream:
+    same records, and (through bamio.counting_view) the same canonical k-mers."""
+    with bamio.BamReader(giab_paths[who], threads=3) as rd:
+        f = rd.next_batch(bamio.MODE_FASTA)
+    with bamio.BamReader(giab_paths[who], threads=3) as rd:
+        s = rd.next_batch(bamio.MODE_SCAN, want_meta=True)
+    with bamio.BamReader(giab_paths[who], threads=3) as rd:
+        a = rd.next_batch(bamio.MODE_ALL)
+    assert f.fasta_keep.all()
+    assert s.rec_index[s.fasta_keep == 1].tolist() == f.rec_index.tolist()
+    assert a.rec_index[a.fasta_keep == 1].tolist() == f.rec_index.tolist()
+    assert 0 < int((s.fasta_keep == 0).sum()) < s.n_reads // 2     # the fixture has supplementary reads
+    view = bamio.counting_view(s)
+    assert np.array_equal(_kmer_multiset(view), _kmer_multiset(f))
+    assert np.array_equal(view.invalid, engine.invalid_positions(view.valid, view.n_bases))
+    assert np.array_equal(s.valid, engine.HostStream(s.codes, s.valid, s.n_bases, s.read_starts,
+                                                     s.read_lens).valid)      # the batch itself is untouched
+
+
+def test_fasta_keep_survives_batch_limits(giab_paths):
+    """The QNAME-run state is carried across batches (and rolled back for a record that a
+    batch limit postponed) in every mode."""
+    with bamio.BamReader(giab_paths["child"], threads=2) as rd:
+        whole = rd.next_batch(bamio.MODE_SCAN)
+    keep = []
+    with bamio.BamReader(giab_paths["child"], threads=2) as rd:
+        for b in rd.batches(bamio.MODE_SCAN, max_bases=50_000):
+            keep += b.fasta_keep.tolist()
+    assert keep == whole.fasta_keep.tolist()
+
+
+@pytest.mark.parametrize("chunk_kb,gap", [(None, None), (64, 16)])
+def test_fetch_records_by_offset(giab_paths, monkeypatch, chunk_kb, gap):
+    """rec_uoff + kdf_bam_fetch_records return exactly the raw records of a full decode,
+    whatever the chunking of the sequential pass that produced the offsets."""
+    if chunk_kb:
+        monkeypatch.setenv("KDF_BAM_CHUNK_KB", str(chunk_kb))
+        monkeypatch.setenv("KDF_BAM_GAP", str(gap))
+    with bamio.BamReader(giab_paths["child"], threads=3) as rd:
+        raws, uoffs = [], []
+        for b in rd.batches(bamio.MODE_ALL, max_bases=400_000, want_meta=3):
+            ro = b.raw_off.astype(np.int64)
+            raws += [bytes(b.raw_blob[ro[i]:ro[i + 1]]) for i in range(b.n_reads)]
+            uoffs += b.rec_uoff.tolist()
+        assert len(set(uoffs)) == len(uoffs) and uoffs == sorted(uoffs)
+        pick = list(range(0, len(uoffs), 37)) + [len(uoffs) - 1, 0, 5, 5]
+        got = rd.fetch_records([uoffs[i] for i in pick])
+        assert got == [raws[i] for i in pick]
+        assert rd.fetch_records([]) == []
+        with pytest.raises(engine.KdfError):
+            rd.fetch_records([uoffs[3] + 1])        # not a record boundary
+
+
+def test_bgzf_write_roundtrip(tmp_path):
+    import gzip
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 0xff00, 0xff00 + 1, 300_001):
+        data = rng.integers(0, 7, size=n, dtype=np.uint8).tobytes()
+        p = str(tmp_path / ("x%d.gz" % n))
+        coff = bamio.bgzf_write(p, data, level=4, threads=3)
+        assert gzip.open(p, "rb").read() == data
+        raw = open(p, "rb").read()
+        assert raw.endswith(obam.BGZF_EOF)
+        assert coff.shape[0] == (n + 0xff00 - 1) // 0xff00 + 1
+        for o in coff.tolist():
+            assert raw[o:o + 4] == b"\x1f\x8b\x08\x04"
+        assert int(coff[-1]) == len(raw) - len(obam.BGZF_EOF)
+
+
+def _one_record_bam(tmp_path, mutate):
+    rec = bytearray(obam.encode_record(0, 10, "read1", 0x41, 60, [(0, 12)], "ACGTACGTACGT"))
+    mutate(rec)
+    good = obam.encode_record(0, 20, "read2", 0x81, 60, [(0, 8)], "ACGTACGT")
+    p = str(tmp_path / "m.bam")
+    obam.write_bam(p, ["chr1"], [1000], [bytes(rec), good])
+    return p
+
+
+@pytest.mark.parametrize("field,value", [("l_seq", 0x7fffff00), ("l_seq", -5), ("n_cigar", 60000),
+                                         ("l_name", 255), ("block_size", 0x7fffffff), ("block_size", 8)])
+def test_corrupt_record_fields_are_reported(tmp_path, field, value):
+    """A record whose l_seq / n_cigar_op / l_read_name do not fit its block_size (or a
+    block_size out of range) is an error — not a segfault in the packer, not garbage."""
+    import struct
+
+    def mutate(rec):
+        if field == "l_seq":
+            struct.pack_into("<i", rec, 4 + 16, value)
+        elif field == "n_cigar":
+            struct.pack_into("<H", rec, 4 + 12, value)
+        elif field == "l_name":
+            rec[4 + 8] = value
+        else:
+            struct.pack_into("<i", rec, 0, value)
+    p = _one_record_bam(tmp_path, mutate)
+    for mode, meta in ((bamio.MODE_FASTA, 0), (bamio.MODE_ALL, 3)):
+        with pytest.raises(engine.KdfError):
+            with bamio.BamReader(p, threads=2) as rd:
+                for b in rd.batches(mode, want_meta=meta):
+                    b.close()
+
+
+def test_corrupt_bgzf_block_is_reported(giab_paths, tmp_path, monkeypatch):
+    """A flipped payload byte fails the block's CRC32 (or the inflate); ISIZE above 64 KiB
+    is rejected before any allocation; KDF_BAM_CRC=0 skips only the CRC comparison."""
+    import struct
+    data = bytearray(open(giab_paths["father"], "rb").read())
+    bsize = struct.unpack_from("<H", data, 16)[0] + 1
+    second = bsize                                     # start of the second block
+    bsize2 = struct.unpack_from("<H", data, second + 16)[0] + 1
+    bad = bytearray(data)
+    struct.pack_into("<I", bad, second + bsize2 - 8, 0xdeadbeef)        # stored CRC32
+    p = str(tmp_path / "crc.bam")
+    open(p, "wb").write(bad)
+    with pytest.raises(engine.KdfError):
+        with bamio.BamReader(p, threads=2) as rd:
+            for b in rd.batches(bamio.MODE_FASTA):
+                b.close()
+    monkeypatch.setenv("KDF_BAM_CRC", "0")
+    with bamio.BamReader(p, threads=2) as rd:
+        n = sum(b.n_reads for b in rd.batches(bamio.MODE_FASTA))
+    assert n > 0
+    monkeypatch.delenv("KDF_BAM_CRC")
+    big = bytearray(data)
+    struct.pack_into("<I", big, second + bsize2 - 4, 1 << 24)           # ISIZE
+    open(p, "wb").write(big)
+    with pytest.raises(engine.KdfError):
+        with bamio.BamReader(p, threads=2) as rd:
+            for b in rd.batches(bamio.MODE_FASTA):
+                b.close()
