@@ -606,12 +606,8 @@ def main():
     # ---- discovery wall time: BAM trio -> candidate BED through the product pipeline ------
     wall = None
     if not args.no_wall and world == 1 and not args.total_genome_mbp:
-        try:
-            from kmer_denovo_filter_b200 import wallbench
-        except ImportError:
-            wallbench = None
-        if wallbench is not None:
-            wall = wallbench.discovery_wall(args, eng, rank)
+        import bench_wall
+        wall = bench_wall.discovery_wall(args, eng, rank)
 
     if rank == 0:
         line = {

@@ -41,6 +41,10 @@ logger = logging.getLogger(__name__)
 
 REF_PLANE = 1  # plane 1 of the child table holds the "in reference" flag
 
+# wall-clock seconds of the stages of the last run_discovery_pipeline call (bench.py's
+# discovery_wall leg reads it; the reference logs per-module times, discovery/pipeline.py:2185-2194)
+LAST_TIMINGS = {}
+
 
 class ChildScanCache:
     """The child BAM decoded ONCE.  The reference reads it three times (``samtools fasta``
@@ -434,7 +438,8 @@ def scan_child_reads(eng, child_bam, table, kmer_size, min_distinct_kmers_per_re
     Yields ``(batch, ndistinct u32[], nhits u32[], hit_read_idx, hit_offset)``
     per batch, hits sorted by (read, offset)."""
     cache = child_cache(child_bam)
-    if cache is not None:
+    pf = None
+    if cache is not None and cache.complete:
         source, owned = cache.batches, False          # decoded once, in Module 1
     else:
         pf = kw.take_prefetch(child_bam, bamio.MODE_SCAN, threads, True, batch_bases)
@@ -467,7 +472,7 @@ def scan_child_reads(eng, child_bam, table, kmer_size, min_distinct_kmers_per_re
             if owned:
                 batch.close()
     finally:
-        if owned:
+        if pf is not None:
             pf.close()
 
 
@@ -529,12 +534,17 @@ def _anchor_and_cluster(child_bam, ref_fasta, proband_unique_kmers, kmer_size,
     unmapped_informative = 0
     total_scanned = 0
     per_read = []  # (record index, n_distinct, n_hits) of reads with >= 1 hit
+    cache = child_cache(child_bam)
+    if cache is not None:
+        cache.hit_reads = []
     for batch, nd, nh, ridx, off, _slot in scan_child_reads(
             eng, child_bam, table, kmer_size, min_distinct_kmers_per_read, threads):
         total_scanned += batch.n_reads
         hit_reads = np.flatnonzero(nh > 0)
         for r in hit_reads.tolist():
             per_read.append((int(batch.rec_index[r]), int(nd[r]), int(nh[r])))
+            if cache is not None:
+                cache.note_hit(batch, r)     # the informative-reads writer fetches these by offset
         informative = np.flatnonzero(nd >= max(1, min_distinct_kmers_per_read))
         lo_i = np.searchsorted(ridx, informative, side="left")
         hi_i = np.searchsorted(ridx, informative, side="right")
@@ -572,6 +582,9 @@ def _anchor_and_cluster(child_bam, ref_fasta, proband_unique_kmers, kmer_size,
         _accumulate_coverage(eng, batch, cov_reads, cov_hits, off, kmer_size, kmer_coverage,
                              read_coverage)
         batch.close()
+    if cache is not None:
+        cache.scanned = True
+        cache.release_batches()      # only the hit list and the reader are needed from here on
     if owns:
         table.close()
     total_informative = len(read_hits) + unmapped_informative
@@ -842,6 +855,23 @@ def _write_informative_reads_discovery(child_bam, ref_fasta, proband_unique_kmer
         owns = True
     records = []
     written = set()
+    cache = child_cache(child_bam)
+    if cache is not None and getattr(cache, "scanned", False):
+        # the anchoring scan has already seen every read with a hit: fetch those records
+        # back by their offsets (a few BGZF blocks) instead of decoding the file again
+        rd = cache.reader
+        uoffs = []
+        for uoff, qname, supp in cache.hit_reads:      # file order
+            if (qname, supp) in written:
+                continue
+            written.add((qname, supp))
+            uoffs.append(uoff)
+        records = [bamio.append_int_tag(raw, "dk", 1) for raw in rd.fetch_records(uoffs)]
+        if owns:
+            table.close()
+        n = bamio.write_sorted_bam(output_bam, rd.header_text, rd.references, rd.lengths, records)
+        logger.info("Informative reads BAM written: %s (%d reads)", output_bam, n)
+        return n
     with bamio.BamReader(child_bam, threads=threads) as rd:
         header_text, names, lens = rd.header_text, rd.references, rd.lengths
         for batch in rd.batches(bamio.MODE_SCAN, max_bases=kw.BATCH_BASES, want_meta=3):
@@ -925,18 +955,54 @@ def run_discovery_pipeline(args, engine=None):
         _write_empty_discovery_outputs(bed_path, metrics_path, summary_path, m, bedpe_path)
         return m
 
+    kw.reset_times()
+    timings = LAST_TIMINGS
+    timings.clear()
+    t_stage = time.perf_counter()
+
+    def lap(name):
+        nonlocal t_stage
+        now = time.perf_counter()
+        timings[name] = timings.get(name, 0.0) + (now - t_stage)
+        t_stage = now
+
+    # the parents are decoded in the background while the child is read and counted (bounded
+    # look-ahead: two batches each)
+    if os.environ.get("KDF_PREFETCH_PARENTS", "1") != "0":
+        kw.start_prefetch(args.mother, bamio.MODE_FASTA, threads)
+        kw.start_prefetch(args.father, bamio.MODE_FASTA, threads)
+    try:
+        return _run_discovery(args, eng, k, threads, min_dk, min_bedgraph_reads, bed_path, info_bam_path,
+                              metrics_path, summary_path, bedpe_path, bedgraph_path, read_cov_bed_path,
+                              finish_empty, lap, start)
+    finally:
+        kw.drop_prefetch()
+        drop_child_caches()
+        timings["decode_threads_s"] = kw.TIMES["decode_s"]
+        timings["decode_wait_s"] = kw.TIMES["decode_wait_s"]
+        timings["total_s"] = time.monotonic() - start
+
+
+def _run_discovery(args, eng, k, threads, min_dk, min_bedgraph_reads, bed_path, info_bam_path,
+                   metrics_path, summary_path, bedpe_path, bedgraph_path, read_cov_bed_path,
+                   finish_empty, lap, start):
+    out_prefix = args.out_prefix
     ref_index = _ensure_ref_jf(args.ref_fasta, k, threads, getattr(args, "ref_jf", None), eng)
+    lap("reference_index_s")
     cand, n_candidates = _extract_child_kmers_discovery(
         args.child, args.ref_fasta, k, args.min_child_count, threads, None,
         jf_hash_size=getattr(args, "jf_hash_size", None), engine=eng)
+    lap("child_decode_and_count_s")
     if n_candidates == 0:
         cand.close()
         return finish_empty(0, 0)
     non_ref, n_non_ref = _subtract_reference_kmers(ref_index, cand, None)
+    lap("reference_subtraction_s")
     if n_non_ref == 0:
         return finish_empty(n_candidates, 0)
     n_pu, pu = _filter_parents_discovery(args.mother, args.father, args.ref_fasta, non_ref, k,
                                          threads, None, args.parent_max_count, engine=eng)
+    lap("parents_decode_and_filter_s")
     if n_pu == 0:
         return finish_empty(n_candidates, n_non_ref)
     pu_table = _build_proband_jf_index(pu, k, None, n_pu, engine=eng)
@@ -945,10 +1011,12 @@ def run_discovery_pipeline(args, engine=None):
         args.child, args.ref_fasta, None, k, merge_distance=args.cluster_distance,
         threads=threads, min_distinct_kmers_per_read=min_dk, proband_jf=pu_table,
         n_proband_unique=n_pu, engine=eng)
+    lap("anchor_scan_and_cluster_s")
     logger.info("[Module 4] Writing informative reads BAM: %s", info_bam_path)
     _write_informative_reads_discovery(args.child, getattr(args, "ref_fasta", None), pu_table, k,
                                        info_bam_path, engine=eng, threads=threads)
     pu_table.close()
+    lap("informative_bam_s")
 
     min_reads, min_kmers = args.min_supporting_reads, args.min_distinct_kmers
     if min_reads > 1 or min_kmers > 1:
@@ -1010,5 +1078,6 @@ def run_discovery_pipeline(args, engine=None):
     _write_discovery_summary(summary_path, regions, region_reads, region_kmers, metrics,
                              candidate_comparison=comparison, region_annotations=annotations,
                              dnm_evaluation=dnm)
+    lap("annotate_and_write_s")
     logger.info("Discovery pipeline finished in %.1fs", time.monotonic() - start)
     return metrics
