@@ -626,10 +626,11 @@ class CudaEngine:
     @staticmethod
     def filter_words(n_keys, max_bytes):
         """32-bit words of the filter for ``n_keys`` keys within ``max_bytes``: 32 bits per
-        key (false positives ~0.4 %) when that fits, else 16 (~1.5 %), else 0 (no filter)."""
-        # KDF_FILTER_MIN_BITS=8 adds an 8-bits-per-key tier (~6 % false positives): untried
-        # at the scale that needs it (31 M keys on 8 GPUs), so not on by default
-        tiers = (1, 2, 4) if os.environ.get("KDF_FILTER_MIN_BITS", "16") == "8" else (1, 2)
+        key (false positives ~0.4 %) when that fits, else 16 (~1.5 %), else 8 (~5 %: the
+        replicated filter set of an 8-GPU run, 31 M keys — one probe in twenty then goes to
+        the table, still far cheaper than binning the whole parent), else 0 (no filter).
+        ``KDF_FILTER_MIN_BITS=16`` drops the last tier."""
+        tiers = (1, 2, 4) if os.environ.get("KDF_FILTER_MIN_BITS", "8") == "8" else (1, 2)
         for per_word in tiers:
             n_words = 1024
             while n_words * per_word < n_keys:
