@@ -502,6 +502,20 @@ int kdf_bam_next_batch(kdf_bam* b, int mode, uint64_t max_bases, int want_meta,
                        kdf_bam_batch* out);
 void kdf_bam_batch_free(kdf_bam_batch* batch);
 const char* kdf_host_last_error(void);
+/* Ranges of a BAM, for region fetches through the .bai (the reference's
+ * bam.fetch(chrom, pos, pos + 1), vcf/pipeline.py:619-726) and for sharding a file over
+ * the ranks of a multi-GPU run (rank r reads a contiguous BGZF range of
+ * every BAM).  kdf_bam_seek repositions the reader at a BGZF virtual offset (block file
+ * offset << 16 | offset in the block) that starts a record — an entry of the .bai linear
+ * index — and drops its read-ahead; the FASTA stream's QNAME-run state starts afresh.
+ * kdf_bam_set_end makes the reader report end of file at the first record that starts
+ * at or after the given virtual offset (~0: no limit).
+ * kdf_bam_set_begin (right after a seek to an EARLIER record): records that start before
+ * this virtual offset only update the QNAME-run state and are not delivered, so a run
+ * of same-QNAME records that straddles a rank boundary collapses as in a sequential read. */
+int kdf_bam_seek(kdf_bam* b, uint64_t voffset);
+int kdf_bam_set_begin(kdf_bam* b, uint64_t voffset);
+int kdf_bam_set_end(kdf_bam* b, uint64_t voffset);
 /* The raw BAM records (bytes after block_size) at the given uncompressed offsets
  * (kdf_bam_batch.rec_uoff of records this reader has already decoded), by inflating
  * only the blocks that hold them: what the informative-reads BAM writer needs

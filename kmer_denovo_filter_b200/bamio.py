@@ -284,6 +284,23 @@ class BamReader:
             if b.at_eof:
                 break
 
+    def seek(self, voffset, begin=None, end=None):
+        """Continue the decode at BGZF virtual offset ``voffset`` (the start of a record:
+        an entry of the .bai linear index).  ``begin``: records before this virtual offset
+        are parsed for the QNAME-run state only; ``end``: end of file is reported at the
+        first record at or after this virtual offset."""
+        for fn, v in ((self.lib.kdf_bam_set_end, end if end is not None else 0xFFFFFFFFFFFFFFFF),
+                      (self.lib.kdf_bam_seek, voffset)):
+            if fn(self.handle, int(v)) != 0:
+                raise _engine.KdfError("cannot seek in %s: %s" % (
+                    self.path, self.lib.kdf_host_last_error().decode()))
+        if begin is not None and self.lib.kdf_bam_set_begin(self.handle, int(begin)) != 0:
+            raise _engine.KdfError(self.lib.kdf_host_last_error().decode())
+
+    def set_end(self, voffset):
+        if self.lib.kdf_bam_set_end(self.handle, int(voffset) if voffset is not None else 0xFFFFFFFFFFFFFFFF) != 0:
+            raise _engine.KdfError(self.lib.kdf_host_last_error().decode())
+
     def fetch_records(self, uoffs):
         """Raw BAM records (bytes after block_size) at uncompressed offsets ``uoffs``
         (``HostBatch.rec_uoff`` of records this reader has decoded): only the BGZF blocks
@@ -325,6 +342,93 @@ class BamReader:
             self.close()
         except Exception:
             pass
+
+
+def read_bai(path):
+    """Parse a ``.bai`` → list (one per reference) of dicts ``{"bins": {bin: [(beg, end)
+    virtual offsets]}, "linear": uint64 array of 16 kbp-window virtual offsets}``."""
+    data = open(path, "rb").read()
+    if data[:4] != b"BAI\x01":
+        raise _engine.KdfError("%s is not a BAI index" % path)
+    n_ref = struct.unpack_from("<i", data, 4)[0]
+    off = 8
+    out = []
+    for _ in range(n_ref):
+        n_bin = struct.unpack_from("<i", data, off)[0]
+        off += 4
+        bins = {}
+        for _b in range(n_bin):
+            b, n_chunk = struct.unpack_from("<Ii", data, off)
+            off += 8
+            ch = np.frombuffer(data, dtype="<u8", count=2 * n_chunk, offset=off).reshape(-1, 2)
+            off += 16 * n_chunk
+            bins[b] = ch
+        n_intv = struct.unpack_from("<i", data, off)[0]
+        off += 4
+        lin = np.frombuffer(data, dtype="<u8", count=n_intv, offset=off).copy()
+        off += 8 * n_intv
+        out.append({"bins": bins, "linear": lin})
+    return out
+
+
+def find_bai(bam_path):
+    for cand in (bam_path + ".bai", os.path.splitext(bam_path)[0] + ".bai"):
+        if os.path.isfile(cand):
+            return cand
+    return None
+
+
+def shard_offsets(bam_path, world):
+    """Virtual offsets that cut a coordinate-sorted, indexed BAM into ``world`` contiguous
+    ranges of about equal compressed size, each starting at a record (an entry of the .bai
+    linear index), plus for every cut a slightly earlier entry to warm the QNAME-run state
+    up from.  → list of ``(warm, begin, end)`` per rank (None = file start / end)."""
+    bai = find_bai(bam_path)
+    if bai is None:
+        raise _engine.KdfError("sharding %s over %d ranks needs its .bai index" % (bam_path, world))
+    entries = np.unique(np.concatenate([r["linear"] for r in read_bai(bai)] + [np.zeros(0, np.uint64)]))
+    entries = entries[entries > 0]
+    size = os.path.getsize(bam_path)
+    cuts, warms = [], []
+    for r in range(1, world):
+        target = np.uint64((size * r // world) << 16)
+        j = int(np.searchsorted(entries, target))
+        if j >= entries.shape[0] or (cuts and int(entries[j]) <= cuts[-1]):
+            cuts.append(None)
+            warms.append(None)
+            continue
+        cuts.append(int(entries[j]))
+        warms.append(int(entries[j - 1]) if j > 0 else None)
+    out = []
+    for r in range(world):
+        begin = cuts[r - 1] if r > 0 else None
+        warm = warms[r - 1] if r > 0 else None
+        end = cuts[r] if r < world - 1 else None
+        if r > 0 and begin is None:      # an earlier cut could not be placed: this rank gets nothing
+            out.append(("empty", None, None))
+            continue
+        if end is None and r < world - 1:
+            nxt = [c for c in cuts[r:] if c is not None]
+            end = nxt[0] if nxt else None
+        out.append((warm, begin, end))
+    return out
+
+
+def open_shard(bam_path, rank, world, threads=None):
+    """A reader over rank ``rank``'s range of the file (``shard_offsets``)."""
+    rd = BamReader(bam_path, threads=threads)
+    if world <= 1:
+        return rd
+    warm, begin, end = shard_offsets(bam_path, world)[rank]
+    if warm == "empty":
+        rd.seek(0, end=0)      # nothing
+        rd.empty_shard = True
+        return rd
+    if begin is None:
+        rd.set_end(end)
+    else:
+        rd.seek(warm if warm is not None else begin, begin=begin, end=end)
+    return rd
 
 
 def counting_view(batch):

@@ -93,6 +93,13 @@ struct Bam {
   uint64_t u_total = 0, c_total = 0;
   std::vector<std::pair<uint64_t, uint64_t>> blk_index;
   uint64_t first_rec_uoff = 0;   // uncompressed offset of the first record (= header size)
+  uint64_t u_limit = ~0ull;      // deliver no record at or past this uncompressed offset (kdf_bam_set_end)
+  uint64_t u_begin = 0;          // records before this offset only update the QNAME-run state (kdf_bam_set_begin)
+  uint64_t begin_coff = ~0ull;
+  uint32_t begin_in = 0;
+  size_t skip_bytes = 0;         // kdf_bam_seek: bytes of the first block that precede the target record
+  uint64_t end_coff = ~0ull;     // kdf_bam_set_end: virtual offset (block, offset in block) to stop at
+  uint32_t end_in = 0;
   int last_set_part = -1;        // read-part bit the last parsed record set in seen_parts (-1: none)
   std::string path;
   // collapse state of the FASTA stream (persists across batches)
@@ -245,6 +252,8 @@ bool read_comp(Bam* b, uint64_t want_bytes, CompBuf& cb, std::string& err) {
     }
     cb.blocks.push_back({(uint64_t)pos, (uint32_t)bsize, isize, cb.total_u});
     if (isize) b->blk_index.emplace_back(b->u_total, b->c_total);
+    if (b->c_total == b->end_coff) b->u_limit = b->u_total + b->end_in;
+    if (b->c_total == b->begin_coff) b->u_begin = b->u_total + b->begin_in;
     b->u_total += isize;
     b->c_total += (uint64_t)bsize;
     cb.total_u += isize;
@@ -635,12 +644,16 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
   size_t off = b->cur.begin;
   uint64_t cur_ustart = b->cur.ustart;
   size_t cur_own = b->cur.own;
-  bool done = false;
+  bool done = false, hit_limit = false;
   std::string perr, rerr;
   // stage 3: parse all complete records currently in the chunk
   auto parse = [&]() {
     while (true) {
       if (buf_size - off < 4) break;
+      if (cur_ustart + (uint64_t)off - (uint64_t)cur_own >= b->u_limit) {   // end of this reader's range
+        hit_limit = true;
+        break;
+      }
       int32_t bs = rd_i32(buf + off);
       if (bs < 32 || bs > (1 << 28)) {
         perr = "corrupt BAM record (block_size out of range)";
@@ -690,6 +703,8 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
       } else if (mode == KDF_BAM_SCAN) {
         if (flag & 0x500) keep = false;
       }
+      // warm-up records of a range (kdf_bam_set_begin): parsed for the QNAME-run state only
+      if (cur_ustart + (uint64_t)off - (uint64_t)cur_own < b->u_begin) keep = false;
       if (keep) {
         if (max_bases && !kept.empty() && n_bases + l_seq + 1 > max_bases) {
           done = true;
@@ -747,6 +762,7 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
       b->ahead2.valid = false;
     }
     if (done) break;   // batch full: the rest of this chunk and the look-ahead wait in the reader
+    if (hit_limit) break;
     // this chunk is exhausted but for an incomplete record at its end
     const size_t tail = buf_size - off;
     if (!b->next.valid) {
@@ -781,9 +797,15 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
     off = b->cur.begin;
     cur_ustart = b->cur.ustart;
     cur_own = b->cur.own;
+    if (b->skip_bytes) {   // first chunk after kdf_bam_seek: the target record starts inside its first block
+      if (buf_size - off < b->skip_bytes) return bail("kdf_bam_seek: offset beyond the end of its block");
+      off += b->skip_bytes;
+      b->skip_bytes = 0;
+    }
   }
   b->cur.begin = off;
-  b->eof = b->file_eof && !b->ahead.valid && !b->next.valid;
+  b->eof = (b->file_eof && !b->ahead.valid && !b->next.valid) || hit_limit;
+  if (hit_limit) b->cur.begin = b->cur.size;   // nothing more to deliver from this range
   // A batch limit postponed a record whose parse had already updated the collapse state:
   // if it set a read-part bit, clear it, so that the record is kept when the next batch
   // parses it again (its QNAME is then still the current one).
@@ -1007,6 +1029,94 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
     out->n_invalid = im->invalid.size();
     out->has_invalid = 1;
   }
+  return KDF_OK;
+}
+
+// ---- ranges ------------------------------------------------------------------
+// Reposition the reader at a BGZF virtual offset (block file offset << 16 | offset inside
+// the block) that is the start of a record — an entry of the .bai linear index, or
+// kdf_bam_batch.rec_voff-style arithmetic of the caller — and forget the read-ahead.
+// The QNAME-run state of the FASTA stream starts afresh.
+int kdf_bam_seek(kdf_bam* h, uint64_t voffset) {
+  Bam* b = reinterpret_cast<Bam*>(h);
+  if (!b) {
+    g_host_err = "kdf_bam_seek: NULL reader";
+    return KDF_ERR_ARG;
+  }
+  const uint64_t coff = voffset >> 16;
+  if (fseeko(b->fh, (off_t)coff, SEEK_SET) != 0) {
+    g_host_err = "kdf_bam_seek: cannot seek";
+    return KDF_ERR_ARG;
+  }
+  if (b->cur.valid) b->put_buf(b->cur.data, b->cur.cap);
+  if (b->next.valid) b->put_buf(b->next.data, b->next.cap);
+  b->cur = Chunk();
+  b->next = Chunk();
+  b->ahead.valid = b->ahead2.valid = false;
+  b->pending.clear();
+  b->carry.clear();
+  b->file_eof = false;
+  b->eof = false;
+  b->c_total = coff;
+  b->skip_bytes = (size_t)(voffset & 0xffff);
+  b->cur_qname.clear();
+  b->seen_parts = 0;
+  b->last_set_part = -1;
+  b->u_limit = ~0ull;
+  b->u_begin = 0;
+  b->begin_coff = ~0ull;
+  if (b->end_coff == coff) b->u_limit = b->u_total + b->end_in;   // (empty range)
+  // an empty current chunk whose "own" data starts where the stream continues
+  size_t cap = 0;
+  uint8_t* p = b->get_buf(1, &cap);
+  if (!p) {
+    g_host_err = "out of memory";
+    return KDF_ERR_ARG;
+  }
+  b->cur.data = p;
+  b->cur.begin = b->cur.size = b->cur.own = 0;
+  b->cur.ustart = b->u_total;
+  b->cur.cap = cap;
+  b->cur.valid = true;
+  return KDF_OK;
+}
+
+// Records that start before this virtual offset are parsed (they update the QNAME-run
+// state of the FASTA stream) but not delivered: a rank seeks a little before its range
+// and sets its true start here, so that a run of same-QNAME records that straddles the
+// boundary is collapsed exactly as in a sequential read.  Call right after kdf_bam_seek.
+int kdf_bam_set_begin(kdf_bam* h, uint64_t voffset) {
+  Bam* b = reinterpret_cast<Bam*>(h);
+  if (!b) {
+    g_host_err = "kdf_bam_set_begin: NULL reader";
+    return KDF_ERR_ARG;
+  }
+  b->begin_coff = voffset >> 16;
+  b->begin_in = (uint32_t)(voffset & 0xffff);
+  b->u_begin = ~0ull;     // until the block is reached, nothing is delivered
+  if (b->begin_coff == b->c_total) b->u_begin = b->u_total + b->begin_in;
+  return KDF_OK;
+}
+
+// Deliver no record that starts at or after this virtual offset (the start of the next
+// rank's range); ~0 removes the limit.  Call before the decode reaches that block.
+int kdf_bam_set_end(kdf_bam* h, uint64_t voffset) {
+  Bam* b = reinterpret_cast<Bam*>(h);
+  if (!b) {
+    g_host_err = "kdf_bam_set_end: NULL reader";
+    return KDF_ERR_ARG;
+  }
+  if (voffset == ~0ull) {
+    b->end_coff = ~0ull;
+    b->end_in = 0;
+    b->u_limit = ~0ull;
+    return KDF_OK;
+  }
+  b->end_coff = voffset >> 16;
+  b->end_in = (uint32_t)(voffset & 0xffff);
+  b->u_limit = ~0ull;
+  for (const auto& e : b->blk_index)      // the block may have been walked already
+    if (e.second == b->end_coff) b->u_limit = e.first + b->end_in;
   return KDF_OK;
 }
 

@@ -110,6 +110,9 @@ _SIGNATURES = {
     "kdf_bam_batch_free": (None, [_vp]),
     "kdf_host_last_error": (ctypes.c_char_p, []),
     "kdf_bam_fetch_records": (_i, [_vp, _vp, _u64, _vp, _u64, _vp, _vp]),
+    "kdf_bam_seek": (_i, [_vp, _u64]),
+    "kdf_bam_set_end": (_i, [_vp, _u64]),
+    "kdf_bam_set_begin": (_i, [_vp, _u64]),
     "kdf_bgzf_write": (_i, [ctypes.c_char_p, _vp, _u64, _i, _i, _vp, _u64, _vp]),
 }
 
