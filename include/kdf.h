@@ -514,6 +514,7 @@ const char* kdf_host_last_error(void);
  * this virtual offset only update the QNAME-run state and are not delivered, so a run
  * of same-QNAME records that straddles a rank boundary collapses as in a sequential read. */
 int kdf_bam_seek(kdf_bam* b, uint64_t voffset);
+int kdf_bam_set_chunk_bytes(kdf_bam* b, uint64_t n);   /* read-ahead per pipeline chunk (default 64 MB) */
 int kdf_bam_set_begin(kdf_bam* b, uint64_t voffset);
 int kdf_bam_set_end(kdf_bam* b, uint64_t voffset);
 /* The raw BAM records (bytes after block_size) at the given uncompressed offsets

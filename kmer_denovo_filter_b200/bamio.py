@@ -297,6 +297,43 @@ class BamReader:
         if begin is not None and self.lib.kdf_bam_set_begin(self.handle, int(begin)) != 0:
             raise _engine.KdfError(self.lib.kdf_host_last_error().decode())
 
+    def fetch(self, tid, beg, end, want_meta=2, mode=MODE_ALL):
+        """Batches holding every record of reference ``tid`` that overlaps ``[beg, end)``
+        (and possibly a few more around it) — ``pysam.AlignmentFile.fetch`` through the
+        .bai linear index: the decode starts at the first record of the 16 kbp window that
+        holds ``beg`` (minus the longest plausible alignment) and stops at the first batch
+        that lies wholly past ``end``.  Needs ``<bam>.bai``."""
+        if getattr(self, "_bai", None) is None:
+            bai = find_bai(self.path)
+            if bai is None:
+                raise _engine.KdfError("region fetch needs an index: %s.bai not found" % self.path)
+            self._bai = read_bai(bai)
+            self.lib.kdf_bam_set_chunk_bytes(self.handle, 256 << 10)
+        if tid < 0 or tid >= len(self._bai):
+            return
+        lin = self._bai[tid]["linear"]
+        if lin.shape[0] == 0:
+            return
+        # a record overlapping `beg` starts at most one read length (or a long deletion) before
+        # it: go back one window further than the one holding beg
+        w = max(min(int(beg) >> 14, lin.shape[0] - 1) - 1, 0)
+        voff = int(lin[w])
+        while voff == 0 and w + 1 < lin.shape[0] and (w + 1) <= (int(beg) >> 14):
+            w += 1
+            voff = int(lin[w])
+        if voff == 0:
+            return
+        self.seek(voff)
+        while True:
+            b = self.next_batch(mode, 1 << 18, want_meta)
+            if b.n_reads == 0:
+                b.close()
+                return
+            past = (b.ref_id != tid) | (b.pos.astype(np.int64) >= int(end))
+            yield b
+            if bool(past.all()) or bool(past[-1]) or b.at_eof:
+                return
+
     def set_end(self, voffset):
         if self.lib.kdf_bam_set_end(self.handle, int(voffset) if voffset is not None else 0xFFFFFFFFFFFFFFFF) != 0:
             raise _engine.KdfError(self.lib.kdf_host_last_error().decode())

@@ -1081,6 +1081,18 @@ int kdf_bam_seek(kdf_bam* h, uint64_t voffset) {
   return KDF_OK;
 }
 
+// Bytes of records the decode pipeline reads ahead per chunk (default 64 MB: right for a
+// sequential pass; a region fetch wants a few hundred KB).
+int kdf_bam_set_chunk_bytes(kdf_bam* h, uint64_t n) {
+  Bam* b = reinterpret_cast<Bam*>(h);
+  if (!b || n < 4096) {
+    g_host_err = "kdf_bam_set_chunk_bytes: bad argument";
+    return KDF_ERR_ARG;
+  }
+  b->chunk_bytes = n;
+  return KDF_OK;
+}
+
 // Records that start before this virtual offset are parsed (they update the QNAME-run
 // state of the FASTA stream) but not delivered: a rank seeks a little before its range
 // and sets its true start here, so that a run of same-QNAME records that straddles the

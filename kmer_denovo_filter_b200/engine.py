@@ -113,6 +113,7 @@ _SIGNATURES = {
     "kdf_bam_seek": (_i, [_vp, _u64]),
     "kdf_bam_set_end": (_i, [_vp, _u64]),
     "kdf_bam_set_begin": (_i, [_vp, _u64]),
+    "kdf_bam_set_chunk_bytes": (_i, [_vp, _u64]),
     "kdf_bgzf_write": (_i, [ctypes.c_char_p, _vp, _u64, _i, _i, _vp, _u64, _vp]),
 }
 

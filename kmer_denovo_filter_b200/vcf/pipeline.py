@@ -153,7 +153,9 @@ def _collect_child_kmers(child_bam, ref_fasta, variants, kmer_size, min_baseq, m
                          debug_kmers, kmer_fasta, flush_threshold=500_000, threads=4):
     """Child k-mers spanning each variant → ``(total_child_kmers, variant_read_kmers)``
     and a k-mer FASTA at ``kmer_fasta`` (reference ``:619-726``).  ``bam.fetch(chrom,
-    pos, pos + 1)`` is restated as one pass over the BAM in file order."""
+    pos, pos + 1)`` goes through the .bai when the BAM has one (only the blocks over the
+    sites are inflated); without an index it is one pass over the file with a sorted-interval
+    lookup per batch."""
     by_chrom = collections.defaultdict(list)
     variant_read_kmers = {}
     for var in variants:
@@ -175,41 +177,77 @@ def _collect_child_kmers(child_bam, ref_fasta, variants, kmer_size, min_baseq, m
             total_written += 1
         batch_set.clear()
 
+    def _take(batch, tid, vlist, vpos):
+        """Reads of ``batch`` on reference ``tid`` against the (position-sorted) variants
+        ``vlist``: one vectorised interval lookup per batch instead of a scan per variant;
+        (variant, read) pairs are visited variant by variant in file order, as
+        ``bam.fetch`` per variant would deliver them."""
+        nonlocal total_reads_scanned
+        flag = batch.flag
+        ok = ((flag & np.uint16(0x4 | 0x100 | 0x800 | 0x400)) == 0) & (batch.mapq >= min_mapq) & \
+            (batch.ref_id == tid)
+        sel = np.flatnonzero(ok)
+        if sel.size == 0:
+            return
+        start = batch.pos.astype(np.int64)[sel]
+        end = start + _reference_lengths(batch)[sel]
+        lo = np.searchsorted(vpos, start, side="left")
+        hi = np.searchsorted(vpos, end, side="left")
+        cover = np.flatnonzero(hi > lo)
+        if cover.size == 0:
+            return
+        pairs = [(v, int(sel[j])) for j in cover.tolist() for v in range(int(lo[j]), int(hi[j]))]
+        pairs.sort()
+        for v, i in pairs:
+            var = vlist[v]
+            pos = var["pos"]
+            key = _var_key(var)
+            read = batch.record(i)
+            total_reads_scanned += 1
+            seq = read.query_sequence
+            quals = read.query_qualities
+            kmers = extract_variant_spanning_kmers(
+                read, pos, kmer_size, min_baseq, ref=var["ref"], alt=var["alt"],
+                seq=seq, quals=quals)
+            if kmers:
+                supports = read_supports_alt(read, pos, var["ref"], var["alt"],
+                                             min_baseq=min_baseq, seq=seq, quals=quals)
+                variant_read_kmers[key].append((read.query_name, kmers, supports))
+                batch_set.update(kmers)
+                if len(batch_set) >= flush_threshold:
+                    _flush()
+
+    for vlist in by_chrom.values():
+        vlist.sort(key=lambda v: v["pos"])      # stable: equal positions keep their VCF order
     with bamio.BamReader(child_bam, threads=threads) as rd:
         tid_of = {name: i for i, name in enumerate(rd.references)}
-        for batch in rd.batches(bamio.MODE_ALL, max_bases=1 << 28, want_meta=2):
-            flag = batch.flag
-            ok = ((flag & np.uint16(0x4 | 0x100 | 0x800 | 0x400)) == 0) & (batch.mapq >= min_mapq)
-            start = batch.pos.astype(np.int64)
-            end = start + _reference_lengths(batch)
+        if bamio.find_bai(child_bam) is not None and os.environ.get("KDF_VCF_FETCH", "1") != "0":
+            # indexed BAM: seek to the blocks over each cluster of sites (the reference's
+            # bam.fetch(chrom, pos, pos + 1)) instead of decoding the whole file
             for chrom, vlist in by_chrom.items():
                 tid = tid_of.get(chrom)
                 if tid is None:
                     continue
-                sel = np.flatnonzero(ok & (batch.ref_id == tid))
-                if sel.size == 0:
-                    continue
-                s_sel, e_sel = start[sel], end[sel]
-                for var in vlist:
-                    pos = var["pos"]
-                    hit = sel[(s_sel <= pos) & (pos < e_sel)]
-                    key = _var_key(var)
-                    for i in hit.tolist():
-                        read = batch.record(i)
-                        total_reads_scanned += 1
-                        seq = read.query_sequence
-                        quals = read.query_qualities
-                        kmers = extract_variant_spanning_kmers(
-                            read, pos, kmer_size, min_baseq, ref=var["ref"], alt=var["alt"],
-                            seq=seq, quals=quals)
-                        if kmers:
-                            supports = read_supports_alt(read, pos, var["ref"], var["alt"],
-                                                         min_baseq=min_baseq, seq=seq, quals=quals)
-                            variant_read_kmers[key].append((read.query_name, kmers, supports))
-                            batch_set.update(kmers)
-                            if len(batch_set) >= flush_threshold:
-                                _flush()
-            batch.close()
+                i = 0
+                while i < len(vlist):
+                    j = i
+                    while j + 1 < len(vlist) and vlist[j + 1]["pos"] - vlist[j]["pos"] < 16384:
+                        j += 1
+                    group = vlist[i:j + 1]
+                    gpos = np.asarray([v["pos"] for v in group], dtype=np.int64)
+                    for batch in rd.fetch(tid, int(gpos[0]), int(gpos[-1]) + 1, want_meta=2):
+                        _take(batch, tid, group, gpos)
+                        batch.close()
+                    i = j + 1
+        else:
+            vpos_of = {chrom: np.asarray([v["pos"] for v in vlist], dtype=np.int64)
+                       for chrom, vlist in by_chrom.items()}
+            for batch in rd.batches(bamio.MODE_ALL, max_bases=1 << 28, want_meta=2):
+                for tid in np.unique(batch.ref_id).tolist():
+                    chrom = rd.references[tid] if 0 <= tid < len(rd.references) else None
+                    if chrom in by_chrom:
+                        _take(batch, tid, by_chrom[chrom], vpos_of[chrom])
+                batch.close()
     if batch_set:
         _flush()
     fasta_fh.close()

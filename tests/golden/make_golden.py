@@ -31,6 +31,9 @@ COPY = {
         "tests/data/giab/HG002_child.bam",
         "tests/data/giab/HG003_father.bam",
         "tests/data/giab/HG004_mother.bam",
+        "tests/data/giab/HG002_child.bam.bai",
+        "tests/data/giab/HG003_father.bam.bai",
+        "tests/data/giab/HG004_mother.bam.bai",
         "tests/data/giab/mini_ref.fa",
         "tests/data/giab/mini_ref.fa.k31.jf",
         "tests/data/giab/candidates.vcf.gz",

@@ -338,3 +338,52 @@ def test_corrupt_bgzf_block_is_reported(giab_paths, tmp_path, monkeypatch):
         with bamio.BamReader(p, threads=2) as rd:
             for b in rd.batches(bamio.MODE_FASTA):
                 b.close()
+
+
+def _records(b):
+    return [(b.record(i).query_name, int(b.flag[i]), int(b.ref_id[i]), int(b.pos[i])) for i in range(b.n_reads)]
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+@pytest.mark.parametrize("mode", [bamio.MODE_FASTA, bamio.MODE_SCAN])
+def test_shards_partition_the_file_exactly(giab_paths, world, mode):
+    """Rank ranges cut at .bai linear-index entries: the ranks' streams, concatenated, are
+    the sequential stream — record for record, including the QNAME-run collapse of the
+    FASTA stream across a boundary (each rank warms the state up from an earlier entry)."""
+    with bamio.BamReader(giab_paths["child"], threads=2) as rd:
+        whole = _records(rd.next_batch(mode, want_meta=True))
+    got = []
+    sizes = []
+    for r in range(world):
+        rd = bamio.open_shard(giab_paths["child"], r, world, threads=2)
+        n0 = len(got)
+        for b in rd.batches(mode, max_bases=300_000, want_meta=True):
+            got += _records(b)
+            b.close()
+        rd.close()
+        sizes.append(len(got) - n0)
+    assert got == whole
+    assert sum(1 for x in sizes if x > 0) >= 2        # the file really was split
+
+
+def test_region_fetch_equals_a_linear_filter(giab_paths, giab_records):
+    """BamReader.fetch through the .bai returns every record overlapping the region (the
+    reference's bam.fetch(chrom, pos, pos + 1))."""
+    recs = giab_records["child"]
+    names = giab_records["child_refs"][0]
+    rng = np.random.default_rng(3)
+    mapped = [r for r in recs if r.ref_id >= 0 and r.pos >= 0 and r.reference_end is not None]
+    with bamio.BamReader(giab_paths["child"], threads=2) as rd:
+        for r in [mapped[int(i)] for i in rng.integers(0, len(mapped), 12)]:
+            tid, pos = r.ref_id, r.pos + 3
+            want = sorted((x.qname, x.flag, x.pos) for x in recs
+                          if x.ref_id == tid and x.reference_end is not None and x.pos <= pos < x.reference_end)
+            got = []
+            for b in rd.fetch(tid, pos, pos + 1, want_meta=True):
+                start = b.pos.astype(np.int64)
+                for i in range(b.n_reads):
+                    rec = b.record(i)
+                    if int(b.ref_id[i]) == tid and rec.reference_end is not None and start[i] <= pos < rec.reference_end:
+                        got.append((rec.query_name, int(b.flag[i]), int(start[i])))
+                b.close()
+            assert sorted(got) == want and want, names[tid]

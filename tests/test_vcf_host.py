@@ -27,7 +27,12 @@ def test_parse_vcf_variants_matches_oracle(giab_paths):
                {k: w[k] for k in ("chrom", "pos", "ref", "alts", "alt", "id")}
 
 
-def test_collect_child_kmers_matches_oracle(giab_paths, giab_records, tmp_path):
+@pytest.mark.parametrize("use_index", [True, False])
+def test_collect_child_kmers_matches_oracle(giab_paths, giab_records, tmp_path, monkeypatch, use_index):
+    """Both routes of the child-side read collection — region fetches through the .bai, and
+    the index-free linear pass with a sorted-interval lookup — against the oracle (same reads
+    per variant, in file order)."""
+    monkeypatch.setenv("KDF_VCF_FETCH", "1" if use_index else "0")
     variants = P._parse_vcf_variants(giab_paths["vcf"], "HG002")
     fa = str(tmp_path / "child_kmers.fa")
     total, vrk = P._collect_child_kmers(giab_paths["child"], None, variants, 31, 20, 20, False, fa)
