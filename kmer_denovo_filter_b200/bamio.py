@@ -565,6 +565,11 @@ def append_int_tag(raw, tag, value):
     return bytes(raw) + tag.encode() + b"i" + struct.pack("<i", int(value))
 
 
+def append_z_tag(raw, tag, text):
+    """BAM record bytes (without block_size) + a ``Z``-typed (string) aux tag."""
+    return bytes(raw) + tag.encode() + b"Z" + text.encode() + b"\0"
+
+
 def _record_span(raw):
     """(ref_id, pos, end, flag) of a raw BAM record."""
     ref_id, pos, l_name, _mq, _bin, n_cig, flag, _l_seq = struct.unpack_from("<iiBBHHHi", raw, 0)

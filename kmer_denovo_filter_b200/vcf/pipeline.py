@@ -12,8 +12,9 @@ Reference map (``vcf/pipeline.py``):
   _parse_vcf_variants :747       _write_annotated_vcf :813
   _write_summary :1360           run_pipeline :1454 (parent scans :1587-1609,
                                  annotate :1662-1728, metrics :1925-1951)
-Not restated: Kraken2 contamination fractions, the HTML report and VCF mode's
-DV-tagged informative-reads BAM (SURVEY §2 rows 12, 16, 17 — out of scope).
+  _write_informative_reads :1307 (DV:Z-tagged BAM of the informative reads)
+Not restated: Kraken2 contamination fractions and the HTML report (SURVEY §2 rows 12, 16,
+17 — out of scope; their flags are refused or warned about, see cli.py).
 """
 
 import collections
@@ -257,6 +258,50 @@ def _collect_child_kmers(child_bam, ref_fasta, variants, kmer_size, min_baseq, m
             logger.info("Variant %s: %d reads, %d unique k-mers", key, len(lst), len(uniq))
     logger.info("[Step 2/5] %d reads scanned, %d k-mers collected", total_reads_scanned, total_written)
     return total_written, variant_read_kmers
+
+
+# ── informative reads (DV-tagged BAM) ──────────────────────────────
+
+def _write_informative_reads(child_bam, ref_fasta, informative_reads_by_variant, output_bam,
+                             threads=4):
+    """Child reads carrying informative k-mers → coordinate-sorted, indexed BAM; each read
+    is tagged ``DV:Z`` with the (sorted, comma-joined) variant keys it supports (reference
+    ``vcf/pipeline.py:1307-1357``).  As there: the regions are visited in sorted (chrom, pos)
+    order, every record that overlaps a site is considered (``bam.fetch``), and a read name
+    is written once — the first record met.  Needs the BAM's ``.bai``."""
+    read_to_variants = {}
+    for var_key, read_names in informative_reads_by_variant.items():
+        for rname in read_names:
+            read_to_variants.setdefault(rname, set()).add(var_key)
+    regions = set()
+    for var_key in informative_reads_by_variant:
+        parts = var_key.split(":")
+        regions.add((parts[0], int(parts[1])))
+    records, written = [], set()
+    with bamio.BamReader(child_bam, threads=threads) as rd:
+        if bamio.find_bai(child_bam) is None:
+            raise bamio._engine.KdfError(
+                "--informative-reads needs an indexed child BAM (%s.bai not found)" % child_bam)
+        tid_of = {name: i for i, name in enumerate(rd.references)}
+        for chrom, pos in sorted(regions):
+            tid = tid_of.get(chrom)
+            if tid is None:
+                continue
+            for batch in rd.fetch(tid, pos, pos + 1, want_meta=3):
+                start = batch.pos.astype(np.int64)
+                end = start + np.maximum(_reference_lengths(batch), 1)
+                hit = np.flatnonzero((batch.ref_id == tid) & (start < pos + 1) & (end > pos))
+                ro = batch.raw_off.astype(np.int64)
+                for i in hit.tolist():
+                    name = batch.record(i).query_name
+                    if name in read_to_variants and name not in written:
+                        written.add(name)
+                        raw = batch.raw_blob[ro[i]:ro[i + 1]].tobytes()
+                        records.append(bamio.append_z_tag(raw, "DV", ",".join(sorted(read_to_variants[name]))))
+                batch.close()
+        n = bamio.write_sorted_bam(output_bam, rd.header_text, rd.references, rd.lengths, records)
+    logger.info("[Step 5/5] Informative reads BAM written: %s (%d reads)", output_bam, n)
+    return n
 
 
 # ── Step 4: annotate ───────────────────────────────────────────────
@@ -537,6 +582,11 @@ def run_pipeline(args, engine=None):
         "variants_with_unique_reads": sum(1 for a in annotations.values() if a["dku"] > 0),
     }
     paths = {"vcf": out_vcf}
+    if getattr(args, "informative_reads", None):
+        logger.info("[Step 5/5] Writing informative reads BAM: %s", args.informative_reads)
+        _write_informative_reads(args.child, getattr(args, "ref_fasta", None), inf_by_var,
+                                 args.informative_reads, threads=threads)
+        paths["informative_reads"] = args.informative_reads
     if getattr(args, "metrics", None):
         with open(args.metrics, "w") as fh:
             json.dump(metrics, fh, indent=2)

@@ -4,6 +4,7 @@ the (golden-pinned) oracle annotations."""
 import gzip
 import os
 
+import numpy as np
 import pytest
 
 from kmer_denovo_filter_b200.vcf import pipeline as P
@@ -167,3 +168,50 @@ def test_tabix_index_structure(oracle_run, giab_paths, tmp_path):
         n_intv = struct.unpack_from("<i", tbi, off)[0]; off += 4 + 8 * n_intv
     assert n_chunks >= n_ref and off == len(tbi)
     assert text.count(b"\nchr") == len(variants)
+
+
+def test_informative_reads_bam_dv_tags(giab_paths, giab_records, tmp_path):
+    """VCF mode's informative-reads BAM (reference vcf/pipeline.py:1307-1357): for every
+    site in sorted order, the first record of each informative read name that overlaps the
+    site, tagged DV:Z with the sorted variant keys; coordinate sorted + .bai."""
+    from kmer_denovo_filter_b200 import bamio
+    recs = giab_records["child"]
+    names = giab_records["child_refs"][0]
+    variants = P._parse_vcf_variants(giab_paths["vcf"], "HG002")
+    # a synthetic "informative" assignment: every third read over each of the first 8 sites
+    by_var = {}
+    for var in variants[:8]:
+        tid = names.index(var["chrom"])
+        over = [r.qname for r in recs if r.ref_id == tid and r.reference_end is not None
+                and r.pos <= var["pos"] < r.reference_end]
+        if over[::3]:
+            by_var[P._var_key(var)] = set(over[::3])
+    assert len(by_var) >= 4
+    out = str(tmp_path / "inf.bam")
+    n = P._write_informative_reads(giab_paths["child"], None, by_var, out, threads=2)
+    # independent restatement over the stdlib reader's records
+    r2v = {}
+    for key, rn in by_var.items():
+        for x in rn:
+            r2v.setdefault(x, set()).add(key)
+    want, written = [], set()
+    for chrom, pos in sorted({(k.split(":")[0], int(k.split(":")[1])) for k in by_var}):
+        tid = names.index(chrom)
+        for r in recs:
+            end = r.reference_end if r.reference_end is not None else r.pos + 1
+            if r.ref_id == tid and r.pos < pos + 1 and end > pos and r.qname in r2v and r.qname not in written:
+                written.add(r.qname)
+                want.append((r.qname, r.flag, r.pos, ",".join(sorted(r2v[r.qname]))))
+    assert n == len(want) > 10
+    with bamio.BamReader(out, threads=2) as rd:
+        b = rd.next_batch(bamio.MODE_ALL, want_meta=3)
+    order = b.ref_id.astype(np.int64) * (1 << 32) + b.pos.astype(np.int64)
+    assert b.n_reads == n and (np.diff(order) >= 0).all()
+    got = []
+    ro = b.raw_off.astype(np.int64)
+    for i in range(n):
+        raw = bytes(b.raw_blob[ro[i]:ro[i + 1]])
+        j = raw.rindex(b"DVZ")
+        got.append((b.record(i).query_name, int(b.flag[i]), int(b.pos[i]), raw[j + 3:-1].decode()))
+    assert sorted(got) == sorted(want)
+    assert os.path.isfile(out + ".bai") and bamio.read_bai(out + ".bai")
