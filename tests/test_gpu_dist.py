@@ -109,7 +109,19 @@ def test_dist_chain_equals_oracle(k, peer, n_passes):
     procs = [ctx.Process(target=_worker, args=(r, world, port, k, q, peer, n_passes)) for r in range(world)]
     for p in procs:
         p.start()
-    got = [q.get(timeout=600) for _ in procs]
+    import queue as _queue
+    import time as _time
+    got, t_end = [], _time.time() + 600
+    while len(got) < len(procs):       # fail at once when a worker dies (do not sit out the timeout)
+        try:
+            got.append(q.get(timeout=2))
+        except _queue.Empty:
+            dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+            if dead or _time.time() > t_end:
+                for p in procs:
+                    if p.is_alive():
+                        p.terminate()
+                pytest.fail("distributed worker failed (exit codes %s)" % [p.exitcode for p in procs])
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0

@@ -606,20 +606,46 @@ def test_update_bins_equals_count_stream(eng, k, monkeypatch):
     assert eng.read_stats(st)["windows"] == n_win
 
 
-def test_hit_coverage_device_equals_host(eng):
-    """K7 on the device (expand + radix sort + run-length encode) == the same expansion
-    on the host, which the CPU suite pins against the reference-named helper."""
-    from kmer_denovo_filter_b200 import engine
+def test_hit_coverage_device_equals_oracle(eng):
+    """K7 on the device (expand + radix sort + run-length encode) against the ORACLE's
+    per-read restatement of core/bam_scanner.py:97-117 merged with Counters
+    (discovery/pipeline.py:851-855) — an implementation that shares no code with the
+    kernel — on random CIGARs with clips, insertions, deletions, skips and padding."""
+    import collections
+    from oracle import discovery as odisc
     from test_postprocess_cpu import _random_alignments
+
+    from oracle import bam as obam
+
+    class Rec:          # the oracle's own get_aligned_pairs (oracle/bam.py) over (pos, cigar)
+        get_aligned_pairs = obam.BamRecord.get_aligned_pairs
+
+        def __init__(self, pos, cigar):
+            self.pos, self.cigar = pos, cigar
+
     for seed, k in ((11, 9), (12, 31), (13, 63)):
-        contig, start, cig_off, cigar, hr, ho, _recs = _random_alignments(seed, n_reads=400, k=k)
-        want = engine.debug_hit_coverage_host(hr, ho, k, contig, start, cig_off, cigar)
-        got = eng.hit_coverage(np.asarray(hr, np.uint32), np.asarray(ho, np.uint32), k,
-                               np.asarray(contig, np.int32), np.asarray(start, np.int64),
-                               np.asarray(cig_off, np.uint64), np.asarray(cigar, np.uint32))
-        assert len(want[0]) > 100
-        for a, b in zip(want, got):
-            assert np.array_equal(a, b)
+        contig, start, cig_off, cigar, hr, ho, recs = _random_alignments(seed, n_reads=400, k=k)
+        kc = collections.defaultdict(collections.Counter)
+        rc = collections.defaultdict(collections.Counter)
+        for c, st, ops, offs in recs:
+            cov = odisc.kmer_ref_positions(Rec(st, ops), offs, k)
+            kc[c].update(cov)
+            for p in cov:
+                rc[c][p] += 1
+        gc, gp, gk, gr = eng.hit_coverage(np.asarray(hr, np.uint32), np.asarray(ho, np.uint32), k,
+                                          np.asarray(contig, np.int32), np.asarray(start, np.int64),
+                                          np.asarray(cig_off, np.uint64), np.asarray(cigar, np.uint32))
+        assert gc.shape[0] > 100
+        got_k = collections.defaultdict(dict)
+        got_r = collections.defaultdict(dict)
+        for c, p, a, b in zip(gc.tolist(), gp.tolist(), gk.tolist(), gr.tolist()):
+            got_k[c][p] = a
+            got_r[c][p] = b
+        assert {c: dict(v) for c, v in kc.items() if v} == dict(got_k)
+        assert {c: dict(v) for c, v in rc.items() if v} == dict(got_r)
+        # sorted by (contig, position)
+        order = gc.astype(np.int64) * (1 << 40) + gp.astype(np.int64)
+        assert (np.diff(order) > 0).all()
     empty = eng.hit_coverage(np.zeros(0, np.uint32), np.zeros(0, np.uint32), 31, np.zeros(1, np.int32),
                              np.zeros(1, np.int64), np.zeros(2, np.uint64), np.zeros(0, np.uint32))
     assert all(a.shape[0] == 0 for a in empty)
