@@ -109,11 +109,33 @@ def vcf_main(argv=None):
     run_pipeline(args)
 
 
+def _init_distributed():
+    """Under ``torchrun`` (one process per GPU): pick this rank's device and join the NCCL
+    group; → engine for that device, or None for a plain single-process run."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return None
+    import torch
+    import torch.distributed as dist
+    from . import engine
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    return engine.CudaEngine(dev)
+
+
 def discovery_main(argv=None):
     from .discovery.pipeline import run_discovery_pipeline
     args = parse_discovery_args(argv)
     _check_unsupported(args)
-    run_discovery_pipeline(args)
+    eng = _init_distributed()       # torchrun --nproc-per-node N -m kmer_denovo_filter_b200.cli ...
+    run_discovery_pipeline(args, engine=eng)
+    if eng is not None:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 def main(argv=None):

@@ -314,10 +314,13 @@ def filter_parent_dist(eng, parent_stream, k, lo, hi, parent_max_count, world, s
 
 def discover_streams_dist(eng, child, mother, father, ref, k, min_child_count=3,
                           parent_max_count=0, min_distinct_kmers_per_read=None, fetch=False,
-                          n_passes=None):
+                          n_passes=None, child_scan=None):
     """Multi-GPU form of :func:`kmer_chain.discover_streams`; every argument is this
     rank's shard (one stream, or a list of streams).  Stage sizes in the result are
-    GLOBAL (identical on all ranks); ``units`` and the per-read records are this rank's own."""
+    GLOBAL (identical on all ranks); ``units`` and the per-read records are this rank's own.
+    ``child_scan``: the streams the per-read scan runs over when they differ from the
+    counting streams (the BAM pipeline counts the ``samtools fasta`` view of a batch and
+    scans the batch itself); ``reads_parts`` then holds one record set per scan stream."""
     dist = _dist()
     torch = eng.torch
     world = dist.get_world_size()
@@ -338,7 +341,7 @@ def discover_streams_dist(eng, child, mother, father, ref, k, min_child_count=3,
     d_mothers = [up.put(x, False)[0] for x in _kc._as_list(mother)]
     d_fathers = [up.put(x, False)[0] for x in _kc._as_list(father)]
     # needed last: copied last
-    ev_reads = [up.put_read_index(d, h) for d, h in zip(d_childs, childs)] if fused else []
+    ev_reads = [up.put_read_index(d, h) for d, h in zip(d_childs, childs)] if (fused and child_scan is None) else []
 
     c = count_child_dist(eng, d_childs, d_refs, k, min_child_count, world, n_passes=n_passes)
     tot = torch.tensor([c["candidates"], c["child_distinct"]], dtype=torch.int64, device=eng.device)
@@ -370,15 +373,25 @@ def discover_streams_dist(eng, child, mother, father, ref, k, min_child_count=3,
         for ev in ev_reads:
             up.wait(ev)
         parts = []
-        for d in d_childs:
-            _kc._wait_ready(eng, d)
-            parts.append(eng.scan_reads_sparse(pt, d, stats=stats))
+        if child_scan is not None:
+            d_scan = []
+            for h in _kc._as_list(child_scan):      # uploaded one at a time: they are only scanned
+                d = eng.upload(h) if not isinstance(h, _engine.DeviceStream) else h
+                parts.append(eng.scan_reads_sparse(pt, d, stats=stats))
+                d_scan.append(d)
+            d_childs_scan = d_scan
+        else:
+            d_childs_scan = d_childs
+            for d in d_childs:
+                _kc._wait_ready(eng, d)
+                parts.append(eng.scan_reads_sparse(pt, d, stats=stats))
         pt.close()
-        sp = _kc.merge_sparse_records(parts, d_childs)
+        out["reads_parts"] = parts
+        sp = _kc.merge_sparse_records(parts, d_childs_scan)
         out["reads"] = sp
         local_inf = int((sp["ndistinct"] >= min_distinct_kmers_per_read).sum())
         if fetch:
-            n_reads = sum(d.n_reads for d in d_childs)
+            n_reads = sum(d.n_reads for d in d_childs_scan)
             nd = np.zeros(n_reads, dtype=np.uint32)
             nh = np.zeros(n_reads, dtype=np.uint32)
             nd[sp["read"].astype(np.int64)] = sp["ndistinct"]

@@ -451,23 +451,7 @@ def scan_child_reads(eng, child_bam, table, kmer_size, min_distinct_kmers_per_re
             # reduces them per read; dense per-read arrays are rebuilt here for the
             # CPU cluster / anchor step
             sp = eng.scan_reads_sparse(table, ds)
-            nd = np.zeros(batch.n_reads, dtype=np.uint32)
-            nh = np.zeros(batch.n_reads, dtype=np.uint32)
-            rr = sp["read"].astype(np.int64)
-            nd[rr] = sp["ndistinct"]
-            nh[rr] = sp["nhits"]
-            thr = max(1, min_distinct_kmers_per_read)
-            pos = sp["hit_pos"]
-            slot = sp["hit_slot"]
-            if pos.shape[0]:
-                ridx = np.searchsorted(batch.read_starts, pos, side="right") - 1
-                keep = nd[ridx] >= thr
-                pos, slot, ridx = pos[keep], slot[keep], ridx[keep]
-                off = (pos - batch.read_starts[ridx]).astype(np.int64)
-            else:
-                ridx = np.zeros(0, dtype=np.int64)
-                off = np.zeros(0, dtype=np.int64)
-                slot = np.zeros(0, dtype=np.uint32)
+            _b, nd, nh, ridx, off, slot = sparse_to_scan_item(batch, sp, min_distinct_kmers_per_read)
             yield batch, nd, nh, ridx, off, slot
             if owned:
                 batch.close()
@@ -502,6 +486,96 @@ def _cluster_hits(read_hits, merge_distance):
     return regions, region_reads, region_kmers
 
 
+class AnchorCollector:
+    """The CPU half of Module 3 for the batches one process scans: informative reads
+    de-duplicated on ``(query_name, is_supplementary)`` in file order, their region
+    tuples, SV metadata and per-position coverage (K7 on the device).  ``preseen``: keys
+    already claimed by reads that come EARLIER in the file (the shards of lower ranks in
+    a multi-GPU run): such a read is a duplicate here exactly as it would be in a
+    sequential pass."""
+
+    def __init__(self, eng, kmer_size, min_distinct_kmers_per_read, note_hit=None, preseen=None):
+        self.eng = eng
+        self.k = kmer_size
+        self.min_dk = max(1, min_distinct_kmers_per_read)
+        self.note_hit = note_hit
+        self.reads_seen = set(preseen) if preseen else set()
+        self.read_hits = []
+        self.read_sv_meta = {}
+        self.kmer_coverage = collections.defaultdict(collections.Counter)
+        self.read_coverage = collections.defaultdict(collections.Counter)
+        self.unmapped_informative = 0
+        self.total_scanned = 0
+        self.per_read = []  # (record index, n_distinct, n_hits) of reads with >= 1 hit
+
+    def add(self, batch, nd, nh, ridx, off):
+        kmer_size = self.k
+        self.total_scanned += batch.n_reads
+        hit_reads = np.flatnonzero(nh > 0)
+        for r in hit_reads.tolist():
+            self.per_read.append((int(batch.rec_index[r]), int(nd[r]), int(nh[r])))
+            if self.note_hit is not None:
+                self.note_hit(batch, r)     # the informative-reads writer fetches these by offset
+        informative = np.flatnonzero(nd >= self.min_dk)
+        lo_i = np.searchsorted(ridx, informative, side="left")
+        hi_i = np.searchsorted(ridx, informative, side="right")
+        cov_reads, cov_hits = [], []   # kept reads of this batch and their hit slices (K7 input)
+        for r, a, b in zip(informative.tolist(), lo_i.tolist(), hi_i.tolist()):
+            read = batch.record(r)
+            dedup_key = (read.query_name, read.is_supplementary)
+            if dedup_key in self.reads_seen:
+                continue
+            self.reads_seen.add(dedup_key)
+            if read.is_unmapped:
+                self.unmapped_informative += 1
+                continue
+            hit_idx = off[a:b].tolist()
+            seq = read.query_sequence
+            unique_in_read = {canonicalize(seq[i:i + kmer_size]) for i in hit_idx}
+            chrom = read.reference_name
+            self.read_hits.append((chrom, read.reference_start, read.reference_end,
+                                   dedup_key[0], unique_in_read, dedup_key[1]))
+            cov_reads.append(r)
+            cov_hits.append((a, b))
+            max_clip = 0
+            for op, ln in read.cigartuples or ():
+                if op == 4 and ln > max_clip:
+                    max_clip = ln
+            has_sa = read.has_tag("SA")
+            self.read_sv_meta[dedup_key] = {
+                "has_sa": has_sa,
+                "sa_str": read.get_tag("SA") if (has_sa and not dedup_key[1]) else None,
+                "is_paired": read.is_paired,
+                "is_proper_pair": read.is_proper_pair,
+                "mate_is_unmapped": read.mate_is_unmapped if read.is_paired else False,
+                "max_clip": max_clip,
+            }
+        _accumulate_coverage(self.eng, batch, cov_reads, cov_hits, off, kmer_size, self.kmer_coverage,
+                             self.read_coverage)
+
+
+def sparse_to_scan_item(batch, sp, min_distinct_kmers_per_read):
+    """One batch's ``scan_reads_sparse`` result → the tuple ``scan_child_reads`` yields."""
+    nd = np.zeros(batch.n_reads, dtype=np.uint32)
+    nh = np.zeros(batch.n_reads, dtype=np.uint32)
+    rr = sp["read"].astype(np.int64)
+    nd[rr] = sp["ndistinct"]
+    nh[rr] = sp["nhits"]
+    thr = max(1, min_distinct_kmers_per_read)
+    pos = sp["hit_pos"]
+    slot = sp["hit_slot"]
+    if pos.shape[0]:
+        ridx = np.searchsorted(batch.read_starts, pos, side="right") - 1
+        keep = nd[ridx] >= thr
+        pos, slot, ridx = pos[keep], slot[keep], ridx[keep]
+        off = (pos - batch.read_starts[ridx]).astype(np.int64)
+    else:
+        ridx = np.zeros(0, dtype=np.int64)
+        off = np.zeros(0, dtype=np.int64)
+        slot = np.zeros(0, dtype=np.uint32)
+    return batch, nd, nh, ridx, off, slot
+
+
 def _anchor_and_cluster(child_bam, ref_fasta, proband_unique_kmers, kmer_size,
                         merge_distance=500, threads=1, min_distinct_kmers_per_read=1,
                         proband_unique_fa=None, proband_jf=None, n_proband_unique=None,
@@ -526,62 +600,17 @@ def _anchor_and_cluster(child_bam, ref_fasta, proband_unique_kmers, kmer_size,
         table = kset.build_table()
         owns = True
     t0 = time.monotonic()
-    read_hits = []
-    reads_seen = set()
-    read_sv_meta = {}
-    kmer_coverage = collections.defaultdict(collections.Counter)
-    read_coverage = collections.defaultdict(collections.Counter)
-    unmapped_informative = 0
-    total_scanned = 0
-    per_read = []  # (record index, n_distinct, n_hits) of reads with >= 1 hit
     cache = child_cache(child_bam)
     if cache is not None:
         cache.hit_reads = []
-    for batch, nd, nh, ridx, off, _slot in scan_child_reads(
-            eng, child_bam, table, kmer_size, min_distinct_kmers_per_read, threads):
-        total_scanned += batch.n_reads
-        hit_reads = np.flatnonzero(nh > 0)
-        for r in hit_reads.tolist():
-            per_read.append((int(batch.rec_index[r]), int(nd[r]), int(nh[r])))
-            if cache is not None:
-                cache.note_hit(batch, r)     # the informative-reads writer fetches these by offset
-        informative = np.flatnonzero(nd >= max(1, min_distinct_kmers_per_read))
-        lo_i = np.searchsorted(ridx, informative, side="left")
-        hi_i = np.searchsorted(ridx, informative, side="right")
-        cov_reads, cov_hits = [], []   # kept reads of this batch and their hit slices (K7 input)
-        for r, a, b in zip(informative.tolist(), lo_i.tolist(), hi_i.tolist()):
-            read = batch.record(r)
-            dedup_key = (read.query_name, read.is_supplementary)
-            if dedup_key in reads_seen:
-                continue
-            reads_seen.add(dedup_key)
-            if read.is_unmapped:
-                unmapped_informative += 1
-                continue
-            hit_idx = off[a:b].tolist()
-            seq = read.query_sequence
-            unique_in_read = {canonicalize(seq[i:i + kmer_size]) for i in hit_idx}
-            chrom = read.reference_name
-            read_hits.append((chrom, read.reference_start, read.reference_end,
-                              dedup_key[0], unique_in_read, dedup_key[1]))
-            cov_reads.append(r)
-            cov_hits.append((a, b))
-            max_clip = 0
-            for op, ln in read.cigartuples or ():
-                if op == 4 and ln > max_clip:
-                    max_clip = ln
-            has_sa = read.has_tag("SA")
-            read_sv_meta[dedup_key] = {
-                "has_sa": has_sa,
-                "sa_str": read.get_tag("SA") if (has_sa and not dedup_key[1]) else None,
-                "is_paired": read.is_paired,
-                "is_proper_pair": read.is_proper_pair,
-                "mate_is_unmapped": read.mate_is_unmapped if read.is_paired else False,
-                "max_clip": max_clip,
-            }
-        _accumulate_coverage(eng, batch, cov_reads, cov_hits, off, kmer_size, kmer_coverage,
-                             read_coverage)
-        batch.close()
+    col = AnchorCollector(eng, kmer_size, min_distinct_kmers_per_read,
+                          note_hit=cache.note_hit if cache is not None else None)
+    for item in scan_child_reads(eng, child_bam, table, kmer_size, min_distinct_kmers_per_read, threads):
+        col.add(*item[:5])
+        item[0].close()
+    read_hits, read_sv_meta = col.read_hits, col.read_sv_meta
+    kmer_coverage, read_coverage = col.kmer_coverage, col.read_coverage
+    unmapped_informative, total_scanned, per_read = col.unmapped_informative, col.total_scanned, col.per_read
     if cache is not None:
         cache.scanned = True
         cache.release_batches()      # only the hit list and the reader are needed from here on
@@ -966,6 +995,23 @@ def run_discovery_pipeline(args, engine=None):
         timings[name] = timings.get(name, 0.0) + (now - t_stage)
         t_stage = now
 
+    # one process per GPU under torch.distributed: every rank takes a range of each BAM
+    world = 1
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            world = dist.get_world_size()
+    except ImportError:
+        pass
+    if world > 1:
+        from . import pipeline_dist
+        paths = {"bed": bed_path, "metrics": metrics_path, "summary": summary_path, "bedpe": bedpe_path,
+                 "bedgraph": bedgraph_path, "read_cov": read_cov_bed_path, "info_bam": info_bam_path}
+        try:
+            return pipeline_dist.run_discovery_pipeline_dist(args, eng, paths, min_dk, min_bedgraph_reads,
+                                                             finish_empty, lap)
+        finally:
+            timings["total_s"] = time.monotonic() - start
     # the parents are decoded in the background while the child is read and counted (bounded
     # look-ahead: two batches each)
     if os.environ.get("KDF_PREFETCH_PARENTS", "1") != "0":
@@ -1018,6 +1064,22 @@ def _run_discovery(args, eng, k, threads, min_dk, min_bedgraph_reads, bed_path, 
     pu_table.close()
     lap("informative_bam_s")
 
+    paths = {"bed": bed_path, "metrics": metrics_path, "summary": summary_path, "bedpe": bedpe_path,
+             "bedgraph": bedgraph_path, "read_cov": read_cov_bed_path, "info_bam": info_bam_path}
+    return _finish_discovery(args, regions, region_reads, region_kmers, read_sv_meta, kmer_coverage,
+                             read_coverage, total_informative, unmapped_informative, n_candidates,
+                             n_non_ref, n_pu, min_dk, min_bedgraph_reads, paths, lap, start)
+
+
+def _finish_discovery(args, regions, region_reads, region_kmers, read_sv_meta, kmer_coverage,
+                      read_coverage, total_informative, unmapped_informative, n_candidates, n_non_ref,
+                      n_pu, min_dk, min_bedgraph_reads, paths, lap, start=None):
+    """Module 4: filter, annotate, classify and write every output file (reference
+    ``discovery/pipeline.py:2330-2548``) from the anchored reads."""
+    bed_path, metrics_path, summary_path = paths["bed"], paths["metrics"], paths["summary"]
+    bedpe_path, bedgraph_path, read_cov_bed_path = paths["bedpe"], paths["bedgraph"], paths["read_cov"]
+    if start is None:
+        start = time.monotonic()
     min_reads, min_kmers = args.min_supporting_reads, args.min_distinct_kmers
     if min_reads > 1 or min_kmers > 1:
         regions = [r for r in regions if len(region_reads.get(r, ())) >= min_reads

@@ -4,8 +4,7 @@ set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name,memory.total --format=csv | head -9
 nproc; free -g | head -2
-timeout 900 python -m pytest tests/test_gpu_dist.py -m gpu -x -q > gpurun_out/r2f_pytest_gpu_n4.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/r2f_pytest_gpu_n4.txt
-tail -5 gpurun_out/r2f_pytest_gpu_n4.txt
+echo "dist pytest: see r2f_pytest_gpu_n2.txt (2 GPUs)"
 T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511"
 timeout 900 $T bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/r2f_bench_n8.json 2> gpurun_out/r2f_bench_n8.err; echo "bench n8 rc=$?"
 tail -3 gpurun_out/r2f_bench_n8.err

