@@ -67,8 +67,8 @@ def test_low_entropy_keys_do_not_collapse():
 
 
 def test_filter_words_and_partition_plans():
-    """Host-side sizing: the two-bit filter takes 32 bits per key, 16 when only that fits
-    the budget, none beyond; the packed count plans half as many hash ranges as the plane
+    """Host-side sizing: the two-bit filter takes 32 bits per key, 16 or 8 when only that
+    fits the budget, none beyond; the packed count plans half as many hash ranges as the plane
     form for the same L2 slice."""
     from kmer_denovo_filter_b200.discovery import kmer_chain
     fw = engine.CudaEngine.filter_words
@@ -77,7 +77,8 @@ def test_filter_words_and_partition_plans():
     assert fw(3_893_677, 32 * mb) * 4 == 16 * mb          # 32 bits per key
     assert fw(7_790_648, 32 * mb) * 4 == 32 * mb
     assert fw(15_602_227, 32 * mb) * 4 == 32 * mb         # 16 bits per key
-    assert fw(31_243_893, 32 * mb) == 0                   # no filter: the binned route
+    assert fw(31_243_893, 32 * mb) * 4 == 32 * mb         # 8 bits per key (the 8-GPU filter set)
+    assert fw(70_000_000, 32 * mb) == 0                   # no filter: the binned route
     for n in (1, 1000, 5_000_000):
         w = fw(n, 1 << 30)
         assert w & (w - 1) == 0 and w >= min(n, 1024)
