@@ -40,6 +40,8 @@ class _Uploader:
         if isinstance(s, _engine.DeviceStream):
             return s, None
         torch = self.torch
+        if self.eng.device.type != "cuda":      # the numpy engine of the CPU tests: no streams
+            return self.eng.upload(s, with_reads=with_reads), None
         if self.side is None:
             self.side = getattr(self.eng, "_copy_stream", None)
             if self.side is None:

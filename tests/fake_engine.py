@@ -94,6 +94,19 @@ class FakeEngine:
         v = st.numpy()
         return {"windows": int(v[0]), "full": int(v[1]), "hits": int(v[2]), "new": int(v[3])}
 
+    # -- data movement: host stream -> "device" stream of CPU tensors
+    def upload(self, hs, non_blocking=False, with_reads=True, copy_stream=None):
+        def t(a, dt):
+            return torch.from_numpy(np.ascontiguousarray(a).view(dt).copy())
+        rs = t(hs.read_starts, np.int64) if (with_reads and hs.read_lens is not None) else None
+        rl = t(hs.read_lens, np.int32) if (with_reads and hs.read_lens is not None) else None
+        return engine.DeviceStream(t(hs.codes, np.int64), t(hs.valid, np.int32), hs.n_bases, rs, rl)
+
+    def hit_coverage(self, *a):
+        """K7 through the host instantiation of the device code (pinned to the reference-named
+        helper by tests/test_postprocess_cpu.py)."""
+        return engine.debug_hit_coverage_host(*a)
+
     # -- binning
     def new_bins(self, k, n_parts, bin_cap, by_owner=False):
         return FakeBins(k, n_parts, bin_cap, by_owner)
