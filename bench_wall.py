@@ -135,8 +135,59 @@ def write_reads_bam(path, contigs, table, read_len, to_ref=None, threads=None, l
         nb = n.encode() + b"\0"
         head += np.int32(len(nb)).tobytes() + nb + np.int32(ln).tobytes()
     data = np.concatenate([np.frombuffer(bytes(head), dtype=np.uint8), rec.view(np.uint8).reshape(-1)])
-    bamio.bgzf_write(path, data, level=level, threads=threads)
+    coff = bamio.bgzf_write(path, data, level=level, threads=threads)
+    write_bai_fixed(path + ".bai", len(contigs), len(head), dt.itemsize, rec["refID"], rec["pos"].astype(np.int64),
+                    L, rec["bin"].astype(np.int64), coff, int(data.shape[0]))
     return {"reads": int(2 * m), "bam_bytes": os.path.getsize(path), "uncompressed_bytes": int(data.shape[0])}
+
+
+def write_bai_fixed(path, n_ref, head_len, rec_size, tid, pos, read_len, bins, coff, total_len):
+    """The .bai of a BAM whose records all have ``rec_size`` bytes (and ``read_len`` aligned
+    bases), sorted by (tid, pos): bins with their chunks and the 16 kbp linear index, from
+    arithmetic on the record number (record i starts at head_len + i * rec_size of the
+    uncompressed stream; BGZF blocks hold 0xff00 bytes)."""
+    import struct
+    BLK = 0xff00
+
+    def voff(u):
+        u = np.asarray(u, dtype=np.int64)
+        b = u // BLK
+        return (coff[np.minimum(b, coff.shape[0] - 1)].astype(np.uint64) << np.uint64(16)) | \
+            (u - b * BLK).astype(np.uint64)
+    n = tid.shape[0]
+    ustart = head_len + np.arange(n + 1, dtype=np.int64) * rec_size
+    ustart[-1] = total_len
+    v = voff(ustart)
+    if total_len % BLK == 0:          # the end of the data is the start of the EOF block
+        v[-1] = np.uint64(int(coff[-1]) << 16)
+    out = bytearray(b"BAI\x01" + struct.pack("<i", n_ref))
+    bounds = np.searchsorted(tid, np.arange(n_ref + 1))
+    for r in range(n_ref):
+        a, b = int(bounds[r]), int(bounds[r + 1])
+        if a == b:
+            out += struct.pack("<ii", 0, 0)
+            continue
+        bb = bins[a:b]
+        run_start = np.flatnonzero(np.concatenate(([True], bb[1:] != bb[:-1])))
+        run_end = np.concatenate((run_start[1:], [b - a]))
+        run_bin = bb[run_start]
+        order = np.argsort(run_bin, kind="stable")
+        ub, first = np.unique(run_bin[order], return_index=True)
+        cnt = np.diff(np.concatenate((first, [order.shape[0]])))
+        out += struct.pack("<i", ub.shape[0])
+        for j in range(ub.shape[0]):
+            sel = order[first[j]:first[j] + cnt[j]]
+            out += struct.pack("<Ii", int(ub[j]), int(sel.shape[0]))
+            ch = np.stack([v[a + run_start[sel]], v[a + run_end[sel]]], axis=1).astype("<u8")
+            out += ch.tobytes()
+        p = pos[a:b]
+        n_intv = int((p[-1] + read_len - 1) >> 14) + 1
+        first_read = np.searchsorted(p + read_len, np.arange(n_intv, dtype=np.int64) << 14, side="right")
+        lin = v[a + np.minimum(first_read, b - a - 1)].astype("<u8")
+        out += struct.pack("<i", n_intv) + lin.tobytes()
+    out += struct.pack("<Q", 0)
+    with open(path, "wb") as fh:
+        fh.write(out)
 
 
 def write_fasta(path, contigs, ref_codes):
@@ -200,6 +251,29 @@ def make_bam_trio(torch, dev, genome_bp, depth, read_len, n_denovo, outdir, thre
     return paths, ev, stats
 
 
+def write_truth_vcf(path, contigs, events, sample="child"):
+    """The injected de novo events as the candidate VCF of VCF mode (config 3)."""
+    with open(path, "w") as fh:
+        fh.write("##fileformat=VCFv4.2\n")
+        for n, ln in contigs:
+            fh.write("##contig=<ID=%s,length=%d>\n" % (n, ln))
+        fh.write('##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">\n')
+        fh.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t%s\n" % sample)
+        order = {n: i for i, (n, _l) in enumerate(contigs)}
+        for chrom, pos, _kind, ref, alt in sorted(events, key=lambda e: (order[e[0]], e[1])):
+            fh.write("%s\t%d\t.\t%s\t%s\t.\tPASS\t.\tGT\t0/1\n" % (chrom, pos + 1, ref, alt))
+
+
+def vcf_args(paths, vcf_path, out_dir, k=31, threads=None):
+    return argparse.Namespace(
+        child=paths["child"], mother=paths["mother"], father=paths["father"], ref_fasta=paths["ref"],
+        vcf=vcf_path, output=os.path.join(out_dir, "annotated.vcf.gz"),
+        metrics=os.path.join(out_dir, "vcf_metrics.json"), summary=os.path.join(out_dir, "vcf_summary.txt"),
+        informative_reads=os.path.join(out_dir, "vcf_informative.bam"), kmer_size=k, min_baseq=20,
+        min_mapq=20, proband_id="child", threads=threads or (os.cpu_count() or 4), memory=None,
+        debug_kmers=False, jf_hash_size=None, tmp_dir=None, kraken2_db=None, report=None)
+
+
 def discovery_args(paths, out_prefix, k=31, threads=None):
     return argparse.Namespace(
         child=paths["child"], mother=paths["mother"], father=paths["father"], ref_fasta=paths["ref"],
@@ -246,6 +320,24 @@ def discovery_wall(args, eng, rank=0):
             runs.append((time.perf_counter() - t0, dict(pipeline.LAST_TIMINGS)))
         wall, stages = runs[-1]
         hit, n_regions = events_detected(os.path.join(tmp, "out.bed"), events)
+        # VCF mode on the same BAMs (BASELINE config 3): the 100 injected events as candidates
+        from kmer_denovo_filter_b200.vcf import pipeline as vpipe
+        vcf_path = os.path.join(tmp, "truth.vcf")
+        write_truth_vcf(vcf_path, contigs_for(genome_bp), events)
+        vruns = []
+        for _ in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            vres = vpipe.run_pipeline(vcf_args(paths, vcf_path, tmp, args.k, threads), engine=eng)
+            torch.cuda.synchronize()
+            vruns.append(time.perf_counter() - t0)
+        ann = vres["annotations"]
+        vcf_mode = {"wall_s": vruns[-1], "first_run_wall_s": vruns[0], "variants": len(ann),
+                    "variants_with_DKU": sum(1 for a in ann.values() if a["dku"] > 0),
+                    "variants_with_DKA": sum(1 for a in ann.values() if a["dka"] > 0),
+                    "total_child_kmers": int(vres["metrics"]["total_child_kmers"]),
+                    "child_unique_kmers": int(vres["metrics"]["child_unique_kmers"]),
+                    "api": "kmer_denovo_filter_b200.vcf.pipeline.run_pipeline (the kmer-denovo CLI entry)"}
         reads = sum(gen[w]["reads"] for w in ("child", "mother", "father"))
         return {
             "genome_bp": genome_bp, "depth": args.depth, "k": args.k,
@@ -259,6 +351,7 @@ def discovery_wall(args, eng, rank=0):
                         "proband_unique_kmers": int(metrics.get("proband_unique_kmers", 0)),
                         "informative_reads": int(metrics.get("informative_reads", 0))},
             "api": "kmer_denovo_filter_b200.discovery.pipeline.run_discovery_pipeline (the kmer-discovery CLI entry)",
+            "vcf_mode": vcf_mode,
         }
     finally:
         shutil.rmtree(tmp, ignore_errors=True)

@@ -59,3 +59,34 @@ def test_bam_trio_matches_the_packed_streams(tmp_path):
         mism.append(sum(1 for x, y in zip(seq, ref) if x != y))
     mism = np.array(mism)
     assert np.median(mism) <= 1 and (mism <= 3).mean() > 0.97      # only reads over an indel disagree
+
+
+def test_synthetic_bai_supports_fetch_and_shards(tmp_path):
+    """The .bai bench_wall writes for its BAMs: region fetches return exactly the reads over
+    a site, and rank shards partition the file."""
+    import bench_wall
+    from kmer_denovo_filter_b200 import bamio
+    genome, depth, L = 300_000, 10, 100
+    paths, events, _stats = bench_wall.make_bam_trio(torch, torch.device("cpu"), genome, depth, L, 10,
+                                                     str(tmp_path), threads=2)
+    assert os.path.isfile(paths["child"] + ".bai")
+    with bamio.BamReader(paths["child"], threads=2) as rd:
+        whole = rd.next_batch(bamio.MODE_ALL, want_meta=True)
+        pos_all = whole.pos.astype(np.int64)
+        names = [whole.record(i).query_name for i in range(whole.n_reads)]
+        for site in (500, 16384, 16385, 100_000, 163_840, genome - 1000):
+            want = sorted((names[i], int(pos_all[i])) for i in np.flatnonzero((pos_all <= site) & (site < pos_all + L)))
+            got = []
+            for b in rd.fetch(0, site, site + 1, want_meta=True):
+                p = b.pos.astype(np.int64)
+                got += [(b.record(i).query_name, int(p[i])) for i in np.flatnonzero((p <= site) & (site < p + L))]
+                b.close()
+            assert sorted(got) == want and want
+    total = 0
+    for r in range(3):
+        rd = bamio.open_shard(paths["child"], r, 3, threads=2)
+        n = sum(b.n_reads for b in rd.batches(bamio.MODE_FASTA, max_bases=1 << 20))
+        rd.close()
+        assert n > 0
+        total += n
+    assert total == whole.n_reads
