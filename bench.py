@@ -532,6 +532,30 @@ def main():
             random_access[name] = {"gops": n_ops / t / 1e9,
                                    "sector_gbs": n_ops * (64 if atomic else 32) / t / 1e9}
         del buf
+        # the ceiling that actually binds the L2-sliced child count: an L2-resident
+        # 48 MB buffer, one 256-bit read per op, alone and with a returning compare-and-swap on
+        # one op in six — the access mix of k_packed_keys
+        small = torch.zeros((48 << 20) // 8, dtype=torch.int64, device=dev)
+        for name, mode in (("l2_read256", 10), ("l2_read256_cas_1_in_6", 11)):
+            eng.bench_random_access(small, n_ops, mode)
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.bench_random_access(small, n_ops, mode)
+            e1.record()
+            torch.cuda.synchronize()
+            random_access[name] = {"gops": n_ops / (e0.elapsed_time(e1) * 1e-3) / 1e9, "buffer_mb": 48}
+        del small
+        for r in ([roofline] if roofline else []) + roofline_all:
+            if r["kernel"].startswith("count_bins"):
+                r["l2_mixed_rate_fraction"] = r["gkmers_per_s"] / random_access["l2_read256_cas_1_in_6"]["gops"]
+                r["l2_mixed_rate_note"] = (
+                    "k-mers/s of the whole count_bins call (insert + mark + emit kernels) / ops/s of the "
+                    "microbenchmark 'one 32 B read per op + returning CAS on one op in six' on an "
+                    "L2-resident 48 MB buffer, same run: the rate the L2 sustains for this kernel's "
+                    "access mix; occupancy, instruction count and atomic latency were each varied "
+                    "without moving the kernel's time (profiles/r2c_count_variants.md)")
         if roofline is not None:
             for r in [roofline] + roofline_all:
                 is_count = kernel_class(r["kernel"])[0] == "count"
@@ -543,6 +567,15 @@ def main():
                     "k-mers/s of this kernel / ops/s of uniformly random 32 B sector %s over 8 GiB "
                     "(table >> L2) measured in this run; > 1 means the table traffic stays in L2 / "
                     "shared memory" % ("read + atomic add" if is_count else "reads"))
+    for r in ([roofline] if roofline else []) + roofline_all:
+        if r["kernel"].startswith("bin_stream_to_peers"):
+            sent = r["kmers_per_launch"] * 8.0 * kw * (world - 1) / max(world, 1)
+            r["interconnect"] = {
+                "bound": "nvlink", "bytes_to_peers_per_launch": sent,
+                "achieved_gbs_per_gpu": sent / (r["kernel_ms_avg"] * 1e-3) / 1e9,
+                "reference": "profiles/r2g_peer_bin_sweep_n8.json: on 8 B200 the same kernel with ONE "
+                             "bin per owner (longest runs) takes 22.8 ms per 1.53 G keys = 470 GB/s per "
+                             "GPU; ncclAllToAll of the same bytes takes 48.8 ms (242 GB/s)"}
     if world > 1:
         dist.barrier()
 

@@ -52,3 +52,44 @@ def test_scan_parent_equals_oracle(eng, giab_paths, giab_records, tmp_path, k):
     want = ovcf.parent_counts(giab_records["father"], k, filt)
     assert got == want
     assert all(v >= 1 for v in got.values())
+
+
+def test_vcf_and_discovery_on_a_synthetic_bam_trio_equal_the_oracle(eng, tmp_path):
+    """BASELINE config 3 in small (200 kbp x 30x trio written as sorted, indexed BAMs, the
+    injected de novo events as the candidate VCF): VCF mode — every variant's DKU / DKT /
+    DKA / PKC fields, the metrics and the DV-tagged informative reads — and discovery mode
+    — stage sizes and BED rows — against the oracle run on the same files read with the
+    oracle's own stdlib BAM reader."""
+    import sys
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import bench_wall
+    from kmer_denovo_filter_b200.discovery import pipeline as DP
+    from kmer_denovo_filter_b200.vcf import pipeline as P
+    from oracle import bam as obam, discovery as odisc, vcf as ovcf
+    genome, depth, L, k = 200_000, 30, 150, 31        # (the oracle is pure Python: ~50 s at this size)
+    paths, events, _st = bench_wall.make_bam_trio(torch, eng.device, genome, depth, L, 8, str(tmp_path), threads=4)
+    vcf_path = str(tmp_path / "truth.vcf")
+    bench_wall.write_truth_vcf(vcf_path, bench_wall.contigs_for(genome), events)
+    recs = {w: obam.read_bam(paths[w])[2] for w in ("child", "mother", "father")}
+    # ---- VCF mode
+    _h, _s, variants = ovcf.parse_vcf(vcf_path, "child")
+    want_ann, want_metrics, _found = ovcf.run(recs["child"], recs["mother"], recs["father"], variants, k)
+    res = P.run_pipeline(bench_wall.vcf_args(paths, vcf_path, str(tmp_path), k, threads=4), engine=eng)
+    assert res["metrics"] == want_metrics
+    assert res["annotations"] == want_ann
+    assert all(a["dku"] > 0 for a in want_ann.values())                  # every injected event is found
+    n_snv = sum(1 for e in events if e[2] == "snv")
+    assert sum(1 for a in want_ann.values() if a["dka"] > 0) >= n_snv - 1
+    # ---- discovery mode on the same files
+    ref_seqs = [s for _n, s in obam.read_fasta(paths["ref"])]
+    want = odisc.run(recs["child"], recs["mother"], recs["father"], ref_seqs, k)
+    m = DP.run_discovery_pipeline(bench_wall.discovery_args(paths, str(tmp_path / "disc"), k, threads=4), engine=eng)
+    assert m["child_candidate_kmers"] == len(want["candidates"])
+    assert m["non_ref_kmers"] == len(want["non_ref"])
+    assert m["proband_unique_kmers"] == len(want["proband_unique"])
+    assert m["informative_reads"] == want["informative"]
+    rows = [l.rstrip("\n").split("\t") for l in open(str(tmp_path / "disc.bed")) if not l.startswith("#")]
+    assert rows == [[str(x) for x in r] for r in want["bed"]]
