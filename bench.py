@@ -638,9 +638,9 @@ def main():
 
     # ---- discovery wall time: BAM trio -> candidate BED through the product pipeline ------
     wall = None
-    if not args.no_wall and world == 1 and not args.total_genome_mbp:
+    if not args.no_wall and not args.total_genome_mbp:
         import bench_wall
-        wall = bench_wall.discovery_wall(args, eng, rank)
+        wall = bench_wall.discovery_wall(args, eng, rank, world)
 
     if rank == 0:
         line = {

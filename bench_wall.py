@@ -298,52 +298,70 @@ def events_detected(bed_path, events, slack=200):
     return hit, len(regions)
 
 
-def discovery_wall(args, eng, rank=0):
-    """bench.py's `discovery_wall` object: BAM trio -> candidate BED through the product CLI path."""
-    if rank != 0:
-        return None
+def discovery_wall(args, eng, rank=0, world=1):
+    """bench.py's `discovery_wall` object: BAM trio -> candidate BED through the product CLI path.
+    With several ranks the SAME trio (not a larger one) is run by the multi-GPU pipeline: every
+    rank decodes 1 / world of each BAM."""
     import torch
     from kmer_denovo_filter_b200.discovery import pipeline
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
     genome_bp = int((args.wall_mbp or args.genome_mbp) * 1e6)
-    threads = os.cpu_count() or 4
-    tmp = tempfile.mkdtemp(prefix="kdf_wall_", dir=os.environ.get("KDF_WALL_TMP"))
-    try:
+    threads = max(2, (os.cpu_count() or 4) // max(world, 1))
+    box = [None]
+    if rank == 0:
+        tmp = tempfile.mkdtemp(prefix="kdf_wall_", dir=os.environ.get("KDF_WALL_TMP"))
         paths, events, gen = make_bam_trio(torch, eng.device, genome_bp, args.depth, args.read_len,
-                                           args.denovo, tmp, threads)
+                                           args.denovo, tmp, os.cpu_count() or 4)
+        box[0] = (tmp, paths)
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)
+    tmp, paths = box[0]
+    try:
         pargs = discovery_args(paths, os.path.join(tmp, "out"), args.k, threads)
         runs = []
         for _ in range(2):           # the first run pays page-cache and allocator warm-up: report the second
             torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
             t0 = time.perf_counter()
             metrics = pipeline.run_discovery_pipeline(pargs, engine=eng)
             torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
             runs.append((time.perf_counter() - t0, dict(pipeline.LAST_TIMINGS)))
+        if rank != 0:
+            return None
         wall, stages = runs[-1]
         hit, n_regions = events_detected(os.path.join(tmp, "out.bed"), events)
-        # VCF mode on the same BAMs (BASELINE config 3): the 100 injected events as candidates
-        from kmer_denovo_filter_b200.vcf import pipeline as vpipe
-        vcf_path = os.path.join(tmp, "truth.vcf")
-        write_truth_vcf(vcf_path, contigs_for(genome_bp), events)
-        vruns = []
-        for _ in range(2):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            vres = vpipe.run_pipeline(vcf_args(paths, vcf_path, tmp, args.k, threads), engine=eng)
-            torch.cuda.synchronize()
-            vruns.append(time.perf_counter() - t0)
-        ann = vres["annotations"]
-        vcf_mode = {"wall_s": vruns[-1], "first_run_wall_s": vruns[0], "variants": len(ann),
-                    "variants_with_DKU": sum(1 for a in ann.values() if a["dku"] > 0),
-                    "variants_with_DKA": sum(1 for a in ann.values() if a["dka"] > 0),
-                    "total_child_kmers": int(vres["metrics"]["total_child_kmers"]),
-                    "child_unique_kmers": int(vres["metrics"]["child_unique_kmers"]),
-                    "api": "kmer_denovo_filter_b200.vcf.pipeline.run_pipeline (the kmer-denovo CLI entry)"}
+        vcf_mode = None
+        if world == 1:
+            # VCF mode on the same BAMs (BASELINE config 3): the 100 injected events as candidates
+            from kmer_denovo_filter_b200.vcf import pipeline as vpipe
+            vcf_path = os.path.join(tmp, "truth.vcf")
+            write_truth_vcf(vcf_path, contigs_for(genome_bp), events)
+            vruns = []
+            for _ in range(2):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                vres = vpipe.run_pipeline(vcf_args(paths, vcf_path, tmp, args.k, threads), engine=eng)
+                torch.cuda.synchronize()
+                vruns.append(time.perf_counter() - t0)
+            ann = vres["annotations"]
+            vcf_mode = {"wall_s": vruns[-1], "first_run_wall_s": vruns[0], "variants": len(ann),
+                        "variants_with_DKU": sum(1 for a in ann.values() if a["dku"] > 0),
+                        "variants_with_DKA": sum(1 for a in ann.values() if a["dka"] > 0),
+                        "total_child_kmers": int(vres["metrics"]["total_child_kmers"]),
+                        "child_unique_kmers": int(vres["metrics"]["child_unique_kmers"]),
+                        "api": "kmer_denovo_filter_b200.vcf.pipeline.run_pipeline (the kmer-denovo CLI entry)"}
         reads = sum(gen[w]["reads"] for w in ("child", "mother", "father"))
         return {
-            "genome_bp": genome_bp, "depth": args.depth, "k": args.k,
+            "genome_bp": genome_bp, "depth": args.depth, "k": args.k, "n_gpus": world,
+            "note": "the same 64 Mbp trio at every N (strong scaling of the product pipeline)" if world > 1 else None,
             "input": {"reads": reads, "bam_bytes": sum(gen[w]["bam_bytes"] for w in ("child", "mother", "father")),
                       "bam_level": 1, "bam_write_seconds": gen["seconds"]},
-            "wall_s": wall, "first_run_wall_s": runs[0][0], "host_threads": threads,
+            "wall_s": wall, "first_run_wall_s": runs[0][0], "host_threads_per_rank": threads,
             "stages_s": {k: round(v, 4) for k, v in stages.items()},
             "reads_per_s": reads / wall,
             "outputs": {"candidate_regions": n_regions, "de_novo_events": len(events),
@@ -354,4 +372,7 @@ def discovery_wall(args, eng, rank=0):
             "vcf_mode": vcf_mode,
         }
     finally:
-        shutil.rmtree(tmp, ignore_errors=True)
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            shutil.rmtree(tmp, ignore_errors=True)
