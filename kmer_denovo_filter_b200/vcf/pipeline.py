@@ -551,6 +551,12 @@ def run_pipeline(args, engine=None):
     variants = _parse_vcf_variants(args.vcf, getattr(args, "proband_id", None))
     logger.info("[Step 1/5] Parsed %d candidate variants", len(variants))
     tmp_root = getattr(args, "tmp_dir", None) or tempfile.gettempdir()
+    # the two whole-file parent scans dominate this mode: start decoding both parents now, in the
+    # background (bounded look-ahead), while the child's reads over the sites are collected
+    from ..core import kmer_engine_wrappers as _kw
+    if os.environ.get("KDF_PREFETCH_PARENTS", "1") != "0":
+        _kw.start_prefetch(args.mother, bamio.MODE_FASTA, threads)
+        _kw.start_prefetch(args.father, bamio.MODE_FASTA, threads)
     with tempfile.TemporaryDirectory(dir=tmp_root) as tmpdir:
         kmer_fasta = os.path.join(tmpdir, "child_kmers.fa")
         total_child_kmers, variant_read_kmers = _collect_child_kmers(
@@ -569,6 +575,7 @@ def run_pipeline(args, engine=None):
                 parent_found_kmers.update(found)
                 logger.info("[Step 3/5] %s done — %d / %d child k-mers found", label, len(found),
                             total_child_kmers)
+    _kw.drop_prefetch()      # (started above; consumed by the scans unless there was nothing to scan)
     child_unique_kmers = max(0, total_child_kmers - len(parent_found_kmers))
     annotations, inf_by_var, _inf_alt = _annotate_variants(variants, variant_read_kmers,
                                                            parent_found_kmers)
