@@ -535,6 +535,18 @@ int kdf_bgzf_write(const char* path, const uint8_t* data /*HOST*/, uint64_t n, i
                    int n_threads, uint64_t* block_coff /*HOST or NULL*/, uint64_t block_cap,
                    uint64_t* n_blocks);
 
+/* One whole BGZF block (header .. CRC32/ISIZE trailer, `csize` bytes) -> its `usize`
+ * inflated bytes, CRC-checked unless verify_crc == 0: the per-block step of every BAM
+ * read above, exposed so it can be checked against zlib block by block
+ * (tests/test_host_inflate.py).  impl 0: the library's own DEFLATE decoder
+ * (csrc/kdf_inflate.cpp), 1: zlib's inflate().  htslib does this in bgzf.c
+ * (bgzf_uncompress), which the reference reaches through `samtools fasta`
+ * (kmer_utils.py:310-340) and pysam.  KDF_OK, or KDF_ERR_ARG for a corrupt block.     */
+int kdf_bgzf_inflate_block(const uint8_t* src /*HOST*/, uint32_t csize, uint8_t* dst /*HOST*/,
+                           uint32_t usize, int verify_crc, int impl);
+/* CRC-32 (gzip polynomial) of a host buffer with the library's routine.              */
+uint32_t kdf_crc32(const uint8_t* data /*HOST*/, uint64_t n);
+
 /* Test hook: runs the device window-iterator templates on the CPU (host
  * instantiation of the same code) so the bit manipulation can be verified
  * without a GPU.  Not used by any product path.                             */

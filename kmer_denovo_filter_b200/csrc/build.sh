@@ -8,5 +8,5 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
   -gencode arch=compute_100a,code=sm_100a \
   -Xcompiler -fPIC,-O3,-Wall,-fopenmp -shared \
   ${KDF_NVCC_EXTRA:-} \
-  -o "${OUT}" "${HERE}/kdf_kernels.cu" "${HERE}/kdf_host.cpp" -lz -lgomp
+  -o "${OUT}" "${HERE}/kdf_kernels.cu" "${HERE}/kdf_host.cpp" "${HERE}/kdf_inflate.cpp" -lz -lgomp
 echo "built ${OUT}"

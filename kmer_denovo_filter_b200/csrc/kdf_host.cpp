@@ -21,15 +21,21 @@
 #include <string.h>
 #include <sys/mman.h>
 #include <sys/types.h>
+#include <omp.h>
+#include <sched.h>
 #include <zlib.h>
+#include <omp.h>
 
+#include <atomic>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <string>
 #include <utility>
 #include <vector>
 
 #include "../../include/kdf.h"
+#include "kdf_inflate.h"
 
 namespace {
 
@@ -41,6 +47,44 @@ template <class T> struct NoInitAlloc : std::allocator<T> {
   template <class U> struct rebind { using other = NoInitAlloc<U>; };
   template <class U> void construct(U* p) noexcept { ::new ((void*)p) U; }
   template <class U, class... A> void construct(U* p, A&&... a) { ::new ((void*)p) U(std::forward<A>(a)...); }
+};
+
+// A growable array of plain values for the batch outputs: resize() leaves new elements
+// uninitialised (they are written by the parallel fill loops, which is also what first touches
+// their pages) and growth goes through realloc(), which moves large blocks by remapping
+// their pages instead of copying them.  (std::vector value-initialises and copies on
+// growth: on one thread, that was a third of the decode time.)
+template <class T> struct PodVec {
+  T* p = nullptr;
+  size_t n = 0, cap = 0;
+  PodVec() = default;
+  PodVec(const PodVec&) = delete;
+  PodVec& operator=(const PodVec&) = delete;
+  ~PodVec() { free(p); }
+  T* data() { return p; }
+  const T* data() const { return p; }
+  size_t size() const { return n; }
+  size_t capacity() const { return cap; }
+  bool empty() const { return n == 0; }
+  T& operator[](size_t i) { return p[i]; }
+  const T& operator[](size_t i) const { return p[i]; }
+  void reserve(size_t want) {
+    if (want <= cap) return;
+    if (want > SIZE_MAX / sizeof(T)) throw std::bad_alloc();
+    void* q = realloc(p, want * sizeof(T));
+    if (!q) throw std::bad_alloc();
+    p = (T*)q;
+    cap = want;
+  }
+  void resize(size_t m) {
+    if (m > cap) reserve(m + m / 2 + 1024);
+    n = m;
+  }
+  void assign(size_t m, T v) {
+    resize(m);
+    for (size_t i = 0; i < m; ++i) p[i] = v;
+  }
+  void clear() { n = 0; }
 };
 
 struct BlockRef {
@@ -59,23 +103,27 @@ struct CompBuf {
   bool valid = false;
 };
 
-// a record taken into the batch being built
-struct Kept {
-  const uint8_t* rec;  // the record body (inside one of the chunk buffers)
-  uint64_t start;      // stream position of its first base
-  uint64_t uoff;       // offset of the record (its block_size word) in the uncompressed stream
-  uint32_t l_seq;
-  uint8_t fasta_keep;  // KDF_BAM_FASTA would keep this record
-};
-
-// an inflated chunk: logical bytes data[begin .. size), `begin` leaves headroom for the
-// unparsed tail of the chunk before it
+// An inflated chunk of the record stream.  data[own .. own + total) is what its BGZF blocks
+// inflate to; data[head .. own) holds the bytes of the previous chunk that belong to a record
+// completed here.  The record walk (filled while the chunk is inflated) gives the compact
+// per-record arrays the consumer works from.
 struct Chunk {
   uint8_t* data = nullptr;
-  size_t begin = 0, size = 0, cap = 0;
-  size_t own = 0;        // where the chunk's own first byte sits (bytes before it: the previous chunk's tail)
+  size_t cap = 0;
+  size_t own = 0, head = 0, total = 0;
   uint64_t ustart = 0;   // uncompressed-stream offset of data[own]
-  bool valid = false;
+  bool valid = false;    // inflated, walked and classified
+  std::vector<int64_t> w_off;   // n_rec + 1: record i is data[own + w_off[i] .. own + w_off[i + 1]) (may start in the head: negative)
+  std::vector<uint16_t> w_flag;
+  std::vector<uint32_t> w_lseq, w_prevp;
+  std::vector<uint8_t> w_cls;
+  size_t n_rec = 0;        // records complete in this chunk
+  size_t sel = 0;          // records [0, sel) are consumed
+  int64_t exit_off = 0;    // start of the first record that is not complete here (== total: none)
+  uint64_t rec_base = 0;   // file-order index of record 0
+  std::string walk_err;    // the walk stopped at exit_off on a corrupt block_size
+  std::string prev_qname;  // QNAME of the last primary record before this chunk
+  std::string last_qname;  // ... and of the last one up to its end
 };
 
 struct Bam {
@@ -100,7 +148,6 @@ struct Bam {
   size_t skip_bytes = 0;         // kdf_bam_seek: bytes of the first block that precede the target record
   uint64_t end_coff = ~0ull;     // kdf_bam_set_end: virtual offset (block, offset in block) to stop at
   uint32_t end_in = 0;
-  int last_set_part = -1;        // read-part bit the last parsed record set in seen_parts (-1: none)
   std::string path;
   // collapse state of the FASTA stream (persists across batches)
   std::string cur_qname;
@@ -116,7 +163,25 @@ struct Bam {
   // chunk after it, and the compressed bytes of the one after that
   Chunk cur, next;
   CompBuf ahead, ahead2;
-  std::vector<Kept> kept;   // records of the batch being built
+  bool range_done = false;   // the end of the range (kdf_bam_set_end) has been delivered
+  // scratch of a round (kdf_bam_next_batch): the hand-over of the record walk from block to
+  // block, each thread's record offsets and where a block's records sit in them, the
+  // selection of the consumer
+  std::vector<std::atomic<int64_t>> chain;
+  std::vector<std::vector<int64_t>> tl_off;
+  std::vector<int64_t> fin_off;
+  std::vector<uint32_t> blk_first, blk_count;
+  std::vector<uint16_t> blk_owner;
+  std::vector<uint32_t> s_idx;
+  std::vector<uint64_t> s_start;
+  std::vector<uint8_t> s_fk;
+  std::vector<const uint8_t*> s_sa;
+  // where the decode time goes (seconds of the calling thread; printed by kdf_bam_close when
+  // KDF_BAM_TIMING is set)
+  struct Timing {
+    double rounds = 0, wait = 0, select = 0, fill = 0, index = 0, invalid = 0;
+    uint64_t n_rounds = 0, n_batches = 0, n_reads = 0;
+  } tm;
   uint8_t* get_buf(size_t n, size_t* cap) {
     size_t best = pool.size();
     for (size_t i = 0; i < pool.size(); ++i)
@@ -150,31 +215,40 @@ struct Bam {
     pool.emplace_back(p, cap);
   }
   ~Bam() {
-    if (cur.valid) free(cur.data);
-    if (next.valid) free(next.data);
+    free(cur.data);
+    free(next.data);
     for (auto& e : pool) free(e.first);
   }
 };
 
-bool inflate_block(const uint8_t* src, uint32_t csize, uint8_t* dst, uint32_t usize, bool verify_crc = true) {
+// impl: 0 the library's own decoder (kdf_inflate.cpp), 1 zlib, -1 whichever KDF_BAM_ZLIB says
+bool inflate_block(const uint8_t* src, uint32_t csize, uint8_t* dst, uint32_t usize, bool verify_crc = true,
+                   int impl = -1) {
   // BGZF: 18-byte header (with BC subfield), deflate payload, crc32 + isize
   if (csize < 26) return false;
   uint16_t xlen = (uint16_t)(src[10] | (src[11] << 8));
   uint32_t hdr = 12 + xlen;
-  z_stream zs;
-  memset(&zs, 0, sizeof(zs));
-  if (inflateInit2(&zs, -15) != Z_OK) return false;
-  zs.next_in = const_cast<uint8_t*>(src + hdr);
-  zs.avail_in = csize - hdr - 8;
-  zs.next_out = dst;
-  zs.avail_out = usize;
-  int rc = inflate(&zs, Z_FINISH);
-  inflateEnd(&zs);
-  if (!(rc == Z_STREAM_END && zs.total_out == usize)) return false;
+  if (hdr + 8 > csize) return false;
+  static const bool env_zlib = getenv("KDF_BAM_ZLIB") != nullptr && atoi(getenv("KDF_BAM_ZLIB")) != 0;
+  if (impl < 0) impl = env_zlib ? 1 : 0;
+  if (impl == 0) {
+    if (!kdf::inflate_raw(src + hdr, csize - hdr - 8, dst, usize)) return false;
+  } else {
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -15) != Z_OK) return false;
+    zs.next_in = const_cast<uint8_t*>(src + hdr);
+    zs.avail_in = csize - hdr - 8;
+    zs.next_out = dst;
+    zs.avail_out = usize;
+    int rc = inflate(&zs, Z_FINISH);
+    inflateEnd(&zs);
+    if (!(rc == Z_STREAM_END && zs.total_out == usize)) return false;
+  }
   if (verify_crc) {
     const uint8_t* tl = src + csize - 8;
     uint32_t want = tl[0] | (tl[1] << 8) | (tl[2] << 16) | ((uint32_t)tl[3] << 24);
-    if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, usize) != want) return false;
+    if (kdf::crc32_of(dst, usize) != want) return false;
   }
   return true;
 }
@@ -270,16 +344,15 @@ bool alloc_chunk(Bam* b, const CompBuf& cb, size_t gap, Chunk& c) {
   uint8_t* p = b->get_buf(gap + cb.total_u + 1, &cap);
   if (!p) return false;
   c.data = p;
-  c.begin = gap;
-  c.own = gap;
+  c.own = c.head = gap;
+  c.total = cb.total_u;
   c.ustart = cb.ustart;
-  c.size = gap + cb.total_u;
   c.cap = cap;
   c.valid = false;   // until inflated
   return true;
 }
 
-// Stage 2 (one block; any thread)
+// one block of `cb` into its place in `c` (any thread)
 inline bool inflate_one(const CompBuf& cb, size_t i, Chunk& c, bool verify_crc) {
   const BlockRef& br = cb.blocks[i];
   if (br.usize == 0) return true;
@@ -313,9 +386,15 @@ bool read_chunk(Bam* b, uint64_t want_bytes, std::vector<uint8_t>& out) {
     g_host_err = "BGZF inflate failed (corrupt block or CRC mismatch)";
     return false;
   }
-  out.insert(out.end(), c.data + c.begin, c.data + c.size);
+  out.insert(out.end(), c.data + c.own, c.data + c.own + c.total);
   b->put_buf(c.data, c.cap);
   return true;
+}
+
+inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();
+#endif
 }
 
 inline int32_t rd_i32(const uint8_t* p) {
@@ -475,26 +554,82 @@ static uint64_t invalid_positions(const uint32_t* valid, uint64_t n_bases, uint3
 }
 
 struct kdf_bam_batch_impl {
-  std::vector<uint64_t, NoInitAlloc<uint64_t>> codes;
-  std::vector<uint32_t, NoInitAlloc<uint32_t>> valid;
-  std::vector<uint32_t> invalid;   // positions of the invalid bases (sparse form of `valid`)
-  std::vector<uint64_t> read_starts;
-  std::vector<uint32_t> read_lens;
-  std::vector<uint64_t> rec_index;
-  std::vector<uint64_t> rec_uoff;     // offset of every kept record in the uncompressed stream
-  std::vector<uint8_t> fasta_keep;    // the record is part of the KDF_BAM_FASTA stream
-  std::vector<int32_t> ref_id, pos, next_ref_id, next_pos;
-  std::vector<uint16_t> flag;
-  std::vector<uint8_t> mapq;
-  std::vector<uint64_t> qname_off, cigar_off, sa_off;  // n+1 each
-  std::vector<char> qname_blob, sa_blob;
-  std::vector<uint32_t> cigar_blob;
-  std::vector<uint64_t> raw_off;    // n+1 (want_meta >= 3): the BAM records themselves
-  std::vector<uint8_t> raw_blob;    //   (bytes after block_size), for BAM output
-  std::vector<uint64_t> qual_off;   // n+1 (want_meta >= 2)
-  std::vector<uint8_t> qual_blob;   // Phred base qualities, l_seq bytes per read
+  PodVec<uint64_t> codes;
+  PodVec<uint32_t> valid;
+  PodVec<uint32_t> invalid;   // positions of the invalid bases (sparse form of `valid`)
+  PodVec<uint64_t> read_starts;
+  PodVec<uint32_t> read_lens;
+  PodVec<uint64_t> rec_index;
+  PodVec<uint64_t> rec_uoff;     // offset of every kept record in the uncompressed stream
+  PodVec<uint8_t> fasta_keep;    // the record is part of the KDF_BAM_FASTA stream
+  PodVec<int32_t> ref_id, pos, next_ref_id, next_pos;
+  PodVec<uint16_t> flag;
+  PodVec<uint8_t> mapq;
+  PodVec<uint64_t> qname_off, cigar_off, sa_off;  // n+1 each
+  PodVec<char> qname_blob, sa_blob;
+  PodVec<uint32_t> cigar_blob;
+  PodVec<uint64_t> raw_off;    // n+1 (want_meta >= 3): the BAM records themselves
+  PodVec<uint8_t> raw_blob;    //   (bytes after block_size), for BAM output
+  PodVec<uint64_t> qual_off;   // n+1 (want_meta >= 2)
+  PodVec<uint8_t> qual_blob;   // Phred base qualities, l_seq bytes per read
   uint64_t n_bases = 0;
+  void reset() {
+    codes.clear(), valid.clear(), invalid.clear(), read_starts.clear(), read_lens.clear(), rec_index.clear();
+    rec_uoff.clear(), fasta_keep.clear(), ref_id.clear(), pos.clear(), next_ref_id.clear(), next_pos.clear();
+    flag.clear(), mapq.clear(), qname_off.clear(), cigar_off.clear(), sa_off.clear(), qname_blob.clear();
+    sa_blob.clear(), cigar_blob.clear(), raw_off.clear(), raw_blob.clear(), qual_off.clear(), qual_blob.clear();
+    n_bases = 0;
+  }
+  size_t bytes() const {
+    return codes.cap * 8 + valid.cap * 4 + invalid.cap * 4 + read_starts.cap * 8 + read_lens.cap * 4 +
+           rec_index.cap * 8 + rec_uoff.cap * 8 + fasta_keep.cap + (ref_id.cap + pos.cap + next_ref_id.cap + next_pos.cap) * 4 +
+           flag.cap * 2 + mapq.cap + (qname_off.cap + cigar_off.cap + sa_off.cap + raw_off.cap + qual_off.cap) * 8 +
+           qname_blob.cap + sa_blob.cap + cigar_blob.cap * 4 + raw_blob.cap + qual_blob.cap;
+  }
 };
+
+// Batches handed back (kdf_bam_batch_free) keep their buffers for the next kdf_bam_next_batch
+// of any reader: a fresh page costs a fault (microseconds under virtualisation), a recycled
+// one nothing.  KDF_BAM_POOL_MB bounds what is held (default 4096; 0: no pooling).
+static std::mutex g_impl_mu;
+static std::vector<kdf_bam_batch_impl*> g_impl_pool;
+static size_t g_impl_pool_bytes = 0;
+
+static kdf_bam_batch_impl* impl_get() {
+  {
+    std::lock_guard<std::mutex> lk(g_impl_mu);
+    if (!g_impl_pool.empty()) {
+      // the largest one: it is the least likely to grow again
+      size_t best = 0;
+      for (size_t i = 1; i < g_impl_pool.size(); ++i)
+        if (g_impl_pool[i]->bytes() > g_impl_pool[best]->bytes()) best = i;
+      kdf_bam_batch_impl* im = g_impl_pool[best];
+      g_impl_pool.erase(g_impl_pool.begin() + (long)best);
+      g_impl_pool_bytes -= im->bytes();
+      im->reset();
+      return im;
+    }
+  }
+  return new kdf_bam_batch_impl;
+}
+
+static void impl_put(kdf_bam_batch_impl* im) {
+  if (!im) return;
+  static const size_t limit = [] {
+    const char* e = getenv("KDF_BAM_POOL_MB");
+    return (size_t)(e ? atof(e) : 4096.0) << 20;
+  }();
+  const size_t sz = im->bytes();
+  {
+    std::lock_guard<std::mutex> lk(g_impl_mu);
+    if (g_impl_pool_bytes + sz <= limit && g_impl_pool.size() < 16) {
+      g_impl_pool.push_back(im);
+      g_impl_pool_bytes += sz;
+      return;
+    }
+  }
+  delete im;
+}
 
 extern "C" {
 
@@ -546,6 +681,14 @@ void kdf_bam_close(kdf_bam* h) {
   Bam* b = reinterpret_cast<Bam*>(h);
   if (!b) return;
   if (b->fh) fclose(b->fh);
+  if (getenv("KDF_BAM_TIMING") && b->tm.n_batches) {
+    const Bam::Timing& t = b->tm;
+    fprintf(stderr,
+            "[kdf_bam] %s: %llu reads, %llu batches, %d threads; %llu rounds %.3f s (inflate+walk phase %.3f, "
+            "select+layout %.3f, classify+pack %.3f) finish %.3f invalid-list %.3f\n",
+            b->path.c_str(), (unsigned long long)t.n_reads, (unsigned long long)t.n_batches, b->threads,
+            (unsigned long long)t.n_rounds, t.rounds, t.wait, t.select, t.fill, t.index, t.invalid);
+  }
   delete b;
 }
 
@@ -583,7 +726,7 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
   // no C++ exception may cross the C ABI: an allocation failure (a huge or corrupt
   // input) comes back as an error code
   try {
-    std::unique_ptr<kdf_bam_batch_impl> im(new kdf_bam_batch_impl);
+    std::unique_ptr<kdf_bam_batch_impl, void (*)(kdf_bam_batch_impl*)> im(impl_get(), impl_put);
     int rc = next_batch_impl(b, mode, max_bases, want_meta, out, im.get());
     if (rc == KDF_OK) im.release();   // owned by *out until kdf_bam_batch_free
     return rc;
@@ -598,102 +741,151 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
   return KDF_ERR_ARG;
 }
 
+// ---- the decode pipeline -------------------------------------------------------------
+//
+// One call of kdf_bam_next_batch runs ROUNDS; a round is one OpenMP parallel region over two
+// chunks of ~64 MB of records:
+//
+//   consume(cur)   select (serial, over compact per-record arrays only): the `samtools fasta`
+//                  collapse state, the keep decision, the batch limit; then, by all threads, the
+//                  kept records are packed straight into the batch (2-bit codes + validity,
+//                  fixed fields, QNAME / CIGAR / SA / quality / raw blobs).  A chunk is recycled
+//                  as soon as its records are consumed: nothing is held back until the batch
+//                  is complete.
+//   produce(next)  every thread inflates BGZF blocks (kdf_inflate.cpp) and, while a block is
+//                  still in its cache, continues the RECORD WALK through it: the chain of
+//                  block_size fields is the only way to find BAM records and is inherently
+//                  serial, so it is handed from block to block (chain[i] = where the walk
+//                  enters block i; a thread waits for the walk of the block before — a
+//                  microsecond against the ~50 us of an inflate).  Then, in parallel, each
+//                  record's header is validated and classified (flag, l_seq, "same QNAME as
+//                  the primary record before it").
+//   read(ahead)    one thread reads the compressed bytes of the chunk after that.
+//
+// A record that is not complete in its chunk (it straddles the boundary, or only its
+// block_size field does) is copied into the headroom in front of the next chunk and walked
+// there; what is not consumed (the rest of cur, the produced next, the read-ahead) stays in the
+// reader for the next call.
+
+constexpr uint8_t C_PRIMARY = 1, C_SAME = 2, C_BAD = 4;
+constexpr uint32_t NO_PREV = 0xffffffffu;
+constexpr int64_t CHAIN_WAIT = INT64_MIN, CHAIN_ABORT = INT64_MIN + 1;
+
+static inline const uint8_t* find_sa_tag(const uint8_t* t, const uint8_t* end, size_t* len) {
+  *len = 0;
+  while (t + 3 <= end) {   // walk the aux tags up to the SA:Z tag (a record has one at most)
+    char t0 = (char)t[0], t1 = (char)t[1], ty = (char)t[2];
+    t += 3;
+    size_t adv = 0;
+    switch (ty) {
+      case 'A': case 'c': case 'C': adv = 1; break;
+      case 's': case 'S': adv = 2; break;
+      case 'i': case 'I': case 'f': adv = 4; break;
+      case 'Z': case 'H': {
+        const uint8_t* z = (const uint8_t*)memchr(t, 0, (size_t)(end - t));
+        if (!z) return nullptr;
+        if (t0 == 'S' && t1 == 'A' && ty == 'Z') {
+          *len = (size_t)(z - t);
+          return t;
+        }
+        adv = (size_t)(z - t) + 1;
+        break;
+      }
+      case 'B': {
+        if (t + 5 > end) return nullptr;
+        char sub = (char)t[0];
+        uint32_t cnt;
+        memcpy(&cnt, t + 1, 4);
+        size_t sz = (sub == 'c' || sub == 'C') ? 1 : ((sub == 's' || sub == 'S') ? 2 : 4);
+        adv = 5 + sz * cnt;
+        break;
+      }
+      default: return nullptr;
+    }
+    if (t >= end) break;
+    t += adv;
+  }
+  return nullptr;
+}
+
+static void recycle_chunk(Bam* b, Chunk& c) {
+  if (c.data) b->put_buf(c.data, c.cap);
+  c.data = nullptr;
+  c.cap = 0;
+  c.valid = false;
+  c.n_rec = c.sel = 0;
+}
+
 static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, kdf_bam_batch* out,
                            kdf_bam_batch_impl* im) {
-  // (the vector lives in the reader: its pages stay mapped from batch to batch, a fresh
-  // one cost a page fault per 128 records in the middle of the serial walk)
-  std::vector<Kept>& kept = b->kept;
-  kept.clear();
-  uint64_t n_bases = 0;
-  // The decode is a three-stage pipeline over chunks of ~64 MB of records: while one
-  // thread walks the records of chunk C (a serial chain: every header is a cache miss),
-  // another reads the compressed bytes of chunk C+2 and the rest inflate chunk C+1.
-  // Chunks whose records were kept stay where they are until the batch is packed; a
-  // record that straddles two chunks is completed by copying the unparsed tail of the
-  // old chunk into the headroom in front of the new one.  What is not consumed (the rest
-  // of the current chunk, the look-ahead) stays in the reader for the next batch.
   const uint64_t CHUNK_BYTES = b->chunk_bytes;
   const size_t GAP = b->gap;
-  std::vector<Chunk> retired;
-  auto release_retired = [&]() {
-    for (auto& c : retired) b->put_buf(c.data, c.cap);
-    retired.clear();
-  };
+  const int nthr = b->threads > 0 ? b->threads : 1;
   auto bail = [&](const std::string& msg) {
     g_host_err = msg;
-    release_retired();
     return KDF_ERR_ARG;
   };
-  if (!b->cur.valid) {   // first call: the bytes that followed the header
-    size_t cap = 0;
-    uint8_t* p = b->get_buf(b->carry.size() + 1, &cap);
-    if (!p) return bail("out of memory");
-    if (!b->carry.empty()) memcpy(p, b->carry.data(), b->carry.size());
-    b->cur.data = p;
-    b->cur.begin = 0;
-    b->cur.own = 0;
-    b->cur.ustart = b->first_rec_uoff;
-    b->cur.size = b->carry.size();
-    b->cur.cap = cap;
-    b->cur.valid = true;
-    b->carry.clear();
+  // ---- the batch under construction ----
+  uint64_t n_bases = 0;      // stream bases so far (reads are separated by one invalid base)
+  size_t n_kept = 0;         // reads so far
+  uint64_t words_zeroed = 0; // stream words [0, words_zeroed) are initialised
+  if (max_bases) {           // address space only: pages are touched as the batch grows
+    im->codes.reserve((max_bases + 31) / 32 + 2);
+    im->valid.reserve((max_bases + 31) / 32 + 2);
   }
-  im->rec_index.reserve(kept.capacity());
-  const uint8_t* buf = b->cur.data;
-  size_t buf_size = b->cur.size;
-  size_t off = b->cur.begin;
-  uint64_t cur_ustart = b->cur.ustart;
-  size_t cur_own = b->cur.own;
+  auto grow = [](auto& v, size_t n) { v.resize(n); };   // (amortised, new elements untouched)
+  im->qname_off.assign(1, 0);
+  im->cigar_off.assign(1, 0);
+  im->sa_off.assign(1, 0);
+  im->qual_off.assign(1, 0);
+  im->raw_off.assign(1, 0);
+  // selection of the current round (indices into cur's record arrays)
+  std::vector<uint32_t>& s_idx = b->s_idx;
+  std::vector<uint64_t>& s_start = b->s_start;
+  std::vector<uint8_t>& s_fk = b->s_fk;
+  std::vector<const uint8_t*>& s_sa = b->s_sa;
   bool done = false, hit_limit = false;
   std::string perr, rerr;
-  // stage 3: parse all complete records currently in the chunk
-  auto parse = [&]() {
-    while (true) {
-      if (buf_size - off < 4) break;
-      if (cur_ustart + (uint64_t)off - (uint64_t)cur_own >= b->u_limit) {   // end of this reader's range
+
+  Chunk& cur = b->cur;
+  Chunk& next = b->next;
+  if (b->range_done) {
+    done = true;   // the end of the range was delivered by an earlier call
+    hit_limit = true;
+  }
+
+  // select: the serial part of consume(cur)
+  auto select = [&]() {
+    s_idx.clear();
+    s_start.clear();
+    s_fk.clear();
+    if (!cur.valid) return;
+    const uint8_t* base = cur.data + cur.own;
+    size_t i = cur.sel;
+    for (; i < cur.n_rec; ++i) {
+      const uint64_t uoff = cur.ustart + (uint64_t)cur.w_off[i];   // (two's complement: w_off may be negative)
+      if (uoff >= b->u_limit) {   // end of this reader's range
         hit_limit = true;
         break;
       }
-      int32_t bs = rd_i32(buf + off);
-      if (bs < 32 || bs > (1 << 28)) {
-        perr = "corrupt BAM record (block_size out of range)";
-        return;
-      }
-      if (buf_size - off - 4 < (size_t)bs) break;
-      const uint8_t* r = buf + off + 4;
-      // the walk is a chain of one cache miss per record header: pull the headers of the
-      // records a few hundred bytes ahead (the chunk buffer has slack past its end)
-      __builtin_prefetch(r + bs + 1024);
-      __builtin_prefetch(r + bs + 1088);
-      uint16_t flag = rd_u16(r + 14);
-      uint8_t l_name = r[8];
-      uint16_t n_cig_v = rd_u16(r + 12);
-      int32_t l_seq_s = rd_i32(r + 16);
-      // the variable-length fields must lie inside the record: a corrupt l_seq / n_cigar /
-      // l_read_name would otherwise send the packer (and the metadata pass) out of bounds
-      if (l_seq_s < 0 || 32ull + l_name + 4ull * n_cig_v + ((uint64_t)l_seq_s + 1) / 2 + (uint64_t)l_seq_s >
-                             (uint64_t)bs) {
+      const uint8_t cls = cur.w_cls[i];
+      if (cls & C_BAD) {
         perr = "corrupt BAM record (field sizes exceed the record)";
-        return;
+        break;
       }
-      uint32_t l_seq = (uint32_t)l_seq_s;
+      const uint16_t flag = cur.w_flag[i];
+      const uint32_t l_seq = cur.w_lseq[i];
       // membership of the `samtools fasta -F 0xD00` stream, tracked in every mode (the
       // discovery pipeline decodes the child ONCE in scan mode and masks the counting
       // stream with this flag)
       bool fasta_keep = false;
-      b->last_set_part = -1;
-      if (!(flag & 0xD00)) {
-        const char* qn = (const char*)r + 32;
-        size_t ql = l_name ? (size_t)l_name - 1 : 0;
-        if (b->cur_qname.size() != ql || memcmp(b->cur_qname.data(), qn, ql) != 0) {
-          b->cur_qname.assign(qn, ql);
-          b->seen_parts = 0;
-        }
+      unsigned seen = b->seen_parts;
+      if (cls & C_PRIMARY) {
+        if (!(cls & C_SAME)) seen = 0;
         bool r1 = flag & 0x40, r2 = flag & 0x80;
         unsigned part = (r1 && !r2) ? 1u : ((r2 && !r1) ? 2u : 0u);
-        if (!(b->seen_parts & (1u << part))) {
-          b->seen_parts |= 1u << part;
-          b->last_set_part = (int)part;
+        if (!(seen & (1u << part))) {
+          seen |= 1u << part;
           fasta_keep = true;
         }
       }
@@ -704,159 +896,503 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
         if (flag & 0x500) keep = false;
       }
       // warm-up records of a range (kdf_bam_set_begin): parsed for the QNAME-run state only
-      if (cur_ustart + (uint64_t)off - (uint64_t)cur_own < b->u_begin) keep = false;
+      if (uoff < b->u_begin) keep = false;
       if (keep) {
-        if (max_bases && !kept.empty() && n_bases + l_seq + 1 > max_bases) {
+        if (max_bases && n_kept + s_idx.size() > 0 && n_bases + l_seq + 1 > max_bases) {
           done = true;
-          break;  // leave this record for the next batch
+          break;  // this record waits for the next batch: the collapse state is as before it
         }
-        uint64_t start = kept.empty() ? 0 : n_bases + 1;
-        const uint64_t uoff = cur_ustart + (uint64_t)off - (uint64_t)cur_own;   // off may lie in the tail before `own`
-        kept.push_back({buf + off + 4, start, uoff, l_seq, (uint8_t)(fasta_keep ? 1 : 0)});
+        const uint64_t start = (n_kept + s_idx.size()) ? n_bases + 1 : 0;
+        s_idx.push_back((uint32_t)i);
+        s_start.push_back(start);
+        s_fk.push_back((uint8_t)(fasta_keep ? 1 : 0));
         n_bases = start + l_seq;
-        im->rec_index.push_back(b->record_index);
       }
-      b->record_index++;
-      off += 4 + (size_t)bs;
+      if (cls & C_PRIMARY) b->seen_parts = seen;
     }
+    (void)base;
+    cur.sel = i;
+    if (i == cur.n_rec && !hit_limit && !done && perr.empty() && !cur.walk_err.empty()) perr = cur.walk_err;
   };
-  while (true) {
-    // the compressed blocks of the next chunk must be at hand (read here only when the
-    // pipeline is cold: otherwise stage 1 of the previous round fetched them)
-    if (!b->next.valid && !b->ahead.valid && !b->file_eof) {
+
+  std::vector<std::atomic<int64_t>>& chain = b->chain;
+  std::vector<std::vector<int64_t>>& tl_off = b->tl_off;
+  if ((int)tl_off.size() < nthr) tl_off.resize((size_t)nthr);
+
+  while (!done) {
+    // ---- what this round does ----
+    const bool cur_live = cur.valid && cur.sel < cur.n_rec;
+    if (!b->ahead.valid && !next.valid && !b->file_eof) {   // cold pipeline: nothing read ahead yet
       if (!read_comp(b, CHUNK_BYTES, b->ahead, rerr)) return bail(rerr);
     }
-    const bool do_inflate = !b->next.valid && b->ahead.valid;
-    Chunk nx;
-    if (do_inflate && !alloc_chunk(b, b->ahead, GAP, nx)) return bail("out of memory");
-    const bool do_read = !b->file_eof && (do_inflate || !b->ahead.valid);
+    // (a file whose records all followed the header in its first blocks has no chunk to
+    // inflate: what parse_header left in `carry` is then walked as a chunk of its own)
+    const bool carry_only = !cur.valid && !next.valid && !b->ahead.valid && !b->carry.empty();
+    if (carry_only) {
+      b->ahead.blocks.clear();
+      b->ahead.total_u = 0;
+      b->ahead.ustart = b->u_total;
+    }
+    const bool do_produce = !next.valid && (b->ahead.valid || carry_only);
+    if (!cur_live && !do_produce && !next.valid) {
+      // nothing left anywhere: the file (or what was read of it) ends here
+      if (cur.valid) {
+        if (!cur.walk_err.empty()) return bail(cur.walk_err);
+        if (cur.exit_off < (int64_t)cur.total) return bail("truncated BAM file (incomplete record at the end)");
+      }
+      break;
+    }
+    if (!cur_live && !do_produce) {   // next is ready and cur is spent: step
+      if (cur.valid && !cur.walk_err.empty()) return bail(cur.walk_err);
+      recycle_chunk(b, cur);
+      std::swap(cur, next);
+      continue;
+    }
+    const double t_round = omp_get_wtime();
+    // ---- produce(next): buffer, the straddling bytes in front of it, the chain entry ----
+    long n_blk = 0;
+    if (do_produce) {
+      const uint8_t* tail = nullptr;
+      size_t tail_len = 0;
+      int64_t entry;
+      if (cur.valid) {
+        tail = cur.data + cur.own + cur.exit_off;   // (exit_off may be negative: still in cur's own head)
+        tail_len = (size_t)((int64_t)cur.total - cur.exit_off);
+        entry = -(int64_t)tail_len;
+      } else if (!b->carry.empty()) {   // first chunk of the file: what followed the header
+        tail = b->carry.data();
+        tail_len = b->carry.size();
+        entry = -(int64_t)tail_len;
+      } else {
+        entry = (int64_t)b->skip_bytes;   // after kdf_bam_seek: the record starts inside the first block
+      }
+      const size_t head = tail_len > GAP ? tail_len : GAP;
+      size_t cap = 0;
+      uint8_t* p = b->get_buf(head + b->ahead.total_u + 1, &cap);
+      if (!p) return bail("out of memory");
+      next.data = p;
+      next.cap = cap;
+      next.own = head;
+      next.head = head - tail_len;
+      next.total = b->ahead.total_u;
+      next.ustart = b->ahead.ustart;
+      if (tail_len) memcpy(p + next.head, tail, tail_len);
+      if (!cur.valid) {
+        if (b->skip_bytes) {
+          if (b->ahead.blocks.empty() || b->skip_bytes > b->ahead.blocks[0].usize) {
+            recycle_chunk(b, next);
+            return bail("kdf_bam_seek: offset beyond the end of its block");
+          }
+          b->skip_bytes = 0;
+        }
+        b->carry.clear();
+        next.prev_qname = b->cur_qname;
+        next.rec_base = b->record_index;
+      } else {
+        next.prev_qname = cur.last_qname;
+        next.rec_base = cur.rec_base + cur.n_rec;
+      }
+      n_blk = (long)b->ahead.blocks.size();
+      if (chain.size() < (size_t)n_blk + 1) {
+        std::vector<std::atomic<int64_t>> bigger((size_t)n_blk + 1 + 256);
+        chain.swap(bigger);
+      }
+      for (long i = 0; i <= n_blk; ++i) chain[(size_t)i].store(CHAIN_WAIT, std::memory_order_relaxed);
+      chain[0].store(entry, std::memory_order_relaxed);
+      b->blk_first.assign((size_t)n_blk, 0);
+      b->blk_count.assign((size_t)n_blk, 0);
+      b->blk_owner.assign((size_t)n_blk, 0);
+      for (int t = 0; t < nthr; ++t) tl_off[(size_t)t].clear();
+      next.walk_err.clear();
+    }
     b->ahead2.valid = false;
+    const bool do_read = !b->file_eof && (do_produce || !b->ahead.valid);
     bool read_ok = true;
-    int bad = 0;
-    const long n_blk = do_inflate ? (long)b->ahead.blocks.size() : 0;
-#pragma omp parallel num_threads(b->threads) reduction(| : bad)
+    std::atomic<int> bad{0};   // a block failed to inflate (seen by every thread after the barrier)
+    std::string werr;   // set by the one walker that meets a corrupt block_size
+    size_t round_kept = 0;
+    uint64_t w_first = 0, w_last = 0;   // stream words this round initialises: [w_first, w_last)
+    const CompBuf& cb = b->ahead;
+    uint8_t* const nbase = do_produce ? next.data + next.own : nullptr;
+    const int64_t ntotal = (int64_t)next.total;
+    std::vector<uint64_t> part_sum;   // per-thread partial sums of the variable-length sizes
+    size_t blocks_rec = 0;            // records the block walkers found (the rest: the finishing walk)
+#pragma omp parallel num_threads(nthr)
     {
-#pragma omp single nowait
-      { parse(); }
+      const int tid = omp_get_thread_num();
+      const int team = omp_get_num_threads();
 #pragma omp single nowait
       {
         if (do_read) read_ok = read_comp(b, CHUNK_BYTES, b->ahead2, rerr);
       }
-#pragma omp for schedule(dynamic, 4) nowait
-      for (long i = 0; i < n_blk; ++i)
-        if (!inflate_one(b->ahead, (size_t)i, nx, b->verify_crc)) bad |= 1;
+#pragma omp single nowait
+      {
+        const double t0 = omp_get_wtime();
+        select();
+        b->tm.select += omp_get_wtime() - t0;
+      }
+      // inflate + record walk, block by block
+#pragma omp for schedule(dynamic, 1) nowait
+      for (long i = 0; i < n_blk; ++i) {
+        const BlockRef& br = cb.blocks[(size_t)i];
+        bool ok = true;
+        if (br.usize)
+          ok = inflate_block(cb.bytes.data() + br.coff, br.csize, nbase + br.uoff, br.usize, b->verify_crc);
+        if (!ok) bad.store(1, std::memory_order_relaxed);
+        int64_t o;
+        for (unsigned spins = 0;; ++spins) {
+          o = chain[(size_t)i].load(std::memory_order_acquire);
+          if (o != CHAIN_WAIT) break;
+          if (spins < 2000)
+            cpu_relax();
+          else
+            sched_yield();
+        }
+        if (!ok || o == CHAIN_ABORT) {
+          chain[(size_t)i + 1].store(CHAIN_ABORT, std::memory_order_release);
+          continue;
+        }
+        std::vector<int64_t>& mine = tl_off[(size_t)tid];
+        const size_t first = mine.size();
+        const int64_t u_end = (int64_t)(br.uoff + br.usize);
+        while (o + 4 <= u_end) {
+          const int32_t bs = rd_i32(nbase + o);
+          if (bs < 32 || bs > (1 << 28)) {
+#pragma omp critical(kdf_walk_err)
+            werr = "corrupt BAM record (block_size out of range)";
+            break;   // the chain stops here: `o` is handed on unchanged and nobody can advance it
+          }
+          if (o + 4 + (int64_t)bs > ntotal) break;   // not complete in this chunk: it goes in front of the next
+          mine.push_back(o);
+          o += 4 + (int64_t)bs;
+        }
+        b->blk_owner[(size_t)i] = (uint16_t)tid;
+        b->blk_first[(size_t)i] = (uint32_t)first;
+        b->blk_count[(size_t)i] = (uint32_t)(mine.size() - first);
+        chain[(size_t)i + 1].store(o, std::memory_order_release);
+      }
+#pragma omp barrier
+      // ---- both selections are known: lay out the outputs (one thread), then fill them ----
+#pragma omp single
+      {
+        const double t0 = omp_get_wtime();
+        b->tm.wait += t0 - t_round;
+        if (do_produce && !bad) {
+          const int64_t ex = chain[(size_t)n_blk].load(std::memory_order_acquire);
+          size_t n = 0;
+          for (long i = 0; i < n_blk; ++i) {
+            const uint32_t c = b->blk_count[(size_t)i];
+            b->blk_count[(size_t)i] = (uint32_t)n;   // from here on: index of the block's first record
+            n += c;
+          }
+          // what the last walker could not reach: records that lie entirely in the head (a file
+          // whose records all followed the header in its first blocks), or behind empty blocks
+          b->fin_off.clear();
+          int64_t fo = ex;
+          if (werr.empty())
+            while (fo + 4 <= ntotal) {
+              const int32_t bs = rd_i32(nbase + fo);
+              if (bs < 32 || bs > (1 << 28)) {
+                werr = "corrupt BAM record (block_size out of range)";
+                break;
+              }
+              if (fo + 4 + (int64_t)bs > ntotal) break;
+              b->fin_off.push_back(fo);
+              fo += 4 + (int64_t)bs;
+            }
+          const size_t n_blocks_rec = n;
+          n += b->fin_off.size();
+          next.n_rec = n;
+          next.sel = 0;
+          next.exit_off = fo;
+          next.walk_err = werr;
+          next.w_off.resize(n + 1);
+          next.w_off[n] = fo;
+          if (!b->fin_off.empty())
+            memcpy(next.w_off.data() + n_blocks_rec, b->fin_off.data(), b->fin_off.size() * sizeof(int64_t));
+          blocks_rec = n_blocks_rec;
+          next.w_flag.resize(n);
+          next.w_lseq.resize(n);
+          next.w_cls.resize(n);
+          next.w_prevp.resize(n);
+        }
+        round_kept = s_idx.size();
+        if (round_kept) {
+          const size_t n1 = n_kept + round_kept;
+          grow(im->read_starts, n1);
+          grow(im->read_lens, n1);
+          grow(im->rec_index, n1);
+          grow(im->rec_uoff, n1);
+          grow(im->fasta_keep, n1);
+          if (want_meta) {
+            grow(im->ref_id, n1);
+            grow(im->pos, n1);
+            grow(im->next_ref_id, n1);
+            grow(im->next_pos, n1);
+            grow(im->flag, n1);
+            grow(im->mapq, n1);
+            grow(im->qname_off, n1 + 1);
+            grow(im->cigar_off, n1 + 1);
+            grow(im->sa_off, n1 + 1);
+            if (want_meta >= 2) grow(im->qual_off, n1 + 1);
+            if (want_meta >= 3) grow(im->raw_off, n1 + 1);
+            if (s_sa.size() < round_kept) s_sa.resize(round_kept);
+          }
+          w_first = words_zeroed;
+          w_last = (n_bases + 31) / 32;
+          if (w_last < w_first) w_last = w_first;
+          grow(im->codes, (size_t)w_last + 1);
+          grow(im->valid, (size_t)w_last + 1);
+          words_zeroed = w_last;
+        }
+        part_sum.assign((size_t)team * 5 + 5, 0);
+        b->tm.select += omp_get_wtime() - t0;
+      }
+      // (implicit barrier)
+      const double t_fill = omp_get_wtime();
+      // gather the record offsets of the produced chunk, block by block
+      if (do_produce && !bad) {
+#pragma omp for schedule(static) nowait
+        for (long i = 0; i < n_blk; ++i) {
+          const size_t at = b->blk_count[(size_t)i];
+          const size_t end = (i + 1 < n_blk) ? b->blk_count[(size_t)i + 1] : blocks_rec;
+          const int64_t* src = tl_off[b->blk_owner[(size_t)i]].data() + b->blk_first[(size_t)i];
+          if (end > at) memcpy(next.w_off.data() + at, src, (end - at) * sizeof(int64_t));
+        }
+      }
+      // initialise the stream words this round reaches
+      if (round_kept) {
+        uint64_t* cw = im->codes.data();
+        uint32_t* vw = im->valid.data();
+#pragma omp for schedule(static) nowait
+        for (long w = (long)w_first; w < (long)w_last; ++w) {
+          cw[w] = 0;
+          vw[w] = 0;
+        }
+      }
+#pragma omp barrier
+      // classify the produced records
+      if (do_produce && !bad) {
+        const size_t n = next.n_rec;
+#pragma omp for schedule(static) nowait
+        for (long i = 0; i < (long)n; ++i) {
+          const uint8_t* r = nbase + next.w_off[(size_t)i] + 4;
+          if ((size_t)i + 8 < n) __builtin_prefetch(nbase + next.w_off[(size_t)i + 8] + 4);
+          const uint64_t bs = (uint64_t)(next.w_off[(size_t)i + 1] - next.w_off[(size_t)i]) - 4;
+          const uint16_t flag = rd_u16(r + 14);
+          const uint8_t l_name = r[8];
+          const uint16_t n_cig_v = rd_u16(r + 12);
+          const int32_t l_seq_s = rd_i32(r + 16);
+          uint8_t cls = 0;
+          // the variable-length fields must lie inside the record: a corrupt l_seq / n_cigar /
+          // l_read_name would otherwise send the packer (and the metadata pass) out of bounds
+          if (l_seq_s < 0 ||
+              32ull + l_name + 4ull * n_cig_v + ((uint64_t)l_seq_s + 1) / 2 + (uint64_t)l_seq_s > bs)
+            cls |= C_BAD;
+          else if (!(flag & 0xD00))
+            cls |= C_PRIMARY;
+          next.w_flag[(size_t)i] = flag;
+          next.w_lseq[(size_t)i] = (uint32_t)l_seq_s;
+          next.w_cls[(size_t)i] = cls;
+        }
+      }
+      // pack the selected records of cur: bases, fixed fields, sizes of the variable ones
+      if (round_kept) {
+        const uint8_t* cbase = cur.data + cur.own;
+        uint64_t sums[5] = {0, 0, 0, 0, 0};
+#pragma omp for schedule(static) nowait
+        for (long j = 0; j < (long)round_kept; ++j) {
+          const size_t i = s_idx[(size_t)j];
+          const size_t g = n_kept + (size_t)j;
+          const uint8_t* r = cbase + cur.w_off[i] + 4;
+          if ((size_t)j + 4 < round_kept) __builtin_prefetch(cbase + cur.w_off[s_idx[(size_t)j + 4]] + 4);
+          const uint64_t bs = (uint64_t)(cur.w_off[i + 1] - cur.w_off[i]) - 4;
+          const uint8_t l_name = r[8];
+          const uint16_t n_cig = rd_u16(r + 12);
+          const uint32_t l_seq = cur.w_lseq[i];
+          const uint8_t* nib = r + 32 + l_name + 4 * (size_t)n_cig;
+          pack_record(nib, l_seq, s_start[(size_t)j], im->codes.data(), im->valid.data());
+          im->read_starts[g] = s_start[(size_t)j];
+          im->read_lens[g] = l_seq;
+          im->rec_index[g] = cur.rec_base + i;
+          im->rec_uoff[g] = cur.ustart + (uint64_t)cur.w_off[i];
+          im->fasta_keep[g] = s_fk[(size_t)j];
+          if (want_meta) {
+            im->ref_id[g] = rd_i32(r);
+            im->pos[g] = rd_i32(r + 4);
+            im->mapq[g] = r[9];
+            im->flag[g] = rd_u16(r + 14);
+            im->next_ref_id[g] = rd_i32(r + 20);
+            im->next_pos[g] = rd_i32(r + 24);
+            const uint64_t ql = l_name ? (uint64_t)l_name - 1 : 0;
+            size_t sl = 0;
+            s_sa[(size_t)j] = find_sa_tag(nib + (l_seq + 1) / 2 + l_seq, r + bs, &sl);
+            // (sizes for now; turned into offsets below)
+            im->qname_off[g + 1] = ql;
+            im->cigar_off[g + 1] = n_cig;
+            im->sa_off[g + 1] = sl;
+            sums[0] += ql, sums[1] += n_cig, sums[2] += sl;
+            if (want_meta >= 2) im->qual_off[g + 1] = l_seq, sums[3] += l_seq;
+            if (want_meta >= 3) im->raw_off[g + 1] = bs, sums[4] += bs;
+          }
+        }
+        for (int q = 0; q < 5; ++q) part_sum[(size_t)tid * 5 + q] = sums[q];
+      }
+#pragma omp barrier
+#pragma omp single
+      {
+        if (do_produce && !bad) {   // link every primary record to the one before it
+          uint32_t prev = NO_PREV;
+          std::string& lq = next.last_qname;
+          lq = next.prev_qname;
+          const size_t n = next.n_rec;
+          for (size_t i = 0; i < n; ++i) {
+            if (next.w_cls[i] & C_BAD) break;
+            if (next.w_cls[i] & C_PRIMARY) {
+              next.w_prevp[i] = prev;
+              prev = (uint32_t)i;
+            }
+          }
+          if (prev != NO_PREV) {
+            const uint8_t* r = nbase + next.w_off[prev] + 4;
+            lq.assign((const char*)r + 32, r[8] ? (size_t)r[8] - 1 : 0);
+          }
+        }
+        if (round_kept && want_meta) {   // exclusive prefix of the per-thread sums; blob sizes
+          uint64_t run[5] = {im->qname_off[n_kept], im->cigar_off[n_kept], im->sa_off[n_kept],
+                             want_meta >= 2 ? im->qual_off[n_kept] : 0, want_meta >= 3 ? im->raw_off[n_kept] : 0};
+          for (int t = 0; t < team; ++t)
+            for (int q = 0; q < 5; ++q) {
+              const uint64_t v = part_sum[(size_t)t * 5 + q];
+              part_sum[(size_t)t * 5 + q] = run[q];
+              run[q] += v;
+            }
+          grow(im->qname_blob, (size_t)run[0]);
+          grow(im->cigar_blob, (size_t)run[1]);
+          grow(im->sa_blob, (size_t)run[2]);
+          if (want_meta >= 2) grow(im->qual_blob, (size_t)run[3]);
+          if (want_meta >= 3) grow(im->raw_blob, (size_t)run[4]);
+        }
+      }
+      // (implicit barrier)
+      if (do_produce && !bad) {   // "same QNAME as the primary record before it"
+        const size_t n = next.n_rec;
+#pragma omp for schedule(static) nowait
+        for (long i = 0; i < (long)n; ++i) {
+          if (!(next.w_cls[(size_t)i] & C_PRIMARY)) continue;
+          const uint8_t* r = nbase + next.w_off[(size_t)i] + 4;
+          const char* qn = (const char*)r + 32;
+          const size_t ql = r[8] ? (size_t)r[8] - 1 : 0;
+          bool same;
+          const uint32_t pv = next.w_prevp[(size_t)i];
+          if (pv == NO_PREV) {   // the run may continue from the chunk before
+            same = next.prev_qname.size() == ql && memcmp(next.prev_qname.data(), qn, ql) == 0;
+          } else {
+            const uint8_t* pr = nbase + next.w_off[pv] + 4;
+            const size_t pl = pr[8] ? (size_t)pr[8] - 1 : 0;
+            same = pl == ql && memcmp(pr + 32, qn, ql) == 0;
+          }
+          if (same) next.w_cls[(size_t)i] |= C_SAME;
+        }
+      }
+      if (round_kept && want_meta) {   // sizes -> offsets, and the variable-length pieces to their places
+        const uint8_t* cbase = cur.data + cur.own;
+        uint64_t run[5];
+        for (int q = 0; q < 5; ++q) run[q] = part_sum[(size_t)tid * 5 + q];
+        // (the same static schedule as the sizing loop: thread `tid` sees the same records)
+#pragma omp for schedule(static) nowait
+        for (long j = 0; j < (long)round_kept; ++j) {
+          const size_t i = s_idx[(size_t)j];
+          const size_t g = n_kept + (size_t)j;
+          const uint8_t* r = cbase + cur.w_off[i] + 4;
+          const uint8_t l_name = r[8];
+          const uint16_t n_cig = rd_u16(r + 12);
+          const uint32_t l_seq = cur.w_lseq[i];
+          const uint64_t ql = im->qname_off[g + 1], nc = im->cigar_off[g + 1], sl = im->sa_off[g + 1];
+          if (ql) memcpy(&im->qname_blob[run[0]], r + 32, ql);
+          const uint8_t* cg = r + 32 + l_name;
+          if (nc) memcpy(&im->cigar_blob[run[1]], cg, 4 * (size_t)nc);
+          if (sl) memcpy(&im->sa_blob[run[2]], s_sa[(size_t)j], sl);
+          run[0] += ql, run[1] += nc, run[2] += sl;
+          im->qname_off[g + 1] = run[0];
+          im->cigar_off[g + 1] = run[1];
+          im->sa_off[g + 1] = run[2];
+          if (want_meta >= 2) {
+            if (l_seq) memcpy(&im->qual_blob[run[3]], cg + 4 * (size_t)n_cig + (l_seq + 1) / 2, l_seq);
+            run[3] += l_seq;
+            im->qual_off[g + 1] = run[3];
+          }
+          if (want_meta >= 3) {
+            const uint64_t bs = im->raw_off[g + 1];
+            if (bs) memcpy(&im->raw_blob[run[4]], r, bs);
+            run[4] += bs;
+            im->raw_off[g + 1] = run[4];
+          }
+        }
+      }
+#pragma omp single nowait
+      { b->tm.fill += omp_get_wtime() - t_fill; }
     }
-    if (do_inflate) {
+    b->tm.rounds += omp_get_wtime() - t_round;
+    b->tm.n_rounds++;
+    n_kept += round_kept;
+    if (do_produce) {
       if (bad) {
-        b->put_buf(nx.data, nx.cap);
+        recycle_chunk(b, next);
         return bail("BGZF inflate failed (corrupt block or CRC mismatch)");
       }
-      nx.valid = true;
-      b->next = nx;
+      next.valid = true;
+      b->record_index = next.rec_base + next.n_rec;
       b->ahead.valid = false;
     }
     if (!read_ok) return bail(rerr);
-    if (!perr.empty()) return bail(perr);
     if (do_read && b->ahead2.valid) {   // ahead is free by now (see do_read)
       std::swap(b->ahead, b->ahead2);
       b->ahead2.valid = false;
     }
-    if (done) break;   // batch full: the rest of this chunk and the look-ahead wait in the reader
-    if (hit_limit) break;
-    // this chunk is exhausted but for an incomplete record at its end
-    const size_t tail = buf_size - off;
-    if (!b->next.valid) {
-      if (b->file_eof && !b->ahead.valid) {
-        if (tail) return bail("truncated BAM file (incomplete record at the end)");
-        break;
-      }
-      continue;   // the look-ahead is still to be inflated: go round again
-    }
-    Chunk& nxt = b->next;
-    if (tail <= nxt.begin) {
-      if (tail) memcpy(nxt.data + nxt.begin - tail, buf + off, tail);
-      nxt.begin -= tail;
-    } else {   // a record longer than the headroom: rebuild the next chunk behind the tail
-      size_t cap = 0, n_next = nxt.size - nxt.begin;
-      uint8_t* p = b->get_buf(tail + n_next + 1, &cap);
-      if (!p) return bail("out of memory");
-      memcpy(p, buf + off, tail);
-      memcpy(p + tail, nxt.data + nxt.begin, n_next);
-      b->put_buf(nxt.data, nxt.cap);
-      nxt.own = tail + (nxt.own - nxt.begin);
-      nxt.data = p;
-      nxt.begin = 0;
-      nxt.size = tail + n_next;
-      nxt.cap = cap;
-    }
-    retired.push_back(b->cur);   // kept records point into it: released after packing
-    b->cur = nxt;
-    b->next = Chunk();
-    buf = b->cur.data;
-    buf_size = b->cur.size;
-    off = b->cur.begin;
-    cur_ustart = b->cur.ustart;
-    cur_own = b->cur.own;
-    if (b->skip_bytes) {   // first chunk after kdf_bam_seek: the target record starts inside its first block
-      if (buf_size - off < b->skip_bytes) return bail("kdf_bam_seek: offset beyond the end of its block");
-      off += b->skip_bytes;
-      b->skip_bytes = 0;
+    if (!perr.empty()) return bail(perr);
+    if (hit_limit) {
+      b->range_done = true;
+      break;
     }
   }
-  b->cur.begin = off;
-  b->eof = (b->file_eof && !b->ahead.valid && !b->next.valid) || hit_limit;
-  if (hit_limit) b->cur.begin = b->cur.size;   // nothing more to deliver from this range
-  // A batch limit postponed a record whose parse had already updated the collapse state:
-  // if it set a read-part bit, clear it, so that the record is kept when the next batch
-  // parses it again (its QNAME is then still the current one).
-  if (done && b->last_set_part >= 0) {
-    b->seen_parts &= ~(1u << b->last_set_part);
-    b->last_set_part = -1;
-  }
-  size_t n = kept.size();
-  uint64_t n_words = (n_bases + 31) / 32;
+  // the QNAME of the last primary record consumed is only needed when the pipeline is reset
+  // (kdf_bam_seek clears it); chunks carry it between themselves
+  // (an incomplete record at the end of the file keeps at_eof off: the next call reports it)
+  b->eof = b->range_done ||
+           (b->file_eof && !b->ahead.valid && !next.valid && b->carry.empty() &&
+            (!cur.valid || (cur.sel == cur.n_rec && cur.exit_off == (int64_t)cur.total && cur.walk_err.empty())));
+  const size_t n = n_kept;
+  const uint64_t n_words = (n_bases + 31) / 32;
   im->n_bases = n_bases;
-  // zero-filled by all threads (also the first touch of these pages)
+  double t_st = omp_get_wtime();
+  auto lap = [&](double& acc) {
+    const double t = omp_get_wtime();
+    acc += t - t_st;
+    t_st = t;
+  };
+  if (im->codes.size() < (n_words ? n_words : 1)) {   // (an empty batch)
+    im->codes.assign(1, 0);
+    im->valid.assign(1, 0);
+  }
   im->codes.resize(n_words ? n_words : 1);
   im->valid.resize(n_words ? n_words : 1);
-  {
-    uint64_t* cw = im->codes.data();
-    uint32_t* vw = im->valid.data();
-    const long nw = (long)(n_words ? n_words : 1);
-#pragma omp parallel for schedule(static) num_threads(b->threads)
-    for (long w = 0; w < nw; ++w) {
-      cw[w] = 0;
-      vw[w] = 0;
-    }
-  }
   im->read_starts.resize(n);
   im->read_lens.resize(n);
-#pragma omp parallel for schedule(static) num_threads(b->threads)
-  for (long i = 0; i < (long)n; ++i) {
-    const uint8_t* r = kept[i].rec;
-    uint8_t l_name = r[8];
-    uint16_t n_cig = rd_u16(r + 12);
-    const uint8_t* nib = r + 32 + l_name + 4 * (size_t)n_cig;
-    pack_record(nib, kept[i].l_seq, kept[i].start, im->codes.data(), im->valid.data());
-    im->read_starts[i] = kept[i].start;
-    im->read_lens[i] = kept[i].l_seq;
-  }
+  im->rec_index.resize(n);
   im->rec_uoff.resize(n);
   im->fasta_keep.resize(n);
-  for (size_t i = 0; i < n; ++i) {
-    im->rec_uoff[i] = kept[i].uoff;
-    im->fasta_keep[i] = kept[i].fasta_keep;
-  }
+  lap(b->tm.index);
   if (n_bases <= 0xffffffffull) {   // sparse form of the validity bitmap (kdf_valid_from_invalid)
     // by word ranges: count, prefix, fill
-    const int parts = b->threads > 1 ? b->threads * 4 : 1;
-    const uint64_t wpp = ((n_words + parts - 1) / parts + 0) | 0;
+    const int parts = nthr > 1 ? nthr * 4 : 1;
+    const uint64_t wpp = (n_words + parts - 1) / parts;
     std::vector<uint64_t> cnt(parts + 1, 0);
     auto range = [&](int t, uint64_t* w0, uint64_t* w1) {
       *w0 = (uint64_t)t * wpp < n_words ? (uint64_t)t * wpp : n_words;
       *w1 = (uint64_t)(t + 1) * wpp < n_words ? (uint64_t)(t + 1) * wpp : n_words;
     };
-    auto scan = [&](int t, uint32_t* out) -> uint64_t {
+    auto scan = [&](int t, uint32_t* o) -> uint64_t {
       uint64_t w0, w1, m = 0;
       range(t, &w0, &w1);
       const uint32_t* v = im->valid.data();
@@ -865,131 +1401,24 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
         if (w == n_words - 1 && (n_bases & 31)) inv &= ~0u << (32 - (n_bases & 31));
         while (inv) {
           int bit = __builtin_clz(inv);
-          if (out) out[m] = (uint32_t)(w * 32 + (uint64_t)bit);
+          if (o) o[m] = (uint32_t)(w * 32 + (uint64_t)bit);
           ++m;
           inv &= ~(0x80000000u >> bit);
         }
       }
       return m;
     };
-#pragma omp parallel for schedule(static) num_threads(b->threads)
+#pragma omp parallel for schedule(static) num_threads(nthr)
     for (int t = 0; t < parts; ++t) cnt[t + 1] = scan(t, nullptr);
     for (int t = 0; t < parts; ++t) cnt[t + 1] += cnt[t];
-    im->invalid.resize(cnt[parts] ? cnt[parts] : 1);
-#pragma omp parallel for schedule(static) num_threads(b->threads)
+    grow(im->invalid, cnt[parts] ? cnt[parts] : 1);
+#pragma omp parallel for schedule(static) num_threads(nthr)
     for (int t = 0; t < parts; ++t) scan(t, im->invalid.data() + cnt[t]);
     im->invalid.resize(cnt[parts]);
   }
-  if (want_meta) {
-    im->ref_id.resize(n);
-    im->pos.resize(n);
-    im->next_ref_id.resize(n);
-    im->next_pos.resize(n);
-    im->flag.resize(n);
-    im->mapq.resize(n);
-    im->qname_off.assign(n + 1, 0);
-    im->cigar_off.assign(n + 1, 0);
-    im->sa_off.assign(n + 1, 0);
-    if (want_meta >= 2) im->qual_off.assign(n + 1, 0);
-    if (want_meta >= 3) im->raw_off.assign(n + 1, 0);
-    // pass 1 (parallel): fixed fields, and the size of every variable-length piece
-    std::vector<const uint8_t*> sa_ptr(n, nullptr);
-    auto find_sa = [](const uint8_t* t, const uint8_t* end, size_t* len) -> const uint8_t* {
-      const uint8_t* found = nullptr;
-      *len = 0;
-      while (t + 3 <= end) {   // walk the aux tags up to the SA:Z tag (a record has one at most)
-        char t0 = (char)t[0], t1 = (char)t[1], ty = (char)t[2];
-        t += 3;
-        size_t adv = 0;
-        switch (ty) {
-          case 'A': case 'c': case 'C': adv = 1; break;
-          case 's': case 'S': adv = 2; break;
-          case 'i': case 'I': case 'f': adv = 4; break;
-          case 'Z': case 'H': {
-            const uint8_t* z = (const uint8_t*)memchr(t, 0, (size_t)(end - t));
-            if (!z) return found;
-            if (t0 == 'S' && t1 == 'A' && ty == 'Z') {
-              *len = (size_t)(z - t);
-              return t;
-            }
-            adv = (size_t)(z - t) + 1;
-            break;
-          }
-          case 'B': {
-            if (t + 5 > end) return found;
-            char sub = (char)t[0];
-            uint32_t cnt;
-            memcpy(&cnt, t + 1, 4);
-            size_t sz = (sub == 'c' || sub == 'C') ? 1 : ((sub == 's' || sub == 'S') ? 2 : 4);
-            adv = 5 + sz * cnt;
-            break;
-          }
-          default: return found;
-        }
-        if (t >= end) break;
-        t += adv;
-      }
-      return found;
-    };
-#pragma omp parallel for schedule(static) num_threads(b->threads)
-    for (long i = 0; i < (long)n; ++i) {
-      const uint8_t* r = kept[i].rec;
-      int32_t bs = rd_i32(r - 4);
-      uint8_t l_name = r[8];
-      uint16_t n_cig = rd_u16(r + 12);
-      uint32_t l_seq = kept[i].l_seq;
-      im->ref_id[i] = rd_i32(r);
-      im->pos[i] = rd_i32(r + 4);
-      im->mapq[i] = r[9];
-      im->flag[i] = rd_u16(r + 14);
-      im->next_ref_id[i] = rd_i32(r + 20);
-      im->next_pos[i] = rd_i32(r + 24);
-      im->qname_off[i + 1] = l_name ? (size_t)l_name - 1 : 0;
-      im->cigar_off[i + 1] = n_cig;
-      if (want_meta >= 3) im->raw_off[i + 1] = (uint64_t)bs;
-      if (want_meta >= 2) im->qual_off[i + 1] = l_seq;
-      const uint8_t* t = r + 32 + l_name + 4 * (size_t)n_cig + (l_seq + 1) / 2 + l_seq;
-      size_t sl = 0;
-      sa_ptr[i] = find_sa(t, r + bs, &sl);
-      im->sa_off[i + 1] = sl;
-    }
-    // offsets
-    for (size_t i = 0; i < n; ++i) {
-      im->qname_off[i + 1] += im->qname_off[i];
-      im->cigar_off[i + 1] += im->cigar_off[i];
-      im->sa_off[i + 1] += im->sa_off[i];
-      if (want_meta >= 2) im->qual_off[i + 1] += im->qual_off[i];
-      if (want_meta >= 3) im->raw_off[i + 1] += im->raw_off[i];
-    }
-    im->qname_blob.resize(im->qname_off[n]);
-    im->cigar_blob.resize(im->cigar_off[n]);
-    im->sa_blob.resize(im->sa_off[n]);
-    if (want_meta >= 2) im->qual_blob.resize(im->qual_off[n]);
-    if (want_meta >= 3) im->raw_blob.resize(im->raw_off[n]);
-    // pass 2 (parallel): copy the pieces to their places
-#pragma omp parallel for schedule(static) num_threads(b->threads)
-    for (long i = 0; i < (long)n; ++i) {
-      const uint8_t* r = kept[i].rec;
-      uint8_t l_name = r[8];
-      uint16_t n_cig = rd_u16(r + 12);
-      uint32_t l_seq = kept[i].l_seq;
-      size_t ql = im->qname_off[i + 1] - im->qname_off[i];
-      if (ql) memcpy(&im->qname_blob[im->qname_off[i]], r + 32, ql);
-      const uint8_t* cg = r + 32 + l_name;
-      if (n_cig) memcpy(&im->cigar_blob[im->cigar_off[i]], cg, 4 * (size_t)n_cig);
-      if (want_meta >= 3) {
-        size_t bs = im->raw_off[i + 1] - im->raw_off[i];
-        if (bs) memcpy(&im->raw_blob[im->raw_off[i]], r, bs);
-      }
-      if (want_meta >= 2 && l_seq) {
-        const uint8_t* q = cg + 4 * (size_t)n_cig + (l_seq + 1) / 2;
-        memcpy(&im->qual_blob[im->qual_off[i]], q, l_seq);
-      }
-      size_t sl = im->sa_off[i + 1] - im->sa_off[i];
-      if (sl) memcpy(&im->sa_blob[im->sa_off[i]], sa_ptr[i], sl);
-    }
-  }
-  release_retired();   // packed: nothing points into the retired chunks any more
+  lap(b->tm.invalid);
+  b->tm.n_batches++;
+  b->tm.n_reads += n;
   memset(out, 0, sizeof(*out));
   out->impl = im;
   out->n_reads = n;
@@ -1023,7 +1452,7 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
       out->raw_blob = im->raw_blob.data();
     }
   }
-  out->at_eof = (b->eof && b->cur.begin == b->cur.size) ? 1 : 0;
+  out->at_eof = b->eof ? 1 : 0;
   if (n_bases <= 0xffffffffull) {
     out->invalid_pos = im->invalid.data();
     out->n_invalid = im->invalid.size();
@@ -1048,10 +1477,9 @@ int kdf_bam_seek(kdf_bam* h, uint64_t voffset) {
     g_host_err = "kdf_bam_seek: cannot seek";
     return KDF_ERR_ARG;
   }
-  if (b->cur.valid) b->put_buf(b->cur.data, b->cur.cap);
-  if (b->next.valid) b->put_buf(b->next.data, b->next.cap);
-  b->cur = Chunk();
-  b->next = Chunk();
+  recycle_chunk(b, b->cur);
+  recycle_chunk(b, b->next);
+  b->range_done = false;
   b->ahead.valid = b->ahead2.valid = false;
   b->pending.clear();
   b->carry.clear();
@@ -1061,23 +1489,10 @@ int kdf_bam_seek(kdf_bam* h, uint64_t voffset) {
   b->skip_bytes = (size_t)(voffset & 0xffff);
   b->cur_qname.clear();
   b->seen_parts = 0;
-  b->last_set_part = -1;
   b->u_limit = ~0ull;
   b->u_begin = 0;
   b->begin_coff = ~0ull;
   if (b->end_coff == coff) b->u_limit = b->u_total + b->end_in;   // (empty range)
-  // an empty current chunk whose "own" data starts where the stream continues
-  size_t cap = 0;
-  uint8_t* p = b->get_buf(1, &cap);
-  if (!p) {
-    g_host_err = "out of memory";
-    return KDF_ERR_ARG;
-  }
-  b->cur.data = p;
-  b->cur.begin = b->cur.size = b->cur.own = 0;
-  b->cur.ustart = b->u_total;
-  b->cur.cap = cap;
-  b->cur.valid = true;
   return KDF_OK;
 }
 
@@ -1238,6 +1653,22 @@ int kdf_bam_fetch_records(kdf_bam* h, const uint64_t* uoffs, uint64_t n, uint8_t
 // written in order, then the EOF marker): the container of the BAM and bgzip-VCF
 // outputs.  block_coff (may be NULL) receives the file offset of every block, so that
 // the caller can turn uncompressed offsets into BAI / TBI virtual offsets.
+int kdf_bgzf_inflate_block(const uint8_t* src, uint32_t csize, uint8_t* dst, uint32_t usize, int verify_crc,
+                           int impl) {
+  if (!src || (!dst && usize) || usize > 65536) {
+    g_host_err = "kdf_bgzf_inflate_block: bad argument";
+    return KDF_ERR_ARG;
+  }
+  uint8_t dummy = 0;
+  if (!inflate_block(src, csize, dst ? dst : &dummy, usize, verify_crc != 0, impl ? 1 : 0)) {
+    g_host_err = "BGZF inflate failed (corrupt block or CRC mismatch)";
+    return KDF_ERR_ARG;
+  }
+  return KDF_OK;
+}
+
+uint32_t kdf_crc32(const uint8_t* data, uint64_t n) { return kdf::crc32_of(data, (size_t)n); }
+
 int kdf_bgzf_write(const char* path, const uint8_t* data, uint64_t n, int level, int n_threads,
                    uint64_t* block_coff, uint64_t block_cap, uint64_t* n_blocks) {
   if (!path || (n && !data)) {
@@ -1325,7 +1756,7 @@ uint64_t kdf_invalid_positions(const uint32_t* valid, uint64_t n_bases, uint32_t
 
 void kdf_bam_batch_free(kdf_bam_batch* batch) {
   if (!batch || !batch->impl) return;
-  delete reinterpret_cast<kdf_bam_batch_impl*>(batch->impl);
+  impl_put(reinterpret_cast<kdf_bam_batch_impl*>(batch->impl));
   memset(batch, 0, sizeof(*batch));
 }
 
