@@ -115,6 +115,8 @@ _SIGNATURES = {
     "kdf_bam_set_begin": (_i, [_vp, _u64]),
     "kdf_bam_set_chunk_bytes": (_i, [_vp, _u64]),
     "kdf_bgzf_write": (_i, [ctypes.c_char_p, _vp, _u64, _i, _i, _vp, _u64, _vp]),
+    "kdf_bgzf_inflate_block": (_i, [_vp, ctypes.c_uint32, _vp, ctypes.c_uint32, _i, _i]),
+    "kdf_crc32": (ctypes.c_uint32, [_vp, _u64]),
 }
 
 _lib = None
@@ -661,9 +663,11 @@ class CudaEngine:
         n_words = self.filter_words(n_keys, max_bytes)
         if not n_words:
             raise KdfError("build_filter: %d keys do not fit a filter of %d bytes" % (n_keys, max_bytes))
+        ev = self._t0()
         table.filter_buf = self.zeros(n_words, self.torch.int32)   # kept alive with the table
         self._check(self.lib.kdf_table_build_filter(table.handle, table.filter_buf.data_ptr(), n_words,
                                                     self.stream_ptr()))
+        self._t1("build_filter", ev)
         self.launches += 1
 
     def clear_plane(self, table, plane):
@@ -698,10 +702,12 @@ class CudaEngine:
 
     def update_keys(self, table, lo, hi=None, mode=MODE_INSERT_ONLY, plane=0, arg=1, stats=None):
         n = int(lo.shape[0])
+        ev = self._t0()
         self._check(self.lib.kdf_update_keys(
             table.handle, lo.data_ptr() if n else None,
             hi.data_ptr() if (hi is not None and n) else None, n, mode, plane, arg,
             stats.data_ptr() if stats is not None else None, self.stream_ptr()))
+        self._t1("update_keys/mode%d" % mode, ev)
         if n:
             self.launches += 1
 
@@ -766,10 +772,12 @@ class CudaEngine:
         p0 = self.zeros(max(n, 1), torch.int32) if want_planes else None
         p1 = self.zeros(max(n, 1), torch.int32) if want_planes else None
         if n:
+            ev = self._t0()
             self._check(self.lib.kdf_lookup_keys(
                 table.handle, lo.data_ptr(), hi.data_ptr() if hi is not None else None, n,
                 found.data_ptr(), p0.data_ptr() if p0 is not None else None,
                 p1.data_ptr() if p1 is not None else None, self.stream_ptr()))
+            self._t1("lookup_keys", ev)
             self.launches += 1
         return found[:n], (p0[:n] if p0 is not None else None), (p1[:n] if p1 is not None else None)
 
