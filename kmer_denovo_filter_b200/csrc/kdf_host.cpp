@@ -816,11 +816,28 @@ static void recycle_chunk(Bam* b, Chunk& c) {
   c.n_rec = c.sel = 0;
 }
 
+static std::atomic<int> g_active_decoders{0};   // readers inside kdf_bam_next_batch right now
+
 static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, kdf_bam_batch* out,
                            kdf_bam_batch_impl* im) {
   const uint64_t CHUNK_BYTES = b->chunk_bytes;
   const size_t GAP = b->gap;
-  const int nthr = b->threads > 0 ? b->threads : 1;
+  const int nthr = b->threads > 0 ? b->threads : 1;   // the most a round may use
+  // Several readers decode at once (the discovery pipeline runs the child and both parents
+  // together): each round then takes its share of the cores instead of every reader
+  // starting a full team (three teams on one set of cores spend their time in barriers
+  // and in the hand-over of the record walk).
+  struct ActiveGuard {
+    ActiveGuard() { g_active_decoders.fetch_add(1, std::memory_order_relaxed); }
+    ~ActiveGuard() { g_active_decoders.fetch_sub(1, std::memory_order_relaxed); }
+  } active_guard;
+  static const int n_procs = omp_get_num_procs() > 0 ? omp_get_num_procs() : 1;
+  auto team_size = [&]() {
+    const int act = g_active_decoders.load(std::memory_order_relaxed);
+    int t = act > 1 ? (n_procs + act - 1) / act : nthr;
+    if (t < 2) t = 2;
+    return t < nthr ? t : nthr;
+  };
   auto bail = [&](const std::string& msg) {
     g_host_err = msg;
     return KDF_ERR_ARG;
@@ -1017,7 +1034,7 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
     const int64_t ntotal = (int64_t)next.total;
     std::vector<uint64_t> part_sum;   // per-thread partial sums of the variable-length sizes
     size_t blocks_rec = 0;            // records the block walkers found (the rest: the finishing walk)
-#pragma omp parallel num_threads(nthr)
+#pragma omp parallel num_threads(team_size())
     {
       const int tid = omp_get_thread_num();
       const int team = omp_get_num_threads();
