@@ -1014,7 +1014,10 @@ def run_discovery_pipeline(args, engine=None):
             timings["total_s"] = time.monotonic() - start
     # the parents are decoded in the background while the child is read and counted (bounded
     # look-ahead: two batches each)
+    # ... and the child's decode (what the first GPU stage waits for) starts before the
+    # reference index is built
     if os.environ.get("KDF_PREFETCH_PARENTS", "1") != "0":
+        kw.start_prefetch(args.child, bamio.MODE_SCAN, threads, True)
         kw.start_prefetch(args.mother, bamio.MODE_FASTA, threads)
         kw.start_prefetch(args.father, bamio.MODE_FASTA, threads)
     try:
