@@ -300,9 +300,9 @@ class BamReader:
     def fetch(self, tid, beg, end, want_meta=2, mode=MODE_ALL):
         """Batches holding every record of reference ``tid`` that overlaps ``[beg, end)``
         (and possibly a few more around it) — ``pysam.AlignmentFile.fetch`` through the
-        .bai linear index: the decode starts at the first record of the 16 kbp window that
-        holds ``beg`` (minus the longest plausible alignment) and stops at the first batch
-        that lies wholly past ``end``.  Needs ``<bam>.bai``."""
+        .bai linear index: the decode starts at the first record that overlaps the 16 kbp
+        window holding ``beg`` and stops at the first batch that lies wholly past ``end``.
+        Needs ``<bam>.bai``."""
         if getattr(self, "_bai", None) is None:
             bai = find_bai(self.path)
             if bai is None:
@@ -314,13 +314,15 @@ class BamReader:
         lin = self._bai[tid]["linear"]
         if lin.shape[0] == 0:
             return
-        # a record overlapping `beg` starts at most one read length (or a long deletion) before
-        # it: go back one window further than the one holding beg
-        w = max(min(int(beg) >> 14, lin.shape[0] - 1) - 1, 0)
-        voff = int(lin[w])
-        while voff == 0 and w + 1 < lin.shape[0] and (w + 1) <= (int(beg) >> 14):
-            w += 1
+        # SAM spec 5.1.3: the linear index holds, per 16 kbp window, the smallest offset of the
+        # alignments that OVERLAP the window — so a record that starts before `beg` and
+        # reaches it is at or after the entry of beg's window.  Windows nothing overlaps are 0
+        # (samtools) or repeat a neighbour: take the first non-empty one the region touches.
+        voff = 0
+        for w in range(min(int(beg) >> 14, lin.shape[0] - 1), min(max(int(end) - 1, int(beg)) >> 14, lin.shape[0] - 1) + 1):
             voff = int(lin[w])
+            if voff:
+                break
         if voff == 0:
             return
         self.seek(voff)

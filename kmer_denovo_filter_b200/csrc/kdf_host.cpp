@@ -266,7 +266,10 @@ bool read_comp(Bam* b, uint64_t want_bytes, CompBuf& cb, std::string& err) {
   cb.valid = false;
   comp.insert(comp.end(), b->pending.begin(), b->pending.end());
   b->pending.clear();
-  const size_t SLAB = 8u << 20;
+  // file reads: 8 MB at a time for a sequential pass, about one chunk's worth for region
+  // fetches (kdf_bam_set_chunk_bytes of a few hundred KB) — what is read past the chunk is
+  // copied to `pending` and back, which for an 8 MB slab cost more than the fetch itself
+  const size_t SLAB = want_bytes / 2 > (8u << 20) ? (8u << 20) : (want_bytes / 2 < (128u << 10) ? (128u << 10) : (size_t)(want_bytes / 2));
   auto refill = [&]() -> bool {
     size_t at = comp.size();
     comp.resize(at + SLAB);
@@ -832,11 +835,16 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
     ~ActiveGuard() { g_active_decoders.fetch_sub(1, std::memory_order_relaxed); }
   } active_guard;
   static const int n_procs = omp_get_num_procs() > 0 ? omp_get_num_procs() : 1;
-  auto team_size = [&]() {
+  auto team_size = [&](long blocks, size_t records) {
     const int act = g_active_decoders.load(std::memory_order_relaxed);
     int t = act > 1 ? (n_procs + act - 1) / act : nthr;
     if (t < 2) t = 2;
-    return t < nthr ? t : nthr;
+    if (t > nthr) t = nthr;
+    // a region fetch inflates a handful of blocks per round: a full team would spend the
+    // round in its barriers
+    const long work = blocks / 16 + (long)(records / 16384);   // (~1 ms of work per thread at least)
+    if (work < t) t = work < 1 ? 1 : (int)work;
+    return t;
   };
   auto bail = [&](const std::string& msg) {
     g_host_err = msg;
@@ -1034,7 +1042,7 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
     const int64_t ntotal = (int64_t)next.total;
     std::vector<uint64_t> part_sum;   // per-thread partial sums of the variable-length sizes
     size_t blocks_rec = 0;            // records the block walkers found (the rest: the finishing walk)
-#pragma omp parallel num_threads(team_size())
+#pragma omp parallel num_threads(team_size(n_blk, cur_live ? cur.n_rec - cur.sel : 0))
     {
       const int tid = omp_get_thread_num();
       const int team = omp_get_num_threads();
@@ -1402,7 +1410,8 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
   lap(b->tm.index);
   if (n_bases <= 0xffffffffull) {   // sparse form of the validity bitmap (kdf_valid_from_invalid)
     // by word ranges: count, prefix, fill
-    const int parts = nthr > 1 ? nthr * 4 : 1;
+    const int thr_inv = team_size((long)(n_words >> 12), 0);   // (a small batch is not worth a team)
+    const int parts = thr_inv > 1 ? thr_inv * 4 : 1;
     const uint64_t wpp = (n_words + parts - 1) / parts;
     std::vector<uint64_t> cnt(parts + 1, 0);
     auto range = [&](int t, uint64_t* w0, uint64_t* w1) {
@@ -1425,11 +1434,11 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
       }
       return m;
     };
-#pragma omp parallel for schedule(static) num_threads(nthr)
+#pragma omp parallel for schedule(static) num_threads(thr_inv)
     for (int t = 0; t < parts; ++t) cnt[t + 1] = scan(t, nullptr);
     for (int t = 0; t < parts; ++t) cnt[t + 1] += cnt[t];
     grow(im->invalid, cnt[parts] ? cnt[parts] : 1);
-#pragma omp parallel for schedule(static) num_threads(nthr)
+#pragma omp parallel for schedule(static) num_threads(thr_inv)
     for (int t = 0; t < parts; ++t) scan(t, im->invalid.data() + cnt[t]);
     im->invalid.resize(cnt[parts]);
   }
