@@ -838,6 +838,14 @@ __device__ __forceinline__ u32 resolve_packed_mark(const TableView<KW>& t, u32 b
 // and the latencies of a chunk would add up: key load (DRAM) -> bucket load (L2) ->
 // CAS.  The loop is therefore software-pipelined three deep: while chunk A is
 // resolved, the bucket loads of chunk B and the key loads of chunk C are in flight.
+// up to KEY_SEGS key arrays consumed by one k_packed_keys launch (see there)
+constexpr int KEY_SEGS = 16;
+struct KeySegs {
+  const u64* lo[KEY_SEGS];
+  const u64* n_dev[KEY_SEGS];   // device count of the segment, or NULL (= n_max)
+  int n;
+};
+
 template <int KW> __device__ __forceinline__ Key<KW> ld_key_pinned(const u64* lo, u64 i);
 template <> __device__ __forceinline__ Key<1> ld_key_pinned<1>(const u64* lo, u64 i) {
   Key<1> k;
@@ -965,17 +973,18 @@ template <int KW, int OP>
 using PackedKeysQueue = typename std::conditional<OP == OP_PACKED_COUNT, PackedQueues<KW>, SlowQueue<KW>>::type;
 
 template <int KW, int OP, bool FILT>
-__global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_packed_keys(TableView<KW> t, const u64* lo, u64 n_max,
-                                                     const u64* n_dev, int sh, u32 sat, u64* stats,
+__global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_packed_keys(TableView<KW> t, const __grid_constant__ KeySegs segs, u64 n_max,
+                                                     int sh, u32 sat, u64* stats,
                                                      int filt_log2, u32 filt_val) {
+  // The keys come as segs.n segments (one per sending rank of a multi-GPU run; one
+  // otherwise): a single launch walks them all — a launch per ~6 M-key segment cost ~8 us
+  // of ramp each, 544 launches per count at 8 GPUs.  The segment table stays in the
+  // kernel's parameter space (constant bank), so it costs the 128-register kernel nothing.
   constexpr int CHUNK = KW == 2 ? 2 : KDF_KEYS_CHUNK;   // two bucket sets live in registers
   constexpr int S = SPB<KW>::v;
   const u64 mask = (1ull << sh) - 1;
-  u64 n = n_max;
-  if (n_dev) {
-    u64 nd = *n_dev;
-    n = nd < n_max ? nd : n_max;
-  }
+  const u64* lo = nullptr;
+  u64 n = 0;
   using Queue = PackedKeysQueue<KW, OP>;
   extern __shared__ __align__(16) unsigned char pk_smem[];   // one queue per warp
   Queue& q = reinterpret_cast<Queue*>(pk_smem)[threadIdx.x >> 5];
@@ -991,7 +1000,7 @@ __global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_packed_keys(TableView<
   LocalStats st = {0, 0, 0, 0};
   HitSink sink = {nullptr, nullptr, 0, nullptr};
   const u64 stride = (u64)gridDim.x * blockDim.x;
-  const u64 n_iter = (n + stride * CHUNK - 1) / (stride * CHUNK);   // warp-uniform (see k_stream)
+  u64 n_iter = 0;   // warp-uniform (see k_stream); set per segment below
   const u64 first = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 
   Key<KW> kA[CHUNK], kB[CHUNK], kC[CHUNK];
@@ -1104,22 +1113,32 @@ __global__ void __launch_bounds__(256, KDF_KEYS_BLOCKS) k_packed_keys(TableView<
     }
   };
 
-  mA = load_keys(0, kA);
-  mB = load_keys(1, kB);
-  load_buckets(kA, mA, iA, bA);
-  for (u64 itn = 0; itn < n_iter; ++itn) {
-    mC = load_keys(itn + 2, kC);
-    load_buckets(kB, mB, iB, bB);
-    resolve(kA, mA, iA, bA);
-#pragma unroll
-    for (int u = 0; u < CHUNK; ++u) {
-      kA[u] = kB[u];
-      bA[u] = bB[u];
-      iA[u] = iB[u];
-      kB[u] = kC[u];
+#pragma unroll 1
+  for (int seg = 0; seg < segs.n; ++seg) {
+    lo = segs.lo[seg];
+    n = n_max;
+    if (segs.n_dev[seg]) {
+      const u64 nd = *segs.n_dev[seg];
+      n = nd < n_max ? nd : n_max;
     }
-    mA = mB;
-    mB = mC;
+    n_iter = (n + stride * CHUNK - 1) / (stride * CHUNK);
+    mA = load_keys(0, kA);
+    mB = load_keys(1, kB);
+    load_buckets(kA, mA, iA, bA);
+    for (u64 itn = 0; itn < n_iter; ++itn) {
+      mC = load_keys(itn + 2, kC);
+      load_buckets(kB, mB, iB, bB);
+      resolve(kA, mA, iA, bA);
+#pragma unroll
+      for (int u = 0; u < CHUNK; ++u) {
+        kA[u] = kB[u];
+        bA[u] = bB[u];
+        iA[u] = iB[u];
+        kB[u] = kC[u];
+      }
+      mA = mB;
+      mB = mC;
+    }
   }
   if constexpr (OP == OP_PACKED_COUNT) {
     tally_packed(st, pq_drain<KW>(&q, t, sh, sat, true));
@@ -2150,22 +2169,31 @@ static int launch_emit_buckets(const kdf_table* t, u32 min0, u32 max0, u32 min1,
 
 template <int KW, int OP>
 static int launch_packed_keys(const kdf_table* t, const u64* lo, u64 n_max, const u64* n_dev, int sh,
-                              u32 sat, u64* stats, cudaStream_t st, int filt_log2, u32 filt_val) {
+                              u32 sat, u64* stats, cudaStream_t st, int filt_log2, u32 filt_val,
+                              int n_src = 1, u64 src_stride = 0, u64 cur_stride = 0) {
   TableView<KW> tv = view_of_table<KW>(t);
   const size_t smem = sizeof(PackedKeysQueue<KW, OP>) * (256 / 32);
   const u64 items = (n_max + KDF_KEYS_CHUNK - 1) / KDF_KEYS_CHUNK;
-  if (filt_log2 > 0) {
-    const void* fn = (const void*)k_packed_keys<KW, OP, true>;
-    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int g = grid_for(fn, 256, smem, items, t->sm_count);
-    k_packed_keys<KW, OP, true><<<g, 256, smem, st>>>(tv, lo, n_max, n_dev, sh, sat, stats, filt_log2, filt_val);
-  } else {
-    const void* fn = (const void*)k_packed_keys<KW, OP, false>;
-    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int g = grid_for(fn, 256, smem, items, t->sm_count);
-    k_packed_keys<KW, OP, false><<<g, 256, smem, st>>>(tv, lo, n_max, n_dev, sh, sat, stats, 0, 0);
+  for (int s0 = 0; s0 < n_src; s0 += KEY_SEGS) {
+    KeySegs segs;
+    segs.n = n_src - s0 < KEY_SEGS ? n_src - s0 : KEY_SEGS;
+    for (int i = 0; i < KEY_SEGS; ++i) {
+      segs.lo[i] = i < segs.n ? lo + (u64)(s0 + i) * src_stride : nullptr;
+      segs.n_dev[i] = (i < segs.n && n_dev) ? n_dev + (u64)(s0 + i) * cur_stride : nullptr;
+    }
+    if (filt_log2 > 0) {
+      const void* fn = (const void*)k_packed_keys<KW, OP, true>;
+      CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int g = grid_for(fn, 256, smem, items, t->sm_count);
+      k_packed_keys<KW, OP, true><<<g, 256, smem, st>>>(tv, segs, n_max, sh, sat, stats, filt_log2, filt_val);
+    } else {
+      const void* fn = (const void*)k_packed_keys<KW, OP, false>;
+      CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int g = grid_for(fn, 256, smem, items, t->sm_count);
+      k_packed_keys<KW, OP, false><<<g, 256, smem, st>>>(tv, segs, n_max, sh, sat, stats, 0, 0);
+    }
+    CUDA_TRY(cudaGetLastError());
   }
-  CUDA_TRY(cudaGetLastError());
   return KDF_OK;
 }
 
@@ -2889,25 +2917,23 @@ int kdf_count_bins_pass(int k, int n_parts, int n_src, int sub_split, int pass_l
     }
     for (int pf = 0; pf < n_parts * sub_split; ++pf) {
       const int p = pf / sub_split;
-      for (int sidx = 0; sidx < n_src; ++sidx) {
-        u64 b = (u64)sidx * n_parts + p;
-        const u64* cb = (const u64*)child_bins + b * child_bin_cap * kw;
+      {   // bins are laid out [source][hash range][bin_cap]: one launch walks bin p of every source
+        const u64* cb = (const u64*)child_bins + (u64)p * child_bin_cap * kw;
+        const u64 sstride = (u64)n_parts * child_bin_cap * kw;
         if (kw == 1)
-          rc = launch_packed_keys<1, OP_PACKED_COUNT>(&t, cb, child_bin_cap, (const u64*)child_cursors + b, sh, sat, ctr, st, filt_log2, pass_base + (u32)pf);
+          rc = launch_packed_keys<1, OP_PACKED_COUNT>(&t, cb, child_bin_cap, (const u64*)child_cursors + p, sh, sat, ctr, st, filt_log2, pass_base + (u32)pf, n_src, sstride, (u64)n_parts);
         else
-          rc = launch_packed_keys<2, OP_PACKED_COUNT>(&t, cb, child_bin_cap, (const u64*)child_cursors + b, sh, sat, ctr, st, filt_log2, pass_base + (u32)pf);
+          rc = launch_packed_keys<2, OP_PACKED_COUNT>(&t, cb, child_bin_cap, (const u64*)child_cursors + p, sh, sat, ctr, st, filt_log2, pass_base + (u32)pf, n_src, sstride, (u64)n_parts);
         if (rc != KDF_OK) return rc;
       }
       if (ref_bins && ref_cursors && !ignore_ref) {
-        for (int sidx = 0; sidx < n_src; ++sidx) {
-          u64 b = (u64)sidx * n_parts + p;
-          const u64* rb = (const u64*)ref_bins + b * ref_bin_cap * kw;
-          if (kw == 1)
-            rc = launch_packed_keys<1, OP_PACKED_MARK>(&t, rb, ref_bin_cap, (const u64*)ref_cursors + b, sh, sat, nullptr, st, filt_log2, pass_base + (u32)pf);
-          else
-            rc = launch_packed_keys<2, OP_PACKED_MARK>(&t, rb, ref_bin_cap, (const u64*)ref_cursors + b, sh, sat, nullptr, st, filt_log2, pass_base + (u32)pf);
-          if (rc != KDF_OK) return rc;
-        }
+        const u64* rb = (const u64*)ref_bins + (u64)p * ref_bin_cap * kw;
+        const u64 sstride = (u64)n_parts * ref_bin_cap * kw;
+        if (kw == 1)
+          rc = launch_packed_keys<1, OP_PACKED_MARK>(&t, rb, ref_bin_cap, (const u64*)ref_cursors + p, sh, sat, nullptr, st, filt_log2, pass_base + (u32)pf, n_src, sstride, (u64)n_parts);
+        else
+          rc = launch_packed_keys<2, OP_PACKED_MARK>(&t, rb, ref_bin_cap, (const u64*)ref_cursors + p, sh, sat, nullptr, st, filt_log2, pass_base + (u32)pf, n_src, sstride, (u64)n_parts);
+        if (rc != KDF_OK) return rc;
       }
       if (kw == 1)
         rc = launch_emit_packed<1>(&t, sh, sat, ignore_ref, count_all, (u64*)out_lo, (u64*)out_hi, out_cap, (u64*)n_out, ctr + 4, ctr + 5, st);
