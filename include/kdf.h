@@ -433,6 +433,18 @@ uint64_t kdf_pack_sequences(const char* seqs, const uint64_t* offsets,
                             uint64_t n_seqs, uint64_t* codes, uint32_t* valid,
                             uint64_t* read_offsets);
 
+/* A whole FASTA text (HOST memory, e.g. the reference genome) into the stream layout,
+ * multi-threaded: header lines (">...") are dropped, line ends and blanks inside the
+ * sequence lines skipped, records separated by one invalid base — what
+ * `jellyfish count -C ref.fa` sees of the file (reference: kmer_utils.py / discovery
+ * pipeline.py:286-332 build ref.k31.jf from it).  kdf_fasta_layout gives the number of
+ * records and the stream length so that the caller can allocate codes / valid
+ * ((n_bases+31)/32 words each, at least one) and seq_starts / seq_lens (n_seqs).   */
+int kdf_fasta_layout(const uint8_t* text /*HOST*/, uint64_t n, int n_threads, uint64_t* n_seqs,
+                     uint64_t* n_bases);
+int kdf_fasta_pack(const uint8_t* text /*HOST*/, uint64_t n, int n_threads, uint64_t* codes /*HOST*/,
+                   uint32_t* valid /*HOST*/, uint64_t* seq_starts /*HOST*/, uint64_t* seq_lens /*HOST*/);
+
 /* ---- host BGZF/BAM decode -> packed batches (CPU, multi-threaded) --------
  * Replaces, for BAM input, `samtools fasta -F 0xD00` in front of Jellyfish
  * (core/jellyfish_wrappers.py:159-165; discovery/pipeline.py:106-112, 369-375)

@@ -278,8 +278,7 @@ def _ensure_ref_jf(ref_fasta, kmer_size, threads, ref_jf=None, engine=None):
         # extracted on the device, so it wins when both are given (the reference prefers the .jf)
         logger.info("Reference index %s ignored: the k-mers are taken from %s", ref_jf, ref_fasta)
     logger.info("Packing reference FASTA: %s (k=%d)", ref_fasta, kmer_size)
-    _names, seqs = bamio.read_fasta_sequences(ref_fasta)
-    hs = _engine.pack_sequences(seqs)
+    hs, _n_records = _engine.pack_fasta_file(ref_fasta, threads)   # (all host threads, in the library)
     return RefIndex(kmer_size, host_stream=hs, source=ref_fasta)
 
 

@@ -1679,6 +1679,161 @@ int kdf_bam_fetch_records(kdf_bam* h, const uint64_t* uoffs, uint64_t n, uint8_t
 // written in order, then the EOF marker): the container of the BAM and bgzip-VCF
 // outputs.  block_coff (may be NULL) receives the file offset of every block, so that
 // the caller can turn uncompressed offsets into BAI / TBI virtual offsets.
+// ---- reference FASTA -> packed stream ------------------------------------------------------
+// The reference genome as one stream (sequences separated by an invalid base), packed by all
+// threads: header lines are located, the sequence bytes are cut into blocks, every block counts
+// its bases (pass 1) and, once the prefix sums give its place in the stream, packs them (pass 2).
+namespace {
+struct FastaLayout {
+  std::vector<uint64_t> seq_beg, seq_end;   // byte range of each record's sequence lines
+  struct Block {
+    uint64_t beg, end;   // bytes
+    uint32_t seq;
+    uint64_t bases;      // non-whitespace bytes in it
+    uint64_t pos;        // stream position of its first base
+  };
+  std::vector<Block> blocks;
+  std::vector<uint64_t> seq_len, seq_start;
+  uint64_t total = 0;
+};
+inline bool fasta_skip(uint8_t c) { return c == '\n' || c == '\r' || c == ' ' || c == '\t' || c == '\v' || c == '\f'; }
+
+void fasta_layout(const uint8_t* text, uint64_t n, int threads, FastaLayout& L) {
+  // header lines: '>' at the start of a line
+  const uint64_t SCAN = 4u << 20;
+  const long n_scan = (long)((n + SCAN - 1) / SCAN);
+  std::vector<std::vector<uint64_t>> found((size_t)(n_scan > 0 ? n_scan : 1));
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+  for (long b = 0; b < n_scan; ++b) {
+    const uint64_t lo = (uint64_t)b * SCAN, hi = lo + SCAN < n ? lo + SCAN : n;
+    const uint8_t* p = text + lo;
+    while (p < text + hi) {
+      const uint8_t* q = (const uint8_t*)memchr(p, '>', (size_t)(text + hi - p));
+      if (!q) break;
+      if (q == text || q[-1] == '\n') found[(size_t)b].push_back((uint64_t)(q - text));
+      p = q + 1;
+    }
+  }
+  std::vector<uint64_t> hdr;
+  for (auto& v : found) hdr.insert(hdr.end(), v.begin(), v.end());
+  const size_t ns = hdr.size();
+  L.seq_beg.resize(ns);
+  L.seq_end.resize(ns);
+  for (size_t j = 0; j < ns; ++j) {
+    const uint8_t* nl = (const uint8_t*)memchr(text + hdr[j], '\n', (size_t)(n - hdr[j]));
+    L.seq_beg[j] = nl ? (uint64_t)(nl - text) + 1 : n;
+    L.seq_end[j] = j + 1 < ns ? hdr[j + 1] : n;
+  }
+  const uint64_t BLK = 1u << 20;
+  L.blocks.clear();
+  for (size_t j = 0; j < ns; ++j)
+    for (uint64_t o = L.seq_beg[j]; o < L.seq_end[j]; o += BLK)
+      L.blocks.push_back({o, o + BLK < L.seq_end[j] ? o + BLK : L.seq_end[j], (uint32_t)j, 0, 0});
+  const long nb = (long)L.blocks.size();
+#pragma omp parallel for schedule(dynamic, 4) num_threads(threads)
+  for (long i = 0; i < nb; ++i) {
+    FastaLayout::Block& k = L.blocks[(size_t)i];
+    uint64_t c = 0;
+    for (uint64_t o = k.beg; o < k.end; ++o) c += fasta_skip(text[o]) ? 0 : 1;
+    k.bases = c;
+  }
+  L.seq_len.assign(ns, 0);
+  L.seq_start.assign(ns, 0);
+  for (auto& k : L.blocks) L.seq_len[k.seq] += k.bases;
+  uint64_t p = 0;
+  for (size_t j = 0; j < ns; ++j) {
+    L.seq_start[j] = p;
+    p += L.seq_len[j] + 1;
+  }
+  L.total = ns ? p - 1 : 0;
+  uint32_t cur = ~0u;
+  uint64_t at = 0;
+  for (auto& k : L.blocks) {
+    if (k.seq != cur) cur = k.seq, at = L.seq_start[cur];
+    k.pos = at;
+    at += k.bases;
+  }
+}
+}  // namespace
+
+int kdf_fasta_layout(const uint8_t* text, uint64_t n, int n_threads, uint64_t* n_seqs, uint64_t* n_bases) {
+  if ((!text && n) || !n_seqs || !n_bases) {
+    g_host_err = "kdf_fasta_layout: NULL argument";
+    return KDF_ERR_ARG;
+  }
+  try {
+    FastaLayout L;
+    fasta_layout(text, n, n_threads > 0 ? n_threads : 1, L);
+    *n_seqs = L.seq_len.size();
+    *n_bases = L.total;
+    return KDF_OK;
+  } catch (const std::exception& e) {
+    g_host_err = std::string("kdf_fasta_layout: ") + e.what();
+    return KDF_ERR_ARG;
+  }
+}
+
+int kdf_fasta_pack(const uint8_t* text, uint64_t n, int n_threads, uint64_t* codes, uint32_t* valid,
+                   uint64_t* seq_starts, uint64_t* seq_lens) {
+  if ((!text && n) || !codes || !valid || !seq_starts || !seq_lens) {
+    g_host_err = "kdf_fasta_pack: NULL argument";
+    return KDF_ERR_ARG;
+  }
+  static const struct Lut {
+    uint8_t v[256];
+    Lut() {
+      memset(v, 4, sizeof(v));
+      v[(int)'A'] = v[(int)'a'] = 0;
+      v[(int)'C'] = v[(int)'c'] = 1;
+      v[(int)'G'] = v[(int)'g'] = 2;
+      v[(int)'T'] = v[(int)'t'] = 3;
+    }
+  } lut;
+  try {
+    const int threads = n_threads > 0 ? n_threads : 1;
+    FastaLayout L;
+    fasta_layout(text, n, threads, L);
+    for (size_t j = 0; j < L.seq_len.size(); ++j) seq_starts[j] = L.seq_start[j], seq_lens[j] = L.seq_len[j];
+    const long n_words = (long)((L.total + 31) / 32);
+#pragma omp parallel for schedule(static) num_threads(threads)
+    for (long w = 0; w < (n_words ? n_words : 1); ++w) codes[w] = 0, valid[w] = 0;
+    const long nb = (long)L.blocks.size();
+#pragma omp parallel for schedule(dynamic, 4) num_threads(threads)
+    for (long i = 0; i < nb; ++i) {
+      const FastaLayout::Block& k = L.blocks[(size_t)i];
+      if (!k.bases) continue;
+      uint64_t p = k.pos;
+      const uint64_t first_w = p >> 5, last_w = (p + k.bases - 1) >> 5;
+      uint64_t cw = 0;
+      uint32_t vw = 0;
+      for (uint64_t o = k.beg; o < k.end; ++o) {
+        const uint8_t ch = text[o];
+        if (fasta_skip(ch)) continue;
+        const uint8_t c = lut.v[ch];
+        if (c < 4) {
+          cw |= (uint64_t)c << (62 - 2 * (p & 31));
+          vw |= 1u << (31 - (p & 31));
+        }
+        if ((p & 31) == 31) {   // the word is complete
+          const uint64_t w = p >> 5;
+          or_word64(codes + w, cw, w == first_w || w == last_w);
+          or_word32(valid + w, vw, w == first_w || w == last_w);
+          cw = 0, vw = 0;
+        }
+        ++p;
+      }
+      if (p & 31) {   // the last, partial word (shared with what follows)
+        or_word64(codes + (p >> 5), cw, true);
+        or_word32(valid + (p >> 5), vw, true);
+      }
+    }
+    return KDF_OK;
+  } catch (const std::exception& e) {
+    g_host_err = std::string("kdf_fasta_pack: ") + e.what();
+    return KDF_ERR_ARG;
+  }
+}
+
 int kdf_bgzf_inflate_block(const uint8_t* src, uint32_t csize, uint8_t* dst, uint32_t usize, int verify_crc,
                            int impl) {
   if (!src || (!dst && usize) || usize > 65536) {

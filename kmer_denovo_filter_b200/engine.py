@@ -117,6 +117,8 @@ _SIGNATURES = {
     "kdf_bgzf_write": (_i, [ctypes.c_char_p, _vp, _u64, _i, _i, _vp, _u64, _vp]),
     "kdf_bgzf_inflate_block": (_i, [_vp, ctypes.c_uint32, _vp, ctypes.c_uint32, _i, _i]),
     "kdf_crc32": (ctypes.c_uint32, [_vp, _u64]),
+    "kdf_fasta_layout": (_i, [_vp, _u64, _i, _vp, _vp]),
+    "kdf_fasta_pack": (_i, [_vp, _u64, _i, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -224,6 +226,41 @@ def pack_sequences(seqs):
     assert got == total
     return HostStream(codes[:n_words], valid[:n_words], total,
                       read_offsets[:n].copy(), lens.astype(np.uint32)).with_sparse_validity()
+
+
+def pack_fasta_file(path, threads=None):
+    """The sequences of a (possibly gzip-compressed) FASTA file as one :class:`HostStream`
+    (records separated by an invalid base), packed by the library with all host threads
+    (``kdf_fasta_pack``).  → ``(HostStream, n_records)``."""
+    lib = load_library()
+    if path.endswith(".gz"):
+        import gzip
+        with gzip.open(path, "rb") as fh:
+            text = np.frombuffer(fh.read(), dtype=np.uint8)
+    else:
+        text = np.fromfile(path, dtype=np.uint8)
+    if threads is None:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    n = int(text.shape[0])
+    tp = _np_ptr(text) if n else None
+    n_seqs, n_bases = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    if lib.kdf_fasta_layout(tp, n, int(threads), ctypes.byref(n_seqs), ctypes.byref(n_bases)) != KDF_OK:
+        raise KdfError(lib.kdf_host_last_error().decode())
+    ns, total = int(n_seqs.value), int(n_bases.value)
+    n_words = (total + 31) // 32
+    codes = np.empty(max(n_words, 1), dtype=np.uint64)
+    valid = np.empty(max(n_words, 1), dtype=np.uint32)
+    starts = np.zeros(max(ns, 1), dtype=np.uint64)
+    lens = np.zeros(max(ns, 1), dtype=np.uint64)
+    if lib.kdf_fasta_pack(tp, n, int(threads), _np_ptr(codes), _np_ptr(valid), _np_ptr(starts),
+                          _np_ptr(lens)) != KDF_OK:
+        raise KdfError(lib.kdf_host_last_error().decode())
+    hs = HostStream(codes[:n_words], valid[:n_words], total, starts[:ns].copy(),
+                    lens[:ns].astype(np.uint32)).with_sparse_validity()
+    return hs, ns
 
 
 def debug_extract_host(hs, k, random_access=False):
