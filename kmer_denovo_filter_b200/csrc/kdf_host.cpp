@@ -598,14 +598,17 @@ static std::mutex g_impl_mu;
 static std::vector<kdf_bam_batch_impl*> g_impl_pool;
 static size_t g_impl_pool_bytes = 0;
 
-static kdf_bam_batch_impl* impl_get() {
+static kdf_bam_batch_impl* impl_get(size_t hint_bytes) {
   {
     std::lock_guard<std::mutex> lk(g_impl_mu);
     if (!g_impl_pool.empty()) {
-      // the largest one: it is the least likely to grow again
+      // the smallest one that is likely to hold the batch (a region fetch should not take the
+      // buffers of a whole-file batch away from the decoder running beside it), else the largest
       size_t best = 0;
-      for (size_t i = 1; i < g_impl_pool.size(); ++i)
-        if (g_impl_pool[i]->bytes() > g_impl_pool[best]->bytes()) best = i;
+      for (size_t i = 1; i < g_impl_pool.size(); ++i) {
+        const size_t a = g_impl_pool[i]->bytes(), c = g_impl_pool[best]->bytes();
+        if (c >= hint_bytes ? (a >= hint_bytes && a < c) : a > c) best = i;
+      }
       kdf_bam_batch_impl* im = g_impl_pool[best];
       g_impl_pool.erase(g_impl_pool.begin() + (long)best);
       g_impl_pool_bytes -= im->bytes();
@@ -729,7 +732,7 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
   // no C++ exception may cross the C ABI: an allocation failure (a huge or corrupt
   // input) comes back as an error code
   try {
-    std::unique_ptr<kdf_bam_batch_impl, void (*)(kdf_bam_batch_impl*)> im(impl_get(), impl_put);
+    std::unique_ptr<kdf_bam_batch_impl, void (*)(kdf_bam_batch_impl*)> im(impl_get(max_bases ? (size_t)(max_bases / 32) * 12 : SIZE_MAX), impl_put);
     int rc = next_batch_impl(b, mode, max_bases, want_meta, out, im.get());
     if (rc == KDF_OK) im.release();   // owned by *out until kdf_bam_batch_free
     return rc;

@@ -97,9 +97,20 @@ def main():
         else:
             open(p, "wb").write(comp[:rng.randrange(1, len(comp))])
         mode, meta = rng.choice([(0, 0), (1, 1), (2, 2), (2, 3)])
+        # KDF_FUZZ_CMD: an AddressSanitizer build of scripts/asan_bam_decode.cpp decodes the file
+        # instead of the Python child (same "ok" / "kdferror" protocol), with a random chunk
+        # size, headroom and thread count
+        cmd = [sys.executable, "-c", CHILD, p, str(mode), str(meta)]
+        env = dict(os.environ)
+        if os.environ.get("KDF_FUZZ_CMD"):
+            cmd = [os.environ["KDF_FUZZ_CMD"], p, str(mode), str(meta), str(rng.choice([1, 2, 3, 8])),
+                   str(rng.choice([0, 50_000, 1_000_000]))]
+            env["ASAN_OPTIONS"] = "detect_leaks=0"
+            if rng.random() < 0.7:
+                env["KDF_BAM_CHUNK_KB"] = str(rng.choice([64, 65, 100, 300, 1000]))
+                env["KDF_BAM_GAP"] = str(rng.choice([0, 1, 17, 300, 5000]))
         try:
-            r = subprocess.run([sys.executable, "-c", CHILD, p, str(mode), str(meta)], capture_output=True,
-                               text=True, timeout=60)
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=120, env=env)
         except subprocess.TimeoutExpired:
             print("HANG", kind, mode, meta)
             sys.exit(1)
