@@ -51,16 +51,28 @@ template <class T> struct NoInitAlloc : std::allocator<T> {
 
 // A growable array of plain values for the batch outputs: resize() leaves new elements
 // uninitialised (they are written by the parallel fill loops, which is also what first touches
-// their pages) and growth goes through realloc(), which moves large blocks by remapping
-// their pages instead of copying them.  (std::vector value-initialises and copies on
-// growth: on one thread, that was a third of the decode time.)
+// their pages).  From 256 KB up the storage is its own anonymous mapping grown with mremap(),
+// which moves pages instead of copying them — malloc/realloc copies (and faults in the copy,
+// on the one thread that lays a round out) until a block passes glibc's moving mmap
+// threshold of up to 32 MB.  (std::vector value-initialises and copies on every growth.)
 template <class T> struct PodVec {
   T* p = nullptr;
   size_t n = 0, cap = 0;
+  bool mapped = false;
+  static constexpr size_t MAP_FROM = 256u << 10;
   PodVec() = default;
   PodVec(const PodVec&) = delete;
   PodVec& operator=(const PodVec&) = delete;
-  ~PodVec() { free(p); }
+  ~PodVec() { release(); }
+  void release() {
+    if (mapped)
+      munmap(p, cap * sizeof(T));
+    else
+      free(p);
+    p = nullptr;
+    n = cap = 0;
+    mapped = false;
+  }
   T* data() { return p; }
   const T* data() const { return p; }
   size_t size() const { return n; }
@@ -70,8 +82,25 @@ template <class T> struct PodVec {
   const T& operator[](size_t i) const { return p[i]; }
   void reserve(size_t want) {
     if (want <= cap) return;
-    if (want > SIZE_MAX / sizeof(T)) throw std::bad_alloc();
-    void* q = realloc(p, want * sizeof(T));
+    if (want > SIZE_MAX / sizeof(T) - 4096) throw std::bad_alloc();
+    size_t bytes = want * sizeof(T);
+    if (bytes >= MAP_FROM) {
+      bytes = (bytes + 4095) & ~(size_t)4095;
+      void* q;
+      if (mapped) {
+        q = mremap(p, cap * sizeof(T), bytes, MREMAP_MAYMOVE);
+      } else {
+        q = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (q != MAP_FAILED && n) memcpy(q, p, n * sizeof(T));
+      }
+      if (q == MAP_FAILED) throw std::bad_alloc();
+      if (!mapped) free(p);
+      p = (T*)q;
+      cap = bytes / sizeof(T);
+      mapped = true;
+      return;
+    }
+    void* q = realloc(p, bytes);
     if (!q) throw std::bad_alloc();
     p = (T*)q;
     cap = want;
@@ -598,17 +627,24 @@ static std::mutex g_impl_mu;
 static std::vector<kdf_bam_batch_impl*> g_impl_pool;
 static size_t g_impl_pool_bytes = 0;
 
-static kdf_bam_batch_impl* impl_get(size_t hint_bytes) {
+static kdf_bam_batch_impl* impl_get(size_t hint_bytes, bool want_meta) {
   {
     std::lock_guard<std::mutex> lk(g_impl_mu);
     if (!g_impl_pool.empty()) {
-      // the smallest one that is likely to hold the batch (a region fetch should not take the
+      // one of the same kind (with / without the metadata arrays) if there is one; among those
+      // the smallest that is likely to hold the batch (a region fetch should not take the
       // buffers of a whole-file batch away from the decoder running beside it), else the largest
-      size_t best = 0;
-      for (size_t i = 1; i < g_impl_pool.size(); ++i) {
-        const size_t a = g_impl_pool[i]->bytes(), c = g_impl_pool[best]->bytes();
-        if (c >= hint_bytes ? (a >= hint_bytes && a < c) : a > c) best = i;
-      }
+      size_t best = SIZE_MAX;
+      for (int any_kind = 0; any_kind < 2 && best == SIZE_MAX; ++any_kind)
+        for (size_t i = 0; i < g_impl_pool.size(); ++i) {
+          if (!any_kind && (g_impl_pool[i]->ref_id.cap > 0) != want_meta) continue;
+          if (best == SIZE_MAX) {
+            best = i;
+            continue;
+          }
+          const size_t a = g_impl_pool[i]->bytes(), c = g_impl_pool[best]->bytes();
+          if (c >= hint_bytes ? (a >= hint_bytes && a < c) : a > c) best = i;
+        }
       kdf_bam_batch_impl* im = g_impl_pool[best];
       g_impl_pool.erase(g_impl_pool.begin() + (long)best);
       g_impl_pool_bytes -= im->bytes();
@@ -732,7 +768,7 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
   // no C++ exception may cross the C ABI: an allocation failure (a huge or corrupt
   // input) comes back as an error code
   try {
-    std::unique_ptr<kdf_bam_batch_impl, void (*)(kdf_bam_batch_impl*)> im(impl_get(max_bases ? (size_t)(max_bases / 32) * 12 : SIZE_MAX), impl_put);
+    std::unique_ptr<kdf_bam_batch_impl, void (*)(kdf_bam_batch_impl*)> im(impl_get(max_bases ? (size_t)(max_bases / 32) * 12 : SIZE_MAX, want_meta != 0), impl_put);
     int rc = next_batch_impl(b, mode, max_bases, want_meta, out, im.get());
     if (rc == KDF_OK) im.release();   // owned by *out until kdf_bam_batch_free
     return rc;
