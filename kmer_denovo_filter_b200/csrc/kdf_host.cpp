@@ -181,16 +181,18 @@ struct Bam {
   uint64_t u_total = 0, c_total = 0;
   std::vector<std::pair<uint64_t, uint64_t>> blk_index;
   uint64_t first_rec_uoff = 0;   // uncompressed offset of the first record (= header size)
-  uint64_t u_limit = ~0ull;      // deliver no record at or past this uncompressed offset (kdf_bam_set_end)
-  uint64_t u_begin = 0;          // records before this offset only update the QNAME-run state (kdf_bam_set_begin)
+  // (atomics: the read-ahead thread sets them when it reaches the block, while the consumer
+  // of an earlier chunk is looking at them)
+  std::atomic<uint64_t> u_limit{~0ull};   // deliver no record at or past this uncompressed offset (kdf_bam_set_end)
+  std::atomic<uint64_t> u_begin{0};       // records before this offset only update the QNAME-run state (kdf_bam_set_begin)
   uint64_t begin_coff = ~0ull;
   uint32_t begin_in = 0;
   size_t skip_bytes = 0;         // kdf_bam_seek: bytes of the first block that precede the target record
   uint64_t end_coff = ~0ull;     // kdf_bam_set_end: virtual offset (block, offset in block) to stop at
   uint32_t end_in = 0;
   std::string path;
-  // collapse state of the FASTA stream (persists across batches)
-  std::string cur_qname;
+  // collapse state of the FASTA stream (persists across batches): the read parts seen in the
+  // current run of same-QNAME primary records (the QNAMEs themselves travel with the chunks)
   unsigned seen_parts = 0;
   // inflate buffers, recycled across chunks and batches: plain malloc memory (no
   // zero-fill, no growth copies) whose pages stay mapped once touched
@@ -977,11 +979,10 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
     s_start.clear();
     s_fk.clear();
     if (!cur.valid) return;
-    const uint8_t* base = cur.data + cur.own;
     size_t i = cur.sel;
     for (; i < cur.n_rec; ++i) {
       const uint64_t uoff = cur.ustart + (uint64_t)cur.w_off[i];   // (two's complement: w_off may be negative)
-      if (uoff >= b->u_limit) {   // end of this reader's range
+      if (uoff >= b->u_limit.load(std::memory_order_relaxed)) {   // end of this reader's range
         hit_limit = true;
         break;
       }
@@ -1013,7 +1014,7 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
         if (flag & 0x500) keep = false;
       }
       // warm-up records of a range (kdf_bam_set_begin): parsed for the QNAME-run state only
-      if (uoff < b->u_begin) keep = false;
+      if (uoff < b->u_begin.load(std::memory_order_relaxed)) keep = false;
       if (keep) {
         if (max_bases && n_kept + s_idx.size() > 0 && n_bases + l_seq + 1 > max_bases) {
           done = true;
@@ -1027,7 +1028,6 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
       }
       if (cls & C_PRIMARY) b->seen_parts = seen;
     }
-    (void)base;
     cur.sel = i;
     if (i == cur.n_rec && !hit_limit && !done && perr.empty() && !cur.walk_err.empty()) perr = cur.walk_err;
   };
@@ -1103,7 +1103,7 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
           b->skip_bytes = 0;
         }
         b->carry.clear();
-        next.prev_qname = b->cur_qname;
+        next.prev_qname.clear();   // nothing precedes the first chunk of a file / of a seek
         next.rec_base = b->record_index;
       } else {
         next.prev_qname = cur.last_qname;
@@ -1605,7 +1605,6 @@ int kdf_bam_seek(kdf_bam* h, uint64_t voffset) {
   b->eof = false;
   b->c_total = coff;
   b->skip_bytes = (size_t)(voffset & 0xffff);
-  b->cur_qname.clear();
   b->seen_parts = 0;
   b->u_limit = ~0ull;
   b->u_begin = 0;

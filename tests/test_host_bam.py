@@ -387,3 +387,36 @@ def test_region_fetch_equals_a_linear_filter(giab_paths, giab_records):
                         got.append((rec.query_name, int(b.flag[i]), int(start[i])))
                 b.close()
             assert sorted(got) == want and want, names[tid]
+
+
+def test_concurrent_readers_equal_sequential(giab_paths):
+    """Three readers decoding at once (what the discovery pipeline does with child, mother and
+    father: they share the cores and the batch-buffer pool) deliver what each delivers alone."""
+    import hashlib
+    import threading
+
+    def digest(path, mode, meta, out, key):
+        h = hashlib.sha256()
+        n = 0
+        with bamio.BamReader(path, threads=4) as rd:
+            for b in rd.batches(mode, max_bases=400_000, want_meta=meta):
+                for name in ("codes", "valid", "invalid", "read_starts", "read_lens", "rec_index", "rec_uoff",
+                             "fasta_keep") + (("pos", "flag", "qname_blob", "cigar_blob") if meta else ()):
+                    h.update(np.ascontiguousarray(getattr(b, name)).tobytes())
+                n += b.n_reads
+                b.close()
+        out[key] = (n, h.hexdigest())
+
+    jobs = [("child", bamio.MODE_SCAN, True), ("mother", bamio.MODE_FASTA, False), ("father", bamio.MODE_FASTA, False)]
+    alone = {}
+    for who, mode, meta in jobs:
+        digest(giab_paths[who], mode, meta, alone, who)
+    for _round in range(3):
+        together = {}
+        ths = [threading.Thread(target=digest, args=(giab_paths[who], mode, meta, together, who))
+               for who, mode, meta in jobs]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        assert together == alone
