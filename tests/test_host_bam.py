@@ -420,3 +420,48 @@ def test_concurrent_readers_equal_sequential(giab_paths):
         for t in ths:
             t.join()
         assert together == alone
+
+
+@pytest.mark.parametrize("chunk_kb,gap,threads,block_payload", [
+    (None, None, 4, 60000), (64, 0, 3, 60000), (100, 17, 8, 777), (300, 5000, 1, 65280), (64, 1, 2, 10_000)])
+def test_long_and_tiny_records_across_blocks_and_chunks(tmp_path, monkeypatch, chunk_kb, gap, threads, block_payload):
+    """Records from 40 bytes to 400 KB (long reads: one record spans many BGZF blocks and more
+    than a pipeline chunk), block sizes that cut block_size fields in two: the chained record
+    walk must hand every record on intact."""
+    import random
+    rng = random.Random(7)
+    recs, want = [], []
+    for i in range(260):
+        n = rng.choice([0, 1, 2, 31, 150, 151, 1000, 20_000, 70_000, 200_000 if i % 40 == 0 else 300])
+        seq = "".join(rng.choice("ACGTN" if i % 7 == 0 else "ACGT") for _ in range(n))
+        flag = rng.choice([0, 0x10, 0x41, 0x81, 0x100, 0x400, 0x800, 0x4])
+        name = "read%d" % (i // 2 if i % 5 else i)      # some runs of equal QNAMEs
+        cigar = [(0, n)] if n and not (flag & 0x4) else []
+        recs.append(obam.encode_record(0, 100 + i, name, flag, 60, cigar, seq,
+                                       qual=bytes(rng.randrange(0, 42) for _ in range(n))))
+        want.append((name, flag, seq))
+    p = str(tmp_path / "long.bam")
+    obam.write_bam(p, ["chr1"], [10_000_000], recs, block_payload=block_payload)
+    if chunk_kb is not None:
+        monkeypatch.setenv("KDF_BAM_CHUNK_KB", str(chunk_kb))
+        monkeypatch.setenv("KDF_BAM_GAP", str(gap))
+    for max_bases in (0, 50_000):
+        got = []
+        with bamio.BamReader(p, threads=threads) as rd:
+            for b in rd.batches(bamio.MODE_ALL, max_bases=max_bases, want_meta=3):
+                for i in range(b.n_reads):
+                    r = b.record(i)
+                    got.append((r.query_name, r.flag, r.query_sequence or ""))
+                    assert bytes(b.raw_blob[int(b.raw_off[i]):int(b.raw_off[i + 1])]) == recs[len(got) - 1][4:]
+                b.close()
+        assert got == want
+    # the `samtools fasta` view of the same file against the oracle's collapse rule
+    orecs = obam.read_bam(p)[2] if hasattr(obam, "read_bam") else None
+    if orecs is not None:
+        keep = obam.fasta_stream(orecs)
+        with bamio.BamReader(p, threads=threads) as rd:
+            names = []
+            for b in rd.batches(bamio.MODE_FASTA, max_bases=80_000, want_meta=True):
+                names += [b.record(i).query_name for i in range(b.n_reads)]
+                b.close()
+        assert names == [r.qname for r in keep]
