@@ -58,6 +58,16 @@ template <class T> struct NoInitAlloc : std::allocator<T> {
 // which moves pages instead of copying them — malloc/realloc copies (and faults in the copy,
 // on the one thread that lays a round out) until a block passes glibc's moving mmap
 // threshold of up to 32 MB.  (std::vector value-initialises and copies on every growth.)
+// Test hook: KDF_BAM_FAIL_ALLOC=n makes the n-th growth of a batch buffer fail, so that the
+// out-of-memory paths (also the ones inside the OpenMP region) can be exercised.
+inline void maybe_fail_alloc() {
+  static const long fail_at = getenv("KDF_BAM_FAIL_ALLOC") ? atol(getenv("KDF_BAM_FAIL_ALLOC")) : 0;
+  if (fail_at > 0) {
+    static std::atomic<long> calls{0};
+    if (calls.fetch_add(1, std::memory_order_relaxed) + 1 == fail_at) throw std::bad_alloc();
+  }
+}
+
 inline bool thp_wanted() {   // KDF_BAM_THP=1: ask for transparent huge pages for the large buffers
   static const bool on = getenv("KDF_BAM_THP") != nullptr && atoi(getenv("KDF_BAM_THP")) != 0;
   return on;
@@ -90,6 +100,7 @@ template <class T> struct PodVec {
   const T& operator[](size_t i) const { return p[i]; }
   void reserve(size_t want) {
     if (want <= cap) return;
+    maybe_fail_alloc();
     if (want > SIZE_MAX / sizeof(T) - 4096) throw std::bad_alloc();
     size_t bytes = want * sizeof(T);
     if (bytes >= MAP_FROM) {
@@ -1125,8 +1136,11 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
     b->ahead2.valid = false;
     const bool do_read = !b->file_eof && (do_produce || !b->ahead.valid);
     bool read_ok = true;
-    std::atomic<int> bad{0};   // a block failed to inflate (seen by every thread after the barrier)
-    std::string werr;   // set by the one walker that meets a corrupt block_size
+    // bit 0: a block failed to inflate; bit 1: an allocation failed inside the region (no C++
+    // exception may leave an OpenMP construct) — seen by every thread after the barrier
+    std::atomic<int> bad{0};
+    std::atomic<int> walk_corrupt{0};   // a walker met a corrupt block_size
+    std::string werr;
     size_t round_kept = 0;
     uint64_t w_first = 0, w_last = 0;   // stream words this round initialises: [w_first, w_last)
     const CompBuf& cb = b->ahead;
@@ -1140,12 +1154,21 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
       const int team = omp_get_num_threads();
 #pragma omp single nowait
       {
-        if (do_read) read_ok = read_comp(b, CHUNK_BYTES, b->ahead2, rerr);
+        try {
+          if (do_read) read_ok = read_comp(b, CHUNK_BYTES, b->ahead2, rerr);
+        } catch (...) {
+          read_ok = false;
+          rerr = "out of memory while reading the BAM";
+        }
       }
 #pragma omp single nowait
       {
         const double t0 = omp_get_wtime();
-        select();
+        try {
+          select();
+        } catch (...) {
+          bad.fetch_or(2, std::memory_order_relaxed);
+        }
         b->tm.select += omp_get_wtime() - t0;
       }
       // inflate + record walk, block by block
@@ -1155,7 +1178,7 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
         bool ok = true;
         if (br.usize)
           ok = inflate_block(cb.bytes.data() + br.coff, br.csize, nbase + br.uoff, br.usize, b->verify_crc);
-        if (!ok) bad.store(1, std::memory_order_relaxed);
+        if (!ok) bad.fetch_or(1, std::memory_order_relaxed);
         int64_t o;
         for (unsigned spins = 0;; ++spins) {
           o = chain[(size_t)i].load(std::memory_order_acquire);
@@ -1172,17 +1195,24 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
         std::vector<int64_t>& mine = tl_off[(size_t)tid];
         const size_t first = mine.size();
         const int64_t u_end = (int64_t)(br.uoff + br.usize);
-        while (o + 4 <= u_end) {
-          const int32_t bs = rd_i32(nbase + o);
-          if (bs < 32 || bs > (1 << 28)) {
-#pragma omp critical(kdf_walk_err)
-            werr = "corrupt BAM record (block_size out of range)";
-            break;   // the chain stops here: `o` is handed on unchanged and nobody can advance it
+        bool corrupt = false;
+        try {
+          while (o + 4 <= u_end) {
+            const int32_t bs = rd_i32(nbase + o);
+            if (bs < 32 || bs > (1 << 28)) {
+              corrupt = true;
+              break;   // the chain stops here: `o` is handed on unchanged and nobody can advance it
+            }
+            if (o + 4 + (int64_t)bs > ntotal) break;   // not complete in this chunk: it goes in front of the next
+            mine.push_back(o);
+            o += 4 + (int64_t)bs;
           }
-          if (o + 4 + (int64_t)bs > ntotal) break;   // not complete in this chunk: it goes in front of the next
-          mine.push_back(o);
-          o += 4 + (int64_t)bs;
+        } catch (...) {
+          bad.fetch_or(2, std::memory_order_relaxed);
+          chain[(size_t)i + 1].store(CHAIN_ABORT, std::memory_order_release);
+          continue;
         }
+        if (corrupt) walk_corrupt.store(1, std::memory_order_relaxed);
         b->blk_owner[(size_t)i] = (uint16_t)tid;
         b->blk_first[(size_t)i] = (uint32_t)first;
         b->blk_count[(size_t)i] = (uint32_t)(mine.size() - first);
@@ -1194,75 +1224,82 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
       {
         const double t0 = omp_get_wtime();
         b->tm.wait += t0 - t_round;
-        if (do_produce && !bad) {
-          const int64_t ex = chain[(size_t)n_blk].load(std::memory_order_acquire);
-          size_t n = 0;
-          for (long i = 0; i < n_blk; ++i) {
-            const uint32_t c = b->blk_count[(size_t)i];
-            b->blk_count[(size_t)i] = (uint32_t)n;   // from here on: index of the block's first record
-            n += c;
-          }
-          // what the last walker could not reach: records that lie entirely in the head (a file
-          // whose records all followed the header in its first blocks), or behind empty blocks
-          b->fin_off.clear();
-          int64_t fo = ex;
-          if (werr.empty())
-            while (fo + 4 <= ntotal) {
-              const int32_t bs = rd_i32(nbase + fo);
-              if (bs < 32 || bs > (1 << 28)) {
-                werr = "corrupt BAM record (block_size out of range)";
-                break;
-              }
-              if (fo + 4 + (int64_t)bs > ntotal) break;
-              b->fin_off.push_back(fo);
-              fo += 4 + (int64_t)bs;
+        try {
+          if (bad.load(std::memory_order_relaxed) & 2) throw std::bad_alloc();   // (the selection is incomplete)
+          if (walk_corrupt.load(std::memory_order_relaxed)) werr = "corrupt BAM record (block_size out of range)";
+          if (do_produce && !bad) {
+            const int64_t ex = chain[(size_t)n_blk].load(std::memory_order_acquire);
+            size_t n = 0;
+            for (long i = 0; i < n_blk; ++i) {
+              const uint32_t c = b->blk_count[(size_t)i];
+              b->blk_count[(size_t)i] = (uint32_t)n;   // from here on: index of the block's first record
+              n += c;
             }
-          const size_t n_blocks_rec = n;
-          n += b->fin_off.size();
-          next.n_rec = n;
-          next.sel = 0;
-          next.exit_off = fo;
-          next.walk_err = werr;
-          next.w_off.resize(n + 1);
-          next.w_off[n] = fo;
-          if (!b->fin_off.empty())
-            memcpy(next.w_off.data() + n_blocks_rec, b->fin_off.data(), b->fin_off.size() * sizeof(int64_t));
-          blocks_rec = n_blocks_rec;
-          next.w_flag.resize(n);
-          next.w_lseq.resize(n);
-          next.w_cls.resize(n);
-          next.w_prevp.resize(n);
-        }
-        round_kept = s_idx.size();
-        if (round_kept) {
-          const size_t n1 = n_kept + round_kept;
-          grow(im->read_starts, n1);
-          grow(im->read_lens, n1);
-          grow(im->rec_index, n1);
-          grow(im->rec_uoff, n1);
-          grow(im->fasta_keep, n1);
-          if (want_meta) {
-            grow(im->ref_id, n1);
-            grow(im->pos, n1);
-            grow(im->next_ref_id, n1);
-            grow(im->next_pos, n1);
-            grow(im->flag, n1);
-            grow(im->mapq, n1);
-            grow(im->qname_off, n1 + 1);
-            grow(im->cigar_off, n1 + 1);
-            grow(im->sa_off, n1 + 1);
-            if (want_meta >= 2) grow(im->qual_off, n1 + 1);
-            if (want_meta >= 3) grow(im->raw_off, n1 + 1);
-            if (s_sa.size() < round_kept) s_sa.resize(round_kept);
+            // what the last walker could not reach: records that lie entirely in the head (a file
+            // whose records all followed the header in its first blocks), or behind empty blocks
+            b->fin_off.clear();
+            int64_t fo = ex;
+            if (werr.empty())
+              while (fo + 4 <= ntotal) {
+                const int32_t bs = rd_i32(nbase + fo);
+                if (bs < 32 || bs > (1 << 28)) {
+                  werr = "corrupt BAM record (block_size out of range)";
+                  break;
+                }
+                if (fo + 4 + (int64_t)bs > ntotal) break;
+                b->fin_off.push_back(fo);
+                fo += 4 + (int64_t)bs;
+              }
+            const size_t n_blocks_rec = n;
+            n += b->fin_off.size();
+            next.n_rec = n;
+            next.sel = 0;
+            next.exit_off = fo;
+            next.walk_err = werr;
+            next.w_off.resize(n + 1);
+            next.w_off[n] = fo;
+            if (!b->fin_off.empty())
+              memcpy(next.w_off.data() + n_blocks_rec, b->fin_off.data(), b->fin_off.size() * sizeof(int64_t));
+            blocks_rec = n_blocks_rec;
+            next.w_flag.resize(n);
+            next.w_lseq.resize(n);
+            next.w_cls.resize(n);
+            next.w_prevp.resize(n);
           }
-          w_first = words_zeroed;
-          w_last = (n_bases + 31) / 32;
-          if (w_last < w_first) w_last = w_first;
-          grow(im->codes, (size_t)w_last + 1);
-          grow(im->valid, (size_t)w_last + 1);
-          words_zeroed = w_last;
+          round_kept = s_idx.size();
+          if (round_kept) {
+            const size_t n1 = n_kept + round_kept;
+            grow(im->read_starts, n1);
+            grow(im->read_lens, n1);
+            grow(im->rec_index, n1);
+            grow(im->rec_uoff, n1);
+            grow(im->fasta_keep, n1);
+            if (want_meta) {
+              grow(im->ref_id, n1);
+              grow(im->pos, n1);
+              grow(im->next_ref_id, n1);
+              grow(im->next_pos, n1);
+              grow(im->flag, n1);
+              grow(im->mapq, n1);
+              grow(im->qname_off, n1 + 1);
+              grow(im->cigar_off, n1 + 1);
+              grow(im->sa_off, n1 + 1);
+              if (want_meta >= 2) grow(im->qual_off, n1 + 1);
+              if (want_meta >= 3) grow(im->raw_off, n1 + 1);
+              if (s_sa.size() < round_kept) s_sa.resize(round_kept);
+            }
+            w_first = words_zeroed;
+            w_last = (n_bases + 31) / 32;
+            if (w_last < w_first) w_last = w_first;
+            grow(im->codes, (size_t)w_last + 1);
+            grow(im->valid, (size_t)w_last + 1);
+            words_zeroed = w_last;
+          }
+          part_sum.assign((size_t)team * 5 + 5, 0);
+        } catch (...) {
+          bad.fetch_or(2, std::memory_order_relaxed);
+          round_kept = 0;
         }
-        part_sum.assign((size_t)team * 5 + 5, 0);
         b->tm.select += omp_get_wtime() - t0;
       }
       // (implicit barrier)
@@ -1358,37 +1395,41 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
 #pragma omp barrier
 #pragma omp single
       {
-        if (do_produce && !bad) {   // link every primary record to the one before it
-          uint32_t prev = NO_PREV;
-          std::string& lq = next.last_qname;
-          lq = next.prev_qname;
-          const size_t n = next.n_rec;
-          for (size_t i = 0; i < n; ++i) {
-            if (next.w_cls[i] & C_BAD) break;
-            if (next.w_cls[i] & C_PRIMARY) {
-              next.w_prevp[i] = prev;
-              prev = (uint32_t)i;
+        try {
+          if (do_produce && !bad) {   // link every primary record to the one before it
+            uint32_t prev = NO_PREV;
+            std::string& lq = next.last_qname;
+            lq = next.prev_qname;
+            const size_t n = next.n_rec;
+            for (size_t i = 0; i < n; ++i) {
+              if (next.w_cls[i] & C_BAD) break;
+              if (next.w_cls[i] & C_PRIMARY) {
+                next.w_prevp[i] = prev;
+                prev = (uint32_t)i;
+              }
+            }
+            if (prev != NO_PREV) {
+              const uint8_t* r = nbase + next.w_off[prev] + 4;
+              lq.assign((const char*)r + 32, r[8] ? (size_t)r[8] - 1 : 0);
             }
           }
-          if (prev != NO_PREV) {
-            const uint8_t* r = nbase + next.w_off[prev] + 4;
-            lq.assign((const char*)r + 32, r[8] ? (size_t)r[8] - 1 : 0);
+          if (round_kept && want_meta) {   // exclusive prefix of the per-thread sums; blob sizes
+            uint64_t run[5] = {im->qname_off[n_kept], im->cigar_off[n_kept], im->sa_off[n_kept],
+                               want_meta >= 2 ? im->qual_off[n_kept] : 0, want_meta >= 3 ? im->raw_off[n_kept] : 0};
+            for (int t = 0; t < team; ++t)
+              for (int q = 0; q < 5; ++q) {
+                const uint64_t v = part_sum[(size_t)t * 5 + q];
+                part_sum[(size_t)t * 5 + q] = run[q];
+                run[q] += v;
+              }
+            grow(im->qname_blob, (size_t)run[0]);
+            grow(im->cigar_blob, (size_t)run[1]);
+            grow(im->sa_blob, (size_t)run[2]);
+            if (want_meta >= 2) grow(im->qual_blob, (size_t)run[3]);
+            if (want_meta >= 3) grow(im->raw_blob, (size_t)run[4]);
           }
-        }
-        if (round_kept && want_meta) {   // exclusive prefix of the per-thread sums; blob sizes
-          uint64_t run[5] = {im->qname_off[n_kept], im->cigar_off[n_kept], im->sa_off[n_kept],
-                             want_meta >= 2 ? im->qual_off[n_kept] : 0, want_meta >= 3 ? im->raw_off[n_kept] : 0};
-          for (int t = 0; t < team; ++t)
-            for (int q = 0; q < 5; ++q) {
-              const uint64_t v = part_sum[(size_t)t * 5 + q];
-              part_sum[(size_t)t * 5 + q] = run[q];
-              run[q] += v;
-            }
-          grow(im->qname_blob, (size_t)run[0]);
-          grow(im->cigar_blob, (size_t)run[1]);
-          grow(im->sa_blob, (size_t)run[2]);
-          if (want_meta >= 2) grow(im->qual_blob, (size_t)run[3]);
-          if (want_meta >= 3) grow(im->raw_blob, (size_t)run[4]);
+        } catch (...) {
+          bad.fetch_or(2, std::memory_order_relaxed);
         }
       }
       // (implicit barrier)
@@ -1412,7 +1453,7 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
           if (same) next.w_cls[(size_t)i] |= C_SAME;
         }
       }
-      if (round_kept && want_meta) {   // sizes -> offsets, and the variable-length pieces to their places
+      if (round_kept && want_meta && !(bad.load(std::memory_order_relaxed) & 2)) {   // sizes -> offsets, and the variable-length pieces to their places
         const uint8_t* cbase = cur.data + cur.own;
         uint64_t run[5];
         for (int q = 0; q < 5; ++q) run[q] = part_sum[(size_t)tid * 5 + q];
@@ -1453,6 +1494,10 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
     b->tm.rounds += omp_get_wtime() - t_round;
     b->tm.n_rounds++;
     n_kept += round_kept;
+    if (bad.load() & 2) {
+      if (do_produce) recycle_chunk(b, next);
+      return bail("out of memory while decoding the BAM");
+    }
     if (do_produce) {
       if (bad) {
         recycle_chunk(b, next);

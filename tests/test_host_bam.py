@@ -465,3 +465,36 @@ def test_long_and_tiny_records_across_blocks_and_chunks(tmp_path, monkeypatch, c
                 names += [b.record(i).query_name for i in range(b.n_reads)]
                 b.close()
         assert names == [r.qname for r in keep]
+
+
+def test_allocation_failure_is_an_error_not_a_crash(giab_paths):
+    """A batch buffer that cannot grow (KDF_BAM_FAIL_ALLOC: the n-th growth throws) must come
+    back as KdfError — also when it happens inside the decoder's parallel region, which no C++
+    exception may leave.  Each case runs in its own process: the hook counts process-wide."""
+    import subprocess
+    import sys
+    code = (
+        "import sys\n"
+        "from kmer_denovo_filter_b200 import bamio, engine\n"
+        "try:\n"
+        "    n = 0\n"
+        "    with bamio.BamReader(sys.argv[1], threads=3) as rd:\n"
+        "        for b in rd.batches(bamio.MODE_SCAN, max_bases=300_000, want_meta=2):\n"
+        "            n += b.n_reads; b.close()\n"
+        "    print('ok', n)\n"
+        "except engine.KdfError as e:\n"
+        "    print('kdferror', e)\n")
+    import os
+    outcomes = set()
+    for fail_at in (1, 2, 5, 9, 14, 23, 10_000):
+        env = dict(os.environ, KDF_BAM_FAIL_ALLOC=str(fail_at), KDF_BAM_POOL_MB="0",
+                   PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        r = subprocess.run([sys.executable, "-c", code, giab_paths["child"]], capture_output=True, text=True,
+                           timeout=120, env=env)
+        assert r.returncode == 0, (fail_at, r.returncode, r.stderr[-400:])
+        word = r.stdout.split()[0]
+        assert word in ("ok", "kdferror"), r.stdout
+        if word == "kdferror":
+            assert "memory" in r.stdout
+        outcomes.add((word, fail_at == 10_000))
+    assert ("kdferror", False) in outcomes and ("ok", True) in outcomes
