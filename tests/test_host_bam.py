@@ -498,3 +498,40 @@ def test_allocation_failure_is_an_error_not_a_crash(giab_paths):
             assert "memory" in r.stdout
         outcomes.add((word, fail_at == 10_000))
     assert ("kdferror", False) in outcomes and ("ok", True) in outcomes
+
+
+@pytest.mark.parametrize("block_payload", [1, 5, 37, 65280])
+def test_stored_blocks_tiny_blocks_and_no_eof_marker(tmp_path, block_payload):
+    """Uncompressed (stored) BGZF blocks down to ONE byte each — every block_size field and
+    every header is then split over several blocks — in a file without the EOF marker block;
+    and a BAM with no record at all."""
+    import struct
+    import zlib
+    recs = [obam.encode_record(0, i, "r%d" % i, 0x10 if i % 3 else 0, 60, [(0, 4)], "ACGT") for i in range(50)]
+    p0 = str(tmp_path / "z.bam")
+    obam.write_bam(p0, ["chr1"], [1000], recs)
+    raw = obam._inflate_all(p0)
+
+    def stored(payload):
+        co = zlib.compressobj(0, zlib.DEFLATED, -15)
+        c = co.compress(payload) + co.flush()
+        return (struct.pack("<BBBBIBBHBBHH", 31, 139, 8, 4, 0, 0, 255, 6, 66, 67, 2, len(c) + 25) + c +
+                struct.pack("<II", zlib.crc32(payload) & 0xFFFFFFFF, len(payload)))
+    p = str(tmp_path / "stored.bam")
+    with open(p, "wb") as fh:
+        for i in range(0, len(raw), block_payload):
+            fh.write(stored(raw[i:i + block_payload]))
+    for threads in (1, 3):
+        n = 0
+        with bamio.BamReader(p, threads=threads) as rd:
+            for b in rd.batches(bamio.MODE_ALL, max_bases=60, want_meta=3):
+                for i in range(b.n_reads):
+                    assert bytes(b.raw_blob[int(b.raw_off[i]):int(b.raw_off[i + 1])]) == recs[n][4:]
+                    n += 1
+                b.close()
+        assert n == len(recs)
+    pe = str(tmp_path / "empty.bam")
+    obam.write_bam(pe, ["chr1"], [1000], [])
+    with bamio.BamReader(pe, threads=2) as rd:
+        b = rd.next_batch(bamio.MODE_ALL, want_meta=3)
+        assert b.n_reads == 0 and b.at_eof
