@@ -66,9 +66,9 @@ inline uint32_t pc_entry(int sym) { return (uint32_t)sym << 16; }
 
 // Canonical Huffman code of lens[0..n) -> look-up table indexed by the next `tb` stream
 // bits (LSB first).  `kind`: 0 litlen, 1 distance, 2 code-length code.  A code set that
-// leaves part of the code space unused is accepted only when it is a single 1-bit code
-// (what zlib accepts; encoders emit it for a block with one distance), the unused half
-// then decodes to F_BAD.  No code at all is legal for distances (a literal-only block).
+// leaves part of the code space unused is accepted only when it is a single 1-bit litlen or
+// distance code (what zlib accepts; encoders emit it for a block with one distance), the
+// unused half then decodes to F_BAD.  No code at all is legal for distances (a literal-only block).
 //
 // Symbols are taken in canonical order (by length, then value) while `code` walks the
 // codewords in bit-reversed form, which is how the stream presents them: the next codeword
@@ -97,7 +97,7 @@ bool build_table(uint32_t* table, int tb, const uint8_t* lens, int n, int kind) 
   }
   auto entry = [kind](int sym) { return kind == 0 ? ll_entry(sym) : kind == 1 ? d_entry(sym) : pc_entry(sym); };
   if (left > 0) {
-    if (maxlen != 1) return false;   // incomplete
+    if (maxlen != 1 || kind == 2) return false;   // incomplete (zlib: never allowed for the code-length code)
     int sym = 0;
     while (lens[sym] != 1) ++sym;
     for (uint32_t i = 0; i < tsize; i += 2) table[i] = entry(sym) | 1u, table[i + 1] = F_BAD | 1;

@@ -46,6 +46,10 @@ def _payloads():
     blob = bytes(rng.getrandbits(8) for _ in range(20000))
     yield blob + bytes(range(256)) * 40 + blob
     yield bytes(rng.getrandbits(8) for _ in range(300))    # shorter than the fast-path margins
+    # geometric symbol frequencies: Huffman codes up to the 15-bit limit (sub-tables of both tables)
+    yield bytes(min(int(rng.expovariate(0.55)), 255) for _ in range(65000))
+    yield b"".join(bytes([min(int(rng.expovariate(0.4)), 255)]) * rng.choice((1, 1, 1, 3, 40, 258, 300))
+                   for _ in range(6000))[:65000]
 
 
 @pytest.mark.parametrize("strategy", [zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE,
