@@ -222,6 +222,9 @@ struct Bam {
   // selection of the consumer
   std::vector<std::atomic<int64_t>> chain;
   std::vector<std::vector<int64_t>> tl_off;
+  std::vector<std::vector<uint16_t>> tl_flag;   // (parallel to tl_off: what the walker could classify while hot)
+  std::vector<std::vector<uint32_t>> tl_lseq;
+  std::vector<std::vector<uint8_t>> tl_cls;
   std::vector<int64_t> fin_off;
   std::vector<uint32_t> blk_first, blk_count;
   std::vector<uint16_t> blk_owner;
@@ -876,6 +879,8 @@ int kdf_bam_next_batch(kdf_bam* h, int mode, uint64_t max_bases, int want_meta,
 // reader for the next call.
 
 constexpr uint8_t C_PRIMARY = 1, C_SAME = 2, C_BAD = 4;
+// (produce only) the header / the QNAME comparison could not be done while the block was hot
+constexpr uint8_t C_PENDING = 0x40, C_PENDING_SAME = 0x20;
 constexpr uint32_t NO_PREV = 0xffffffffu;
 constexpr int64_t CHAIN_WAIT = INT64_MIN, CHAIN_ABORT = INT64_MIN + 1;
 
@@ -925,6 +930,21 @@ static void recycle_chunk(Bam* b, Chunk& c) {
 }
 
 static std::atomic<int> g_active_decoders{0};   // readers inside kdf_bam_next_batch right now
+
+// A record's header: validate the variable-length fields against the record size `bs` (a
+// corrupt l_seq / n_cigar / l_read_name would otherwise send the packer and the metadata pass
+// out of bounds) and classify it.  → C_BAD, C_PRIMARY or 0
+static inline uint8_t classify_header(const uint8_t* r, uint64_t bs, uint16_t* flag_out, uint32_t* lseq_out) {
+  const uint16_t flag = rd_u16(r + 14);
+  const uint8_t l_name = r[8];
+  const uint16_t n_cig_v = rd_u16(r + 12);
+  const int32_t l_seq_s = rd_i32(r + 16);
+  *flag_out = flag;
+  *lseq_out = (uint32_t)l_seq_s;
+  if (l_seq_s < 0 || 32ull + l_name + 4ull * n_cig_v + ((uint64_t)l_seq_s + 1) / 2 + (uint64_t)l_seq_s > bs)
+    return C_BAD;
+  return (flag & 0xD00) ? 0 : C_PRIMARY;
+}
 
 static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, kdf_bam_batch* out,
                            kdf_bam_batch_impl* im) {
@@ -1045,7 +1065,13 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
 
   std::vector<std::atomic<int64_t>>& chain = b->chain;
   std::vector<std::vector<int64_t>>& tl_off = b->tl_off;
-  if ((int)tl_off.size() < nthr) tl_off.resize((size_t)nthr);
+  if ((int)tl_off.size() < nthr) {
+    tl_off.resize((size_t)nthr);
+    b->tl_flag.resize((size_t)nthr);
+    b->tl_lseq.resize((size_t)nthr);
+    b->tl_cls.resize((size_t)nthr);
+  }
+  static const bool hot_classify = !(getenv("KDF_BAM_WALK_CLASSIFY") && atoi(getenv("KDF_BAM_WALK_CLASSIFY")) == 0);
 
   while (!done) {
     // ---- what this round does ----
@@ -1130,7 +1156,12 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
       b->blk_first.assign((size_t)n_blk, 0);
       b->blk_count.assign((size_t)n_blk, 0);
       b->blk_owner.assign((size_t)n_blk, 0);
-      for (int t = 0; t < nthr; ++t) tl_off[(size_t)t].clear();
+      for (int t = 0; t < nthr; ++t) {
+        tl_off[(size_t)t].clear();
+        b->tl_flag[(size_t)t].clear();
+        b->tl_lseq[(size_t)t].clear();
+        b->tl_cls[(size_t)t].clear();
+      }
       next.walk_err.clear();
     }
     b->ahead2.valid = false;
@@ -1217,6 +1248,59 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
         b->blk_first[(size_t)i] = (uint32_t)first;
         b->blk_count[(size_t)i] = (uint32_t)(mine.size() - first);
         chain[(size_t)i + 1].store(o, std::memory_order_release);
+        // Off the hand-over path, while the block is still in this core's cache: the headers
+        // that lie entirely in what is inflated so far (everything below u_end) are validated
+        // and classified here, and a primary record is compared with the primary record before
+        // it when that one is in this block too.  What cannot be decided yet (a header or QNAME
+        // that continues in the next block, the first primary record of a block) is marked and
+        // left to the passes after the barrier.
+        try {
+          std::vector<uint16_t>& fl = b->tl_flag[(size_t)tid];
+          std::vector<uint32_t>& ls = b->tl_lseq[(size_t)tid];
+          std::vector<uint8_t>& cl = b->tl_cls[(size_t)tid];
+          const size_t cnt = mine.size() - first;
+          fl.resize(first + cnt);
+          ls.resize(first + cnt);
+          cl.resize(first + cnt);
+          const uint8_t* prev_name = nullptr;   // QNAME of the previous primary record of this block, if readable
+          size_t prev_len = 0;
+          bool prev_known = false;              // a primary record came before in this block
+          for (size_t j = first; j < first + cnt; ++j) {
+            const int64_t ro = mine[j];
+            const int64_t next_ro = j + 1 < first + cnt ? mine[j + 1] : o;
+            uint8_t cls = C_PENDING;
+            uint16_t flag = 0;
+            uint32_t lseq = 0;
+            if (hot_classify && ro + 36 <= u_end) {
+              const uint8_t* r = nbase + ro + 4;
+              cls = classify_header(r, (uint64_t)(next_ro - ro) - 4, &flag, &lseq);
+              if (cls & C_PRIMARY) {
+                const size_t ql = r[8] ? (size_t)r[8] - 1 : 0;
+                const bool name_here = ro + 36 + (int64_t)r[8] <= u_end;
+                if (name_here && prev_known && prev_name) {
+                  if (prev_len == ql && memcmp(prev_name, r + 32, ql) == 0) cls |= C_SAME;
+                } else {
+                  cls |= C_PENDING_SAME;
+                }
+                prev_known = true;
+                prev_name = name_here ? r + 32 : nullptr;
+                prev_len = ql;
+              } else if (cls & C_BAD) {
+                prev_known = false;   // (the passes behind stop at a corrupt record anyway)
+                prev_name = nullptr;
+              }
+            } else {
+              // unknown kind: it may be a primary record, so the next one cannot rely on prev_*
+              prev_known = false;
+              prev_name = nullptr;
+            }
+            fl[j] = flag;
+            ls[j] = lseq;
+            cl[j] = cls;
+          }
+        } catch (...) {
+          bad.fetch_or(2, std::memory_order_relaxed);
+        }
       }
 #pragma omp barrier
       // ---- both selections are known: lay out the outputs (one thread), then fill them ----
@@ -1310,8 +1394,17 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
         for (long i = 0; i < n_blk; ++i) {
           const size_t at = b->blk_count[(size_t)i];
           const size_t end = (i + 1 < n_blk) ? b->blk_count[(size_t)i + 1] : blocks_rec;
-          const int64_t* src = tl_off[b->blk_owner[(size_t)i]].data() + b->blk_first[(size_t)i];
-          if (end > at) memcpy(next.w_off.data() + at, src, (end - at) * sizeof(int64_t));
+          const size_t ow = b->blk_owner[(size_t)i], f0 = b->blk_first[(size_t)i];
+          if (end > at) {
+            memcpy(next.w_off.data() + at, tl_off[ow].data() + f0, (end - at) * sizeof(int64_t));
+            memcpy(next.w_flag.data() + at, b->tl_flag[ow].data() + f0, (end - at) * sizeof(uint16_t));
+            memcpy(next.w_lseq.data() + at, b->tl_lseq[ow].data() + f0, (end - at) * sizeof(uint32_t));
+            memcpy(next.w_cls.data() + at, b->tl_cls[ow].data() + f0, (end - at) * sizeof(uint8_t));
+          }
+        }
+#pragma omp single nowait
+        {
+          for (size_t i = blocks_rec; i < next.n_rec; ++i) next.w_cls[i] = C_PENDING;   // (the finishing walk's)
         }
       }
       // initialise the stream words this round reaches
@@ -1325,28 +1418,20 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
         }
       }
 #pragma omp barrier
-      // classify the produced records
+      // classify what the walkers had to leave (a header that crossed a block boundary)
       if (do_produce && !bad) {
         const size_t n = next.n_rec;
 #pragma omp for schedule(static) nowait
         for (long i = 0; i < (long)n; ++i) {
+          if (!(next.w_cls[(size_t)i] & C_PENDING)) continue;
           const uint8_t* r = nbase + next.w_off[(size_t)i] + 4;
-          if ((size_t)i + 8 < n) __builtin_prefetch(nbase + next.w_off[(size_t)i + 8] + 4);
           const uint64_t bs = (uint64_t)(next.w_off[(size_t)i + 1] - next.w_off[(size_t)i]) - 4;
-          const uint16_t flag = rd_u16(r + 14);
-          const uint8_t l_name = r[8];
-          const uint16_t n_cig_v = rd_u16(r + 12);
-          const int32_t l_seq_s = rd_i32(r + 16);
-          uint8_t cls = 0;
-          // the variable-length fields must lie inside the record: a corrupt l_seq / n_cigar /
-          // l_read_name would otherwise send the packer (and the metadata pass) out of bounds
-          if (l_seq_s < 0 ||
-              32ull + l_name + 4ull * n_cig_v + ((uint64_t)l_seq_s + 1) / 2 + (uint64_t)l_seq_s > bs)
-            cls |= C_BAD;
-          else if (!(flag & 0xD00))
-            cls |= C_PRIMARY;
+          uint16_t flag;
+          uint32_t lseq;
+          uint8_t cls = classify_header(r, bs, &flag, &lseq);
+          if (cls & C_PRIMARY) cls |= C_PENDING_SAME;
           next.w_flag[(size_t)i] = flag;
-          next.w_lseq[(size_t)i] = (uint32_t)l_seq_s;
+          next.w_lseq[(size_t)i] = lseq;
           next.w_cls[(size_t)i] = cls;
         }
       }
@@ -1437,7 +1522,8 @@ static int next_batch_impl(Bam* b, int mode, uint64_t max_bases, int want_meta, 
         const size_t n = next.n_rec;
 #pragma omp for schedule(static) nowait
         for (long i = 0; i < (long)n; ++i) {
-          if (!(next.w_cls[(size_t)i] & C_PRIMARY)) continue;
+          if (!(next.w_cls[(size_t)i] & C_PENDING_SAME)) continue;
+          next.w_cls[(size_t)i] &= (uint8_t)~C_PENDING_SAME;
           const uint8_t* r = nbase + next.w_off[(size_t)i] + 4;
           const char* qn = (const char*)r + 32;
           const size_t ql = r[8] ? (size_t)r[8] - 1 : 0;

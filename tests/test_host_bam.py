@@ -535,3 +535,50 @@ def test_stored_blocks_tiny_blocks_and_no_eof_marker(tmp_path, block_payload):
     with bamio.BamReader(pe, threads=2) as rd:
         b = rd.next_batch(bamio.MODE_ALL, want_meta=3)
         assert b.n_reads == 0 and b.at_eof
+
+
+_DIGEST_CODE = r'''
+import hashlib, os, sys
+import numpy as np
+from kmer_denovo_filter_b200 import bamio
+path = sys.argv[1]
+for mode, mb, meta, ck, gap, thr in ((0, 0, 0, None, None, 4), (1, 100000, 1, 64, 0, 3), (2, 333333, 3, 100, 17, 8),
+                                     (1, 0, 2, 300, 5000, 1), (0, 1000000, 1, 65, 1, 2)):
+    if ck is None:
+        os.environ.pop("KDF_BAM_CHUNK_KB", None); os.environ.pop("KDF_BAM_GAP", None)
+    else:
+        os.environ["KDF_BAM_CHUNK_KB"] = str(ck); os.environ["KDF_BAM_GAP"] = str(gap)
+    h = hashlib.sha256(); n = 0
+    with bamio.BamReader(path, threads=thr) as rd:
+        for b in rd.batches(mode, max_bases=mb, want_meta=meta):
+            names = ["codes", "valid", "invalid", "read_starts", "read_lens", "rec_index", "rec_uoff", "fasta_keep"]
+            if meta: names += ["ref_id", "pos", "flag", "mapq", "qname_off", "qname_blob", "cigar_off", "cigar_blob", "sa_blob"]
+            if meta >= 2: names += ["qual_blob"]
+            if meta >= 3: names += ["raw_off", "raw_blob"]
+            for name in names:
+                h.update(np.ascontiguousarray(getattr(b, name)).tobytes())
+            h.update(b"|%d|%d|" % (b.n_reads, b.n_bases)); n += b.n_reads
+            b.close()
+    print(mode, mb, meta, n, h.hexdigest())
+'''
+
+
+@pytest.mark.parametrize("who", ["child", "mother"])
+def test_decoder_switches_do_not_change_the_batches(giab_paths, who):
+    """Headers classified by the walker while a block is hot / all of them after the barrier;
+    own inflate / zlib; vector / scalar base packing: the same batches, bit for bit."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for label, extra in (("default", {}), ("cold_classify", {"KDF_BAM_WALK_CLASSIFY": "0"}),
+                         ("zlib", {"KDF_BAM_ZLIB": "1", "KDF_CRC_ZLIB": "1"}), ("scalar_pack", {"KDF_PACK_SCALAR": "1"})):
+        env = dict(os.environ, PYTHONPATH=root, **extra)
+        r = subprocess.run([sys.executable, "-c", _DIGEST_CODE, giab_paths[who]], capture_output=True, text=True,
+                           timeout=300, env=env)
+        assert r.returncode == 0, r.stderr[-500:]
+        outs[label] = r.stdout
+    assert len(outs["default"].splitlines()) == 5
+    for label in ("cold_classify", "zlib", "scalar_pack"):
+        assert outs[label] == outs["default"], label
